@@ -1,0 +1,69 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/_ref/libskity_ref.so (the
+reference's own software backend, built by oracle/build_ref.py).  Only tests/,
+__graft_entry__.smoke() and bench.py's CPU-baseline legs may import this."""
+import ctypes
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libskity_ref.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.ref_render_scene.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
+                                          ctypes.POINTER(ctypes.c_double)]
+        _lib.ref_render_scene.restype = ctypes.c_int
+        _lib.ref_raster_path.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+        _lib.ref_raster_path.restype = ctypes.c_long
+        _lib.ref_stack_blur.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
+                                        ctypes.c_void_p]
+        _lib.ref_stack_blur.restype = ctypes.c_int
+    return _lib
+
+
+def render_scene(blob, return_seconds=False):
+    """Render an SKSC blob with the reference SW canvas -> (H, W, 4) uint8 premul RGBA."""
+    _, _, w, h, _, _ = struct.unpack_from("<6I", blob, 0)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    sec = ctypes.c_double(0.0)
+    rc = lib().ref_render_scene(blob, len(blob), out.ctypes.data, ctypes.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"ref_render_scene failed: {rc}")
+    return (out, sec.value) if return_seconds else out
+
+
+def raster_path(path, matrix6=(1, 0, 0, 0, 1, 0), clip=(-1e9, -1e9, 1e9, 1e9), cap=1 << 22):
+    """SWRaster::RastePath on one PathData -> (spans int32[n,4] = x,y,len,cover ; bounds float32[4])."""
+    rec = path.encode()
+    m = np.asarray(matrix6, dtype=np.float32)
+    c = np.asarray(clip, dtype=np.float32)
+    spans = np.zeros((cap, 4), dtype=np.int32)
+    bounds = np.zeros(4, dtype=np.float32)
+    n = lib().ref_raster_path(rec, len(rec), m.ctypes.data, c.ctypes.data, spans.ctypes.data, cap,
+                              bounds.ctypes.data)
+    if n < 0:
+        raise RuntimeError(f"ref_raster_path failed: {n}")
+    if n > cap:
+        return raster_path(path, matrix6, clip, cap=int(n))
+    return spans[:n].copy(), bounds
+
+
+def stack_blur(rgba, radius):
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w, _ = rgba.shape
+    out = np.zeros_like(rgba)
+    rc = lib().ref_stack_blur(rgba.ctypes.data, w, h, int(radius), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("ref_stack_blur failed")
+    return out

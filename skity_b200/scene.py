@@ -1,0 +1,288 @@
+"""SKSC scene blobs: a serialised sequence of skity::Canvas calls.
+
+One blob drives both the reference software canvas (oracle/_ref, through
+skity_b200/host/scene_player.hpp) and the CUDA canvas, the way the reference's
+golden harness replays one DisplayList on every backend
+(test/golden/common/golden_test_env.hpp:45-47).  The synthetic generators
+implement the seeded workloads of BASELINE.json / SURVEY.md §8(d).
+"""
+import struct
+
+import numpy as np
+
+MAGIC = 0x43534B53  # "SKSC"
+
+# skity::Path::Verb (include/skity/graphic/path.hpp:45-60)
+MOVE, LINE, QUAD, CONIC, CUBIC, CLOSE = 0, 1, 2, 3, 4, 5
+# skity::Paint::Style / Cap / Join (include/skity/graphic/paint.hpp:46-104)
+FILL, STROKE, STROKE_AND_FILL = 0, 1, 2
+BUTT, ROUND_CAP, SQUARE = 0, 1, 2
+MITER, ROUND_JOIN, BEVEL = 0, 1, 2
+# skity::TileMode (include/skity/graphic/tile_mode.hpp:13-30)
+CLAMP, REPEAT, MIRROR, DECAL = 0, 1, 2, 3
+WINDING, EVEN_ODD = 0, 1
+
+OP_SAVE, OP_RESTORE, OP_TRANSLATE, OP_SCALE, OP_ROTATE, OP_CONCAT = 1, 2, 3, 4, 5, 6
+OP_CLIP_RECT, OP_CLIP_PATH, OP_DRAW_PATH, OP_DRAW_RECT = 7, 8, 9, 10
+
+
+class PathData:
+    """Verbs + points in the reference's Path layout (xy only)."""
+
+    def __init__(self, fill_type=WINDING):
+        self.fill_type = fill_type
+        self.verbs = []
+        self.pts = []
+        self.weights = []
+
+    def move_to(self, x, y):
+        self.verbs.append(MOVE)
+        self.pts += [x, y]
+        return self
+
+    def line_to(self, x, y):
+        self.verbs.append(LINE)
+        self.pts += [x, y]
+        return self
+
+    def quad_to(self, x1, y1, x2, y2):
+        self.verbs.append(QUAD)
+        self.pts += [x1, y1, x2, y2]
+        return self
+
+    def conic_to(self, x1, y1, x2, y2, w):
+        self.verbs.append(CONIC)
+        self.pts += [x1, y1, x2, y2]
+        self.weights.append(w)
+        return self
+
+    def cubic_to(self, x1, y1, x2, y2, x3, y3):
+        self.verbs.append(CUBIC)
+        self.pts += [x1, y1, x2, y2, x3, y3]
+        return self
+
+    def close(self):
+        self.verbs.append(CLOSE)
+        return self
+
+    def encode(self):
+        nv = len(self.verbs)
+        pts = np.asarray(self.pts, dtype=np.float32)
+        ws = np.asarray(self.weights, dtype=np.float32)
+        verbs = bytes(self.verbs) + b"\0" * ((-nv) % 4)
+        return struct.pack("<4I", self.fill_type, nv, len(pts) // 2, len(ws)) + verbs + pts.tobytes() + ws.tobytes()
+
+
+class Paint:
+    def __init__(self, style=FILL, fill=(0, 0, 0, 1), stroke=(0, 0, 0, 1), stroke_width=1.0, miter=4.0,
+                 cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None):
+        self.style, self.fill, self.stroke = style, fill, stroke
+        self.stroke_width, self.miter, self.cap, self.join = stroke_width, miter, cap, join
+        self.blur_radius, self.blur_style = blur_radius, blur_style
+        self.shader = shader  # dict(type=1|2|3, p=(..4), tile=, colors=[(r,g,b,a)..], stops=[..]|None, local=None|6)
+
+    def encode(self):
+        out = struct.pack("<I2f2I", self.style, self.stroke_width, self.miter, self.cap, self.join)
+        out += np.asarray(self.fill, dtype=np.float32).tobytes()
+        out += np.asarray(self.stroke, dtype=np.float32).tobytes()
+        if self.blur_radius > 0:
+            out += struct.pack("<If", self.blur_style, self.blur_radius)
+        else:
+            out += struct.pack("<If", 0, 0.0)
+        sh = self.shader
+        if not sh:
+            return out + struct.pack("<I", 0)
+        colors = np.asarray(sh["colors"], dtype=np.float32).reshape(-1, 4)
+        stops = sh.get("stops")
+        stops = np.asarray(stops if stops is not None else [], dtype=np.float32)
+        local = sh.get("local")
+        out += struct.pack("<I", sh["type"])
+        out += np.asarray(sh["p"], dtype=np.float32).tobytes()
+        out += struct.pack("<4I", sh.get("tile", CLAMP), len(colors), len(stops), 1 if local is not None else 0)
+        out += np.asarray(local if local is not None else [1, 0, 0, 0, 1, 0], dtype=np.float32).tobytes()
+        out += colors.tobytes() + stops.tobytes()
+        return out
+
+
+class Scene:
+    def __init__(self, width, height):
+        self.width, self.height = int(width), int(height)
+        self.ops = []
+        self.n_draws = 0
+
+    def _op(self, code, payload=b""):
+        assert len(payload) % 4 == 0
+        self.ops.append(struct.pack("<2I", code, len(payload)) + payload)
+
+    def save(self):
+        self._op(OP_SAVE)
+
+    def restore(self):
+        self._op(OP_RESTORE)
+
+    def translate(self, dx, dy):
+        self._op(OP_TRANSLATE, struct.pack("<2f", dx, dy))
+
+    def scale(self, sx, sy):
+        self._op(OP_SCALE, struct.pack("<2f", sx, sy))
+
+    def rotate(self, deg):
+        self._op(OP_ROTATE, struct.pack("<f", deg))
+
+    def concat(self, m6):
+        self._op(OP_CONCAT, np.asarray(m6, dtype=np.float32).tobytes())
+
+    def clip_rect(self, l, t, r, b, intersect=True):
+        self._op(OP_CLIP_RECT, struct.pack("<4fI", l, t, r, b, 1 if intersect else 0))
+
+    def clip_path(self, path, intersect=True):
+        self._op(OP_CLIP_PATH, path.encode() + struct.pack("<I", 1 if intersect else 0))
+
+    def draw_path(self, path, paint):
+        self._op(OP_DRAW_PATH, path.encode() + paint.encode())
+        self.n_draws += 1
+
+    def draw_rect(self, l, t, r, b, paint):
+        self._op(OP_DRAW_RECT, struct.pack("<4f", l, t, r, b) + paint.encode())
+        self.n_draws += 1
+
+    def encode(self):
+        return struct.pack("<6I", MAGIC, 1, self.width, self.height, len(self.ops), 0) + b"".join(self.ops)
+
+
+# ---------------------------------------------------------------------------
+# Workloads.  numpy RandomState is MT19937, seeded per config.
+# ---------------------------------------------------------------------------
+
+def star_path(fill_type=WINDING):
+    """README star (README.md:105-126; also test/golden/cases/clip/clip.cc:51-65)."""
+    p = PathData(fill_type)
+    p.move_to(199, 34)
+    for x, y in [(253, 143), (374, 160), (287, 244), (307, 365), (199, 309), (97, 365), (112, 245), (26, 161),
+                 (146, 143)]:
+        p.line_to(x, y)
+    return p.close()
+
+
+README_BLUE = (0x42 / 255.0, 0x85 / 255.0, 0xF4 / 255.0, 1.0)
+
+
+def scene_c0(blur=True, plain=True):
+    """Config 0: README star, kFill, nonzero, 0x4285F4, plus MakeBlur(kNormal,10) copy at +400."""
+    s = Scene(800, 600)
+    if plain:
+        s.draw_path(star_path(), Paint(fill=README_BLUE))
+    if blur:
+        s.save()
+        s.translate(400, 0)
+        s.draw_path(star_path(), Paint(fill=README_BLUE, blur_radius=10.0))
+        s.restore()
+    return s
+
+
+def _random_closed_path(rng, cx, cy, box, index, n_seg=4):
+    """4 segments, even index quads / odd index cubics, control points uniform in a box."""
+    half = box * 0.5
+
+    def pt():
+        return (np.float32(cx + rng.uniform(-half, half)), np.float32(cy + rng.uniform(-half, half)))
+
+    p = PathData(EVEN_ODD if index % 3 == 0 else WINDING)
+    p.move_to(*pt())
+    for _ in range(n_seg):
+        if index % 2 == 0:
+            a, b = pt(), pt()
+            p.quad_to(a[0], a[1], b[0], b[1])
+        else:
+            a, b, c = pt(), pt(), pt()
+            p.cubic_to(a[0], a[1], b[0], b[1], c[0], c[1])
+    return p.close()
+
+
+def scene_random_fills(n_paths, size, seed, box=256.0, width=None, height=None):
+    """C1 / C4a / C4b family: random quad/cubic closed paths, solid colour, alpha in [0.5,1]."""
+    w = width or size
+    h = height or size
+    rng = np.random.RandomState(seed)
+    s = Scene(w, h)
+    for i in range(n_paths):
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        path = _random_closed_path(rng, cx, cy, box, i)
+        col = (rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.5, 1.0))
+        s.draw_path(path, Paint(fill=tuple(np.float32(c) for c in col)))
+    return s
+
+
+def scene_c1(n_paths=10000, size=4096, seed=1):
+    return scene_random_fills(n_paths, size, seed, 256.0)
+
+
+def scene_c4a(n_paths=1000000, size=16384, seed=4):
+    return scene_random_fills(n_paths, size, seed, 128.0)
+
+
+def scene_c4b(index, n_paths=1000):
+    return scene_random_fills(n_paths, 0, 5 + index, 256.0, width=1920, height=1080)
+
+
+def _random_gradient(rng, cx, cy, box, kind):
+    n = int(rng.randint(3, 6))
+    colors = [(rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.5, 1.0)) for _ in range(n)]
+    stops = None
+    if rng.uniform() < 0.5:
+        stops = np.sort(rng.uniform(0, 1, n)).astype(np.float32)
+        stops[0], stops[-1] = 0.0, 1.0
+    tile = [CLAMP, REPEAT, MIRROR][int(rng.randint(0, 3))]
+    half = box * 0.5
+    if kind == 1:
+        p = (cx - rng.uniform(0, half), cy - rng.uniform(0, half), cx + rng.uniform(0, half), cy + rng.uniform(0, half))
+    elif kind == 2:
+        p = (cx, cy, rng.uniform(box * 0.1, half), 0.0)
+    else:
+        p = (cx, cy, 0.0, 360.0)
+    return dict(type=kind, p=tuple(np.float32(v) for v in p), tile=tile, colors=colors, stops=stops)
+
+
+def scene_c2(n_paths=20000, size=4096, seed=2, clip_every=500, clip_box=1024.0, max_depth=3):
+    """Gradient-heavy: fill/stroke/stroke+fill cycle, linear/radial/sweep shaders, nested ClipPath."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    depth = 0
+    for i in range(n_paths):
+        if clip_every and i % clip_every == 0:
+            if depth >= max_depth:
+                while depth > 0:
+                    s.restore()
+                    depth -= 1
+            s.save()
+            depth += 1
+            ccx, ccy = rng.uniform(size * 0.25, size * 0.75), rng.uniform(size * 0.25, size * 0.75)
+            blob = _random_closed_path(rng, ccx, ccy, clip_box * max(1.0, size / 2048.0), 1)
+            blob.fill_type = WINDING
+            s.clip_path(blob, True)
+        cx, cy = rng.uniform(0, size), rng.uniform(0, size)
+        path = _random_closed_path(rng, cx, cy, 256.0, i)
+        style = i % 3
+        kind = 1 + (i % 3)
+        paint = Paint(style=style, stroke_width=float(np.float32(rng.uniform(1, 8))), cap=(i // 3) % 3,
+                      join=(i // 9) % 3, fill=(0, 0, 0, 1), stroke=(0, 0, 0, 1),
+                      shader=_random_gradient(rng, cx, cy, 256.0, kind))
+        s.draw_path(path, paint)
+    while depth > 0:
+        s.restore()
+        depth -= 1
+    return s
+
+
+def scene_c3(n_paths=2000, size=8192, seed=3, box=512.0):
+    """Blur stress: MaskFilter::MakeBlur(kNormal, r), sigma U[4,64] => r=(sigma-0.5)/0.57735."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    for i in range(n_paths):
+        cx, cy = rng.uniform(0, size), rng.uniform(0, size)
+        path = _random_closed_path(rng, cx, cy, box, i)
+        col = (rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.5, 1.0))
+        sigma = rng.uniform(4.0, 64.0)
+        radius = float(np.float32((sigma - 0.5) / 0.57735))
+        s.draw_path(path, Paint(fill=tuple(np.float32(c) for c in col), blur_radius=radius))
+    return s
