@@ -1,0 +1,89 @@
+"""TEST INFRASTRUCTURE — ctypes binding of the plain-C oracle port (oracle/skb_oracle.c).
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this."""
+import ctypes
+import os
+import struct
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskb_oracle.so")
+SRC_PATH = os.path.join(_HERE, "skb_oracle.c")
+_lib = None
+
+SEG_DTYPE = np.dtype([("type_flags", "<u4"), ("w", "<f4"), ("p", "<f4", (8,)), ("start", "<f4", (2,))])
+
+
+def build(force=False):
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "skb_dl.h")
+    if (not force and os.path.exists(LIB_PATH)
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(SRC_PATH), os.path.getmtime(hdr))):
+        return LIB_PATH
+    subprocess.check_call(["gcc", "-O2", "-std=c99", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
+                           "-Wall", "-Wno-unused-function", "-o", LIB_PATH, SRC_PATH, "-lm"])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.skbo_render.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.skbo_render.restype = ctypes.c_int
+        _lib.skbo_raster_path.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+        _lib.skbo_raster_path.restype = ctypes.c_long
+        _lib.skbo_stack_blur.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return _lib
+
+
+def dl_header(dl):
+    names = ["magic", "version", "total_bytes", "flags", "n_surfaces", "n_ops", "n_paths", "n_segs", "n_paints",
+             "n_stop_floats", "n_clip_states", "reserved0", "off_surfaces", "off_ops", "off_paths", "off_segs",
+             "off_paints", "off_stops"]
+    return dict(zip(names, struct.unpack_from("<18I", dl, 0)))
+
+
+def render(dl, initial=None):
+    """Execute a display list on the CPU port -> (H, W, 4) uint8 premultiplied RGBA of surface 0."""
+    h = dl_header(dl)
+    w, hh = struct.unpack_from("<2I", dl, h["off_surfaces"])
+    out = np.zeros((hh, w, 4), dtype=np.uint8)
+    init_ptr = None
+    if initial is not None:
+        initial = np.ascontiguousarray(initial, dtype=np.uint8)
+        init_ptr = initial.ctypes.data
+    rc = lib().skbo_render(dl, len(dl), init_ptr, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"skbo_render failed: {rc}")
+    return out
+
+
+def raster_path(segs, ctm=(1, 0, 0, 0, 1, 0), clip=(-1e9, -1e9, 1e9, 1e9), even_odd=False, cap=1 << 22):
+    segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    m = np.asarray(ctm, dtype=np.float32)
+    c = np.asarray(clip, dtype=np.float32)
+    spans = np.zeros((cap, 4), dtype=np.int32)
+    bounds = np.zeros(4, dtype=np.float32)
+    n = lib().skbo_raster_path(segs.ctypes.data, len(segs), m.ctypes.data, c.ctypes.data, int(even_odd),
+                               spans.ctypes.data, cap, bounds.ctypes.data)
+    if n > cap:
+        return raster_path(segs, ctm, clip, even_odd, int(n))
+    return spans[:n].copy(), bounds
+
+
+def stack_blur(rgba, radius):
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w, _ = rgba.shape
+    out = np.zeros_like(rgba)
+    lib().skbo_stack_blur(rgba.ctypes.data, out.ctypes.data, w, h, int(radius))
+    return out
+
+
+def dl_segments(dl, path_index):
+    """Segments of one path of a display list as a SEG_DTYPE array."""
+    h = dl_header(dl)
+    seg_off, n_segs = struct.unpack_from("<2I", dl, h["off_paths"] + 16 * path_index)
+    return np.frombuffer(dl, dtype=SEG_DTYPE, count=n_segs, offset=h["off_segs"] + 48 * seg_off).copy()

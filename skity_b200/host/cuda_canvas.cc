@@ -1,0 +1,548 @@
+#include "skity_b200/host/cuda_canvas.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <skity/effect/mask_filter.hpp>
+#include <skity/effect/path_effect.hpp>
+#include <skity/effect/shader.hpp>
+#include <skity/geometry/stroke.hpp>
+#include <skity/graphic/paint.hpp>
+#include <skity/graphic/path.hpp>
+
+namespace skity {
+
+// ---------------------------------------------------------------------------
+// Path lowering
+// ---------------------------------------------------------------------------
+namespace {
+
+struct LPoint {
+  float x, y;
+  bool cubic_end;  // value is the source p3; the real point is the computed end of that cubic
+};
+
+// The destination path Stroke::QuadPath builds (src/geometry/stroke.cc:914-962), with
+// conics and cubics kept as curves.  MoveTo / Close / InjectMoveToIfNeed follow
+// src/graphic/path.cc:494-506,837-860,1327-1339.
+struct LoweredPath {
+  struct Item {
+    uint8_t verb;   // Path::Verb numbering
+    float p[8];     // curve-maths points handed out by Path::Iter (p0 = source previous point)
+    float w;
+  };
+  std::vector<Item> items;
+  std::vector<LPoint> points;
+  std::vector<uint8_t> verbs;
+  int32_t last_move_to_index = ~0;
+
+  void MoveTo(float x, float y) {
+    if (!verbs.empty() && verbs.back() == 0) {
+      points.back() = LPoint{x, y, false};
+      items.back().p[0] = x;
+      items.back().p[1] = y;
+    } else {
+      last_move_to_index = static_cast<int32_t>(points.size());
+      verbs.push_back(0);
+      points.push_back(LPoint{x, y, false});
+      Item it{};
+      it.verb = 0;
+      it.p[0] = x;
+      it.p[1] = y;
+      items.push_back(it);
+    }
+  }
+  void InjectMoveToIfNeed() {
+    if (last_move_to_index < 0) {
+      float x = 0, y = 0;
+      if (!verbs.empty()) {
+        // a cubic end can never be a contour start, so this is always an exact point
+        const LPoint& pt = points[static_cast<size_t>(~last_move_to_index)];
+        x = pt.x;
+        y = pt.y;
+      }
+      MoveTo(x, y);
+    }
+  }
+  void Segment(uint8_t verb, const Point pts[4], int n_pts, float w) {
+    InjectMoveToIfNeed();
+    Item it{};
+    it.verb = verb;
+    it.w = w;
+    for (int i = 0; i < n_pts; i++) {
+      it.p[2 * i] = pts[i].x;
+      it.p[2 * i + 1] = pts[i].y;
+    }
+    items.push_back(it);
+    verbs.push_back(verb);
+    // only the last point matters for chaining; interior control points never become starts
+    points.push_back(LPoint{pts[n_pts - 1].x, pts[n_pts - 1].y, verb == 4});
+  }
+  void Close() {
+    if (!verbs.empty() && verbs.back() != 5) {
+      verbs.push_back(5);
+      Item it{};
+      it.verb = 5;
+      items.push_back(it);
+    }
+    last_move_to_index ^= ~last_move_to_index >> (8 * sizeof(last_move_to_index) - 1);
+  }
+};
+
+}  // namespace
+
+void LowerPathToSegs(const Path& src, std::vector<skb_dl_seg>* out) {
+  LoweredPath dst;
+  {
+    Path::Iter iter{src, false};
+    Point pts[4] = {};
+    for (;;) {
+      Path::Verb verb = iter.Next(pts);
+      bool done = false;
+      switch (verb) {
+        case Path::Verb::kMove:
+          dst.MoveTo(pts[0].x, pts[0].y);
+          break;
+        case Path::Verb::kLine:
+          dst.Segment(1, pts, 2, 0.f);
+          break;
+        case Path::Verb::kQuad:
+          dst.Segment(2, pts, 3, 0.f);
+          break;
+        case Path::Verb::kConic:
+          dst.Segment(3, pts, 3, iter.ConicWeight());
+          break;
+        case Path::Verb::kCubic:
+          dst.Segment(4, pts, 4, 0.f);
+          break;
+        case Path::Verb::kClose:
+          dst.Close();
+          break;
+        case Path::Verb::kDone:
+          done = true;
+          break;
+      }
+      if (done) break;
+    }
+  }
+
+  // PathEdgeIter traversal (src/graphic/path_priv.hpp:75-167): auto-close every contour.
+  bool needs_close = false;
+  LPoint move_pt{0, 0, false};
+  LPoint last_pt{0, 0, false};
+  size_t contour_first_seg = 0;
+  bool contour_open = false;
+  auto emit = [&](uint32_t type, const float* p, float w, const LPoint& start) {
+    skb_dl_seg s{};
+    s.type_flags = type | (start.cubic_end ? SKB_SEG_P0_FROM_PREV_CUBIC : 0u);
+    s.w = w;
+    if (p) std::memcpy(s.p, p, sizeof(s.p));
+    s.start[0] = start.x;
+    s.start[1] = start.y;
+    out->push_back(s);
+  };
+  auto closeline = [&]() {
+    float p[8] = {last_pt.x, last_pt.y, move_pt.x, move_pt.y, 0, 0, 0, 0};
+    emit(SKB_SEG_CLOSE, p, 0.f, last_pt);
+    needs_close = false;
+    last_pt = move_pt;
+  };
+  auto end_contour = [&]() {
+    if (contour_open && out->size() == contour_first_seg) {
+      // a MoveTo that stays in the path without any segment: bounds only
+      emit(SKB_SEG_POINT, nullptr, 0.f, move_pt);
+    }
+    contour_open = false;
+  };
+  size_t pi = 0;
+  for (const auto& it : dst.items) {
+    switch (it.verb) {
+      case 0:
+        if (needs_close) closeline();
+        end_contour();
+        move_pt = dst.points[pi++];
+        last_pt = move_pt;
+        contour_open = true;
+        contour_first_seg = out->size();
+        break;
+      case 5:
+        if (needs_close) closeline();
+        break;
+      default: {
+        static const uint32_t kType[5] = {0, SKB_SEG_LINE, SKB_SEG_QUAD, SKB_SEG_CONIC, SKB_SEG_CUBIC};
+        emit(kType[it.verb], it.p, it.w, last_pt);
+        last_pt = dst.points[pi++];
+        needs_close = true;
+      } break;
+    }
+  }
+  if (needs_close) closeline();
+  end_contour();
+}
+
+// ---------------------------------------------------------------------------
+// Canvas
+// ---------------------------------------------------------------------------
+CudaCanvas::CudaCanvas(skb::DlBuilder* builder, uint32_t surface, uint32_t width, uint32_t height)
+    : Canvas(), builder_(builder), surface_(surface), width_(width), height_(height) {
+  state_stack_.emplace_back(State());
+}
+
+void CudaCanvas::NoteUnsupported(const char* what) {
+  if (unsupported_.empty()) unsupported_ = what;
+}
+
+// SWCanvas::CurrentTransform with a zero global offset (sw_canvas.hpp:179-182)
+Matrix CudaCanvas::CurrentTransform() const {
+  return Matrix::Translate(-0.f, -0.f) * GetTotalMatrix();
+}
+
+// SWCanvas::GetScanClipBounds (sw_canvas.hpp:152-156)
+Rect CudaCanvas::ScanClipBounds() const {
+  Rect clip_bounds = GetGlobalClipBounds();
+  clip_bounds.Offset(-0.f, -0.f);
+  return clip_bounds;
+}
+
+void CudaCanvas::OnSave() { state_stack_.emplace_back(state_stack_.back()); }
+
+void CudaCanvas::OnRestore() {
+  if (state_stack_.size() == 1) return;
+  state_stack_.pop_back();
+}
+
+void CudaCanvas::OnRestoreToCount(int saveCount) {
+  if (saveCount < 1) return;
+  while (state_stack_.size() > static_cast<size_t>(saveCount)) this->OnRestore();
+}
+
+void CudaCanvas::OnFlush() {}
+
+// SWCanvas::OnClipRect (sw_canvas.cc:297-313): an intersecting rect under a
+// scale/translate CTM only tightens the integer scan rectangle.
+void CudaCanvas::OnClipRect(const Rect& rect, ClipOp op) {
+  if (op == ClipOp::kDifference || !CurrentTransform().OnlyScaleAndTranslate()) {
+    Canvas::OnClipRect(rect, op);
+    return;
+  }
+}
+
+// SWCanvas::OnClipPath (sw_canvas.cc:315-336)
+void CudaCanvas::OnClipPath(const Path& path, ClipOp op) {
+  std::vector<skb_dl_seg> segs;
+  LowerPathToSegs(path, &segs);
+  skb_dl_op o{};
+  o.kind = SKB_OP_CLIP;
+  o.surface = surface_;
+  o.path = builder_->AddPath(segs);
+  o.clip_in = state_stack_.back().clip_id;
+  o.clip_out = builder_->NewClipState();
+  o.fill_type = path.GetFillType() == Path::PathFillType::kEvenOdd ? 1u : 0u;
+  o.aux = op == ClipOp::kIntersect ? 1u : 0u;
+  Matrix m = CurrentTransform();
+  o.ctm[0] = m.GetScaleX();
+  o.ctm[1] = m.GetSkewX();
+  o.ctm[2] = m.GetTranslateX();
+  o.ctm[3] = m.GetSkewY();
+  o.ctm[4] = m.GetScaleY();
+  o.ctm[5] = m.GetTranslateY();
+  Rect cb = ScanClipBounds();
+  o.clip_bounds[0] = cb.Left();
+  o.clip_bounds[1] = cb.Top();
+  o.clip_bounds[2] = cb.Right();
+  o.clip_bounds[3] = cb.Bottom();
+  builder_->AddOp(o);
+  state_stack_.back().clip_id = o.clip_out;
+}
+
+void CudaCanvas::EmitFill(const Path& path, const Matrix& m, uint32_t paint_index) {
+  if (m.HasPersp()) {
+    NoteUnsupported("perspective CTM");
+    return;
+  }
+  std::vector<skb_dl_seg> segs;
+  LowerPathToSegs(path, &segs);
+  if (segs.empty()) return;
+  skb_dl_op o{};
+  o.kind = SKB_OP_FILL;
+  o.surface = surface_;
+  o.path = builder_->AddPath(segs);
+  o.paint = paint_index;
+  o.clip_in = state_stack_.back().clip_id;
+  o.fill_type = path.GetFillType() == Path::PathFillType::kEvenOdd ? 1u : 0u;
+  o.ctm[0] = m.GetScaleX();
+  o.ctm[1] = m.GetSkewX();
+  o.ctm[2] = m.GetTranslateX();
+  o.ctm[3] = m.GetSkewY();
+  o.ctm[4] = m.GetScaleY();
+  o.ctm[5] = m.GetTranslateY();
+  Rect cb = ScanClipBounds();
+  o.clip_bounds[0] = cb.Left();
+  o.clip_bounds[1] = cb.Top();
+  o.clip_bounds[2] = cb.Right();
+  o.clip_bounds[3] = cb.Bottom();
+  builder_->AddOp(o);
+}
+
+namespace {
+
+// PointsToUnit (src/render/sw/sw_span_brush.cc:164-198), same Matrix calls in the same order.
+Matrix PointsToUnit(const Shader::GradientInfo& info, Shader::GradientType type) {
+  if (type == Shader::GradientType::kLinear) {
+    Vec2 start = Vec2{(info.point[0])};
+    Vec2 stop = Vec2{info.point[1]};
+    Vec2 ss = stop - start;
+    float length = ss.Length();
+    float scale = length > 0 ? 1.0f / length : 0;
+    Vec2 unit_ss = ss * scale;
+    float sine = -unit_ss.y;
+    float cosine = unit_ss.x;
+    Matrix rotate;
+    rotate.SetScaleX(cosine);
+    rotate.SetSkewX(-sine);
+    rotate.SetSkewY(sine);
+    rotate.SetScaleY(cosine);
+    return rotate * Matrix::Scale(scale, scale) * Matrix::Translate(-start.x, -start.y);
+  } else if (type == Shader::GradientType::kRadial) {
+    float radius = info.radius[0];
+    Vec2 center = Vec2{info.point[0]};
+    float scale = radius > 0 ? 1.0f / radius : 0;
+    return Matrix::Scale(scale, scale) * Matrix::Translate(-center.x, -center.y);
+  } else if (type == Shader::GradientType::kSweep) {
+    Vec2 center = Vec2{info.point[0]};
+    return Matrix::Translate(-center.x, -center.y);
+  }
+  return Matrix{};
+}
+
+void StoreAffine(const Matrix& m, float out[6]) {
+  out[0] = m.GetScaleX();
+  out[1] = m.GetSkewX();
+  out[2] = m.GetTranslateX();
+  out[3] = m.GetSkewY();
+  out[4] = m.GetScaleY();
+  out[5] = m.GetTranslateY();
+}
+
+// ComputeBoundsIfStroke (src/render/sw/sw_canvas.cc:135-144)
+Rect ComputeBoundsIfStroke(Rect bounds, const Paint& paint) {
+  if (paint.GetStyle() != Paint::kFill_Style) {
+    float stroke_width = paint.GetStrokeWidth();
+    bounds.SetLTRB(std::floor(bounds.Left() - stroke_width), std::floor(bounds.Top() - stroke_width),
+                   std::floor(bounds.Right() + stroke_width), std::floor(bounds.Bottom() + stroke_width));
+  }
+  return bounds;
+}
+
+}  // namespace
+
+// SWCanvas::GenerateBrush (sw_canvas.cc:727-795), not-drawing-layer branch.
+uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
+  skb_dl_paint p{};
+  p.global_alpha = 255;
+  if (paint.GetColorFilter()) NoteUnsupported("color filter");
+  if (paint.GetBlendMode() != BlendMode::kSrcOver) NoteUnsupported("blend mode other than SrcOver");
+  auto shader = paint.GetShader();
+  if (shader) {
+    Shader::GradientInfo info{};
+    Shader::GradientType type = shader->AsGradient(&info);
+    if (type == Shader::kLinear || type == Shader::kRadial || type == Shader::kSweep) {
+      Matrix device_to_local;
+      shader->GetLocalMatrix().Invert(&device_to_local);
+      Matrix layer_to_local;
+      CurrentTransform().Invert(&layer_to_local);
+      device_to_local = device_to_local * layer_to_local;
+      Matrix ptu = PointsToUnit(info, type) * device_to_local;
+      StoreAffine(ptu, p.m);
+      p.type = type == Shader::kLinear ? SKB_PAINT_LINEAR
+                                       : (type == Shader::kRadial ? SKB_PAINT_RADIAL : SKB_PAINT_SWEEP);
+      p.tile_mode = static_cast<uint32_t>(info.tile_mode);
+      p.n_colors = static_cast<uint32_t>(info.colors.size());
+      p.has_stops = info.color_offsets.empty() ? 0u : 1u;
+      std::vector<float> cols(4 * info.colors.size());
+      for (size_t i = 0; i < info.colors.size(); i++) {
+        cols[4 * i + 0] = info.colors[i].x;
+        cols[4 * i + 1] = info.colors[i].y;
+        cols[4 * i + 2] = info.colors[i].z;
+        cols[4 * i + 3] = info.colors[i].w;
+      }
+      std::vector<float> offs(info.colors.size(), 0.f);
+      for (size_t i = 0; i < info.color_offsets.size() && i < offs.size(); i++) offs[i] = info.color_offsets[i];
+      p.stop_off = builder_->AddStops(cols.data(), offs.data(), p.n_colors);
+      p.bias = info.radius[0];
+      p.scale = info.radius[1];
+      return builder_->AddPaint(p);
+    }
+    if (type == Shader::kConical) {
+      NoteUnsupported("two-point conical gradient");
+    } else if (shader->AsImage()) {
+      NoteUnsupported("image shader");
+    }
+  }
+  Color4f color = stroke ? paint.GetStrokeColor() : paint.GetFillColor();
+  p.type = SKB_PAINT_SOLID;
+  p.color[0] = color.r;
+  p.color[1] = color.g;
+  p.color[2] = color.b;
+  p.color[3] = color.a;
+  return builder_->AddPaint(p);
+}
+
+void CudaCanvas::FillPath(const Path& path, const Paint& paint, bool stroke) {
+  EmitFill(path, CurrentTransform(), MakeBrush(paint, stroke));
+}
+
+// SWCanvas::OnDrawPath (sw_canvas.cc:357-411)
+void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
+  if (paint.GetMaskFilter() || paint.GetImageFilter()) {
+    if (paint.GetMaskFilter() && paint.GetMaskFilter()->GetBlurStyle() == BlurStyle::kNormal &&
+        !paint.GetImageFilter()) {
+      HandleMaskBlur(path, paint);
+    } else {
+      NoteUnsupported("mask/image filter other than MaskFilter::MakeBlur(kNormal)");
+    }
+    return;
+  }
+
+  bool need_fill = paint.GetStyle() != Paint::kStroke_Style;
+  bool need_stroke = paint.GetStyle() != Paint::kFill_Style;
+
+  auto draw_fill = [&]() {
+    Path temp;
+    if (paint.GetPathEffect() && paint.GetPathEffect()->FilterPath(&temp, path, false, paint)) {
+      FillPath(temp, paint, false);
+    } else {
+      FillPath(path, paint, false);
+    }
+  };
+  auto draw_stroke = [&]() {
+    Stroke stroke(paint);
+    Path temp;
+    Path quad;
+    Path outline;
+    if (paint.GetPathEffect() && paint.GetPathEffect()->FilterPath(&temp, path, true, paint)) {
+      stroke.QuadPath(temp, &quad);
+      stroke.StrokePath(quad, &outline);
+    } else {
+      stroke.QuadPath(path, &quad);
+      stroke.StrokePath(quad, &outline);
+    }
+    FillPath(outline, paint, true);
+  };
+  // DrawFillStrokeInPaintOrder (src/render/paint_order.hpp:12-31)
+  if (paint.GetStyle() == Paint::kStrokeThenFill_Style) {
+    if (need_stroke) draw_stroke();
+    if (need_fill) draw_fill();
+  } else {
+    if (need_fill) draw_fill();
+    if (need_stroke) draw_stroke();
+  }
+}
+
+// SWCanvas::OnDrawPaint (sw_canvas.cc:413-439): the whole bitmap, identity transform, no scan clip.
+void CudaCanvas::OnDrawPaint(const Paint& paint) {
+  Rect bounds = Rect::MakeWH(Width(), Height());
+  Path path;
+  path.AddRect(bounds);
+  std::vector<skb_dl_seg> segs;
+  LowerPathToSegs(path, &segs);
+  skb_dl_op o{};
+  o.kind = SKB_OP_FILL;
+  o.surface = surface_;
+  o.path = builder_->AddPath(segs);
+  o.paint = MakeBrush(paint, false);
+  o.clip_in = state_stack_.back().clip_id;
+  o.fill_type = 0;
+  StoreAffine(Matrix{}, o.ctm);
+  o.clip_bounds[0] = -1E9F;  // SWRaster::kCullRect (sw_raster.hpp:84)
+  o.clip_bounds[1] = -1E9F;
+  o.clip_bounds[2] = 1E9F;
+  o.clip_bounds[3] = 1E9F;
+  builder_->AddOp(o);
+}
+
+// SWCanvas::HandleFilter + MaskFilterOnFilter(kNormal) + ImageFilterBase::BlurBitmapToCanvas
+// (sw_canvas.cc:797-826, mask_filter.cc:51-60, image_filter.cc:33-41,184-194).
+void CudaCanvas::HandleMaskBlur(const Path& path, const Paint& paint) {
+  Paint work_paint = paint;
+  work_paint.SetMaskFilter(nullptr);
+  work_paint.SetImageFilter(nullptr);
+
+  auto mask_filter = paint.GetMaskFilter();
+  Rect bounds = ComputeBoundsIfStroke(path.GetBounds(), paint);
+  float radius = mask_filter->GetBlurRadius();
+  Rect fb = Rect::MakeLTRB(std::floor(bounds.Left() - radius), std::floor(bounds.Top() - radius),
+                           std::ceil(bounds.Right() + radius), std::ceil(bounds.Bottom() + radius));
+  uint32_t w = static_cast<uint32_t>(fb.Width());
+  uint32_t h = static_cast<uint32_t>(fb.Height());
+  if (w == 0 || h == 0) return;  // the reference dereferences a null temp canvas here
+
+  uint32_t temp = builder_->AddSurface(w, h);
+  {
+    CudaCanvas temp_canvas(builder_, temp, w, h);
+    temp_canvas.Translate(-fb.Left(), -fb.Top());
+    temp_canvas.DrawPath(path, work_paint);
+    if (!temp_canvas.Unsupported().empty()) NoteUnsupported(temp_canvas.Unsupported().c_str());
+  }
+  uint32_t blurred = builder_->AddSurface(w, h);
+  skb_dl_op b{};
+  b.kind = SKB_OP_BLUR;
+  b.surface = blurred;
+  b.aux = temp;
+  b.clip_bounds[0] = std::round(std::max(radius, radius));
+  builder_->AddOp(b);
+
+  DrawSurfaceImage(blurred, w, h, fb, work_paint);
+}
+
+// Canvas::DrawImage(image, rect, paint) -> SWCanvas::OnDrawImageRect (sw_canvas.cc:641-677)
+// -> GenerateBrush image branch (sw_canvas.cc:755-787), for an image that lives on the device.
+void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih, const Rect& dst,
+                                  const Paint& paint) {
+  Rect src = Rect::MakeWH(iw, ih);
+  if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
+  Matrix local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
+                        Matrix::Scale(dst.Width() / src.Width(), dst.Height() / src.Height()) *
+                        Matrix::Translate(-src.Left(), -src.Top());
+  Matrix inverse;
+  local_matrix.Invert(&inverse);
+  Matrix matrix = Matrix::Scale(1.f / iw, 1.f / ih) * inverse;
+  Matrix layer_to_local;
+  CurrentTransform().Invert(&layer_to_local);
+  matrix = matrix * layer_to_local;
+
+  skb_dl_paint p{};
+  p.type = SKB_PAINT_IMAGE;
+  p.tile_mode = 3;
+  StoreAffine(matrix, p.m);
+  p.image_surface = src_surface;
+  // work_paint.SetStyle(kFill) precedes GetAlphaF() in the reference (sw_canvas.cc:656,784)
+  p.global_alpha = static_cast<uint8_t>(255 * paint.GetFillColor().a);
+  if (paint.GetColorFilter()) NoteUnsupported("color filter");
+  if (paint.GetBlendMode() != BlendMode::kSrcOver) NoteUnsupported("blend mode other than SrcOver");
+  uint32_t paint_index = builder_->AddPaint(p);
+
+  Path path;
+  path.AddRect(dst);
+  EmitFill(path, CurrentTransform(), paint_index);
+}
+
+void CudaCanvas::OnSaveLayer(const Rect&, const Paint&) {
+  // SWCanvas::OnSaveLayer renders into an offscreen bitmap (sw_canvas.cc:441-484); not on the
+  // hot path of this round.  Keep Save/Restore balanced.
+  NoteUnsupported("SaveLayer");
+  state_stack_.emplace_back(state_stack_.back());
+}
+
+void CudaCanvas::OnDrawBlob(const TextBlob*, float, float, Paint const&) { NoteUnsupported("text"); }
+
+void CudaCanvas::OnDrawGlyphs(uint32_t, const GlyphID*, const float*, const float*, const Font&,
+                              const Paint&) {
+  NoteUnsupported("text");
+}
+
+void CudaCanvas::OnDrawImageRect(std::shared_ptr<Image>, const Rect&, const Rect&, const SamplingOptions&,
+                                 Paint const*) {
+  NoteUnsupported("DrawImage of a host image");
+}
+
+}  // namespace skity

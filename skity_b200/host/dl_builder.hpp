@@ -1,0 +1,126 @@
+// Host-side builder of the flat display list (include/skb_dl.h).
+//
+// Deep-copies everything at call time into one arena, the way the reference's
+// RecordingCanvas copies Path/Paint into its op stream
+// (src/recorder/recorded_op.hpp:238-243): the caller may destroy its Path /
+// Paint / Shader as soon as the Canvas call returns.
+#ifndef SKITY_B200_HOST_DL_BUILDER_HPP
+#define SKITY_B200_HOST_DL_BUILDER_HPP
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "include/skb_dl.h"
+
+namespace skb {
+
+class DlBuilder {
+ public:
+  DlBuilder() = default;
+
+  void Reset(uint32_t canvas_w, uint32_t canvas_h) {
+    surfaces_.clear();
+    ops_.clear();
+    paths_.clear();
+    segs_.clear();
+    paints_.clear();
+    stops_.clear();
+    n_clip_states_ = 0;
+    AddSurface(canvas_w, canvas_h);
+  }
+
+  uint32_t AddSurface(uint32_t w, uint32_t h) {
+    skb_dl_surface s{};
+    s.width = w;
+    s.height = h;
+    surfaces_.push_back(s);
+    return static_cast<uint32_t>(surfaces_.size() - 1);
+  }
+
+  uint32_t NewClipState() { return ++n_clip_states_; }
+
+  uint32_t AddPath(const std::vector<skb_dl_seg>& segs) {
+    skb_dl_path p{};
+    p.seg_off = static_cast<uint32_t>(segs_.size());
+    p.n_segs = static_cast<uint32_t>(segs.size());
+    segs_.insert(segs_.end(), segs.begin(), segs.end());
+    paths_.push_back(p);
+    return static_cast<uint32_t>(paths_.size() - 1);
+  }
+
+  uint32_t AddPaint(const skb_dl_paint& p) {
+    paints_.push_back(p);
+    return static_cast<uint32_t>(paints_.size() - 1);
+  }
+
+  // returns the float offset of the block in the stop pool
+  uint32_t AddStops(const float* colors4, const float* stops, uint32_t n) {
+    uint32_t off = static_cast<uint32_t>(stops_.size());
+    stops_.insert(stops_.end(), colors4, colors4 + 4 * static_cast<size_t>(n));
+    if (stops) {
+      stops_.insert(stops_.end(), stops, stops + n);
+    } else {
+      stops_.insert(stops_.end(), n, 0.f);
+    }
+    return off;
+  }
+
+  void AddOp(const skb_dl_op& op) { ops_.push_back(op); }
+
+  size_t OpCount() const { return ops_.size(); }
+  uint32_t SurfaceCount() const { return static_cast<uint32_t>(surfaces_.size()); }
+
+  std::vector<uint8_t> Serialize() const {
+    auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
+    skb_dl_header h{};
+    h.magic = SKB_DL_MAGIC;
+    h.version = SKB_DL_VERSION;
+    h.n_surfaces = static_cast<uint32_t>(surfaces_.size());
+    h.n_ops = static_cast<uint32_t>(ops_.size());
+    h.n_paths = static_cast<uint32_t>(paths_.size());
+    h.n_segs = static_cast<uint32_t>(segs_.size());
+    h.n_paints = static_cast<uint32_t>(paints_.size());
+    h.n_stop_floats = static_cast<uint32_t>(stops_.size());
+    h.n_clip_states = n_clip_states_;
+    size_t off = align16(sizeof(h));
+    h.off_surfaces = static_cast<uint32_t>(off);
+    off = align16(off + surfaces_.size() * sizeof(skb_dl_surface));
+    h.off_ops = static_cast<uint32_t>(off);
+    off = align16(off + ops_.size() * sizeof(skb_dl_op));
+    h.off_paths = static_cast<uint32_t>(off);
+    off = align16(off + paths_.size() * sizeof(skb_dl_path));
+    h.off_segs = static_cast<uint32_t>(off);
+    off = align16(off + segs_.size() * sizeof(skb_dl_seg));
+    h.off_paints = static_cast<uint32_t>(off);
+    off = align16(off + paints_.size() * sizeof(skb_dl_paint));
+    h.off_stops = static_cast<uint32_t>(off);
+    off = align16(off + stops_.size() * sizeof(float));
+    h.total_bytes = static_cast<uint32_t>(off);
+    std::vector<uint8_t> out(off, 0);
+    std::memcpy(out.data(), &h, sizeof(h));
+    auto put = [&](uint32_t o, const void* p, size_t n) {
+      if (n) std::memcpy(out.data() + o, p, n);
+    };
+    put(h.off_surfaces, surfaces_.data(), surfaces_.size() * sizeof(skb_dl_surface));
+    put(h.off_ops, ops_.data(), ops_.size() * sizeof(skb_dl_op));
+    put(h.off_paths, paths_.data(), paths_.size() * sizeof(skb_dl_path));
+    put(h.off_segs, segs_.data(), segs_.size() * sizeof(skb_dl_seg));
+    put(h.off_paints, paints_.data(), paints_.size() * sizeof(skb_dl_paint));
+    put(h.off_stops, stops_.data(), stops_.size() * sizeof(float));
+    return out;
+  }
+
+ private:
+  std::vector<skb_dl_surface> surfaces_;
+  std::vector<skb_dl_op> ops_;
+  std::vector<skb_dl_path> paths_;
+  std::vector<skb_dl_seg> segs_;
+  std::vector<skb_dl_paint> paints_;
+  std::vector<float> stops_;
+  uint32_t n_clip_states_ = 0;
+};
+
+}  // namespace skb
+
+#endif  // SKITY_B200_HOST_DL_BUILDER_HPP

@@ -166,7 +166,7 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
   paint->SetStrokeColor(sc[0], sc[1], sc[2], sc[3]);
   if (blur_style != 0) {
     paint->SetMaskFilter(
-        skity::MaskFilter::MakeBlur(static_cast<skity::BlurStyle>(blur_style - 1), blur_radius));
+        skity::MaskFilter::MakeBlur(static_cast<skity::BlurStyle>(blur_style), blur_radius));
   }
   if (shader != 0) {
     float p[4];
