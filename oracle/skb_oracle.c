@@ -808,13 +808,113 @@ static void walk_edges(edge* E, int even_odd, builder* sb, int start_y, int stop
   }
 }
 
-static int edge_cmp(const void* pa, const void* pb) { /* SortEdges — :679-697 */
-  const edge* a = (const edge*)pa;
-  const edge* b = (const edge*)pb;
+/* SortEdges — sw_raster.cc:679-697: std::sort by (upper_y, x, dx).  std::sort is not
+ * stable and stroke outlines are full of edges with identical keys, so the result
+ * the reference produces depends on libstdc++'s algorithm.  It is restated here
+ * (GCC 13 bits/stl_algo.h: introsort, threshold 16, median-of-three to first,
+ * unguarded partition, final insertion sort; heapsort when the depth limit hits). */
+static inline int edge_less(const edge* a, const edge* b) {
   int va = a->upper_y, vb = b->upper_y;
   if (va == vb) { va = a->x; vb = b->x; }
   if (va == vb) { va = a->dx; vb = b->dx; }
-  return va < vb ? -1 : (va > vb ? 1 : 0);
+  return va < vb;
+}
+static inline void edge_swap(edge* a, edge* b) { edge t = *a; *a = *b; *b = t; }
+static void ss_unguarded_linear_insert(edge* last) {
+  edge val = *last;
+  edge* next = last - 1;
+  while (edge_less(&val, next)) { *last = *next; last = next; --next; }
+  *last = val;
+}
+static void ss_insertion_sort(edge* first, edge* last) {
+  if (first == last) return;
+  for (edge* i = first + 1; i != last; ++i) {
+    if (edge_less(i, first)) {
+      edge val = *i;
+      memmove(first + 1, first, (size_t)(i - first) * sizeof(edge));
+      *first = val;
+    } else {
+      ss_unguarded_linear_insert(i);
+    }
+  }
+}
+static void ss_adjust_heap(edge* first, long hole, long len, edge value) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (edge_less(first + child, first + (child - 1))) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  long parent = (hole - 1) / 2; /* __push_heap */
+  while (hole > top && edge_less(first + parent, &value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+static void ss_heap_sort(edge* first, edge* last) { /* __partial_sort(first,last,last) */
+  long len = last - first;
+  if (len >= 2) { /* __make_heap */
+    long parent = (len - 2) / 2;
+    for (;;) {
+      edge v = first[parent];
+      ss_adjust_heap(first, parent, len, v);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  while (last - first > 1) { /* __sort_heap */
+    --last;
+    edge v = *last;
+    *last = *first;
+    ss_adjust_heap(first, 0, last - first, v);
+  }
+}
+static void ss_introsort_loop(edge* first, edge* last, long depth) {
+  while (last - first > 16) {
+    if (depth == 0) { ss_heap_sort(first, last); return; }
+    --depth;
+    edge* mid = first + (last - first) / 2;
+    edge *a = first + 1, *b = mid, *c = last - 1; /* __move_median_to_first */
+    if (edge_less(a, b)) {
+      if (edge_less(b, c)) edge_swap(first, b);
+      else if (edge_less(a, c)) edge_swap(first, c);
+      else edge_swap(first, a);
+    } else if (edge_less(a, c)) edge_swap(first, a);
+    else if (edge_less(b, c)) edge_swap(first, c);
+    else edge_swap(first, b);
+    edge *lo = first + 1, *hi = last; /* __unguarded_partition */
+    for (;;) {
+      while (edge_less(lo, first)) ++lo;
+      --hi;
+      while (edge_less(first, hi)) --hi;
+      if (!(lo < hi)) break;
+      edge_swap(lo, hi);
+      ++lo;
+    }
+    ss_introsort_loop(lo, last, depth);
+    last = lo;
+  }
+}
+static void sort_edges(edge* first, size_t n) {
+  if (n == 0) return;
+  long lg = 0;
+  for (size_t v = n; v > 1; v >>= 1) lg++;
+  ss_introsort_loop(first, first + n, lg * 2);
+  if (n > 16) {
+    ss_insertion_sort(first, first + 16);
+    for (edge* i = first + 16; i != first + n; ++i) ss_unguarded_linear_insert(i);
+  } else {
+    ss_insertion_sort(first, first + n);
+  }
 }
 
 /* SWRaster::RastePath — sw_raster.cc:731-786.  Appends spans to `out`; bounds4 = raster bounds_. */
@@ -856,7 +956,7 @@ static void raster_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ct
   }
   free(pb.v);
   if (ne == 2) { free(E); return; }
-  qsort(E + 2, ne - 2, sizeof(edge), edge_cmp);
+  sort_edges(E + 2, ne - 2);
   /* ProcessEdges — :706-729 */
   for (size_t i = 2; i < ne; i++) { E[i].prev = (int)i - 1; E[i].next = (int)i + 1; }
   E[2].prev = HEAD;
@@ -939,7 +1039,7 @@ static void lerp_color(const skb_dl_paint* p, const float* pool, float t, float 
   else if (p->tile_mode == 1) { t = t - floorf(t); }
   else if (p->tile_mode == 2) {
     float t1 = t - 1;
-    float t2 = (float)(t1 - 2 * floor(t1 * 0.5)) - 1; /* std::floor(double) — mixed precision as in the reference */
+    float t2 = (float)(t1 - 2 * floor(t1 * 0.5) - 1); /* evaluated in double, rounded once (t1 * 0.5 promotes) */
     t = fabsf(t2);
   }
   int n = (int)p->n_colors;
@@ -1086,7 +1186,10 @@ static void spans_subtract(const spanvec* sub, const spanvec* min, spanvec* out)
   }
   free(ms.v);
 }
-typedef struct clip_state { spanvec spans; int op; int has; } clip_state; /* SWCanvas::State */
+/* SWCanvas::State — sw_canvas.hpp:26-45.  HasClip() is `!clip_spans_.empty()`: a clip whose span
+ * list came out EMPTY (e.g. two disjoint nested clips) behaves as NO clip at all. */
+typedef struct clip_state { spanvec spans; int op; } clip_state;
+static inline int clip_has(const clip_state* c) { return c && c->spans.n > 0; }
 /* State::PerformClip — sw_canvas.cc:158-176 */
 static void perform_clip(const clip_state* st, const spanvec* in, spanvec* out) {
   if (st->op == 0) { spans_subtract(in, &st->spans, out); return; }
@@ -1102,8 +1205,7 @@ static int merge_cmp(const void* pa, const void* pb) {
 /* SWCanvas::OnClipPath + State::RecursiveClip/PerformMerge — sw_canvas.cc:178-217,315-336 */
 static void clip_refine(const clip_state* parent, const spanvec* fresh, int op, clip_state* out) {
   memset(out, 0, sizeof(*out));
-  out->has = 1;
-  if (!parent || !parent->has) {
+  if (!clip_has(parent)) {
     for (size_t i = 0; i < fresh->n; i++) sv_push(&out->spans, fresh->v[i].x, fresh->v[i].y, fresh->v[i].len, fresh->v[i].cover);
     out->op = op;
     return;
@@ -1224,7 +1326,7 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
         spans.n = 0;
         raster_path(segs + p->seg_off, p->n_segs, op->ctm, op->clip_bounds, (int)op->fill_type, &spans, NULL);
         const spanvec* use = &spans;
-        if (op->clip_in) {
+        if (op->clip_in && clip_has(&clips[op->clip_in])) {
           clipped.n = 0;
           perform_clip(&clips[op->clip_in], &spans, &clipped);
           use = &clipped;
