@@ -1,0 +1,116 @@
+/*
+ * skb.h — C ABI of the B200 rasterisation backend (libskb.so).
+ *
+ * This is the boundary the CUDA side exports and the only thing the host-side
+ * skity plug-in (skity_b200/host/) binds.  Conventions follow the reference's
+ * own C API (module/capi): opaque handles `typedef struct x_s* x`
+ * (include/skity_c/skity_base.h:34), every fallible call returns a result enum
+ * that is 0 on success and negative on failure (:47-56), out-parameters last,
+ * create/destroy pairs, no exceptions cross the boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to its root):
+ *   skb_device_create / destroy     GLContextCreate(void*) and the GPUContext lifetime
+ *                                   (include/skity/gpu/gpu_context_gl.hpp:115, src/gpu/gl/gpu_context_impl_gl.cc:74-82)
+ *   skb_surface_create / destroy    GPUContext::CreateSurface(GPUSurfaceDescriptor*) (include/skity/gpu/gpu_context.hpp:73-90);
+ *                                   on the CPU path: Bitmap(w,h,kPremul) + Canvas::MakeSoftwareCanvas (src/render/sw/sw_canvas.cc:146-156)
+ *   skb_frame_begin                 GPUSurface::LockCanvas(bool clear) (include/skity/gpu/gpu_surface.hpp:96-104)
+ *   skb_frame_encode                the draw calls of one frame: what SWCanvas::OnDrawPath/OnClipPath/HandleFilter
+ *                                   hand to SWRaster::RastePath + SWSpanBrush::Brush + SWStackBlur
+ *                                   (src/render/sw/sw_canvas.cc:315-411,797-826), as a flat list (include/skb_dl.h)
+ *   skb_frame_flush                 Canvas::Flush / GPUSurface::Flush (include/skity/gpu/gpu_surface.hpp:106-111)
+ *   skb_surface_read_pixels         GPUSurface::ReadPixels(const Rect&) (include/skity/gpu/gpu_surface.hpp:113-128)
+ *   skb_surface_device_ptr          (no equivalent) device address of the band, for the NCCL gather
+ *
+ * Pixels are premultiplied RGBA8 (bytes R,G,B,A), the configuration the
+ * reference's Bitmap(AlphaType::kPremul_AlphaType, ColorType::kRGBA) has.
+ * Threading: like GPUContext, one thread drives a device and its surfaces
+ * (include/skity/gpu/gpu_context.hpp:65,101).
+ */
+#ifndef SKB_H
+#define SKB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SKB_API
+#else
+#define SKB_API __attribute__((visibility("default")))
+#endif
+
+typedef struct skb_device_s* skb_device;
+typedef struct skb_surface_s* skb_surface;
+
+typedef enum skb_result {
+  SKB_SUCCESS = 0,
+  SKB_ERROR_INVALID_ARGUMENT = -1,
+  SKB_ERROR_CUDA = -2,          /* a CUDA runtime call or kernel failed; see skb_get_last_error_string() */
+  SKB_ERROR_OUT_OF_MEMORY = -3,
+  SKB_ERROR_UNSUPPORTED = -4,   /* the display list uses something outside the backend's scope */
+  SKB_ERROR_BAD_DISPLAY_LIST = -5,
+  SKB_ERROR_NO_DEVICE = -6      /* no usable CUDA device: there is no CPU fallback */
+} skb_result;
+
+/* Per-frame counters and device timings (CUDA events on the surface's stream). */
+typedef struct skb_frame_stats {
+  uint32_t n_ops, n_segs, n_prims, n_edges_slots;
+  uint64_t n_rows, n_records, n_items, n_items_nonempty, n_cmds, n_tiles;
+  uint64_t pool_capacity;
+  uint32_t n_launches;   /* kernels launched by the last flush */
+  uint32_t n_retries;    /* record-pool overflows that forced a re-run */
+  float ms_total;        /* first launch to last launch, device time */
+  float ms_stage[8];     /* 0 flatten, 1 setup+scans, 2 walk, 3 coverage, 4 bin, 5 fine, 6 blur, 7 clip */
+  uint64_t bytes_fine;   /* algorithmic bytes of the fine pass (pixels + commands + masks) */
+  uint64_t bytes_cover;  /* algorithmic bytes of the coverage pass (records in, masks out) */
+} skb_frame_stats;
+
+SKB_API skb_result skb_device_create(int ordinal, skb_device* out_device);
+SKB_API void skb_device_destroy(skb_device device);
+SKB_API skb_result skb_device_sm_count(skb_device device, int* out_sm_count);
+
+SKB_API skb_result skb_surface_create(skb_device device, uint32_t width, uint32_t height, skb_surface* out_surface);
+SKB_API void skb_surface_destroy(skb_surface surface);
+
+/* Restrict rendering to the tile band [y0, y1) of the canvas (rows rounded outwards to 16).
+ * Used to split one canvas across GPUs; y1 = 0 resets to the whole surface. */
+SKB_API skb_result skb_surface_set_band(skb_surface surface, uint32_t y0, uint32_t y1);
+
+/* clear != 0 zeroes the surface (transparent black), like LockCanvas(true). */
+SKB_API skb_result skb_frame_begin(skb_surface surface, int clear);
+/* Copies the display list to the device (host -> device, asynchronous on the surface's stream
+ * when `display_list` is pinned) and validates it.  One display list per frame. */
+SKB_API skb_result skb_frame_encode(skb_surface surface, const void* display_list, size_t bytes);
+/* Launches every stage for the encoded frame.  Asynchronous unless the record pool overflows. */
+SKB_API skb_result skb_frame_flush(skb_surface surface);
+/* Blocks until the surface's stream is idle; returns the first asynchronous error. */
+SKB_API skb_result skb_surface_sync(skb_surface surface);
+
+/* Copies the rectangle to host memory (rows `stride` bytes apart).  Synchronises. */
+SKB_API skb_result skb_surface_read_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
+                                           uint32_t height, void* dst, size_t stride);
+/* Uploads pixels into the surface (the LockCanvas(false) case: drawing over existing content). */
+SKB_API skb_result skb_surface_write_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
+                                            uint32_t height, const void* src, size_t stride);
+SKB_API skb_result skb_surface_device_ptr(skb_surface surface, void** out_ptr, size_t* out_pitch_bytes);
+SKB_API skb_result skb_surface_stream(skb_surface surface, void** out_cuda_stream);
+
+SKB_API skb_result skb_frame_get_stats(skb_surface surface, skb_frame_stats* out_stats);
+
+/* Test tap: coverage the last flushed frame computed for raster op `op_index`, as the two
+ * planes the fine pass blends in order (directly emitted spans, then accumulated spans), over
+ * the rectangle; dst planes are width*height bytes each. */
+SKB_API skb_result skb_debug_read_coverage(skb_surface surface, uint32_t op_index, int32_t x, int32_t y,
+                                           uint32_t width, uint32_t height, uint8_t* direct, uint8_t* accum);
+
+SKB_API const char* skb_get_last_error_string(void);
+SKB_API const char* skb_version_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SKB_H */

@@ -1,0 +1,1416 @@
+// skb_backend.cu — CUDA kernels of the raster pipeline and the C ABI (include/skb.h).
+//
+// Stages per frame (all on the surface's stream; sm_100a only):
+//   1 flatten   k_op_init, k_seg_count, scan, k_flatten   curves -> lowered primitives -> edges
+//   2 setup     k_op_setup, scans                          bounds, scan rectangles, work-item tables
+//   3 walk      k_walk                                     active-edge sweep -> trapezoid rows (TrapRec)
+//   4 coverage  k_cover                                    per (op, 16x16 tile): A8 masks + tile classes
+//   5 bin       scan, k_scatter                            per-tile command lists
+//   6 fine      k_fine                                     paint + SrcOver, 128-bit RGBA8 loads/stores
+//   7 blur      k_blur_h, k_blur_v                         StackBlur-exact triangular filter
+// HBM layout: see DESIGN.md §3.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "include/skb.h"
+#include "skity_b200/csrc/skb_stages.cuh"
+
+namespace skb {
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+
+#define SKB_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+      return SKB_ERROR_CUDA;                                                                 \
+    }                                                                                        \
+  } while (0)
+
+// ------------------------------------------------------------------ device tables
+struct SurfDesc {
+  uint8_t* px;          // premultiplied RGBA8, rows `pitch` bytes apart, padded to whole tiles
+  uint32_t w, h;        // logical size
+  uint32_t pitch;       // bytes
+  uint32_t tiles_x, tiles_y;
+  uint32_t tile_base;   // first global tile index
+  uint32_t row0, row1;  // rows this device renders (band), whole surface for temporaries
+};
+
+#define SKB_CMD_SOLID 0x80000000u
+
+__device__ __forceinline__ uint32_t find_interval(const uint32_t* off, uint32_t n, uint32_t v) {
+  // largest i in [0, n) with off[i] <= v   (off is non-decreasing, off[0] <= v)
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (off[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------- scan
+// Exclusive prefix sum of n uint32 in place, 2048 elements per CTA, recursive over block sums.
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_BLOCK (SCAN_THREADS * SCAN_ITEMS)
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_block(uint32_t* data, uint32_t n, uint32_t* block_sums) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    v[i] = idx < n ? data[idx] : 0u;
+    sum += v[i];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0u;
+    uint32_t wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = wi - w;  // exclusive
+    if (lane == SCAN_THREADS / 32 - 1 && block_sums) block_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + (incl - sum);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    if (idx < n) data[idx] = run;
+    run += v[i];
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* data, uint32_t n, const uint32_t* block_offsets) {
+  const uint32_t add = block_offsets[blockIdx.x];
+  const uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    uint32_t idx = base + i;
+    if (idx < n) data[idx] += add;
+  }
+}
+
+// ------------------------------------------------------------------ stage 1: flatten
+struct FrameTables {
+  const skb_dl_op* ops;
+  const skb_dl_path* paths;
+  const skb_dl_seg* segs;
+  const skb_dl_paint* paints;
+  const float* stops;
+  uint32_t n_ops, n_segs;
+};
+
+__global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op) {
+  uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= t.n_ops) return;
+  OpGeom g;
+  memset(&g, 0, sizeof(g));
+  g.bmin_x = g.bmin_y = INT_MAX;
+  g.bmax_x = g.bmax_y = INT_MIN;
+  g.empty = 1;
+  const skb_dl_op o = t.ops[op];
+  if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+    const skb_dl_path p = t.paths[o.path];
+    for (uint32_t i = 0; i < p.n_segs; i++) {
+      uint32_t s = p.seg_off + i;
+      seg_op[s] = op;
+      if ((t.segs[s].type_flags & SKB_SEG_TYPE_MASK) == SKB_SEG_POINT) {
+        V2 q = xform(o.ctm, seg_start_point(t.segs, s));
+        int32_t kx = float_key(q.x), ky = float_key(q.y);
+        g.bmin_x = min(g.bmin_x, kx); g.bmax_x = max(g.bmax_x, kx);
+        g.bmin_y = min(g.bmin_y, ky); g.bmax_y = max(g.bmax_y, ky);
+      }
+    }
+  }
+  geom[op] = g;
+}
+
+__global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= t.n_segs) return;
+  prim_cnt[s] = (uint32_t)seg_prim_count(t.segs[s]);
+}
+
+// One thread per lowered primitive: resolve (segment, k) from the scanned counts, evaluate and
+// transform its control points, fold them into the path bounds, emit its 0..2 edges.
+__global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_prims, const uint32_t* seg_op, OpGeom* geom,
+                          Edge* edges) {
+  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+  if (prim >= n_prims) return;
+  uint32_t seg = find_interval(prim_off, t.n_segs, prim);
+  int k = (int)(prim - prim_off[seg]);
+  int n = (int)(prim_off[seg + 1] - prim_off[seg]);
+  uint32_t op = seg_op[seg];
+  const float* ctm = t.ops[op].ctm;
+  V2 p[3];
+  int np = seg_prim(t.segs, seg, k, n, ctm, p);
+  OpGeom* g = &geom[op];
+  for (int j = 0; j < np; j++) {
+    int32_t kx = float_key(p[j].x), ky = float_key(p[j].y);
+    atomicMin(&g->bmin_x, kx); atomicMax(&g->bmax_x, kx);
+    atomicMin(&g->bmin_y, ky); atomicMax(&g->bmax_y, ky);
+  }
+  Edge slot[2];
+  flatten_prim(np, p, slot);
+  Edge* dst = edges + (size_t)2 * prim + (size_t)2 * op + 2;
+  dst[0] = slot[0];
+  dst[1] = slot[1];
+}
+
+// ------------------------------------------------------------------- stage 2: setup
+__global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom, const SurfDesc* surfs, uint32_t* row_cnt,
+                           uint32_t* item_cnt) {
+  uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= t.n_ops) return;
+  const skb_dl_op o = t.ops[op];
+  uint32_t rows = 0, items = 0;
+  if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+    OpGeom g = geom[op];
+    const skb_dl_path p = t.paths[o.path];
+    uint32_t first_prim = prim_off[p.seg_off];
+    uint32_t n_prims = prim_off[p.seg_off + p.n_segs] - first_prim;
+    g.first_prim = first_prim;
+    g.slot_base = 2 * first_prim + 2 * op;
+    g.n_slots = 2 + 2 * n_prims;
+    const SurfDesc sd = surfs[o.surface];
+    op_setup(g, o.clip_bounds, sd.w, sd.h, p.n_segs > 0);
+    if (!g.empty && g.ntx > 0) {
+      // keep only the tile rows this device renders (band split); the rows outside are another GPU's
+      int ty0 = max(g.ty0, (int)(sd.row0 / SKB_TILE));
+      int ty1 = min(g.ty0 + g.nty, (int)((sd.row1 + SKB_TILE - 1) / SKB_TILE));
+      if (ty1 <= ty0) {
+        g.ntx = g.nty = 0;
+      } else {
+        g.ty0 = ty0;
+        g.nty = ty1 - ty0;
+      }
+    }
+    if (!g.empty && g.ntx > 0) {
+      rows = (uint32_t)(g.nty * SKB_TILE);
+      items = (uint32_t)(g.ntx * g.nty);
+    }
+    if (o.kind == SKB_OP_FILL) {
+      const skb_dl_paint pt = t.paints[o.paint];
+      g.color = pt.type == SKB_PAINT_SOLID ? color4f_to_pm_word(pt.color[0], pt.color[1], pt.color[2], pt.color[3]) : 0u;
+    }
+    geom[op] = g;
+  }
+  row_cnt[op] = rows;
+  item_cnt[op] = items;
+}
+
+// -------------------------------------------------------------------- stage 3: walk
+__global__ void __launch_bounds__(64) k_walk(FrameTables t, OpGeom* geom, const uint32_t* row_base, Edge* edges, int32_t* ord,
+                                             TrapRec* pool, uint32_t* pool_next, uint32_t pool_cap, uint32_t* overflow,
+                                             uint2* rows) {
+  uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= t.n_ops) return;
+  const OpGeom g = geom[op];
+  if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  RecSink sink;
+  sink.pool = pool;
+  sink.pool_next = pool_next;
+  sink.pool_cap = pool_cap;
+  sink.overflow = overflow;
+  sink.rows = rows + row_base[op];
+  sink.row0 = g.ty0 * SKB_TILE;
+  sink.n_rows = g.nty * SKB_TILE;
+  sink_init(sink);
+  // rows below the last tile row are never read: stop the sweep there (rows are independent of later ones)
+  int stop_y = min(g.stop_y, sink.row0 + sink.n_rows);
+  walk_path(edges + g.slot_base, (int)g.n_slots, ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
+            g.left_clip, g.right_clip, (int)t.ops[op].fill_type, sink);
+}
+
+// ---------------------------------------------------------------- stage 4: coverage
+// One warp per (op, tile).  Lane L owns the 8 horizontally adjacent pixels (L&1)*8.. of tile row
+// L>>1, so a tile's A8 mask is written as 32 x 8 contiguous bytes = one coalesced 256-byte store.
+struct CoverArgs {
+  const OpGeom* geom;
+  const uint32_t* item_base;  // n_ops + 1
+  const uint32_t* row_base;
+  uint32_t n_ops, n_items;
+  const skb_dl_op* ops;
+  const SurfDesc* surfs;
+  const TrapRec* pool;
+  const uint2* rows;
+  uint8_t* mask0;  // n_items * 256: plane blended first (direct spans, or the only plane)
+  uint8_t* mask1;  // n_items * 256: accumulated spans where a pixel of the tile has both
+  uint8_t* item_flags;
+  uint32_t* tile_cnt;
+};
+#define SKB_ITEM_PLANE0 1u
+#define SKB_ITEM_SOLID 2u
+#define SKB_ITEM_PLANE1 4u
+
+__device__ __forceinline__ void cover_row8(const TrapRec* __restrict__ pool, uint2 row, int x0, int xmin, int xmax, uint32_t d[8],
+                                           uint32_t a[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
+  uint32_t idx = row.x;
+  for (uint32_t k = 0; k < row.y; k++, idx++) {
+    TrapRec r = pool[idx];
+    if (r.flags & SKB_REC_LINK) {
+      idx = (uint32_t)r.y;
+      r = pool[idx];
+    }
+    int e0, e1;
+    trap_extent(r, &e0, &e1);
+    if (e1 <= x0 || e0 >= x0 + 8) continue;
+    const uint32_t full = r.flags & 0xFF;
+    const bool direct = full == 0xFF && !((r.flags >> 8) & 1);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      int x = x0 + j;
+      uint8_t v;
+      if (x >= xmin && x < xmax && trap_alpha_at(r, x, &v)) {
+        if (direct) d[j] = v; else a[j] += v;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) a[j] = a[j] > 255u ? 255u : a[j];
+}
+
+__global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
+  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (item >= c.n_items) return;
+  const uint32_t op = find_interval(c.item_base, c.n_ops, item);
+  const OpGeom g = c.geom[op];
+  const uint32_t local = item - c.item_base[op];
+  const int tx = g.tx0 + (int)(local % (uint32_t)g.ntx);
+  const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
+  const SurfDesc sd = c.surfs[c.ops[op].surface];
+  const int y = ty * SKB_TILE + (lane >> 1);
+  const int x0 = tx * SKB_TILE + (lane & 1) * 8;
+  uint32_t d[8], a[8];
+  const int xmax = min(g.scan_r, (int)sd.w);
+  const int xmin = max(g.scan_l, 0);
+  if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) {
+    uint2 row = c.rows[c.row_base[op] + (uint32_t)(y - g.ty0 * SKB_TILE)];
+    cover_row8(c.pool, row, x0, xmin, xmax, d, a);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
+  }
+  bool any = false, both = false, solid = true;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    any |= (d[j] | a[j]) != 0;
+    both |= d[j] != 0 && a[j] != 0;
+    solid &= d[j] == 255 && a[j] == 0;
+  }
+  any = __any_sync(0xffffffffu, any);
+  both = __any_sync(0xffffffffu, both);
+  solid = __all_sync(0xffffffffu, solid);
+  uint32_t flags = 0;
+  if (any) {
+    flags = SKB_ITEM_PLANE0;
+    if (solid) {
+      flags |= SKB_ITEM_SOLID;
+    } else {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t v0 = both ? d[j] : (d[j] | a[j]);
+        uint32_t v1 = both ? d[j + 4] : (d[j + 4] | a[j + 4]);
+        lo |= v0 << (8 * j);
+        hi |= v1 << (8 * j);
+      }
+      reinterpret_cast<uint2*>(c.mask0 + (size_t)item * 256)[lane] = make_uint2(lo, hi);
+      if (both) {
+        flags |= SKB_ITEM_PLANE1;
+        lo = hi = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          lo |= a[j] << (8 * j);
+          hi |= a[j + 4] << (8 * j);
+        }
+        reinterpret_cast<uint2*>(c.mask1 + (size_t)item * 256)[lane] = make_uint2(lo, hi);
+      }
+    }
+  }
+  if (lane == 0) {
+    c.item_flags[item] = (uint8_t)flags;
+    if (flags && c.ops[op].kind == SKB_OP_FILL) {
+      uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
+      atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
+    }
+  }
+}
+
+// --------------------------------------------------------------------- stage 5: bin
+__global__ void k_scatter(CoverArgs c, const uint32_t* tile_off, uint32_t* tile_fill, uint2* cmds) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= c.n_items) return;
+  const uint32_t flags = c.item_flags[item];
+  if (!flags) return;
+  const uint32_t op = find_interval(c.item_base, c.n_ops, item);
+  if (c.ops[op].kind != SKB_OP_FILL) return;
+  const OpGeom g = c.geom[op];
+  const uint32_t local = item - c.item_base[op];
+  const int tx = g.tx0 + (int)(local % (uint32_t)g.ntx);
+  const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
+  const SurfDesc sd = c.surfs[c.ops[op].surface];
+  const uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
+  const uint32_t n = (flags & SKB_ITEM_PLANE1) ? 2u : 1u;
+  uint32_t pos = tile_off[tile] + atomicAdd(&tile_fill[tile], n);
+  cmds[pos] = make_uint2(op << 1, item | ((flags & SKB_ITEM_SOLID) ? SKB_CMD_SOLID : 0u));
+  if (n == 2) cmds[pos + 1] = make_uint2((op << 1) | 1u, item);
+}
+
+// -------------------------------------------------------------------- stage 6: fine
+struct FineArgs {
+  const uint32_t* tile_off;
+  const uint2* cmds;
+  uint2* cmds_sorted;  // scratch for tiles whose list does not fit the shared-memory sorter
+  uint32_t tile_begin, tile_end;
+  const SurfDesc* surfs;
+  const uint32_t* surf_tile_base;  // n_surfaces + 1
+  uint32_t n_surfaces;
+  const OpGeom* geom;
+  const skb_dl_op* ops;
+  const skb_dl_paint* paints;
+  const float* stops;
+  const uint8_t* mask0;
+  const uint8_t* mask1;
+};
+#define FINE_WARPS 4
+#define FINE_SORT_CAP 256
+
+__global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
+  __shared__ uint2 s_cmd[FINE_WARPS][FINE_SORT_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tile = a.tile_begin + blockIdx.x * FINE_WARPS + warp;
+  if (tile >= a.tile_end) return;
+  const uint32_t c0 = a.tile_off[tile];
+  const uint32_t n = a.tile_off[tile + 1] - c0;
+  if (n == 0) return;
+  const uint32_t s = find_interval(a.surf_tile_base, a.n_surfaces, tile);
+  const SurfDesc sd = a.surfs[s];
+  const uint32_t local = tile - sd.tile_base;
+  const int tx = (int)(local % sd.tiles_x), ty = (int)(local / sd.tiles_x);
+  const int y = ty * SKB_TILE + (lane >> 1);
+  const int x0 = tx * SKB_TILE + (lane & 1) * 8;
+
+  // order the tile's commands by (op, plane): draws must be composited in draw order
+  const uint2* list;
+  if (n <= FINE_SORT_CAP) {
+    uint32_t N = 32;
+    while (N < n) N <<= 1;
+    for (uint32_t i = lane; i < N; i += 32) s_cmd[warp][i] = i < n ? a.cmds[c0 + i] : make_uint2(0xFFFFFFFFu, 0u);
+    __syncwarp();
+    for (uint32_t k = 2; k <= N; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = lane; i < N; i += 32) {
+          uint32_t ixj = i ^ j;
+          if (ixj > i) {
+            uint2 u = s_cmd[warp][i], v = s_cmd[warp][ixj];
+            bool up = (i & k) == 0;
+            if ((u.x > v.x) == up) {
+              s_cmd[warp][i] = v;
+              s_cmd[warp][ixj] = u;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    list = s_cmd[warp];
+  } else {
+    // rank sort through global scratch (keys are unique): rare, only for very deep tiles
+    for (uint32_t i = lane; i < n; i += 32) {
+      uint2 u = a.cmds[c0 + i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n; j++) rank += a.cmds[c0 + j].x < u.x;
+      a.cmds_sorted[c0 + rank] = u;
+    }
+    __threadfence_block();
+    __syncwarp();
+    list = a.cmds_sorted + c0;
+  }
+
+  uint32_t* prow = reinterpret_cast<uint32_t*>(sd.px + (size_t)y * sd.pitch) + x0;
+  uint4 q0 = reinterpret_cast<uint4*>(prow)[0];
+  uint4 q1 = reinterpret_cast<uint4*>(prow)[1];
+  uint32_t dst[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+
+  for (uint32_t i = 0; i < n; i++) {
+    const uint2 cmd = list[i];
+    const uint32_t op = cmd.x >> 1;
+    const uint32_t pidx = a.ops[op].paint;
+    const uint32_t ptype = a.paints[pidx].type;
+    uint32_t lo, hi;
+    if (cmd.y & SKB_CMD_SOLID) {
+      lo = hi = 0xFFFFFFFFu;
+    } else {
+      const uint8_t* m = ((cmd.x & 1u) ? a.mask1 : a.mask0) + (size_t)(cmd.y & 0x7FFFFFFFu) * 256;
+      uint2 mv = reinterpret_cast<const uint2*>(m)[lane];
+      lo = mv.x;
+      hi = mv.y;
+    }
+    if ((lo | hi) == 0) continue;
+    if (ptype == SKB_PAINT_SOLID) {
+      const uint32_t color = a.geom[op].color;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
+        if (cv) dst[j] = blend_cover(dst[j], color, cv);
+      }
+    } else {
+      const skb_dl_paint pt = a.paints[pidx];
+      const uint32_t galpha = ptype == SKB_PAINT_IMAGE ? (pt.global_alpha & 0xFF) : 0xFFu;
+      SurfaceView img;
+      img.px = nullptr;
+      img.w = img.h = img.pitch = 0;
+      if (ptype == SKB_PAINT_IMAGE) {
+        const SurfDesc is = a.surfs[pt.image_surface];
+        img.px = is.px;
+        img.w = is.w;
+        img.h = is.h;
+        img.pitch = is.pitch;
+      }
+#pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
+        cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
+        if (cv) dst[j] = blend_cover(dst[j], paint_color(pt, a.stops, img, x0 + j, y), cv);
+      }
+    }
+  }
+  reinterpret_cast<uint4*>(prow)[0] = make_uint4(dst[0], dst[1], dst[2], dst[3]);
+  reinterpret_cast<uint4*>(prow)[1] = make_uint4(dst[4], dst[5], dst[6], dst[7]);
+}
+
+// -------------------------------------------------------------------- stage 7: blur
+// SWStackBlur (sw_stack_blur.cc:18-284) as the triangular filter it computes:
+//   sum(x) = SUM_{i=-r..r} (r+1-|i|) * p[clamp(x+i, 0, n-1)],   out = uint8((sum * mul[r]) >> shr[r])
+// With m = r+1, T = prefix sum of the clamp-extended row and U = prefix sum of T:
+//   sum(x) = U[x+m+1] - 2*U[x+1] + U[x-m+1]      (box_m * box_m = triangle)
+// All sums are kept mod 2^32 — the result (< 2^24) is exact.
+struct BlurJob {
+  uint32_t src, dst;  // surface ids
+  int32_t radius;
+};
+
+// Horizontal pass: one CTA per (job, row).  The extended row (n + 2m + 1 samples x 4 channels)
+// lives in shared memory; two block-wide scans produce U.
+__global__ void __launch_bounds__(256) k_blur_h(const BlurJob* jobs, const uint32_t* job_row_base, uint32_t n_jobs,
+                                                const SurfDesc* surfs) {
+  extern __shared__ uint32_t sm[];  // [4][len] then per-thread partials
+  const uint32_t grow = blockIdx.x;
+  const uint32_t job = find_interval(job_row_base, n_jobs, grow);
+  const BlurJob jb = jobs[job];
+  const SurfDesc S = surfs[jb.src], D = surfs[jb.dst];
+  const int y = (int)(grow - job_row_base[job]);
+  const int n = (int)S.w;
+  const uint32_t* srow = reinterpret_cast<const uint32_t*>(S.px + (size_t)y * S.pitch);
+  uint32_t* drow = reinterpret_cast<uint32_t*>(D.px + (size_t)y * D.pitch);
+  int r = jb.radius > 254 ? 254 : jb.radius;
+  if (r <= 1) {
+    for (int x = threadIdx.x; x < n; x += blockDim.x) drow[x] = srow[x];
+    return;
+  }
+  const int m = r + 1;
+  const int len = n + 2 * m + 1;  // extended index j = k - m for k in [0, len): j in [-m, n+m]
+  uint32_t* U = sm;                // U[c*len + k], exclusive double prefix
+  __shared__ uint32_t part[4][256];
+  const int T = blockDim.x;
+  const int chunk = (len + T - 1) / T;
+  const int k0 = min((int)threadIdx.x * chunk, len), k1 = min(k0 + chunk, len);
+  // pass 1: T (exclusive prefix of e) into U[]
+  uint32_t acc[4] = {0, 0, 0, 0};
+  for (int k = k0; k < k1; k++) {
+    int j = k - m;
+    j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
+    uint32_t px = srow[j];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      U[c * len + k] = acc[c];
+      acc[c] += (px >> (8 * c)) & 0xFF;
+    }
+  }
+  for (int pass = 0; pass < 2; pass++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) part[c][threadIdx.x] = acc[c];
+    __syncthreads();
+    // exclusive scan of the per-thread totals (256 values per channel) by warp 0..3, one channel each
+    if (threadIdx.x < 128) {
+      const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      uint32_t carry = 0;
+      for (int base = 0; base < T; base += 32) {
+        uint32_t v = part[c][base + lane];
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        part[c][base + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    uint32_t off[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) off[c] = part[c][threadIdx.x];
+    __syncthreads();
+    if (pass == 0) {
+      // finalise T, then turn it into U (exclusive prefix of T) chunk-locally
+#pragma unroll
+      for (int c = 0; c < 4; c++) acc[c] = 0;
+      for (int k = k0; k < k1; k++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t tv = U[c * len + k] + off[c];
+          U[c * len + k] = acc[c];
+          acc[c] += tv;
+        }
+      }
+    } else {
+      for (int k = k0; k < k1; k++) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) U[c * len + k] += off[c];
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t mul;
+  int shr;
+  blur_mul_shr(r, &mul, &shr);
+  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+    // extended index j maps to k = j + m;  U[j] here means prefix over samples < j
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t* Uc = U + c * len;
+      uint32_t sum = Uc[x + m + 1 + m] - 2u * Uc[x + 1 + m] + Uc[x - m + 1 + m];
+      out |= (uint32_t)(uint8_t)(((uint64_t)sum * mul) >> shr) << (8 * c);
+    }
+    drow[x] = out;
+  }
+}
+
+// Vertical pass, in place on the destination: one thread per column, three running (T, U) pairs
+// at rows y+m+1, y+1, y-m+1.  Reproduces the reference's seeding of out_sum.b/.a from the G channel
+// (sw_stack_blur.cc:178-179): bytes 0 and 3 drift by -y*(r+1)*(g0 - b0|a0) in 64-bit arithmetic.
+// Reads of the column lead/lag the writes by >= 1 row only through values already consumed, so the
+// pass needs a separate source: `tmp` holds the H-blurred rows (the job's dst is written last).
+__global__ void __launch_bounds__(128) k_blur_v(const BlurJob* jobs, const uint32_t* job_col_base, uint32_t n_jobs,
+                                                const SurfDesc* surfs, const uint8_t* const* tmp_px) {
+  const uint32_t gcol = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gcol >= job_col_base[n_jobs]) return;
+  const uint32_t job = find_interval(job_col_base, n_jobs, gcol);
+  const BlurJob jb = jobs[job];
+  const SurfDesc D = surfs[jb.dst];
+  int r = jb.radius > 254 ? 254 : jb.radius;
+  if (r <= 1) return;  // the horizontal kernel already copied
+  const int x = (int)(gcol - job_col_base[job]);
+  const int h = (int)D.h;
+  const int m = r + 1;
+  const uint8_t* src = tmp_px[job];
+  const size_t pitch = D.pitch;
+  auto sample = [&](int j) -> uint32_t {
+    j = j < 0 ? 0 : (j > h - 1 ? h - 1 : j);
+    return *reinterpret_cast<const uint32_t*>(src + (size_t)j * pitch + (size_t)x * 4);
+  };
+  // running prefix pairs: P(k) = (T[k], U[k]) with T[k] = sum_{j<k} e[j], U[k] = sum_{j<k} T[j], extended index from -m
+  uint32_t Tl[4] = {0, 0, 0, 0}, Ul[4] = {0, 0, 0, 0};  // at index y+m+1
+  uint32_t Tm[4] = {0, 0, 0, 0}, Um[4] = {0, 0, 0, 0};  // at index y+1
+  uint32_t Tg[4] = {0, 0, 0, 0}, Ug[4] = {0, 0, 0, 0};  // at index y-m+1
+  auto advance = [&](uint32_t* Tt, uint32_t* Uu, int j) {
+    uint32_t px = sample(j);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      Uu[c] += Tt[c];
+      Tt[c] += (px >> (8 * c)) & 0xFF;
+    }
+  };
+  // all three start at extended index -m (T = U = 0); bring them to y=0 positions
+  for (int j = -m; j < m + 1; j++) advance(Tl, Ul, j);      // -> index m+1
+  for (int j = -m; j < 1; j++) advance(Tm, Um, j);          // -> index 1
+  for (int j = -m; j < -m + 1; j++) advance(Tg, Ug, j);     // -> index -m+1
+  const uint32_t p0 = sample(0);
+  const uint64_t g0 = (p0 >> 8) & 0xFF, b0 = p0 & 0xFF, a0 = (p0 >> 24) & 0xFF;
+  const uint64_t drift0 = (uint64_t)m * (g0 - b0), drift3 = (uint64_t)m * (g0 - a0);
+  uint32_t mul;
+  int shr;
+  blur_mul_shr(r, &mul, &shr);
+  uint8_t* dcol = D.px + (size_t)x * 4;
+  for (int y = 0; y < h; y++) {
+    uint32_t out = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      uint64_t sum = (uint64_t)(uint32_t)(Ul[c] - 2u * Um[c] + Ug[c]);
+      if (c == 0) sum -= (uint64_t)y * drift0;
+      if (c == 3) sum -= (uint64_t)y * drift3;
+      out |= (uint32_t)(uint8_t)((sum * (uint64_t)mul) >> shr) << (8 * c);
+    }
+    *reinterpret_cast<uint32_t*>(dcol + (size_t)y * pitch) = out;
+    advance(Tl, Ul, y + m + 1);
+    advance(Tm, Um, y + 1);
+    advance(Tg, Ug, y - m + 1);
+  }
+}
+
+// ----------------------------------------------------------------------- debug tap
+__global__ void k_read_coverage(CoverArgs c, uint32_t op, int x, int y, uint32_t w, uint32_t h, uint8_t* direct, uint8_t* accum) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  int px = x + (int)(i % w), py = y + (int)(i / w);
+  uint8_t dv = 0, av = 0;
+  const OpGeom g = c.geom[op];
+  if (!g.empty && g.ntx > 0 && px >= 0 && py >= 0) {
+    int tx = px / SKB_TILE, ty = py / SKB_TILE;
+    if (tx >= g.tx0 && tx < g.tx0 + g.ntx && ty >= g.ty0 && ty < g.ty0 + g.nty) {
+      uint32_t item = c.item_base[op] + (uint32_t)((ty - g.ty0) * g.ntx + (tx - g.tx0));
+      uint32_t f = c.item_flags[item];
+      int lx = px % SKB_TILE, ly = py % SKB_TILE;
+      if (f & SKB_ITEM_SOLID) {
+        dv = 255;
+      } else if (f & SKB_ITEM_PLANE0) {
+        // masks do not say which span kind produced a lone value; report it as `direct`
+        dv = c.mask0[(size_t)item * 256 + ly * 16 + lx];
+        if (f & SKB_ITEM_PLANE1) av = c.mask1[(size_t)item * 256 + ly * 16 + lx];
+      }
+    }
+  }
+  direct[i] = dv;
+  accum[i] = av;
+}
+
+// =========================================================================== host side
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace skb
+
+using namespace skb;
+
+struct skb_device_s {
+  int ordinal = 0;
+  int sm_count = 0;
+};
+
+struct skb_surface_s {
+  skb_device dev = nullptr;
+  uint32_t w = 0, h = 0;
+  uint32_t band_y0 = 0, band_y1 = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10] = {};
+  // canvas pixels (persistent)
+  uint8_t* canvas = nullptr;
+  uint32_t pitch = 0, tiles_x = 0, tiles_y = 0;
+  // frame
+  std::vector<uint8_t> host_dl;
+  bool have_frame = false;
+  bool flushed = false;
+  skb_frame_stats stats = {};
+  // device buffers (grow-only)
+  Buf dl, geom, seg_op, prim_cnt, edges, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
+      tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
+      blur_tmp;
+  // host mirrors kept for the debug tap
+  uint32_t n_ops = 0, n_items = 0;
+  std::vector<SurfDesc> h_surfs;
+};
+
+namespace skb {
+
+static skb_result buf_reserve(Buf& b, size_t bytes) {
+  if (bytes <= b.cap) return SKB_SUCCESS;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(&b.p, want);
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    return SKB_ERROR_OUT_OF_MEMORY;
+  }
+  b.cap = want;
+  return SKB_SUCCESS;
+}
+static void buf_free(Buf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+#define SKB_TRY(expr)                     \
+  do {                                    \
+    skb_result _r = (expr);               \
+    if (_r != SKB_SUCCESS) return _r;     \
+  } while (0)
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// exclusive scan of data[0..n] (n+1 entries, data[n] must be 0 on entry) -> data[n] = total
+static skb_result scan_exclusive(skb_surface s, uint32_t* data, uint32_t n_plus_1, uint32_t* launches) {
+  // levels of block sums live in scan_tmp
+  std::vector<uint32_t> sizes;
+  uint32_t n = n_plus_1;
+  size_t total = 0;
+  while (n > SCAN_BLOCK) {
+    n = cdiv(n, SCAN_BLOCK);
+    sizes.push_back(n);
+    total += n;
+  }
+  SKB_TRY(buf_reserve(s->scan_tmp, (total + 1) * 4));
+  std::vector<uint32_t*> lv;
+  uint32_t* base = (uint32_t*)s->scan_tmp.p;
+  for (uint32_t sz : sizes) {
+    lv.push_back(base);
+    base += sz;
+  }
+  // up-sweep
+  uint32_t* cur = data;
+  n = n_plus_1;
+  for (size_t l = 0; l <= sizes.size(); l++) {
+    uint32_t blocks = cdiv(n, SCAN_BLOCK);
+    k_scan_block<<<blocks, SCAN_THREADS, 0, s->stream>>>(cur, n, l < sizes.size() ? lv[l] : nullptr);
+    (*launches)++;
+    if (l < sizes.size()) {
+      cur = lv[l];
+      n = sizes[l];
+    }
+  }
+  // down-sweep
+  for (size_t l = sizes.size(); l-- > 0;) {
+    uint32_t* child = l == 0 ? data : lv[l - 1];
+    uint32_t child_n = l == 0 ? n_plus_1 : sizes[l - 1];
+    k_scan_add<<<cdiv(child_n, SCAN_BLOCK), SCAN_THREADS, 0, s->stream>>>(child, child_n, lv[l]);
+    (*launches)++;
+  }
+  SKB_CUDA(cudaGetLastError());
+  return SKB_SUCCESS;
+}
+
+static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
+  if (bytes < sizeof(skb_dl_header)) return SKB_ERROR_BAD_DISPLAY_LIST;
+  skb_dl_header h;
+  memcpy(&h, dl, sizeof(h));
+  if (h.magic != SKB_DL_MAGIC || h.version != SKB_DL_VERSION || h.total_bytes > bytes) {
+    set_error("display list: bad magic/version/size");
+    return SKB_ERROR_BAD_DISPLAY_LIST;
+  }
+  auto in_range = [&](uint32_t off, uint64_t n, size_t sz) { return (uint64_t)off + n * sz <= h.total_bytes && off % 16 == 0; };
+  if (!in_range(h.off_surfaces, h.n_surfaces, sizeof(skb_dl_surface)) || !in_range(h.off_ops, h.n_ops, sizeof(skb_dl_op)) ||
+      !in_range(h.off_paths, h.n_paths, sizeof(skb_dl_path)) || !in_range(h.off_segs, h.n_segs, sizeof(skb_dl_seg)) ||
+      !in_range(h.off_paints, h.n_paints, sizeof(skb_dl_paint)) || !in_range(h.off_stops, h.n_stop_floats, 4) ||
+      h.n_surfaces == 0) {
+    set_error("display list: section out of range");
+    return SKB_ERROR_BAD_DISPLAY_LIST;
+  }
+  const skb_dl_op* ops = (const skb_dl_op*)(dl + h.off_ops);
+  const skb_dl_path* paths = (const skb_dl_path*)(dl + h.off_paths);
+  const skb_dl_paint* paints = (const skb_dl_paint*)(dl + h.off_paints);
+  for (uint32_t i = 0; i < h.n_ops; i++) {
+    const skb_dl_op& o = ops[i];
+    if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+      if (o.path >= h.n_paths || o.surface >= h.n_surfaces || (o.kind == SKB_OP_FILL && o.paint >= h.n_paints) ||
+          o.clip_in > h.n_clip_states) {
+        set_error("display list: op index out of range");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      const skb_dl_path& p = paths[o.path];
+      if ((uint64_t)p.seg_off + p.n_segs > h.n_segs) {
+        set_error("display list: path segments out of range");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      if (o.kind == SKB_OP_FILL) {
+        const skb_dl_paint& pt = paints[o.paint];
+        if (pt.type > SKB_PAINT_IMAGE || (pt.type == SKB_PAINT_IMAGE && pt.image_surface >= h.n_surfaces) ||
+            (pt.type >= SKB_PAINT_LINEAR && pt.type <= SKB_PAINT_SWEEP &&
+             ((uint64_t)pt.stop_off + 5ull * pt.n_colors > h.n_stop_floats || pt.n_colors < 1))) {
+          set_error("display list: bad paint");
+          return SKB_ERROR_BAD_DISPLAY_LIST;
+        }
+      }
+      if (o.kind == SKB_OP_CLIP || o.clip_in != 0) {
+        set_error("path clips (Canvas::ClipPath) are not implemented on the device yet");
+        return SKB_ERROR_UNSUPPORTED;
+      }
+    } else if (o.kind == SKB_OP_BLUR) {
+      if (o.surface >= h.n_surfaces || o.aux >= h.n_surfaces || o.surface == 0 || o.aux == 0) {
+        set_error("display list: blur surface out of range");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+    } else {
+      set_error("display list: unknown op kind");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
+  }
+  return SKB_SUCCESS;
+}
+
+static skb_result run_frame(skb_surface s) {
+  const uint8_t* dl = s->host_dl.data();
+  skb_dl_header h;
+  memcpy(&h, dl, sizeof(h));
+  const skb_dl_surface* hs = (const skb_dl_surface*)(dl + h.off_surfaces);
+  const skb_dl_op* hops = (const skb_dl_op*)(dl + h.off_ops);
+  cudaStream_t st = s->stream;
+  skb_frame_stats& S = s->stats;
+  memset(&S, 0, sizeof(S));
+  S.n_ops = h.n_ops;
+  S.n_segs = h.n_segs;
+  uint32_t launches = 0;
+
+  if (hs[0].width != s->w || hs[0].height != s->h) {
+    set_error("display list canvas size differs from the surface");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+
+  // ---- surfaces: canvas + temporaries (zeroed like Bitmap's calloc, src/io/pixmap.cc:77)
+  std::vector<SurfDesc>& surfs = s->h_surfs;
+  surfs.assign(h.n_surfaces, SurfDesc());
+  std::vector<uint32_t> tile_base(h.n_surfaces + 1, 0);
+  size_t temp_bytes = 0;
+  std::vector<size_t> temp_off(h.n_surfaces, 0);
+  for (uint32_t i = 0; i < h.n_surfaces; i++) {
+    SurfDesc& d = surfs[i];
+    d.w = hs[i].width;
+    d.h = hs[i].height;
+    d.tiles_x = cdiv(d.w, SKB_TILE);
+    d.tiles_y = cdiv(d.h, SKB_TILE);
+    d.pitch = d.tiles_x * SKB_TILE * 4;
+    d.tile_base = tile_base[i];
+    d.row0 = 0;
+    d.row1 = d.h;
+    tile_base[i + 1] = tile_base[i] + d.tiles_x * d.tiles_y;
+    if (i > 0) {
+      temp_off[i] = temp_bytes;
+      temp_bytes += (size_t)d.pitch * d.tiles_y * SKB_TILE;
+    }
+  }
+  if (s->band_y1 > 0) {
+    surfs[0].row0 = s->band_y0;
+    surfs[0].row1 = s->band_y1 < s->h ? s->band_y1 : s->h;
+  }
+  SKB_TRY(buf_reserve(s->temp_px, temp_bytes + 256));
+  surfs[0].px = s->canvas;
+  for (uint32_t i = 1; i < h.n_surfaces; i++) surfs[i].px = (uint8_t*)s->temp_px.p + temp_off[i];
+  if (temp_bytes) SKB_CUDA(cudaMemsetAsync(s->temp_px.p, 0, temp_bytes, st));
+  const uint32_t n_tiles = tile_base[h.n_surfaces];
+  S.n_tiles = n_tiles;
+  SKB_TRY(buf_reserve(s->surfs, surfs.size() * sizeof(SurfDesc)));
+  SKB_TRY(buf_reserve(s->surf_tile_base, tile_base.size() * 4));
+  SKB_CUDA(cudaMemcpyAsync(s->surfs.p, surfs.data(), surfs.size() * sizeof(SurfDesc), cudaMemcpyHostToDevice, st));
+  SKB_CUDA(cudaMemcpyAsync(s->surf_tile_base.p, tile_base.data(), tile_base.size() * 4, cudaMemcpyHostToDevice, st));
+
+  FrameTables t;
+  const uint8_t* ddl = (const uint8_t*)s->dl.p;
+  t.ops = (const skb_dl_op*)(ddl + h.off_ops);
+  t.paths = (const skb_dl_path*)(ddl + h.off_paths);
+  t.segs = (const skb_dl_seg*)(ddl + h.off_segs);
+  t.paints = (const skb_dl_paint*)(ddl + h.off_paints);
+  t.stops = (const float*)(ddl + h.off_stops);
+  t.n_ops = h.n_ops;
+  t.n_segs = h.n_segs;
+  const uint32_t n_ops = h.n_ops, n_segs = h.n_segs;
+  s->n_ops = n_ops;
+  if (n_ops == 0) {
+    s->flushed = true;
+    return SKB_SUCCESS;
+  }
+
+  SKB_TRY(buf_reserve(s->geom, (size_t)n_ops * sizeof(OpGeom)));
+  SKB_TRY(buf_reserve(s->seg_op, (size_t)(n_segs + 1) * 4));
+  SKB_TRY(buf_reserve(s->prim_cnt, (size_t)(n_segs + 1) * 4));
+  SKB_TRY(buf_reserve(s->row_cnt, (size_t)(n_ops + 1) * 4));
+  SKB_TRY(buf_reserve(s->item_cnt, (size_t)(n_ops + 1) * 4));
+  SKB_TRY(buf_reserve(s->counters, 64));
+  OpGeom* geom = (OpGeom*)s->geom.p;
+  uint32_t* seg_op = (uint32_t*)s->seg_op.p;
+  uint32_t* prim_off = (uint32_t*)s->prim_cnt.p;
+  uint32_t* row_base = (uint32_t*)s->row_cnt.p;
+  uint32_t* item_base = (uint32_t*)s->item_cnt.p;
+  uint32_t* counters = (uint32_t*)s->counters.p;  // [0] pool_next, [1] overflow
+
+  cudaEventRecord(s->ev[0], st);
+  // ---- stage 1: flatten
+  k_op_init<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, seg_op);
+  launches++;
+  uint32_t n_prims = 0;
+  if (n_segs) {
+    SKB_CUDA(cudaMemsetAsync(prim_off + n_segs, 0, 4, st));
+    k_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(t, prim_off);
+    launches++;
+    SKB_TRY(scan_exclusive(s, prim_off, n_segs + 1, &launches));
+    SKB_CUDA(cudaMemcpyAsync(&n_prims, prim_off + n_segs, 4, cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+  }
+  S.n_prims = n_prims;
+  const size_t n_slots = (size_t)2 * n_prims + (size_t)2 * n_ops + 2;
+  S.n_edges_slots = (uint32_t)n_slots;
+  SKB_TRY(buf_reserve(s->edges, n_slots * sizeof(Edge)));
+  SKB_TRY(buf_reserve(s->ord, n_slots * 4));
+  Edge* edges = (Edge*)s->edges.p;
+
+  uint64_t n_rows = 0, n_items = 0;
+  uint32_t pool_cap = 0;
+  for (int attempt = 0;; attempt++) {
+    if (n_prims) {
+      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges);
+      launches++;
+    }
+    if (attempt == 0) {
+      cudaEventRecord(s->ev[1], st);
+      // ---- stage 2: setup
+      SKB_CUDA(cudaMemsetAsync(row_base + n_ops, 0, 4, st));
+      SKB_CUDA(cudaMemsetAsync(item_base + n_ops, 0, 4, st));
+      k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base);
+      launches++;
+      SKB_TRY(scan_exclusive(s, row_base, n_ops + 1, &launches));
+      SKB_TRY(scan_exclusive(s, item_base, n_ops + 1, &launches));
+      uint32_t tot[2] = {0, 0};
+      SKB_CUDA(cudaMemcpyAsync(&tot[0], row_base + n_ops, 4, cudaMemcpyDeviceToHost, st));
+      SKB_CUDA(cudaMemcpyAsync(&tot[1], item_base + n_ops, 4, cudaMemcpyDeviceToHost, st));
+      SKB_CUDA(cudaStreamSynchronize(st));
+      n_rows = tot[0];
+      n_items = tot[1];
+      S.n_rows = n_rows;
+      S.n_items = n_items;
+      s->n_items = (uint32_t)n_items;
+      uint64_t want = 2 * n_rows + (uint64_t)SKB_CHUNK * 2 * n_ops + 4096;
+      if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
+      pool_cap = (uint32_t)want;
+      SKB_TRY(buf_reserve(s->rows, (n_rows + 1) * sizeof(uint2)));
+      SKB_TRY(buf_reserve(s->mask0, (n_items + 1) * 256));
+      SKB_TRY(buf_reserve(s->mask1, (n_items + 1) * 256));
+      SKB_TRY(buf_reserve(s->item_flags, n_items + 16));
+      SKB_TRY(buf_reserve(s->tile_cnt, (size_t)(n_tiles + 1) * 4));
+      SKB_TRY(buf_reserve(s->tile_fill, (size_t)(n_tiles + 1) * 4));
+      cudaEventRecord(s->ev[2], st);
+    }
+    SKB_TRY(buf_reserve(s->pool, (size_t)pool_cap * sizeof(TrapRec)));
+    pool_cap = (uint32_t)(s->pool.cap / sizeof(TrapRec));
+    S.pool_capacity = pool_cap;
+    // ---- stage 3: walk
+    SKB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
+    if (n_rows) SKB_CUDA(cudaMemsetAsync(s->rows.p, 0, n_rows * sizeof(uint2), st));
+    k_walk<<<cdiv(n_ops, 64), 64, 0, st>>>(t, geom, row_base, edges, (int32_t*)s->ord.p, (TrapRec*)s->pool.p, counters, pool_cap,
+                                           counters + 1, (uint2*)s->rows.p);
+    launches++;
+    uint32_t hc[2];
+    SKB_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+    S.n_records = hc[0];
+    if (!hc[1]) break;
+    if (attempt >= 6 || pool_cap >= 0x7FFFFFF0u) {
+      set_error("trapezoid record pool exhausted");
+      return SKB_ERROR_OUT_OF_MEMORY;
+    }
+    S.n_retries++;
+    uint64_t bigger = (uint64_t)pool_cap * 2;
+    pool_cap = bigger > 0x7FFFFFF0ull ? 0x7FFFFFF0u : (uint32_t)bigger;
+    // the sweep mutates the edges: rebuild them and walk again
+  }
+  cudaEventRecord(s->ev[3], st);
+
+  // ---- stage 4: coverage
+  CoverArgs ca;
+  ca.geom = geom;
+  ca.item_base = item_base;
+  ca.row_base = row_base;
+  ca.n_ops = n_ops;
+  ca.n_items = (uint32_t)n_items;
+  ca.ops = t.ops;
+  ca.surfs = (const SurfDesc*)s->surfs.p;
+  ca.pool = (const TrapRec*)s->pool.p;
+  ca.rows = (const uint2*)s->rows.p;
+  ca.mask0 = (uint8_t*)s->mask0.p;
+  ca.mask1 = (uint8_t*)s->mask1.p;
+  ca.item_flags = (uint8_t*)s->item_flags.p;
+  ca.tile_cnt = (uint32_t*)s->tile_cnt.p;
+  SKB_CUDA(cudaMemsetAsync(s->tile_cnt.p, 0, (size_t)(n_tiles + 1) * 4, st));
+  SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
+  if (n_items) {
+    k_cover<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
+    launches++;
+  }
+  cudaEventRecord(s->ev[4], st);
+  // ---- stage 5: bin
+  SKB_TRY(scan_exclusive(s, (uint32_t*)s->tile_cnt.p, n_tiles + 1, &launches));
+  uint32_t n_cmds = 0;
+  SKB_CUDA(cudaMemcpyAsync(&n_cmds, (uint32_t*)s->tile_cnt.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+  SKB_CUDA(cudaStreamSynchronize(st));
+  S.n_cmds = n_cmds;
+  SKB_TRY(buf_reserve(s->cmds, ((size_t)n_cmds + 1) * sizeof(uint2)));
+  SKB_TRY(buf_reserve(s->cmds_sorted, ((size_t)n_cmds + 1) * sizeof(uint2)));
+  if (n_items) {
+    k_scatter<<<cdiv(n_items, 256), 256, 0, st>>>(ca, (const uint32_t*)s->tile_cnt.p, (uint32_t*)s->tile_fill.p, (uint2*)s->cmds.p);
+    launches++;
+  }
+  cudaEventRecord(s->ev[5], st);
+
+  // ---- stages 6 + 7: fine pass over temporaries, blur, fine pass over the canvas
+  FineArgs fa;
+  fa.tile_off = (const uint32_t*)s->tile_cnt.p;
+  fa.cmds = (const uint2*)s->cmds.p;
+  fa.cmds_sorted = (uint2*)s->cmds_sorted.p;
+  fa.surfs = (const SurfDesc*)s->surfs.p;
+  fa.surf_tile_base = (const uint32_t*)s->surf_tile_base.p;
+  fa.n_surfaces = h.n_surfaces;
+  fa.geom = geom;
+  fa.ops = t.ops;
+  fa.paints = t.paints;
+  fa.stops = t.stops;
+  fa.mask0 = ca.mask0;
+  fa.mask1 = ca.mask1;
+  float ms_fine_tmp = 0;
+  (void)ms_fine_tmp;
+  if (h.n_surfaces > 1) {
+    fa.tile_begin = tile_base[1];
+    fa.tile_end = n_tiles;
+    if (fa.tile_end > fa.tile_begin) {
+      k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
+      launches++;
+    }
+  }
+  cudaEventRecord(s->ev[6], st);
+  // blur jobs
+  std::vector<BlurJob> jobs;
+  for (uint32_t i = 0; i < n_ops; i++) {
+    if (hops[i].kind == SKB_OP_BLUR) {
+      BlurJob j;
+      j.src = hops[i].aux;
+      j.dst = hops[i].surface;
+      j.radius = (int32_t)hops[i].clip_bounds[0];
+      if (surfs[j.src].w != surfs[j.dst].w || surfs[j.src].h != surfs[j.dst].h) {
+        set_error("blur: source and destination surfaces differ in size");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      jobs.push_back(j);
+    }
+  }
+  if (!jobs.empty()) {
+    const uint32_t nj = (uint32_t)jobs.size();
+    std::vector<uint32_t> rowb(nj + 1, 0), colb(nj + 1, 0);
+    std::vector<const uint8_t*> tmp_ptrs(nj);
+    size_t max_len = 0, tmp_bytes = 0;
+    std::vector<size_t> tmp_off(nj);
+    for (uint32_t i = 0; i < nj; i++) {
+      const SurfDesc& d = surfs[jobs[i].dst];
+      rowb[i + 1] = rowb[i] + d.h;
+      colb[i + 1] = colb[i] + d.w;
+      int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
+      if (r > 1) max_len = std::max(max_len, (size_t)d.w + 2 * (size_t)(r + 1) + 1);
+      tmp_off[i] = tmp_bytes;
+      tmp_bytes += (size_t)d.pitch * d.tiles_y * SKB_TILE;
+    }
+    const size_t smem = max_len * 16;
+    if (smem > 200 * 1024) {
+      set_error("blur: surface too wide for the shared-memory row scan");
+      return SKB_ERROR_UNSUPPORTED;
+    }
+    // H pass writes into a scratch copy of each destination, V pass reads it and writes the destination
+    SKB_TRY(buf_reserve(s->blur_tmp, tmp_bytes + 256));
+    std::vector<SurfDesc> hsurf2 = surfs;  // descriptors with dst redirected to scratch for the H pass
+    SKB_TRY(buf_reserve(s->blur_jobs, nj * sizeof(BlurJob)));
+    SKB_TRY(buf_reserve(s->blur_rows, (nj + 1) * 4));
+    SKB_TRY(buf_reserve(s->blur_cols, (nj + 1) * 4));
+    SKB_TRY(buf_reserve(s->blur_tmp_ptrs, nj * sizeof(void*)));
+    for (uint32_t i = 0; i < nj; i++) tmp_ptrs[i] = (const uint8_t*)s->blur_tmp.p + tmp_off[i];
+    // the H kernel addresses its destination through SurfDesc: give it a table where dst.px = scratch
+    std::vector<SurfDesc> htab = surfs;
+    for (uint32_t i = 0; i < nj; i++) htab[jobs[i].dst].px = (uint8_t*)tmp_ptrs[i];
+    Buf& htab_buf = s->scan_tmp;  // reuse: scans are done
+    SKB_TRY(buf_reserve(htab_buf, htab.size() * sizeof(SurfDesc)));
+    SKB_CUDA(cudaMemcpyAsync(htab_buf.p, htab.data(), htab.size() * sizeof(SurfDesc), cudaMemcpyHostToDevice, st));
+    SKB_CUDA(cudaMemcpyAsync(s->blur_jobs.p, jobs.data(), nj * sizeof(BlurJob), cudaMemcpyHostToDevice, st));
+    SKB_CUDA(cudaMemcpyAsync(s->blur_rows.p, rowb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
+    SKB_CUDA(cudaMemcpyAsync(s->blur_cols.p, colb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
+    SKB_CUDA(cudaMemcpyAsync(s->blur_tmp_ptrs.p, tmp_ptrs.data(), nj * sizeof(void*), cudaMemcpyHostToDevice, st));
+    if (smem > 48 * 1024) SKB_CUDA(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_blur_h<<<rowb[nj], 256, smem, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj,
+                                           (const SurfDesc*)htab_buf.p);
+    launches++;
+    // radius <= 1: the H kernel copied src into scratch; finish with a plain copy into dst
+    for (uint32_t i = 0; i < nj; i++) {
+      int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
+      if (r <= 1) {
+        const SurfDesc& d = surfs[jobs[i].dst];
+        SKB_CUDA(cudaMemcpyAsync(d.px, tmp_ptrs[i], (size_t)d.pitch * d.h, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    k_blur_v<<<cdiv(colb[nj], 128), 128, 0, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_cols.p, nj,
+                                                  (const SurfDesc*)s->surfs.p, (const uint8_t* const*)s->blur_tmp_ptrs.p);
+    launches++;
+  }
+  cudaEventRecord(s->ev[7], st);
+  {
+    // canvas tiles of this device's band
+    uint32_t ty0 = surfs[0].row0 / SKB_TILE, ty1 = cdiv(surfs[0].row1, SKB_TILE);
+    fa.tile_begin = ty0 * surfs[0].tiles_x;
+    fa.tile_end = ty1 * surfs[0].tiles_x;
+    if (fa.tile_end > fa.tile_begin) {
+      k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
+      launches++;
+    }
+  }
+  cudaEventRecord(s->ev[8], st);
+  SKB_CUDA(cudaGetLastError());
+  S.n_launches = launches;
+  // algorithmic bytes: fine = canvas band load+store + 8 B/command + 256 B/mask command;
+  // coverage = 32 B/record in + 256 B/non-empty mask out
+  uint64_t band_px = (uint64_t)(surfs[0].row1 - surfs[0].row0) * s->w;
+  S.bytes_fine = band_px * 8 + (uint64_t)n_cmds * (8 + 256);
+  S.bytes_cover = S.n_records * 32 + (uint64_t)n_cmds * 256;
+  s->flushed = true;
+  return SKB_SUCCESS;
+}
+
+}  // namespace skb
+
+// ================================================================================ C ABI
+extern "C" {
+
+const char* skb_get_last_error_string(void) { return g_last_error.c_str(); }
+const char* skb_version_string(void) { return "skity-b200 0.1 (sm_100a)"; }
+
+skb_result skb_device_create(int ordinal, skb_device* out) {
+  if (!out) return SKB_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this backend has no CPU fallback)");
+    return SKB_ERROR_NO_DEVICE;
+  }
+  if (ordinal < 0 || ordinal >= count) {
+    set_error("device ordinal out of range");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+  SKB_CUDA(cudaSetDevice(ordinal));
+  cudaDeviceProp prop;
+  SKB_CUDA(cudaGetDeviceProperties(&prop, ordinal));
+  if (prop.major < 10) {
+    set_error(std::string("device ") + prop.name + " is not sm_100-class; kernels are built for sm_100a only");
+    return SKB_ERROR_NO_DEVICE;
+  }
+  skb_device d = new skb_device_s();
+  d->ordinal = ordinal;
+  d->sm_count = prop.multiProcessorCount;
+  *out = d;
+  return SKB_SUCCESS;
+}
+
+void skb_device_destroy(skb_device d) { delete d; }
+
+skb_result skb_device_sm_count(skb_device d, int* out) {
+  if (!d || !out) return SKB_ERROR_INVALID_ARGUMENT;
+  *out = d->sm_count;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_create(skb_device d, uint32_t w, uint32_t h, skb_surface* out) {
+  if (!d || !out || w == 0 || h == 0 || w > 65535 * 16 || h > 65535 * 16) return SKB_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  SKB_CUDA(cudaSetDevice(d->ordinal));
+  skb_surface s = new skb_surface_s();
+  s->dev = d;
+  s->w = w;
+  s->h = h;
+  s->tiles_x = cdiv(w, SKB_TILE);
+  s->tiles_y = cdiv(h, SKB_TILE);
+  s->pitch = s->tiles_x * SKB_TILE * 4;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&s->canvas, (size_t)s->pitch * s->tiles_y * SKB_TILE);
+  if (e == cudaSuccess) e = cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream);
+  for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+  if (e != cudaSuccess) {
+    set_error(std::string("surface create: ") + cudaGetErrorString(e));
+    skb_surface_destroy(s);
+    return e == cudaErrorMemoryAllocation ? SKB_ERROR_OUT_OF_MEMORY : SKB_ERROR_CUDA;
+  }
+  *out = s;
+  return SKB_SUCCESS;
+}
+
+void skb_surface_destroy(skb_surface s) {
+  if (!s) return;
+  cudaSetDevice(s->dev->ordinal);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
+                 &s->counters, &s->mask0, &s->mask1, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
+                 &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
+                 &s->blur_tmp_ptrs, &s->blur_tmp};
+  for (Buf* b : bufs) buf_free(*b);
+  if (s->canvas) cudaFree(s->canvas);
+  for (int i = 0; i < 10; i++)
+    if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+skb_result skb_surface_set_band(skb_surface s, uint32_t y0, uint32_t y1) {
+  if (!s) return SKB_ERROR_INVALID_ARGUMENT;
+  if (y1 == 0) {
+    s->band_y0 = s->band_y1 = 0;
+    return SKB_SUCCESS;
+  }
+  if (y0 >= y1 || y0 % SKB_TILE != 0 || (y1 % SKB_TILE != 0 && y1 < s->h)) {
+    set_error("band rows must be multiples of 16");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+  s->band_y0 = y0;
+  s->band_y1 = y1;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_frame_begin(skb_surface s, int clear) {
+  if (!s) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  if (clear) SKB_CUDA(cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream));
+  s->have_frame = false;
+  s->flushed = false;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
+  if (!s || !dl) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_TRY(validate_dl((const uint8_t*)dl, bytes));
+  skb_dl_header h;
+  memcpy(&h, dl, sizeof(h));
+  // the header tables (surfaces, ops) are also read on the host while launching
+  s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_paths);
+  SKB_TRY(buf_reserve(s->dl, h.total_bytes));
+  SKB_CUDA(cudaMemcpyAsync(s->dl.p, dl, h.total_bytes, cudaMemcpyHostToDevice, s->stream));
+  s->have_frame = true;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_frame_flush(skb_surface s) {
+  if (!s) return SKB_ERROR_INVALID_ARGUMENT;
+  if (!s->have_frame) {
+    set_error("skb_frame_flush without skb_frame_encode");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  return run_frame(s);
+}
+
+skb_result skb_surface_sync(skb_surface s) {
+  if (!s) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_read_pixels(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst, size_t stride) {
+  if (!s || !dst || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
+                             cudaMemcpyDeviceToHost, s->stream));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_write_pixels(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, const void* src,
+                                    size_t stride) {
+  if (!s || !src || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaMemcpy2DAsync(s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, src, stride, (size_t)w * 4, h,
+                             cudaMemcpyHostToDevice, s->stream));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_device_ptr(skb_surface s, void** out_ptr, size_t* out_pitch) {
+  if (!s || !out_ptr) return SKB_ERROR_INVALID_ARGUMENT;
+  *out_ptr = s->canvas;
+  if (out_pitch) *out_pitch = s->pitch;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_stream(skb_surface s, void** out_stream) {
+  if (!s || !out_stream) return SKB_ERROR_INVALID_ARGUMENT;
+  *out_stream = (void*)s->stream;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_frame_get_stats(skb_surface s, skb_frame_stats* out) {
+  if (!s || !out) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  if (s->flushed && s->n_ops) {
+    float ms = 0;
+    // ev: 0 start, 1 after flatten, 2 after setup, 3 after walk, 4 after cover, 5 after bin, 6 after fine(temps),
+    //     7 after blur, 8 after fine(canvas)
+    static const int stage_of[8] = {0, 1, 2, 3, 4, 5, 6, 5};
+    for (int i = 0; i < 8; i++) s->stats.ms_stage[i] = 0;
+    for (int i = 0; i < 8; i++) {
+      if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->stats.ms_stage[stage_of[i]] += ms;
+    }
+    if (cudaEventElapsedTime(&ms, s->ev[0], s->ev[8]) == cudaSuccess) s->stats.ms_total = ms;
+    cudaGetLastError();
+  }
+  *out = s->stats;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_debug_read_coverage(skb_surface s, uint32_t op, int32_t x, int32_t y, uint32_t w, uint32_t h, uint8_t* direct,
+                                   uint8_t* accum) {
+  if (!s || !direct || !accum || !s->flushed || op >= s->n_ops || w == 0 || h == 0) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  uint8_t *dd = nullptr, *da = nullptr;
+  SKB_CUDA(cudaMalloc((void**)&dd, (size_t)w * h));
+  SKB_CUDA(cudaMalloc((void**)&da, (size_t)w * h));
+  CoverArgs ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.geom = (const OpGeom*)s->geom.p;
+  ca.item_base = (const uint32_t*)s->item_cnt.p;
+  ca.n_ops = s->n_ops;
+  ca.n_items = s->n_items;
+  ca.mask0 = (uint8_t*)s->mask0.p;
+  ca.mask1 = (uint8_t*)s->mask1.p;
+  ca.item_flags = (uint8_t*)s->item_flags.p;
+  k_read_coverage<<<cdiv((uint64_t)w * h, 256), 256, 0, s->stream>>>(ca, op, x, y, w, h, dd, da);
+  cudaError_t e = cudaMemcpyAsync(direct, dd, (size_t)w * h, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(accum, da, (size_t)w * h, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(dd);
+  cudaFree(da);
+  if (e != cudaSuccess) {
+    set_error(std::string("read coverage: ") + cudaGetErrorString(e));
+    return SKB_ERROR_CUDA;
+  }
+  return SKB_SUCCESS;
+}
+
+}  // extern "C"

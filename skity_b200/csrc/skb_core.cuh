@@ -1,0 +1,755 @@
+// skb_core.cuh — per-thread building blocks of the CUDA raster pipeline.
+//
+// Everything here is a pure function of its arguments (no warp collectives, no
+// globals), marked SKB_HD so the same code is compiled by nvcc into the kernels
+// of skb_kernels.cu and by g++ into the CPU simulation the tests use to check
+// kernel logic where no GPU is present (tests/sim/).
+//
+// The arithmetic reproduces Skity's software rasteriser bit for bit; each block
+// cites the reference file:line whose behaviour it has to match:
+//   * 16.16 / 26.6 fixed point with wrapping int32 shifts  (src/render/sw/sw_subpixel.hpp:19-90)
+//   * edges, quadratic forward differencing                 (src/render/sw/sw_edge.cc:18-297)
+//   * the analytic-AA edge walk                             (src/render/sw/sw_raster.cc:138-247,546-677)
+//   * per-pixel trapezoid coverage                          (src/render/sw/sw_raster.cc:249-544)
+//   * colour / blend integer maths                          (src/graphic/color_priv.hpp:20-80)
+// Float maths must be compiled with one rounding per operation (-fmad=false).
+#ifndef SKB_CORE_CUH
+#define SKB_CORE_CUH
+
+#include <stdint.h>
+#include <math.h>
+
+#include "include/skb_dl.h"
+
+#if defined(__CUDACC__)
+#define SKB_HD __host__ __device__ __forceinline__
+#define SKB_HDN __host__ __device__
+#else
+#define SKB_HD inline
+#define SKB_HDN inline
+#endif
+
+#if !defined(__CUDACC__)
+struct uint2 { unsigned int x, y; };  // host stand-in for the CUDA vector type (CPU simulation builds)
+#endif
+
+namespace skb {
+
+typedef int32_t fx;
+#define SKB_FX1 65536
+#define SKB_FX_MAX 0x7FFFFFFF
+#define SKB_FX_MIN (-0x7FFFFFFF)
+#define SKB_TILE 16
+
+// ------------------------------------------------------------------ fixed point
+SKB_HD fx shl(fx v, int s) { return (fx)((uint32_t)v << s); }
+SKB_HD fx fx_add(fx a, fx b) { return (fx)((uint32_t)a + (uint32_t)b); }
+SKB_HD fx fx_sub(fx a, fx b) { return (fx)((uint32_t)a - (uint32_t)b); }
+SKB_HD fx fx_abs(fx v) { return v < 0 ? (fx)(0u - (uint32_t)v) : v; }
+SKB_HD fx fx_mul(fx a, fx b) { return (fx)(((int64_t)a * (int64_t)b) >> 16); }
+SKB_HD fx fx_div(fx n, fx d) {  // SWFixedDiv: 64-bit quotient clamped to +-0x7FFFFFFF
+  int64_t q = (int64_t)((uint64_t)(int64_t)n << 16) / (int64_t)d;
+  if (q < (int64_t)SKB_FX_MIN) q = SKB_FX_MIN;
+  if (q > (int64_t)SKB_FX_MAX) q = SKB_FX_MAX;
+  return (fx)q;
+}
+SKB_HD fx snap_y(fx y) { return (fx)((((uint32_t)y + (SKB_FX1 >> 3)) >> 14) << 14); }
+SKB_HD int fx_floor_i(fx x) { return x >> 16; }
+SKB_HD int fx_ceil_i(fx x) { return (fx)((uint32_t)x + SKB_FX1 - 1) >> 16; }
+SKB_HD int fx_round_i(fx x) { return (fx)((uint32_t)x + (SKB_FX1 >> 1)) >> 16; }
+SKB_HD fx fx_round_fx(fx x) { return (fx)(((uint32_t)x + (SKB_FX1 >> 1)) & 0xFFFF0000u); }
+SKB_HD fx fx_ceil_fx(fx x) { return (fx)(((uint32_t)x + SKB_FX1 - 1) & 0xFFFF0000u); }
+SKB_HD fx fx_floor_fx(fx x) { return (fx)((uint32_t)x & 0xFFFF0000u); }
+SKB_HD fx i_to_fx(int n) { return (fx)((uint32_t)n << 16); }
+SKB_HD fx fx_min(fx a, fx b) { return a < b ? a : b; }
+SKB_HD fx fx_max(fx a, fx b) { return a > b ? a : b; }
+SKB_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+// static_cast<int>(float) as x86-64 performs it (cvttss2si: out of range / NaN -> INT_MIN)
+SKB_HD int32_t f2i(float v) {
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return (int32_t)0x80000000;
+  return (int32_t)v;
+}
+
+// ------------------------------------------------------------------------ edges
+// One active edge of the scan converter (SWEdge + SWQuadEdge, sw_edge.hpp:18-81), 80 bytes.
+struct Edge {
+  fx x, y, dx, dy, upper_x, upper_y, lower_y;
+  fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y, snapped_x, snapped_y;
+  int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24
+  int32_t prev, next;
+};
+SKB_HD int edge_count(const Edge& e) { return e.curve & 0xFF; }
+SKB_HD int edge_shift(const Edge& e) { return (e.curve >> 8) & 0xFF; }
+SKB_HD int edge_winding(const Edge& e) { return (int)(int8_t)((e.curve >> 16) & 0xFF); }
+SKB_HD void edge_set_curve(Edge& e, int count, int shift, int winding) {
+  e.curve = (count & 0xFF) | ((shift & 0xFF) << 8) | ((winding & 0xFF) << 16) | (e.curve & 0xFF000000);
+}
+SKB_HD void edge_set_count(Edge& e, int count) { e.curve = (e.curve & ~0xFF) | (count & 0xFF); }
+SKB_HD void edge_negate_winding(Edge& e) {
+  int w = -edge_winding(e);
+  e.curve = (e.curve & ~0xFF0000) | ((w & 0xFF) << 16);
+}
+
+// SWEdge::UpdateLine (sw_edge.cc:44-70)
+SKB_HD int update_line(Edge& e, fx x0, fx y0, fx x1, fx y1, fx slope) {
+  if (y0 > y1) {
+    fx t = x0; x0 = x1; x1 = t;
+    t = y0; y0 = y1; y1 = t;
+    edge_negate_winding(e);
+  }
+  fx x0x1 = fx_sub(x1, x0) >> 10;
+  fx y0y1 = fx_sub(y1, y0) >> 10;
+  if (y0y1 == 0) return 0;
+  e.x = x0;
+  e.y = y0;
+  e.dx = slope;
+  e.dy = (x0x1 == 0 || slope == 0) ? SKB_FX_MAX : fx_abs(fx_div(y0y1, x0x1));
+  e.upper_x = x0;
+  e.upper_y = y0;
+  e.lower_y = y1;
+  return 1;
+}
+
+// float pixel coordinate -> 16.16 as SetLine does: trunc(v*4*64) << 10 >> 2 (sw_edge.cc:22-29)
+SKB_HD fx line_coord(float v) { return shl(f2i((v * 4.0f) * 64.0f), 10) >> 2; }
+
+// SWEdge::SetLine (sw_edge.cc:18-42)
+SKB_HD int set_line(Edge& e, float x0f, float y0f, float x1f, float y1f) {
+  fx x0 = line_coord(x0f), y0 = snap_y(line_coord(y0f));
+  fx x1 = line_coord(x1f), y1 = snap_y(line_coord(y1f));
+  edge_set_curve(e, 0, 0, 1);
+  fx y0y1 = fx_sub(y1, y0) >> 10;
+  if (y0y1 == 0) return 0;
+  fx x0x1 = fx_sub(x1, x0) >> 10;
+  fx slope = fx_div(x0x1, y0y1);
+  return update_line(e, x0, y0, x1, y1, slope);
+}
+
+// SWQuadEdge::UpdateQuad (sw_edge.cc:233-292)
+SKB_HDN int update_quad(Edge& e) {
+  int success = 0;
+  int count = edge_count(e);
+  fx oldx = e.qx, oldy = e.qy, dx = e.qdx, dy = e.qdy;
+  fx newx = 0, newy = 0, nsx = 0, nsy = 0;
+  const int shift = edge_shift(e);
+  do {
+    fx slope;
+    if (--count > 0) {
+      newx = fx_add(oldx, dx >> shift);
+      newy = fx_add(oldy, dy >> shift);
+      if (fx_abs(dy >> shift) >= SKB_FX1 * 2) {
+        fx diffy = fx_sub(newy, e.snapped_y) >> 10;
+        slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+        nsy = fx_min(e.q_last_y, fx_round_fx(newy));
+        nsx = fx_sub(newx, fx_mul(slope, fx_sub(newy, nsy)));
+      } else {
+        nsy = fx_min(e.q_last_y, snap_y(newy));
+        nsx = newx;
+        fx diffy = fx_sub(nsy, e.snapped_y) >> 10;
+        slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+      }
+      dx = fx_add(dx, e.qddx);
+      dy = fx_add(dy, e.qddy);
+    } else {
+      newx = e.q_last_x;
+      newy = e.q_last_y;
+      nsy = newy;
+      nsx = newx;
+      fx diffy = fx_sub(newy, e.snapped_y) >> 10;
+      slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+    }
+    if (slope < SKB_FX_MAX) success = update_line(e, e.snapped_x, e.snapped_y, nsx, nsy, slope);
+    oldx = newx;
+    oldy = newy;
+  } while (count > 0 && !success);
+  e.qx = newx;
+  e.qy = newy;
+  e.qdx = dx;
+  e.qdy = dy;
+  e.snapped_x = nsx;
+  e.snapped_y = nsy;
+  edge_set_count(e, count);
+  return success;
+}
+
+// diff_to_shift with shiftAA = 2 (sw_edge.cc:97-119)
+SKB_HD int diff_to_shift(fx dx, fx dy) {
+  dx = fx_abs(dx);
+  dy = fx_abs(dy);
+  fx dist = fx_max(dx, dy) + (fx_min(dx, dy) >> 1);
+  dist = fx_add(dist, 1 << 4) >> 5;
+  return (32 - clz32((uint32_t)dist)) >> 1;
+}
+
+// SWQuadEdge::SetQuad (sw_edge.cc:121-231). p = x0 y0 x1 y1 x2 y2 of a y-monotone quad.
+// On success *first_y / *last_y receive q_first_y / q_last_y (used by CanBeIgnored).
+SKB_HDN int set_quad(Edge& e, const float* p, fx* first_y, fx* last_y) {
+  fx x0 = f2i(p[0] * 256.0f), y0 = f2i(p[1] * 256.0f);
+  fx x1 = f2i(p[2] * 256.0f), y1 = f2i(p[3] * 256.0f);
+  fx x2 = f2i(p[4] * 256.0f), y2 = f2i(p[5] * 256.0f);
+  int w = 1;
+  if (y0 > y2) {
+    fx t = x0; x0 = x2; x2 = t;
+    t = y0; y0 = y2; y2 = t;
+    w = -1;
+  }
+  int top = fx_add(y0, 32) >> 6, bottom = fx_add(y2, 32) >> 6;
+  if (top == bottom) return 0;
+  fx ddx = fx_sub(fx_sub(shl(x1, 1), x0), x2) >> 2;
+  fx ddy = fx_sub(fx_sub(shl(y1, 1), y0), y2) >> 2;
+  int shift = diff_to_shift(ddx, ddy);
+  if (shift == 0) shift = 1;
+  else if (shift > 6) shift = 6;
+  edge_set_curve(e, 1 << shift, shift - 1, w);
+  fx A = shl(fx_add(fx_sub(fx_sub(x0, x1), x1), x2), 9);
+  fx B = shl(fx_sub(x1, x0), 10);
+  e.qx = shl(x0, 10) >> 2;
+  e.qdx = fx_add(B, A >> shift) >> 2;
+  e.qddx = (A >> (shift - 1)) >> 2;
+  A = shl(fx_add(fx_sub(fx_sub(y0, y1), y1), y2), 9);
+  B = shl(fx_sub(y1, y0), 10);
+  e.qy = snap_y(shl(y0, 10) >> 2);
+  e.qdy = fx_add(B, A >> shift) >> 2;
+  e.qddy = (A >> (shift - 1)) >> 2;
+  e.q_last_x = shl(x2, 10) >> 2;
+  e.q_last_y = snap_y(shl(y2, 10) >> 2);
+  *first_y = e.qy;
+  *last_y = e.q_last_y;
+  e.snapped_x = e.qx;
+  e.snapped_y = e.qy;
+  e.x = e.y = e.dx = e.dy = e.upper_x = e.upper_y = e.lower_y = 0;
+  update_quad(e);
+  return 1;
+}
+
+// SWEdge::CanBeIgnored (sw_edge.cc:72-88)
+SKB_HD int can_be_ignored(float scan_top, float scan_bottom, fx y0, fx y1) {
+  fx start_y = snap_y(line_coord(scan_top));
+  fx stop_y = snap_y(line_coord(scan_bottom));
+  return (y0 >= stop_y || y1 <= start_y);
+}
+
+// ----------------------------------------------------------- curve lowering (fp32)
+struct V2 { float x, y; };
+SKB_HD V2 v2(float x, float y) { V2 r; r.x = x; r.y = y; return r; }
+
+// Matrix * (x, y, 0, 1) in glm's order: (m0*x + m1*y) + (m2*0 + m3*1)
+// (Path::CopyWithMatrix src/graphic/path.cc:1274-1296 -> src/geometry/matrix.cc:463)
+SKB_HD V2 xform(const float* m, V2 p) {
+  float zx = 0.0f * 0.0f + m[2] * 1.0f;
+  float zy = 0.0f * 0.0f + m[5] * 1.0f;
+  return v2((m[0] * p.x + m[1] * p.y) + zx, (m[3] * p.x + m[4] * p.y) + zy);
+}
+
+struct CubicCoeff { V2 A, B, C, D; };  // src/geometry/geometry.cc:135-169
+SKB_HD CubicCoeff cubic_coeff(V2 p0, V2 p1, V2 p2, V2 p3) {
+  CubicCoeff c;
+  c.A = v2((p3.x + 3.0f * (p1.x - p2.x)) - p0.x, (p3.y + 3.0f * (p1.y - p2.y)) - p0.y);
+  c.B = v2(3.0f * ((p2.x - (p1.x + p1.x)) + p0.x), 3.0f * ((p2.y - (p1.y + p1.y)) + p0.y));
+  c.C = v2(3.0f * (p1.x - p0.x), 3.0f * (p1.y - p0.y));
+  c.D = p0;
+  return c;
+}
+SKB_HD V2 cubic_eval(const CubicCoeff& c, float t) {
+  return v2(((c.A.x * t + c.B.x) * t + c.C.x) * t + c.D.x, ((c.A.y * t + c.B.y) * t + c.C.y) * t + c.D.y);
+}
+struct QuadCoeff { V2 A, B, C; };  // geometry.cc:44-67
+SKB_HD QuadCoeff quad_coeff(V2 q0, V2 q1, V2 q2) {
+  QuadCoeff c;
+  c.C = q0;
+  c.B = v2((q1.x - q0.x) + (q1.x - q0.x), (q1.y - q0.y) + (q1.y - q0.y));
+  c.A = v2((q2.x - (q1.x + q1.x)) + q0.x, (q2.y - (q1.y + q1.y)) + q0.y);
+  return c;
+}
+SKB_HD V2 quad_eval(const QuadCoeff& c, float t) {
+  return v2((c.A.x * t + c.B.x) * t + c.C.x, (c.A.y * t + c.B.y) * t + c.C.y);
+}
+
+// Cubic::ToQuads subdivision count (src/geometry/cubic.cc:29-38): double pow, ceil, >= 1.
+SKB_HDN int cubic_quad_count(V2 p1, V2 c1, V2 c2, V2 p2) {
+  const float accuracy = 0.1f;
+  const double max_hypot2 = 432.0 * (double)accuracy * (double)accuracy;
+  V2 a = v2(c1.x * 3.0f - p1.x, c1.y * 3.0f - p1.y);
+  V2 b = v2(c2.x * 3.0f - p2.x, c2.y * 3.0f - p2.y);
+  V2 p = v2(b.x - a.x, b.y - a.y);
+  float err = p.x * p.x + p.y * p.y;
+  double n = ceil(pow((double)err / max_hypot2, 1. / 6.0));
+  if (!(n > 1.)) n = 1.;
+  if (n > 4096.) n = 4096.;  // guard; the reference allocates without bound
+  return (int)n;
+}
+
+// k-th quad of Cubic::ToQuads (cubic.cc:39-61): returns control and end point (source space).
+SKB_HD void cubic_sub_quad(const CubicCoeff& cc, const QuadCoeff& qc, int k, int cnt, V2* ctrl, V2* end) {
+  double quad_count = (double)cnt;
+  float t0 = (float)((double)k / quad_count), t1 = (float)((double)(k + 1) / quad_count);
+  V2 a = cubic_eval(cc, t0), b = cubic_eval(cc, t1);
+  float sc = (t1 - t0) * (1.f / 3.f);
+  V2 ta = quad_eval(qc, t0), tb = quad_eval(qc, t1);
+  V2 c1 = v2(a.x + ta.x * sc, a.y + ta.y * sc);
+  V2 c2 = v2(b.x - tb.x * sc, b.y - tb.y * sc);
+  *ctrl = v2(((c1.x * 3.f - a.x) + (c2.x * 3.f - b.x)) / 4.f, ((c1.y * 3.f - a.y) + (c2.y * 3.f - b.y)) / 4.f);
+  *end = b;
+}
+
+// Conic -> exactly two quads (Stroke::QuadPath stroke.cc:929-939, Conic::Chop + subdivided conic.cc:26-65,169-199)
+SKB_HD int between_f(float a, float b, float c) { return (a - b) * (c - b) <= 0; }
+SKB_HD int finite_f(float v) { return (v - v) == 0.0f; }
+SKB_HDN void conic_to_quads(V2 p0, V2 p1, V2 p2, float w, V2 out[5]) {
+  float scale = 1.0f / (w + 1.0f);
+  V2 wp1 = v2(w * p1.x, w * p1.y);
+  V2 m = v2(((p0.x + (wp1.x + wp1.x)) + p2.x) * scale * 0.5f, ((p0.y + (wp1.y + wp1.y)) + p2.y) * scale * 0.5f);
+  if (!(finite_f(m.x) && finite_f(m.y))) {
+    double w_d = w, w_2 = w_d * 2, scale_half = 1 / (1 + w_d) * 0.5;
+    m.x = (float)((p0.x + w_2 * p1.x + p2.x) * scale_half);
+    m.y = (float)((p0.y + w_2 * p1.y + p2.y) * scale_half);
+  }
+  V2 d0p1 = v2((p0.x + wp1.x) * scale, (p0.y + wp1.y) * scale);
+  V2 d1p1 = v2((wp1.x + p2.x) * scale, (wp1.y + p2.y) * scale);
+  V2 d0p2 = m, d1p0 = m;
+  float startY = p0.y, endY = p2.y;
+  if (between_f(startY, p1.y, endY)) {
+    float midY = d0p2.y;
+    if (!between_f(startY, midY, endY)) {
+      float closerY = fabsf(midY - startY) < fabsf(midY - endY) ? startY : endY;
+      d0p2.y = d1p0.y = closerY;
+    }
+    if (!between_f(startY, d0p1.y, d0p2.y)) d0p1.y = startY;
+    if (!between_f(d1p0.y, d1p1.y, endY)) d1p1.y = endY;
+  }
+  out[0] = p0; out[1] = d0p1; out[2] = d0p2; out[3] = d1p1; out[4] = p2;
+  float prod = 0;
+  for (int i = 0; i < 5; i++) prod *= (out[i].x * out[i].y);
+  if (!(prod == 0)) {
+    for (int i = 1; i < 4; i++) out[i] = p1;
+  }
+}
+
+// ChopQuadAtYExtrema (src/geometry/geometry.cc:311-349). Returns 1 or 2 monotone quads in dst[5].
+SKB_HDN int chop_quad_y(const V2 src[3], V2 dst[5]) {
+  float a = src[0].y, b = src[1].y, c = src[2].y;
+  float ab = a - b, bc = b - c;
+  if (ab < 0) bc = -bc;
+  if (ab == 0 || bc < 0) {
+    float number = a - b, denom = a - b - b + c;
+    if (number < 0) { number = -number; denom = -denom; }
+    if (!(denom == 0 || number == 0 || number >= denom)) {
+      float r = number / denom;
+      if (r == r && r != 0) {
+        V2 p01 = v2(src[0].x + (src[1].x - src[0].x) * r, src[0].y + (src[1].y - src[0].y) * r);
+        V2 p12 = v2(src[1].x + (src[2].x - src[1].x) * r, src[1].y + (src[2].y - src[1].y) * r);
+        dst[0] = src[0];
+        dst[1] = p01;
+        dst[2] = v2(p01.x + (p12.x - p01.x) * r, p01.y + (p12.y - p01.y) * r);
+        dst[3] = p12;
+        dst[4] = src[2];
+        dst[1].y = dst[3].y = dst[2].y;
+        return 2;
+      }
+    }
+    b = fabsf(a - b) < fabsf(b - c) ? a : c;
+  }
+  dst[0] = src[0];
+  dst[1] = src[1];
+  dst[2] = src[2];
+  dst[1].y = b;
+  return 1;
+}
+
+// Number of lowered primitives (lines / quads) a display-list segment expands to.
+SKB_HDN int seg_prim_count(const skb_dl_seg& s) {
+  switch (s.type_flags & SKB_SEG_TYPE_MASK) {
+    case SKB_SEG_LINE:
+    case SKB_SEG_CLOSE:
+    case SKB_SEG_QUAD:
+      return 1;
+    case SKB_SEG_CONIC:
+      return 2;
+    case SKB_SEG_CUBIC:
+      return cubic_quad_count(v2(s.p[0], s.p[1]), v2(s.p[2], s.p[3]), v2(s.p[4], s.p[5]), v2(s.p[6], s.p[7]));
+    default:
+      return 0;
+  }
+}
+
+// The point a segment really starts at in the lowered path (see SKB_SEG_P0_FROM_PREV_CUBIC).
+SKB_HDN V2 seg_start_point(const skb_dl_seg* segs, uint32_t i) {
+  const skb_dl_seg& s = segs[i];
+  if (s.type_flags & SKB_SEG_P0_FROM_PREV_CUBIC) {
+    const skb_dl_seg& c = segs[i - 1];
+    CubicCoeff cc = cubic_coeff(v2(c.p[0], c.p[1]), v2(c.p[2], c.p[3]), v2(c.p[4], c.p[5]), v2(c.p[6], c.p[7]));
+    return cubic_eval(cc, 1.0f);
+  }
+  return v2(s.start[0], s.start[1]);
+}
+
+// k-th lowered primitive of segment i, transformed by the CTM.  Returns 2 (line) or 3 (quad).
+SKB_HDN int seg_prim(const skb_dl_seg* segs, uint32_t i, int k, int n_prims, const float* ctm, V2 out[3]) {
+  const skb_dl_seg& s = segs[i];
+  uint32_t type = s.type_flags & SKB_SEG_TYPE_MASK;
+  V2 p0 = v2(s.p[0], s.p[1]), p1 = v2(s.p[2], s.p[3]), p2 = v2(s.p[4], s.p[5]), p3 = v2(s.p[6], s.p[7]);
+  switch (type) {
+    case SKB_SEG_LINE:
+    case SKB_SEG_CLOSE:
+      out[0] = xform(ctm, seg_start_point(segs, i));
+      out[1] = xform(ctm, p1);
+      out[2] = out[1];
+      return 2;
+    case SKB_SEG_QUAD:
+      out[0] = xform(ctm, seg_start_point(segs, i));
+      out[1] = xform(ctm, p1);
+      out[2] = xform(ctm, p2);
+      return 3;
+    case SKB_SEG_CONIC: {
+      V2 q[5];
+      conic_to_quads(p0, p1, p2, s.w, q);
+      if (k == 0) {
+        out[0] = xform(ctm, seg_start_point(segs, i));
+        out[1] = xform(ctm, q[1]);
+        out[2] = xform(ctm, q[2]);
+      } else {
+        out[0] = xform(ctm, q[2]);
+        out[1] = xform(ctm, q[3]);
+        out[2] = xform(ctm, q[4]);
+      }
+      return 3;
+    }
+    case SKB_SEG_CUBIC: {
+      CubicCoeff cc = cubic_coeff(p0, p1, p2, p3);
+      QuadCoeff qc = quad_coeff(v2(3.f * (p1.x - p0.x), 3.f * (p1.y - p0.y)), v2(3.f * (p2.x - p1.x), 3.f * (p2.y - p1.y)),
+                                v2(3.f * (p3.x - p2.x), 3.f * (p3.y - p2.y)));
+      V2 ctrl, end;
+      cubic_sub_quad(cc, qc, k, n_prims, &ctrl, &end);
+      if (k == 0) {
+        out[0] = xform(ctm, seg_start_point(segs, i));
+      } else {
+        double quad_count = (double)n_prims;
+        out[0] = xform(ctm, cubic_eval(cc, (float)((double)k / quad_count)));
+      }
+      out[1] = xform(ctm, ctrl);
+      out[2] = xform(ctm, end);
+      return 3;
+    }
+    default:
+      return 0;
+  }
+}
+
+// ------------------------------------------------- trapezoid rows (walker output)
+// One call of blit_trapezoid_row (sw_raster.cc:457-544) as the walker would make it.
+struct TrapRec {
+  int32_t y;           // pixel row
+  fx ul, ur, ll, lr;   // upper-left/right, lower-left/right x of the band's interval
+  fx ldy, rdy;         // |dy/dx| of the left / right edge
+  uint32_t flags;      // full alpha (bits 0-7) | no_real_span_builder << 8
+};
+#define SKB_REC_LINK 0x80000000u  // flags of the chunk-link pseudo record (y = next record index)
+
+SKB_HD uint8_t partial_alpha_mul(uint32_t alpha, uint32_t full) { return (uint8_t)((alpha * full) >> 8); }
+SKB_HD uint8_t trapezoid_to_alpha(fx l1, fx l2) { return (uint8_t)((fx_add(l1, l2) / 2) >> 8); }
+SKB_HD uint8_t partial_triangle_to_alpha(fx a, fx b) {
+  uint32_t area = (uint32_t)(a >> 11) * (uint32_t)(a >> 11) * (uint32_t)(b >> 11);
+  return (uint8_t)((((fx)area) >> 8) & 0xFF);
+}
+
+// compute_alpha_below_line evaluated at index j (sw_raster.cc:343-368)
+SKB_HD uint8_t alpha_below_at(int j, fx l, fx r, fx dY, uint32_t full) {
+  int R = fx_ceil_i(r);
+  if (R == 1) {
+    return partial_alpha_mul(trapezoid_to_alpha(l, r), full);
+  }
+  fx first = fx_sub(SKB_FX1, l);
+  fx last = fx_sub(r, shl(R - 1, 16));
+  fx lastH = fx_mul(last, dY);
+  if (j == R - 1) return (uint8_t)(fx_mul(last, lastH) >> 9);
+  if (j == 0) return (uint8_t)(full - partial_triangle_to_alpha(first, dY));
+  fx a16 = fx_add(fx_add(lastH, dY >> 1), (fx)((uint32_t)(R - 2 - j) * (uint32_t)dY));
+  return (uint8_t)((a16 >> 8) & 0xFF);
+}
+// compute_alpha_above_line evaluated at index j (sw_raster.cc:314-339)
+SKB_HD uint8_t alpha_above_at(int j, fx l, fx r, fx dY, uint32_t full) {
+  int R = fx_ceil_i(r);
+  if (R == 1) {
+    return partial_alpha_mul((uint8_t)(fx_sub(fx_sub(shl(R, 17), l), r) >> 9), full);
+  }
+  fx first = fx_sub(SKB_FX1, l);
+  fx last = fx_sub(r, shl(R - 1, 16));
+  fx firstH = fx_mul(first, dY);
+  if (j == 0) return (uint8_t)(fx_mul(first, firstH) >> 9);
+  if (j == R - 1) return (uint8_t)(full - partial_triangle_to_alpha(last, dY));
+  fx a16 = fx_add(fx_add(firstH, dY >> 1), (fx)((uint32_t)(j - 1) * (uint32_t)dY));
+  return (uint8_t)(a16 >> 8);
+}
+
+// blit_aaa_trapezoid_row at pixel x (sw_raster.cc:370-455). `accum` = the row goes through the
+// accumulating SpanBuilder (partial-height band or "too close"), which scales single alphas.
+SKB_HDN bool aaa_row_at(int x, fx ul, fx ur, fx ll, fx lr, fx lDY, fx rDY, uint32_t full, bool accum, uint8_t* out) {
+  int L = fx_floor_i(ul), R = fx_ceil_i(lr);
+  int len = R - L;
+  if (x < L || x >= R) return false;
+  if (len == 1) {
+    uint8_t a = trapezoid_to_alpha(fx_sub(ur, ul), fx_sub(lr, ll));
+    *out = accum ? partial_alpha_mul(a, full) : a;
+    return true;
+  }
+  int i = x - L;
+  uint32_t a = full;
+  int uL = L, lL = fx_ceil_i(ll);
+  if (uL + 2 == lL) {
+    fx first = fx_sub(fx_add(i_to_fx(uL), SKB_FX1), ul);
+    fx second = fx_sub(fx_sub(ll, ul), first);
+    if (i == 0) {
+      uint8_t a1 = (uint8_t)(full - partial_triangle_to_alpha(first, lDY));
+      a = a > a1 ? a - a1 : 0;
+    } else if (i == 1) {
+      uint8_t a2 = partial_triangle_to_alpha(second, lDY);
+      a = a > a2 ? a - a2 : 0;
+    }
+  } else if (x < lL) {
+    uint8_t t = alpha_below_at(x - uL, fx_sub(ul, i_to_fx(uL)), fx_sub(ll, i_to_fx(uL)), lDY, full);
+    a = a > t ? a - t : 0;
+  }
+  int uR = fx_floor_i(ur), lR = R;
+  if (uR + 2 == lR) {
+    fx first = fx_sub(fx_add(i_to_fx(uR), SKB_FX1), ur);
+    fx second = fx_sub(fx_sub(lr, ur), first);
+    if (i == len - 2) {
+      uint8_t a1 = partial_triangle_to_alpha(first, rDY);
+      a = a > a1 ? a - a1 : 0;
+    } else if (i == len - 1) {
+      uint8_t a2 = (uint8_t)(full - partial_triangle_to_alpha(second, rDY));
+      a = a > a2 ? a - a2 : 0;
+    }
+  } else if (x >= uR) {
+    uint8_t t = alpha_above_at(x - uR, fx_sub(ur, i_to_fx(uR)), fx_sub(lr, i_to_fx(uR)), rDY, full);
+    a = a > t ? a - t : 0;
+  }
+  *out = (uint8_t)a;
+  return true;
+}
+
+// Pixel extent [x0, x1) a trapezoid row can touch (conservative; used for culling).
+SKB_HD void trap_extent(const TrapRec& r, int* x0, int* x1) {
+  fx lo = fx_min(fx_min(r.ul, r.ll), fx_min(r.ur, r.lr));
+  fx hi = fx_max(fx_max(r.ul, r.ll), fx_max(r.ur, r.lr));
+  *x0 = fx_floor_i(lo);
+  *x1 = fx_ceil_i(hi);
+}
+
+// blit_trapezoid_row evaluated at one pixel (sw_raster.cc:457-544): returns whether the
+// reference would emit a coverage value for pixel x, and that value.
+SKB_HDN bool trap_alpha_at(const TrapRec& r, int x, uint8_t* out) {
+  fx ul = r.ul, ur = r.ur, ll = r.ll, lr = r.lr;
+  const uint32_t full = r.flags & 0xFF;
+  const bool accum = !(full == 0xFF && !((r.flags >> 8) & 1));
+  if (ul > ur) return false;
+  if (ll > lr) {  // approximate_intersection (sw_raster.cc:253-262)
+    fx l1 = ul, r1 = ll, l2 = ur, r2 = lr;
+    if (l1 > r1) { fx t = l1; l1 = r1; r1 = t; }
+    if (l2 > r2) { fx t = l2; l2 = r2; r2 = t; }
+    ll = lr = fx_add(fx_max(l1, l2), fx_min(r1, r2)) / 2;
+  }
+  if (ul == ur && ll == lr) return false;
+  if (ul > ll) { fx t = ul; ul = ll; ll = t; }
+  if (ur > lr) { fx t = ur; ur = lr; lr = t; }
+  fx joinLeft = fx_ceil_fx(ll);
+  fx joinRite = fx_floor_fx(ur);
+  if (joinLeft <= joinRite) {
+    if (ul < joinLeft) {
+      int len = fx_ceil_i(fx_sub(joinLeft, ul));
+      int x0 = ul >> 16;
+      if (len == 1) {
+        if (x == x0) {
+          uint8_t a = trapezoid_to_alpha(fx_sub(joinLeft, ul), fx_sub(joinLeft, ll));
+          *out = accum ? partial_alpha_mul(a, full) : a;
+          return true;
+        }
+      } else if (len == 2) {
+        if (x == x0 || x == x0 + 1) {
+          fx first = fx_sub(fx_sub(joinLeft, SKB_FX1), ul);
+          fx second = fx_sub(fx_sub(ll, ul), first);
+          *out = x == x0 ? partial_triangle_to_alpha(first, r.ldy)
+                         : (uint8_t)(full - partial_triangle_to_alpha(second, r.ldy));
+          return true;
+        }
+      } else {
+        if (aaa_row_at(x, ul, joinLeft, ll, joinLeft, r.ldy, SKB_FX_MAX, full, accum, out)) return true;
+      }
+    }
+    if (joinLeft < joinRite) {
+      int xs = fx_floor_i(joinLeft);
+      int n = fx_floor_i(fx_sub(joinRite, joinLeft));
+      if (x >= xs && x < xs + n) {
+        *out = (uint8_t)full;
+        return true;
+      }
+    }
+    if (lr > joinRite) {
+      int len = fx_ceil_i(fx_sub(lr, joinRite));
+      int x0 = joinRite >> 16;
+      if (len == 1) {
+        if (x == x0) {
+          uint8_t a = trapezoid_to_alpha(fx_sub(ur, joinRite), fx_sub(lr, joinRite));
+          *out = accum ? partial_alpha_mul(a, full) : a;
+          return true;
+        }
+      } else if (len == 2) {
+        if (x == x0 || x == x0 + 1) {
+          fx first = fx_sub(fx_add(joinRite, SKB_FX1), ur);
+          fx second = fx_sub(fx_sub(lr, ur), first);
+          *out = x == x0 ? (uint8_t)(full - partial_triangle_to_alpha(first, r.rdy))
+                         : partial_triangle_to_alpha(second, r.rdy);
+          return true;
+        }
+      } else {
+        if (aaa_row_at(x, joinRite, ur, joinRite, lr, SKB_FX_MAX, r.rdy, full, accum, out)) return true;
+      }
+    }
+    return false;
+  }
+  return aaa_row_at(x, ul, ur, ll, lr, r.ldy, r.rdy, full, accum, out);
+}
+
+// ------------------------------------------------------------- colour and blend
+// Pixels are handled as little-endian words of the R,G,B,A bytes in memory:
+// word = R | G<<8 | B<<16 | A<<24.  AlphaMulQ / SrcOver treat the four bytes alike
+// (alpha sits in the top byte in both layouts), so no swizzle is needed.
+SKB_HD uint32_t mul_div_255_round(uint32_t a, uint32_t b) {
+  uint32_t prod = a * b + 128;
+  return (prod + (prod >> 8)) >> 8;
+}
+SKB_HD uint32_t unit_to_byte(float f) {  // Color4fToColor per channel (src/graphic/color.cc:53-59): clamp, truncate
+  float v = f * 255.0f;
+  v = v < 0.f ? 0.f : v;
+  v = v > 255.f ? 255.f : v;
+  if (!(v == v)) v = 0.f;
+  return (uint32_t)(uint8_t)v;
+}
+// Color4f (unpremultiplied r,g,b,a) -> premultiplied pixel word (Color4fToColor + ColorToPMColor)
+SKB_HD uint32_t color4f_to_pm_word(float r, float g, float b, float a) {
+  uint32_t A = unit_to_byte(a), R = unit_to_byte(r), G = unit_to_byte(g), B = unit_to_byte(b);
+  if (A != 255) {
+    R = mul_div_255_round(R, A);
+    G = mul_div_255_round(G, A);
+    B = mul_div_255_round(B, A);
+  }
+  return R | (G << 8) | (B << 16) | (A << 24);
+}
+SKB_HD uint32_t alpha_mul_q(uint32_t c, uint32_t scale) {  // color_priv.hpp:62-68
+  const uint32_t mask = 0xFF00FF;
+  uint32_t rb = ((c & mask) * scale) >> 8;
+  uint32_t ag = ((c >> 8) & mask) * scale;
+  return (rb & mask) | (ag & ~mask);
+}
+// One SWSpanBrush::BrushH + SWRenderTarget::BlendPixel(kSrcOver) step on a premultiplied target
+// (sw_span_brush.cc:108-119, sw_render_target.cc:88-113, color_priv.hpp:70-72).
+SKB_HD uint32_t blend_cover(uint32_t dst, uint32_t color, uint32_t cover) {
+  if (cover != 255) color = alpha_mul_q(color, cover);
+  uint32_t a = color >> 24;
+  if (a == 0) return dst;
+  if (a == 255) return color;
+  return color + alpha_mul_q(dst, 256 - a);
+}
+
+// GradientColorBrush::LerpColor (sw_span_brush.cc:21-32,239-299) -> premultiplied pixel word
+SKB_HDN uint32_t gradient_color(const skb_dl_paint& p, const float* pool, float t) {
+  const float* colors = pool + p.stop_off;
+  const float* stops = colors + 4 * (size_t)p.n_colors;
+  if (fabsf(t) <= (1.0f / 4096)) t = 0.0f;
+  else if (fabsf(t - 1.0f) <= (1.0f / 4096)) t = 1.0f;
+  if (p.tile_mode == 3 && (t < 0.0f || t >= 1.0f)) return 0;
+  if (p.tile_mode == 0) {
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+  } else if (p.tile_mode == 1) {
+    t = t - floorf(t);
+  } else if (p.tile_mode == 2) {
+    double t1 = (double)(t - 1);
+    t = fabsf((float)(t1 - 2 * floor((double)(t - 1) * 0.5) - 1));
+  }
+  int n = (int)p.n_colors;
+  float step = 1.f / (n - 1);
+  int si = 0, ei = 1;
+  float start = 0.f, end = 0.f;
+  int i = 0;
+  bool first = p.has_stops && t <= stops[0];
+  if (!first) {
+    for (i = 0; i < n - 1; i++) {
+      if (p.has_stops) { start = stops[i]; end = stops[i + 1]; }
+      else { start = step * i; end = step * (i + 1); }
+      if (t >= start && t <= end) { si = i; ei = i + 1; break; }
+    }
+  }
+  float c[4];
+  if (first) {
+    for (int k = 0; k < 4; k++) c[k] = colors[k];
+  } else if (i == n - 1 && n > 0) {
+    for (int k = 0; k < 4; k++) c[k] = colors[4 * (n - 1) + k];
+  } else {
+    float total = end - start, value = t - start, mix = 0.5f;
+    if (total > 0) mix = value / total;
+    for (int k = 0; k < 4; k++) c[k] = colors[4 * si + k] * (1 - mix) + colors[4 * ei + k] * mix;
+  }
+  return color4f_to_pm_word(c[0], c[1], c[2], c[3]);
+}
+
+// u8 -> float -> u8 round trip of the nearest sampler (Color4fFromColor, Color4fToColor; color.cc:44-59)
+SKB_HD uint32_t requant(uint32_t c) {
+  float f = (float)c / 255.f;
+  return unit_to_byte(f);
+}
+
+struct SurfaceView { const uint8_t* px; uint32_t w, h, pitch; };  // pitch in bytes
+
+// Source colour of paint `p` at pixel centre (x+.5, y+.5): premultiplied pixel word.
+// Solid sw_span_brush.cc:140-152, Linear :312-320, Sweep :337-354, Radial :371-379,
+// Pixmap :569-579 + bitmap_sampler.cc:26-40,85-108.
+// `img` is the surface an IMAGE paint samples (ignored by the other paint types).
+SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const SurfaceView& img, int x, int y) {
+  if (p.type == SKB_PAINT_SOLID) return color4f_to_pm_word(p.color[0], p.color[1], p.color[2], p.color[3]);
+  float fxc = x + 0.5f, fyc = y + 0.5f;
+  float u = fxc * p.m[0] + fyc * p.m[1] + p.m[2];
+  float v = fxc * p.m[3] + fyc * p.m[4] + p.m[5];
+  switch (p.type) {
+    case SKB_PAINT_LINEAR:
+      return gradient_color(p, pool, u);
+    case SKB_PAINT_RADIAL:
+      return gradient_color(p, pool, sqrtf(u * u + v * v));
+    case SKB_PAINT_SWEEP: {
+      float angle = atan2f(-v, -u);
+      const float k1Over2Pi = 0.1591549430918f;
+      float t = (float)(((double)(angle * k1Over2Pi) + 0.5 + (double)p.bias) * (double)p.scale);
+      return gradient_color(p, pool, t);
+    }
+    case SKB_PAINT_IMAGE: {
+      const SurfaceView& s = img;
+      if (u < 0.0f || u >= 1.0f || v < 0.0f || v >= 1.0f) return 0;
+      float px = u * (float)s.w, py = v * (float)s.h;
+      uint32_t ix = (uint32_t)px, iy = (uint32_t)py;
+      if (ix > s.w - 1) ix = s.w - 1;
+      if (iy > s.h - 1) iy = s.h - 1;
+      const uint8_t* t = s.px + (size_t)iy * s.pitch + (size_t)ix * 4;
+      return requant(t[0]) | (requant(t[1]) << 8) | (requant(t[2]) << 16) | (requant(t[3]) << 24);
+    }
+    default:
+      return 0;
+  }
+}
+
+// SWStackBlur reciprocal (sw_stack_blur.cc:286-338): shr = max s with 2^s/(r+1)^2 <= 512, mul = ceil(2^s/(r+1)^2)
+SKB_HD void blur_mul_shr(int radius, uint32_t* mul, int* shr) {
+  uint64_t d = (uint64_t)(radius + 1) * (uint64_t)(radius + 1);
+  int s = 0;
+  while ((1ull << (s + 1)) <= 512ull * d) s++;
+  *shr = s;
+  *mul = (uint32_t)(((1ull << s) + d - 1) / d);
+}
+
+}  // namespace skb
+
+#endif  // SKB_CORE_CUH

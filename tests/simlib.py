@@ -1,0 +1,39 @@
+"""Builds and binds tests/sim/sim_core.cc — the CPU simulation of the CUDA stages' per-thread code."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_REPO = os.path.dirname(_HERE)
+_SRC = os.path.join(_HERE, "sim", "sim_core.cc")
+_LIB = os.path.join(_HERE, "sim", "libskb_sim.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [_SRC] + [os.path.join(_REPO, "skity_b200", "csrc", f) for f in
+                         ("skb_core.cuh", "skb_walk.cuh", "skb_stages.cuh")] + [os.path.join(_REPO, "include", "skb_dl.h")]
+        if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                                   f"-I{_REPO}", _SRC, "-o", _LIB])
+        _lib = ctypes.CDLL(_LIB)
+        _lib.sim_path_cover.restype = ctypes.c_long
+        _lib.sim_path_cover.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    return _lib
+
+
+def path_cover(segs, ctm, clip, even_odd, w, h):
+    segs = np.ascontiguousarray(segs)
+    m = np.asarray(ctm, dtype=np.float32)
+    c = np.asarray(clip, dtype=np.float32)
+    d = np.zeros((h, w), dtype=np.uint8)
+    a = np.zeros((h, w), dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.int64)
+    n = lib().sim_path_cover(segs.ctypes.data, len(segs), m.ctypes.data, c.ctypes.data, int(even_odd), w, h,
+                             d.ctypes.data, a.ctypes.data, stats.ctypes.data)
+    return d, a, int(n), stats
