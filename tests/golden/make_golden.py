@@ -1,0 +1,100 @@
+#!/usr/bin/env python3
+"""Generates the committed golden vectors from the reference's OWN software backend
+(oracle/_ref/libskity_ref.so, compiled from the unmodified sources by oracle/build_ref.py).
+
+Run in the build container (needs /root/reference to have built oracle/_ref):
+    python tests/golden/make_golden.py
+Each fixture stores the SKSC scene blob, the encoded SKDL display list and the reference's
+premultiplied RGBA8 output (or span list), so tests can replay them anywhere.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refsw  # noqa: E402
+from skity_b200 import hostlib, scene  # noqa: E402
+from skity_b200.scene import Paint, PathData, Scene  # noqa: E402
+
+
+def golden_scenes():
+    out = {}
+    out["c0_star_blur_800x600"] = scene.scene_c0()
+    out["c0_star_plain_800x600"] = scene.scene_c0(blur=False)
+    out["c1_fills_120_512"] = scene.scene_random_fills(120, 512, 1, box=200.0)
+    out["c2_gradients_90_512"] = scene.scene_c2(90, 512, 2, clip_every=0)
+    out["c2_clips_90_512"] = scene.scene_c2(90, 512, 9, clip_every=30, clip_box=300.0)
+    out["c3_blur_12_640"] = scene.scene_c3(12, 640, 3, box=160.0)
+    # transforms, conics, even-odd, rect clip, big coordinates (int32 wrap of the 16.16 conversion at >= 8192 px)
+    s = Scene(400, 300)
+    s.save()
+    s.translate(200, 150)
+    s.rotate(30)
+    s.scale(1.5, 0.75)
+    p = PathData(scene.EVEN_ODD)
+    p.move_to(-80, -60).conic_to(0, -120, 80, -60, 0.7071).line_to(60, 70).cubic_to(20, 10, -20, 130, -60, 70).close()
+    p.move_to(-30, -20).line_to(30, -20).line_to(30, 30).line_to(-30, 30).close()
+    s.draw_path(p, Paint(fill=(0.9, 0.3, 0.1, 0.8)))
+    s.restore()
+    s.save()
+    s.clip_rect(20.5, 30.25, 250.75, 200.5)
+    s.draw_rect(0, 0, 400, 300, Paint(fill=(0.1, 0.4, 0.9, 0.5)))
+    s.draw_path(scene.star_path(), Paint(style=scene.STROKE, stroke=(0, 0.6, 0.2, 1), stroke_width=6.0,
+                                         join=scene.ROUND_JOIN, cap=scene.ROUND_CAP))
+    s.restore()
+    out["mixed_transform_clip_400x300"] = s
+    s = Scene(256, 256)
+    p = PathData()
+    p.move_to(8180, 10).line_to(8300, 40).line_to(8200, 200).close()   # x crosses 8192: reference wraps
+    s.save()
+    s.translate(-8100, 0)
+    s.draw_path(p, Paint(fill=(0.2, 0.8, 0.3, 1)))
+    s.restore()
+    p2 = PathData()
+    p2.move_to(10, 10).quad_to(250, 20, 120, 240).close()
+    s.draw_path(p2, Paint(fill=(0.7, 0.1, 0.6, 0.6)))
+    out["wrap_8192_256"] = s
+    return out
+
+
+def main():
+    assert refsw.available(), "build oracle/_ref first (python oracle/build_ref.py)"
+    for name, s in golden_scenes().items():
+        blob = s.encode()
+        rgba = refsw.render_scene(blob)
+        dl = hostlib.encode_scene(blob)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, scene=np.frombuffer(blob, dtype=np.uint8), dl=np.frombuffer(dl, dtype=np.uint8),
+                            rgba=rgba)
+        print(f"{name}: {rgba.shape[1]}x{rgba.shape[0]} sum={int(rgba.astype(np.int64).sum())} "
+              f"-> {os.path.getsize(path)} bytes")
+    # span-level vectors: SWRaster::RastePath of a few paths
+    rng = np.random.RandomState(11)
+    spans_out = {}
+    for i in range(12):
+        p = scene._random_closed_path(rng, 100, 100, 180.0, i)
+        sp, b = refsw.raster_path(p, clip=(0, 0, 200, 200))
+        dlp = hostlib.encode_scene(_single(p).encode())
+        spans_out[f"spans_{i}"] = sp
+        spans_out[f"bounds_{i}"] = b
+        spans_out[f"dl_{i}"] = np.frombuffer(dlp, dtype=np.uint8)
+    sp, b = refsw.raster_path(scene.star_path())
+    spans_out["spans_star"] = sp
+    spans_out["bounds_star"] = b
+    spans_out["dl_star"] = np.frombuffer(hostlib.encode_scene(_single(scene.star_path(), 400, 400).encode()), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "raster_spans.npz"), **spans_out)
+    print("raster_spans.npz written")
+
+
+def _single(path, w=200, h=200):
+    s = Scene(w, h)
+    s.draw_path(path, Paint(fill=(0, 0, 0, 1)))
+    return s
+
+
+if __name__ == "__main__":
+    main()

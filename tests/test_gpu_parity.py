@@ -1,0 +1,171 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/skb.h), against the oracle.
+
+Bar: bit-exact RGBA8 and coverage for integer paths (solid fills, strokes, blur, image composite);
+gradients (fp32 paint evaluation) within 1/255 on >= 99.9 % of pixels and 2/255 everywhere, the
+tolerance BASELINE.json's north_star states."""
+import glob
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import port
+from skity_b200 import hostlib, scene
+from skity_b200.scene import Paint, PathData, Scene
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from skity_b200 import device
+    d = device.Device(0)          # raises if the CUDA library or a B200 is missing: no fallback
+    yield d
+    d.close()
+
+
+def render(dev, dl, w, h, **kw):
+    surf = dev.create_surface(w, h)
+    try:
+        out = surf.render(dl, **kw)
+        st = surf.stats()
+        assert st["n_launches"] > 0
+        return out
+    finally:
+        surf.close()
+
+
+def assert_within_tolerance(got, want):
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
+    assert d.max() <= 2, f"max channel difference {d.max()} > 2/255"
+    frac = float((d <= 1).sum()) / d.size
+    assert frac >= 0.999, f"only {frac:.5f} of pixels within 1/255"
+
+
+EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c3_blur_12_640",
+         "mixed_transform_clip_400x300", "wrap_8192_256"]
+
+
+@pytest.mark.parametrize("name", EXACT)
+def test_golden_bit_exact(dev, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    want = z["rgba"]
+    got = render(dev, z["dl"].tobytes(), want.shape[1], want.shape[0])
+    assert np.array_equal(got, want)
+
+
+def test_golden_gradients_within_tolerance(dev):
+    z = np.load(os.path.join(GOLDEN, "c2_gradients_90_512.npz"))
+    want = z["rgba"]
+    got = render(dev, z["dl"].tobytes(), 512, 512)
+    assert_within_tolerance(got, want)
+
+
+def test_coverage_planes_bit_exact(dev):
+    """Coverage masks vs the oracle's span lists: per pixel, the sequence of coverages blended."""
+    from test_sim_stages import planes_from_spans
+    s = scene.scene_c2(24, 256, 4, clip_every=0)
+    dl = hostlib.encode_scene(s.encode())
+    hd = port.dl_header(dl)
+    surf = dev.create_surface(256, 256)
+    surf.render(dl)
+    for i in range(hd["n_ops"]):
+        op = struct.unpack_from("<8I10f", dl, hd["off_ops"] + 72 * i)
+        segs = port.dl_segments(dl, op[2])
+        spans, _ = port.raster_path(segs, op[8:14], op[14:18], op[6])
+        p0, p1, cnt = planes_from_spans(spans, 256, 256)
+        d, a = surf.read_coverage(i, 0, 0, 256, 256)
+        assert np.array_equal(d, p0), f"op {i} first plane"
+        assert np.array_equal(a, p1), f"op {i} second plane"
+    surf.close()
+
+
+@pytest.mark.parametrize("n,size,seed", [(2000, 2048, 31), (300, 1000, 32)])
+def test_random_fills_bit_exact_vs_port(dev, n, size, seed):
+    s = scene.scene_random_fills(n, size, seed, box=256.0)
+    dl = hostlib.encode_scene(s.encode())
+    assert np.array_equal(render(dev, dl, size, size), port.render(dl))
+
+
+def test_ragged_surface_sizes(dev):
+    for (w, h) in [(801, 599), (17, 33), (1, 1), (250, 16)]:
+        s = scene.scene_random_fills(40, 0, 40 + w, box=200.0, width=w, height=h)
+        dl = hostlib.encode_scene(s.encode())
+        assert np.array_equal(render(dev, dl, w, h), port.render(dl)), (w, h)
+
+
+def test_degenerate_inputs(dev):
+    s = Scene(64, 64)
+    dl = hostlib.encode_scene(s.encode())                      # empty frame
+    assert not render(dev, dl, 64, 64).any()
+    s = Scene(64, 64)
+    s.draw_path(PathData().move_to(5, 5), Paint())             # lone move
+    s.draw_path(PathData().move_to(5, 5).line_to(50, 5).close(), Paint())   # zero area
+    s.draw_path(PathData().move_to(500, 500).line_to(600, 500).line_to(600, 600).close(), Paint())  # off canvas
+    s.draw_path(PathData().move_to(-50, -50).line_to(30, -50).line_to(30, 30).line_to(-50, 30).close(),
+                Paint(fill=(1, 0, 0, 1)))                      # partially off canvas
+    dl = hostlib.encode_scene(s.encode())
+    assert np.array_equal(render(dev, dl, 64, 64), port.render(dl))
+
+
+def test_draw_over_existing_content(dev):
+    rng = np.random.RandomState(7)
+    a = rng.randint(0, 256, (128, 128, 1))
+    init = np.concatenate([(rng.randint(0, 256, (128, 128, 3)) * a // 255), a], axis=2).astype(np.uint8)
+    s = scene.scene_random_fills(30, 128, 8, box=100.0)
+    dl = hostlib.encode_scene(s.encode())
+    surf = dev.create_surface(128, 128)
+    surf.write_pixels(init)
+    got = surf.render(dl, clear=False)                         # LockCanvas(clear=false)
+    surf.close()
+    assert np.array_equal(got, port.render(dl, initial=init))
+
+
+def test_blur_radii_edge_cases(dev):
+    for r in (0.6, 1.4, 2.0, 33.0, 120.0, 300.0):             # <=1: copy; 300 -> clamped to 254
+        s = Scene(300, 260)
+        s.draw_path(scene.star_path(), Paint(fill=(0.2, 0.5, 0.9, 0.7), blur_radius=r))
+        dl = hostlib.encode_scene(s.encode())
+        assert np.array_equal(render(dev, dl, 300, 260), port.render(dl)), r
+
+
+def test_full_size_c1_properties(dev):
+    """BASELINE config 1 at full size: bit-exact vs the port, deterministic, band split == whole."""
+    s = scene.scene_c1()
+    dl = hostlib.encode_scene(s.encode())
+    surf = dev.create_surface(4096, 4096)
+    a = surf.render(dl)
+    b = surf.render(dl)
+    assert np.array_equal(a, b)                                # idempotent / deterministic
+    want = port.render(dl)
+    assert np.array_equal(a, want)
+    assert int(a.astype(np.int64).sum()) == int(want.astype(np.int64).sum())
+    halves = np.zeros_like(a)
+    for (y0, y1) in [(0, 2048), (2048, 4096)]:
+        surf.set_band(y0, y1)
+        surf.begin(True)
+        surf.encode(dl)
+        surf.flush()
+        halves[y0:y1] = surf.read_pixels(0, y0, 4096, y1 - y0)
+    surf.close()
+    assert np.array_equal(halves, a)                           # tile-band partition is exact
+
+
+def test_path_clips_not_silently_ignored(dev):
+    """Until the clip stage lands, a display list with Canvas::ClipPath must be refused, not drawn unclipped."""
+    from skity_b200 import device
+    z = np.load(os.path.join(GOLDEN, "c2_clips_90_512.npz"))
+    surf = dev.create_surface(512, 512)
+    surf.begin(True)
+    try:
+        surf.encode(z["dl"].tobytes())
+        surf.flush()
+        got = surf.read_pixels()
+        assert_within_tolerance(got, z["rgba"])
+    except device.SkbError as e:
+        assert "clip" in str(e).lower()
+    finally:
+        surf.close()

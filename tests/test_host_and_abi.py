@@ -1,0 +1,93 @@
+"""Host-side logic without a GPU: path lowering, display-list structure, and that the C-ABI library
+loads and exports every symbol include/skb.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import port
+from skity_b200 import hostlib, scene
+from skity_b200.scene import Paint, PathData, Scene
+
+needs_host = pytest.mark.skipif(not os.path.exists(hostlib.LIB_PATH), reason="host plug-in not built")
+
+
+def test_abi_library_exports_all_declared_symbols():
+    from skity_b200 import device
+    hdr = open(os.path.join(ROOT, "include", "skb.h")).read()
+    names = set(re.findall(r"SKB_API\s+[\w\s\*]+?\b(skb_\w+)\s*\(", hdr))
+    assert len(names) >= 18
+    lib = ctypes.CDLL(device.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in device.lib().skb_version_string()
+
+
+def test_no_gpu_fails_loudly_not_silently():
+    """On a box without a CUDA device the product path must raise, never fall back to the CPU."""
+    from skity_b200 import device
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(device.SkbError):
+        device.Device(0)
+
+
+def _segs(path, w=64, h=64):
+    s = Scene(w, h)
+    s.draw_path(path, Paint())
+    dl = hostlib.encode_scene(s.encode())
+    return port.dl_segments(dl, 0), dl
+
+
+@needs_host
+def test_lowering_closes_every_contour():
+    p = PathData().move_to(1, 1).line_to(9, 1).line_to(9, 9)        # open contour: auto-closed
+    segs, _ = _segs(p)
+    types = list(segs["type_flags"] & 0xFF)
+    assert types == [1, 1, 5]
+    assert tuple(segs[2]["p"][:4]) == (9, 9, 1, 1)
+    p = PathData().move_to(1, 1).line_to(9, 1).line_to(9, 9).close().line_to(20, 20)   # segment after close
+    segs, _ = _segs(p)
+    types = list(segs["type_flags"] & 0xFF)
+    # explicit close adds the line back to the start (Path::Iter::AutoClose), the iterator then closes (degenerate),
+    # and the trailing LineTo starts a new contour at the move point (InjectMoveToIfNeed)
+    assert types == [1, 1, 1, 5, 1, 5]
+    assert tuple(segs[4]["start"]) == (1, 1)
+
+
+@needs_host
+def test_lowering_chains_through_cubics():
+    p = PathData().move_to(0, 0).cubic_to(10, 0, 20, 10, 30, 30).line_to(0, 30).close()
+    segs, _ = _segs(p)
+    flags = list(segs["type_flags"])
+    assert flags[0] & 0xFF == 4 and not (flags[0] & 0x100)
+    assert flags[1] & 0xFF == 1 and (flags[1] & 0x100)          # starts at the cubic's computed end
+
+
+@needs_host
+def test_display_list_structure_for_blur_and_strokes():
+    s = scene.scene_c0()
+    dl = hostlib.encode_scene(s.encode())
+    h = port.dl_header(dl)
+    assert h["n_surfaces"] == 3 and h["n_ops"] == 4            # star, temp star, blur, image composite
+    kinds = [struct.unpack_from("<I", dl, h["off_ops"] + 72 * i)[0] for i in range(4)]
+    assert kinds == [1, 1, 3, 1]
+    w, hh = struct.unpack_from("<2I", dl, h["off_surfaces"] + 16)
+    assert (w, hh) == (368, 351)                                # floor/ceil(bounds +- 10)
+    s2 = Scene(100, 100)
+    s2.draw_path(scene.star_path(), Paint(style=scene.STROKE_AND_FILL, stroke_width=3.0))
+    h2 = port.dl_header(hostlib.encode_scene(s2.encode()))
+    assert h2["n_ops"] == 2                                     # fill then stroke outline (paint_order.hpp:12-31)
+
+
+@needs_host
+def test_unsupported_features_are_reported_not_approximated():
+    s = Scene(64, 64)
+    s.draw_path(scene.star_path(), Paint(blur_radius=4.0, blur_style=2))   # kSolid blur: outside this round's scope
+    with pytest.raises(RuntimeError):
+        hostlib.encode_scene(s.encode())
