@@ -698,6 +698,10 @@ __global__ void k_read_coverage(CoverArgs c, uint32_t op, int x, int y, uint32_t
         // masks do not say which span kind produced a lone value; report it as `direct`
         dv = c.mask0[(size_t)item * 256 + ly * 16 + lx];
         if (f & SKB_ITEM_PLANE1) av = c.mask1[(size_t)item * 256 + ly * 16 + lx];
+        if (dv == 0 && av != 0) {  // report the blend SEQUENCE: zero coverage is never blended
+          dv = av;
+          av = 0;
+        }
       }
     }
   }
@@ -1296,7 +1300,7 @@ skb_result skb_frame_begin(skb_surface s, int clear) {
   if (!s) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   if (clear) SKB_CUDA(cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream));
-  s->have_frame = false;
+  // the last encoded display list stays resident: a frame may be flushed again without re-uploading it
   s->flushed = false;
   return SKB_SUCCESS;
 }

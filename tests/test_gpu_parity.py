@@ -32,7 +32,7 @@ def render(dev, dl, w, h, **kw):
     try:
         out = surf.render(dl, **kw)
         st = surf.stats()
-        assert st["n_launches"] > 0
+        assert st["n_launches"] > 0 or st["n_ops"] == 0
         return out
     finally:
         surf.close()
