@@ -159,7 +159,7 @@ __global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt) {
 // One thread per lowered primitive: resolve (segment, k) from the scanned counts, evaluate and
 // transform its control points, fold them into the path bounds, emit its 0..2 edges.
 __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_prims, const uint32_t* seg_op, OpGeom* geom,
-                          Edge* edges) {
+                          Edge* edges, QuadState* quads) {
   uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
   if (prim >= n_prims) return;
   uint32_t seg = find_interval(prim_off, t.n_segs, prim);
@@ -176,10 +176,13 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
     atomicMin(&g->bmin_y, ky); atomicMax(&g->bmax_y, ky);
   }
   Edge slot[2];
-  flatten_prim(np, p, slot);
-  Edge* dst = edges + (size_t)2 * prim + (size_t)2 * op + 2;
-  dst[0] = slot[0];
-  dst[1] = slot[1];
+  QuadState qslot[2];
+  flatten_prim(np, p, slot, qslot);
+  const size_t at = (size_t)2 * prim + (size_t)2 * op + 2;
+  edges[at] = slot[0];
+  edges[at + 1] = slot[1];
+  if ((slot[0].curve >> 25) & 1) quads[at] = qslot[0];
+  if ((slot[1].curve >> 25) & 1) quads[at + 1] = qslot[1];
 }
 
 // ------------------------------------------------------------------- stage 2: setup
@@ -225,26 +228,67 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
 }
 
 // -------------------------------------------------------------------- stage 3: walk
-__global__ void __launch_bounds__(64) k_walk(FrameTables t, OpGeom* geom, const uint32_t* row_base, Edge* edges, int32_t* ord,
-                                             TrapRec* pool, uint32_t* pool_next, uint32_t pool_cap, uint32_t* overflow,
-                                             uint2* rows) {
+// One thread sweeps one path.  The sweep is a long chain of dependent, branchy integer work, so a
+// warp of 32 different paths serialises heavily.  When a frame has far fewer paths than the GPU has
+// thread slots, the paths are therefore SPREAD: only every (32/lanes)-th lane of a warp carries a
+// path, which cuts the divergence per warp and multiplies the number of warps the schedulers can
+// interleave.  k_walk_list first compacts the non-empty ops into a list.
+__global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, uint32_t* list) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const OpGeom g = geom[op];
   if (g.empty || g.ntx == 0 || g.nty == 0) return;
-  RecSink sink;
-  sink.pool = pool;
-  sink.pool_next = pool_next;
-  sink.pool_cap = pool_cap;
-  sink.overflow = overflow;
-  sink.rows = rows + row_base[op];
+  // warp-aggregated append
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  list[base + __popc(m & ((1u << lane) - 1))] = op;
+}
+
+struct WalkArgs {
+  FrameTables t;
+  const OpGeom* geom;
+  const uint32_t* row_base;
+  Edge* edges;
+  QuadState* quads;
+  int32_t* ord;
+  TrapRec* pool;
+  uint32_t* pool_next;
+  uint32_t pool_cap;
+  uint32_t* overflow;
+  uint2* rows;
+  const uint32_t* list;   // ops of this class
+  const uint32_t* count;  // how many
+};
+
+__device__ __forceinline__ void walk_setup_sink(const WalkArgs& a, uint32_t op, const OpGeom& g, RecSink& sink) {
+  sink.pool = a.pool;
+  sink.pool_next = a.pool_next;
+  sink.pool_cap = a.pool_cap;
+  sink.overflow = a.overflow;
+  sink.rows = a.rows + a.row_base[op];
   sink.row0 = g.ty0 * SKB_TILE;
   sink.n_rows = g.nty * SKB_TILE;
   sink_init(sink);
-  // rows below the last tile row are never read: stop the sweep there (rows are independent of later ones)
+}
+
+__global__ void __launch_bounds__(64) k_walk(WalkArgs a, int lane_stride) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid % (uint32_t)lane_stride) return;
+  const uint32_t i = tid / (uint32_t)lane_stride;
+  if (i >= *a.count) return;
+  const uint32_t op = a.list[i];
+  const OpGeom g = a.geom[op];
+  if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  RecSink sink;
+  walk_setup_sink(a, op, g, sink);
+  // rows below the last tile row are never read: stop the sweep there (rows do not depend on later ones)
   int stop_y = min(g.stop_y, sink.row0 + sink.n_rows);
-  walk_path(edges + g.slot_base, (int)g.n_slots, ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
-            g.left_clip, g.right_clip, (int)t.ops[op].fill_type, sink);
+  walk_path(a.edges + g.slot_base, a.quads + g.slot_base, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f,
+            g.scan_bottom_f, g.start_y, stop_y, g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink);
 }
 
 // ---------------------------------------------------------------- stage 4: coverage
@@ -254,7 +298,7 @@ struct CoverArgs {
   const OpGeom* geom;
   const uint32_t* item_base;  // n_ops + 1
   const uint32_t* row_base;
-  uint32_t n_ops, n_items;
+  uint32_t n_ops, n_items, n_trows;
   const skb_dl_op* ops;
   const SurfDesc* surfs;
   const TrapRec* pool;
@@ -268,10 +312,9 @@ struct CoverArgs {
 #define SKB_ITEM_SOLID 2u
 #define SKB_ITEM_PLANE1 4u
 
-__device__ __forceinline__ void cover_row8(const TrapRec* __restrict__ pool, uint2 row, int x0, int xmin, int xmax, uint32_t d[8],
-                                           uint32_t a[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
+// Generic (slow) evaluation of 8 pixels of a row: every record re-read and re-prepared.
+__device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool, uint2 row, int x0, int xmin, int xmax,
+                                                uint32_t d[8], uint32_t a[8]) {
   uint32_t idx = row.x;
   for (uint32_t k = 0; k < row.y; k++, idx++) {
     TrapRec r = pool[idx];
@@ -279,88 +322,161 @@ __device__ __forceinline__ void cover_row8(const TrapRec* __restrict__ pool, uin
       idx = (uint32_t)r.y;
       r = pool[idx];
     }
-    int e0, e1;
-    trap_extent(r, &e0, &e1);
-    if (e1 <= x0 || e0 >= x0 + 8) continue;
-    const uint32_t full = r.flags & 0xFF;
-    const bool direct = full == 0xFF && !((r.flags >> 8) & 1);
-#pragma unroll
+    const TrapPrep pr = trap_prepare(r);
+    if (pr.mode == 0 || pr.R <= x0 || pr.L >= x0 + 8) continue;
+#pragma unroll 1
     for (int j = 0; j < 8; j++) {
       int x = x0 + j;
       uint8_t v;
-      if (x >= xmin && x < xmax && trap_alpha_at(r, x, &v)) {
-        if (direct) d[j] = v; else a[j] += v;
+      if (x >= xmin && x < xmax && trap_prep_alpha(pr, x, &v)) {
+        if (!pr.accum) d[j] = v; else a[j] += v;
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; j++) a[j] = a[j] > 255u ? 255u : a[j];
 }
 
+// Range summary of one record kept in registers across the tiles of a row.
+struct RecRange {
+  int L, R, jl, jr;   // pixels [L,R) get a value, [jl,jr) get `full`
+  uint32_t idx;       // record index in the pool
+  uint32_t full_accum;  // full | accum << 8 | live << 9
+};
+#define COVER_RMAX 4
+
+// One warp per (op, tile row): lane L owns pixel row L>>1 of the tile row and the 8-pixel half L&1 of
+// every tile.  The lane's trapezoid rows are loaded and summarised ONCE, then every tile in the
+// covered x-range is classified (empty / solid / partial) with range tests; only pixels under a
+// slanted edge run the triangle/ramp formulas.  A tile's A8 mask is one coalesced 256-byte store.
 __global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
-  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t trow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (item >= c.n_items) return;
-  const uint32_t op = find_interval(c.item_base, c.n_ops, item);
+  if (trow >= c.n_trows) return;
+  const uint32_t op = find_interval(c.row_base, c.n_ops, trow * SKB_TILE);
   const OpGeom g = c.geom[op];
-  const uint32_t local = item - c.item_base[op];
-  const int tx = g.tx0 + (int)(local % (uint32_t)g.ntx);
-  const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
-  const SurfDesc sd = c.surfs[c.ops[op].surface];
+  const uint32_t tr = trow - c.row_base[op] / SKB_TILE;
+  const int ty = g.ty0 + (int)tr;
+  const skb_dl_op o = c.ops[op];
+  const SurfDesc sd = c.surfs[o.surface];
   const int y = ty * SKB_TILE + (lane >> 1);
-  const int x0 = tx * SKB_TILE + (lane & 1) * 8;
-  uint32_t d[8], a[8];
   const int xmax = min(g.scan_r, (int)sd.w);
   const int xmin = max(g.scan_l, 0);
-  if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) {
-    uint2 row = c.rows[c.row_base[op] + (uint32_t)(y - g.ty0 * SKB_TILE)];
-    cover_row8(c.pool, row, x0, xmin, xmax, d, a);
-  } else {
+  uint2 row = make_uint2(0u, 0u);
+  if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)(lane >> 1)];
+
+  RecRange rr[COVER_RMAX];
+  int lo = INT_MAX, hi = INT_MIN;
+  {
+    uint32_t idx = row.x;
+    for (uint32_t k = 0; k < row.y; k++, idx++) {
+      TrapRec r = c.pool[idx];
+      if (r.flags & SKB_REC_LINK) {
+        idx = (uint32_t)r.y;
+        r = c.pool[idx];
+      }
+      const TrapPrep pr = trap_prepare(r);
+      if (pr.mode != 0 && pr.R > pr.L) {
+        lo = min(lo, pr.L);
+        hi = max(hi, pr.R);
+      }
+      if (k < COVER_RMAX) {
+        rr[k].L = pr.L; rr[k].R = pr.mode ? pr.R : pr.L; rr[k].jl = pr.jl; rr[k].jr = pr.jr;
+        rr[k].idx = idx;
+        rr[k].full_accum = pr.full | (pr.accum ? 0x100u : 0u);
+      }
+    }
+  }
+  const bool generic = row.y > COVER_RMAX;
+  const int nrec = row.y > COVER_RMAX ? COVER_RMAX : (int)row.y;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+  }
+  lo = max(lo, xmin);
+  hi = min(hi, xmax);
+  if (hi <= lo) return;  // nothing in this tile row (item flags were zeroed)
+  const int tx_begin = max(g.tx0, lo / SKB_TILE);
+  const int tx_end = min(g.tx0 + g.ntx, (hi + SKB_TILE - 1) / SKB_TILE);
+  const uint32_t item_row = c.item_base[op] + tr * (uint32_t)g.ntx;
+  const bool is_fill = o.kind == SKB_OP_FILL;
+
+  for (int tx = tx_begin; tx < tx_end; tx++) {
+    const int x0 = tx * SKB_TILE + (lane & 1) * 8;
+    uint32_t d[8], a[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
-  }
-  bool any = false, both = false, solid = true;
+    if (generic) {
+      cover_row8_generic(c.pool, row, x0, xmin, xmax, d, a);
+    } else {
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    any |= (d[j] | a[j]) != 0;
-    both |= d[j] != 0 && a[j] != 0;
-    solid &= d[j] == 255 && a[j] == 0;
-  }
-  any = __any_sync(0xffffffffu, any);
-  both = __any_sync(0xffffffffu, both);
-  solid = __all_sync(0xffffffffu, solid);
-  uint32_t flags = 0;
-  if (any) {
-    flags = SKB_ITEM_PLANE0;
+      for (int k = 0; k < COVER_RMAX; k++) {
+        if (k >= nrec) break;
+        const RecRange q = rr[k];
+        if (q.R <= x0 || q.L >= x0 + 8) continue;
+        const uint32_t full = q.full_accum & 0xFF;
+        const bool accum = (q.full_accum >> 8) & 1;
+        if (x0 >= q.jl && x0 + 8 <= q.jr && x0 >= xmin && x0 + 8 <= xmax) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (accum) a[j] += full; else d[j] = full;
+          }
+          continue;
+        }
+        // at least one pixel is under a slanted edge (or at the clip border): evaluate per pixel
+        const TrapPrep pr = trap_prepare(c.pool[q.idx]);
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+          int x = x0 + j;
+          uint8_t v;
+          if (x >= xmin && x < xmax && trap_prep_alpha(pr, x, &v)) {
+            if (accum) a[j] += v; else d[j] = v;
+          }
+        }
+      }
+    }
+    bool any = false, both = false, solid = true;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      a[j] = a[j] > 255u ? 255u : a[j];
+      any |= (d[j] | a[j]) != 0;
+      both |= d[j] != 0 && a[j] != 0;
+      solid &= d[j] == 255 && a[j] == 0;
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (!any) continue;
+    both = __any_sync(0xffffffffu, both);
+    solid = __all_sync(0xffffffffu, solid);
+    const uint32_t item = item_row + (uint32_t)(tx - g.tx0);
+    uint32_t flags = SKB_ITEM_PLANE0;
     if (solid) {
       flags |= SKB_ITEM_SOLID;
     } else {
-      uint32_t lo = 0, hi = 0;
+      uint32_t w0 = 0, w1 = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         uint32_t v0 = both ? d[j] : (d[j] | a[j]);
         uint32_t v1 = both ? d[j + 4] : (d[j + 4] | a[j + 4]);
-        lo |= v0 << (8 * j);
-        hi |= v1 << (8 * j);
+        w0 |= v0 << (8 * j);
+        w1 |= v1 << (8 * j);
       }
-      reinterpret_cast<uint2*>(c.mask0 + (size_t)item * 256)[lane] = make_uint2(lo, hi);
+      reinterpret_cast<uint2*>(c.mask0 + (size_t)item * 256)[lane] = make_uint2(w0, w1);
       if (both) {
         flags |= SKB_ITEM_PLANE1;
-        lo = hi = 0;
+        w0 = w1 = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          lo |= a[j] << (8 * j);
-          hi |= a[j + 4] << (8 * j);
+          w0 |= a[j] << (8 * j);
+          w1 |= a[j + 4] << (8 * j);
         }
-        reinterpret_cast<uint2*>(c.mask1 + (size_t)item * 256)[lane] = make_uint2(lo, hi);
+        reinterpret_cast<uint2*>(c.mask1 + (size_t)item * 256)[lane] = make_uint2(w0, w1);
       }
     }
-  }
-  if (lane == 0) {
-    c.item_flags[item] = (uint8_t)flags;
-    if (flags && c.ops[op].kind == SKB_OP_FILL) {
-      uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
-      atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
+    if (lane == 0) {
+      c.item_flags[item] = (uint8_t)flags;
+      if (is_fill) {
+        uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
+        atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
+      }
     }
   }
 }
@@ -739,7 +855,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
-  Buf dl, geom, seg_op, prim_cnt, edges, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -981,6 +1097,8 @@ static skb_result run_frame(skb_surface s) {
   const size_t n_slots = (size_t)2 * n_prims + (size_t)2 * n_ops + 2;
   S.n_edges_slots = (uint32_t)n_slots;
   SKB_TRY(buf_reserve(s->edges, n_slots * sizeof(Edge)));
+  SKB_TRY(buf_reserve(s->quads, n_slots * sizeof(QuadState)));
+  SKB_TRY(buf_reserve(s->walk_lists, (size_t)n_ops * 4 + 16));
   SKB_TRY(buf_reserve(s->ord, n_slots * 4));
   Edge* edges = (Edge*)s->edges.p;
 
@@ -988,7 +1106,7 @@ static skb_result run_frame(skb_surface s) {
   uint32_t pool_cap = 0;
   for (int attempt = 0;; attempt++) {
     if (n_prims) {
-      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges);
+      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, (QuadState*)s->quads.p);
       launches++;
     }
     if (attempt == 0) {
@@ -1026,9 +1144,32 @@ static skb_result run_frame(skb_surface s) {
     // ---- stage 3: walk
     SKB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
     if (n_rows) SKB_CUDA(cudaMemsetAsync(s->rows.p, 0, n_rows * sizeof(uint2), st));
-    k_walk<<<cdiv(n_ops, 64), 64, 0, st>>>(t, geom, row_base, edges, (int32_t*)s->ord.p, (TrapRec*)s->pool.p, counters, pool_cap,
-                                           counters + 1, (uint2*)s->rows.p);
-    launches++;
+    {
+      // counters: [0] pool_next, [1] overflow, [4] number of ops to sweep
+      k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p);
+      launches++;
+      WalkArgs wa;
+      wa.t = t;
+      wa.geom = geom;
+      wa.row_base = row_base;
+      wa.edges = edges;
+      wa.quads = (QuadState*)s->quads.p;
+      wa.ord = (int32_t*)s->ord.p;
+      wa.pool = (TrapRec*)s->pool.p;
+      wa.pool_next = counters;
+      wa.pool_cap = pool_cap;
+      wa.overflow = counters + 1;
+      wa.rows = (uint2*)s->rows.p;
+      wa.list = (const uint32_t*)s->walk_lists.p;
+      wa.count = counters + 4;
+      // spread paths over warps while the GPU has spare thread slots (about 16 warps per SM wanted)
+      int lane_stride = 1;
+      const uint64_t want_threads = (uint64_t)s->dev->sm_count * 16 * 32;
+      while (lane_stride < 8 && (uint64_t)n_ops * lane_stride * 2 <= want_threads) lane_stride *= 2;
+      if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
+      k_walk<<<cdiv((uint64_t)n_ops * lane_stride, 64), 64, 0, st>>>(wa, lane_stride);
+      launches++;
+    }
     uint32_t hc[2];
     SKB_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
     SKB_CUDA(cudaStreamSynchronize(st));
@@ -1052,6 +1193,7 @@ static skb_result run_frame(skb_surface s) {
   ca.row_base = row_base;
   ca.n_ops = n_ops;
   ca.n_items = (uint32_t)n_items;
+  ca.n_trows = (uint32_t)(n_rows / SKB_TILE);
   ca.ops = t.ops;
   ca.surfs = (const SurfDesc*)s->surfs.p;
   ca.pool = (const TrapRec*)s->pool.p;
@@ -1063,7 +1205,8 @@ static skb_result run_frame(skb_surface s) {
   SKB_CUDA(cudaMemsetAsync(s->tile_cnt.p, 0, (size_t)(n_tiles + 1) * 4, st));
   SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
   if (n_items) {
-    k_cover<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
+    SKB_CUDA(cudaMemsetAsync(s->item_flags.p, 0, n_items, st));
+    k_cover<<<cdiv((uint64_t)ca.n_trows * 32, 128), 128, 0, st>>>(ca);
     launches++;
   }
   cudaEventRecord(s->ev[4], st);
@@ -1269,7 +1412,7 @@ void skb_surface_destroy(skb_surface s) {
   if (!s) return;
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
+  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};

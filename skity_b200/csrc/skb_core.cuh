@@ -47,8 +47,21 @@ SKB_HD fx fx_add(fx a, fx b) { return (fx)((uint32_t)a + (uint32_t)b); }
 SKB_HD fx fx_sub(fx a, fx b) { return (fx)((uint32_t)a - (uint32_t)b); }
 SKB_HD fx fx_abs(fx v) { return v < 0 ? (fx)(0u - (uint32_t)v) : v; }
 SKB_HD fx fx_mul(fx a, fx b) { return (fx)(((int64_t)a * (int64_t)b) >> 16); }
-SKB_HD fx fx_div(fx n, fx d) {  // SWFixedDiv: 64-bit quotient clamped to +-0x7FFFFFFF
+SKB_HD fx fx_div(fx n, fx d) {  // SWFixedDiv: 64-bit quotient (truncating) clamped to +-0x7FFFFFFF
+#if defined(__CUDA_ARCH__) && !defined(SKB_NO_FAST_DIV)
+  // |n << 16| < 2^47 and |d| < 2^31: an FP64 quotient is within one of the exact integer quotient,
+  // one remainder check makes it exact — far cheaper than the emulated 64-bit integer division.
+  const bool neg = (n < 0) != (d < 0);
+  const uint64_t a = (uint64_t)(n < 0 ? -(int64_t)n : (int64_t)n) << 16;
+  const uint64_t b = (uint64_t)(d < 0 ? -(int64_t)d : (int64_t)d);
+  uint64_t qa = (uint64_t)__double2ull_rz(__ddiv_rn((double)a, (double)b));
+  int64_t r = (int64_t)(a - qa * b);
+  if (r < 0) qa--;
+  else if ((uint64_t)r >= b) qa++;
+  int64_t q = neg ? -(int64_t)qa : (int64_t)qa;
+#else
   int64_t q = (int64_t)((uint64_t)(int64_t)n << 16) / (int64_t)d;
+#endif
   if (q < (int64_t)SKB_FX_MIN) q = SKB_FX_MIN;
   if (q > (int64_t)SKB_FX_MAX) q = SKB_FX_MAX;
   return (fx)q;
@@ -77,12 +90,18 @@ SKB_HD int32_t f2i(float v) {
 }
 
 // ------------------------------------------------------------------------ edges
-// One active edge of the scan converter (SWEdge + SWQuadEdge, sw_edge.hpp:18-81), 80 bytes.
+// One edge of the scan converter, split by access frequency:
+//   Edge      (SWEdge, sw_edge.hpp:18-63)  — touched for every band; 40 bytes, small enough to keep
+//                                            a whole path's active list in shared memory
+//   QuadState (SWQuadEdge, sw_edge.hpp:65-81) — forward-difference state, touched only when an edge
+//                                            steps to its next chord; stays in global memory
 struct Edge {
   fx x, y, dx, dy, upper_x, upper_y, lower_y;
-  fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y, snapped_x, snapped_y;
-  int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24
+  int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24 | quadratic << 25
   int32_t prev, next;
+};
+struct QuadState {
+  fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y, snapped_x, snapped_y;
 };
 SKB_HD int edge_count(const Edge& e) { return e.curve & 0xFF; }
 SKB_HD int edge_shift(const Edge& e) { return (e.curve >> 8) & 0xFF; }
@@ -132,10 +151,10 @@ SKB_HD int set_line(Edge& e, float x0f, float y0f, float x1f, float y1f) {
 }
 
 // SWQuadEdge::UpdateQuad (sw_edge.cc:233-292)
-SKB_HDN int update_quad(Edge& e) {
+SKB_HDN int update_quad(Edge& e, QuadState& q) {
   int success = 0;
   int count = edge_count(e);
-  fx oldx = e.qx, oldy = e.qy, dx = e.qdx, dy = e.qdy;
+  fx oldx = q.qx, oldy = q.qy, dx = q.qdx, dy = q.qdy;
   fx newx = 0, newy = 0, nsx = 0, nsy = 0;
   const int shift = edge_shift(e);
   do {
@@ -144,36 +163,36 @@ SKB_HDN int update_quad(Edge& e) {
       newx = fx_add(oldx, dx >> shift);
       newy = fx_add(oldy, dy >> shift);
       if (fx_abs(dy >> shift) >= SKB_FX1 * 2) {
-        fx diffy = fx_sub(newy, e.snapped_y) >> 10;
-        slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
-        nsy = fx_min(e.q_last_y, fx_round_fx(newy));
+        fx diffy = fx_sub(newy, q.snapped_y) >> 10;
+        slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+        nsy = fx_min(q.q_last_y, fx_round_fx(newy));
         nsx = fx_sub(newx, fx_mul(slope, fx_sub(newy, nsy)));
       } else {
-        nsy = fx_min(e.q_last_y, snap_y(newy));
+        nsy = fx_min(q.q_last_y, snap_y(newy));
         nsx = newx;
-        fx diffy = fx_sub(nsy, e.snapped_y) >> 10;
-        slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+        fx diffy = fx_sub(nsy, q.snapped_y) >> 10;
+        slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
       }
-      dx = fx_add(dx, e.qddx);
-      dy = fx_add(dy, e.qddy);
+      dx = fx_add(dx, q.qddx);
+      dy = fx_add(dy, q.qddy);
     } else {
-      newx = e.q_last_x;
-      newy = e.q_last_y;
+      newx = q.q_last_x;
+      newy = q.q_last_y;
       nsy = newy;
       nsx = newx;
-      fx diffy = fx_sub(newy, e.snapped_y) >> 10;
-      slope = diffy ? fx_div(fx_sub(newx, e.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+      fx diffy = fx_sub(newy, q.snapped_y) >> 10;
+      slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
     }
-    if (slope < SKB_FX_MAX) success = update_line(e, e.snapped_x, e.snapped_y, nsx, nsy, slope);
+    if (slope < SKB_FX_MAX) success = update_line(e, q.snapped_x, q.snapped_y, nsx, nsy, slope);
     oldx = newx;
     oldy = newy;
   } while (count > 0 && !success);
-  e.qx = newx;
-  e.qy = newy;
-  e.qdx = dx;
-  e.qdy = dy;
-  e.snapped_x = nsx;
-  e.snapped_y = nsy;
+  q.qx = newx;
+  q.qy = newy;
+  q.qdx = dx;
+  q.qdy = dy;
+  q.snapped_x = nsx;
+  q.snapped_y = nsy;
   edge_set_count(e, count);
   return success;
 }
@@ -189,7 +208,7 @@ SKB_HD int diff_to_shift(fx dx, fx dy) {
 
 // SWQuadEdge::SetQuad (sw_edge.cc:121-231). p = x0 y0 x1 y1 x2 y2 of a y-monotone quad.
 // On success *first_y / *last_y receive q_first_y / q_last_y (used by CanBeIgnored).
-SKB_HDN int set_quad(Edge& e, const float* p, fx* first_y, fx* last_y) {
+SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* last_y) {
   fx x0 = f2i(p[0] * 256.0f), y0 = f2i(p[1] * 256.0f);
   fx x1 = f2i(p[2] * 256.0f), y1 = f2i(p[3] * 256.0f);
   fx x2 = f2i(p[4] * 256.0f), y2 = f2i(p[5] * 256.0f);
@@ -209,22 +228,22 @@ SKB_HDN int set_quad(Edge& e, const float* p, fx* first_y, fx* last_y) {
   edge_set_curve(e, 1 << shift, shift - 1, w);
   fx A = shl(fx_add(fx_sub(fx_sub(x0, x1), x1), x2), 9);
   fx B = shl(fx_sub(x1, x0), 10);
-  e.qx = shl(x0, 10) >> 2;
-  e.qdx = fx_add(B, A >> shift) >> 2;
-  e.qddx = (A >> (shift - 1)) >> 2;
+  q.qx = shl(x0, 10) >> 2;
+  q.qdx = fx_add(B, A >> shift) >> 2;
+  q.qddx = (A >> (shift - 1)) >> 2;
   A = shl(fx_add(fx_sub(fx_sub(y0, y1), y1), y2), 9);
   B = shl(fx_sub(y1, y0), 10);
-  e.qy = snap_y(shl(y0, 10) >> 2);
-  e.qdy = fx_add(B, A >> shift) >> 2;
-  e.qddy = (A >> (shift - 1)) >> 2;
-  e.q_last_x = shl(x2, 10) >> 2;
-  e.q_last_y = snap_y(shl(y2, 10) >> 2);
-  *first_y = e.qy;
-  *last_y = e.q_last_y;
-  e.snapped_x = e.qx;
-  e.snapped_y = e.qy;
+  q.qy = snap_y(shl(y0, 10) >> 2);
+  q.qdy = fx_add(B, A >> shift) >> 2;
+  q.qddy = (A >> (shift - 1)) >> 2;
+  q.q_last_x = shl(x2, 10) >> 2;
+  q.q_last_y = snap_y(shl(y2, 10) >> 2);
+  *first_y = q.qy;
+  *last_y = q.q_last_y;
+  q.snapped_x = q.qx;
+  q.snapped_y = q.qy;
   e.x = e.y = e.dx = e.dy = e.upper_x = e.upper_y = e.lower_y = 0;
-  update_quad(e);
+  update_quad(e, q);
   return 1;
 }
 
@@ -614,6 +633,102 @@ SKB_HDN bool trap_alpha_at(const TrapRec& r, int x, uint8_t* out) {
     return false;
   }
   return aaa_row_at(x, ul, ur, ll, lr, r.ldy, r.rdy, full, accum, out);
+}
+
+// ---- prepared form: normalise a record once, then evaluate many pixels cheaply ---------------
+// Most pixels of a trapezoid row are either outside it or in its fully covered interior; only the
+// few pixels under the two slanted edges need the triangle/ramp formulas.  trap_prepare() does the
+// per-record work of blit_trapezoid_row (swaps, join points) once; trap_prep_alpha() is then a
+// range test for interior/outside pixels and the edge formulas otherwise.  Results are identical
+// to trap_alpha_at() (checked exhaustively by the tests).
+struct TrapPrep {
+  fx ul, ur, ll, lr, ldy, rdy, join_left, join_rite;
+  int L, R;    // pixels [L, R) receive a value
+  int jl, jr;  // pixels [jl, jr) receive `full`
+  uint32_t full;
+  int mode;    // 0 nothing, 1 left part / interior / right part, 2 one anti-aliased row
+  bool accum;
+};
+
+SKB_HDN TrapPrep trap_prepare(const TrapRec& r) {
+  TrapPrep p;
+  fx ul = r.ul, ur = r.ur, ll = r.ll, lr = r.lr;
+  p.full = r.flags & 0xFF;
+  p.accum = !(p.full == 0xFF && !((r.flags >> 8) & 1));
+  p.ldy = r.ldy;
+  p.rdy = r.rdy;
+  p.mode = 0;
+  p.L = p.R = p.jl = p.jr = 0;
+  p.ul = p.ur = p.ll = p.lr = p.join_left = p.join_rite = 0;
+  if (ul > ur) return p;
+  if (ll > lr) {
+    fx l1 = ul, r1 = ll, l2 = ur, r2 = lr;
+    if (l1 > r1) { fx t = l1; l1 = r1; r1 = t; }
+    if (l2 > r2) { fx t = l2; l2 = r2; r2 = t; }
+    ll = lr = fx_add(fx_max(l1, l2), fx_min(r1, r2)) / 2;
+  }
+  if (ul == ur && ll == lr) return p;
+  if (ul > ll) { fx t = ul; ul = ll; ll = t; }
+  if (ur > lr) { fx t = ur; ur = lr; lr = t; }
+  p.ul = ul; p.ur = ur; p.ll = ll; p.lr = lr;
+  p.join_left = fx_ceil_fx(ll);
+  p.join_rite = fx_floor_fx(ur);
+  if (p.join_left <= p.join_rite) {
+    p.mode = 1;
+    p.jl = p.join_left >> 16;
+    p.jr = p.join_rite >> 16;
+    p.L = ul < p.join_left ? (ul >> 16) : p.jl;
+    p.R = lr > p.join_rite ? p.jr + fx_ceil_i(fx_sub(lr, p.join_rite)) : p.jr;
+  } else {
+    p.mode = 2;
+    p.L = fx_floor_i(ul);
+    p.R = fx_ceil_i(lr);
+    int lL = fx_ceil_i(ll), uR = fx_floor_i(ur);
+    if (p.R - p.L > 1 && lL < uR) {
+      p.jl = lL;
+      p.jr = uR;
+    } else {
+      p.jl = p.jr = p.L;
+    }
+  }
+  return p;
+}
+
+SKB_HDN bool trap_prep_alpha(const TrapPrep& p, int x, uint8_t* out) {
+  if (p.mode == 0 || x < p.L || x >= p.R) return false;
+  if (x >= p.jl && x < p.jr) {
+    *out = (uint8_t)p.full;
+    return true;
+  }
+  if (p.mode == 2) return aaa_row_at(x, p.ul, p.ur, p.ll, p.lr, p.ldy, p.rdy, p.full, p.accum, out);
+  if (x < p.jl) {
+    int len = p.jl - p.L;
+    if (len == 1) {
+      uint8_t a = trapezoid_to_alpha(fx_sub(p.join_left, p.ul), fx_sub(p.join_left, p.ll));
+      *out = p.accum ? partial_alpha_mul(a, p.full) : a;
+      return true;
+    }
+    if (len == 2) {
+      fx first = fx_sub(fx_sub(p.join_left, SKB_FX1), p.ul);
+      fx second = fx_sub(fx_sub(p.ll, p.ul), first);
+      *out = x == p.L ? partial_triangle_to_alpha(first, p.ldy) : (uint8_t)(p.full - partial_triangle_to_alpha(second, p.ldy));
+      return true;
+    }
+    return aaa_row_at(x, p.ul, p.join_left, p.ll, p.join_left, p.ldy, SKB_FX_MAX, p.full, p.accum, out);
+  }
+  int len = p.R - p.jr;
+  if (len == 1) {
+    uint8_t a = trapezoid_to_alpha(fx_sub(p.ur, p.join_rite), fx_sub(p.lr, p.join_rite));
+    *out = p.accum ? partial_alpha_mul(a, p.full) : a;
+    return true;
+  }
+  if (len == 2) {
+    fx first = fx_sub(fx_add(p.join_rite, SKB_FX1), p.ur);
+    fx second = fx_sub(fx_sub(p.lr, p.ur), first);
+    *out = x == p.jr ? (uint8_t)(p.full - partial_triangle_to_alpha(first, p.rdy)) : partial_triangle_to_alpha(second, p.rdy);
+    return true;
+  }
+  return aaa_row_at(x, p.join_rite, p.ur, p.join_rite, p.lr, SKB_FX_MAX, p.rdy, p.full, p.accum, out);
 }
 
 // ------------------------------------------------------------- colour and blend

@@ -96,13 +96,12 @@ SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t 
 // (SWEdgeBuilder::AddLine / ChopQuadAtYExtrema + AddQuad, sw_edge.cc:299-336).  Edges go to
 // slot[0], slot[1]; the valid bit (24) tells the walker which are live, bit 25 marks quadratics
 // whose cull extent (q_first_y, q_last_y) is parked in prev/next.
-SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2]) {
+SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2], QuadState qslot[2]) {
   slot[0].curve = 0;
   slot[1].curve = 0;
   if (npts == 2) {
     Edge e;
     e.curve = 0;
-    e.qx = e.qy = e.qdx = e.qdy = e.qddx = e.qddy = e.q_last_x = e.q_last_y = e.snapped_x = e.snapped_y = 0;
     e.prev = e.next = -1;
     if (set_line(e, p[0].x, p[0].y, p[1].x, p[1].y)) {
       e.curve |= 1 << 24;
@@ -113,14 +112,16 @@ SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2]) {
     int k = chop_quad_y(p, mono);
     for (int j = 0; j < k; j++) {
       Edge e;
+      QuadState qs;
       e.curve = 0;
       float q[6] = {mono[2 * j].x, mono[2 * j].y, mono[2 * j + 1].x, mono[2 * j + 1].y, mono[2 * j + 2].x, mono[2 * j + 2].y};
       fx fy, ly;
-      if (set_quad(e, q, &fy, &ly)) {
+      if (set_quad(e, qs, q, &fy, &ly)) {
         e.curve |= (1 << 24) | (1 << 25);
         e.prev = fy;
         e.next = ly;
         slot[j] = e;
+        qslot[j] = qs;
       }
     }
   }
@@ -144,11 +145,9 @@ SKB_HDN PixelCover cover_pixel(const TrapRec* pool, uint2 row, int x) {
       idx = (uint32_t)r.y;
       r = pool[idx];
     }
-    int x0, x1;
-    trap_extent(r, &x0, &x1);
-    if (x < x0 || x >= x1) continue;
     uint8_t a;
-    if (!trap_alpha_at(r, x, &a)) continue;
+    const TrapPrep pr = trap_prepare(r);
+    if (!trap_prep_alpha(pr, x, &a)) continue;
     const uint32_t full = r.flags & 0xFF;
     if (full == 0xFF && !((r.flags >> 8) & 1)) {
       pc.direct = a;  // direct spans of one row never overlap (edges_too_close routes overlaps to accum)

@@ -282,8 +282,11 @@ SKB_HD bool too_close_edges(const Edge* E, int prev, int next, fx lowerY) {  // 
 // Sweep one path.  E[0..n_slots): slot 0/1 are the sentinels, the others hold candidate edges
 // (valid bit = curve bit 24, set by the flatten stage).  `ord` is scratch for n_slots ints.
 // Bounds are the integers SWRaster::RastePath derives (sw_raster.cc:741-780).
-SKB_HDN void walk_path(Edge* E, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y, int stop_y,
-                       fx left_clip, fx right_clip, int even_odd, RecSink& sink) {
+// Q holds the quadratic state of slot i at Q[qmap ? qmap[i] : i] (qmap lets a caller that packed
+// the live edges into a smaller array keep the quadratic state where the flatten stage left it).
+SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots, int32_t* ord, float scan_top_f,
+                       float scan_bottom_f, int start_y, int stop_y, fx left_clip, fx right_clip, int even_odd,
+                       RecSink& sink) {
   // SWEdgeBuilder culling (sw_edge.cc:322-336) + SortEdges + ProcessEdges (sw_raster.cc:679-729)
   int n = 0;
   for (int i = 2; i < n_slots; i++) {
@@ -386,9 +389,10 @@ SKB_HDN void walk_path(Edge* E, int n_slots, int32_t* ord, float scan_top_f, flo
       int next = c.next;
       while (c.lower_y <= next_y) {
         if (edge_count(c) > 0) {
-          c.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
-          c.snapped_y = c.y;
-          if (!update_quad(c)) break;
+          QuadState& q = Q[qmap ? (int)qmap[cur] : cur];
+          q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
+          q.snapped_y = c.y;
+          if (!update_quad(c, q)) break;
         } else {
           break;
         }

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libskb.so")
+LIB_PATH = os.environ.get("SKB_LIB", os.path.join(_PKG, "lib", "libskb.so"))
 _lib = None
 
 

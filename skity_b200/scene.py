@@ -214,15 +214,15 @@ def scene_random_fills(n_paths, size, seed, box=256.0, width=None, height=None):
 
 
 def scene_c1(n_paths=10000, size=4096, seed=1):
-    return scene_random_fills(n_paths, size, seed, 256.0)
+    return scene_random_fills_fast(n_paths, size, seed, 256.0)
 
 
 def scene_c4a(n_paths=1000000, size=16384, seed=4):
-    return scene_random_fills(n_paths, size, seed, 128.0)
+    return scene_random_fills_fast(n_paths, size, seed, 128.0)
 
 
 def scene_c4b(index, n_paths=1000):
-    return scene_random_fills(n_paths, 0, 5 + index, 256.0, width=1920, height=1080)
+    return scene_random_fills_fast(n_paths, 0, 5 + index, 256.0, width=1920, height=1080)
 
 
 def _random_gradient(rng, cx, cy, box, kind):
@@ -286,3 +286,86 @@ def scene_c3(n_paths=2000, size=8192, seed=3, box=512.0):
         radius = float(np.float32((sigma - 0.5) / 0.57735))
         s.draw_path(path, Paint(fill=tuple(np.float32(c) for c in col), blur_radius=radius))
     return s
+
+
+# ---------------------------------------------------------------------------
+# Vectorised generator for the random-fill family (identical bytes to scene_random_fills, ~100x faster)
+# ---------------------------------------------------------------------------
+class SceneBlob:
+    """A pre-encoded SKSC scene (same interface as Scene for the harnesses)."""
+
+    def __init__(self, width, height, n_draws, blob):
+        self.width, self.height, self.n_draws, self._blob = int(width), int(height), int(n_draws), blob
+
+    def encode(self):
+        return self._blob
+
+
+def scene_random_fills_fast(n_paths, size, seed, box=256.0, width=None, height=None):
+    w = width or size
+    h = height or size
+    rng = np.random.RandomState(seed)
+    n_even = (n_paths + 1) // 2          # quads
+    n_odd = n_paths // 2                 # cubics
+    per_even, per_odd = 2 + 2 + 16 + 4, 2 + 2 + 24 + 4
+    # the scalar generator interleaves even/odd paths: reproduce its exact draw order
+    counts = np.where(np.arange(n_paths) % 2 == 0, per_even, per_odd)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    u = rng.random_sample(int(starts[-1]))
+    half = box * 0.5
+
+    def build(idx, n_pts_xy, verbs, op_bytes):
+        m = len(idx)
+        if m == 0:
+            return np.zeros((0, op_bytes), np.uint8)
+        base = starts[idx]
+        cx = 0.0 + (w - 0.0) * u[base]
+        cy = 0.0 + (h - 0.0) * u[base + 1]
+        k = np.arange(n_pts_xy)
+        raw = u[base[:, None] + 2 + k[None, :]]
+        off = -half + (half - -half) * raw
+        centre = np.where(k[None, :] % 2 == 0, cx[:, None], cy[:, None])
+        pts = (centre + off).astype(np.float32)
+        cb = base + 2 + n_pts_xy
+        col = np.stack([0.0 + 1.0 * u[cb], 0.0 + 1.0 * u[cb + 1], 0.0 + 1.0 * u[cb + 2], 0.5 + (1.0 - 0.5) * u[cb + 3]],
+                       axis=1).astype(np.float32)
+        rec = np.zeros((m, op_bytes), np.uint8)
+        nv = len(verbs)
+        vpad = (nv + 3) & ~3
+        path_bytes = 16 + vpad + 4 * n_pts_xy
+        hdr = np.zeros((m, 6), np.uint32)
+        hdr[:, 0] = OP_DRAW_PATH
+        hdr[:, 1] = op_bytes - 8
+        hdr[:, 2] = np.where(idx % 3 == 0, EVEN_ODD, WINDING)
+        hdr[:, 3] = nv
+        hdr[:, 4] = n_pts_xy // 2
+        hdr[:, 5] = 0
+        rec[:, :24] = hdr.view(np.uint8).reshape(m, 24)
+        rec[:, 24:24 + nv] = np.asarray(verbs, np.uint8)[None, :]
+        rec[:, 24 + vpad:24 + vpad + 4 * n_pts_xy] = pts.view(np.uint8).reshape(m, 4 * n_pts_xy)
+        po = 8 + path_bytes
+        paint = np.zeros((m, 16), np.float32)
+        pu = paint.view(np.uint32)
+        pu[:, 0] = FILL
+        paint[:, 1] = 1.0
+        paint[:, 2] = 4.0
+        pu[:, 3] = BUTT
+        pu[:, 4] = MITER
+        paint[:, 5:9] = col
+        paint[:, 9:13] = np.asarray([0, 0, 0, 1], np.float32)[None, :]
+        rec[:, po:po + 64] = paint.view(np.uint8).reshape(m, 64)
+        return rec
+
+    even_idx = np.arange(0, n_paths, 2)
+    odd_idx = np.arange(1, n_paths, 2)
+    ev = build(even_idx, 18, [MOVE, QUAD, QUAD, QUAD, QUAD, CLOSE], 168)
+    od = build(odd_idx, 26, [MOVE, CUBIC, CUBIC, CUBIC, CUBIC, CLOSE], 200)
+    pair = 168 + 200
+    body = np.zeros(n_even * 168 + n_odd * 200, np.uint8)
+    if n_odd:
+        both = body[:n_odd * pair].reshape(n_odd, pair)
+        both[:, :168] = ev[:n_odd]
+        both[:, 168:] = od
+    if n_even > n_odd:
+        body[n_odd * pair:] = ev[-1]
+    return SceneBlob(w, h, n_paths, struct.pack("<6I", MAGIC, 1, w, h, n_paths, 0) + body.tobytes())

@@ -35,7 +35,9 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
     if (ky > g.bmax_y) g.bmax_y = ky;
   };
   std::vector<Edge> E(2 + 2 * (size_t)n_prims);
+  std::vector<QuadState> Q(E.size());
   std::memset(E.data(), 0, E.size() * sizeof(Edge));
+  std::memset(Q.data(), 0, Q.size() * sizeof(QuadState));
   for (uint32_t i = 0; i < n_segs; i++) {
     if ((segs[i].type_flags & SKB_SEG_TYPE_MASK) == SKB_SEG_POINT) bound(xform(ctm, seg_start_point(segs, i)));
     int n = (int)(prim_off[i + 1] - prim_off[i]);
@@ -43,7 +45,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
       V2 p[3];
       int np = seg_prim(segs, i, k, n, ctm, p);
       for (int j = 0; j < np; j++) bound(p[j]);
-      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)]);
+      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)]);
     }
   }
   op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
@@ -59,6 +61,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
   std::vector<int32_t> ord(E.size());
   for (;;) {
     std::vector<Edge> Ew = E;
+    std::vector<QuadState> Qw = Q;
     RecSink sink;
     sink.pool = pool.data();
     sink.pool_next = &pool_next;
@@ -68,7 +71,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
     sink.row0 = g.scan_t;
     sink.n_rows = n_rows;
     sink_init(sink);
-    walk_path(Ew.data(), (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
+    walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
               g.right_clip, even_odd, sink);
     if (!overflow) break;
     pool.resize(pool.size() * 4);
