@@ -146,7 +146,10 @@ def build_host(ref="/root/reference", verbose=True):
     stubs_o = stubs_c[:-2] + ".o"
     _run(["gcc", "-O1", "-fPIC", "-w", "-c", stubs_c, "-o", stubs_o])
     lib = host_lib_path()
-    link = ["g++", "-shared", "-o", lib, *objs, stubs_o, "-lpthread", "-ldl"]
+    if not os.path.exists(cuda_lib_path()):
+        raise RuntimeError("build the CUDA library first (build_cuda): the plug-in links its C ABI")
+    link = ["g++", "-shared", "-o", lib, *objs, stubs_o, f"-L{LIBDIR}", "-l:libskb.so", "-Wl,-rpath,$ORIGIN",
+            "-Wl,--no-undefined", "-lpthread", "-ldl"]
     _run(link)
     if verbose:
         print(f"built {lib} ({len(SKITY_CORE_TUS)} skity core TUs + {len(own)} plug-in sources, {len(missing)} stubs)")

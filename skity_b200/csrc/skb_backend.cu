@@ -178,11 +178,20 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
   Edge slot[2];
   QuadState qslot[2];
   flatten_prim(np, p, slot, qslot);
-  const size_t at = (size_t)2 * prim + (size_t)2 * op + 2;
-  edges[at] = slot[0];
-  edges[at + 1] = slot[1];
-  if ((slot[0].curve >> 25) & 1) quads[at] = qslot[0];
-  if ((slot[1].curve >> 25) & 1) quads[at + 1] = qslot[1];
+  // Each path owns one contiguous region of 80 bytes per slot: its Edge array followed by its
+  // QuadState array, so the sweep's working set per path stays within a few cache lines.
+  const skb_dl_path pa = t.paths[t.ops[op].path];
+  const uint32_t first_prim = prim_off[pa.seg_off];
+  const uint32_t n_slots = 2 + 2 * (prim_off[pa.seg_off + pa.n_segs] - first_prim);
+  const size_t slot_base = (size_t)2 * first_prim + (size_t)2 * op;
+  uint8_t* region = reinterpret_cast<uint8_t*>(edges) + slot_base * (sizeof(Edge) + sizeof(QuadState));
+  Edge* E = reinterpret_cast<Edge*>(region);
+  QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)n_slots * sizeof(Edge));
+  const uint32_t at = 2 + 2 * (prim - first_prim);
+  E[at] = slot[0];
+  E[at + 1] = slot[1];
+  if ((slot[0].curve >> 25) & 1) Q[at] = qslot[0];
+  if ((slot[1].curve >> 25) & 1) Q[at + 1] = qslot[1];
 }
 
 // ------------------------------------------------------------------- stage 2: setup
@@ -287,8 +296,11 @@ __global__ void __launch_bounds__(64) k_walk(WalkArgs a, int lane_stride) {
   walk_setup_sink(a, op, g, sink);
   // rows below the last tile row are never read: stop the sweep there (rows do not depend on later ones)
   int stop_y = min(g.stop_y, sink.row0 + sink.n_rows);
-  walk_path(a.edges + g.slot_base, a.quads + g.slot_base, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f,
-            g.scan_bottom_f, g.start_y, stop_y, g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink);
+  uint8_t* region = reinterpret_cast<uint8_t*>(a.edges) + (size_t)g.slot_base * (sizeof(Edge) + sizeof(QuadState));
+  Edge* E = reinterpret_cast<Edge*>(region);
+  QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
+  walk_path(E, Q, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
+            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink);
 }
 
 // ---------------------------------------------------------------- stage 4: coverage
@@ -337,18 +349,31 @@ __device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool
 
 // Range summary of one record kept in registers across the tiles of a row.
 struct RecRange {
-  int L, R, jl, jr;   // pixels [L,R) get a value, [jl,jr) get `full`
-  uint32_t idx;       // record index in the pool
-  uint32_t full_accum;  // full | accum << 8 | live << 9
+  int L, R, jl, jr;     // pixels [L,R) get a value, [jl,jr) get `full` (all clipped to the scan/surface x-range)
+  int lbase, rbase;     // queue positions of the left-zone [L,jl) and right-zone [jr,R) pixel values
+  uint32_t full_accum;  // full | accum << 8
 };
 #define COVER_RMAX 4
+#define COVER_WARPS 4
+#define COVER_QCAP 768  // edge-pixel tasks per tile row that fit the shared-memory queue
 
-// One warp per (op, tile row): lane L owns pixel row L>>1 of the tile row and the 8-pixel half L&1 of
-// every tile.  The lane's trapezoid rows are loaded and summarised ONCE, then every tile in the
-// covered x-range is classified (empty / solid / partial) with range tests; only pixels under a
-// slanted edge run the triangle/ramp formulas.  A tile's A8 mask is one coalesced 256-byte store.
-__global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
-  const uint32_t trow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// One warp per (op, tile row).  Lane L owns pixel row L>>1 of the tile row and the 8-pixel half L&1
+// of every tile.  Work is split by KIND of pixel so that the expensive part is evenly spread:
+//   1. each lane summarises its row's trapezoid records as ranges (outside / edge zone / interior);
+//   2. the edge-zone pixels of all 16 rows — the only ones that need the triangle/ramp formulas —
+//      are queued in shared memory and evaluated by all 32 lanes, one task each per round;
+//   3. the tiles of the covered x-range are then assembled with range tests and queue look-ups,
+//      classified (empty / solid / partial) by ballot, and stored as coalesced 256-byte A8 masks.
+__global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
+  // zone descriptors of the 16 rows x COVER_RMAX records: queue base, record, and the two pixel zones
+  __shared__ int32_t z_base[COVER_WARPS][16 * COVER_RMAX];
+  __shared__ uint32_t z_rec[COVER_WARPS][16 * COVER_RMAX];
+  __shared__ int32_t z_l0[COVER_WARPS][16 * COVER_RMAX];   // left zone  [l0, l0 + nl)
+  __shared__ int32_t z_nl[COVER_WARPS][16 * COVER_RMAX];
+  __shared__ int32_t z_r0[COVER_WARPS][16 * COVER_RMAX];   // right zone [r0, ...)
+  __shared__ uint8_t q_val[COVER_WARPS][COVER_QCAP];
+  const int wib = threadIdx.x >> 5;
+  const uint32_t trow = blockIdx.x * COVER_WARPS + wib;
   const int lane = threadIdx.x & 31;
   if (trow >= c.n_trows) return;
   const uint32_t op = find_interval(c.row_base, c.n_ops, trow * SKB_TILE);
@@ -363,8 +388,13 @@ __global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
   uint2 row = make_uint2(0u, 0u);
   if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)(lane >> 1)];
 
+  // ---- 1. range summaries
   RecRange rr[COVER_RMAX];
+  uint32_t ridx[COVER_RMAX];
   int lo = INT_MAX, hi = INT_MIN;
+  int n_tasks = 0;
+  const bool generic = row.y > COVER_RMAX;
+  const int nrec = generic ? 0 : (int)row.y;
   {
     uint32_t idx = row.x;
     for (uint32_t k = 0; k < row.y; k++, idx++) {
@@ -374,38 +404,90 @@ __global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
         r = c.pool[idx];
       }
       const TrapPrep pr = trap_prepare(r);
-      if (pr.mode != 0 && pr.R > pr.L) {
-        lo = min(lo, pr.L);
-        hi = max(hi, pr.R);
+      int L = pr.L, R = pr.mode ? pr.R : pr.L;
+      L = max(L, xmin);
+      R = min(R, xmax);
+      if (R > L) {
+        lo = min(lo, L);
+        hi = max(hi, R);
       }
       if (k < COVER_RMAX) {
-        rr[k].L = pr.L; rr[k].R = pr.mode ? pr.R : pr.L; rr[k].jl = pr.jl; rr[k].jr = pr.jr;
-        rr[k].idx = idx;
-        rr[k].full_accum = pr.full | (pr.accum ? 0x100u : 0u);
+        RecRange q;
+        q.L = L;
+        q.R = max(R, L);
+        q.jl = min(max(pr.jl, q.L), q.R);
+        q.jr = min(max(pr.jr, q.jl), q.R);
+        q.lbase = n_tasks;
+        q.rbase = n_tasks + (q.jl - q.L);
+        q.full_accum = pr.full | (pr.accum ? 0x100u : 0u);
+        if (!generic) n_tasks += (q.jl - q.L) + (q.R - q.jr);
+        rr[k] = q;
+        ridx[k] = idx;
       }
     }
   }
-  const bool generic = row.y > COVER_RMAX;
-  const int nrec = row.y > COVER_RMAX ? COVER_RMAX : (int)row.y;
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
   }
-  lo = max(lo, xmin);
-  hi = min(hi, xmax);
   if (hi <= lo) return;  // nothing in this tile row (item flags were zeroed)
+
+  // ---- 2. queue and evaluate the edge-zone pixels (even lanes own their row's tasks)
+  int mine = (lane & 1) ? 0 : n_tasks;
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  int base = incl - mine;
+  base = __shfl_sync(0xffffffffu, base, lane & ~1);  // the odd lane of a row uses its partner's slots
+  const bool queued = total <= COVER_QCAP;
+  if (queued) {
+    if (!(lane & 1)) {
+      const int d0 = (lane >> 1) * COVER_RMAX;
+#pragma unroll
+      for (int k = 0; k < COVER_RMAX; k++) {
+        const bool live = k < nrec;
+        z_base[wib][d0 + k] = base + (live ? rr[k].lbase : n_tasks);
+        z_rec[wib][d0 + k] = live ? ridx[k] : 0u;
+        z_l0[wib][d0 + k] = live ? rr[k].L : 0;
+        z_nl[wib][d0 + k] = live ? rr[k].jl - rr[k].L : 0;
+        z_r0[wib][d0 + k] = live ? rr[k].jr : 0;
+      }
+    }
+    __syncwarp();
+    // every lane takes one edge-zone pixel per round: find its descriptor by binary search on the bases
+    for (int p = lane; p < total; p += 32) {
+      int lo_d = 0, hi_d = 16 * COVER_RMAX;
+      while (hi_d - lo_d > 1) {
+        int mid = (lo_d + hi_d) >> 1;
+        if (z_base[wib][mid] <= p) lo_d = mid; else hi_d = mid;
+      }
+      const int off = p - z_base[wib][lo_d];
+      const int nl = z_nl[wib][lo_d];
+      const int x = off < nl ? z_l0[wib][lo_d] + off : z_r0[wib][lo_d] + (off - nl);
+      const TrapPrep pr = trap_prepare(c.pool[z_rec[wib][lo_d]]);
+      uint8_t v = 0;
+      if (!trap_prep_alpha(pr, x, &v)) v = 0;
+      q_val[wib][p] = v;
+    }
+    __syncwarp();
+  }
+
+  // ---- 3. assemble, classify and store the tiles
   const int tx_begin = max(g.tx0, lo / SKB_TILE);
   const int tx_end = min(g.tx0 + g.ntx, (hi + SKB_TILE - 1) / SKB_TILE);
   const uint32_t item_row = c.item_base[op] + tr * (uint32_t)g.ntx;
   const bool is_fill = o.kind == SKB_OP_FILL;
-
   for (int tx = tx_begin; tx < tx_end; tx++) {
     const int x0 = tx * SKB_TILE + (lane & 1) * 8;
     uint32_t d[8], a[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
-    if (generic) {
+    if (generic || !queued) {
       cover_row8_generic(c.pool, row, x0, xmin, xmax, d, a);
     } else {
 #pragma unroll
@@ -415,22 +497,22 @@ __global__ void __launch_bounds__(128) k_cover(CoverArgs c) {
         if (q.R <= x0 || q.L >= x0 + 8) continue;
         const uint32_t full = q.full_accum & 0xFF;
         const bool accum = (q.full_accum >> 8) & 1;
-        if (x0 >= q.jl && x0 + 8 <= q.jr && x0 >= xmin && x0 + 8 <= xmax) {
+        if (x0 >= q.jl && x0 + 8 <= q.jr) {
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             if (accum) a[j] += full; else d[j] = full;
           }
           continue;
         }
-        // at least one pixel is under a slanted edge (or at the clip border): evaluate per pixel
-        const TrapPrep pr = trap_prepare(c.pool[q.idx]);
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 8; j++) {
-          int x = x0 + j;
-          uint8_t v;
-          if (x >= xmin && x < xmax && trap_prep_alpha(pr, x, &v)) {
-            if (accum) a[j] += v; else d[j] = v;
-          }
+          const int x = x0 + j;
+          if (x < q.L || x >= q.R) continue;
+          uint32_t v;
+          if (x >= q.jl && x < q.jr) v = full;
+          else if (x < q.jl) v = q_val[wib][base + q.lbase + (x - q.L)];
+          else v = q_val[wib][base + q.rbase + (x - q.jr)];
+          if (accum) a[j] += v; else d[j] = v;
         }
       }
     }
@@ -1096,8 +1178,7 @@ static skb_result run_frame(skb_surface s) {
   S.n_prims = n_prims;
   const size_t n_slots = (size_t)2 * n_prims + (size_t)2 * n_ops + 2;
   S.n_edges_slots = (uint32_t)n_slots;
-  SKB_TRY(buf_reserve(s->edges, n_slots * sizeof(Edge)));
-  SKB_TRY(buf_reserve(s->quads, n_slots * sizeof(QuadState)));
+  SKB_TRY(buf_reserve(s->edges, n_slots * (sizeof(Edge) + sizeof(QuadState))));
   SKB_TRY(buf_reserve(s->walk_lists, (size_t)n_ops * 4 + 16));
   SKB_TRY(buf_reserve(s->ord, n_slots * 4));
   Edge* edges = (Edge*)s->edges.p;
@@ -1106,7 +1187,7 @@ static skb_result run_frame(skb_surface s) {
   uint32_t pool_cap = 0;
   for (int attempt = 0;; attempt++) {
     if (n_prims) {
-      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, (QuadState*)s->quads.p);
+      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, nullptr);
       launches++;
     }
     if (attempt == 0) {
@@ -1153,7 +1234,7 @@ static skb_result run_frame(skb_surface s) {
       wa.geom = geom;
       wa.row_base = row_base;
       wa.edges = edges;
-      wa.quads = (QuadState*)s->quads.p;
+      wa.quads = nullptr;
       wa.ord = (int32_t*)s->ord.p;
       wa.pool = (TrapRec*)s->pool.p;
       wa.pool_next = counters;
@@ -1162,9 +1243,10 @@ static skb_result run_frame(skb_surface s) {
       wa.rows = (uint2*)s->rows.p;
       wa.list = (const uint32_t*)s->walk_lists.p;
       wa.count = counters + 4;
-      // spread paths over warps while the GPU has spare thread slots (about 16 warps per SM wanted)
+      // spread paths over warps while the GPU has spare thread slots (about 32 warps per SM wanted;
+      // measured on C1: stride 1 5.2 ms, 4 2.6 ms, 8 2.0 ms, 32 2.6 ms)
       int lane_stride = 1;
-      const uint64_t want_threads = (uint64_t)s->dev->sm_count * 16 * 32;
+      const uint64_t want_threads = (uint64_t)s->dev->sm_count * 32 * 32;
       while (lane_stride < 8 && (uint64_t)n_ops * lane_stride * 2 <= want_threads) lane_stride *= 2;
       if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
       k_walk<<<cdiv((uint64_t)n_ops * lane_stride, 64), 64, 0, st>>>(wa, lane_stride);
@@ -1206,7 +1288,7 @@ static skb_result run_frame(skb_surface s) {
   SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
   if (n_items) {
     SKB_CUDA(cudaMemsetAsync(s->item_flags.p, 0, n_items, st));
-    k_cover<<<cdiv((uint64_t)ca.n_trows * 32, 128), 128, 0, st>>>(ca);
+    k_cover<<<cdiv(ca.n_trows, COVER_WARPS), COVER_WARPS * 32, 0, st>>>(ca);
     launches++;
   }
   cudaEventRecord(s->ev[4], st);

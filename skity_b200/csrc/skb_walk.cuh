@@ -41,12 +41,27 @@ struct RecSink {
   uint32_t cur;
   uint32_t left;
   int cur_row;          // relative row of the records being written, -1 = none
+  uint32_t row_first;   // first record and record count of that row (flushed to rows[] when it ends)
+  uint32_t row_count;
 };
 
 SKB_HD void sink_init(RecSink& s) {
   s.cur = 0xFFFFFFFFu;
   s.left = 0;
   s.cur_row = -1;
+  s.row_first = 0;
+  s.row_count = 0;
+}
+
+// Writes the finished row's (first record, count) entry; called when the sweep moves to another row
+// and once more after the sweep.
+SKB_HD void sink_flush_row(RecSink& s) {
+  if (s.cur_row >= 0 && s.row_count > 0) {
+    uint2 e;
+    e.x = s.row_first;
+    e.y = s.row_count;
+    s.rows[s.cur_row] = e;
+  }
 }
 
 SKB_HDN void sink_emit(RecSink& s, const TrapRec& r) {
@@ -69,14 +84,15 @@ SKB_HDN void sink_emit(RecSink& s, const TrapRec& r) {
     s.left = SKB_CHUNK - 1;
   }
   if (rel != s.cur_row) {
+    sink_flush_row(s);
     s.cur_row = rel;
-    s.rows[rel].x = s.cur;
-    s.rows[rel].y = 0;
+    s.row_first = s.cur;
+    s.row_count = 0;
   }
   s.pool[s.cur] = r;
   s.cur++;
   s.left--;
-  s.rows[rel].y++;
+  s.row_count++;
 }
 
 // ---- SortEdges: libstdc++ std::sort (GCC 13 bits/stl_algo.h) on an index array --------------
@@ -425,6 +441,7 @@ SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots,
     if (y >= i_to_fx(stop_y)) break;
     insert_new_edges(E, cur, y, &nny);
   }
+  sink_flush_row(sink);
 }
 
 }  // namespace skb

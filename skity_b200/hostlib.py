@@ -18,6 +18,9 @@ def lib():
                                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_encode_scene.restype = ctypes.c_int
         _lib.skbh_free.argtypes = [ctypes.c_void_p]
+        _lib.skbh_render_scene_cuda.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_char_p, ctypes.c_size_t]
+        _lib.skbh_render_scene_cuda.restype = ctypes.c_int
     return _lib
 
 
@@ -36,3 +39,18 @@ def encode_scene(blob, allow_unsupported=False):
     if msg.value and not allow_unsupported:
         raise RuntimeError(f"scene uses a feature outside the CUDA backend's scope: {msg.value.decode()}")
     return data
+
+
+def render_scene_cuda(blob, device_ordinal=0):
+    """Replay an SKSC scene through the complete skity plug-in path on the GPU:
+    CudaContextCreate -> GPUContext::CreateSurface -> LockCanvas -> Canvas calls -> Flush -> ReadPixels."""
+    import struct
+
+    import numpy as np
+    _, _, w, h, _, _ = struct.unpack_from("<6I", blob, 0)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    msg = ctypes.create_string_buffer(512)
+    rc = lib().skbh_render_scene_cuda(blob, len(blob), device_ordinal, out.ctypes.data, msg, 512)
+    if rc != 0:
+        raise RuntimeError(f"skbh_render_scene_cuda failed ({rc}): {msg.value.decode(errors='replace')}")
+    return out

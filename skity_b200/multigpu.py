@@ -1,0 +1,78 @@
+"""Multi-GPU partitioning of the raster path (one process per GPU, torch.distributed for plumbing).
+
+The path shards with NO data-path collective:
+  * batch of independent canvases  -> canvas i is rendered by rank i % world      (canvas_owner)
+  * one large canvas               -> contiguous bands of tile rows, the display list replicated on
+                                      every rank, each rank rendering only its band  (band_ranges)
+The only collective is the read-back gather of the bands to rank 0 (gather_bands): point-to-point
+sends of each band's contiguous rows — NCCL over NVLink on GPUs, gloo on CPU for the tests.
+"""
+import numpy as np
+
+TILE = 16
+
+
+def canvas_owner(index, world):
+    return index % world
+
+
+def band_ranges(height, world):
+    """Contiguous, tile-aligned row bands [(y0, y1)] * world covering [0, height).  Ranks beyond the
+    number of tile rows get empty bands (y0 == y1)."""
+    tiles_y = (height + TILE - 1) // TILE
+    out = []
+    for r in range(world):
+        t0 = tiles_y * r // world
+        t1 = tiles_y * (r + 1) // world
+        out.append((min(t0 * TILE, height), min(t1 * TILE, height)))
+    return out
+
+
+class _CudaBuffer:
+    """Exposes raw device memory to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def surface_band_tensor(surface, y0, y1):
+    """1-D uint8 CUDA tensor aliasing rows [y0, y1) of a device surface (rows are pitch bytes apart,
+    so a band is one contiguous block)."""
+    import torch
+    ptr, pitch = surface.device_ptr()
+    n = (y1 - y0) * pitch
+    if n == 0:
+        return torch.empty(0, dtype=torch.uint8, device="cuda"), pitch
+    return torch.as_tensor(_CudaBuffer(ptr + y0 * pitch, n), device="cuda"), pitch
+
+
+def gather_bands(band_tensor_of, bands, rank, world, dist):
+    """Gathers every rank's band into rank 0's full image.
+
+    band_tensor_of(y0, y1) -> 1-D uint8 tensor aliasing rows [y0, y1) of THIS rank's image buffer.
+    On rank 0 the other ranks' bands are received straight into its own buffer; other ranks send."""
+    if world == 1:
+        return
+    if rank == 0:
+        reqs = []
+        for r in range(1, world):
+            y0, y1 = bands[r]
+            if y1 > y0:
+                reqs.append(dist.irecv(band_tensor_of(y0, y1), src=r))
+        for q in reqs:
+            q.wait()
+    else:
+        y0, y1 = bands[rank]
+        if y1 > y0:
+            dist.send(band_tensor_of(y0, y1), dst=0)
+
+
+def host_band_tensor_factory(image):
+    """band_tensor_of for a host (H, W, 4) uint8 numpy image (CPU/gloo path of the tests)."""
+    import torch
+    flat = torch.from_numpy(image.reshape(-1))
+    row = image.shape[1] * image.shape[2]
+
+    def f(y0, y1):
+        return flat[y0 * row:y1 * row]
+    return f

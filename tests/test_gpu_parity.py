@@ -169,3 +169,13 @@ def test_path_clips_not_silently_ignored(dev):
         assert "clip" in str(e).lower()
     finally:
         surf.close()
+
+
+def test_plugin_path_matches_reference():
+    """The complete skity plug-in path — CudaContextCreate -> GPUContext::CreateSurface -> LockCanvas ->
+    the README's Canvas calls -> Flush -> ReadPixels — must reproduce the reference software canvas."""
+    z = np.load(os.path.join(GOLDEN, "c0_star_blur_800x600.npz"))
+    got = hostlib.render_scene_cuda(z["scene"].tobytes())
+    assert np.array_equal(got, z["rgba"])
+    z = np.load(os.path.join(GOLDEN, "mixed_transform_clip_400x300.npz"))
+    assert np.array_equal(hostlib.render_scene_cuda(z["scene"].tobytes()), z["rgba"])
