@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "include/skb.h"
+#include "skity_b200/csrc/skb_clip.cuh"
 #include "skity_b200/csrc/skb_stages.cuh"
 
 namespace skb {
@@ -210,7 +211,7 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
     g.slot_base = 2 * first_prim + 2 * op;
     g.n_slots = 2 + 2 * n_prims;
     const SurfDesc sd = surfs[o.surface];
-    op_setup(g, o.clip_bounds, sd.w, sd.h, p.n_segs > 0);
+    op_setup(g, o.clip_bounds, sd.w, sd.h, p.n_segs > 0, (o.kind == SKB_OP_CLIP || o.clip_in != 0) ? 1 : 0);
     if (!g.empty && g.ntx > 0) {
       // keep only the tile rows this device renders (band split); the rows outside are another GPU's
       int ty0 = max(g.ty0, (int)(sd.row0 / SKB_TILE));
@@ -317,12 +318,15 @@ struct CoverArgs {
   const uint2* rows;
   uint8_t* mask0;  // n_items * 256: plane blended first (direct spans, or the only plane)
   uint8_t* mask1;  // n_items * 256: accumulated spans where a pixel of the tile has both
-  uint8_t* item_flags;
+  uint8_t* mask[SKB_CLIP_PLANES];  // all planes (0,1 as above; 2.. only used by clipped draws)
+  uint16_t* item_flags;
   uint32_t* tile_cnt;
 };
+// item flags (u16): bit k = coverage plane k present (k < SKB_CLIP_PLANES = 8), bit 8 = plane 0 is solid 255
 #define SKB_ITEM_PLANE0 1u
-#define SKB_ITEM_SOLID 2u
-#define SKB_ITEM_PLANE1 4u
+#define SKB_ITEM_PLANE1 2u
+#define SKB_ITEM_SOLID 256u
+#define SKB_ITEM_PLANE_MASK 255u
 
 // Generic (slow) evaluation of 8 pixels of a row: every record re-read and re-prepared.
 __device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool, uint2 row, int x0, int xmin, int xmax,
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   const uint32_t tr = trow - c.row_base[op] / SKB_TILE;
   const int ty = g.ty0 + (int)tr;
   const skb_dl_op o = c.ops[op];
+  if (o.kind != SKB_OP_FILL || o.clip_in != 0) return;  // clip paths and clipped draws: k_clip_rows
   const SurfDesc sd = c.surfs[o.surface];
   const int y = ty * SKB_TILE + (lane >> 1);
   const int xmax = min(g.scan_r, (int)sd.w);
@@ -554,11 +559,180 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
       }
     }
     if (lane == 0) {
-      c.item_flags[item] = (uint8_t)flags;
+      c.item_flags[item] = (uint16_t)flags;
       if (is_fill) {
         uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
         atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------- stage 4b: path clips
+// Clip states and clipped draws are produced row by row (skb_clip.cuh): one thread sweeps one pixel
+// row of one op.  A clip state is a per-pixel table of up to SKB_CLIP_MAXE (span start, coverage)
+// entries over the clip path's scan rectangle; a clipped draw becomes up to SKB_CLIP_PLANES
+// coverage planes (the k-th coverage blended into a pixel lives in plane k).
+struct ClipStateDesc {
+  int32_t rx0, ry0, rw, rh;  // region covered by the table (scan rectangle + 1 column, on the surface)
+  uint32_t table_off;        // first pixel of the table (in pixels)
+  uint32_t nonempty;         // SWCanvas::State::HasClip(): some span exists
+  uint32_t op;
+  uint32_t pad;
+};
+
+__global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* surfs, ClipStateDesc* states, uint32_t* px_cnt) {
+  uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= t.n_ops) return;
+  const skb_dl_op o = t.ops[op];
+  if (o.kind != SKB_OP_CLIP) return;
+  const OpGeom g = geom[op];
+  const SurfDesc sd = surfs[o.surface];
+  ClipStateDesc d;
+  d.rx0 = d.ry0 = d.rw = d.rh = 0;
+  d.table_off = 0;
+  d.nonempty = 0;
+  d.op = op;
+  d.pad = 0;
+  if (!g.empty) {
+    d.rx0 = max(g.scan_l, 0);
+    d.ry0 = max(g.scan_t, 0);
+    d.rw = max(min(g.scan_r + 1, (int)sd.w) - d.rx0, 0);
+    d.rh = max(min(g.scan_b, (int)sd.h) - d.ry0, 0);
+    if (d.rw == 0 || d.rh == 0) d.rw = d.rh = 0;
+  }
+  states[o.clip_out] = d;
+  px_cnt[o.clip_out] = (uint32_t)(d.rw * d.rh);
+}
+
+struct ClipArgs {
+  CoverArgs c;
+  ClipStateDesc* states;
+  const uint32_t* state_px_off;  // scanned px_cnt
+  uint32_t* table;               // SKB_CLIP_MAXE entries per pixel
+  const uint8_t* op_depth;       // nesting depth of the state a CLIP op defines
+  uint32_t* overflow;            // set when a pixel needs more entries / planes than provided
+  uint32_t n_rows;
+};
+
+// mode 0: build the clip states of nesting depth `level`; mode 1: rasterise the clipped draws.
+__global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int level) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= a.n_rows) return;
+  const CoverArgs& c = a.c;
+  const uint32_t op = find_interval(c.row_base, c.n_ops, r);
+  const skb_dl_op o = c.ops[op];
+  if (mode == 0) {
+    if (o.kind != SKB_OP_CLIP || a.op_depth[op] != (uint8_t)level) return;
+  } else {
+    if (o.kind != SKB_OP_FILL || o.clip_in == 0) return;
+  }
+  const OpGeom g = c.geom[op];
+  if (g.empty || g.ntx == 0) return;
+  const SurfDesc sd = c.surfs[o.surface];
+  const int y = g.ty0 * SKB_TILE + (int)(r - c.row_base[op]);
+  if (y < g.scan_t || y >= g.scan_b || y >= (int)sd.h) return;
+  const uint2 row = c.rows[r];
+  if (row.y == 0) return;
+
+  // parent clip state (C side)
+  ClipStateDesc par;
+  par.rw = par.rh = 0;
+  bool clipped = false;
+  if (o.clip_in != 0) {
+    par = a.states[o.clip_in];
+    clipped = par.nonempty != 0;
+  }
+  const bool c_row_in = clipped && y >= par.ry0 && y < par.ry0 + par.rh;
+  const uint32_t* c_row = c_row_in ? a.table + ((size_t)a.state_px_off[o.clip_in] + (size_t)(y - par.ry0) * par.rw) * SKB_CLIP_MAXE
+                                   : nullptr;
+  // own state (mode 0)
+  ClipStateDesc own;
+  uint32_t* own_row = nullptr;
+  if (mode == 0) {
+    own = a.states[o.clip_out];
+    if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
+    own_row = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+  }
+
+  ClipRowState st;
+  clip_row_begin(st, c.pool, row);
+  int x_first = g.scan_l, x_last = g.scan_r;  // inclusive: the pixel after the last span can receive the `+ 1`
+  if (st.n_prep >= 0) {
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int k = 0; k < st.n_prep; k++) {
+      if (st.prep[k].mode == 0) continue;
+      lo = min(lo, st.prep[k].L);
+      hi = max(hi, st.prep[k].R);
+    }
+    if (hi <= lo) return;
+    x_first = max(x_first, lo);
+    x_last = min(x_last, hi);
+  }
+  x_last = min(x_last, (int)sd.w - 1);
+  const int cap = mode == 0 ? SKB_CLIP_MAXE : SKB_CLIP_PLANES;
+  const uint32_t item_row = c.item_base[op] + (uint32_t)((y / SKB_TILE) - g.ty0) * (uint32_t)g.ntx;
+  bool wrote = false, over = false;
+  for (int x = x_first; x <= x_last; x++) {
+    SpanSide ld, od, la, oa;
+    clip_row_step(st, c.pool, row, x, ld, od, la, oa);
+    if (x < 0) continue;
+    if ((ld.cover | od.cover | la.cover | oa.cover) == 0) continue;
+    const uint32_t* clist = nullptr;
+    int n_c = 0;
+    if (c_row && x >= par.rx0 && x < par.rx0 + par.rw) {
+      clist = c_row + (size_t)(x - par.rx0) * SKB_CLIP_MAXE;
+      while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
+    }
+    ClipOut out;
+    clip_combine(ld, od, la, oa, clist, n_c, clipped, cap, out);
+    over |= out.overflow;
+    if (out.n == 0) continue;
+    if (mode == 0) {
+      if (x >= own.rx0 && x < own.rx0 + own.rw) {
+        uint32_t* e = own_row + (size_t)(x - own.rx0) * SKB_CLIP_MAXE;
+        for (int k = 0; k < out.n; k++) e[k] = out.e[k];
+        wrote = true;
+      }
+    } else {
+      const int tx = x / SKB_TILE;
+      if (tx < g.tx0 || tx >= g.tx0 + g.ntx) continue;
+      const size_t at = (size_t)(item_row + (uint32_t)(tx - g.tx0)) * 256 + (size_t)(y % SKB_TILE) * SKB_TILE + (x % SKB_TILE);
+      for (int k = 0; k < out.n; k++) c.mask[k][at] = (uint8_t)clip_entry_cover(out.e[k]);
+    }
+  }
+  if (wrote) a.states[o.clip_out].nonempty = 1;
+  if (over) *a.overflow = 1;
+}
+
+// One warp per (op, tile) item of a clipped draw: which planes are present, is plane 0 solid.
+__global__ void __launch_bounds__(128) k_clip_classify(CoverArgs c) {
+  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (item >= c.n_items) return;
+  const uint32_t op = find_interval(c.item_base, c.n_ops, item);
+  const skb_dl_op o = c.ops[op];
+  if (o.kind != SKB_OP_FILL || o.clip_in == 0) return;
+  uint32_t flags = 0;
+  bool solid = true;
+#pragma unroll
+  for (int k = 0; k < SKB_CLIP_PLANES; k++) {
+    const uint2 v = reinterpret_cast<const uint2*>(c.mask[k] + (size_t)item * 256)[lane];
+    const bool nz = (v.x | v.y) != 0;
+    if (__any_sync(0xffffffffu, nz)) flags |= 1u << k;
+    if (k == 0) solid = (v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
+  }
+  solid = __all_sync(0xffffffffu, solid) && flags == 1u;
+  if (solid) flags |= SKB_ITEM_SOLID;
+  if (lane == 0) {
+    c.item_flags[item] = (uint16_t)flags;
+    if (flags) {
+      const OpGeom g = c.geom[op];
+      const uint32_t local = item - c.item_base[op];
+      const int tx = g.tx0 + (int)(local % (uint32_t)g.ntx);
+      const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
+      const SurfDesc sd = c.surfs[o.surface];
+      atomicAdd(&c.tile_cnt[sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx], (uint32_t)__popc(flags & SKB_ITEM_PLANE_MASK));
     }
   }
 }
@@ -577,10 +751,12 @@ __global__ void k_scatter(CoverArgs c, const uint32_t* tile_off, uint32_t* tile_
   const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
   const SurfDesc sd = c.surfs[c.ops[op].surface];
   const uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
-  const uint32_t n = (flags & SKB_ITEM_PLANE1) ? 2u : 1u;
+  const uint32_t n = (uint32_t)__popc(flags & SKB_ITEM_PLANE_MASK);
   uint32_t pos = tile_off[tile] + atomicAdd(&tile_fill[tile], n);
-  cmds[pos] = make_uint2(op << 1, item | ((flags & SKB_ITEM_SOLID) ? SKB_CMD_SOLID : 0u));
-  if (n == 2) cmds[pos + 1] = make_uint2((op << 1) | 1u, item);
+  for (uint32_t k = 0; k < SKB_CLIP_PLANES; k++) {
+    if (!((flags >> k) & 1u)) continue;
+    cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u));
+  }
 }
 
 // -------------------------------------------------------------------- stage 6: fine
@@ -596,8 +772,7 @@ struct FineArgs {
   const skb_dl_op* ops;
   const skb_dl_paint* paints;
   const float* stops;
-  const uint8_t* mask0;
-  const uint8_t* mask1;
+  const uint8_t* mask[SKB_CLIP_PLANES];
 };
 #define FINE_WARPS 4
 #define FINE_SORT_CAP 256
@@ -661,14 +836,14 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
 
   for (uint32_t i = 0; i < n; i++) {
     const uint2 cmd = list[i];
-    const uint32_t op = cmd.x >> 1;
+    const uint32_t op = cmd.x >> 3;
     const uint32_t pidx = a.ops[op].paint;
     const uint32_t ptype = a.paints[pidx].type;
     uint32_t lo, hi;
     if (cmd.y & SKB_CMD_SOLID) {
       lo = hi = 0xFFFFFFFFu;
     } else {
-      const uint8_t* m = ((cmd.x & 1u) ? a.mask1 : a.mask0) + (size_t)(cmd.y & 0x7FFFFFFFu) * 256;
+      const uint8_t* m = a.mask[cmd.x & 7u] + (size_t)(cmd.y & 0x7FFFFFFFu) * 256;
       uint2 mv = reinterpret_cast<const uint2*>(m)[lane];
       lo = mv.x;
       hi = mv.y;
@@ -927,7 +1102,7 @@ struct skb_surface_s {
   uint32_t w = 0, h = 0;
   uint32_t band_y0 = 0, band_y1 = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
   // canvas pixels (persistent)
   uint8_t* canvas = nullptr;
   uint32_t pitch = 0, tiles_x = 0, tiles_y = 0;
@@ -937,7 +1112,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -1061,8 +1236,12 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
           return SKB_ERROR_BAD_DISPLAY_LIST;
         }
       }
-      if (o.kind == SKB_OP_CLIP || o.clip_in != 0) {
-        set_error("path clips (Canvas::ClipPath) are not implemented on the device yet");
+      if (o.kind == SKB_OP_CLIP && (o.clip_out == 0 || o.clip_out > h.n_clip_states)) {
+        set_error("display list: clip state id out of range");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      if (o.kind == SKB_OP_CLIP && o.aux != 1) {
+        set_error("ClipOp::kDifference path clips are not implemented on the device (intersecting clips are)");
         return SKB_ERROR_UNSUPPORTED;
       }
     } else if (o.kind == SKB_OP_BLUR) {
@@ -1214,7 +1393,7 @@ static skb_result run_frame(skb_surface s) {
       SKB_TRY(buf_reserve(s->rows, (n_rows + 1) * sizeof(uint2)));
       SKB_TRY(buf_reserve(s->mask0, (n_items + 1) * 256));
       SKB_TRY(buf_reserve(s->mask1, (n_items + 1) * 256));
-      SKB_TRY(buf_reserve(s->item_flags, n_items + 16));
+      SKB_TRY(buf_reserve(s->item_flags, 2 * n_items + 16));
       SKB_TRY(buf_reserve(s->tile_cnt, (size_t)(n_tiles + 1) * 4));
       SKB_TRY(buf_reserve(s->tile_fill, (size_t)(n_tiles + 1) * 4));
       cudaEventRecord(s->ev[2], st);
@@ -1282,14 +1461,93 @@ static skb_result run_frame(skb_surface s) {
   ca.rows = (const uint2*)s->rows.p;
   ca.mask0 = (uint8_t*)s->mask0.p;
   ca.mask1 = (uint8_t*)s->mask1.p;
-  ca.item_flags = (uint8_t*)s->item_flags.p;
+  for (int k = 0; k < SKB_CLIP_PLANES; k++) ca.mask[k] = nullptr;
+  ca.mask[0] = ca.mask0;
+  ca.mask[1] = ca.mask1;
+  ca.item_flags = (uint16_t*)s->item_flags.p;
   ca.tile_cnt = (uint32_t*)s->tile_cnt.p;
+  // clip structure of the frame (host side): nesting depth of every clip state, clipped draws present?
+  bool has_clip_ops = false, has_clipped_fills = false;
+  int max_depth = 0;
+  std::vector<uint8_t> op_depth;
+  {
+    std::vector<int> state_depth(h.n_clip_states + 1, 0);
+    for (uint32_t i = 0; i < n_ops; i++) {
+      if (hops[i].kind == SKB_OP_CLIP) {
+        if (!has_clip_ops) op_depth.assign(n_ops, 0);
+        has_clip_ops = true;
+        int d = state_depth[hops[i].clip_in] + 1;
+        if (d > 250) {
+          set_error("clip stack deeper than 250");
+          return SKB_ERROR_UNSUPPORTED;
+        }
+        state_depth[hops[i].clip_out] = d;
+        op_depth[i] = (uint8_t)d;
+        max_depth = std::max(max_depth, d);
+      } else if (hops[i].kind == SKB_OP_FILL && hops[i].clip_in != 0) {
+        has_clipped_fills = true;
+      }
+    }
+  }
+  if (has_clipped_fills) {
+    for (int k = 2; k < SKB_CLIP_PLANES; k++) {
+      SKB_TRY(buf_reserve(s->mask_extra[k - 2], (n_items + 1) * 256));
+      ca.mask[k] = (uint8_t*)s->mask_extra[k - 2].p;
+    }
+    // clipped draws write single bytes of their planes: start from zero
+    for (int k = 0; k < SKB_CLIP_PLANES; k++) SKB_CUDA(cudaMemsetAsync(ca.mask[k], 0, n_items * 256, st));
+  }
   SKB_CUDA(cudaMemsetAsync(s->tile_cnt.p, 0, (size_t)(n_tiles + 1) * 4, st));
   SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
   if (n_items) {
-    SKB_CUDA(cudaMemsetAsync(s->item_flags.p, 0, n_items, st));
+    SKB_CUDA(cudaMemsetAsync(s->item_flags.p, 0, 2 * n_items, st));
     k_cover<<<cdiv(ca.n_trows, COVER_WARPS), COVER_WARPS * 32, 0, st>>>(ca);
     launches++;
+  }
+  cudaEventRecord(s->ev[9], st);
+  if (has_clip_ops && n_rows) {
+    // ---- stage 4b: clip states (by nesting depth), then the clipped draws
+    const uint32_t n_states = h.n_clip_states;
+    SKB_TRY(buf_reserve(s->clip_states, (size_t)(n_states + 2) * sizeof(ClipStateDesc)));
+    SKB_TRY(buf_reserve(s->clip_px, (size_t)(n_states + 2) * 4));
+    SKB_TRY(buf_reserve(s->op_depth, n_ops));
+    SKB_CUDA(cudaMemsetAsync(s->clip_states.p, 0, (size_t)(n_states + 2) * sizeof(ClipStateDesc), st));
+    SKB_CUDA(cudaMemsetAsync(s->clip_px.p, 0, (size_t)(n_states + 2) * 4, st));
+    SKB_CUDA(cudaMemcpyAsync(s->op_depth.p, op_depth.data(), n_ops, cudaMemcpyHostToDevice, st));
+    k_clip_sizes<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, (const SurfDesc*)s->surfs.p, (ClipStateDesc*)s->clip_states.p,
+                                                 (uint32_t*)s->clip_px.p);
+    launches++;
+    SKB_TRY(scan_exclusive(s, (uint32_t*)s->clip_px.p, n_states + 2, &launches));
+    uint32_t total_px = 0;
+    SKB_CUDA(cudaMemcpyAsync(&total_px, (uint32_t*)s->clip_px.p + n_states + 1, 4, cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+    SKB_TRY(buf_reserve(s->clip_table, ((size_t)total_px + 1) * SKB_CLIP_MAXE * 4));
+    SKB_CUDA(cudaMemsetAsync(s->clip_table.p, 0, ((size_t)total_px + 1) * SKB_CLIP_MAXE * 4, st));
+    ClipArgs cl;
+    cl.c = ca;
+    cl.states = (ClipStateDesc*)s->clip_states.p;
+    cl.state_px_off = (const uint32_t*)s->clip_px.p;
+    cl.table = (uint32_t*)s->clip_table.p;
+    cl.op_depth = (const uint8_t*)s->op_depth.p;
+    cl.overflow = counters + 2;
+    cl.n_rows = (uint32_t)n_rows;
+    for (int level = 1; level <= max_depth; level++) {
+      k_clip_rows<<<cdiv(n_rows, 128), 128, 0, st>>>(cl, 0, level);
+      launches++;
+    }
+    if (has_clipped_fills) {
+      k_clip_rows<<<cdiv(n_rows, 128), 128, 0, st>>>(cl, 1, 0);
+      launches++;
+      k_clip_classify<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
+      launches++;
+    }
+    uint32_t over = 0;
+    SKB_CUDA(cudaMemcpyAsync(&over, counters + 2, 4, cudaMemcpyDeviceToHost, st));
+    SKB_CUDA(cudaStreamSynchronize(st));
+    if (over) {
+      set_error("clip stack: a pixel is covered by more clip spans / coverage planes than the device tables hold");
+      return SKB_ERROR_UNSUPPORTED;
+    }
   }
   cudaEventRecord(s->ev[4], st);
   // ---- stage 5: bin
@@ -1318,8 +1576,7 @@ static skb_result run_frame(skb_surface s) {
   fa.ops = t.ops;
   fa.paints = t.paints;
   fa.stops = t.stops;
-  fa.mask0 = ca.mask0;
-  fa.mask1 = ca.mask1;
+  for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.mask[k] = ca.mask[k];
   float ms_fine_tmp = 0;
   (void)ms_fine_tmp;
   if (h.n_surfaces > 1) {
@@ -1480,7 +1737,7 @@ skb_result skb_surface_create(skb_device d, uint32_t w, uint32_t h, skb_surface*
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->canvas, (size_t)s->pitch * s->tiles_y * SKB_TILE);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream);
-  for (int i = 0; i < 10 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+  for (int i = 0; i < 12 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
   if (e != cudaSuccess) {
     set_error(std::string("surface create: ") + cudaGetErrorString(e));
     skb_surface_destroy(s);
@@ -1494,13 +1751,13 @@ void skb_surface_destroy(skb_surface s) {
   if (!s) return;
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
+  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
   for (Buf* b : bufs) buf_free(*b);
   if (s->canvas) cudaFree(s->canvas);
-  for (int i = 0; i < 10; i++)
+  for (int i = 0; i < 12; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -1601,10 +1858,13 @@ skb_result skb_frame_get_stats(skb_surface s, skb_frame_stats* out) {
     float ms = 0;
     // ev: 0 start, 1 after flatten, 2 after setup, 3 after walk, 4 after cover, 5 after bin, 6 after fine(temps),
     //     7 after blur, 8 after fine(canvas)
-    static const int stage_of[8] = {0, 1, 2, 3, 4, 5, 6, 5};
+    //     9 after k_cover (ev 3..9 = coverage, 9..4 = clip stage)
+    static const int from_ev[9] = {0, 1, 2, 3, 9, 4, 5, 6, 7};
+    static const int to_ev[9] = {1, 2, 3, 9, 4, 5, 6, 7, 8};
+    static const int stage_of[9] = {0, 1, 2, 3, 7, 4, 5, 6, 5};
     for (int i = 0; i < 8; i++) s->stats.ms_stage[i] = 0;
-    for (int i = 0; i < 8; i++) {
-      if (cudaEventElapsedTime(&ms, s->ev[i], s->ev[i + 1]) == cudaSuccess) s->stats.ms_stage[stage_of[i]] += ms;
+    for (int i = 0; i < 9; i++) {
+      if (cudaEventElapsedTime(&ms, s->ev[from_ev[i]], s->ev[to_ev[i]]) == cudaSuccess) s->stats.ms_stage[stage_of[i]] += ms;
     }
     if (cudaEventElapsedTime(&ms, s->ev[0], s->ev[8]) == cudaSuccess) s->stats.ms_total = ms;
     cudaGetLastError();
@@ -1628,7 +1888,7 @@ skb_result skb_debug_read_coverage(skb_surface s, uint32_t op, int32_t x, int32_
   ca.n_items = s->n_items;
   ca.mask0 = (uint8_t*)s->mask0.p;
   ca.mask1 = (uint8_t*)s->mask1.p;
-  ca.item_flags = (uint8_t*)s->item_flags.p;
+  ca.item_flags = (uint16_t*)s->item_flags.p;
   k_read_coverage<<<cdiv((uint64_t)w * h, 256), 256, 0, s->stream>>>(ca, op, x, y, w, h, dd, da);
   cudaError_t e = cudaMemcpyAsync(direct, dd, (size_t)w * h, cudaMemcpyDeviceToHost, s->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(accum, da, (size_t)w * h, cudaMemcpyDeviceToHost, s->stream);

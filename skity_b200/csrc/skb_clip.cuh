@@ -1,0 +1,188 @@
+// skb_clip.cuh — the path-clip stack, per pixel row.
+//
+// The reference keeps a clip as a LIST OF SPANS and clips a draw by intersecting span lists
+// (SWCanvas::State::PerformClip / FindSpan, src/render/sw/sw_canvas.cc:158-265).  Observable
+// consequences that a per-pixel min(coverage) would miss, all reproduced here:
+//   * a pixel is blended once per (draw span, clip span) PAIR that covers it, in list order;
+//   * FindSpan's `+ 1` (:257): a clip span that starts inside a draw span S and reaches past its
+//     end also yields the pixel just after S — so the span ending at a pixel matters too;
+//   * the nested clip is the list of those sub-spans (RecursiveClip :178-193), starts included;
+//   * HasClip() is "list non-empty": a clip that rasterised to nothing clips nothing (sw_canvas.hpp:36).
+// The span structure of a rasterised path follows from its trapezoid rows: a directly emitted row
+// gives one-pixel spans under its slanted edges and ONE span for its fully covered interior
+// (blit_full_alpha, sw_raster.cc:303-310); accumulated rows are run-length encoded by equal value
+// (SpanBuilder::Flush, :108-136) and come after the direct spans of the row.
+//
+// One thread sweeps one pixel row left to right (pure per-thread code, shared with the CPU
+// simulation).  Per pixel it forms the "S side" (own direct / own accumulated span, and the direct /
+// accumulated span ENDING at this pixel), reads the "C side" (the clip state's spans covering the
+// pixel: start + coverage, in list order) and emits the ordered list of resulting coverages.
+#ifndef SKB_CLIP_CUH
+#define SKB_CLIP_CUH
+
+#include "skity_b200/csrc/skb_core.cuh"
+
+namespace skb {
+
+#define SKB_CLIP_MAXE 8          // spans of a clip state that may cover one pixel
+#define SKB_CLIP_PLANES 8        // coverage planes of a clipped draw
+#define SKB_CLIP_RMAX 6          // prepared records per row kept in registers/local memory
+#define SKB_CLIP_START_BIAS (1 << 22)
+
+// A clip-state entry: coverage (bits 0-7, never 0) | (span start x + bias) << 8.  0 = no entry.
+SKB_HD uint32_t clip_entry(int start, uint32_t cover) { return cover | ((uint32_t)(start + SKB_CLIP_START_BIAS) << 8); }
+SKB_HD int clip_entry_start(uint32_t e) { return (int)(e >> 8) - SKB_CLIP_START_BIAS; }
+SKB_HD uint32_t clip_entry_cover(uint32_t e) { return e & 0xFF; }
+
+struct SpanSide {   // one span on the S side at the current pixel
+  uint32_t cover;   // 0 = absent
+  int start;
+};
+
+// Ordered output of one pixel.
+struct ClipOut {
+  uint32_t e[SKB_CLIP_MAXE > SKB_CLIP_PLANES ? SKB_CLIP_MAXE : SKB_CLIP_PLANES];
+  int n;
+  bool overflow;
+};
+
+SKB_HD void clip_out_push(ClipOut& o, int cap, int start, uint32_t cover) {
+  if (cover == 0) return;  // zero coverage never changes a pixel
+  if (o.n >= cap) { o.overflow = true; return; }
+  o.e[o.n++] = clip_entry(start, cover);
+}
+
+// Combine the S side of a pixel with the clip spans covering it (FindSpan, all three cases).
+//   own   : S contains the pixel            -> every C gives min(cover), sub-span starts at max(S.x, C.x)
+//   left  : S ends exactly at the pixel     -> only C with C.x > S.x (the `+ 1`), sub-span starts at C.x
+// Order: spans in emission order (direct before accumulated, left before own), C in list order.
+SKB_HDN void clip_combine(const SpanSide& left_d, const SpanSide& own_d, const SpanSide& left_a, const SpanSide& own_a,
+                          const uint32_t* clist, int n_c, bool clipped, int cap, ClipOut& out) {
+  out.n = 0;
+  out.overflow = false;
+  if (!clipped) {  // HasClip() false: the raster spans themselves
+    clip_out_push(out, cap, own_d.start, own_d.cover);
+    clip_out_push(out, cap, own_a.start, own_a.cover);
+    return;
+  }
+  const SpanSide* seq[4] = {&left_d, &own_d, &left_a, &own_a};
+  for (int k = 0; k < 4; k++) {
+    const SpanSide& s = *seq[k];
+    if (s.cover == 0) continue;
+    const bool is_left = (k & 1) == 0;
+    for (int i = 0; i < n_c; i++) {
+      const int cstart = clip_entry_start(clist[i]);
+      const uint32_t ccover = clip_entry_cover(clist[i]);
+      const uint32_t m = ccover < s.cover ? ccover : s.cover;
+      if (is_left) {
+        if (cstart > s.start) clip_out_push(out, cap, cstart, m);
+      } else {
+        clip_out_push(out, cap, cstart > s.start ? cstart : s.start, m);
+      }
+    }
+  }
+}
+
+// Sweep state of one row.
+struct ClipRowState {
+  TrapPrep prep[SKB_CLIP_RMAX];
+  int n_prep;      // records prepared (row has at most SKB_CLIP_RMAX) or -1: evaluate generically
+  // previous pixel
+  uint32_t prev_d, prev_a;
+  int prev_d_start, prev_a_start;
+  bool prev_d_ends;  // the direct span covering the previous pixel ends at the current pixel
+};
+
+// S side of pixel x of a row given its trapezoid records; advances the sweep state.
+// Must be called for consecutive x starting at the row's first possibly covered pixel.
+SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int x, SpanSide& left_d, SpanSide& own_d,
+                           SpanSide& left_a, SpanSide& own_a) {
+  uint32_t d = 0, acc = 0;
+  int d_start = x;
+  bool d_ends_next = true;
+  if (st.n_prep >= 0) {
+    for (int k = 0; k < st.n_prep; k++) {
+      const TrapPrep& p = st.prep[k];
+      uint8_t v;
+      if (!trap_prep_alpha(p, x, &v)) continue;
+      if (!p.accum) {
+        d = v;
+        if (p.mode == 1 && x >= p.jl && x < p.jr) {  // interior of a direct row: one long span
+          d_start = p.jl;
+          d_ends_next = (x + 1 == p.jr);
+        } else {
+          d_start = x;
+          d_ends_next = true;
+        }
+      } else {
+        acc += v;
+      }
+    }
+  } else {
+    uint32_t idx = row.x;
+    for (uint32_t k = 0; k < row.y; k++, idx++) {
+      TrapRec r = pool[idx];
+      if (r.flags & SKB_REC_LINK) {
+        idx = (uint32_t)r.y;
+        r = pool[idx];
+      }
+      const TrapPrep p = trap_prepare(r);
+      uint8_t v;
+      if (!trap_prep_alpha(p, x, &v)) continue;
+      if (!p.accum) {
+        d = v;
+        if (p.mode == 1 && x >= p.jl && x < p.jr) {
+          d_start = p.jl;
+          d_ends_next = (x + 1 == p.jr);
+        } else {
+          d_start = x;
+          d_ends_next = true;
+        }
+      } else {
+        acc += v;
+      }
+    }
+  }
+  const uint32_t a = acc > 255u ? 255u : acc;
+  // spans ending at this pixel
+  left_d.cover = st.prev_d_ends ? st.prev_d : 0u;
+  left_d.start = st.prev_d_start;
+  const bool a_run_continues = a != 0 && a == st.prev_a;
+  left_a.cover = (st.prev_a != 0 && !a_run_continues) ? st.prev_a : 0u;
+  left_a.start = st.prev_a_start;
+  // spans covering this pixel
+  own_d.cover = d;
+  own_d.start = d_start;
+  own_a.cover = a;
+  own_a.start = a_run_continues ? st.prev_a_start : x;
+  // advance
+  st.prev_d = d;
+  st.prev_d_start = d_start;
+  st.prev_d_ends = d != 0 ? d_ends_next : false;
+  st.prev_a = a;
+  st.prev_a_start = own_a.start;
+}
+
+SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
+  st.prev_d = st.prev_a = 0;
+  st.prev_d_start = st.prev_a_start = 0;
+  st.prev_d_ends = false;
+  if (row.y > (uint32_t)SKB_CLIP_RMAX) {
+    st.n_prep = -1;
+    return;
+  }
+  st.n_prep = (int)row.y;
+  uint32_t idx = row.x;
+  for (uint32_t k = 0; k < row.y; k++, idx++) {
+    TrapRec r = pool[idx];
+    if (r.flags & SKB_REC_LINK) {
+      idx = (uint32_t)r.y;
+      r = pool[idx];
+    }
+    st.prep[k] = trap_prepare(r);
+  }
+}
+
+}  // namespace skb
+
+#endif  // SKB_CLIP_CUH

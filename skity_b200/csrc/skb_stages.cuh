@@ -58,7 +58,9 @@ SKB_HD uint32_t f2u_wrap(float f) {
 
 // Second half of RastePath's prologue: bounds_ = floor/ceil(path bounds); scan = bounds ∩ clip,
 // floor/ceil'd; empty test; WalkEdges arguments.  surf_w/h bound the tile rectangle.
-SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t surf_h, bool have_points) {
+// extra_right = 1 for ops that go through the clip stage: FindSpan's `+ 1` can reach the pixel just right of
+// the scan rectangle, so their tile rectangle is one pixel wider.
+SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t surf_h, bool have_points, int extra_right = 0) {
   g.empty = 1;
   g.ntx = g.nty = 0;
   g.tx0 = g.ty0 = 0;
@@ -84,7 +86,7 @@ SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t 
   g.empty = 0;
   // tiles: scan rectangle ∩ surface (SWSpanBrush::Brush clips spans to the bitmap, sw_span_brush.cc:80-99)
   int x0 = g.scan_l < 0 ? 0 : g.scan_l, y0 = g.scan_t < 0 ? 0 : g.scan_t;
-  int x1 = g.scan_r > (int)surf_w ? (int)surf_w : g.scan_r, y1 = g.scan_b > (int)surf_h ? (int)surf_h : g.scan_b;
+  int x1 = g.scan_r + extra_right > (int)surf_w ? (int)surf_w : g.scan_r + extra_right, y1 = g.scan_b > (int)surf_h ? (int)surf_h : g.scan_b;
   if (x0 >= x1 || y0 >= y1) return;  // rasterised but entirely off-surface: no tiles
   g.tx0 = x0 / SKB_TILE;
   g.ty0 = y0 / SKB_TILE;

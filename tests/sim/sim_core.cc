@@ -96,3 +96,170 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Whole-frame CPU simulation (fills, gradients, path clips; no blur): every op goes through the same
+// per-thread stage functions the kernels use, pixels are composited in op order.
+#include "skity_b200/csrc/skb_clip.cuh"
+
+namespace {
+
+struct SimOp {
+  OpGeom g;
+  std::vector<uint2> rows;
+  std::vector<TrapRec> pool;
+  bool ok = false;
+};
+
+void sim_raster_op(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, const float* clip, int even_odd, int surf_w,
+                   int surf_h, SimOp& out) {
+  std::vector<uint32_t> prim_off(n_segs + 1, 0);
+  for (uint32_t i = 0; i < n_segs; i++) prim_off[i + 1] = prim_off[i] + (uint32_t)seg_prim_count(segs[i]);
+  uint32_t n_prims = prim_off[n_segs];
+  OpGeom& g = out.g;
+  std::memset(&g, 0, sizeof(g));
+  g.bmin_x = g.bmin_y = INT_MAX;
+  g.bmax_x = g.bmax_y = INT_MIN;
+  bool have = false;
+  auto bound = [&](V2 p) {
+    have = true;
+    int32_t kx = float_key(p.x), ky = float_key(p.y);
+    if (kx < g.bmin_x) g.bmin_x = kx;
+    if (kx > g.bmax_x) g.bmax_x = kx;
+    if (ky < g.bmin_y) g.bmin_y = ky;
+    if (ky > g.bmax_y) g.bmax_y = ky;
+  };
+  std::vector<Edge> E(2 + 2 * (size_t)n_prims);
+  std::vector<QuadState> Q(E.size());
+  std::memset(E.data(), 0, E.size() * sizeof(Edge));
+  std::memset(Q.data(), 0, Q.size() * sizeof(QuadState));
+  for (uint32_t i = 0; i < n_segs; i++) {
+    if ((segs[i].type_flags & SKB_SEG_TYPE_MASK) == SKB_SEG_POINT) bound(xform(ctm, seg_start_point(segs, i)));
+    int n = (int)(prim_off[i + 1] - prim_off[i]);
+    for (int k = 0; k < n; k++) {
+      V2 p[3];
+      int np = seg_prim(segs, i, k, n, ctm, p);
+      for (int j = 0; j < np; j++) bound(p[j]);
+      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)]);
+    }
+  }
+  op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
+  out.ok = !g.empty;
+  if (g.empty) return;
+  int n_rows = g.scan_b - g.scan_t;
+  out.rows.assign((size_t)n_rows, uint2{0, 0});
+  out.pool.assign((size_t)1 << 14, TrapRec());
+  uint32_t pool_next = 0, overflow = 0;
+  std::vector<int32_t> ord(E.size());
+  for (;;) {
+    std::vector<Edge> Ew = E;
+    std::vector<QuadState> Qw = Q;
+    RecSink sink;
+    sink.pool = out.pool.data();
+    sink.pool_next = &pool_next;
+    sink.pool_cap = (uint32_t)out.pool.size();
+    sink.overflow = &overflow;
+    sink.rows = out.rows.data();
+    sink.row0 = g.scan_t;
+    sink.n_rows = n_rows;
+    sink_init(sink);
+    walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y,
+              g.left_clip, g.right_clip, even_odd, sink);
+    if (!overflow) break;
+    out.pool.resize(out.pool.size() * 4);
+    pool_next = 0;
+    overflow = 0;
+    std::fill(out.rows.begin(), out.rows.end(), uint2{0, 0});
+  }
+}
+
+struct SimClipState {
+  int rx0 = 0, ry0 = 0, rw = 0, rh = 0;
+  std::vector<uint32_t> entries;  // rw*rh*MAXE
+  bool nonempty = false;
+};
+
+}  // namespace
+
+extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba, int64_t* stats) {
+  (void)bytes;
+  const skb_dl_header* h = (const skb_dl_header*)dl;
+  const skb_dl_surface* sd = (const skb_dl_surface*)(dl + h->off_surfaces);
+  const skb_dl_op* ops = (const skb_dl_op*)(dl + h->off_ops);
+  const skb_dl_path* paths = (const skb_dl_path*)(dl + h->off_paths);
+  const skb_dl_seg* segs = (const skb_dl_seg*)(dl + h->off_segs);
+  const skb_dl_paint* paints = (const skb_dl_paint*)(dl + h->off_paints);
+  const float* pool = (const float*)(dl + h->off_stops);
+  if (h->n_surfaces != 1) return -10;  // blur temporaries are not simulated
+  const int W = (int)sd[0].width, H = (int)sd[0].height;
+  std::vector<uint32_t> canvas((size_t)W * H, 0u);
+  std::vector<SimClipState> states(h->n_clip_states + 1);
+  stats[0] = stats[1] = 0;
+  SurfaceView none;
+  none.px = nullptr;
+  none.w = none.h = none.pitch = 0;
+  for (uint32_t i = 0; i < h->n_ops; i++) {
+    const skb_dl_op& o = ops[i];
+    if (o.kind != SKB_OP_FILL && o.kind != SKB_OP_CLIP) return -11;
+    SimOp so;
+    const skb_dl_path& p = paths[o.path];
+    sim_raster_op(segs + p.seg_off, p.n_segs, o.ctm, o.clip_bounds, (int)o.fill_type, W, H, so);
+    const SimClipState* parent = o.clip_in ? &states[o.clip_in] : nullptr;
+    const bool clipped = parent && parent->nonempty;
+    SimClipState* target = nullptr;
+    if (o.kind == SKB_OP_CLIP) {
+      if (o.aux != 1) return -12;  // only intersecting clips
+      target = &states[o.clip_out];
+      if (so.ok) {
+        const OpGeom& g = so.g;
+        target->rx0 = g.scan_l < 0 ? 0 : g.scan_l;
+        target->ry0 = g.scan_t < 0 ? 0 : g.scan_t;
+        int x1 = g.scan_r + 1 > W ? W : g.scan_r + 1, y1 = g.scan_b > H ? H : g.scan_b;
+        target->rw = x1 > target->rx0 ? x1 - target->rx0 : 0;
+        target->rh = y1 > target->ry0 ? y1 - target->ry0 : 0;
+        target->entries.assign((size_t)target->rw * target->rh * SKB_CLIP_MAXE, 0u);
+      }
+    }
+    if (!so.ok) continue;
+    const OpGeom& g = so.g;
+    const skb_dl_paint* paint = o.kind == SKB_OP_FILL ? &paints[o.paint] : nullptr;
+    for (int y = g.scan_t; y < g.scan_b; y++) {
+      if (y < 0 || y >= H) continue;
+      uint2 row = so.rows[(size_t)(y - g.scan_t)];
+      if (row.y == 0) continue;
+      ClipRowState st;
+      clip_row_begin(st, so.pool.data(), row);
+      for (int x = g.scan_l; x <= g.scan_r && x < W; x++) {
+        SpanSide ld, od, la, oa;
+        clip_row_step(st, so.pool.data(), row, x, ld, od, la, oa);
+        if (x < 0) continue;
+        const uint32_t* clist = nullptr;
+        int n_c = 0;
+        if (clipped && x >= parent->rx0 && x < parent->rx0 + parent->rw && y >= parent->ry0 && y < parent->ry0 + parent->rh) {
+          clist = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - parent->rx0)) * SKB_CLIP_MAXE];
+          while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
+        }
+        ClipOut out;
+        clip_combine(ld, od, la, oa, clist, n_c, clipped, o.kind == SKB_OP_CLIP ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, out);
+        if (out.overflow) stats[0]++;
+        if (out.n > stats[1]) stats[1] = out.n;
+        if (o.kind == SKB_OP_CLIP) {
+          if (x >= target->rx0 && x < target->rx0 + target->rw && y >= target->ry0 && y < target->ry0 + target->rh) {
+            uint32_t* e = &target->entries[((size_t)(y - target->ry0) * target->rw + (x - target->rx0)) * SKB_CLIP_MAXE];
+            for (int k = 0; k < out.n; k++) e[k] = out.e[k];
+            if (out.n) target->nonempty = true;
+          }
+        } else {
+          for (int k = 0; k < out.n; k++) {
+            uint32_t cv = clip_entry_cover(out.e[k]);
+            uint32_t galpha = paint->type == SKB_PAINT_IMAGE ? (paint->global_alpha & 0xFF) : 0xFFu;
+            cv &= galpha;
+            if (cv) canvas[(size_t)y * W + x] = blend_cover(canvas[(size_t)y * W + x], paint_color(*paint, pool, none, x, y), cv);
+          }
+        }
+      }
+    }
+  }
+  std::memcpy(out_rgba, canvas.data(), (size_t)W * H * 4);
+  return 0;
+}

@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [_SRC] + [os.path.join(_REPO, "skity_b200", "csrc", f) for f in
-                         ("skb_core.cuh", "skb_walk.cuh", "skb_stages.cuh")] + [os.path.join(_REPO, "include", "skb_dl.h")]
+                         ("skb_core.cuh", "skb_walk.cuh", "skb_stages.cuh", "skb_clip.cuh")] + [os.path.join(_REPO, "include", "skb_dl.h")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                    f"-I{_REPO}", _SRC, "-o", _LIB])
@@ -24,7 +24,22 @@ def lib():
         _lib.sim_path_cover.restype = ctypes.c_long
         _lib.sim_path_cover.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.sim_render_dl.restype = ctypes.c_int
+        _lib.sim_render_dl.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
+
+
+def render_dl(dl):
+    """Whole-frame CPU simulation of the device stages (fills, gradients, path clips; no blur)."""
+    import struct
+    off_surfaces = struct.unpack_from("<18I", dl, 0)[12]
+    w, h = struct.unpack_from("<2I", dl, off_surfaces)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    stats = np.zeros(4, dtype=np.int64)
+    rc = lib().sim_render_dl(dl, len(dl), out.ctypes.data, stats.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"sim_render_dl failed: {rc}")
+    return out, stats
 
 
 def path_cover(segs, ctm, clip, even_odd, w, h):

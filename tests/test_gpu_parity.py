@@ -154,21 +154,74 @@ def test_full_size_c1_properties(dev):
     assert np.array_equal(halves, a)                           # tile-band partition is exact
 
 
-def test_path_clips_not_silently_ignored(dev):
-    """Until the clip stage lands, a display list with Canvas::ClipPath must be refused, not drawn unclipped."""
-    from skity_b200 import device
+def test_golden_clipped_gradients_within_tolerance(dev):
     z = np.load(os.path.join(GOLDEN, "c2_clips_90_512.npz"))
-    surf = dev.create_surface(512, 512)
+    got = render(dev, z["dl"].tobytes(), 512, 512)
+    assert_within_tolerance(got, z["rgba"])
+
+
+def _clip_scene(seed, n, size, every, box, depth=3):
+    """Solid-colour draws (integer maths only -> bit-exact) under a nested ClipPath stack."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    d = 0
+    for i in range(n):
+        if i % every == 0:
+            if d >= depth:
+                while d > 0:
+                    s.restore()
+                    d -= 1
+            s.save()
+            d += 1
+            blob = scene._random_closed_path(rng, rng.uniform(size * .3, size * .7), rng.uniform(size * .3, size * .7), box, 1)
+            s.clip_path(blob, True)
+        cx, cy = rng.uniform(0, size), rng.uniform(0, size)
+        path = scene._random_closed_path(rng, cx, cy, size * 0.5, i)
+        col = tuple(np.float32(v) for v in (rng.uniform(), rng.uniform(), rng.uniform(), rng.uniform(0.4, 1.0)))
+        style = i % 3
+        s.draw_path(path, Paint(style=style, fill=col, stroke=col, stroke_width=float(np.float32(rng.uniform(1, 9)))))
+    while d > 0:
+        s.restore()
+        d -= 1
+    return s
+
+
+@pytest.mark.parametrize("seed", [51, 52, 53])
+def test_nested_path_clips_bit_exact(dev, seed):
+    s = _clip_scene(seed, 90, 400, 15, 260.0)
+    dl = hostlib.encode_scene(s.encode())
+    assert np.array_equal(render(dev, dl, 400, 400), port.render(dl))
+
+
+def test_clip_that_rasterises_to_nothing_clips_nothing(dev):
+    """SWCanvas::State::HasClip() is `!clip_spans_.empty()` (sw_canvas.hpp:36): two disjoint nested clips
+    leave an EMPTY span list, after which draws are not clipped at all."""
+    s = Scene(200, 200)
+    s.save()
+    # two triangles whose bounding boxes overlap but whose interiors do not
+    s.clip_path(PathData().move_to(10, 10).line_to(150, 10).line_to(10, 150).close(), True)
+    s.clip_path(PathData().move_to(190, 190).line_to(190, 60).line_to(60, 190).close(), True)
+    s.draw_rect(0, 0, 200, 200, Paint(fill=(1, 0, 0, 1)))
+    s.restore()
+    dl = hostlib.encode_scene(s.encode())
+    want = port.render(dl)
+    assert want[100, 100, 3] == 255                      # the reference really draws inside the clip bounds
+    assert np.array_equal(render(dev, dl, 200, 200), want)
+
+
+def test_difference_clip_is_refused_not_approximated(dev):
+    from skity_b200 import device
+    s = Scene(64, 64)
+    s.save()
+    s.clip_path(scene.star_path(), False)
+    s.draw_rect(0, 0, 64, 64, Paint(fill=(0, 0, 1, 1)))
+    s.restore()
+    dl = hostlib.encode_scene(s.encode())
+    surf = dev.create_surface(64, 64)
     surf.begin(True)
-    try:
-        surf.encode(z["dl"].tobytes())
-        surf.flush()
-        got = surf.read_pixels()
-        assert_within_tolerance(got, z["rgba"])
-    except device.SkbError as e:
-        assert "clip" in str(e).lower()
-    finally:
-        surf.close()
+    with pytest.raises(device.SkbError):
+        surf.encode(dl)
+    surf.close()
 
 
 def test_plugin_path_matches_reference():

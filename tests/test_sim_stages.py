@@ -68,3 +68,18 @@ def test_sim_strokes_and_transforms():
         s.ops.append(blob[off:off + 8 + nbytes])
         off += 8 + nbytes
     check_scene(s)
+
+
+def test_sim_whole_frame_with_nested_clips():
+    """Clip stage logic (skb_clip.cuh) on the CPU: whole frames with nested ClipPath vs the oracle port."""
+    import os
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c2_clips_90_512.npz"))
+    got, stats = simlib.render_dl(z["dl"].tobytes())
+    assert stats[0] == 0
+    assert np.array_equal(got, z["rgba"])
+    s = scene.scene_c2(60, 384, 6, clip_every=12, clip_box=240.0, max_depth=3)
+    dl = hostlib.encode_scene(s.encode())
+    got, stats = simlib.render_dl(dl)
+    assert stats[0] == 0
+    assert np.array_equal(got, port.render(dl))
