@@ -351,30 +351,27 @@ __device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool
   }
 }
 
-// Range summary of one record kept in registers across the tiles of a row.
-struct RecRange {
-  int L, R, jl, jr;     // pixels [L,R) get a value, [jl,jr) get `full` (all clipped to the scan/surface x-range)
-  int lbase, rbase;     // queue positions of the left-zone [L,jl) and right-zone [jr,R) pixel values
-  uint32_t full_accum;  // full | accum << 8
-};
-#define COVER_RMAX 4
+#define COVER_RSM 8      // records per pixel row summarised in shared memory (more -> generic path)
 #define COVER_WARPS 4
-#define COVER_QCAP 768  // edge-pixel tasks per tile row that fit the shared-memory queue
+#define COVER_QCAP 768   // edge-pixel tasks per tile row that fit the shared-memory queue
+#define COVER_ND (16 * COVER_RSM)
 
 // One warp per (op, tile row).  Lane L owns pixel row L>>1 of the tile row and the 8-pixel half L&1
 // of every tile.  Work is split by KIND of pixel so that the expensive part is evenly spread:
-//   1. each lane summarises its row's trapezoid records as ranges (outside / edge zone / interior);
+//   1. the even lane of each row summarises the row's trapezoid records as ranges
+//      (outside / edge zone / interior) in shared memory;
 //   2. the edge-zone pixels of all 16 rows — the only ones that need the triangle/ramp formulas —
-//      are queued in shared memory and evaluated by all 32 lanes, one task each per round;
-//   3. the tiles of the covered x-range are then assembled with range tests and queue look-ups,
+//      are evaluated by all 32 lanes, one pixel each per round (descriptor found by binary search);
+//   3. the tiles of the covered x-range are then assembled with range tests and look-ups,
 //      classified (empty / solid / partial) by ballot, and stored as coalesced 256-byte A8 masks.
 __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
-  // zone descriptors of the 16 rows x COVER_RMAX records: queue base, record, and the two pixel zones
-  __shared__ int32_t z_base[COVER_WARPS][16 * COVER_RMAX];
-  __shared__ uint32_t z_rec[COVER_WARPS][16 * COVER_RMAX];
-  __shared__ int32_t z_l0[COVER_WARPS][16 * COVER_RMAX];   // left zone  [l0, l0 + nl)
-  __shared__ int32_t z_nl[COVER_WARPS][16 * COVER_RMAX];
-  __shared__ int32_t z_r0[COVER_WARPS][16 * COVER_RMAX];   // right zone [r0, ...)
+  __shared__ int32_t z_base[COVER_WARPS][COVER_ND];   // queue position of the record's first edge pixel
+  __shared__ uint32_t z_rec[COVER_WARPS][COVER_ND];   // record index in the pool
+  __shared__ int32_t z_L[COVER_WARPS][COVER_ND];      // pixels [L, R) get a value (clipped to scan/surface)
+  __shared__ int32_t z_R[COVER_WARPS][COVER_ND];
+  __shared__ int32_t z_jl[COVER_WARPS][COVER_ND];     // pixels [jl, jr) get `full`
+  __shared__ int32_t z_jr[COVER_WARPS][COVER_ND];
+  __shared__ uint16_t z_fa[COVER_WARPS][COVER_ND];    // full | accum << 8
   __shared__ uint8_t q_val[COVER_WARPS][COVER_QCAP];
   const int wib = threadIdx.x >> 5;
   const uint32_t trow = blockIdx.x * COVER_WARPS + wib;
@@ -393,14 +390,13 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   uint2 row = make_uint2(0u, 0u);
   if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)(lane >> 1)];
 
-  // ---- 1. range summaries
-  RecRange rr[COVER_RMAX];
-  uint32_t ridx[COVER_RMAX];
+  // ---- 1. range summaries (even lanes, one per pixel row)
+  const int d0 = (lane >> 1) * COVER_RSM;
   int lo = INT_MAX, hi = INT_MIN;
   int n_tasks = 0;
-  const bool generic = row.y > COVER_RMAX;
+  const bool generic = row.y > COVER_RSM;
   const int nrec = generic ? 0 : (int)row.y;
-  {
+  if (!(lane & 1)) {
     uint32_t idx = row.x;
     for (uint32_t k = 0; k < row.y; k++, idx++) {
       TrapRec r = c.pool[idx];
@@ -409,25 +405,23 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
         r = c.pool[idx];
       }
       const TrapPrep pr = trap_prepare(r);
-      int L = pr.L, R = pr.mode ? pr.R : pr.L;
-      L = max(L, xmin);
-      R = min(R, xmax);
+      int L = max(pr.L, xmin), R = min(pr.mode ? pr.R : pr.L, xmax);
       if (R > L) {
         lo = min(lo, L);
         hi = max(hi, R);
       }
-      if (k < COVER_RMAX) {
-        RecRange q;
-        q.L = L;
-        q.R = max(R, L);
-        q.jl = min(max(pr.jl, q.L), q.R);
-        q.jr = min(max(pr.jr, q.jl), q.R);
-        q.lbase = n_tasks;
-        q.rbase = n_tasks + (q.jl - q.L);
-        q.full_accum = pr.full | (pr.accum ? 0x100u : 0u);
-        if (!generic) n_tasks += (q.jl - q.L) + (q.R - q.jr);
-        rr[k] = q;
-        ridx[k] = idx;
+      if (!generic) {
+        R = max(R, L);
+        const int jl = min(max(pr.jl, L), R);
+        const int jr = min(max(pr.jr, jl), R);
+        z_base[wib][d0 + k] = n_tasks;  // relative to this row's base, fixed up below
+        z_rec[wib][d0 + k] = idx;
+        z_L[wib][d0 + k] = L;
+        z_R[wib][d0 + k] = R;
+        z_jl[wib][d0 + k] = jl;
+        z_jr[wib][d0 + k] = jr;
+        z_fa[wib][d0 + k] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u));
+        n_tasks += (jl - L) + (R - jr);
       }
     }
   }
@@ -438,42 +432,32 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   }
   if (hi <= lo) return;  // nothing in this tile row (item flags were zeroed)
 
-  // ---- 2. queue and evaluate the edge-zone pixels (even lanes own their row's tasks)
-  int mine = (lane & 1) ? 0 : n_tasks;
-  int incl = mine;
+  // ---- 2. evaluate the edge-zone pixels
+  int incl = n_tasks;  // odd lanes contribute 0
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
-  int base = incl - mine;
-  base = __shfl_sync(0xffffffffu, base, lane & ~1);  // the odd lane of a row uses its partner's slots
+  const int base = incl - n_tasks;
   const bool queued = total <= COVER_QCAP;
+  if (!(lane & 1)) {
+    // absolute queue positions; unused descriptor slots take the row's end position so that the
+    // base array stays non-decreasing for the binary search
+    for (int k = 0; k < COVER_RSM; k++) z_base[wib][d0 + k] = k < nrec ? z_base[wib][d0 + k] + base : base + n_tasks;
+  }
+  __syncwarp();
   if (queued) {
-    if (!(lane & 1)) {
-      const int d0 = (lane >> 1) * COVER_RMAX;
-#pragma unroll
-      for (int k = 0; k < COVER_RMAX; k++) {
-        const bool live = k < nrec;
-        z_base[wib][d0 + k] = base + (live ? rr[k].lbase : n_tasks);
-        z_rec[wib][d0 + k] = live ? ridx[k] : 0u;
-        z_l0[wib][d0 + k] = live ? rr[k].L : 0;
-        z_nl[wib][d0 + k] = live ? rr[k].jl - rr[k].L : 0;
-        z_r0[wib][d0 + k] = live ? rr[k].jr : 0;
-      }
-    }
-    __syncwarp();
-    // every lane takes one edge-zone pixel per round: find its descriptor by binary search on the bases
     for (int p = lane; p < total; p += 32) {
-      int lo_d = 0, hi_d = 16 * COVER_RMAX;
+      int lo_d = 0, hi_d = COVER_ND;
       while (hi_d - lo_d > 1) {
         int mid = (lo_d + hi_d) >> 1;
         if (z_base[wib][mid] <= p) lo_d = mid; else hi_d = mid;
       }
       const int off = p - z_base[wib][lo_d];
-      const int nl = z_nl[wib][lo_d];
-      const int x = off < nl ? z_l0[wib][lo_d] + off : z_r0[wib][lo_d] + (off - nl);
+      const int nl = z_jl[wib][lo_d] - z_L[wib][lo_d];
+      const int x = off < nl ? z_L[wib][lo_d] + off : z_jr[wib][lo_d] + (off - nl);
       const TrapPrep pr = trap_prepare(c.pool[z_rec[wib][lo_d]]);
       uint8_t v = 0;
       if (!trap_prep_alpha(pr, x, &v)) v = 0;
@@ -483,40 +467,42 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   }
 
   // ---- 3. assemble, classify and store the tiles
+  const int my_nrec = __shfl_sync(0xffffffffu, nrec, lane & ~1);
+  const bool my_generic = __shfl_sync(0xffffffffu, (int)generic, lane & ~1) != 0;
   const int tx_begin = max(g.tx0, lo / SKB_TILE);
   const int tx_end = min(g.tx0 + g.ntx, (hi + SKB_TILE - 1) / SKB_TILE);
   const uint32_t item_row = c.item_base[op] + tr * (uint32_t)g.ntx;
-  const bool is_fill = o.kind == SKB_OP_FILL;
   for (int tx = tx_begin; tx < tx_end; tx++) {
     const int x0 = tx * SKB_TILE + (lane & 1) * 8;
     uint32_t d[8], a[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
-    if (generic || !queued) {
+    if (my_generic || !queued) {
       cover_row8_generic(c.pool, row, x0, xmin, xmax, d, a);
     } else {
-#pragma unroll
-      for (int k = 0; k < COVER_RMAX; k++) {
-        if (k >= nrec) break;
-        const RecRange q = rr[k];
-        if (q.R <= x0 || q.L >= x0 + 8) continue;
-        const uint32_t full = q.full_accum & 0xFF;
-        const bool accum = (q.full_accum >> 8) & 1;
-        if (x0 >= q.jl && x0 + 8 <= q.jr) {
+      for (int k = 0; k < my_nrec; k++) {
+        const int L = z_L[wib][d0 + k], R = z_R[wib][d0 + k];
+        if (R <= x0 || L >= x0 + 8) continue;
+        const int jl = z_jl[wib][d0 + k], jr = z_jr[wib][d0 + k];
+        const uint32_t fa = z_fa[wib][d0 + k];
+        const uint32_t full = fa & 0xFF;
+        const bool accum = (fa >> 8) & 1;
+        if (x0 >= jl && x0 + 8 <= jr) {
 #pragma unroll
           for (int j = 0; j < 8; j++) {
             if (accum) a[j] += full; else d[j] = full;
           }
           continue;
         }
+        const int qb = z_base[wib][d0 + k];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const int x = x0 + j;
-          if (x < q.L || x >= q.R) continue;
+          if (x < L || x >= R) continue;
           uint32_t v;
-          if (x >= q.jl && x < q.jr) v = full;
-          else if (x < q.jl) v = q_val[wib][base + q.lbase + (x - q.L)];
-          else v = q_val[wib][base + q.rbase + (x - q.jr)];
+          if (x >= jl && x < jr) v = full;
+          else if (x < jl) v = q_val[wib][qb + (x - L)];
+          else v = q_val[wib][qb + (jl - L) + (x - jr)];
           if (accum) a[j] += v; else d[j] = v;
         }
       }
@@ -560,10 +546,8 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
     }
     if (lane == 0) {
       c.item_flags[item] = (uint16_t)flags;
-      if (is_fill) {
-        uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
-        atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
-      }
+      uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
+      atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
     }
   }
 }

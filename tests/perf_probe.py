@@ -14,6 +14,8 @@ for name in which:
     elif name == 'c3': s = scene.scene_c3()
     elif name == 'c3s': s = scene.scene_c3(200, 4096, 3)
     elif name == 'c2': s = scene.scene_c2(20000, 4096, 2, clip_every=0)
+    elif name == 'c2clip': s = scene.scene_c2(20000, 4096, 2)
+    elif name == 'c2clip2k': s = scene.scene_c2(2000, 4096, 2)
     t = time.time(); dl = hostlib.encode_scene(s.encode()); te = time.time() - t
     surf = dev.create_surface(s.width, s.height)
     for it in range(3):
