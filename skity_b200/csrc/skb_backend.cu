@@ -351,7 +351,7 @@ __device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool
   }
 }
 
-#define COVER_RSM 8      // records per pixel row summarised in shared memory (more -> generic path)
+#define COVER_RSM 16     // records per pixel row summarised in shared memory (more -> generic path)
 #define COVER_WARPS 4
 #define COVER_QCAP 768   // edge-pixel tasks per tile row that fit the shared-memory queue
 #define COVER_ND (16 * COVER_RSM)
@@ -373,6 +373,9 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   __shared__ int32_t z_jr[COVER_WARPS][COVER_ND];
   __shared__ uint16_t z_fa[COVER_WARPS][COVER_ND];    // full | accum << 8
   __shared__ uint8_t q_val[COVER_WARPS][COVER_QCAP];
+  __shared__ int32_t r_pre[COVER_WARPS][16];
+  __shared__ int32_t r_cnt[COVER_WARPS][16];
+  __shared__ uint32_t r_first[COVER_WARPS][16];
   const int wib = threadIdx.x >> 5;
   const uint32_t trow = blockIdx.x * COVER_WARPS + wib;
   const int lane = threadIdx.x & 31;
@@ -390,13 +393,62 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   uint2 row = make_uint2(0u, 0u);
   if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)(lane >> 1)];
 
-  // ---- 1. range summaries (even lanes, one per pixel row)
+  // ---- 1. range summaries: the records of the 16 pixel rows are spread over all 32 lanes
   const int d0 = (lane >> 1) * COVER_RSM;
-  int lo = INT_MAX, hi = INT_MIN;
-  int n_tasks = 0;
   const bool generic = row.y > COVER_RSM;
   const int nrec = generic ? 0 : (int)row.y;
+  // exclusive prefix of the per-row record counts (even lanes carry their row, odd lanes 0)
+  int cnt = (lane & 1) ? 0 : nrec;
+  int pre = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, pre, d);
+    if (lane >= d) pre += t;
+  }
+  const int n_tot = __shfl_sync(0xffffffffu, pre, 31);
+  pre -= cnt;
+  int lo = INT_MAX, hi = INT_MIN;
   if (!(lane & 1)) {
+    r_pre[wib][lane >> 1] = pre;
+    r_cnt[wib][lane >> 1] = cnt;
+    r_first[wib][lane >> 1] = row.x;
+  }
+  __syncwarp();
+  for (int p = lane; p < n_tot; p += 32) {
+    // which row owns record p: the last row with records whose prefix is <= p
+    int rr_ = 0;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+      if (r_cnt[wib][r] > 0 && r_pre[wib][r] <= p) rr_ = r;
+    }
+    const int rlane = 2 * rr_;
+    const int k = p - r_pre[wib][rr_];
+    const uint32_t first = r_first[wib][rr_];
+    // k-th record of the row: records are consecutive except for a chunk-link slot (slot 31 of a chunk)
+    uint32_t idx = first + (uint32_t)k;
+    if ((first & (SKB_CHUNK - 1)) + (uint32_t)k >= SKB_CHUNK - 1) {
+      const uint32_t next = (uint32_t)c.pool[first | (SKB_CHUNK - 1)].y;
+      idx = next + ((first & (SKB_CHUNK - 1)) + (uint32_t)k - (SKB_CHUNK - 1));
+    }
+    const TrapPrep pr = trap_prepare(c.pool[idx]);
+    int L = max(pr.L, xmin), R = min(pr.mode ? pr.R : pr.L, xmax);
+    if (R > L) {
+      lo = min(lo, L);
+      hi = max(hi, R);
+    }
+    R = max(R, L);
+    const int jl = min(max(pr.jl, L), R);
+    const int jr = min(max(pr.jr, jl), R);
+    const int at = (rlane >> 1) * COVER_RSM + k;
+    z_rec[wib][at] = idx;
+    z_L[wib][at] = L;
+    z_R[wib][at] = R;
+    z_jl[wib][at] = jl;
+    z_jr[wib][at] = jr;
+    z_fa[wib][at] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u));
+  }
+  // rows with more records than the table holds: extents from a plain scan of their records
+  if (generic && !(lane & 1)) {
     uint32_t idx = row.x;
     for (uint32_t k = 0; k < row.y; k++, idx++) {
       TrapRec r = c.pool[idx];
@@ -410,19 +462,15 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
         lo = min(lo, L);
         hi = max(hi, R);
       }
-      if (!generic) {
-        R = max(R, L);
-        const int jl = min(max(pr.jl, L), R);
-        const int jr = min(max(pr.jr, jl), R);
-        z_base[wib][d0 + k] = n_tasks;  // relative to this row's base, fixed up below
-        z_rec[wib][d0 + k] = idx;
-        z_L[wib][d0 + k] = L;
-        z_R[wib][d0 + k] = R;
-        z_jl[wib][d0 + k] = jl;
-        z_jr[wib][d0 + k] = jr;
-        z_fa[wib][d0 + k] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u));
-        n_tasks += (jl - L) + (R - jr);
-      }
+    }
+  }
+  __syncwarp();
+  // per-row queue sizes and relative bases (even lanes)
+  int n_tasks = 0;
+  if (!(lane & 1)) {
+    for (int k = 0; k < nrec; k++) {
+      z_base[wib][d0 + k] = n_tasks;
+      n_tasks += (z_jl[wib][d0 + k] - z_L[wib][d0 + k]) + (z_R[wib][d0 + k] - z_jr[wib][d0 + k]);
     }
   }
 #pragma unroll
