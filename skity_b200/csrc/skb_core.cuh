@@ -95,12 +95,12 @@ SKB_HD int32_t f2i(float v) {
 //                                            a whole path's active list in shared memory
 //   QuadState (SWQuadEdge, sw_edge.hpp:65-81) — forward-difference state, touched only when an edge
 //                                            steps to its next chord; stays in global memory
-struct Edge {
+struct alignas(8) Edge {
   fx x, y, dx, dy, upper_x, upper_y, lower_y;
   int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24 | quadratic << 25
   int32_t prev, next;
 };
-struct QuadState {
+struct alignas(8) QuadState {
   fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y, snapped_x, snapped_y;
 };
 SKB_HD int edge_count(const Edge& e) { return e.curve & 0xFF; }
@@ -462,7 +462,7 @@ SKB_HDN int seg_prim(const skb_dl_seg* segs, uint32_t i, int k, int n_prims, con
 
 // ------------------------------------------------- trapezoid rows (walker output)
 // One call of blit_trapezoid_row (sw_raster.cc:457-544) as the walker would make it.
-struct TrapRec {
+struct alignas(16) TrapRec {  // 32 bytes: moved as two 128-bit words
   int32_t y;           // pixel row
   fx ul, ur, ll, lr;   // upper-left/right, lower-left/right x of the band's interval
   fx ldy, rdy;         // |dy/dx| of the left / right edge
