@@ -30,6 +30,10 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this
+# workload (profiles/r01_ncu_top3_c1.txt); None where no capture exists
+NCU_TRAFFIC = {("c1", "k_walk"): 35013120 + 118759680, ("c1", "k_cover"): 146969856 + 129862912}
+
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
 
@@ -160,14 +164,14 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = np.zeros(8)
     launches = 0
-    bytes_fine = bytes_cover = 0
+    bytes_fine = bytes_cover = bytes_walk = 0
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
         st = surf.stats()      # waits for the frame; per-stage CUDA-event timings of this step
         stage_ms += np.array(st["ms_stage"])
         launches += st["n_launches"]
-        bytes_fine, bytes_cover = st["bytes_fine"], st["bytes_cover"]
+        bytes_fine, bytes_cover, bytes_walk = st["bytes_fine"], st["bytes_cover"], st["bytes_walk"]
     e1.record(stream)
     barrier()
     ms_resident = e0.elapsed_time(e1) / args.steps
@@ -197,13 +201,12 @@ def run_ours(args):
         stage_ms /= args.steps
         peak, peak_kind = measured_peak()
         names = device.STAGE_NAMES
-        # dominant kernel: coverage (k_cover) or fine (k_fine) are the two HBM-facing passes the
-        # north star sets the roofline target on; report whichever takes longer, plus both in `stages`
-        cover_ms, fine_ms = float(stage_ms[3]), float(stage_ms[5])
-        if cover_ms >= fine_ms:
-            dom, dom_ms, dom_bytes = "k_cover (coverage)", cover_ms, bytes_cover
-        else:
-            dom, dom_ms, dom_bytes = "k_fine (fine)", fine_ms, bytes_fine
+        # dominant kernel = the longest of the three data-facing stages, each a single kernel:
+        # k_walk (sweep), k_cover (coverage), k_fine (paint + blend)
+        cands = [("k_walk (edge sweep)", float(stage_ms[2]), bytes_walk),
+                 ("k_cover (coverage)", float(stage_ms[3]), bytes_cover),
+                 ("k_fine (paint+blend)", float(stage_ms[5]), bytes_fine)]
+        dom, dom_ms, dom_bytes = max(cands, key=lambda c: c[1])
         achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -218,9 +221,11 @@ def run_ours(args):
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(ms_e2e, 4)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": None, "peak_kind": peak_kind,
+                         "frac": round(achieved / peak, 5), "traffic": NCU_TRAFFIC.get((args.workload, dom.split()[0])),
+                         "peak_kind": peak_kind,
                          "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": round(dom_ms, 4)},
-            "stages_ms": {names[i]: round(float(stage_ms[i]), 4) for i in range(7)},
+            "stages_ms": {names[i]: round(float(stage_ms[i]), 4) for i in range(8)},
+            "stage_frac_of_hbm_roofline": {n: round(b / (m / 1e3) / 1e9 / peak, 5) if m > 0 else None for n, m, b in cands},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

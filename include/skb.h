@@ -66,6 +66,7 @@ typedef struct skb_frame_stats {
   float ms_stage[8];     /* 0 flatten, 1 setup+scans, 2 walk, 3 coverage, 4 bin, 5 fine, 6 blur, 7 clip */
   uint64_t bytes_fine;   /* algorithmic bytes of the fine pass (pixels + commands + masks) */
   uint64_t bytes_cover;  /* algorithmic bytes of the coverage pass (records in, masks out) */
+  uint64_t bytes_walk;   /* algorithmic bytes of the sweep (edge slots in, records + row table out) */
 } skb_frame_stats;
 
 SKB_API skb_result skb_device_create(int ordinal, skb_device* out_device);
