@@ -58,6 +58,29 @@ def golden_scenes():
     p2.move_to(10, 10).quad_to(250, 20, 120, 240).close()
     s.draw_path(p2, Paint(fill=(0.7, 0.1, 0.6, 0.6)))
     out["wrap_8192_256"] = s
+    # the reference's own unit test SWCanvas.StrokeThenFillDrawsFillAfterStroke (test/ut/render/sw_canvas_test.cc:67-86)
+    s = Scene(48, 48)
+    s.draw_rect(10, 10, 34, 34, Paint(style=3, stroke_width=10.0, stroke=(1, 0, 0, 1), fill=(1, 1, 1, 1)))
+    out["ut_stroke_then_fill_48"] = s
+    # the reference's golden test ShapeGolden.CanonicalEdgesExact (test/golden/cases/shape/shape.cc:624-672)
+    s = Scene(192, 144)
+    s.draw_rect(0, 0, 192, 144, Paint(fill=(0, 0, 0, 1)))          # canvas->Clear(Color_BLACK)
+    white = Paint(fill=(1, 1, 1, 1))
+
+    def add_rect(p, l, t, r, b):                                    # Path::AddRect, kCW from the top-left corner
+        return p.move_to(l, t).line_to(r, t).line_to(r, b).line_to(l, b).close()
+    w = PathData(scene.WINDING)
+    add_rect(w, 8.5, 8.5, 31.5, 31.5)
+    w.move_to(40, 8).line_to(72, 24).line_to(40, 40).close()
+    w.move_to(88, 8).line_to(88, 40).line_to(120, 24).close()
+    w.move_to(16, 48).line_to(48, 64).line_to(16, 80).line_to(0, 64).close()
+    add_rect(w, 128.5, 8.5, 151.5, 87.5)
+    s.draw_path(w, white)
+    e = PathData(scene.EVEN_ODD)
+    add_rect(e, 72.5, 48.5, 119.5, 87.5)
+    add_rect(e, 88.5, 60.5, 103.5, 76.5)
+    s.draw_path(e, white)
+    out["golden_canonical_edges_192x144"] = s
     return out
 
 
@@ -68,8 +91,15 @@ def main():
         rgba = refsw.render_scene(blob)
         dl = hostlib.encode_scene(blob)
         path = os.path.join(HERE, name + ".npz")
+        extra = {}
+        if name == "golden_canonical_edges_192x144":
+            # the reference's checked-in golden image of this test (coverage-AA GPU backend, exact-match rule):
+            # decoded here so the vector travels without the reference tree
+            from PIL import Image
+            png = "/root/reference/test/golden/cases/shape/coverage_aa_images/canonical_edges_exact.png"
+            extra["reference_png"] = np.array(Image.open(png).convert("RGBA"))
         np.savez_compressed(path, scene=np.frombuffer(blob, dtype=np.uint8), dl=np.frombuffer(dl, dtype=np.uint8),
-                            rgba=rgba)
+                            rgba=rgba, **extra)
         print(f"{name}: {rgba.shape[1]}x{rgba.shape[0]} sum={int(rgba.astype(np.int64).sum())} "
               f"-> {os.path.getsize(path)} bytes")
     # span-level vectors: SWRaster::RastePath of a few paths
