@@ -96,6 +96,9 @@ SKB_API skb_result skb_surface_read_pixels(skb_surface surface, uint32_t x, uint
 /* Uploads pixels into the surface (the LockCanvas(false) case: drawing over existing content). */
 SKB_API skb_result skb_surface_write_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
                                             uint32_t height, const void* src, size_t stride);
+/* Reads back surface `index` (> 0) of the last flushed display list — a canvas of a batch
+ * (SKB_SURFACE_CANVAS in include/skb_dl.h).  Valid until the next skb_frame_flush. */
+SKB_API skb_result skb_frame_read_surface(skb_surface surface, uint32_t index, void* dst, size_t stride);
 SKB_API skb_result skb_surface_device_ptr(skb_surface surface, void** out_ptr, size_t* out_pitch_bytes);
 SKB_API skb_result skb_surface_stream(skb_surface surface, void** out_cuda_stream);
 

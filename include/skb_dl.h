@@ -47,6 +47,12 @@ typedef struct skb_dl_header {
   uint32_t reserved1[2];
 } skb_dl_header; /* 80 bytes */
 
+/* flags bit 0: the surface is a CANVAS of a batch (a final image the caller reads back with
+ * skb_frame_read_surface), not a blur temporary.  Canvases are composited after the blur stage,
+ * like surface 0.  A batch of independent canvases is one display list whose ops target surfaces
+ * 1..N: all canvases share every launch, which is what makes many small canvases efficient. */
+#define SKB_SURFACE_CANVAS 1u
+
 typedef struct skb_dl_surface {
   uint32_t width;
   uint32_t height;

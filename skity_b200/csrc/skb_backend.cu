@@ -45,6 +45,8 @@ struct SurfDesc {
   uint32_t tiles_x, tiles_y;
   uint32_t tile_base;   // first global tile index
   uint32_t row0, row1;  // rows this device renders (band), whole surface for temporaries
+  uint32_t final_pass;  // composited after the blur stage (surface 0 and batch canvases)
+  uint32_t pad;
 };
 
 #define SKB_CMD_SOLID 0x80000000u
@@ -797,6 +799,7 @@ struct FineArgs {
   const uint2* cmds;
   uint2* cmds_sorted;  // scratch for tiles whose list does not fit the shared-memory sorter
   uint32_t tile_begin, tile_end;
+  uint32_t final_pass;  // which surfaces this launch composites
   const SurfDesc* surfs;
   const uint32_t* surf_tile_base;  // n_surfaces + 1
   uint32_t n_surfaces;
@@ -819,6 +822,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
   if (n == 0) return;
   const uint32_t s = find_interval(a.surf_tile_base, a.n_surfaces, tile);
   const SurfDesc sd = a.surfs[s];
+  if (sd.final_pass != a.final_pass) return;
   const uint32_t local = tile - sd.tile_base;
   const int tx = (int)(local % sd.tiles_x), ty = (int)(local / sd.tiles_x);
   const int y = ty * SKB_TILE + (lane >> 1);
@@ -1323,6 +1327,8 @@ static skb_result run_frame(skb_surface s) {
     d.tile_base = tile_base[i];
     d.row0 = 0;
     d.row1 = d.h;
+    d.final_pass = (i == 0 || (hs[i].flags & SKB_SURFACE_CANVAS)) ? 1u : 0u;
+    d.pad = 0;
     tile_base[i + 1] = tile_base[i] + d.tiles_x * d.tiles_y;
     if (i > 0) {
       temp_off[i] = temp_bytes;
@@ -1338,6 +1344,10 @@ static skb_result run_frame(skb_surface s) {
   for (uint32_t i = 1; i < h.n_surfaces; i++) surfs[i].px = (uint8_t*)s->temp_px.p + temp_off[i];
   if (temp_bytes) SKB_CUDA(cudaMemsetAsync(s->temp_px.p, 0, temp_bytes, st));
   const uint32_t n_tiles = tile_base[h.n_surfaces];
+  bool has_temporaries = false, has_batch_canvases = false;
+  for (uint32_t i = 1; i < h.n_surfaces; i++) {
+    if (surfs[i].final_pass) has_batch_canvases = true; else has_temporaries = true;
+  }
   S.n_tiles = n_tiles;
   SKB_TRY(buf_reserve(s->surfs, surfs.size() * sizeof(SurfDesc)));
   SKB_TRY(buf_reserve(s->surf_tile_base, tile_base.size() * 4));
@@ -1614,7 +1624,8 @@ static skb_result run_frame(skb_surface s) {
   if (h.n_surfaces > 1) {
     fa.tile_begin = tile_base[1];
     fa.tile_end = n_tiles;
-    if (fa.tile_end > fa.tile_begin) {
+    fa.final_pass = 0;
+    if (fa.tile_end > fa.tile_begin && has_temporaries) {
       k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
       launches++;
     }
@@ -1695,7 +1706,14 @@ static skb_result run_frame(skb_surface s) {
     uint32_t ty0 = surfs[0].row0 / SKB_TILE, ty1 = cdiv(surfs[0].row1, SKB_TILE);
     fa.tile_begin = ty0 * surfs[0].tiles_x;
     fa.tile_end = ty1 * surfs[0].tiles_x;
+    fa.final_pass = 1;
     if (fa.tile_end > fa.tile_begin) {
+      k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
+      launches++;
+    }
+    if (has_batch_canvases) {  // the canvases of a batch: every surface flagged SKB_SURFACE_CANVAS
+      fa.tile_begin = tile_base[1];
+      fa.tile_end = n_tiles;
       k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
       launches++;
     }
@@ -1866,6 +1884,16 @@ skb_result skb_surface_write_pixels(skb_surface s, uint32_t x, uint32_t y, uint3
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   SKB_CUDA(cudaMemcpy2DAsync(s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, src, stride, (size_t)w * 4, h,
                              cudaMemcpyHostToDevice, s->stream));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_frame_read_surface(skb_surface s, uint32_t index, void* dst, size_t stride) {
+  if (!s || !dst || !s->flushed || index == 0 || index >= s->h_surfs.size()) return SKB_ERROR_INVALID_ARGUMENT;
+  const SurfDesc& d = s->h_surfs[index];
+  if (stride < (size_t)d.w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaMemcpy2DAsync(dst, stride, d.px, d.pitch, (size_t)d.w * 4, d.h, cudaMemcpyDeviceToHost, s->stream));
   SKB_CUDA(cudaStreamSynchronize(s->stream));
   return SKB_SUCCESS;
 }

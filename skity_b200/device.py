@@ -61,6 +61,7 @@ def lib():
         L.skb_surface_sync.argtypes = [vp]
         L.skb_surface_read_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_surface_write_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
+        L.skb_frame_read_surface.argtypes = [vp, u32, vp, sz]
         L.skb_surface_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
         L.skb_surface_stream.argtypes = [vp, ctypes.POINTER(vp)]
         L.skb_frame_get_stats.argtypes = [vp, ctypes.POINTER(FrameStats)]
@@ -143,6 +144,13 @@ class Surface:
         rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
         h, w, _ = rgba.shape
         _check(lib().skb_surface_write_pixels(self._h, x, y, w, h, rgba.ctypes.data, w * 4), "skb_surface_write_pixels")
+
+    def read_batch_canvas(self, index, width, height, out=None):
+        """Read back canvas `index` (1-based) of the last flushed batch display list."""
+        if out is None:
+            out = np.empty((height, width, 4), dtype=np.uint8)
+        _check(lib().skb_frame_read_surface(self._h, index, out.ctypes.data, width * 4), "skb_frame_read_surface")
+        return out
 
     def device_ptr(self):
         p, pitch = ctypes.c_void_p(), ctypes.c_size_t()

@@ -38,6 +38,41 @@ int skbh_encode_scene(const uint8_t* scene, size_t n, uint8_t** out, size_t* out
   return 0;
 }
 
+// Batch of independent canvases: scene i is replayed onto its own canvas surface of ONE
+// display list; surface 0 is a 16x16 dummy.  `scenes` holds the blobs back to back, sizes[i] bytes each.
+// canvas_ids[i] receives the surface index of scene i's canvas (blur temporaries take indices in between).
+int skbh_encode_scene_batch(const uint8_t* scenes, const size_t* sizes, uint32_t count, uint32_t* canvas_ids,
+                            uint8_t** out, size_t* out_n, char* unsupported, size_t cap) {
+  skb::DlBuilder builder;
+  builder.Reset(16, 16);
+  std::string first_unsupported;
+  size_t off = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    if (sizes[i] < sizeof(skb_scene::Header)) return -1;
+    skb_scene::Header h;
+    std::memcpy(&h, scenes + off, sizeof(h));
+    if (h.magic != skb_scene::kMagic) return -1;
+    uint32_t sid = builder.AddSurface(h.width, h.height, SKB_SURFACE_CANVAS);
+    if (canvas_ids) canvas_ids[i] = sid;
+    skity::CudaCanvas canvas(&builder, sid, h.width, h.height);
+    int rc = skb_scene::Play(scenes + off, sizes[i], &canvas);
+    if (rc != 0) return rc;
+    canvas.Flush();
+    if (first_unsupported.empty()) first_unsupported = canvas.Unsupported();
+    off += sizes[i];
+  }
+  std::vector<uint8_t> blob = builder.Serialize();
+  *out = static_cast<uint8_t*>(std::malloc(blob.size() ? blob.size() : 1));
+  if (!*out) return -8;
+  std::memcpy(*out, blob.data(), blob.size());
+  *out_n = blob.size();
+  if (unsupported && cap) {
+    std::strncpy(unsupported, first_unsupported.c_str(), cap - 1);
+    unsupported[cap - 1] = 0;
+  }
+  return 0;
+}
+
 void skbh_free(void* p) { std::free(p); }
 
 }  // extern "C"

@@ -30,10 +30,11 @@ class DlBuilder {
     AddSurface(canvas_w, canvas_h);
   }
 
-  uint32_t AddSurface(uint32_t w, uint32_t h) {
+  uint32_t AddSurface(uint32_t w, uint32_t h, uint32_t flags = 0) {
     skb_dl_surface s{};
     s.width = w;
     s.height = h;
+    s.flags = flags;
     surfaces_.push_back(s);
     return static_cast<uint32_t>(surfaces_.size() - 1);
   }

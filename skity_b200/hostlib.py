@@ -18,6 +18,10 @@ def lib():
                                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_encode_scene.restype = ctypes.c_int
         _lib.skbh_free.argtypes = [ctypes.c_void_p]
+        _lib.skbh_encode_scene_batch.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_uint32,
+                                                 ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                                 ctypes.c_char_p, ctypes.c_size_t]
+        _lib.skbh_encode_scene_batch.restype = ctypes.c_int
         _lib.skbh_render_scene_cuda.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_render_scene_cuda.restype = ctypes.c_int
@@ -39,6 +43,27 @@ def encode_scene(blob, allow_unsupported=False):
     if msg.value and not allow_unsupported:
         raise RuntimeError(f"scene uses a feature outside the CUDA backend's scope: {msg.value.decode()}")
     return data
+
+
+def encode_scene_batch(blobs, allow_unsupported=False):
+    """Replay a batch of independent scenes into ONE display list.  Returns (display list bytes, canvas surface
+    index of every scene) — blur temporaries take surface indices in between."""
+    joined = b"".join(blobs)
+    sizes = (ctypes.c_size_t * len(blobs))(*[len(b) for b in blobs])
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    msg = ctypes.create_string_buffer(256)
+    ids = (ctypes.c_uint32 * len(blobs))()
+    rc = lib().skbh_encode_scene_batch(joined, sizes, len(blobs), ids, ctypes.byref(out), ctypes.byref(n), msg, 256)
+    if rc != 0:
+        raise RuntimeError(f"skbh_encode_scene_batch failed: {rc}")
+    try:
+        data = ctypes.string_at(out, n.value)
+    finally:
+        lib().skbh_free(out)
+    if msg.value and not allow_unsupported:
+        raise RuntimeError(f"scene uses a feature outside the CUDA backend's scope: {msg.value.decode()}")
+    return data, list(ids)
 
 
 def render_scene_cuda(blob, device_ordinal=0):

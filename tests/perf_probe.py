@@ -11,6 +11,15 @@ for name in which:
     elif name == 'p100k': s = scene.scene_random_fills_fast(100000, 8192, 9, box=192.0)
     elif name == 'c4a': s = scene.scene_c4a()
     elif name == 'c4b': s = scene.scene_c4b(0)
+    elif name.startswith('c4bbatch'):
+        n = int(name[8:] or 64)
+        blobs = [scene.scene_c4b(i).encode() for i in range(n)]
+        t = time.time(); dl, _ids = hostlib.encode_scene_batch(blobs); te = time.time() - t
+        surf = dev.create_surface(16, 16)
+        for it in range(3):
+            surf.begin(True); surf.encode(dl); surf.flush(); surf.sync(); st = surf.stats()
+        print(name, 'encode %.2fs' % te, 'dev %.2f ms' % st['ms_total'], dict(zip(device.STAGE_NAMES, [round(x, 3) for x in st['ms_stage']])), 'canvases/s %.0f' % (n / st['ms_total'] * 1e3), 'Mpix/s %.0f' % (n * 1920 * 1080 / 1e3 / st['ms_total']), 'paths/s %.0f' % (n * 1000 / st['ms_total'] * 1e3), flush=True)
+        surf.close(); continue
     elif name == 'c3': s = scene.scene_c3()
     elif name == 'c3s': s = scene.scene_c3(200, 4096, 3)
     elif name == 'c2': s = scene.scene_c2(20000, 4096, 2, clip_every=0)

@@ -232,3 +232,48 @@ def test_plugin_path_matches_reference():
     assert np.array_equal(got, z["rgba"])
     z = np.load(os.path.join(GOLDEN, "mixed_transform_clip_400x300.npz"))
     assert np.array_equal(hostlib.render_scene_cuda(z["scene"].tobytes()), z["rgba"])
+
+
+def test_batch_of_canvases_in_one_display_list(dev):
+    """A batch of independent canvases (BASELINE config 4b) is ONE display list whose ops target canvas
+    surfaces 1..N: every canvas must equal what it renders to on its own."""
+    scenes = [scene.scene_random_fills(60, 0, 70, box=150.0, width=320, height=200),
+              scene.scene_c0(),
+              _clip_scene(71, 40, 256, 10, 180.0),
+              scene.scene_random_fills(25, 0, 72, box=90.0, width=97, height=131),
+              scene.scene_c3(3, 300, 73, box=100.0)]
+    blobs = [s.encode() for s in scenes]
+    dl, ids = hostlib.encode_scene_batch(blobs)
+    assert ids[0] == 1 and ids[2] > 3          # blur temporaries of the star scene sit in between
+    surf = dev.create_surface(16, 16)
+    surf.begin(True)
+    surf.encode(dl)
+    surf.flush()
+    for i, s in enumerate(scenes):
+        got = surf.read_batch_canvas(ids[i], s.width, s.height)
+        want = port.render(hostlib.encode_scene(blobs[i]))
+        assert np.array_equal(got, want), f"canvas {i}"
+    surf.close()
+
+
+def test_large_canvas_band_split_and_determinism(dev):
+    """16384 x 16384 (BASELINE config 4a's canvas): four tile bands reproduce the whole frame."""
+    s = scene.scene_random_fills_fast(40000, 16384, 4, box=128.0)
+    dl = hostlib.encode_scene(s.encode())
+    surf = dev.create_surface(16384, 16384)
+    surf.begin(True)
+    surf.encode(dl)
+    surf.flush()
+    whole = surf.read_pixels(0, 0, 16384, 8192)          # the reference wraps coordinates >= 8192 px: upper half only
+    ssum = int(whole.astype(np.uint64).sum())
+    assert ssum > 0
+    from skity_b200 import multigpu
+    bands = multigpu.band_ranges(16384, 4)
+    got = np.zeros_like(whole)
+    for (y0, y1) in bands[:2]:
+        surf.set_band(y0, y1)
+        surf.begin(True)
+        surf.flush()
+        got[y0:y1] = surf.read_pixels(0, y0, 16384, y1 - y0)
+    surf.close()
+    assert np.array_equal(got, whole)
