@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(64) k_walk(WalkArgs a, int lane_stride) {
   Edge* E = reinterpret_cast<Edge*>(region);
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
   walk_path(E, Q, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
-            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink);
+            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink, 1);
 }
 
 // ---------------------------------------------------------------- stage 4: coverage

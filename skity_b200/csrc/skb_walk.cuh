@@ -300,10 +300,15 @@ SKB_HD bool too_close_edges(const Edge* E, int prev, int next, fx lowerY) {  // 
 // Bounds are the integers SWRaster::RastePath derives (sw_raster.cc:741-780).
 // Q holds the quadratic state of slot i at Q[qmap ? qmap[i] : i] (qmap lets a caller that packed
 // the live edges into a smaller array keep the quadratic state where the flatten stage left it).
-SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots, int32_t* ord, float scan_top_f,
-                       float scan_bottom_f, int start_y, int stop_y, fx left_clip, fx right_clip, int even_odd,
-                       RecSink& sink) {
-  // SWEdgeBuilder culling (sw_edge.cc:322-336) + SortEdges + ProcessEdges (sw_raster.cc:679-729)
+// `flat` selects the single-loop form of the band sweep (walk_bands_flat), which is what the GPU runs.
+struct WalkState {
+  fx y, nny;
+};
+
+// SWEdgeBuilder culling (sw_edge.cc:322-336) + SortEdges + ProcessEdges (sw_raster.cc:679-729) and
+// the prologue of WalkEdges (:549-563).  Returns false when the path has no edge to sweep.
+SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
+                           fx left_clip, fx right_clip, WalkState& ws) {
   int n = 0;
   for (int i = 2; i < n_slots; i++) {
     if (!((E[i].curve >> 24) & 1)) continue;
@@ -315,7 +320,7 @@ SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots,
     if (can_be_ignored(scan_top_f, scan_bottom_f, y0, y1)) continue;
     ord[n++] = i;
   }
-  if (n == 0) return;
+  if (n == 0) return false;
   sort_edge_indices(E, ord, n);
   for (int i = 0; i < n; i++) {
     E[ord[i]].prev = i == 0 ? SKB_HEAD : ord[i - 1];
@@ -324,32 +329,39 @@ SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots,
   Edge& H = E[SKB_HEAD];
   Edge& T = E[SKB_TAIL];
   H.prev = -1; H.next = ord[0];
-  H.upper_y = H.lower_y = SKB_FX_MIN; H.x = SKB_FX_MIN; H.dx = 0; H.dy = SKB_FX_MAX; H.upper_x = SKB_FX_MIN;
+  H.upper_y = H.lower_y = SKB_FX_MIN; H.dx = 0; H.dy = SKB_FX_MAX;
   H.curve = 0; H.y = 0;
   T.prev = ord[n - 1]; T.next = -1;
-  T.upper_y = T.lower_y = SKB_FX_MAX; T.x = SKB_FX_MAX; T.dx = 0; T.dy = SKB_FX_MAX; T.upper_x = SKB_FX_MAX;
+  T.upper_y = T.lower_y = SKB_FX_MAX; T.dx = 0; T.dy = SKB_FX_MAX;
   T.curve = 0; T.y = 0;
-
   // WalkEdges (sw_raster.cc:546-677)
   H.x = H.upper_x = left_clip;
   T.x = T.upper_x = right_clip;
   fx y = fx_max(E[H.next].upper_y, i_to_fx(start_y));
   fx nny = SKB_FX_MAX;
-  {
-    int e;
-    for (e = H.next; E[e].upper_y <= y; e = E[e].next) {
-      Edge& q = E[e];  // SWEdge::GoY(dst) (sw_edge.hpp:43-51)
-      if (y == fx_add(q.y, SKB_FX1)) {
-        q.x = fx_add(q.x, q.dx);
-        q.y = y;
-      } else if (q.y != y) {
-        q.x = fx_add(q.upper_x, fx_mul(q.dx, fx_sub(q.y, q.upper_y)));
-        q.y = y;
-      }
-      upd_nny(q.lower_y, y, &nny);
+  int e;
+  for (e = H.next; E[e].upper_y <= y; e = E[e].next) {
+    Edge& q = E[e];  // SWEdge::GoY(dst) (sw_edge.hpp:43-51)
+    if (y == fx_add(q.y, SKB_FX1)) {
+      q.x = fx_add(q.x, q.dx);
+      q.y = y;
+    } else if (q.y != y) {
+      q.x = fx_add(q.upper_x, fx_mul(q.dx, fx_sub(q.y, q.upper_y)));
+      q.y = y;
     }
-    upd_nny(E[e].upper_y, y, &nny);
+    upd_nny(q.lower_y, y, &nny);
   }
+  upd_nny(E[e].upper_y, y, &nny);
+  ws.y = y;
+  ws.nny = nny;
+  return true;
+}
+
+// The band loop as the reference writes it: a loop over bands around a loop over the active edges.
+SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, WalkState ws, int stop_y, fx left_clip,
+                               fx right_clip, int even_odd, RecSink& sink) {
+  Edge& H = E[SKB_HEAD];
+  fx y = ws.y, nny = ws.nny;
   const int mask = even_odd ? 1 : -1;
   for (;;) {
     int w = 0;
@@ -443,6 +455,140 @@ SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots,
   }
   sink_flush_row(sink);
 }
+
+// The same sweep as ONE loop: every iteration handles one active edge and, when that was the last
+// edge of the band, the band's epilogue and the next band's prologue.  A warp of 32 paths then runs
+// the same instruction stream however many edges and bands each path has — the nested form makes
+// every lane wait for the longest inner loop of the warp at every band.
+SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx left_clip, fx right_clip,
+                             int even_odd, RecSink& sink) {
+  const int mask = even_odd ? 1 : -1;
+  const fx stop_fx = i_to_fx(stop_y);
+  fx y = ws.y, nny = ws.nny;
+  int w = 0, cur = 0, left_edge = SKB_HEAD, prev_right = 0, y_shift = 0;
+  bool in_interval = false;
+  fx prev_x = 0, next_y = 0, left = 0, left_dy = 0;
+  uint32_t full = 0;
+#define SKB_BEGIN_BAND()                                                        \
+  do {                                                                          \
+    w = 0;                                                                      \
+    in_interval = false;                                                        \
+    prev_x = left_clip;                                                         \
+    next_y = fx_min(nny, fx_ceil_fx(fx_add(y, 1)));                             \
+    cur = E[SKB_HEAD].next;                                                     \
+    left_edge = SKB_HEAD;                                                       \
+    left = left_clip;                                                           \
+    left_dy = 0;                                                                \
+    prev_right = fx_floor_i(left_clip);                                         \
+    nny = SKB_FX_MAX;                                                           \
+    y_shift = 0;                                                                \
+    if (fx_sub(next_y, y) & (SKB_FX1 >> 2)) {                                   \
+      y_shift = 2;                                                              \
+      next_y = fx_add(y, SKB_FX1 >> 2);                                         \
+    } else if (fx_sub(next_y, y) & (SKB_FX1 >> 1)) {                            \
+      y_shift = 1;                                                              \
+    }                                                                           \
+    full = (uint32_t)(uint8_t)fx_round_i((fx)(0xFF * fx_sub(next_y, y)));       \
+  } while (0)
+  SKB_BEGIN_BAND();
+  bool done = false;
+  while (!done) {
+    if (E[cur].upper_y <= y) {
+      Edge c = E[cur];
+      w += edge_winding(c);
+      const bool prev_in = in_interval;
+      in_interval = (w & mask) != 0;
+      const bool is_left = in_interval && !prev_in, is_right = !in_interval && prev_in;
+      const fx old_x = c.x;
+      c.y = next_y;
+      c.x = fx_add(c.x, c.dx >> y_shift);
+      if (is_left) {
+        left = fx_max(old_x, left_clip);
+        left_dy = c.dy;
+        left_edge = cur;
+      } else if (is_right) {
+        const fx right = fx_min(right_clip, old_x);
+        const fx le_x = E[left_edge].x;
+        TrapRec r;
+        r.y = y >> 16;
+        r.ul = left;
+        r.ur = right;
+        r.ll = fx_max(left_clip, le_x);
+        r.lr = fx_min(right_clip, c.x);
+        r.ldy = left_dy;
+        r.rdy = c.dy;
+        bool no_real = false;
+        if (full == 0xFF) {
+          const int nx = c.next;  // too_close_edges(cur, cur->next, next_y) with cur's advanced x
+          no_real = (prev_right > fx_floor_i(left) || prev_right > fx_floor_i(le_x)) ||
+                    (E[nx].upper_y < next_y && fx_add(c.x, SKB_FX1) >= fx_sub(E[nx].x, fx_abs(E[nx].dx)));
+        }
+        r.flags = full | (no_real ? 0x100u : 0u);
+        sink_emit(sink, r);
+        prev_right = fx_ceil_i(fx_max(right, c.x));
+      }
+      const int next = c.next;
+      while (c.lower_y <= next_y) {
+        if (edge_count(c) > 0) {
+          QuadState& q = Q[cur];
+          q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
+          q.snapped_y = c.y;
+          if (!update_quad(c, q)) break;
+        } else {
+          break;
+        }
+      }
+      // write back what changed (the links are edited in place below)
+      E[cur].x = c.x; E[cur].y = c.y; E[cur].dx = c.dx; E[cur].dy = c.dy;
+      E[cur].upper_x = c.upper_x; E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
+      if (c.lower_y <= next_y) {
+        remove_edge(E, cur);
+      } else {
+        upd_nny(c.lower_y, next_y, &nny);
+        if (c.x < prev_x) backward_insert_on_x(E, cur);
+        else prev_x = c.x;
+        check_intersection(E, cur, next_y, &nny);
+      }
+      cur = next;
+    }
+    if (E[cur].upper_y > y) {
+      if (in_interval) {
+        TrapRec r;
+        r.y = y >> 16;
+        r.ul = left;
+        r.ur = right_clip;
+        r.ll = fx_max(left_clip, E[left_edge].x);
+        r.lr = right_clip;
+        r.ldy = left_dy;
+        r.rdy = 0;
+        bool no_real = full == 0xFF && too_close_edges(E, E[left_edge].prev, left_edge, next_y);
+        r.flags = full | (no_real ? 0x100u : 0u);
+        sink_emit(sink, r);
+      }
+      y = next_y;
+      if (y >= stop_fx) {
+        done = true;
+      } else {
+        insert_new_edges(E, cur, y, &nny);
+        SKB_BEGIN_BAND();
+      }
+    }
+  }
+#undef SKB_BEGIN_BAND
+  sink_flush_row(sink);
+}
+
+// mode: 0 = nested loops (the reference's shape, kept as a cross-check), 1 = flat loop (what the GPU runs)
+SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots, int32_t* ord, float scan_top_f,
+                       float scan_bottom_f, int start_y, int stop_y, fx left_clip, fx right_clip, int even_odd,
+                       RecSink& sink, int mode = 1) {
+  const int flat = mode != 0;
+  WalkState ws;
+  if (!walk_prologue(E, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws)) return;
+  if (flat && !qmap) walk_bands_flat(E, Q, ws, stop_y, left_clip, right_clip, even_odd, sink);
+  else walk_bands_nested(E, Q, qmap, ws, stop_y, left_clip, right_clip, even_odd, sink);
+}
+
 
 }  // namespace skb
 

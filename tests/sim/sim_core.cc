@@ -4,12 +4,20 @@
 // Test infrastructure only; built by tests/simlib.py with g++.
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "skity_b200/csrc/skb_stages.cuh"
 
 using namespace skb;
+
+// SKB_SIM_WALK_MODE selects the sweep variant (skb_walk.cuh walk_path `mode`); default = what the GPU runs.
+static int sim_walk_mode() {
+  const char* m = getenv("SKB_SIM_WALK_MODE");
+  return m ? atoi(m) : 1;
+}
+
 
 extern "C" {
 
@@ -72,7 +80,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
     sink.n_rows = n_rows;
     sink_init(sink);
     walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
-              g.right_clip, even_odd, sink);
+              g.right_clip, even_odd, sink, sim_walk_mode());
     if (!overflow) break;
     pool.resize(pool.size() * 4);
     pool_next = 0;
@@ -164,7 +172,7 @@ void sim_raster_op(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, co
     sink.n_rows = n_rows;
     sink_init(sink);
     walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y,
-              g.left_clip, g.right_clip, even_odd, sink);
+              g.left_clip, g.right_clip, even_odd, sink, sim_walk_mode());
     if (!overflow) break;
     out.pool.resize(out.pool.size() * 4);
     pool_next = 0;

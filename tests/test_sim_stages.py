@@ -83,3 +83,12 @@ def test_sim_whole_frame_with_nested_clips():
     got, stats = simlib.render_dl(dl)
     assert stats[0] == 0
     assert np.array_equal(got, port.render(dl))
+
+
+def test_sim_sweep_nested_form_agrees(monkeypatch):
+    """The sweep exists in two forms (skb_walk.cuh): the flat single loop the GPU runs (covered
+    above) and the reference-shaped nested loops; both must produce the oracle's coverage."""
+    monkeypatch.setenv("SKB_SIM_WALK_MODE", "0")
+    check_scene(scene.scene_c0(blur=False))
+    check_scene(scene.scene_c2(16, 256, 5, clip_every=0))
+    check_scene(scene.scene_random_fills(24, 256, 9, box=160.0))
