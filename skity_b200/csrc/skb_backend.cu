@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -330,58 +331,41 @@ struct CoverArgs {
 #define SKB_ITEM_SOLID 256u
 #define SKB_ITEM_PLANE_MASK 255u
 
-// Generic (slow) evaluation of 8 pixels of a row: every record re-read and re-prepared.
-__device__ __noinline__ void cover_row8_generic(const TrapRec* __restrict__ pool, uint2 row, int x0, int xmin, int xmax,
-                                                uint32_t d[8], uint32_t a[8]) {
-  uint32_t idx = row.x;
-  for (uint32_t k = 0; k < row.y; k++, idx++) {
-    TrapRec r = pool[idx];
-    if (r.flags & SKB_REC_LINK) {
-      idx = (uint32_t)r.y;
-      r = pool[idx];
-    }
-    const TrapPrep pr = trap_prepare(r);
-    if (pr.mode == 0 || pr.R <= x0 || pr.L >= x0 + 8) continue;
-#pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-      int x = x0 + j;
-      uint8_t v;
-      if (x >= xmin && x < xmax && trap_prep_alpha(pr, x, &v)) {
-        if (!pr.accum) d[j] = v; else a[j] += v;
-      }
-    }
-  }
-}
-
-#define COVER_RSM 16     // records per pixel row summarised in shared memory (more -> generic path)
 #define COVER_WARPS 4
-#define COVER_QCAP 768   // edge-pixel tasks per tile row that fit the shared-memory queue
-#define COVER_ND (16 * COVER_RSM)
+#define COVER_CW 128                 // pixels per chunk of a tile row (8 tiles) held in shared memory
+#define COVER_ND 128                 // trapezoid records summarised per pass
+#define COVER_UNIT 4                 // edge pixels evaluated per work unit
 
-// One warp per (op, tile row).  Lane L owns pixel row L>>1 of the tile row and the 8-pixel half L&1
-// of every tile.  Work is split by KIND of pixel so that the expensive part is evenly spread:
-//   1. the even lane of each row summarises the row's trapezoid records as ranges
-//      (outside / edge zone / interior) in shared memory;
-//   2. the edge-zone pixels of all 16 rows — the only ones that need the triangle/ramp formulas —
-//      are evaluated by all 32 lanes, one pixel each per round (descriptor found by binary search);
-//   3. the tiles of the covered x-range are then assembled with range tests and look-ups,
-//      classified (empty / solid / partial) by ballot, and stored as coalesced 256-byte A8 masks.
+struct alignas(16) CoverWarpSmem {
+  uint32_t D[16][COVER_CW / 4];      // directly emitted coverage, one byte per pixel
+  uint32_t A[16][COVER_CW / 2];      // accumulated coverage, 16 bits per pixel (saturated when read)
+  uint32_t z_rec[COVER_ND];          // record index in the pool
+  int32_t z_base[COVER_ND + 1];      // first work unit of the record (exclusive prefix)
+  int16_t z_L[COVER_ND], z_R[COVER_ND];    // pixels [L, R) get a value; chunk-relative, clipped
+  int16_t z_jl[COVER_ND], z_jr[COVER_ND];  // pixels [jl, jr) get `full`
+  uint16_t z_fa[COVER_ND];           // full | accum << 8 | row << 12
+  int32_t r_pre[16], r_cnt[16];
+  uint32_t r_first[16];
+};
+
+// One warp per (op, tile row).  The tile row is processed in chunks of COVER_CW pixels whose coverage
+// is built in shared memory, then cut into 16x16 A8 masks:
+//   1. the row's trapezoid records (all 16 pixel rows, COVER_ND per pass) are summarised in parallel
+//      as ranges: outside / edge zone / interior;
+//   2. the edge-zone pixels — the only ones that need the triangle/ramp formulas — are split into
+//      units of COVER_UNIT pixels and evaluated by all 32 lanes (unit -> record by binary search);
+//      values go straight into the chunk (byte store for direct spans, 16-bit atomic add for
+//      accumulated ones: safely_add_alpha saturates, and a saturating sum is order-independent);
+//   3. interiors are filled one record per lane;
+//   4. lane L then owns pixel row L>>1 and the 8-pixel half L&1 of each tile: two vector loads,
+//      classification (empty / solid / one plane / two planes) by ballot, coalesced 256-byte stores.
 __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
-  __shared__ int32_t z_base[COVER_WARPS][COVER_ND];   // queue position of the record's first edge pixel
-  __shared__ uint32_t z_rec[COVER_WARPS][COVER_ND];   // record index in the pool
-  __shared__ int32_t z_L[COVER_WARPS][COVER_ND];      // pixels [L, R) get a value (clipped to scan/surface)
-  __shared__ int32_t z_R[COVER_WARPS][COVER_ND];
-  __shared__ int32_t z_jl[COVER_WARPS][COVER_ND];     // pixels [jl, jr) get `full`
-  __shared__ int32_t z_jr[COVER_WARPS][COVER_ND];
-  __shared__ uint16_t z_fa[COVER_WARPS][COVER_ND];    // full | accum << 8
-  __shared__ uint8_t q_val[COVER_WARPS][COVER_QCAP];
-  __shared__ int32_t r_pre[COVER_WARPS][16];
-  __shared__ int32_t r_cnt[COVER_WARPS][16];
-  __shared__ uint32_t r_first[COVER_WARPS][16];
+  __shared__ CoverWarpSmem sm_all[COVER_WARPS];
   const int wib = threadIdx.x >> 5;
   const uint32_t trow = blockIdx.x * COVER_WARPS + wib;
   const int lane = threadIdx.x & 31;
   if (trow >= c.n_trows) return;
+  CoverWarpSmem& sm = sm_all[wib];
   const uint32_t op = find_interval(c.row_base, c.n_ops, trow * SKB_TILE);
   const OpGeom g = c.geom[op];
   const uint32_t tr = trow - c.row_base[op] / SKB_TILE;
@@ -389,215 +373,208 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   const skb_dl_op o = c.ops[op];
   if (o.kind != SKB_OP_FILL || o.clip_in != 0) return;  // clip paths and clipped draws: k_clip_rows
   const SurfDesc sd = c.surfs[o.surface];
-  const int y = ty * SKB_TILE + (lane >> 1);
   const int xmax = min(g.scan_r, (int)sd.w);
   const int xmin = max(g.scan_l, 0);
+  // lanes 0..15 own the row table entries of the 16 pixel rows
   uint2 row = make_uint2(0u, 0u);
-  if (y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)(lane >> 1)];
-
-  // ---- 1. range summaries: the records of the 16 pixel rows are spread over all 32 lanes
-  const int d0 = (lane >> 1) * COVER_RSM;
-  const bool generic = row.y > COVER_RSM;
-  const int nrec = generic ? 0 : (int)row.y;
-  // exclusive prefix of the per-row record counts (even lanes carry their row, odd lanes 0)
-  int cnt = (lane & 1) ? 0 : nrec;
-  int pre = cnt;
+  {
+    const int y = ty * SKB_TILE + lane;
+    if (lane < 16 && y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)lane];
+  }
+  int pre = (int)row.y;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(0xffffffffu, pre, d);
     if (lane >= d) pre += t;
   }
   const int n_tot = __shfl_sync(0xffffffffu, pre, 31);
-  pre -= cnt;
-  int lo = INT_MAX, hi = INT_MIN;
-  if (!(lane & 1)) {
-    r_pre[wib][lane >> 1] = pre;
-    r_cnt[wib][lane >> 1] = cnt;
-    r_first[wib][lane >> 1] = row.x;
+  if (n_tot == 0) return;  // nothing in this tile row (item flags were zeroed)
+  if (lane < 16) {
+    sm.r_pre[lane] = pre - (int)row.y;
+    sm.r_cnt[lane] = (int)row.y;
+    sm.r_first[lane] = row.x;
   }
   __syncwarp();
-  for (int p = lane; p < n_tot; p += 32) {
-    // which row owns record p: the last row with records whose prefix is <= p
-    int rr_ = 0;
-#pragma unroll
-    for (int r = 0; r < 16; r++) {
-      if (r_cnt[wib][r] > 0 && r_pre[wib][r] <= p) rr_ = r;
-    }
-    const int rlane = 2 * rr_;
-    const int k = p - r_pre[wib][rr_];
-    const uint32_t first = r_first[wib][rr_];
-    // k-th record of the row: records are consecutive except for a chunk-link slot (slot 31 of a chunk)
-    uint32_t idx = first + (uint32_t)k;
-    if ((first & (SKB_CHUNK - 1)) + (uint32_t)k >= SKB_CHUNK - 1) {
-      const uint32_t next = (uint32_t)c.pool[first | (SKB_CHUNK - 1)].y;
-      idx = next + ((first & (SKB_CHUNK - 1)) + (uint32_t)k - (SKB_CHUNK - 1));
-    }
-    const TrapPrep pr = trap_prepare(c.pool[idx]);
-    int L = max(pr.L, xmin), R = min(pr.mode ? pr.R : pr.L, xmax);
-    if (R > L) {
-      lo = min(lo, L);
-      hi = max(hi, R);
-    }
-    R = max(R, L);
-    const int jl = min(max(pr.jl, L), R);
-    const int jr = min(max(pr.jr, jl), R);
-    const int at = (rlane >> 1) * COVER_RSM + k;
-    z_rec[wib][at] = idx;
-    z_L[wib][at] = L;
-    z_R[wib][at] = R;
-    z_jl[wib][at] = jl;
-    z_jr[wib][at] = jr;
-    z_fa[wib][at] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u));
-  }
-  // rows with more records than the table holds: extents from a plain scan of their records
-  if (generic && !(lane & 1)) {
-    uint32_t idx = row.x;
-    for (uint32_t k = 0; k < row.y; k++, idx++) {
-      TrapRec r = c.pool[idx];
-      if (r.flags & SKB_REC_LINK) {
-        idx = (uint32_t)r.y;
-        r = c.pool[idx];
-      }
-      const TrapPrep pr = trap_prepare(r);
-      int L = max(pr.L, xmin), R = min(pr.mode ? pr.R : pr.L, xmax);
-      if (R > L) {
-        lo = min(lo, L);
-        hi = max(hi, R);
-      }
-    }
-  }
-  __syncwarp();
-  // per-row queue sizes and relative bases (even lanes)
-  int n_tasks = 0;
-  if (!(lane & 1)) {
-    for (int k = 0; k < nrec; k++) {
-      z_base[wib][d0 + k] = n_tasks;
-      n_tasks += (z_jl[wib][d0 + k] - z_L[wib][d0 + k]) + (z_R[wib][d0 + k] - z_jr[wib][d0 + k]);
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
-    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
-  }
-  if (hi <= lo) return;  // nothing in this tile row (item flags were zeroed)
+  const uint32_t item_row = c.item_base[op] + tr * (uint32_t)g.ntx;
+  uint8_t* const Db = reinterpret_cast<uint8_t*>(&sm.D[0][0]);
+  uint32_t* const Aw = &sm.A[0][0];
 
-  // ---- 2. evaluate the edge-zone pixels
-  int incl = n_tasks;  // odd lanes contribute 0
+  const int x_end_all = (g.tx0 + g.ntx) * SKB_TILE;
+  for (int cx = g.tx0 * SKB_TILE; cx < x_end_all; cx += COVER_CW) {
+    const int cx_end = min(cx + COVER_CW, x_end_all);
+    const int cl = max(xmin, cx), cr = min(xmax, cx_end);
+    if (cr <= cl) continue;
+    // zero the chunk
+    __syncwarp();
+    {
+      uint4* z = reinterpret_cast<uint4*>(&sm.D[0][0]);
+      constexpr int n16 = (int)((sizeof(sm.D) + sizeof(sm.A)) / 16);
+      static_assert(offsetof(CoverWarpSmem, A) == sizeof(sm.D), "D and A are zeroed as one block");
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += t;
-  }
-  const int total = __shfl_sync(0xffffffffu, incl, 31);
-  const int base = incl - n_tasks;
-  const bool queued = total <= COVER_QCAP;
-  if (!(lane & 1)) {
-    // absolute queue positions; unused descriptor slots take the row's end position so that the
-    // base array stays non-decreasing for the binary search
-    for (int k = 0; k < COVER_RSM; k++) z_base[wib][d0 + k] = k < nrec ? z_base[wib][d0 + k] + base : base + n_tasks;
-  }
-  __syncwarp();
-  if (queued) {
-    for (int p = lane; p < total; p += 32) {
-      int lo_d = 0, hi_d = COVER_ND;
-      while (hi_d - lo_d > 1) {
-        int mid = (lo_d + hi_d) >> 1;
-        if (z_base[wib][mid] <= p) lo_d = mid; else hi_d = mid;
+      for (int i = 0; i < n16 / 32; i++) z[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int pbase = 0; pbase < n_tot; pbase += COVER_ND) {
+      const int npass = min(COVER_ND, n_tot - pbase);
+      __syncwarp();
+      // ---- 1. range summaries
+      for (int p = lane; p < COVER_ND; p += 32) {
+        int units = 0;
+        if (p < npass) {
+          const int P = pbase + p;
+          int rr_ = 0;  // the row that owns record P: the last row with records whose prefix is <= P
+#pragma unroll
+          for (int r = 0; r < 16; r++) {
+            if (sm.r_cnt[r] > 0 && sm.r_pre[r] <= P) rr_ = r;
+          }
+          const uint32_t first = sm.r_first[rr_];
+          // k-th record of the row: consecutive slots, the last slot of every chunk links to the next chunk
+          uint32_t pos = (first & (SKB_CHUNK - 1)) + (uint32_t)(P - sm.r_pre[rr_]);
+          uint32_t cb = first & ~(SKB_CHUNK - 1);
+          while (pos >= SKB_CHUNK - 1) {
+            cb = (uint32_t)c.pool[cb | (SKB_CHUNK - 1)].y;
+            pos -= SKB_CHUNK - 1;
+          }
+          const uint32_t idx = cb + pos;
+          const TrapPrep pr = trap_prepare(c.pool[idx]);
+          int L = max(pr.L, cl), R = min(pr.mode ? pr.R : pr.L, cr);
+          if (R > L) {
+            lo = min(lo, L);
+            hi = max(hi, R);
+          }
+          R = max(R, L);
+          const int jl = min(max(pr.jl, L), R);
+          const int jr = min(max(pr.jr, jl), R);
+          sm.z_rec[p] = idx;
+          sm.z_L[p] = (int16_t)(L - cx);
+          sm.z_R[p] = (int16_t)(R - cx);
+          sm.z_jl[p] = (int16_t)(jl - cx);
+          sm.z_jr[p] = (int16_t)(jr - cx);
+          sm.z_fa[p] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u) | ((uint32_t)rr_ << 12));
+          units = (jl - L + COVER_UNIT - 1) / COVER_UNIT + (R - jr + COVER_UNIT - 1) / COVER_UNIT;
+        }
+        sm.z_base[p] = units;
       }
-      const int off = p - z_base[wib][lo_d];
-      const int nl = z_jl[wib][lo_d] - z_L[wib][lo_d];
-      const int x = off < nl ? z_L[wib][lo_d] + off : z_jr[wib][lo_d] + (off - nl);
-      const TrapPrep pr = trap_prepare(c.pool[z_rec[wib][lo_d]]);
-      uint8_t v = 0;
-      if (!trap_prep_alpha(pr, x, &v)) v = 0;
-      q_val[wib][p] = v;
+      __syncwarp();
+      // exclusive prefix of the unit counts
+      int carry = 0;
+#pragma unroll
+      for (int b = 0; b < COVER_ND; b += 32) {
+        const int v = sm.z_base[b + lane];
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += t;
+        }
+        sm.z_base[b + lane] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      const int total = carry;
+      if (lane == 0) sm.z_base[COVER_ND] = total;
+      __syncwarp();
+      // ---- 2. edge-zone pixels
+      for (int u = lane; u < total; u += 32) {
+        int lo_d = 0, hi_d = COVER_ND;
+        while (hi_d - lo_d > 1) {
+          int mid = (lo_d + hi_d) >> 1;
+          if (sm.z_base[mid] <= u) lo_d = mid; else hi_d = mid;
+        }
+        const int e = lo_d;
+        const int off = u - sm.z_base[e];
+        const int L = sm.z_L[e], jl = sm.z_jl[e], jr = sm.z_jr[e], R = sm.z_R[e];
+        const int nl = (jl - L + COVER_UNIT - 1) / COVER_UNIT;
+        int xs, xe;
+        if (off < nl) {
+          xs = L + off * COVER_UNIT;
+          xe = min(xs + COVER_UNIT, jl);
+        } else {
+          xs = jr + (off - nl) * COVER_UNIT;
+          xe = min(xs + COVER_UNIT, R);
+        }
+        const uint32_t fa = sm.z_fa[e];
+        const int rr_ = (int)(fa >> 12);
+        const bool accum = (fa >> 8) & 1;
+        const TrapPrep pr = trap_prepare(c.pool[sm.z_rec[e]]);
+        for (int xr = xs; xr < xe; xr++) {
+          uint8_t v = 0;
+          if (!trap_prep_alpha(pr, cx + xr, &v) || v == 0) continue;
+          if (accum) atomicAdd(&Aw[(rr_ * COVER_CW + xr) >> 1], (uint32_t)v << (16 * (xr & 1)));
+          else Db[rr_ * COVER_CW + xr] = v;
+        }
+      }
+      // ---- 3. interiors
+      for (int p = lane; p < npass; p += 32) {
+        int x = sm.z_jl[p];
+        const int xe = sm.z_jr[p];
+        if (xe <= x) continue;
+        const uint32_t fa = sm.z_fa[p];
+        const int rr_ = (int)(fa >> 12);
+        const uint32_t full = fa & 0xFF;
+        if ((fa >> 8) & 1) {
+          if (full == 0) continue;
+          uint32_t* Ar = Aw + rr_ * (COVER_CW / 2);
+          if (x & 1) {
+            atomicAdd(&Ar[x >> 1], full << 16);
+            x++;
+          }
+          for (; x + 2 <= xe; x += 2) atomicAdd(&Ar[x >> 1], full | (full << 16));
+          if (x < xe) atomicAdd(&Ar[x >> 1], full);
+        } else {
+          uint8_t* Dr = Db + rr_ * COVER_CW;
+          for (; x < xe && (x & 3); x++) Dr[x] = (uint8_t)full;
+          for (; x + 4 <= xe; x += 4) *reinterpret_cast<uint32_t*>(Dr + x) = full * 0x01010101u;
+          for (; x < xe; x++) Dr[x] = (uint8_t)full;
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+      hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
     }
     __syncwarp();
-  }
+    if (hi <= lo) continue;
 
-  // ---- 3. assemble, classify and store the tiles
-  const int my_nrec = __shfl_sync(0xffffffffu, nrec, lane & ~1);
-  const bool my_generic = __shfl_sync(0xffffffffu, (int)generic, lane & ~1) != 0;
-  const int tx_begin = max(g.tx0, lo / SKB_TILE);
-  const int tx_end = min(g.tx0 + g.ntx, (hi + SKB_TILE - 1) / SKB_TILE);
-  const uint32_t item_row = c.item_base[op] + tr * (uint32_t)g.ntx;
-  for (int tx = tx_begin; tx < tx_end; tx++) {
-    const int x0 = tx * SKB_TILE + (lane & 1) * 8;
-    uint32_t d[8], a[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { d[j] = 0; a[j] = 0; }
-    if (my_generic || !queued) {
-      cover_row8_generic(c.pool, row, x0, xmin, xmax, d, a);
-    } else {
-      for (int k = 0; k < my_nrec; k++) {
-        const int L = z_L[wib][d0 + k], R = z_R[wib][d0 + k];
-        if (R <= x0 || L >= x0 + 8) continue;
-        const int jl = z_jl[wib][d0 + k], jr = z_jr[wib][d0 + k];
-        const uint32_t fa = z_fa[wib][d0 + k];
-        const uint32_t full = fa & 0xFF;
-        const bool accum = (fa >> 8) & 1;
-        if (x0 >= jl && x0 + 8 <= jr) {
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            if (accum) a[j] += full; else d[j] = full;
-          }
-          continue;
-        }
-        const int qb = z_base[wib][d0 + k];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const int x = x0 + j;
-          if (x < L || x >= R) continue;
-          uint32_t v;
-          if (x >= jl && x < jr) v = full;
-          else if (x < jl) v = q_val[wib][qb + (x - L)];
-          else v = q_val[wib][qb + (jl - L) + (x - jr)];
-          if (accum) a[j] += v; else d[j] = v;
+    // ---- 4. cut the chunk into tiles, classify and store
+    const int tx_begin = lo / SKB_TILE;
+    const int tx_end = (hi + SKB_TILE - 1) / SKB_TILE;
+    const int prow = lane >> 1, half = lane & 1;
+    for (int tx = tx_begin; tx < tx_end; tx++) {
+      const int xr = tx * SKB_TILE - cx + half * 8;
+      const uint2 dv = *reinterpret_cast<const uint2*>(Db + prow * COVER_CW + xr);
+      uint4 av = *reinterpret_cast<const uint4*>(Aw + ((prow * COVER_CW + xr) >> 1));
+      // saturate the 16-bit sums and pack them to bytes
+      av.x = __vminu2(av.x, 0x00FF00FFu);
+      av.y = __vminu2(av.y, 0x00FF00FFu);
+      av.z = __vminu2(av.z, 0x00FF00FFu);
+      av.w = __vminu2(av.w, 0x00FF00FFu);
+      const uint32_t a0 = __byte_perm(av.x, av.y, 0x6420), a1 = __byte_perm(av.z, av.w, 0x6420);
+      // bytes that are non-zero, as 0x80 flags
+      const uint32_t nd0 = ((dv.x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | dv.x) & 0x80808080u;
+      const uint32_t nd1 = ((dv.y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | dv.y) & 0x80808080u;
+      const uint32_t na0 = ((a0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | a0) & 0x80808080u;
+      const uint32_t na1 = ((a1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | a1) & 0x80808080u;
+      const bool any = __any_sync(0xffffffffu, (dv.x | dv.y | a0 | a1) != 0);
+      if (!any) continue;
+      const bool both = __any_sync(0xffffffffu, ((nd0 & na0) | (nd1 & na1)) != 0);
+      const bool solid = __all_sync(0xffffffffu, (dv.x & dv.y) == 0xFFFFFFFFu && (a0 | a1) == 0);
+      const uint32_t item = item_row + (uint32_t)(tx - g.tx0);
+      uint32_t flags = SKB_ITEM_PLANE0;
+      if (solid) {
+        flags |= SKB_ITEM_SOLID;
+      } else {
+        reinterpret_cast<uint2*>(c.mask0 + (size_t)item * 256)[lane] = both ? dv : make_uint2(dv.x | a0, dv.y | a1);
+        if (both) {
+          flags |= SKB_ITEM_PLANE1;
+          reinterpret_cast<uint2*>(c.mask1 + (size_t)item * 256)[lane] = make_uint2(a0, a1);
         }
       }
-    }
-    bool any = false, both = false, solid = true;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      a[j] = a[j] > 255u ? 255u : a[j];
-      any |= (d[j] | a[j]) != 0;
-      both |= d[j] != 0 && a[j] != 0;
-      solid &= d[j] == 255 && a[j] == 0;
-    }
-    any = __any_sync(0xffffffffu, any);
-    if (!any) continue;
-    both = __any_sync(0xffffffffu, both);
-    solid = __all_sync(0xffffffffu, solid);
-    const uint32_t item = item_row + (uint32_t)(tx - g.tx0);
-    uint32_t flags = SKB_ITEM_PLANE0;
-    if (solid) {
-      flags |= SKB_ITEM_SOLID;
-    } else {
-      uint32_t w0 = 0, w1 = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t v0 = both ? d[j] : (d[j] | a[j]);
-        uint32_t v1 = both ? d[j + 4] : (d[j + 4] | a[j + 4]);
-        w0 |= v0 << (8 * j);
-        w1 |= v1 << (8 * j);
+      if (lane == 0) {
+        c.item_flags[item] = (uint16_t)flags;
+        uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
+        atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
       }
-      reinterpret_cast<uint2*>(c.mask0 + (size_t)item * 256)[lane] = make_uint2(w0, w1);
-      if (both) {
-        flags |= SKB_ITEM_PLANE1;
-        w0 = w1 = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          w0 |= a[j] << (8 * j);
-          w1 |= a[j + 4] << (8 * j);
-        }
-        reinterpret_cast<uint2*>(c.mask1 + (size_t)item * 256)[lane] = make_uint2(w0, w1);
-      }
-    }
-    if (lane == 0) {
-      c.item_flags[item] = (uint16_t)flags;
-      uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
-      atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
     }
   }
 }
