@@ -93,6 +93,11 @@ SKB_API skb_result skb_surface_sync(skb_surface surface);
 /* Copies the rectangle to host memory (rows `stride` bytes apart).  Synchronises. */
 SKB_API skb_result skb_surface_read_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
                                            uint32_t height, void* dst, size_t stride);
+/* Same copy, enqueued on the surface's stream without waiting: `dst` (pinned host memory for a truly
+ * asynchronous copy) is valid after the next skb_surface_sync().  Lets an application keep two
+ * surfaces in flight so that the read-back of one frame overlaps the rendering of the next. */
+SKB_API skb_result skb_surface_read_pixels_async(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
+                                                 uint32_t height, void* dst, size_t stride);
 /* Uploads pixels into the surface (the LockCanvas(false) case: drawing over existing content). */
 SKB_API skb_result skb_surface_write_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
                                             uint32_t height, const void* src, size_t stride);

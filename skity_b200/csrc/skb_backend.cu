@@ -1116,6 +1116,10 @@ struct skb_surface_s {
   uint32_t band_y0 = 0, band_y1 = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[12] = {};
+  // host-mapped words the device writes counts into: reading them does not queue behind another
+  // surface's read-back on the copy engine
+  uint32_t* mapped_host = nullptr;
+  uint32_t* mapped_dev = nullptr;
   // canvas pixels (persistent)
   uint8_t* canvas = nullptr;
   uint32_t pitch = 0, tiles_x = 0, tiles_y = 0;
@@ -1134,6 +1138,19 @@ struct skb_surface_s {
 };
 
 namespace skb {
+
+__global__ void k_fetch_words(uint32_t* dst, const uint32_t* src, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+// Brings n (<= 16) device words to the host and waits for them.
+static skb_result fetch_words(skb_surface s, uint32_t* out, const uint32_t* dev_src, int n) {
+  k_fetch_words<<<1, 32, 0, s->stream>>>(s->mapped_dev, dev_src, n);
+  SKB_CUDA(cudaGetLastError());
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  for (int i = 0; i < n; i++) out[i] = ((volatile uint32_t*)s->mapped_host)[i];
+  return SKB_SUCCESS;
+}
 
 static skb_result buf_reserve(Buf& b, size_t bytes) {
   if (bytes <= b.cap) return SKB_SUCCESS;
@@ -1370,8 +1387,8 @@ static skb_result run_frame(skb_surface s) {
     k_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(t, prim_off);
     launches++;
     SKB_TRY(scan_exclusive(s, prim_off, n_segs + 1, &launches));
-    SKB_CUDA(cudaMemcpyAsync(&n_prims, prim_off + n_segs, 4, cudaMemcpyDeviceToHost, st));
-    SKB_CUDA(cudaStreamSynchronize(st));
+    SKB_TRY(fetch_words(s, &n_prims, prim_off + n_segs, 1));
+    launches++;
   }
   S.n_prims = n_prims;
   const size_t n_slots = (size_t)2 * n_prims + (size_t)2 * n_ops + 2;
@@ -1398,9 +1415,9 @@ static skb_result run_frame(skb_surface s) {
       SKB_TRY(scan_exclusive(s, row_base, n_ops + 1, &launches));
       SKB_TRY(scan_exclusive(s, item_base, n_ops + 1, &launches));
       uint32_t tot[2] = {0, 0};
-      SKB_CUDA(cudaMemcpyAsync(&tot[0], row_base + n_ops, 4, cudaMemcpyDeviceToHost, st));
-      SKB_CUDA(cudaMemcpyAsync(&tot[1], item_base + n_ops, 4, cudaMemcpyDeviceToHost, st));
-      SKB_CUDA(cudaStreamSynchronize(st));
+      SKB_TRY(fetch_words(s, &tot[0], row_base + n_ops, 1));
+      SKB_TRY(fetch_words(s, &tot[1], item_base + n_ops, 1));
+      launches += 2;
       n_rows = tot[0];
       n_items = tot[1];
       S.n_rows = n_rows;
@@ -1451,8 +1468,8 @@ static skb_result run_frame(skb_surface s) {
       launches++;
     }
     uint32_t hc[2];
-    SKB_CUDA(cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, st));
-    SKB_CUDA(cudaStreamSynchronize(st));
+    SKB_TRY(fetch_words(s, hc, counters, 2));
+    launches++;
     S.n_records = hc[0];
     if (!hc[1]) break;
     if (attempt >= 6 || pool_cap >= 0x7FFFFFF0u) {
@@ -1538,8 +1555,8 @@ static skb_result run_frame(skb_surface s) {
     launches++;
     SKB_TRY(scan_exclusive(s, (uint32_t*)s->clip_px.p, n_states + 2, &launches));
     uint32_t total_px = 0;
-    SKB_CUDA(cudaMemcpyAsync(&total_px, (uint32_t*)s->clip_px.p + n_states + 1, 4, cudaMemcpyDeviceToHost, st));
-    SKB_CUDA(cudaStreamSynchronize(st));
+    SKB_TRY(fetch_words(s, &total_px, (uint32_t*)s->clip_px.p + n_states + 1, 1));
+    launches++;
     SKB_TRY(buf_reserve(s->clip_table, ((size_t)total_px + 1) * SKB_CLIP_MAXE * 4));
     SKB_CUDA(cudaMemsetAsync(s->clip_table.p, 0, ((size_t)total_px + 1) * SKB_CLIP_MAXE * 4, st));
     ClipArgs cl;
@@ -1561,8 +1578,8 @@ static skb_result run_frame(skb_surface s) {
       launches++;
     }
     uint32_t over = 0;
-    SKB_CUDA(cudaMemcpyAsync(&over, counters + 2, 4, cudaMemcpyDeviceToHost, st));
-    SKB_CUDA(cudaStreamSynchronize(st));
+    SKB_TRY(fetch_words(s, &over, counters + 2, 1));
+    launches++;
     if (over) {
       set_error("clip stack: a pixel is covered by more clip spans / coverage planes than the device tables hold");
       return SKB_ERROR_UNSUPPORTED;
@@ -1572,8 +1589,8 @@ static skb_result run_frame(skb_surface s) {
   // ---- stage 5: bin
   SKB_TRY(scan_exclusive(s, (uint32_t*)s->tile_cnt.p, n_tiles + 1, &launches));
   uint32_t n_cmds = 0;
-  SKB_CUDA(cudaMemcpyAsync(&n_cmds, (uint32_t*)s->tile_cnt.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
-  SKB_CUDA(cudaStreamSynchronize(st));
+  SKB_TRY(fetch_words(s, &n_cmds, (uint32_t*)s->tile_cnt.p + n_tiles, 1));
+  launches++;
   S.n_cmds = n_cmds;
   SKB_TRY(buf_reserve(s->cmds, ((size_t)n_cmds + 1) * sizeof(uint2)));
   SKB_TRY(buf_reserve(s->cmds_sorted, ((size_t)n_cmds + 1) * sizeof(uint2)));
@@ -1766,6 +1783,8 @@ skb_result skb_surface_create(skb_device d, uint32_t w, uint32_t h, skb_surface*
   if (e == cudaSuccess) e = cudaMalloc((void**)&s->canvas, (size_t)s->pitch * s->tiles_y * SKB_TILE);
   if (e == cudaSuccess) e = cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream);
   for (int i = 0; i < 12 && e == cudaSuccess; i++) e = cudaEventCreate(&s->ev[i]);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->mapped_host, 64, cudaHostAllocMapped);
+  if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&s->mapped_dev, s->mapped_host, 0);
   if (e != cudaSuccess) {
     set_error(std::string("surface create: ") + cudaGetErrorString(e));
     skb_surface_destroy(s);
@@ -1785,6 +1804,7 @@ void skb_surface_destroy(skb_surface s) {
                  &s->blur_tmp_ptrs, &s->blur_tmp};
   for (Buf* b : bufs) buf_free(*b);
   if (s->canvas) cudaFree(s->canvas);
+  if (s->mapped_host) cudaFreeHost(s->mapped_host);
   for (int i = 0; i < 12; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -1852,6 +1872,15 @@ skb_result skb_surface_read_pixels(skb_surface s, uint32_t x, uint32_t y, uint32
   SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
                              cudaMemcpyDeviceToHost, s->stream));
   SKB_CUDA(cudaStreamSynchronize(s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_read_pixels_async(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst,
+                                         size_t stride) {
+  if (!s || !dst || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
+                             cudaMemcpyDeviceToHost, s->stream));
   return SKB_SUCCESS;
 }
 

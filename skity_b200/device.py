@@ -60,6 +60,7 @@ def lib():
         L.skb_frame_flush.argtypes = [vp]
         L.skb_surface_sync.argtypes = [vp]
         L.skb_surface_read_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
+        L.skb_surface_read_pixels_async.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_surface_write_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_frame_read_surface.argtypes = [vp, u32, vp, sz]
         L.skb_surface_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
@@ -139,6 +140,12 @@ class Surface:
             out = np.empty((h, w, 4), dtype=np.uint8)
         _check(lib().skb_surface_read_pixels(self._h, x, y, w, h, out.ctypes.data, w * 4), "skb_surface_read_pixels")
         return out
+
+    def read_pixels_async(self, out, x=0, y=0):
+        """Enqueue the read-back on the surface's stream; `out` (h, w, 4 uint8, ideally pinned) is valid
+        after the next sync()."""
+        h, w, _ = out.shape
+        _check(lib().skb_surface_read_pixels_async(self._h, x, y, w, h, out.ctypes.data, w * 4), "skb_surface_read_pixels_async")
 
     def write_pixels(self, rgba, x=0, y=0):
         rgba = np.ascontiguousarray(rgba, dtype=np.uint8)

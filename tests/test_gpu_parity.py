@@ -277,3 +277,25 @@ def test_large_canvas_band_split_and_determinism(dev):
         got[y0:y1] = surf.read_pixels(0, y0, 16384, y1 - y0)
     surf.close()
     assert np.array_equal(got, whole)
+
+
+def test_two_surfaces_in_flight_with_async_read_back(dev):
+    """skb_surface_read_pixels_async: frames alternate between two surfaces without waiting for the
+    read-back (what bench.py's end-to-end loop does); every frame must equal the synchronous result."""
+    s = scene.scene_random_fills(300, 640, 77, box=200.0)
+    dl = hostlib.encode_scene(s.encode())
+    want, _ = port.render(dl)
+    lanes = [(dev.create_surface(640, 640), np.zeros((640, 640, 4), np.uint8)) for _ in range(2)]
+    try:
+        for i in range(6):
+            sf, out = lanes[i & 1]
+            sf.begin(True)
+            sf.encode(dl)
+            sf.flush()
+            sf.read_pixels_async(out)
+        for sf, out in lanes:
+            sf.sync()
+            assert np.array_equal(out, want)
+    finally:
+        for sf, _ in lanes:
+            sf.close()
