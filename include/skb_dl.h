@@ -133,7 +133,9 @@ typedef struct skb_dl_paint {
   float scale;        /* SWEEP: info.radius[1] */
   uint32_t image_surface; /* IMAGE: source surface id */
   uint32_t global_alpha;  /* uint8(255*alpha), ANDed with coverage (sw_span_brush.cc:101) */
-  uint32_t reserved;
+  uint32_t blend;         /* 0 = kSrcOver (the default); otherwise skity::BlendMode value + 1.  Modes
+                             SWRenderTarget does not implement are sent as kSrcOver, its own fall-back
+                             (blend_mode.cc:129-133) */
 } skb_dl_paint; /* 80 bytes */
 
 #ifdef __cplusplus

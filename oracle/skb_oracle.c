@@ -1026,6 +1026,71 @@ static inline void blend_src_over(uint8_t* px, uint32_t src) {
   px[3] = (uint8_t)(src >> 24);
 }
 
+/* PorterDuffBlend — src/graphic/blend_mode.cc:92-192 (colours A<<24|R<<16|G<<8|B, premultiplied) */
+static inline uint32_t pm_color_mul(uint32_t s, uint32_t d) { /* color_priv.hpp:74-79 */
+  return (mul_div_255_round(s >> 24, d >> 24) << 24) | (mul_div_255_round((s >> 16) & 0xFF, (d >> 16) & 0xFF) << 16) |
+         (mul_div_255_round((s >> 8) & 0xFF, (d >> 8) & 0xFF) << 8) | mul_div_255_round(s & 0xFF, d & 0xFF);
+}
+static float soft_light_component(float sx, float sy, float dx, float dy) { /* blend_mode.cc:92-108 */
+  if (2.f * sx <= sy) {
+    return dx * dx * (sy - 2 * sx) / dy + (1 - dy) * sx + dx * (-sy + 2 * sx + 1);
+  } else if (4.f * dx <= dy) {
+    float DSqd = dx * dx, DCub = DSqd * dx, DaSqd = dy * dy, DaCub = DaSqd * dy;
+    return (DaSqd * (sx - dx * (3 * sy - 6 * sx - 1)) + 12 * dy * DSqd * (sy - 2 * sx) - 16 * DCub * (sy - 2 * sx) -
+            DaCub * sx) / DaSqd;
+  }
+  return dx * (sy - 2 * sx + 1) + sx - sqrtf(dy * dx) * (sy - 2 * sx) - dy * sx;
+}
+static uint32_t porter_duff(uint32_t src, uint32_t dst, uint32_t mode) {
+  uint32_t sa = src >> 24, da = dst >> 24;
+  if (mode > 14 && mode != 21) mode = 3; /* :129-133 */
+  switch (mode) {
+    case 0: return 0;
+    case 1: return src;
+    case 2: return dst;
+    case 3: return sa == 0 ? dst : src + alpha_mul_q(dst, 256 - sa);
+    case 4: return da == 255 ? dst : dst + alpha_mul_q(src, 256 - da);
+    case 5: return da == 255 ? src : alpha_mul_q(src, da + 1);
+    case 6: return sa == 255 ? dst : alpha_mul_q(dst, sa + 1);
+    case 7: return da == 0 ? src : alpha_mul_q(src, 256 - da);
+    case 8: return sa == 0 ? dst : alpha_mul_q(dst, 256 - sa);
+    case 9: return alpha_mul_q(src, da + 1) + alpha_mul_q(dst, 256 - sa);
+    case 10: return alpha_mul_q(dst, sa + 1) + alpha_mul_q(src, 256 - da);
+    case 11: return alpha_mul_q(src, 256 - da) + alpha_mul_q(dst, 256 - sa);
+    case 12: {
+      uint32_t r = 0;
+      for (int sh = 0; sh < 32; sh += 8) {
+        uint32_t v = ((src >> sh) & 0xFF) + ((dst >> sh) & 0xFF);
+        r |= (v > 255u ? 255u : v) << sh;
+      }
+      return r;
+    }
+    case 13: return pm_color_mul(src, dst);
+    case 14: return src + dst - pm_color_mul(src, dst);
+    case 21: {
+      if (da == 0) return src;
+      float s4[4], d4[4], o[4]; /* r g b a, Color4fFromColor color.cc:44-51 */
+      s4[0] = ((src >> 16) & 0xFF) / 255.f; s4[1] = ((src >> 8) & 0xFF) / 255.f; s4[2] = (src & 0xFF) / 255.f; s4[3] = sa / 255.f;
+      d4[0] = ((dst >> 16) & 0xFF) / 255.f; d4[1] = ((dst >> 8) & 0xFF) / 255.f; d4[2] = (dst & 0xFF) / 255.f; d4[3] = da / 255.f;
+      for (int k = 0; k < 3; k++) o[k] = soft_light_component(s4[k], s4[3], d4[k], d4[3]);
+      o[3] = s4[3] + (1 - s4[3]) * d4[3];
+      return color4f_to_color(o);
+    }
+    default: return dst;
+  }
+}
+/* SWRenderTarget::BlendPixel on a premultiplied RGBA target, any mode — sw_render_target.cc:12-35.
+ * FastBlend (:97-141) short-cuts give the values the formulas give. */
+static inline void blend_pixel(uint8_t* px, uint32_t src, uint32_t mode) {
+  if (mode == 3) { blend_src_over(px, src); return; }
+  uint32_t dst = ((uint32_t)px[3] << 24) | ((uint32_t)px[0] << 16) | ((uint32_t)px[1] << 8) | px[2];
+  uint32_t r = porter_duff(src, dst, mode);
+  px[0] = (uint8_t)(r >> 16);
+  px[1] = (uint8_t)(r >> 8);
+  px[2] = (uint8_t)r;
+  px[3] = (uint8_t)(r >> 24);
+}
+
 typedef struct surface { uint32_t w, h; uint8_t* px; } surface;
 
 /* GradientColorBrush::LerpColor — sw_span_brush.cc:21-32,239-299 */
@@ -1108,6 +1173,7 @@ static void brush_spans(surface* dst, const skbo_span* spans, size_t n, const sk
                         const surface* surfs) {
   int iw = (int)dst->w, ih = (int)dst->h;
   uint32_t galpha = p->type == SKB_PAINT_IMAGE ? (p->global_alpha & 0xFF) : 255u;
+  uint32_t mode = p->blend ? p->blend - 1 : 3u;
   for (size_t i = 0; i < n; i++) {
     int x = spans[i].x, y = spans[i].y, len = spans[i].len;
     if (y < 0 || y >= ih) continue;
@@ -1119,7 +1185,7 @@ static void brush_spans(surface* dst, const skbo_span* spans, size_t n, const sk
     for (int l = 0; l < len; l++) {
       uint32_t color = paint_color(p, pool, surfs, x + l, y);
       if (alpha != 255) color = alpha_mul_q(color, alpha);
-      blend_src_over(dst->px + ((size_t)y * dst->w + (x + l)) * 4, color);
+      blend_pixel(dst->px + ((size_t)y * dst->w + (x + l)) * 4, color, mode);
     }
   }
 }

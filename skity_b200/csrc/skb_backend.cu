@@ -51,6 +51,8 @@ struct SurfDesc {
 };
 
 #define SKB_CMD_SOLID 0x80000000u
+#define SKB_CMD_ZERO 0x40000000u   // the item has a zero-coverage map (CoverArgs::zmask)
+#define SKB_CMD_ITEM_MASK 0x3FFFFFFFu
 
 __device__ __forceinline__ uint32_t find_interval(const uint32_t* off, uint32_t n, uint32_t v) {
   // largest i in [0, n) with off[i] <= v   (off is non-decreasing, off[0] <= v)
@@ -324,11 +326,15 @@ struct CoverArgs {
   uint8_t* mask[SKB_CLIP_PLANES];  // all planes (0,1 as above; 2.. only used by clipped draws)
   uint16_t* item_flags;
   uint32_t* tile_cnt;
+  const skb_dl_paint* paints;
+  uint8_t* zmask;  // n_items * 256, only with blend modes that act on zero-coverage pixels: 1 = touched by a direct span
 };
-// item flags (u16): bit k = coverage plane k present (k < SKB_CLIP_PLANES = 8), bit 8 = plane 0 is solid 255
+// item flags (u16): bit k = coverage plane k present (k < SKB_CLIP_PLANES = 8), bit 8 = plane 0 is solid 255,
+// bit 9 = zmask holds this item's zero-coverage map
 #define SKB_ITEM_PLANE0 1u
 #define SKB_ITEM_PLANE1 2u
 #define SKB_ITEM_SOLID 256u
+#define SKB_ITEM_ZERO 512u
 #define SKB_ITEM_PLANE_MASK 255u
 
 #define COVER_WARPS 4
@@ -375,6 +381,8 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   const SurfDesc sd = c.surfs[o.surface];
   const int xmax = min(g.scan_r, (int)sd.w);
   const int xmin = max(g.scan_l, 0);
+  // blend modes that change the destination under a zero source: remember which pixels a direct span touched
+  const bool zmode = c.zmask != nullptr && blend_zero_src_matters(paint_blend_mode(c.paints[o.paint]));
   // lanes 0..15 own the row table entries of the 16 pixel rows
   uint2 row = make_uint2(0u, 0u);
   {
@@ -498,7 +506,11 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
         const TrapPrep pr = trap_prepare(c.pool[sm.z_rec[e]]);
         for (int xr = xs; xr < xe; xr++) {
           uint8_t v = 0;
-          if (!trap_prep_alpha(pr, cx + xr, &v) || v == 0) continue;
+          if (!trap_prep_alpha(pr, cx + xr, &v)) continue;
+          if (v == 0) {  // bit 15 of the pixel's 16-bit sum: touched by a direct span whose coverage is 0
+            if (zmode && !accum) atomicAdd(&Aw[(rr_ * COVER_CW + xr) >> 1], 0x8000u << (16 * (xr & 1)));
+            continue;
+          }
           if (accum) atomicAdd(&Aw[(rr_ * COVER_CW + xr) >> 1], (uint32_t)v << (16 * (xr & 1)));
           else Db[rr_ * COVER_CW + xr] = v;
         }
@@ -544,6 +556,15 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
       const int xr = tx * SKB_TILE - cx + half * 8;
       const uint2 dv = *reinterpret_cast<const uint2*>(Db + prow * COVER_CW + xr);
       uint4 av = *reinterpret_cast<const uint4*>(Aw + ((prow * COVER_CW + xr) >> 1));
+      uint32_t z0 = 0, z1 = 0;
+      if (zmode) {
+        z0 = __byte_perm((av.x >> 15) & 0x00010001u, (av.y >> 15) & 0x00010001u, 0x6420);
+        z1 = __byte_perm((av.z >> 15) & 0x00010001u, (av.w >> 15) & 0x00010001u, 0x6420);
+        av.x &= 0x7FFF7FFFu;
+        av.y &= 0x7FFF7FFFu;
+        av.z &= 0x7FFF7FFFu;
+        av.w &= 0x7FFF7FFFu;
+      }
       // saturate the 16-bit sums and pack them to bytes
       av.x = __vminu2(av.x, 0x00FF00FFu);
       av.y = __vminu2(av.y, 0x00FF00FFu);
@@ -555,12 +576,17 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
       const uint32_t nd1 = ((dv.y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | dv.y) & 0x80808080u;
       const uint32_t na0 = ((a0 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | a0) & 0x80808080u;
       const uint32_t na1 = ((a1 & 0x7F7F7F7Fu) + 0x7F7F7F7Fu | a1) & 0x80808080u;
-      const bool any = __any_sync(0xffffffffu, (dv.x | dv.y | a0 | a1) != 0);
+      const bool any = __any_sync(0xffffffffu, (dv.x | dv.y | a0 | a1 | z0 | z1) != 0);
       if (!any) continue;
+      const bool anyz = zmode && __any_sync(0xffffffffu, (z0 | z1) != 0);
       const bool both = __any_sync(0xffffffffu, ((nd0 & na0) | (nd1 & na1)) != 0);
       const bool solid = __all_sync(0xffffffffu, (dv.x & dv.y) == 0xFFFFFFFFu && (a0 | a1) == 0);
       const uint32_t item = item_row + (uint32_t)(tx - g.tx0);
       uint32_t flags = SKB_ITEM_PLANE0;
+      if (anyz) {
+        flags |= SKB_ITEM_ZERO;
+        reinterpret_cast<uint2*>(c.zmask + (size_t)item * 256)[lane] = make_uint2(z0, z1);
+      }
       if (solid) {
         flags |= SKB_ITEM_SOLID;
       } else {
@@ -766,7 +792,8 @@ __global__ void k_scatter(CoverArgs c, const uint32_t* tile_off, uint32_t* tile_
   uint32_t pos = tile_off[tile] + atomicAdd(&tile_fill[tile], n);
   for (uint32_t k = 0; k < SKB_CLIP_PLANES; k++) {
     if (!((flags >> k) & 1u)) continue;
-    cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u));
+    cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u) |
+                                                ((k == 0 && (flags & SKB_ITEM_ZERO)) ? SKB_CMD_ZERO : 0u));
   }
 }
 
@@ -785,6 +812,7 @@ struct FineArgs {
   const skb_dl_paint* paints;
   const float* stops;
   const uint8_t* mask[SKB_CLIP_PLANES];
+  const uint8_t* zmask;
 };
 #define FINE_WARPS 4
 #define FINE_SORT_CAP 256
@@ -856,13 +884,20 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
     if (cmd.y & SKB_CMD_SOLID) {
       lo = hi = 0xFFFFFFFFu;
     } else {
-      const uint8_t* m = a.mask[cmd.x & 7u] + (size_t)(cmd.y & 0x7FFFFFFFu) * 256;
+      const uint8_t* m = a.mask[cmd.x & 7u] + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256;
       uint2 mv = reinterpret_cast<const uint2*>(m)[lane];
       lo = mv.x;
       hi = mv.y;
     }
-    if ((lo | hi) == 0) continue;
-    if (ptype == SKB_PAINT_SOLID) {
+    uint32_t zlo = 0, zhi = 0;
+    if (cmd.y & SKB_CMD_ZERO) {
+      uint2 zv = reinterpret_cast<const uint2*>(a.zmask + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256)[lane];
+      zlo = zv.x;
+      zhi = zv.y;
+    }
+    if ((lo | hi | zlo | zhi) == 0) continue;
+    const uint32_t bmode = a.paints[pidx].blend;
+    if (ptype == SKB_PAINT_SOLID && bmode == 0) {
       const uint32_t color = a.geom[op].color;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -883,10 +918,14 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
         img.pitch = is.pitch;
       }
 #pragma unroll 1
+      const uint32_t mode = paint_blend_mode(pt);
+      const bool zmode = blend_zero_src_matters(mode);
       for (int j = 0; j < 8; j++) {
         uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
+        // a span reaches the pixel when its coverage is non-zero, or zero on a direct span (zmask)
+        const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
         cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
-        if (cv) dst[j] = blend_cover(dst[j], paint_color(pt, a.stops, img, x0 + j, y), cv);
+        if (cv || (touched && zmode)) dst[j] = blend_cover_mode(dst[j], paint_color(pt, a.stops, img, x0 + j, y), cv, mode);
       }
     }
   }
@@ -1126,10 +1165,11 @@ struct skb_surface_s {
   // frame
   std::vector<uint8_t> host_dl;
   bool have_frame = false;
+  bool zero_blend = false;  // some paint blends with a mode that acts on zero-coverage pixels
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, zmask, item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -1264,6 +1304,14 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
              ((uint64_t)pt.stop_off + 5ull * pt.n_colors > h.n_stop_floats || pt.n_colors < 1))) {
           set_error("display list: bad paint");
           return SKB_ERROR_BAD_DISPLAY_LIST;
+        }
+        if (pt.blend > 22 || (pt.blend > 15 && pt.blend != 22)) {
+          set_error("display list: blend mode outside what SWRenderTarget implements (kClear..kScreen, kSoftLight)");
+          return SKB_ERROR_BAD_DISPLAY_LIST;
+        }
+        if (o.clip_in != 0 && pt.blend && blend_zero_src_matters(pt.blend - 1)) {
+          set_error("blend modes that act on zero-coverage pixels are not implemented under a path clip");
+          return SKB_ERROR_UNSUPPORTED;
         }
       }
       if (o.kind == SKB_OP_CLIP && (o.clip_out == 0 || o.clip_out > h.n_clip_states)) {
@@ -1502,6 +1550,12 @@ static skb_result run_frame(skb_surface s) {
   ca.mask[1] = ca.mask1;
   ca.item_flags = (uint16_t*)s->item_flags.p;
   ca.tile_cnt = (uint32_t*)s->tile_cnt.p;
+  ca.paints = t.paints;
+  ca.zmask = nullptr;
+  if (s->zero_blend) {
+    SKB_TRY(buf_reserve(s->zmask, (n_items + 1) * 256));
+    ca.zmask = (uint8_t*)s->zmask.p;
+  }
   // clip structure of the frame (host side): nesting depth of every clip state, clipped draws present?
   bool has_clip_ops = false, has_clipped_fills = false;
   int max_depth = 0;
@@ -1613,6 +1667,7 @@ static skb_result run_frame(skb_surface s) {
   fa.paints = t.paints;
   fa.stops = t.stops;
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.mask[k] = ca.mask[k];
+  fa.zmask = ca.zmask;
   float ms_fine_tmp = 0;
   (void)ms_fine_tmp;
   if (h.n_surfaces > 1) {
@@ -1799,7 +1854,7 @@ void skb_surface_destroy(skb_surface s) {
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
   Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
-                 &s->counters, &s->mask0, &s->mask1, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
+                 &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
   for (Buf* b : bufs) buf_free(*b);
@@ -1843,6 +1898,12 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
   memcpy(&h, dl, sizeof(h));
   // the header tables (surfaces, ops) are also read on the host while launching
   s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_paths);
+  s->zero_blend = false;
+  {
+    const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
+    for (uint32_t i = 0; i < h.n_paints; i++)
+      if (paints[i].blend && blend_zero_src_matters(paints[i].blend - 1)) s->zero_blend = true;
+  }
   SKB_TRY(buf_reserve(s->dl, h.total_bytes));
   SKB_CUDA(cudaMemcpyAsync(s->dl.p, dl, h.total_bytes, cudaMemcpyHostToDevice, s->stream));
   s->have_frame = true;

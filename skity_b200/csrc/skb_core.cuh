@@ -772,6 +772,86 @@ SKB_HD uint32_t blend_cover(uint32_t dst, uint32_t color, uint32_t cover) {
   return color + alpha_mul_q(dst, 256 - a);
 }
 
+// PorterDuffBlend (src/graphic/blend_mode.cc:92-192) on premultiplied pixel words.  Every mode treats
+// the colour channels alike, so the R/B order of the word does not matter; alpha is the top byte.
+// `mode` is skity::BlendMode's value; modes the reference does not implement (above kScreen, other
+// than kSoftLight) fall back to kSrcOver there (:129-133) — the host canonicalises them.
+#define SKB_BLEND_SRC_OVER 3u
+SKB_HD uint32_t pm_color_mul(uint32_t s, uint32_t d) {  // PMColorMul (color_priv.hpp:74-79)
+  return (mul_div_255_round(s >> 24, d >> 24) << 24) | (mul_div_255_round((s >> 16) & 0xFF, (d >> 16) & 0xFF) << 16) |
+         (mul_div_255_round((s >> 8) & 0xFF, (d >> 8) & 0xFF) << 8) | mul_div_255_round(s & 0xFF, d & 0xFF);
+}
+SKB_HD float soft_light_component(float sx, float sy, float dx, float dy) {  // blend_mode.cc:92-108
+  if (2.f * sx <= sy) {
+    return dx * dx * (sy - 2 * sx) / dy + (1 - dy) * sx + dx * (-sy + 2 * sx + 1);
+  } else if (4.f * dx <= dy) {
+    float DSqd = dx * dx;
+    float DCub = DSqd * dx;
+    float DaSqd = dy * dy;
+    float DaCub = DaSqd * dy;
+    return (DaSqd * (sx - dx * (3 * sy - 6 * sx - 1)) + 12 * dy * DSqd * (sy - 2 * sx) - 16 * DCub * (sy - 2 * sx) -
+            DaCub * sx) /
+           DaSqd;
+  } else {
+    return dx * (sy - 2 * sx + 1) + sx - sqrtf(dy * dx) * (sy - 2 * sx) - dy * sx;
+  }
+}
+SKB_HDN uint32_t porter_duff(uint32_t src, uint32_t dst, uint32_t mode) {
+  const uint32_t sa = src >> 24, da = dst >> 24;
+  switch (mode) {
+    case 0: return 0;                                                 // kClear
+    case 1: return src;                                               // kSrc
+    case 2: return dst;                                               // kDst
+    case 3: return sa == 0 ? dst : src + alpha_mul_q(dst, 256 - sa);  // kSrcOver (PMSrcOver)
+    case 4: return da == 255 ? dst : dst + alpha_mul_q(src, 256 - da);                // kDstOver
+    case 5: return da == 255 ? src : alpha_mul_q(src, da + 1);                        // kSrcIn
+    case 6: return sa == 255 ? dst : alpha_mul_q(dst, sa + 1);                        // kDstIn
+    case 7: return da == 0 ? src : alpha_mul_q(src, 256 - da);                        // kSrcOut
+    case 8: return sa == 0 ? dst : alpha_mul_q(dst, 256 - sa);                        // kDstOut
+    case 9: return alpha_mul_q(src, da + 1) + alpha_mul_q(dst, 256 - sa);             // kSrcATop
+    case 10: return alpha_mul_q(dst, sa + 1) + alpha_mul_q(src, 256 - da);            // kDstATop
+    case 11: return alpha_mul_q(src, 256 - da) + alpha_mul_q(dst, 256 - sa);          // kXor
+    case 12: {                                                                        // kPlus
+      uint32_t r = 0;
+      for (int sh = 0; sh < 32; sh += 8) {
+        uint32_t v = ((src >> sh) & 0xFF) + ((dst >> sh) & 0xFF);
+        r |= (v > 255u ? 255u : v) << sh;
+      }
+      return r;
+    }
+    case 13: return pm_color_mul(src, dst);                                           // kModulate
+    case 14: return src + dst - pm_color_mul(src, dst);                               // kScreen
+    case 21: {                                                                        // kSoftLight
+      if (da == 0) return src;
+      float s[4], d[4];
+      for (int k = 0; k < 4; k++) {  // Color4fFromColor (color.cc:44-51)
+        s[k] = (float)((src >> (8 * k)) & 0xFF) / 255.f;
+        d[k] = (float)((dst >> (8 * k)) & 0xFF) / 255.f;
+      }
+      uint32_t r = 0;
+      for (int k = 0; k < 3; k++) r |= unit_to_byte(soft_light_component(s[k], s[3], d[k], d[3])) << (8 * k);
+      r |= unit_to_byte(s[3] + (1 - s[3]) * d[3]) << 24;
+      return r;
+    }
+    default: return dst;
+  }
+}
+// SWSpanBrush::BrushH + SWRenderTarget::BlendPixel for any blend mode (sw_span_brush.cc:108-119,
+// sw_render_target.cc:12-35; FastBlend's shortcuts :97-141 give the same values as the formulas).
+// Modes whose result changes the destination even when the (coverage-scaled) source is zero.  The
+// reference's directly emitted spans include pixels whose coverage came out as 0
+// (RealSpanBuilder::BuildSpans, sw_raster.cc:45-53), so for these modes such pixels are blended too;
+// accumulated spans never carry 0 (SpanBuilder::Flush :111-134).
+SKB_HD bool blend_zero_src_matters(uint32_t mode) {
+  return mode == 0 || mode == 1 || mode == 5 || mode == 6 || mode == 7 || mode == 10 || mode == 13 || mode == 21;
+}
+SKB_HD uint32_t paint_blend_mode(const skb_dl_paint& p) { return p.blend ? p.blend - 1 : SKB_BLEND_SRC_OVER; }
+SKB_HD uint32_t blend_cover_mode(uint32_t dst, uint32_t color, uint32_t cover, uint32_t mode) {
+  if (mode == SKB_BLEND_SRC_OVER) return blend_cover(dst, color, cover);
+  if (cover != 255) color = alpha_mul_q(color, cover);
+  return porter_duff(color, dst, mode);
+}
+
 // GradientColorBrush::LerpColor (sw_span_brush.cc:21-32,239-299) -> premultiplied pixel word
 SKB_HDN uint32_t gradient_color(const skb_dl_paint& p, const float* pool, float t) {
   const float* colors = pool + p.stop_off;

@@ -336,11 +336,33 @@ Rect ComputeBoundsIfStroke(Rect bounds, const Paint& paint) {
 }  // namespace
 
 // SWCanvas::GenerateBrush (sw_canvas.cc:727-795), not-drawing-layer branch.
+// SWRenderTarget implements kClear..kScreen and kSoftLight; everything else falls back to kSrcOver
+// (src/graphic/blend_mode.cc:129-133).  0 encodes the default.
+static uint32_t EncodeBlend(BlendMode mode) {
+  auto m = static_cast<int32_t>(mode);
+  if (m < 0 || (m > static_cast<int32_t>(BlendMode::kScreen) && mode != BlendMode::kSoftLight)) return 0;
+  return mode == BlendMode::kSrcOver ? 0u : static_cast<uint32_t>(m) + 1u;
+}
+
+// include/skb_dl.h: these modes change the destination even where a span's coverage is 0
+static bool BlendNeedsZeroCoverage(uint32_t encoded) {
+  switch (encoded) {
+    case 1: case 2: case 6: case 7: case 8: case 11: case 14: case 22:
+      return true;
+    default:
+      return false;
+  }
+}
+
 uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
   skb_dl_paint p{};
   p.global_alpha = 255;
+  p.blend = EncodeBlend(paint.GetBlendMode());
+  if (BlendNeedsZeroCoverage(p.blend) && state_stack_.back().clip_id != 0) {
+    NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
+    p.blend = 0;
+  }
   if (paint.GetColorFilter()) NoteUnsupported("color filter");
-  if (paint.GetBlendMode() != BlendMode::kSrcOver) NoteUnsupported("blend mode other than SrcOver");
   auto shader = paint.GetShader();
   if (shader) {
     Shader::GradientInfo info{};
@@ -517,8 +539,12 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
   p.image_surface = src_surface;
   // work_paint.SetStyle(kFill) precedes GetAlphaF() in the reference (sw_canvas.cc:656,784)
   p.global_alpha = static_cast<uint8_t>(255 * paint.GetFillColor().a);
+  p.blend = EncodeBlend(paint.GetBlendMode());
+  if (BlendNeedsZeroCoverage(p.blend) && state_stack_.back().clip_id != 0) {
+    NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
+    p.blend = 0;
+  }
   if (paint.GetColorFilter()) NoteUnsupported("color filter");
-  if (paint.GetBlendMode() != BlendMode::kSrcOver) NoteUnsupported("blend mode other than SrcOver");
   uint32_t paint_index = builder_->AddPaint(p);
 
   Path path;

@@ -16,6 +16,7 @@
 //            3 outer,4 inner), f32 blur_radius, u32 shader(0 none,1 linear,2 radial,3 sweep)
 //            [shader: f32 p[4], u32 tile_mode, u32 n_colors, u32 n_stops, u32 has_local,
 //             f32 local[6] (sx kx tx ky sy ty), f32 rgba[4*n_colors], f32 stops[n_stops]]
+//            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode)
 #ifndef SKITY_B200_HOST_SCENE_PLAYER_HPP
 #define SKITY_B200_HOST_SCENE_PLAYER_HPP
 
@@ -157,6 +158,8 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
   float blur_radius = r.F32();
   uint32_t shader = r.U32();
   if (!r.ok()) return false;
+  const bool extras = (style & 0x100u) != 0;
+  style &= 0xFFu;
   paint->SetStyle(static_cast<skity::Paint::Style>(style));
   paint->SetStrokeWidth(sw);
   paint->SetStrokeMiter(miter);
@@ -201,6 +204,11 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
     }
     if (sh && has_local) sh->SetLocalMatrix(Affine(local));
     paint->SetShader(sh);
+  }
+  if (extras) {
+    uint32_t blend = r.U32();
+    if (!r.ok() || blend > static_cast<uint32_t>(skity::BlendMode::kLastMode)) return false;
+    paint->SetBlendMode(static_cast<skity::BlendMode>(blend));
   }
   return true;
 }

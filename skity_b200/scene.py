@@ -75,23 +75,29 @@ class PathData:
 
 class Paint:
     def __init__(self, style=FILL, fill=(0, 0, 0, 1), stroke=(0, 0, 0, 1), stroke_width=1.0, miter=4.0,
-                 cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None):
+                 cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None, blend=None):
         self.style, self.fill, self.stroke = style, fill, stroke
         self.stroke_width, self.miter, self.cap, self.join = stroke_width, miter, cap, join
         self.blur_radius, self.blur_style = blur_radius, blur_style
+        self.blend = blend    # skity::BlendMode value, None = default (kSrcOver)
         self.shader = shader  # dict(type=1|2|3, p=(..4), tile=, colors=[(r,g,b,a)..], stops=[..]|None, local=None|6)
 
     def encode(self):
-        out = struct.pack("<I2f2I", self.style, self.stroke_width, self.miter, self.cap, self.join)
+        extras = self.blend is not None
+        out = struct.pack("<I2f2I", self.style | (0x100 if extras else 0), self.stroke_width, self.miter, self.cap, self.join)
         out += np.asarray(self.fill, dtype=np.float32).tobytes()
         out += np.asarray(self.stroke, dtype=np.float32).tobytes()
         if self.blur_radius > 0:
             out += struct.pack("<If", self.blur_style, self.blur_radius)
         else:
             out += struct.pack("<If", 0, 0.0)
+        return out + self._encode_shader() + (struct.pack("<I", self.blend) if extras else b"")
+
+    def _encode_shader(self):
+        out = b""
         sh = self.shader
         if not sh:
-            return out + struct.pack("<I", 0)
+            return struct.pack("<I", 0)
         colors = np.asarray(sh["colors"], dtype=np.float32).reshape(-1, 4)
         stops = sh.get("stops")
         stops = np.asarray(stops if stops is not None else [], dtype=np.float32)
@@ -369,3 +375,30 @@ def scene_random_fills_fast(n_paths, size, seed, box=256.0, width=None, height=N
     if n_even > n_odd:
         body[n_odd * pair:] = ev[-1]
     return SceneBlob(w, h, n_paths, struct.pack("<6I", MAGIC, 1, w, h, n_paths, 0) + body.tobytes())
+
+
+def scene_blend_modes(seed=21, size=480):
+    """Every blend mode SWRenderTarget implements (kClear..kScreen, kSoftLight; one unsupported mode,
+    kOverlay, which falls back to kSrcOver: src/graphic/blend_mode.cc:125-192) over a busy backdrop,
+    with translucent and opaque sources, a gradient source and anti-aliased edges."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size * 0.5, Paint(fill=(0.9, 0.8, 0.2, 1.0)))
+    s.draw_rect(0, size * 0.25, size * 0.6, size, Paint(fill=(0.1, 0.5, 0.9, 0.6)))
+    for i in range(10):
+        p = _random_closed_path(rng, rng.uniform(0, size), rng.uniform(0, size), 200.0, i)
+        s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (rng.uniform(0.3, 1.0),)))
+    modes = list(range(0, 15)) + [21, 15]
+    cols = 5
+    cell = size / cols
+    for k, mode in enumerate(modes):
+        cx, cy = (k % cols + 0.5) * cell, (k // cols + 0.5) * cell
+        p = _random_closed_path(rng, cx, cy, cell * 1.1, k)
+        alpha = 1.0 if k % 3 == 0 else float(rng.uniform(0.3, 0.9))
+        if k % 4 == 3:
+            sh = dict(type=1, p=(cx - cell / 2, cy, cx + cell / 2, cy), tile=CLAMP,
+                      colors=[(1, 0, 0, 1), (0, 1, 0, 0.5), (0, 0, 1, 1)], stops=None)
+            s.draw_path(p, Paint(shader=sh, blend=mode))
+        else:
+            s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), blend=mode))
+    return s

@@ -81,12 +81,16 @@ def golden_scenes():
     add_rect(e, 88.5, 60.5, 103.5, 76.5)
     s.draw_path(e, white)
     out["golden_canonical_edges_192x144"] = s
+    out["blend_modes_480"] = scene.scene_blend_modes()
     return out
 
 
 def main():
     assert refsw.available(), "build oracle/_ref first (python oracle/build_ref.py)"
+    only = set(sys.argv[1:])        # optional: regenerate just the named fixtures
     for name, s in golden_scenes().items():
+        if only and name not in only:
+            continue
         blob = s.encode()
         rgba = refsw.render_scene(blob)
         dl = hostlib.encode_scene(blob)
@@ -102,6 +106,8 @@ def main():
                             rgba=rgba, **extra)
         print(f"{name}: {rgba.shape[1]}x{rgba.shape[0]} sum={int(rgba.astype(np.int64).sum())} "
               f"-> {os.path.getsize(path)} bytes")
+    if only and "raster_spans" not in only:
+        return
     # span-level vectors: SWRaster::RastePath of a few paths
     rng = np.random.RandomState(11)
     spans_out = {}

@@ -46,7 +46,8 @@ def assert_within_tolerance(got, want):
 
 
 EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c3_blur_12_640",
-         "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144"]
+         "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144",
+         "blend_modes_480"]
 
 
 @pytest.mark.parametrize("name", EXACT)
@@ -284,7 +285,7 @@ def test_two_surfaces_in_flight_with_async_read_back(dev):
     read-back (what bench.py's end-to-end loop does); every frame must equal the synchronous result."""
     s = scene.scene_random_fills(300, 640, 77, box=200.0)
     dl = hostlib.encode_scene(s.encode())
-    want, _ = port.render(dl)
+    want = port.render(dl)
     lanes = [(dev.create_surface(640, 640), np.zeros((640, 640, 4), np.uint8)) for _ in range(2)]
     try:
         for i in range(6):
