@@ -63,17 +63,20 @@ typedef struct skb_dl_surface {
 enum skb_dl_op_kind {
   SKB_OP_FILL = 1, /* SWRaster::RastePath + SWSpanBrush::Brush of one path */
   SKB_OP_CLIP = 2, /* SWCanvas::OnClipPath: rasterise and combine into a new clip state */
-  SKB_OP_BLUR = 3  /* SWStackBlur: surface aux -> surface `surface`, radius in clip_bounds[0] */
+  SKB_OP_BLUR = 3  /* SWStackBlur: surface aux -> surface `surface`, radius in clip_bounds[0]; fill_type = what is
+                      then done to the blurred pixels with the unblurred ones at hand: 0 nothing (BlurStyle::kNormal,
+                      ImageFilters::Blur), 2 kSolid, 3 kOuter, 4 kInner (src/effect/mask_filter.cc:64-100),
+                      5 drop shadow (src/effect/image_filter.cc:222-233) with the colour in `paint` */
 };
 
 typedef struct skb_dl_op {
   uint32_t kind;
   uint32_t surface;   /* FILL/CLIP: target surface; BLUR: destination surface */
   uint32_t path;      /* FILL/CLIP */
-  uint32_t paint;     /* FILL */
+  uint32_t paint;     /* FILL; BLUR style 5: the shadow's skity::Color (A<<24|R<<16|G<<8|B, unpremultiplied) */
   uint32_t clip_in;   /* FILL: clip state applied; CLIP: state being refined (0 = none) */
   uint32_t clip_out;  /* CLIP: id of the state this op defines */
-  uint32_t fill_type; /* 0 nonzero winding, 1 even-odd (Path::PathFillType) */
+  uint32_t fill_type; /* 0 nonzero winding, 1 even-odd (Path::PathFillType); BLUR: style, see SKB_OP_BLUR */
   uint32_t aux;       /* CLIP: Canvas::ClipOp (0 difference, 1 intersect); BLUR: source surface */
   float ctm[6];       /* sx kx tx ky sy ty — SWCanvas::CurrentTransform() */
   float clip_bounds[4]; /* l t r b — SWCanvas::GetScanClipBounds(); BLUR: [0] = integer radius */
@@ -120,9 +123,13 @@ enum skb_dl_paint_type {
   SKB_PAINT_IMAGE = 4 /* PixmapBrush, nearest, decal/decal (the blur composite) */
 };
 
+/* IMAGE paints: the sampled surface holds unpremultiplied pixels (PixmapBrush premultiplies after sampling,
+ * sw_span_brush.cc:573-576) — ORed into tile_mode */
+#define SKB_PAINT_IMAGE_UNPREMUL 0x100u
+
 typedef struct skb_dl_paint {
   uint32_t type;
-  uint32_t tile_mode; /* skity::TileMode: 0 clamp 1 repeat 2 mirror 3 decal */
+  uint32_t tile_mode; /* skity::TileMode: 0 clamp 1 repeat 2 mirror 3 decal (low byte) */
   float color[4];     /* SOLID: unpremultiplied r g b a as Paint holds them (Color4f) */
   float m[6];         /* gradients: PointsToUnit * device_to_local; IMAGE: Scale(1/w,1/h) * inv(local) * inv(CTM)
                          — sx kx tx ky sy ty, as GenerateBrush builds it (sw_canvas.cc:727-795) */

@@ -1162,7 +1162,9 @@ static uint32_t paint_color(const skb_dl_paint* p, const float* pool, const surf
       if (ix > s->w - 1) ix = s->w - 1;
       if (iy > s->h - 1) iy = s->h - 1;
       const uint8_t* t = s->px + ((size_t)iy * s->w + ix) * 4;
-      return (requant(t[3]) << 24) | (requant(t[0]) << 16) | (requant(t[1]) << 8) | requant(t[2]);
+      uint32_t c = (requant(t[3]) << 24) | (requant(t[0]) << 16) | (requant(t[1]) << 8) | requant(t[2]);
+      /* an unpremultiplied texture is premultiplied after sampling — sw_span_brush.cc:573-576 */
+      return (p->tile_mode & SKB_PAINT_IMAGE_UNPREMUL) ? color_to_pm(c) : c;
     }
   }
   return 0;
@@ -1411,6 +1413,33 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
         surface* s = &surfs[op->aux];
         if (d->w != s->w || d->h != s->h) { rc = -3; break; }
         stack_blur(s->px, d->px, (int)s->w, (int)s->h, (int)op->clip_bounds[0]);
+        /* MaskFilterOnFilter styles — src/effect/mask_filter.cc:64-100 ; DropShadowImageFilter::OnFilter —
+         * src/effect/image_filter.cc:222-233 (pixels are R,G,B,A bytes) */
+        if (op->fill_type) {
+          for (size_t i = 0; i < (size_t)s->w * s->h; i++) {
+            const uint8_t* raw = s->px + 4 * i;
+            uint8_t* out = d->px + 4 * i;
+            uint32_t raw_a = raw[3], blur_a = out[3];
+            if (op->fill_type == 2) {
+              if (raw_a > 0) memcpy(out, raw, 4);
+            } else if (op->fill_type == 3) {
+              if (raw_a > 0 && raw_a >= blur_a) memset(out, 0, 4);
+            } else if (op->fill_type == 4) {
+              if (raw_a > 0) {
+                const float a_factor = 1.f / 255.f;
+                uint32_t c = ((uint32_t)out[3] << 24) | ((uint32_t)out[0] << 16) | ((uint32_t)out[1] << 8) | out[2];
+                c = alpha_mul_q(c, (unsigned)(a_factor * raw_a * blur_a));
+                out[0] = (uint8_t)(c >> 16); out[1] = (uint8_t)(c >> 8); out[2] = (uint8_t)c; out[3] = (uint8_t)(c >> 24);
+              } else {
+                memset(out, 0, 4);
+              }
+            } else if (op->fill_type == 5) {
+              uint32_t col = op->paint; /* the filter's Color, unpremultiplied A<<24|R<<16|G<<8|B */
+              if (blur_a > 0) { out[0] = (uint8_t)(col >> 16); out[1] = (uint8_t)(col >> 8); out[2] = (uint8_t)col; out[3] = (uint8_t)blur_a; }
+              else memset(out, 0, 4);
+            }
+          }
+        }
       } break;
       default:
         rc = -4;

@@ -46,7 +46,7 @@ struct SurfDesc {
   uint32_t tiles_x, tiles_y;
   uint32_t tile_base;   // first global tile index
   uint32_t row0, row1;  // rows this device renders (band), whole surface for temporaries
-  uint32_t final_pass;  // composited after the blur stage (surface 0 and batch canvases)
+  uint32_t level;       // pass in which the surface is composited: after every surface its draws sample or are blurred from
   uint32_t pad;
 };
 
@@ -235,6 +235,7 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
     if (o.kind == SKB_OP_FILL) {
       const skb_dl_paint pt = t.paints[o.paint];
       g.color = pt.type == SKB_PAINT_SOLID ? color4f_to_pm_word(pt.color[0], pt.color[1], pt.color[2], pt.color[3]) : 0u;
+      g.fast_solid = (pt.type == SKB_PAINT_SOLID && pt.blend == 0) ? 1u : 0u;
     }
     geom[op] = g;
   }
@@ -803,7 +804,7 @@ struct FineArgs {
   const uint2* cmds;
   uint2* cmds_sorted;  // scratch for tiles whose list does not fit the shared-memory sorter
   uint32_t tile_begin, tile_end;
-  uint32_t final_pass;  // which surfaces this launch composites
+  uint32_t level;  // which surfaces this launch composites
   const SurfDesc* surfs;
   const uint32_t* surf_tile_base;  // n_surfaces + 1
   uint32_t n_surfaces;
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
   if (n == 0) return;
   const uint32_t s = find_interval(a.surf_tile_base, a.n_surfaces, tile);
   const SurfDesc sd = a.surfs[s];
-  if (sd.final_pass != a.final_pass) return;
+  if (sd.level != a.level) return;
   const uint32_t local = tile - sd.tile_base;
   const int tx = (int)(local % sd.tiles_x), ty = (int)(local / sd.tiles_x);
   const int y = ty * SKB_TILE + (lane >> 1);
@@ -878,8 +879,6 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
   for (uint32_t i = 0; i < n; i++) {
     const uint2 cmd = list[i];
     const uint32_t op = cmd.x >> 3;
-    const uint32_t pidx = a.ops[op].paint;
-    const uint32_t ptype = a.paints[pidx].type;
     uint32_t lo, hi;
     if (cmd.y & SKB_CMD_SOLID) {
       lo = hi = 0xFFFFFFFFu;
@@ -889,22 +888,25 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
       lo = mv.x;
       hi = mv.y;
     }
-    uint32_t zlo = 0, zhi = 0;
-    if (cmd.y & SKB_CMD_ZERO) {
-      uint2 zv = reinterpret_cast<const uint2*>(a.zmask + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256)[lane];
-      zlo = zv.x;
-      zhi = zv.y;
-    }
-    if ((lo | hi | zlo | zhi) == 0) continue;
-    const uint32_t bmode = a.paints[pidx].blend;
-    if (ptype == SKB_PAINT_SOLID && bmode == 0) {
-      const uint32_t color = a.geom[op].color;
+    const uint2 gc = *reinterpret_cast<const uint2*>(&a.geom[op].color);  // color, fast_solid
+    if (gc.y) {
+      if ((lo | hi) == 0) continue;
+      const uint32_t color = gc.x;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
         if (cv) dst[j] = blend_cover(dst[j], color, cv);
       }
     } else {
+      uint32_t zlo = 0, zhi = 0;
+      if (cmd.y & SKB_CMD_ZERO) {
+        uint2 zv = reinterpret_cast<const uint2*>(a.zmask + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256)[lane];
+        zlo = zv.x;
+        zhi = zv.y;
+      }
+      if ((lo | hi | zlo | zhi) == 0) continue;
+      const uint32_t pidx = a.ops[op].paint;
+      const uint32_t ptype = a.paints[pidx].type;
       const skb_dl_paint pt = a.paints[pidx];
       const uint32_t galpha = ptype == SKB_PAINT_IMAGE ? (pt.global_alpha & 0xFF) : 0xFFu;
       SurfaceView img;
@@ -942,14 +944,39 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
 struct BlurJob {
   uint32_t src, dst;  // surface ids
   int32_t radius;
+  uint32_t style;     // 0 plain blur; BlurStyle kSolid 2 / kOuter 3 / kInner 4 (mask_filter.cc:64-100); 5 drop shadow
+  uint32_t color;     // style 5: the shadow colour (unpremultiplied A<<24|R<<16|G<<8|B)
 };
+
+// What MaskFilterOnFilter / DropShadowImageFilter::OnFilter do to the blurred bitmap with the unblurred
+// one at hand (src/effect/mask_filter.cc:64-100, src/effect/image_filter.cc:222-233), one thread per pixel.
+__global__ void k_blur_style(SurfDesc raw, SurfDesc dst, uint32_t style, uint32_t color) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)dst.w * dst.h) return;
+  const uint32_t x = (uint32_t)(i % dst.w), y = (uint32_t)(i / dst.w);
+  uint32_t* out = reinterpret_cast<uint32_t*>(dst.px + (size_t)y * dst.pitch) + x;
+  const uint32_t raw_c = reinterpret_cast<const uint32_t*>(raw.px + (size_t)y * raw.pitch)[x];
+  const uint32_t blur_c = *out;
+  const uint32_t raw_a = raw_c >> 24, blur_a = blur_c >> 24;
+  if (style == 2) {  // kSolid: the shape itself over its blur
+    if (raw_a > 0) *out = raw_c;
+  } else if (style == 3) {  // kOuter: only the halo
+    if (raw_a > 0 && raw_a >= blur_a) *out = 0;
+  } else if (style == 4) {  // kInner: the blur inside the shape
+    const float a_factor = 1.f / 255.f;
+    *out = raw_a > 0 ? alpha_mul_q(blur_c, (uint32_t)(a_factor * raw_a * blur_a)) : 0u;
+  } else if (style == 5) {  // drop shadow: the shadow colour (kept unpremultiplied) with the blurred alpha
+    *out = blur_a > 0 ? (((color >> 16) & 0xFF) | (((color >> 8) & 0xFF) << 8) | ((color & 0xFF) << 16) | (blur_a << 24)) : 0u;
+  }
+}
+
 
 // Horizontal pass: one CTA per (job, row).  The extended row (n + 2m + 1 samples x 4 channels)
 // lives in shared memory; two block-wide scans produce U.
 __global__ void __launch_bounds__(256) k_blur_h(const BlurJob* jobs, const uint32_t* job_row_base, uint32_t n_jobs,
-                                                const SurfDesc* surfs) {
+                                                const SurfDesc* surfs, uint32_t first_row) {
   extern __shared__ uint32_t sm[];  // [4][len] then per-thread partials
-  const uint32_t grow = blockIdx.x;
+  const uint32_t grow = first_row + blockIdx.x;
   const uint32_t job = find_interval(job_row_base, n_jobs, grow);
   const BlurJob jb = jobs[job];
   const SurfDesc S = surfs[jb.src], D = surfs[jb.dst];
@@ -1048,9 +1075,10 @@ __global__ void __launch_bounds__(256) k_blur_h(const BlurJob* jobs, const uint3
 // Reads of the column lead/lag the writes by >= 1 row only through values already consumed, so the
 // pass needs a separate source: `tmp` holds the H-blurred rows (the job's dst is written last).
 __global__ void __launch_bounds__(128) k_blur_v(const BlurJob* jobs, const uint32_t* job_col_base, uint32_t n_jobs,
-                                                const SurfDesc* surfs, const uint8_t* const* tmp_px) {
-  const uint32_t gcol = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gcol >= job_col_base[n_jobs]) return;
+                                                const SurfDesc* surfs, const uint8_t* const* tmp_px, uint32_t first_col,
+                                                uint32_t end_col) {
+  const uint32_t gcol = first_col + blockIdx.x * blockDim.x + threadIdx.x;
+  if (gcol >= end_col) return;
   const uint32_t job = find_interval(job_col_base, n_jobs, gcol);
   const BlurJob jb = jobs[job];
   const SurfDesc D = surfs[jb.dst];
@@ -1165,6 +1193,11 @@ struct skb_surface_s {
   // frame
   std::vector<uint8_t> host_dl;
   bool have_frame = false;
+  std::vector<uint32_t> surf_level;  // per surface: dependency depth (see SurfDesc::level)
+  uint32_t max_level = 0;
+  cudaEvent_t ev_blur[2 * 16] = {};  // around the blur section of every level
+  uint32_t n_levels_timed = 0;
+  std::vector<uint8_t> surf_drawn;   // per surface: some FILL op targets it
   bool zero_blend = false;  // some paint blends with a mode that acts on zero-coverage pixels
   bool flushed = false;
   skb_frame_stats stats = {};
@@ -1323,8 +1356,12 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
         return SKB_ERROR_UNSUPPORTED;
       }
     } else if (o.kind == SKB_OP_BLUR) {
-      if (o.surface >= h.n_surfaces || o.aux >= h.n_surfaces || o.surface == 0 || o.aux == 0) {
+      if (o.surface >= h.n_surfaces || o.aux >= h.n_surfaces || o.surface == 0 || o.aux == 0 || o.surface == o.aux) {
         set_error("display list: blur surface out of range");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      if (o.fill_type == 1 || o.fill_type > 5) {
+        set_error("display list: unknown blur style");
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
     } else {
@@ -1369,7 +1406,7 @@ static skb_result run_frame(skb_surface s) {
     d.tile_base = tile_base[i];
     d.row0 = 0;
     d.row1 = d.h;
-    d.final_pass = (i == 0 || (hs[i].flags & SKB_SURFACE_CANVAS)) ? 1u : 0u;
+    d.level = s->surf_level[i];
     d.pad = 0;
     tile_base[i + 1] = tile_base[i] + d.tiles_x * d.tiles_y;
     if (i > 0) {
@@ -1386,10 +1423,6 @@ static skb_result run_frame(skb_surface s) {
   for (uint32_t i = 1; i < h.n_surfaces; i++) surfs[i].px = (uint8_t*)s->temp_px.p + temp_off[i];
   if (temp_bytes) SKB_CUDA(cudaMemsetAsync(s->temp_px.p, 0, temp_bytes, st));
   const uint32_t n_tiles = tile_base[h.n_surfaces];
-  bool has_temporaries = false, has_batch_canvases = false;
-  for (uint32_t i = 1; i < h.n_surfaces; i++) {
-    if (surfs[i].final_pass) has_batch_canvases = true; else has_temporaries = true;
-  }
   S.n_tiles = n_tiles;
   SKB_TRY(buf_reserve(s->surfs, surfs.size() * sizeof(SurfDesc)));
   SKB_TRY(buf_reserve(s->surf_tile_base, tile_base.size() * 4));
@@ -1668,19 +1701,7 @@ static skb_result run_frame(skb_surface s) {
   fa.stops = t.stops;
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.mask[k] = ca.mask[k];
   fa.zmask = ca.zmask;
-  float ms_fine_tmp = 0;
-  (void)ms_fine_tmp;
-  if (h.n_surfaces > 1) {
-    fa.tile_begin = tile_base[1];
-    fa.tile_end = n_tiles;
-    fa.final_pass = 0;
-    if (fa.tile_end > fa.tile_begin && has_temporaries) {
-      k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
-      launches++;
-    }
-  }
-  cudaEventRecord(s->ev[6], st);
-  // blur jobs
+  // blur jobs of the whole frame, sorted by the level of their destination
   std::vector<BlurJob> jobs;
   for (uint32_t i = 0; i < n_ops; i++) {
     if (hops[i].kind == SKB_OP_BLUR) {
@@ -1688,6 +1709,8 @@ static skb_result run_frame(skb_surface s) {
       j.src = hops[i].aux;
       j.dst = hops[i].surface;
       j.radius = (int32_t)hops[i].clip_bounds[0];
+      j.style = hops[i].fill_type;
+      j.color = hops[i].paint;
       if (surfs[j.src].w != surfs[j.dst].w || surfs[j.src].h != surfs[j.dst].h) {
         set_error("blur: source and destination surfaces differ in size");
         return SKB_ERROR_BAD_DISPLAY_LIST;
@@ -1695,10 +1718,12 @@ static skb_result run_frame(skb_surface s) {
       jobs.push_back(j);
     }
   }
-  if (!jobs.empty()) {
-    const uint32_t nj = (uint32_t)jobs.size();
-    std::vector<uint32_t> rowb(nj + 1, 0), colb(nj + 1, 0);
-    std::vector<const uint8_t*> tmp_ptrs(nj);
+  std::stable_sort(jobs.begin(), jobs.end(), [&](const BlurJob& x, const BlurJob& y) { return surfs[x.dst].level < surfs[y.dst].level; });
+  const uint32_t nj = (uint32_t)jobs.size();
+  std::vector<uint32_t> rowb(nj + 1, 0), colb(nj + 1, 0);
+  std::vector<const uint8_t*> tmp_ptrs(nj);
+  size_t blur_smem = 0;
+  if (nj) {
     size_t max_len = 0, tmp_bytes = 0;
     std::vector<size_t> tmp_off(nj);
     for (uint32_t i = 0; i < nj; i++) {
@@ -1710,14 +1735,13 @@ static skb_result run_frame(skb_surface s) {
       tmp_off[i] = tmp_bytes;
       tmp_bytes += (size_t)d.pitch * d.tiles_y * SKB_TILE;
     }
-    const size_t smem = max_len * 16;
-    if (smem > 200 * 1024) {
+    blur_smem = max_len * 16;
+    if (blur_smem > 200 * 1024) {
       set_error("blur: surface too wide for the shared-memory row scan");
       return SKB_ERROR_UNSUPPORTED;
     }
     // H pass writes into a scratch copy of each destination, V pass reads it and writes the destination
     SKB_TRY(buf_reserve(s->blur_tmp, tmp_bytes + 256));
-    std::vector<SurfDesc> hsurf2 = surfs;  // descriptors with dst redirected to scratch for the H pass
     SKB_TRY(buf_reserve(s->blur_jobs, nj * sizeof(BlurJob)));
     SKB_TRY(buf_reserve(s->blur_rows, (nj + 1) * 4));
     SKB_TRY(buf_reserve(s->blur_cols, (nj + 1) * 4));
@@ -1733,34 +1757,64 @@ static skb_result run_frame(skb_surface s) {
     SKB_CUDA(cudaMemcpyAsync(s->blur_rows.p, rowb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
     SKB_CUDA(cudaMemcpyAsync(s->blur_cols.p, colb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
     SKB_CUDA(cudaMemcpyAsync(s->blur_tmp_ptrs.p, tmp_ptrs.data(), nj * sizeof(void*), cudaMemcpyHostToDevice, st));
-    if (smem > 48 * 1024) SKB_CUDA(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_blur_h<<<rowb[nj], 256, smem, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj,
-                                           (const SurfDesc*)htab_buf.p);
-    launches++;
-    // radius <= 1: the H kernel copied src into scratch; finish with a plain copy into dst
-    for (uint32_t i = 0; i < nj; i++) {
-      int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
-      if (r <= 1) {
+    if (blur_smem > 48 * 1024)
+      SKB_CUDA(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
+  }
+  if (s->max_level >= 16) {
+    set_error("more than 16 dependent passes (nested layers / filters)");
+    return SKB_ERROR_UNSUPPORTED;
+  }
+  // Level by level: first the blurs that produce surfaces of this level, then the fine pass of the
+  // surfaces drawn at this level (their image sources and blur inputs are complete by construction).
+  s->n_levels_timed = s->max_level + 1;
+  uint32_t j0 = 0;
+  for (uint32_t level = 0; level <= s->max_level; level++) {
+    if (!s->ev_blur[2 * level]) {
+      SKB_CUDA(cudaEventCreate(&s->ev_blur[2 * level]));
+      SKB_CUDA(cudaEventCreate(&s->ev_blur[2 * level + 1]));
+    }
+    cudaEventRecord(s->ev_blur[2 * level], st);
+    uint32_t j1 = j0;
+    while (j1 < nj && surfs[jobs[j1].dst].level == level) j1++;
+    if (j1 > j0) {
+      k_blur_h<<<rowb[j1] - rowb[j0], 256, blur_smem, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj,
+                                                             (const SurfDesc*)s->scan_tmp.p, rowb[j0]);
+      launches++;
+      // radius <= 1: the H kernel copied src into scratch; finish with a plain copy into dst
+      for (uint32_t i = j0; i < j1; i++) {
+        int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
+        if (r <= 1) {
+          const SurfDesc& d = surfs[jobs[i].dst];
+          SKB_CUDA(cudaMemcpyAsync(d.px, tmp_ptrs[i], (size_t)d.pitch * d.h, cudaMemcpyDeviceToDevice, st));
+        }
+      }
+      k_blur_v<<<cdiv(colb[j1] - colb[j0], 128), 128, 0, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_cols.p, nj,
+                                                                 (const SurfDesc*)s->surfs.p,
+                                                                 (const uint8_t* const*)s->blur_tmp_ptrs.p, colb[j0], colb[j1]);
+      launches++;
+      for (uint32_t i = j0; i < j1; i++) {
+        if (jobs[i].style == 0) continue;
         const SurfDesc& d = surfs[jobs[i].dst];
-        SKB_CUDA(cudaMemcpyAsync(d.px, tmp_ptrs[i], (size_t)d.pitch * d.h, cudaMemcpyDeviceToDevice, st));
+        k_blur_style<<<cdiv((uint64_t)d.w * d.h, 256), 256, 0, st>>>(surfs[jobs[i].src], d, jobs[i].style, jobs[i].color);
+        launches++;
       }
     }
-    k_blur_v<<<cdiv(colb[nj], 128), 128, 0, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_cols.p, nj,
-                                                  (const SurfDesc*)s->surfs.p, (const uint8_t* const*)s->blur_tmp_ptrs.p);
-    launches++;
-  }
-  cudaEventRecord(s->ev[7], st);
-  {
-    // canvas tiles of this device's band
-    uint32_t ty0 = surfs[0].row0 / SKB_TILE, ty1 = cdiv(surfs[0].row1, SKB_TILE);
-    fa.tile_begin = ty0 * surfs[0].tiles_x;
-    fa.tile_end = ty1 * surfs[0].tiles_x;
-    fa.final_pass = 1;
-    if (fa.tile_end > fa.tile_begin) {
-      k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
-      launches++;
+    j0 = j1;
+    cudaEventRecord(s->ev_blur[2 * level + 1], st);
+    // fine pass of this level
+    fa.level = level;
+    if (surfs[0].level == level) {  // the canvas: only the tiles of this device's band
+      uint32_t ty0 = surfs[0].row0 / SKB_TILE, ty1 = cdiv(surfs[0].row1, SKB_TILE);
+      fa.tile_begin = ty0 * surfs[0].tiles_x;
+      fa.tile_end = ty1 * surfs[0].tiles_x;
+      if (fa.tile_end > fa.tile_begin) {
+        k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
+        launches++;
+      }
     }
-    if (has_batch_canvases) {  // the canvases of a batch: every surface flagged SKB_SURFACE_CANVAS
+    bool others = false;
+    for (uint32_t i = 1; i < h.n_surfaces && !others; i++) others = surfs[i].level == level && s->surf_drawn[i];
+    if (others) {
       fa.tile_begin = tile_base[1];
       fa.tile_end = n_tiles;
       k_fine<<<cdiv(fa.tile_end - fa.tile_begin, FINE_WARPS), FINE_WARPS * 32, 0, st>>>(fa);
@@ -1862,6 +1916,8 @@ void skb_surface_destroy(skb_surface s) {
   if (s->mapped_host) cudaFreeHost(s->mapped_host);
   for (int i = 0; i < 12; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  for (int i = 0; i < 32; i++)
+    if (s->ev_blur[i]) cudaEventDestroy(s->ev_blur[i]);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
@@ -1898,6 +1954,37 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
   memcpy(&h, dl, sizeof(h));
   // the header tables (surfaces, ops) are also read on the host while launching
   s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_paths);
+  // dependency depth of every surface: a surface is composited after the surfaces its draws sample
+  // (image paints) and after the source of the blur that produces it
+  {
+    const skb_dl_op* ops = (const skb_dl_op*)((const uint8_t*)dl + h.off_ops);
+    const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
+    s->surf_level.assign(h.n_surfaces, 0);
+    s->surf_drawn.assign(h.n_surfaces, 0);
+    for (uint32_t i = 0; i < h.n_ops; i++) {
+      const skb_dl_op& o = ops[i];
+      uint32_t src = 0xFFFFFFFFu;
+      if (o.kind == SKB_OP_FILL) {
+        s->surf_drawn[o.surface] = 1;
+        if (paints[o.paint].type == SKB_PAINT_IMAGE) src = paints[o.paint].image_surface;
+      } else if (o.kind == SKB_OP_BLUR) {
+        src = o.aux;
+      }
+      if (src != 0xFFFFFFFFu) s->surf_level[o.surface] = std::max(s->surf_level[o.surface], s->surf_level[src] + 1);
+    }
+    s->max_level = 0;
+    for (uint32_t i = 0; i < h.n_ops; i++) {  // a source must have been complete when it was used
+      const skb_dl_op& o = ops[i];
+      uint32_t src = 0xFFFFFFFFu;
+      if (o.kind == SKB_OP_FILL && paints[o.paint].type == SKB_PAINT_IMAGE) src = paints[o.paint].image_surface;
+      if (o.kind == SKB_OP_BLUR) src = o.aux;
+      if (src != 0xFFFFFFFFu && s->surf_level[src] >= s->surf_level[o.surface]) {
+        set_error("display list: a surface is sampled before the draws and blurs that feed it");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+    }
+    for (uint32_t l : s->surf_level) s->max_level = std::max(s->max_level, l);
+  }
   s->zero_blend = false;
   {
     const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
@@ -1984,15 +2071,21 @@ skb_result skb_frame_get_stats(skb_surface s, skb_frame_stats* out) {
   SKB_CUDA(cudaStreamSynchronize(s->stream));
   if (s->flushed && s->n_ops) {
     float ms = 0;
-    // ev: 0 start, 1 after flatten, 2 after setup, 3 after walk, 4 after cover, 5 after bin, 6 after fine(temps),
-    //     7 after blur, 8 after fine(canvas)
+    // ev: 0 start, 1 after flatten, 2 after setup, 3 after walk, 4 after cover, 5 after bin, 8 after the last fine pass
     //     9 after k_cover (ev 3..9 = coverage, 9..4 = clip stage)
-    static const int from_ev[9] = {0, 1, 2, 3, 9, 4, 5, 6, 7};
-    static const int to_ev[9] = {1, 2, 3, 9, 4, 5, 6, 7, 8};
-    static const int stage_of[9] = {0, 1, 2, 3, 7, 4, 5, 6, 5};
+    static const int from_ev[7] = {0, 1, 2, 3, 9, 4, 5};
+    static const int to_ev[7] = {1, 2, 3, 9, 4, 5, 8};
+    static const int stage_of[7] = {0, 1, 2, 3, 7, 4, 5};
     for (int i = 0; i < 8; i++) s->stats.ms_stage[i] = 0;
-    for (int i = 0; i < 9; i++) {
+    for (int i = 0; i < 7; i++) {
       if (cudaEventElapsedTime(&ms, s->ev[from_ev[i]], s->ev[to_ev[i]]) == cudaSuccess) s->stats.ms_stage[stage_of[i]] += ms;
+    }
+    // the blur sections sit inside ev 5..8: move their time from "fine" to "blur"
+    for (uint32_t l = 0; l < s->n_levels_timed; l++) {
+      if (cudaEventElapsedTime(&ms, s->ev_blur[2 * l], s->ev_blur[2 * l + 1]) == cudaSuccess) {
+        s->stats.ms_stage[6] += ms;
+        s->stats.ms_stage[5] -= ms;
+      }
     }
     if (cudaEventElapsedTime(&ms, s->ev[0], s->ev[8]) == cudaSuccess) s->stats.ms_total = ms;
     cudaGetLastError();

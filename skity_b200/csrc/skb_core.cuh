@@ -929,7 +929,15 @@ SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const Sur
       if (ix > s.w - 1) ix = s.w - 1;
       if (iy > s.h - 1) iy = s.h - 1;
       const uint8_t* t = s.px + (size_t)iy * s.pitch + (size_t)ix * 4;
-      return requant(t[0]) | (requant(t[1]) << 8) | (requant(t[2]) << 16) | (requant(t[3]) << 24);
+      uint32_t r = requant(t[0]), g = requant(t[1]), b = requant(t[2]);
+      const uint32_t a = requant(t[3]);
+      // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
+      if ((p.tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
+        r = mul_div_255_round(r, a);
+        g = mul_div_255_round(g, a);
+        b = mul_div_255_round(b, a);
+      }
+      return r | (g << 8) | (b << 16) | (a << 24);
     }
     default:
       return 0;

@@ -3,6 +3,8 @@
 #ifndef SKB_STAGES_CUH
 #define SKB_STAGES_CUH
 
+#include <cstddef>
+
 #include "skity_b200/csrc/skb_core.cuh"
 #include "skity_b200/csrc/skb_walk.cuh"
 
@@ -47,7 +49,9 @@ struct OpGeom {
   uint32_t item_base;                      // first (op, tile) work item
   uint32_t first_prim;
   uint32_t color;                          // SOLID paints: premultiplied pixel word
+  uint32_t fast_solid;                     // SOLID paint blended kSrcOver: the fine pass needs nothing but `color`
 };
+static_assert(offsetof(OpGeom, color) % 8 == 0 && sizeof(OpGeom) % 8 == 0, "the fine pass loads (color, fast_solid) as one 64-bit word");
 
 // float -> int the way x86-64 does for (int)f and static_cast<uint32_t>(f) (via 64-bit truncation)
 SKB_HD int32_t f2i_trunc(float f) { return f2i(f); }

@@ -1,7 +1,10 @@
 #include "skity_b200/host/cuda_canvas.hpp"
 
+#include "src/effect/image_filter_base.hpp"
+
 #include <cmath>
 #include <cstring>
+#include <skity/effect/image_filter.hpp>
 #include <skity/effect/mask_filter.hpp>
 #include <skity/effect/path_effect.hpp>
 #include <skity/effect/shader.hpp>
@@ -416,12 +419,7 @@ void CudaCanvas::FillPath(const Path& path, const Paint& paint, bool stroke) {
 // SWCanvas::OnDrawPath (sw_canvas.cc:357-411)
 void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
   if (paint.GetMaskFilter() || paint.GetImageFilter()) {
-    if (paint.GetMaskFilter() && paint.GetMaskFilter()->GetBlurStyle() == BlurStyle::kNormal &&
-        !paint.GetImageFilter()) {
-      HandleMaskBlur(path, paint);
-    } else {
-      NoteUnsupported("mask/image filter other than MaskFilter::MakeBlur(kNormal)");
-    }
+    HandleFilter(path, paint);
     return;
   }
 
@@ -484,16 +482,29 @@ void CudaCanvas::OnDrawPaint(const Paint& paint) {
 
 // SWCanvas::HandleFilter + MaskFilterOnFilter(kNormal) + ImageFilterBase::BlurBitmapToCanvas
 // (sw_canvas.cc:797-826, mask_filter.cc:51-60, image_filter.cc:33-41,184-194).
-void CudaCanvas::HandleMaskBlur(const Path& path, const Paint& paint) {
+// SWCanvas::HandleFilter (sw_canvas.cc:797-826) with MaskFilterOnFilter (src/effect/mask_filter.cc:51-103),
+// BlurImageFilter::OnFilter and DropShadowImageFilter::OnFilter (src/effect/image_filter.cc:196-238): the
+// path is drawn into an offscreen surface, blurred into a second one, post-processed per pixel for the
+// blur styles / the shadow colour, and composited back as an image.
+void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
   Paint work_paint = paint;
   work_paint.SetMaskFilter(nullptr);
   work_paint.SetImageFilter(nullptr);
 
   auto mask_filter = paint.GetMaskFilter();
+  auto image_filter = As_IFB(paint.GetImageFilter().get());
+  if (!mask_filter) {
+    auto type = image_filter->GetType();
+    if (type != ImageFilterType::kBlur && type != ImageFilterType::kDropShadow) {
+      NoteUnsupported("image filter other than Blur / DropShadow");
+      return;
+    }
+  }
   Rect bounds = ComputeBoundsIfStroke(path.GetBounds(), paint);
-  float radius = mask_filter->GetBlurRadius();
-  Rect fb = Rect::MakeLTRB(std::floor(bounds.Left() - radius), std::floor(bounds.Top() - radius),
-                           std::ceil(bounds.Right() + radius), std::ceil(bounds.Bottom() + radius));
+  float radius_x = mask_filter ? mask_filter->GetBlurRadius() : image_filter->GetRadiusX();
+  float radius_y = mask_filter ? mask_filter->GetBlurRadius() : image_filter->GetRadiusY();
+  Rect fb = Rect::MakeLTRB(std::floor(bounds.Left() - radius_x), std::floor(bounds.Top() - radius_y),
+                           std::ceil(bounds.Right() + radius_x), std::ceil(bounds.Bottom() + radius_y));
   uint32_t w = static_cast<uint32_t>(fb.Width());
   uint32_t h = static_cast<uint32_t>(fb.Height());
   if (w == 0 || h == 0) return;  // the reference dereferences a null temp canvas here
@@ -510,16 +521,37 @@ void CudaCanvas::HandleMaskBlur(const Path& path, const Paint& paint) {
   b.kind = SKB_OP_BLUR;
   b.surface = blurred;
   b.aux = temp;
-  b.clip_bounds[0] = std::round(std::max(radius, radius));
+  b.clip_bounds[0] = std::round(std::max(radius_x, radius_y));
+  if (mask_filter) {
+    switch (mask_filter->GetBlurStyle()) {
+      case BlurStyle::kSolid: b.fill_type = 2; break;
+      case BlurStyle::kOuter: b.fill_type = 3; break;
+      case BlurStyle::kInner: b.fill_type = 4; break;
+      default: b.fill_type = 0; break;
+    }
+    builder_->AddOp(b);
+    DrawSurfaceImage(blurred, w, h, fb, work_paint, false);
+    return;
+  }
+  if (image_filter->GetType() == ImageFilterType::kBlur) {
+    builder_->AddOp(b);
+    DrawSurfaceImage(blurred, w, h, fb, work_paint, false);
+    return;
+  }
+  // drop shadow: the blurred alpha tinted with the (unpremultiplied) shadow colour, offset, then the shape
+  b.fill_type = 5;
+  b.paint = image_filter->GetColor();
   builder_->AddOp(b);
-
-  DrawSurfaceImage(blurred, w, h, fb, work_paint);
+  Rect offset_bounds = fb;
+  offset_bounds.Offset(image_filter->GetOffsetX(), image_filter->GetOffsetY());
+  DrawSurfaceImage(blurred, w, h, offset_bounds, work_paint, true);
+  DrawSurfaceImage(temp, w, h, fb, work_paint, false);
 }
 
 // Canvas::DrawImage(image, rect, paint) -> SWCanvas::OnDrawImageRect (sw_canvas.cc:641-677)
 // -> GenerateBrush image branch (sw_canvas.cc:755-787), for an image that lives on the device.
 void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih, const Rect& dst,
-                                  const Paint& paint) {
+                                  const Paint& paint, bool unpremul) {
   Rect src = Rect::MakeWH(iw, ih);
   if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
   Matrix local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
@@ -534,7 +566,7 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
 
   skb_dl_paint p{};
   p.type = SKB_PAINT_IMAGE;
-  p.tile_mode = 3;
+  p.tile_mode = 3u | (unpremul ? SKB_PAINT_IMAGE_UNPREMUL : 0u);
   StoreAffine(matrix, p.m);
   p.image_surface = src_surface;
   // work_paint.SetStyle(kFill) precedes GetAlphaF() in the reference (sw_canvas.cc:656,784)

@@ -16,13 +16,16 @@
 //            3 outer,4 inner), f32 blur_radius, u32 shader(0 none,1 linear,2 radial,3 sweep)
 //            [shader: f32 p[4], u32 tile_mode, u32 n_colors, u32 n_stops, u32 has_local,
 //             f32 local[6] (sx kx tx ky sy ty), f32 rgba[4*n_colors], f32 stops[n_stops]]
-//            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode)
+//            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode),
+//             u32 image_filter (0 none, 1 ImageFilters::Blur, 2 ImageFilters::DropShadow),
+//             f32 dx, f32 dy, f32 sigma_x, f32 sigma_y, u32 shadow colour (A<<24|R<<16|G<<8|B)
 #ifndef SKITY_B200_HOST_SCENE_PLAYER_HPP
 #define SKITY_B200_HOST_SCENE_PLAYER_HPP
 
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <skity/effect/image_filter.hpp>
 #include <skity/effect/mask_filter.hpp>
 #include <skity/effect/shader.hpp>
 #include <skity/geometry/matrix.hpp>
@@ -207,8 +210,14 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
   }
   if (extras) {
     uint32_t blend = r.U32();
-    if (!r.ok() || blend > static_cast<uint32_t>(skity::BlendMode::kLastMode)) return false;
+    uint32_t filter = r.U32();
+    float f[4];
+    r.Get(f, 16);
+    uint32_t shadow = r.U32();
+    if (!r.ok() || blend > static_cast<uint32_t>(skity::BlendMode::kLastMode) || filter > 2) return false;
     paint->SetBlendMode(static_cast<skity::BlendMode>(blend));
+    if (filter == 1) paint->SetImageFilter(skity::ImageFilters::Blur(f[2], f[3]));
+    if (filter == 2) paint->SetImageFilter(skity::ImageFilters::DropShadow(f[0], f[1], f[2], f[3], shadow, nullptr));
   }
   return true;
 }

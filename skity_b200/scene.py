@@ -75,15 +75,18 @@ class PathData:
 
 class Paint:
     def __init__(self, style=FILL, fill=(0, 0, 0, 1), stroke=(0, 0, 0, 1), stroke_width=1.0, miter=4.0,
-                 cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None, blend=None):
+                 cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None, blend=None,
+                 image_filter=None):
         self.style, self.fill, self.stroke = style, fill, stroke
         self.stroke_width, self.miter, self.cap, self.join = stroke_width, miter, cap, join
         self.blur_radius, self.blur_style = blur_radius, blur_style
         self.blend = blend    # skity::BlendMode value, None = default (kSrcOver)
+        # None | dict(type=1, sigma=(sx, sy)) ImageFilters::Blur | dict(type=2, offset=(dx, dy), sigma=(sx, sy), color=0xAARRGGBB)
+        self.image_filter = image_filter
         self.shader = shader  # dict(type=1|2|3, p=(..4), tile=, colors=[(r,g,b,a)..], stops=[..]|None, local=None|6)
 
     def encode(self):
-        extras = self.blend is not None
+        extras = self.blend is not None or self.image_filter is not None
         out = struct.pack("<I2f2I", self.style | (0x100 if extras else 0), self.stroke_width, self.miter, self.cap, self.join)
         out += np.asarray(self.fill, dtype=np.float32).tobytes()
         out += np.asarray(self.stroke, dtype=np.float32).tobytes()
@@ -91,7 +94,14 @@ class Paint:
             out += struct.pack("<If", self.blur_style, self.blur_radius)
         else:
             out += struct.pack("<If", 0, 0.0)
-        return out + self._encode_shader() + (struct.pack("<I", self.blend) if extras else b"")
+        out += self._encode_shader()
+        if extras:
+            f = self.image_filter or {}
+            dx, dy = f.get("offset", (0.0, 0.0))
+            sx, sy = f.get("sigma", (0.0, 0.0))
+            out += struct.pack("<2I4fI", 3 if self.blend is None else self.blend, f.get("type", 0), dx, dy, sx, sy,
+                               f.get("color", 0))
+        return out
 
     def _encode_shader(self):
         out = b""
@@ -401,4 +411,46 @@ def scene_blend_modes(seed=21, size=480):
             s.draw_path(p, Paint(shader=sh, blend=mode))
         else:
             s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), blend=mode))
+    return s
+
+
+def scene_filters(seed=33, size=512):
+    """Mask-filter blur styles (kNormal/kSolid/kOuter/kInner, src/effect/mask_filter.cc:51-103) and the image
+    filters the SW backend implements by blurring (ImageFilters::Blur / DropShadow,
+    src/effect/image_filter.cc:196-238), on fills and strokes, over a non-empty backdrop."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.95, 0.95, 0.9, 1.0)))
+    s.draw_rect(size * 0.3, 0, size * 0.6, size, Paint(fill=(0.2, 0.3, 0.5, 0.5)))
+    cell = size / 4
+    k = 0
+    for style in (1, 2, 3, 4):
+        for j in range(2):
+            cx, cy = (k % 4 + 0.5) * cell, (k // 4 + 0.5) * cell
+            p = _random_closed_path(rng, cx, cy, cell * 0.7, k)
+            col = tuple(rng.uniform(0, 1, 3)) + ((1.0,) if j == 0 else (0.6,))
+            if j == 0:
+                s.draw_path(p, Paint(fill=col, blur_radius=float(rng.uniform(2, 14)), blur_style=style))
+            else:
+                s.draw_path(p, Paint(style=STROKE, stroke=col, stroke_width=6.0, blur_radius=float(rng.uniform(2, 9)),
+                                     blur_style=style))
+            k += 1
+    for j in range(4):
+        cx, cy = (k % 4 + 0.5) * cell, (k // 4 + 0.5) * cell
+        p = _random_closed_path(rng, cx, cy, cell * 0.7, k)
+        col = tuple(rng.uniform(0, 1, 3)) + (float(rng.uniform(0.5, 1.0)),)
+        if j < 2:
+            f = dict(type=1, sigma=(float(rng.uniform(1, 6)), float(rng.uniform(1, 6))))
+        else:
+            f = dict(type=2, offset=(float(rng.uniform(-9, 9)), float(rng.uniform(3, 9))),
+                     sigma=(float(rng.uniform(1, 5)), float(rng.uniform(1, 5))), color=0xC0102060 if j == 2 else 0xFF203010)
+        s.draw_path(p, Paint(fill=col, image_filter=f))
+        k += 1
+    s.save()
+    s.translate(size * 0.5, size * 0.85)
+    s.rotate(-12)
+    s.scale(1.4, 0.8)
+    s.draw_path(_random_closed_path(rng, 0, 0, 90.0, 3),
+                Paint(fill=(0.8, 0.1, 0.2, 0.9), image_filter=dict(type=2, offset=(6.0, 5.0), sigma=(3.0, 3.0), color=0x80000000)))
+    s.restore()
     return s

@@ -82,6 +82,7 @@ def golden_scenes():
     s.draw_path(e, white)
     out["golden_canonical_edges_192x144"] = s
     out["blend_modes_480"] = scene.scene_blend_modes()
+    out["filters_512"] = scene.scene_filters()
     return out
 
 
