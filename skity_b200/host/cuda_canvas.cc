@@ -191,25 +191,45 @@ CudaCanvas::CudaCanvas(skb::DlBuilder* builder, uint32_t surface, uint32_t width
 }
 
 void CudaCanvas::NoteUnsupported(const char* what) {
+  if (parent_canvas_) {
+    parent_canvas_->NoteUnsupported(what);
+    return;
+  }
   if (unsupported_.empty()) unsupported_ = what;
 }
 
-// SWCanvas::CurrentTransform with a zero global offset (sw_canvas.hpp:179-182)
+// SWCanvas::CurrentTransform (sw_canvas.hpp:179-182)
 Matrix CudaCanvas::CurrentTransform() const {
-  return Matrix::Translate(-0.f, -0.f) * GetTotalMatrix();
+  return Matrix::Translate(-global_offset_.x, -global_offset_.y) * GetTotalMatrix();
 }
 
-// SWCanvas::GetScanClipBounds (sw_canvas.hpp:152-156)
+// SWCanvas::GetScanClipBounds (sw_canvas.hpp:157-161)
 Rect CudaCanvas::ScanClipBounds() const {
   Rect clip_bounds = GetGlobalClipBounds();
-  clip_bounds.Offset(-0.f, -0.f);
+  clip_bounds.Offset(-global_offset_.x, -global_offset_.y);
   return clip_bounds;
 }
 
-void CudaCanvas::OnSave() { state_stack_.emplace_back(state_stack_.back()); }
+// SWCanvas::OnSave (sw_canvas.cc:679-686)
+void CudaCanvas::OnSave() {
+  if (PeekLayerStack()) {
+    PeekLayerStack()->canvas->Save();
+    return;
+  }
+  state_stack_.emplace_back(state_stack_.back());
+}
 
+// SWCanvas::OnRestore (sw_canvas.cc:688-708)
 void CudaCanvas::OnRestore() {
   if (state_stack_.size() == 1) return;
+  if (PeekLayerStack()) {
+    CudaCanvas* sub_canvas = PeekLayerStack()->canvas.get();
+    if (sub_canvas->state_stack_.size() > 1) {
+      sub_canvas->Restore();
+      return;
+    }
+  }
+  if (state_stack_.back().has_layer) OnLayerRestore();
   state_stack_.pop_back();
 }
 
@@ -223,6 +243,10 @@ void CudaCanvas::OnFlush() {}
 // SWCanvas::OnClipRect (sw_canvas.cc:297-313): an intersecting rect under a
 // scale/translate CTM only tightens the integer scan rectangle.
 void CudaCanvas::OnClipRect(const Rect& rect, ClipOp op) {
+  if (PeekLayerStack()) {
+    PeekLayerStack()->canvas->ClipRect(rect, op);
+    return;
+  }
   if (op == ClipOp::kDifference || !CurrentTransform().OnlyScaleAndTranslate()) {
     Canvas::OnClipRect(rect, op);
     return;
@@ -231,6 +255,11 @@ void CudaCanvas::OnClipRect(const Rect& rect, ClipOp op) {
 
 // SWCanvas::OnClipPath (sw_canvas.cc:315-336)
 void CudaCanvas::OnClipPath(const Path& path, ClipOp op) {
+  if (PeekLayerStack()) {
+    PeekLayerStack()->canvas->ClipPath(path, op);
+    return;
+  }
+  if (surface_ == kNoSurface) return;
   std::vector<skb_dl_seg> segs;
   LowerPathToSegs(path, &segs);
   skb_dl_op o{};
@@ -258,6 +287,7 @@ void CudaCanvas::OnClipPath(const Path& path, ClipOp op) {
 }
 
 void CudaCanvas::EmitFill(const Path& path, const Matrix& m, uint32_t paint_index) {
+  if (surface_ == kNoSurface) return;
   if (m.HasPersp()) {
     NoteUnsupported("perspective CTM");
     return;
@@ -418,6 +448,10 @@ void CudaCanvas::FillPath(const Path& path, const Paint& paint, bool stroke) {
 
 // SWCanvas::OnDrawPath (sw_canvas.cc:357-411)
 void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
+  if (PeekLayerStack()) {
+    PeekLayerStack()->canvas->DrawPath(path, paint);
+    return;
+  }
   if (paint.GetMaskFilter() || paint.GetImageFilter()) {
     HandleFilter(path, paint);
     return;
@@ -460,6 +494,11 @@ void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
 
 // SWCanvas::OnDrawPaint (sw_canvas.cc:413-439): the whole bitmap, identity transform, no scan clip.
 void CudaCanvas::OnDrawPaint(const Paint& paint) {
+  if (PeekLayerStack()) {
+    PeekLayerStack()->canvas->DrawPaint(paint);
+    return;
+  }
+  if (surface_ == kNoSurface) return;
   Rect bounds = Rect::MakeWH(Width(), Height());
   Path path;
   path.AddRect(bounds);
@@ -554,15 +593,43 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
                                   const Paint& paint, bool unpremul) {
   Rect src = Rect::MakeWH(iw, ih);
   if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
-  Matrix local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
-                        Matrix::Scale(dst.Width() / src.Width(), dst.Height() / src.Height()) *
-                        Matrix::Translate(-src.Left(), -src.Top());
+  if (PeekLayerStack()) {  // OnDrawImageRect ends in OnDrawPath, which an open layer takes over (sw_canvas.cc:360-363)
+    PeekLayerStack()->canvas->DrawSurfaceImage(src_surface, iw, ih, dst, paint, unpremul);
+    return;
+  }
+  if (paint.GetMaskFilter() || paint.GetImageFilter()) {
+    NoteUnsupported("mask / image filter on an image or layer composite");
+    return;
+  }
+  Path path;
+  path.AddRect(dst);
+  Matrix local_matrix;
+  if (IsDrawingLayer()) {
+    local_matrix = Matrix::Scale(1.f / src.Width(), 1.f / src.Height()) * Matrix::Translate(-src.Left(), -src.Top());
+  } else {
+    local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
+                   Matrix::Scale(dst.Width() / src.Width(), dst.Height() / src.Height()) *
+                   Matrix::Translate(-src.Left(), -src.Top());
+  }
   Matrix inverse;
   local_matrix.Invert(&inverse);
   Matrix matrix = Matrix::Scale(1.f / iw, 1.f / ih) * inverse;
-  Matrix layer_to_local;
-  CurrentTransform().Invert(&layer_to_local);
-  matrix = matrix * layer_to_local;
+  if (IsDrawingLayer()) {
+    // GenerateBrush maps the raster bounds of the drawn rectangle onto the layer (sw_canvas.cc:772-776);
+    // the bounds are SWRaster::RastePath's (sw_raster.cc:737-745)
+    Paint plain;
+    Stroke stroke(plain);
+    Path quad;
+    stroke.QuadPath(path, &quad);
+    Rect sb = quad.CopyWithMatrix(Matrix(CurrentTransform())).GetBounds();
+    Rect bounds = Rect::MakeLTRB(std::floor(sb.Left()), std::floor(sb.Top()), std::ceil(sb.Right()), std::ceil(sb.Bottom()));
+    matrix = matrix * Matrix::Scale(1.0f / bounds.Width(), 1.0f / bounds.Height()) *
+             Matrix::Translate(-bounds.Left(), -bounds.Top());
+  } else {
+    Matrix layer_to_local;
+    CurrentTransform().Invert(&layer_to_local);
+    matrix = matrix * layer_to_local;
+  }
 
   skb_dl_paint p{};
   p.type = SKB_PAINT_IMAGE;
@@ -578,17 +645,62 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
   }
   if (paint.GetColorFilter()) NoteUnsupported("color filter");
   uint32_t paint_index = builder_->AddPaint(p);
-
-  Path path;
-  path.AddRect(dst);
   EmitFill(path, CurrentTransform(), paint_index);
 }
 
-void CudaCanvas::OnSaveLayer(const Rect&, const Paint&) {
-  // SWCanvas::OnSaveLayer renders into an offscreen bitmap (sw_canvas.cc:441-484); not on the
-  // hot path of this round.  Keep Save/Restore balanced.
-  NoteUnsupported("SaveLayer");
+// SWCanvas::OnSaveLayer + GenerateLayer + LayerState::Init (sw_canvas.cc:267-280,441-484,880-889):
+// an offscreen surface as large as the layer's device-space bounds, drawn into by a sub-canvas that
+// shares this canvas's CTM stack and global clip, shifted by the layer's device-space origin.
+void CudaCanvas::OnSaveLayer(const Rect& bounds, const Paint& paint) {
   state_stack_.emplace_back(state_stack_.back());
+  if (PeekLayerStack()) PeekLayerStack()->canvas->OnSave();
+  state_stack_.back().has_layer = true;
+
+  Paint work_paint{paint};
+  work_paint.SetStyle(Paint::kFill_Style);
+  auto layer_bounds = work_paint.ComputeFastBounds(bounds);
+
+  CudaCanvas* target_canvas = this;
+  if (PeekLayerStack()) target_canvas = PeekLayerStack()->canvas.get();
+
+  auto canvas_matrix = target_canvas->CurrentTransform();
+  Rect device_bounds = Rect::MakeWH(target_canvas->Width(), target_canvas->Height());
+  Rect scan_clip_bounds = target_canvas->ScanClipBounds();
+  if (!device_bounds.Intersect(scan_clip_bounds)) device_bounds.SetEmpty();
+
+  Matrix device_to_local;
+  if (canvas_matrix.Invert(&device_to_local)) {
+    Rect local_clip_bounds;
+    device_to_local.MapRect(&local_clip_bounds, device_bounds);
+    if (!layer_bounds.Intersect(local_clip_bounds)) layer_bounds.SetEmpty();
+  }
+  Rect rel_bounds{};
+  canvas_matrix.MapRect(&rel_bounds, layer_bounds);
+
+  auto layer = std::make_unique<LayerState>();
+  layer->rel_bounds = rel_bounds;
+  layer->log_bounds = layer_bounds;
+  layer->width = static_cast<uint32_t>(std::ceil(rel_bounds.Width()));
+  layer->height = static_cast<uint32_t>(std::ceil(rel_bounds.Height()));
+  layer->surface = (layer->width && layer->height) ? builder_->AddSurface(layer->width, layer->height) : kNoSurface;
+  layer->canvas = std::make_unique<CudaCanvas>(builder_, layer->surface, layer->width, layer->height);
+  layer->canvas->SetTracingCanvasState(false);
+  layer->canvas->parent_canvas_ = this;
+  layer->canvas->global_offset_ = target_canvas->global_offset_ + Vec2{rel_bounds.Left(), rel_bounds.Top()};
+  layer->paint = paint;
+  layer_stack_.emplace_back(std::move(layer));
+}
+
+// SWCanvas::OnLayerRestore (sw_canvas.cc:891-902): the layer is drawn back as an image with the layer paint
+void CudaCanvas::OnLayerRestore() {
+  auto layer = std::move(layer_stack_.back());
+  layer_stack_.pop_back();
+  if (PeekLayerStack()) PeekLayerStack()->canvas->OnRestore();
+  SetDrawingLayer(layer->paint.GetMaskFilter() == nullptr);
+  if (layer->surface != kNoSurface) {
+    DrawSurfaceImage(layer->surface, layer->width, layer->height, layer->log_bounds, layer->paint, false);
+  }
+  SetDrawingLayer(false);
 }
 
 void CudaCanvas::OnDrawBlob(const TextBlob*, float, float, Paint const&) { NoteUnsupported("text"); }

@@ -30,6 +30,15 @@ class CudaCanvas : public Canvas {
   // draws are dropped, never approximated on the CPU.
   const std::string& Unsupported() const { return unsupported_; }
 
+  // The reference's sub-canvas plumbing (SWCanvas, sw_canvas.hpp:106-182): a layer canvas shares the
+  // root's CTM stack and global clip bounds, and sees them through its own device-space offset.
+  CanvasState* GetCanvasState() const override {
+    return parent_canvas_ ? parent_canvas_->GetCanvasState() : Canvas::GetCanvasState();
+  }
+  const Rect& GetGlobalClipBounds() const override {
+    return parent_canvas_ ? parent_canvas_->GetGlobalClipBounds() : Canvas::GetGlobalClipBounds();
+  }
+
  protected:
   void OnClipRect(const Rect& rect, ClipOp op) override;
   void OnClipPath(const Path& path, ClipOp op) override;
@@ -51,7 +60,17 @@ class CudaCanvas : public Canvas {
  private:
   struct State {
     uint32_t clip_id = 0;  // 0 = no clip spans (SWCanvas::State::HasClip() == false)
+    bool has_layer = false;
   };
+  // SWCanvas::LayerState (sw_canvas.hpp:48-63): an offscreen surface + the canvas that draws into it
+  struct LayerState {
+    Rect rel_bounds = {};
+    Rect log_bounds = {};
+    uint32_t surface = 0, width = 0, height = 0;
+    std::unique_ptr<CudaCanvas> canvas;
+    Paint paint = {};
+  };
+  static constexpr uint32_t kNoSurface = 0xFFFFFFFFu;  // a zero-sized layer: draws into it vanish
 
   Matrix CurrentTransform() const;
   Rect ScanClipBounds() const;
@@ -61,6 +80,10 @@ class CudaCanvas : public Canvas {
   void HandleFilter(const Path& path, const Paint& paint);
   void DrawSurfaceImage(uint32_t src_surface, uint32_t w, uint32_t h, const Rect& dst,
                         const Paint& paint, bool unpremul);
+  LayerState* PeekLayerStack() { return layer_stack_.empty() ? nullptr : layer_stack_.back().get(); }
+  void OnLayerRestore();
+  bool IsDrawingLayer() const { return parent_canvas_ ? parent_canvas_->drawing_layer_ : drawing_layer_; }
+  void SetDrawingLayer(bool v) { (parent_canvas_ ? parent_canvas_->drawing_layer_ : drawing_layer_) = v; }
   void NoteUnsupported(const char* what);
 
   skb::DlBuilder* builder_;
@@ -68,6 +91,10 @@ class CudaCanvas : public Canvas {
   uint32_t width_;
   uint32_t height_;
   std::vector<State> state_stack_;
+  std::vector<std::unique_ptr<LayerState>> layer_stack_;
+  CudaCanvas* parent_canvas_ = nullptr;
+  Vec2 global_offset_ = Vec2{0.f, 0.f};
+  bool drawing_layer_ = false;
   std::string unsupported_;
 };
 

@@ -47,6 +47,7 @@ enum Op : uint32_t {
   kClipPath = 8,
   kDrawPath = 9,
   kDrawRect = 10,
+  kSaveLayer = 11,  // f32 ltrb[4], paint -> Canvas::SaveLayer(bounds, paint); closed by kRestore
 };
 
 constexpr uint32_t kMagic = 0x43534B53u;  // "SKSC"
@@ -282,6 +283,13 @@ inline int Play(const uint8_t* data, size_t n, skity::Canvas* canvas) {
         skity::Paint paint;
         if (!ReadPaint(r, &paint)) return -3;
         canvas->DrawRect(skity::Rect::MakeLTRB(q[0], q[1], q[2], q[3]), paint);
+      } break;
+      case kSaveLayer: {
+        float q[4];
+        r.Get(q, 16);
+        skity::Paint paint;
+        if (!ReadPaint(r, &paint)) return -3;
+        canvas->SaveLayer(skity::Rect::MakeLTRB(q[0], q[1], q[2], q[3]), paint);
       } break;
       default:
         return -4;

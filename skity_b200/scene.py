@@ -23,7 +23,7 @@ CLAMP, REPEAT, MIRROR, DECAL = 0, 1, 2, 3
 WINDING, EVEN_ODD = 0, 1
 
 OP_SAVE, OP_RESTORE, OP_TRANSLATE, OP_SCALE, OP_ROTATE, OP_CONCAT = 1, 2, 3, 4, 5, 6
-OP_CLIP_RECT, OP_CLIP_PATH, OP_DRAW_PATH, OP_DRAW_RECT = 7, 8, 9, 10
+OP_CLIP_RECT, OP_CLIP_PATH, OP_DRAW_PATH, OP_DRAW_RECT, OP_SAVE_LAYER = 7, 8, 9, 10, 11
 
 
 class PathData:
@@ -135,6 +135,10 @@ class Scene:
 
     def restore(self):
         self._op(OP_RESTORE)
+
+    def save_layer(self, l, t, r, b, paint):
+        """Canvas::SaveLayer(bounds, paint); the matching restore() composites the layer with `paint`."""
+        self._op(OP_SAVE_LAYER, struct.pack("<4f", l, t, r, b) + paint.encode())
 
     def translate(self, dx, dy):
         self._op(OP_TRANSLATE, struct.pack("<2f", dx, dy))
@@ -454,3 +458,57 @@ def scene_filters(seed=33, size=512):
                 Paint(fill=(0.8, 0.1, 0.2, 0.9), image_filter=dict(type=2, offset=(6.0, 5.0), sigma=(3.0, 3.0), color=0x80000000)))
     s.restore()
     return s
+
+
+def scene_layers(seed=44, size=512):
+    """SaveLayer (SWCanvas::OnSaveLayer / OnLayerRestore, src/render/sw/sw_canvas.cc:441-484,891-902):
+    translucent and blend-mode layers, a layer under a rotated CTM (fractional device-space origin), Save /
+    clips inside a layer, a blurred draw inside a layer, and a layer nested in a layer."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.92, 0.9, 0.85, 1.0)))
+    for i in range(6):
+        p = _random_closed_path(rng, rng.uniform(0, size), rng.uniform(0, size), 220.0, i)
+        s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (rng.uniform(0.4, 1.0),)))
+    # 1. translucent group
+    s.save_layer(40.5, 30.25, 260.75, 240.5, Paint(fill=(0, 0, 0, 0.55)))
+    s.draw_rect(60, 50, 200, 180, Paint(fill=(0.9, 0.1, 0.1, 1.0)))
+    s.draw_path(_random_closed_path(rng, 170, 150, 160.0, 1), Paint(fill=(0.1, 0.7, 0.2, 0.8)))
+    s.restore()
+    # 2. layer under a rotated, scaled CTM, with a Save + rect clip + path clip inside
+    s.save()
+    s.translate(330, 140)
+    s.rotate(17)
+    s.scale(1.2, 0.9)
+    s.save_layer(-110, -90, 120, 100, Paint(fill=(0, 0, 0, 0.8), blend=14))
+    s.draw_rect(-100, -80, 100, 90, Paint(fill=(0.2, 0.3, 0.9, 0.9)))
+    s.save()
+    s.clip_rect(-60, -50, 70, 60)
+    s.clip_path(star_path_small(70.0))
+    s.draw_rect(-100, -80, 100, 90, Paint(fill=(1.0, 0.9, 0.1, 1.0)))
+    s.restore()
+    s.draw_path(_random_closed_path(rng, 30, 20, 120.0, 2), Paint(style=STROKE, stroke=(0, 0, 0, 0.7), stroke_width=5.0))
+    s.restore()
+    s.restore()
+    # 3. nested layers with a blurred draw inside
+    s.save_layer(60, 280, 470, 500, Paint(fill=(0, 0, 0, 0.9)))
+    s.draw_rect(80, 300, 300, 480, Paint(fill=(0.1, 0.6, 0.7, 1.0)))
+    s.draw_path(_random_closed_path(rng, 330, 390, 150.0, 3), Paint(fill=(0.8, 0.2, 0.6, 1.0), blur_radius=6.0, blur_style=1))
+    s.save_layer(200.5, 320.5, 450, 470, Paint(fill=(0, 0, 0, 0.5), blend=12))
+    s.draw_path(_random_closed_path(rng, 320, 400, 170.0, 4), Paint(fill=(0.9, 0.8, 0.1, 1.0)))
+    s.restore()
+    s.restore()
+    return s
+
+
+def star_path_small(r):
+    """Five-pointed star centred on the origin (winding fill)."""
+    p = PathData(WINDING)
+    for k in range(5):
+        a = -np.pi / 2 + k * 4 * np.pi / 5
+        x, y = float(r * np.cos(a)), float(r * np.sin(a))
+        if k == 0:
+            p.move_to(x, y)
+        else:
+            p.line_to(x, y)
+    return p.close()

@@ -83,6 +83,7 @@ def golden_scenes():
     out["golden_canonical_edges_192x144"] = s
     out["blend_modes_480"] = scene.scene_blend_modes()
     out["filters_512"] = scene.scene_filters()
+    out["layers_512"] = scene.scene_layers()
     return out
 
 
