@@ -120,7 +120,12 @@ enum skb_dl_paint_type {
   SKB_PAINT_LINEAR = 1,
   SKB_PAINT_RADIAL = 2,
   SKB_PAINT_SWEEP = 3,
-  SKB_PAINT_IMAGE = 4 /* PixmapBrush, nearest, decal/decal (the blur composite) */
+  SKB_PAINT_IMAGE = 4, /* PixmapBrush, nearest, decal/decal (the blur composite) */
+  SKB_PAINT_CONICAL = 5 /* two-point conical gradient: m = device_to_local; the constants
+                           ConicalGradientColorBrush::OnPreBrush derives (sw_span_brush.cc:405-444) follow the
+                           stops in the float pool, 16 floats: kind (0 transparent, 1 concentric, 2 equal radii,
+                           3 general, 5 general with the circles swapped), c0.x, c0.y, scale, scale_sign, bias,
+                           r0/|c1-c0|, transform sx kx tx ky sy ty, r1, r1^2, f */
 };
 
 /* IMAGE paints: the sampled surface holds unpremultiplied pixels (PixmapBrush premultiplies after sampling,

@@ -1154,6 +1154,43 @@ static uint32_t paint_color(const skb_dl_paint* p, const float* pool, const surf
       lerp_color(p, pool, t, c);
       return color_to_pm(color4f_to_color(c));
     }
+    case SKB_PAINT_CONICAL: { /* ConicalGradientColorBrush::CalculateConical — sw_span_brush.cc:450-513 */
+      const float* e = pool + p->stop_off + 5 * (size_t)p->n_colors;
+      int kind = (int)e[0];
+      float t;
+      if (kind == 1) {
+        float qx = (u - e[1]) * e[3], qy = (v - e[2]) * e[3];
+        t = sqrtf(qx * qx + qy * qy) * e[4] - e[5];
+      } else if (kind == 2) {
+        float r = e[6], r_2 = r * r;
+        float x2 = u * e[7] + v * e[8] + e[9], y2 = u * e[10] + v * e[11] + e[12];
+        t = r_2 - y2 * y2;
+        if (t < 0.0) return 0;
+        t = x2 + sqrtf(t);
+      } else if (kind == 3 || kind == 5) {
+        float x2 = u * e[7] + v * e[8] + e[9], y2 = u * e[10] + v * e[11] + e[12];
+        float r1 = e[13], r1sq = e[14], f = e[15], xt = -1.f;
+        if (fabsf(r1 - 1.f) < (1.0f / 4096)) {
+          xt = (x2 * x2 + y2 * y2) / 2;
+        } else if (r1 > 1.f) {
+          float m = r1sq - 1.f, delta = m * y2 * y2 + r1sq * x2 * x2;
+          xt = (sqrtf(delta) - x2) / m;
+        } else {
+          float m = r1sq - 1.f, delta = m * y2 * y2 + r1sq * x2 * x2;
+          if (delta > 0) {
+            float xt1 = (sqrtf(delta) - x2) / m, xt2 = (-sqrtf(delta) - x2) / m;
+            xt = 1.f - f < 0 ? (xt2 < xt1 ? xt2 : xt1) : (xt1 < xt2 ? xt2 : xt1);
+          }
+        }
+        if (xt < 0) return 0;
+        t = f + (1.f - f) * xt;
+        if (kind == 5) t = (float)(1.0 - t);
+      } else {
+        return 0;
+      }
+      lerp_color(p, pool, t, c);
+      return color_to_pm(color4f_to_color(c));
+    }
     case SKB_PAINT_IMAGE: {
       const surface* s = &surfs[p->image_surface];
       if (u < 0.0 || u >= 1.0 || v < 0.0 || v >= 1.0) return 0; /* decal/decal */

@@ -1332,9 +1332,11 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
       }
       if (o.kind == SKB_OP_FILL) {
         const skb_dl_paint& pt = paints[o.paint];
-        if (pt.type > SKB_PAINT_IMAGE || (pt.type == SKB_PAINT_IMAGE && pt.image_surface >= h.n_surfaces) ||
-            (pt.type >= SKB_PAINT_LINEAR && pt.type <= SKB_PAINT_SWEEP &&
-             ((uint64_t)pt.stop_off + 5ull * pt.n_colors > h.n_stop_floats || pt.n_colors < 1))) {
+        const bool gradient = (pt.type >= SKB_PAINT_LINEAR && pt.type <= SKB_PAINT_SWEEP) || pt.type == SKB_PAINT_CONICAL;
+        if (pt.type > SKB_PAINT_CONICAL || (pt.type == SKB_PAINT_IMAGE && pt.image_surface >= h.n_surfaces) ||
+            (gradient && ((uint64_t)pt.stop_off + 5ull * pt.n_colors + (pt.type == SKB_PAINT_CONICAL ? 16u : 0u) >
+                              h.n_stop_floats ||
+                          pt.n_colors < 1))) {
           set_error("display list: bad paint");
           return SKB_ERROR_BAD_DISPLAY_LIST;
         }

@@ -921,6 +921,49 @@ SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const Sur
       float t = (float)(((double)(angle * k1Over2Pi) + 0.5 + (double)p.bias) * (double)p.scale);
       return gradient_color(p, pool, t);
     }
+    case SKB_PAINT_CONICAL: {  // ConicalGradientColorBrush::CalculateConical (sw_span_brush.cc:450-513)
+      const float* e = pool + p.stop_off + 5 * (size_t)p.n_colors;
+      const int kind = (int)e[0];
+      float t;
+      if (kind == 1) {
+        float qx = (u - e[1]) * e[3], qy = (v - e[2]) * e[3];
+        t = sqrtf(qx * qx + qy * qy) * e[4] - e[5];
+      } else if (kind == 2) {
+        float r = e[6];
+        float r_2 = r * r;
+        float x2 = u * e[7] + v * e[8] + e[9];
+        float y2 = u * e[10] + v * e[11] + e[12];
+        t = r_2 - y2 * y2;
+        if (t < 0.0f) return 0;
+        t = x2 + sqrtf(t);
+      } else if (kind == 3 || kind == 5) {
+        float x2 = u * e[7] + v * e[8] + e[9];
+        float y2 = u * e[10] + v * e[11] + e[12];
+        const float r1 = e[13], r1sq = e[14], f = e[15];
+        float xt = -1.f;
+        if (fabsf(r1 - 1.f) < (1.0f / 4096)) {
+          xt = (x2 * x2 + y2 * y2) / 2;
+        } else if (r1 > 1.f) {
+          float m = r1sq - 1.f;
+          float delta = m * y2 * y2 + r1sq * x2 * x2;
+          xt = (sqrtf(delta) - x2) / m;
+        } else {
+          float m = r1sq - 1.f;
+          float delta = m * y2 * y2 + r1sq * x2 * x2;
+          if (delta > 0) {
+            float xt1 = (sqrtf(delta) - x2) / m;
+            float xt2 = (-sqrtf(delta) - x2) / m;
+            xt = 1.f - f < 0 ? (xt2 < xt1 ? xt2 : xt1) : (xt1 < xt2 ? xt2 : xt1);  // std::min / std::max
+          }
+        }
+        if (xt < 0) return 0;
+        t = f + (1.f - f) * xt;
+        if (kind == 5) t = 1.0f - t;
+      } else {
+        return 0;  // negative radius, or concentric circles of equal radius: transparent
+      }
+      return gradient_color(p, pool, t);
+    }
     case SKB_PAINT_IMAGE: {
       const SurfaceView& s = img;
       if (u < 0.0f || u >= 1.0f || v < 0.0f || v >= 1.0f) return 0;

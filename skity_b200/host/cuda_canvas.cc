@@ -347,6 +347,14 @@ Matrix PointsToUnit(const Shader::GradientInfo& info, Shader::GradientType type)
   return Matrix{};
 }
 
+// PointsToUnit(p0, p1) (sw_span_brush.cc:197-216): the unit-segment transform the conical brush uses
+Matrix PointsToUnit2(const Point& p0, const Point& p1) {
+  Shader::GradientInfo two{};
+  two.point[0] = p0;
+  two.point[1] = p1;
+  return PointsToUnit(two, Shader::GradientType::kLinear);
+}
+
 void StoreAffine(const Matrix& m, float out[6]) {
   out[0] = m.GetScaleX();
   out[1] = m.GetSkewX();
@@ -400,16 +408,18 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
   if (shader) {
     Shader::GradientInfo info{};
     Shader::GradientType type = shader->AsGradient(&info);
-    if (type == Shader::kLinear || type == Shader::kRadial || type == Shader::kSweep) {
+    if (type == Shader::kLinear || type == Shader::kRadial || type == Shader::kSweep || type == Shader::kConical) {
       Matrix device_to_local;
       shader->GetLocalMatrix().Invert(&device_to_local);
       Matrix layer_to_local;
       CurrentTransform().Invert(&layer_to_local);
       device_to_local = device_to_local * layer_to_local;
-      Matrix ptu = PointsToUnit(info, type) * device_to_local;
+      // the conical brush keeps device_to_local apart from its unit transforms (sw_span_brush.cc:393-394)
+      Matrix ptu = type == Shader::kConical ? device_to_local : PointsToUnit(info, type) * device_to_local;
       StoreAffine(ptu, p.m);
       p.type = type == Shader::kLinear ? SKB_PAINT_LINEAR
-                                       : (type == Shader::kRadial ? SKB_PAINT_RADIAL : SKB_PAINT_SWEEP);
+                                       : (type == Shader::kRadial ? SKB_PAINT_RADIAL
+                                                                  : (type == Shader::kSweep ? SKB_PAINT_SWEEP : SKB_PAINT_CONICAL));
       p.tile_mode = static_cast<uint32_t>(info.tile_mode);
       p.n_colors = static_cast<uint32_t>(info.colors.size());
       p.has_stops = info.color_offsets.empty() ? 0u : 1u;
@@ -425,13 +435,51 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
       p.stop_off = builder_->AddStops(cols.data(), offs.data(), p.n_colors);
       p.bias = info.radius[0];
       p.scale = info.radius[1];
+      if (type == Shader::kConical) {
+        // ConicalGradientColorBrush::OnPreBrush (sw_span_brush.cc:405-444), evaluated once here
+        float e[16] = {};
+        Point c0 = info.point[0], c1 = info.point[1];
+        float r0 = info.radius[0], r1 = info.radius[1];
+        float delta_center = (c1 - c0).Length();
+        float delta_radius = std::abs(r1 - r0);
+        if (!(r0 < 0 || r1 < 0)) {
+          bool radial = delta_center < kNearlyZero;
+          bool strip = delta_radius < kNearlyZero;
+          if (radial) {
+            e[0] = 4.f;  // concentric with equal radii: transparent
+            if (!strip) {
+              e[0] = 1.f;
+              e[1] = c0.x;
+              e[2] = c0.y;
+              e[3] = 1.0 / delta_radius;
+              e[4] = delta_radius < 0 ? -1.f : 1.f;
+              e[5] = r0 / delta_radius;
+            }
+          } else if (strip) {
+            e[0] = 2.f;
+            e[6] = r0 / delta_center;
+            StoreAffine(PointsToUnit2(c0, c1), e + 7);
+          } else {
+            bool swap_01 = r1 < kNearlyZero;
+            if (swap_01) {
+              std::swap(c0, c1);
+              std::swap(r0, r1);
+            }
+            float f = r0 / (r0 - r1);
+            Point cf = c0 * (1.f - f) + c1 * f;
+            r1 = r1 / (c1 - cf).Length();
+            e[0] = swap_01 ? 5.f : 3.f;
+            StoreAffine(PointsToUnit2(cf, c1), e + 7);
+            e[13] = r1;
+            e[14] = r1 * r1;
+            e[15] = f;
+          }
+        }
+        builder_->AddFloats(e, 16);
+      }
       return builder_->AddPaint(p);
     }
-    if (type == Shader::kConical) {
-      NoteUnsupported("two-point conical gradient");
-    } else if (shader->AsImage()) {
-      NoteUnsupported("image shader");
-    }
+    if (shader->AsImage()) NoteUnsupported("image shader");
   }
   Color4f color = stroke ? paint.GetStrokeColor() : paint.GetFillColor();
   p.type = SKB_PAINT_SOLID;

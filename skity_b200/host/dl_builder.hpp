@@ -67,6 +67,9 @@ class DlBuilder {
     return off;
   }
 
+  // appends to the float pool (directly behind the block AddStops just returned)
+  void AddFloats(const float* v, uint32_t n) { stops_.insert(stops_.end(), v, v + n); }
+
   void AddOp(const skb_dl_op& op) { ops_.push_back(op); }
 
   size_t OpCount() const { return ops_.size(); }

@@ -13,7 +13,8 @@
 //            verbs use skity::Path::Verb numbering (include/skity/graphic/path.hpp:45-60)
 //   paint  : u32 style, f32 stroke_width, f32 miter, u32 cap, u32 join,
 //            f32 fill_rgba[4], f32 stroke_rgba[4], u32 blur_style(0 none,1 normal,2 solid,
-//            3 outer,4 inner), f32 blur_radius, u32 shader(0 none,1 linear,2 radial,3 sweep)
+//            3 outer,4 inner), f32 blur_radius, u32 shader(0 none,1 linear,2 radial,3 sweep,
+//            4 two-point conical: f32 r0, r1 follow the stops)
 //            [shader: f32 p[4], u32 tile_mode, u32 n_colors, u32 n_stops, u32 has_local,
 //             f32 local[6] (sx kx tx ky sy ty), f32 rgba[4*n_colors], f32 stops[n_stops]]
 //            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode),
@@ -203,6 +204,12 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
     } else if (shader == 3) {
       sh = skity::Shader::MakeSweep(p[0], p[1], p[2], p[3], colors.data(), pos,
                                     static_cast<int>(nc), tm);
+    } else if (shader == 4) {  // two-point conical: p = start.xy, end.xy; radii follow the stops
+      float rr[2];
+      r.Get(rr, 8);
+      if (!r.ok()) return false;
+      sh = skity::Shader::MakeTwoPointConical(skity::Point{p[0], p[1], 0.f, 1.f}, rr[0], skity::Point{p[2], p[3], 0.f, 1.f},
+                                              rr[1], colors.data(), pos, static_cast<int>(nc), tm);
     } else {
       return false;
     }

@@ -117,6 +117,8 @@ class Paint:
         out += struct.pack("<4I", sh.get("tile", CLAMP), len(colors), len(stops), 1 if local is not None else 0)
         out += np.asarray(local if local is not None else [1, 0, 0, 0, 1, 0], dtype=np.float32).tobytes()
         out += colors.tobytes() + stops.tobytes()
+        if sh["type"] == 4:
+            out += struct.pack("<2f", *sh["radii"])
         return out
 
 
@@ -512,3 +514,44 @@ def star_path_small(r):
         else:
             p.line_to(x, y)
     return p.close()
+
+
+def scene_conical(seed=55, size=512):
+    """Two-point conical gradients (ConicalGradientColorBrush, src/render/sw/sw_span_brush.cc:385-530): the
+    general case with r1 above, below and at the focal unit radius, swapped circles (r1 ~ 0), concentric
+    circles, equal radii, a negative radius; all tile modes, with stops and a local matrix."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(1, 1, 1, 1)))
+    cell = size / 4
+    cases = [
+        ((0.3, 0.5), 0.1, (0.7, 0.5), 0.45),   # general, growing
+        ((0.3, 0.5), 0.45, (0.7, 0.5), 0.1),   # general, shrinking
+        ((0.3, 0.3), 0.2, (0.6, 0.6), 0.0),    # end radius 0: circles swapped
+        ((0.5, 0.5), 0.05, (0.5, 0.5), 0.5),   # concentric
+        ((0.2, 0.5), 0.25, (0.8, 0.5), 0.25),  # equal radii: strip
+        ((0.5, 0.5), 0.3, (0.5, 0.5), 0.3),    # concentric and equal: transparent
+        ((0.3, 0.5), -0.1, (0.7, 0.5), 0.4),   # negative radius: transparent
+        ((0.2, 0.2), 0.0, (0.5, 0.5), 0.6),    # start radius 0 (focal on centre)
+        ((0.4, 0.5), 0.2, (0.6, 0.5), 0.2 + 0.2),  # r1 relative to focal distance near 1
+        ((0.45, 0.5), 0.3, (0.6, 0.5), 0.35),
+        ((0.1, 0.9), 0.05, (0.9, 0.1), 0.3),
+        ((0.5, 0.2), 0.15, (0.5, 0.8), 0.5),
+    ]
+    for k, (a, ra, b, rb) in enumerate(cases):
+        x0, y0 = (k % 4) * cell, (k // 4) * cell
+        colors = [tuple(rng.uniform(0, 1, 3)) + (float(rng.uniform(0.5, 1)),) for _ in range(3 + k % 3)]
+        stops = sorted(float(v) for v in rng.uniform(0, 1, len(colors))) if k % 2 else None
+        if stops:
+            stops[0], stops[-1] = 0.0, 1.0
+        sh = dict(type=4, p=(x0 + a[0] * cell, y0 + a[1] * cell, x0 + b[0] * cell, y0 + b[1] * cell),
+                  radii=(ra * cell, rb * cell), tile=k % 4, colors=colors, stops=stops,
+                  local=(1.0, 0.1, 3.0, -0.05, 0.95, -2.0) if k % 5 == 4 else None)
+        s.draw_rect(x0 + 4, y0 + 4, x0 + cell - 4, y0 + cell - 4, Paint(shader=sh))
+    s.save()
+    s.translate(size * 0.5, size * 0.88)
+    s.rotate(20)
+    sh = dict(type=4, p=(-60, 0, 40, 10), radii=(10.0, 70.0), tile=MIRROR, colors=[(1, 0, 0, 1), (0, 0, 1, 0.6), (0, 1, 0, 1)], stops=None)
+    s.draw_path(_random_closed_path(rng, 0, 0, 200.0, 2), Paint(shader=sh))
+    s.restore()
+    return s

@@ -58,11 +58,13 @@ def test_golden_bit_exact(dev, name):
     assert np.array_equal(got, want)
 
 
-def test_golden_gradients_within_tolerance(dev):
-    z = np.load(os.path.join(GOLDEN, "c2_gradients_90_512.npz"))
+@pytest.mark.parametrize("name", ["c2_gradients_90_512", "conical_512"])
+def test_golden_gradients_within_tolerance(dev, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
     want = z["rgba"]
     got = render(dev, z["dl"].tobytes(), 512, 512)
     assert_within_tolerance(got, want)
+    print(name, "pixels differing from the reference:", int((got != want).any(axis=2).sum()))
 
 
 def test_coverage_planes_bit_exact(dev):
