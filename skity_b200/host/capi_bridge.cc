@@ -7,6 +7,9 @@
 #include <string>
 #include <vector>
 
+#include <skity/recorder/display_list.hpp>
+#include <skity/recorder/picture_recorder.hpp>
+
 #include "skity_b200/host/cuda_canvas.hpp"
 #include "skity_b200/host/scene_player.hpp"
 
@@ -68,6 +71,39 @@ int skbh_encode_scene_batch(const uint8_t* scenes, const size_t* sizes, uint32_t
   *out_n = blob.size();
   if (unsupported && cap) {
     std::strncpy(unsupported, first_unsupported.c_str(), cap - 1);
+    unsupported[cap - 1] = 0;
+  }
+  return 0;
+}
+
+// The reference's own wire format as input: the scene is first RECORDED with skity::PictureRecorder into a
+// skity::DisplayList (include/skity/recorder/display_list.hpp:37-116, src/recorder/recorded_op.hpp) and the
+// display list is then replayed onto the CUDA canvas with DisplayList::Draw — the way recorded pictures
+// (.skp replays, the golden harness: test/golden/common/golden_test_env.hpp:45-47) reach any backend.
+int skbh_encode_recorded_scene(const uint8_t* scene, size_t n, uint8_t** out, size_t* out_n, char* unsupported,
+                               size_t cap) {
+  if (n < sizeof(skb_scene::Header)) return -1;
+  skb_scene::Header h;
+  std::memcpy(&h, scene, sizeof(h));
+  if (h.magic != skb_scene::kMagic) return -1;
+  skity::PictureRecorder recorder;
+  recorder.BeginRecording(skity::Rect::MakeWH(static_cast<float>(h.width), static_cast<float>(h.height)));
+  int rc = skb_scene::Play(scene, n, recorder.GetRecordingCanvas());
+  if (rc != 0) return rc;
+  std::unique_ptr<skity::DisplayList> picture = recorder.FinishRecording();
+  if (!picture) return -9;
+  skb::DlBuilder builder;
+  builder.Reset(h.width, h.height);
+  skity::CudaCanvas canvas(&builder, 0, h.width, h.height);
+  picture->Draw(&canvas);
+  canvas.Flush();
+  std::vector<uint8_t> blob = builder.Serialize();
+  *out = static_cast<uint8_t*>(std::malloc(blob.size() ? blob.size() : 1));
+  if (!*out) return -8;
+  std::memcpy(*out, blob.data(), blob.size());
+  *out_n = blob.size();
+  if (unsupported && cap) {
+    std::strncpy(unsupported, canvas.Unsupported().c_str(), cap - 1);
     unsupported[cap - 1] = 0;
   }
   return 0;

@@ -17,6 +17,8 @@ def lib():
         _lib.skbh_encode_scene.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p),
                                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_encode_scene.restype = ctypes.c_int
+        _lib.skbh_encode_recorded_scene.argtypes = _lib.skbh_encode_scene.argtypes
+        _lib.skbh_encode_recorded_scene.restype = ctypes.c_int
         _lib.skbh_free.argtypes = [ctypes.c_void_p]
         _lib.skbh_encode_scene_batch.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t), ctypes.c_uint32,
                                                  ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
@@ -28,12 +30,14 @@ def lib():
     return _lib
 
 
-def encode_scene(blob, allow_unsupported=False):
-    """Replay an SKSC scene through CudaCanvas and return the SKDL display list bytes."""
+def encode_scene(blob, allow_unsupported=False, recorded=False):
+    """Replay an SKSC scene through CudaCanvas and return the SKDL display list bytes.  With `recorded` the
+    scene is first recorded into a skity::DisplayList (PictureRecorder) and that picture is replayed."""
     out = ctypes.c_void_p()
     n = ctypes.c_size_t()
     msg = ctypes.create_string_buffer(256)
-    rc = lib().skbh_encode_scene(blob, len(blob), ctypes.byref(out), ctypes.byref(n), msg, 256)
+    fn = lib().skbh_encode_recorded_scene if recorded else lib().skbh_encode_scene
+    rc = fn(blob, len(blob), ctypes.byref(out), ctypes.byref(n), msg, 256)
     if rc != 0:
         raise RuntimeError(f"skbh_encode_scene failed: {rc}")
     try:

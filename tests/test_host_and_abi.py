@@ -93,3 +93,14 @@ def test_unsupported_features_are_reported_not_approximated():
     s.draw_rect(0, 0, 64, 64, Paint(blend=0))
     with pytest.raises(RuntimeError):
         hostlib.encode_scene(s.encode())
+
+
+def test_recorded_display_list_replays_to_the_same_frame():
+    """The reference's own wire format as input: each scene is recorded with
+    skity::PictureRecorder into a skity::DisplayList and DisplayList::Draw replays it onto the CUDA canvas;
+    the encoded frame must be byte-identical to the one the direct Canvas calls produce."""
+    scenes = [scene.scene_c0(), scene.scene_c2(60, 512, 9, clip_every=20, clip_box=300.0), scene.scene_layers(),
+              scene.scene_filters(), scene.scene_blend_modes(), scene.scene_conical()]
+    for s in scenes:
+        blob = s.encode()
+        assert hostlib.encode_scene(blob, recorded=True) == hostlib.encode_scene(blob)
