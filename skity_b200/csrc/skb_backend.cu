@@ -234,7 +234,8 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
     }
     if (o.kind == SKB_OP_FILL) {
       const skb_dl_paint pt = t.paints[o.paint];
-      g.color = pt.type == SKB_PAINT_SOLID ? color4f_to_pm_word(pt.color[0], pt.color[1], pt.color[2], pt.color[3]) : 0u;
+      // kept in the order the fine pass blends in (swap_rb)
+      g.color = pt.type == SKB_PAINT_SOLID ? swap_rb(color4f_to_pm_word(pt.color[0], pt.color[1], pt.color[2], pt.color[3])) : 0u;
       g.fast_solid = (pt.type == SKB_PAINT_SOLID && pt.blend == 0) ? 1u : 0u;
     }
     geom[op] = g;
@@ -580,7 +581,9 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
       const bool any = __any_sync(0xffffffffu, (dv.x | dv.y | a0 | a1 | z0 | z1) != 0);
       if (!any) continue;
       const bool anyz = zmode && __any_sync(0xffffffffu, (z0 | z1) != 0);
-      const bool both = __any_sync(0xffffffffu, ((nd0 & na0) | (nd1 & na1)) != 0);
+      // a pixel carries two spans when it has an accumulated value and a direct one — including a direct span
+      // whose coverage is 0 where that still blends (z)
+      const bool both = __any_sync(0xffffffffu, (((nd0 | (z0 << 7)) & na0) | ((nd1 | (z1 << 7)) & na1)) != 0);
       const bool solid = __all_sync(0xffffffffu, (dv.x & dv.y) == 0xFFFFFFFFu && (a0 | a1) == 0);
       const uint32_t item = item_row + (uint32_t)(tx - g.tx0);
       uint32_t flags = SKB_ITEM_PLANE0;
@@ -874,7 +877,9 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
   uint32_t* prow = reinterpret_cast<uint32_t*>(sd.px + (size_t)y * sd.pitch) + x0;
   uint4 q0 = reinterpret_cast<uint4*>(prow)[0];
   uint4 q1 = reinterpret_cast<uint4*>(prow)[1];
-  uint32_t dst[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+  // blended in the reference's register order (see swap_rb), swapped back when stored
+  uint32_t dst[8] = {swap_rb(q0.x), swap_rb(q0.y), swap_rb(q0.z), swap_rb(q0.w),
+                     swap_rb(q1.x), swap_rb(q1.y), swap_rb(q1.z), swap_rb(q1.w)};
 
   for (uint32_t i = 0; i < n; i++) {
     const uint2 cmd = list[i];
@@ -927,12 +932,12 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
         // a span reaches the pixel when its coverage is non-zero, or zero on a direct span (zmask)
         const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
         cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
-        if (cv || (touched && zmode)) dst[j] = blend_cover_mode(dst[j], paint_color(pt, a.stops, img, x0 + j, y), cv, mode);
+        if (cv || (touched && zmode)) dst[j] = blend_cover_mode(dst[j], swap_rb(paint_color(pt, a.stops, img, x0 + j, y)), cv, mode);
       }
     }
   }
-  reinterpret_cast<uint4*>(prow)[0] = make_uint4(dst[0], dst[1], dst[2], dst[3]);
-  reinterpret_cast<uint4*>(prow)[1] = make_uint4(dst[4], dst[5], dst[6], dst[7]);
+  reinterpret_cast<uint4*>(prow)[0] = make_uint4(swap_rb(dst[0]), swap_rb(dst[1]), swap_rb(dst[2]), swap_rb(dst[3]));
+  reinterpret_cast<uint4*>(prow)[1] = make_uint4(swap_rb(dst[4]), swap_rb(dst[5]), swap_rb(dst[6]), swap_rb(dst[7]));
 }
 
 // -------------------------------------------------------------------- stage 7: blur

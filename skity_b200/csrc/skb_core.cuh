@@ -735,6 +735,12 @@ SKB_HDN bool trap_prep_alpha(const TrapPrep& p, int x, uint8_t* out) {
 // Pixels are handled as little-endian words of the R,G,B,A bytes in memory:
 // word = R | G<<8 | B<<16 | A<<24.  AlphaMulQ / SrcOver treat the four bytes alike
 // (alpha sits in the top byte in both layouts), so no swizzle is needed.
+// The reference blends in registers laid out A<<24|R<<16|G<<8|B.  Its packed adds (PMSrcOver and the
+// other Porter-Duff sums) let a channel that overflows carry into the next one up — B into G, G into R, R
+// into A — which happens for real when a source is not a valid premultiplied colour (StackBlur's seeding
+// quirk produces such pixels).  To carry the same way, destination and source are swapped into that
+// order around every blend (one PRMT each way).
+SKB_HD uint32_t swap_rb(uint32_t c) { return (c & 0xFF00FF00u) | ((c >> 16) & 0xFFu) | ((c & 0xFFu) << 16); }
 SKB_HD uint32_t mul_div_255_round(uint32_t a, uint32_t b) {
   uint32_t prod = a * b + 128;
   return (prod + (prod >> 8)) >> 8;

@@ -48,7 +48,7 @@ struct OpGeom {
   uint32_t row_base;                       // first entry in the row table
   uint32_t item_base;                      // first (op, tile) work item
   uint32_t first_prim;
-  uint32_t color;                          // SOLID paints: premultiplied pixel word
+  uint32_t color;                          // SOLID paints: premultiplied colour, A<<24|R<<16|G<<8|B
   uint32_t fast_solid;                     // SOLID paint blended kSrcOver: the fine pass needs nothing but `color`
 };
 static_assert(offsetof(OpGeom, color) % 8 == 0 && sizeof(OpGeom) % 8 == 0, "the fine pass loads (color, fast_solid) as one 64-bit word");

@@ -16,7 +16,7 @@ t0 = time.time()
 
 def rand_scene(seed):
     rng = np.random.RandomState(seed)
-    kind = seed % 6
+    kind = seed % 10
     w, h = int(rng.randint(40, 700)), int(rng.randint(40, 700))
     if kind == 0:
         return scene.scene_random_fills(int(rng.randint(5, 150)), 0, seed, box=float(rng.uniform(20, 500)), width=w, height=h), True
@@ -46,6 +46,14 @@ def rand_scene(seed):
                                  cap=int(rng.randint(0, 3)), join=int(rng.randint(0, 3))))
             s.restore()
         return s, True
+    if kind == 6:
+        return scene.scene_blend_modes(seed, size=int(rng.randint(160, 600))), False
+    if kind == 7:
+        return scene.scene_filters(seed, size=int(rng.randint(200, 600))), True
+    if kind == 8:
+        return scene.scene_layers(seed, size=int(rng.randint(300, 640))), True
+    if kind == 9:
+        return scene.scene_conical(seed, size=int(rng.randint(200, 600))), False
     s = Scene(w, h)  # solid draws under nested clips and rect clips
     depth = 0
     for i in range(int(rng.randint(5, 60))):
@@ -75,7 +83,7 @@ for r in range(n_rounds):
     try:
         got = surf.render(dl)
     except device.SkbError as e:
-        print('seed', seed, 'kind', seed % 6, 'ERROR', e)
+        print('seed', seed, 'kind', seed % 10, 'ERROR', e)
         bad += 1
         surf.close()
         continue
@@ -85,5 +93,5 @@ for r in range(n_rounds):
     if not ok:
         bad += 1
         ys, xs = np.nonzero(d)
-        print('seed', seed, 'kind', seed % 6, s.width, s.height, 'MISMATCH max', d.max(), 'n', len(ys), list(zip(xs[:4], ys[:4])))
+        print('seed', seed, 'kind', seed % 10, s.width, s.height, 'MISMATCH max', d.max(), 'n', len(ys), list(zip(xs[:4], ys[:4])))
 print(f'fuzz: {n_rounds} scenes, {bad} bad, {time.time() - t0:.1f}s')

@@ -262,7 +262,7 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
             uint32_t cv = clip_entry_cover(out.e[k]);
             uint32_t galpha = paint->type == SKB_PAINT_IMAGE ? (paint->global_alpha & 0xFF) : 0xFFu;
             cv &= galpha;
-            if (cv) canvas[(size_t)y * W + x] = blend_cover_mode(canvas[(size_t)y * W + x], paint_color(*paint, pool, none, x, y), cv, paint_blend_mode(*paint));
+            if (cv) canvas[(size_t)y * W + x] = swap_rb(blend_cover_mode(swap_rb(canvas[(size_t)y * W + x]), swap_rb(paint_color(*paint, pool, none, x, y)), cv, paint_blend_mode(*paint)));
           }
         }
       }
