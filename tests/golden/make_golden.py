@@ -85,6 +85,11 @@ def golden_scenes():
     out["filters_512"] = scene.scene_filters()
     out["layers_512"] = scene.scene_layers()
     out["conical_512"] = scene.scene_conical()
+    # found by the GPU fuzz: StackBlur's seeding quirk yields pixels that are not valid premultiplied colours, whose
+    # SrcOver sum overflows a channel and carries into the next one up in the reference's A|R|G|B registers
+    out["filters_channel_carry_283"] = scene.scene_filters(5107, size=283)
+    # found by the GPU fuzz: a pixel with a zero-coverage direct span AND an accumulated span under kSrcIn / kScreen
+    out["blend_zero_then_accum_418"] = scene.scene_blend_modes(5016, size=418)
     return out
 
 
