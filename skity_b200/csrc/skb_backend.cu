@@ -657,9 +657,13 @@ struct ClipArgs {
 };
 
 // mode 0: build the clip states of nesting depth `level`; mode 1: rasterise the clipped draws.
-__global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int level) {
+// A row is shared by several threads, SKB_CLIP_SEG pixels each (blockIdx.y = which run of pixels): every
+// thread but the first seeks the sweep state to its first pixel (clip_row_seek).
+#define SKB_CLIP_SEG 64
+__global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int level, int seg_px) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.n_rows) return;
+  const int seg = (int)blockIdx.y;
   const CoverArgs& c = a.c;
   const uint32_t op = find_interval(c.row_base, c.n_ops, r);
   const skb_dl_op o = c.ops[op];
@@ -711,6 +715,16 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     x_last = min(x_last, hi);
   }
   x_last = min(x_last, (int)sd.w - 1);
+  if (st.n_prep >= 0) {
+    // pixels left of the surface only feed the sweep state: the runs are laid out from x = 0
+    const int x0 = max(x_first, 0) + seg * seg_px;
+    if (x0 > x_last) return;
+    clip_row_seek(st, c.pool, row, x_first, x0);
+    x_first = x0;
+    x_last = min(x_last, x0 + seg_px - 1);
+  } else if (seg != 0) {
+    return;  // a row with more records than the state holds is swept by one thread
+  }
   const int cap = mode == 0 ? SKB_CLIP_MAXE : SKB_CLIP_PLANES;
   const uint32_t item_row = c.item_base[op] + (uint32_t)((y / SKB_TILE) - g.ty0) * (uint32_t)g.ntx;
   bool wrote = false, over = false;
@@ -1661,12 +1675,17 @@ static skb_result run_frame(skb_surface s) {
     cl.op_depth = (const uint8_t*)s->op_depth.p;
     cl.overflow = counters + 2;
     cl.n_rows = (uint32_t)n_rows;
+    uint32_t max_w = 0;
+    for (const SurfDesc& d : surfs) max_w = std::max(max_w, d.w);
+    int seg_px = SKB_CLIP_SEG;
+    if (getenv("SKB_CLIP_SEG")) seg_px = std::max(1, atoi(getenv("SKB_CLIP_SEG")));
+    const dim3 clip_grid(cdiv(n_rows, 128), cdiv(max_w + 1, (uint32_t)seg_px));
     for (int level = 1; level <= max_depth; level++) {
-      k_clip_rows<<<cdiv(n_rows, 128), 128, 0, st>>>(cl, 0, level);
+      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level, seg_px);
       launches++;
     }
     if (has_clipped_fills) {
-      k_clip_rows<<<cdiv(n_rows, 128), 128, 0, st>>>(cl, 1, 0);
+      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0, seg_px);
       launches++;
       k_clip_classify<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
       launches++;

@@ -26,7 +26,8 @@ namespace skb {
 
 #define SKB_CLIP_MAXE 8          // spans of a clip state that may cover one pixel
 #define SKB_CLIP_PLANES 8        // coverage planes of a clipped draw
-#define SKB_CLIP_RMAX 6          // prepared records per row kept in registers/local memory
+#define SKB_CLIP_RMAX 20         // prepared records per row kept in thread-local memory; rows with more are swept
+                                 // by one thread that re-reads the records for every pixel
 #define SKB_CLIP_START_BIAS (1 << 22)
 
 // A clip-state entry: coverage (bits 0-7, never 0) | (span start x + bias) << 8.  0 = no entry.
@@ -161,6 +162,53 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
   st.prev_d_ends = d != 0 ? d_ends_next : false;
   st.prev_a = a;
   st.prev_a_start = own_a.start;
+}
+
+// Accumulated coverage of pixel x from the prepared records (saturated), without touching the sweep state.
+SKB_HDN uint32_t clip_row_accum_at(const ClipRowState& st, int x) {
+  uint32_t acc = 0;
+  for (int k = 0; k < st.n_prep; k++) {
+    const TrapPrep& p = st.prep[k];
+    uint8_t v;
+    if (p.accum && trap_prep_alpha(p, x, &v)) acc += v;
+  }
+  return acc > 255u ? 255u : acc;
+}
+
+// Puts the sweep state where a sweep from `x_first` would have it after pixel x0 - 1, so that several threads
+// can share one row (each takes a run of pixels).  Only for rows whose records are all prepared (n_prep >= 0).
+// Everything about pixel x0 - 1 follows from the records alone except the START of the accumulated run it
+// belongs to — the run of equal, non-zero accumulated coverage — which is found by walking left: whole
+// stretches where every record contributes a constant are skipped at once, only edge zones are walked pixel by
+// pixel.
+SKB_HDN void clip_row_seek(ClipRowState& st, const TrapRec* pool, uint2 row, int x_first, int x0) {
+  if (x0 <= x_first) return;
+  SpanSide ld, od, la, oa;
+  st.prev_d = st.prev_a = 0;
+  st.prev_d_ends = false;
+  clip_row_step(st, pool, row, x0 - 1, ld, od, la, oa);  // from a blank state: everything but prev_a_start is right
+  const uint32_t a0 = st.prev_a;
+  if (a0 == 0) return;
+  int cur = x0 - 1;
+  for (;;) {
+    // leftmost pixel zl <= cur such that every accumulating record is constant on [zl, cur]
+    int zl = x_first;
+    for (int k = 0; k < st.n_prep; k++) {
+      const TrapPrep& p = st.prep[k];
+      if (!p.accum || p.mode == 0) continue;
+      int z;
+      if (cur >= p.R) z = p.R;                          // right of the record: 0 back to its end
+      else if (cur < p.L) continue;                     // left of it: 0 all the way
+      else if (cur >= p.jl && cur < p.jr) z = p.jl;     // interior: `full` back to jl
+      else z = cur;                                     // edge zone: nothing assumed
+      zl = z > zl ? z : zl;
+    }
+    cur = zl;
+    if (cur <= x_first) break;
+    if (clip_row_accum_at(st, cur - 1) != a0) break;
+    cur--;
+  }
+  st.prev_a_start = cur;
 }
 
 SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {

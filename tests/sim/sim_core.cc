@@ -202,7 +202,7 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
   const int W = (int)sd[0].width, H = (int)sd[0].height;
   std::vector<uint32_t> canvas((size_t)W * H, 0u);
   std::vector<SimClipState> states(h->n_clip_states + 1);
-  stats[0] = stats[1] = 0;
+  stats[0] = stats[1] = stats[2] = stats[3] = 0;  // [0] plane overflows, [1] most planes on a pixel, [3] clip_row_seek mismatches
   SurfaceView none;
   none.px = nullptr;
   none.w = none.h = none.pitch = 0;
@@ -239,6 +239,18 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
       clip_row_begin(st, so.pool.data(), row);
       for (int x = g.scan_l; x <= g.scan_r && x < W; x++) {
         SpanSide ld, od, la, oa;
+        // the GPU lets several threads share a row: a thread entering at x must reconstruct this very state
+        if (st.n_prep >= 0 && x > g.scan_l && (x - g.scan_l) % 7 == 0) {
+          ClipRowState t = st;
+          t.prev_d = t.prev_a = 0xDEAD;
+          t.prev_d_start = t.prev_a_start = -12345;
+          t.prev_d_ends = true;
+          clip_row_seek(t, so.pool.data(), row, g.scan_l, x);
+          const bool same = t.prev_d == st.prev_d && t.prev_a == st.prev_a && t.prev_d_ends == st.prev_d_ends &&
+                            (st.prev_d == 0 || t.prev_d_start == st.prev_d_start) &&
+                            (st.prev_a == 0 || t.prev_a_start == st.prev_a_start);
+          if (!same) stats[3]++;
+        }
         clip_row_step(st, so.pool.data(), row, x, ld, od, la, oa);
         if (x < 0) continue;
         const uint32_t* clist = nullptr;

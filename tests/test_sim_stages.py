@@ -77,6 +77,7 @@ def test_sim_whole_frame_with_nested_clips():
     z = np.load(os.path.join(ROOT, "tests", "golden", "c2_clips_90_512.npz"))
     got, stats = simlib.render_dl(z["dl"].tobytes())
     assert stats[0] == 0
+    assert stats[3] == 0, "clip_row_seek must reproduce the sequential sweep state at any pixel of a row"
     assert np.array_equal(got, z["rgba"])
     s = scene.scene_c2(60, 384, 6, clip_every=12, clip_box=240.0, max_depth=3)
     dl = hostlib.encode_scene(s.encode())
@@ -92,3 +93,14 @@ def test_sim_sweep_nested_form_agrees(monkeypatch):
     check_scene(scene.scene_c0(blur=False))
     check_scene(scene.scene_c2(16, 256, 5, clip_every=0))
     check_scene(scene.scene_random_fills(24, 256, 9, box=160.0))
+
+
+@pytest.mark.parametrize("seed", [61, 62])
+def test_sim_clip_rows_shared_between_threads(seed):
+    """More clipped frames through the CPU build of the clip stage: pixels equal to the oracle port, and the
+    state a thread reconstructs when it enters a row in the middle (clip_row_seek) equal to the sequential one."""
+    s = scene.scene_c2(40, 384, seed, clip_every=6, clip_box=260.0)
+    dl = hostlib.encode_scene(s.encode())
+    got, stats = simlib.render_dl(dl)
+    assert stats[0] == 0 and stats[3] == 0
+    assert np.array_equal(got, port.render(dl))
