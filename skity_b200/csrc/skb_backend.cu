@@ -202,7 +202,7 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
 
 // ------------------------------------------------------------------- stage 2: setup
 __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom, const SurfDesc* surfs, uint32_t* row_cnt,
-                           uint32_t* item_cnt) {
+                           uint32_t* item_cnt, uint32_t* too_big) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const skb_dl_op o = t.ops[op];
@@ -216,8 +216,14 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
     g.slot_base = 2 * first_prim + 2 * op;
     g.n_slots = 2 + 2 * n_prims;
     const SurfDesc sd = surfs[o.surface];
-    op_setup(g, o.clip_bounds, sd.w, sd.h, p.n_segs > 0, (o.kind == SKB_OP_CLIP || o.clip_in != 0) ? 1 : 0);
-    if (!g.empty && g.ntx > 0) {
+    const bool is_clip = o.kind == SKB_OP_CLIP;
+    op_setup(g, o.clip_bounds, sd.w, sd.h, p.n_segs > 0, (is_clip || o.clip_in != 0) ? 1 : 0, is_clip ? 1 : 0);
+    if (is_clip && !g.empty && (int64_t)g.ntx * g.nty > (1 << 20)) {  // a clip path reaching absurdly far off the surface (> 2^28 pixels)
+      *too_big = 1;
+      g.ntx = g.nty = 0;
+    }
+    // a clip state is needed whole on every device: no band restriction for clip paths
+    if (!is_clip && !g.empty && g.ntx > 0) {
       // keep only the tile rows this device renders (band split); the rows outside are another GPU's
       int ty0 = max(g.ty0, (int)(sd.row0 / SKB_TILE));
       int ty1 = min(g.ty0 + g.nty, (int)((sd.row1 + SKB_TILE - 1) / SKB_TILE));
@@ -230,7 +236,7 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
     }
     if (!g.empty && g.ntx > 0) {
       rows = (uint32_t)(g.nty * SKB_TILE);
-      items = (uint32_t)(g.ntx * g.nty);
+      items = is_clip ? 0u : (uint32_t)(g.ntx * g.nty);  // clip paths fill clip tables, not tile masks
     }
     if (o.kind == SKB_OP_FILL) {
       const skb_dl_paint pt = t.paints[o.paint];
@@ -635,12 +641,14 @@ __global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* 
   d.nonempty = 0;
   d.op = op;
   d.pad = 0;
-  if (!g.empty) {
-    d.rx0 = max(g.scan_l, 0);
-    d.ry0 = max(g.scan_t, 0);
-    d.rw = max(min(g.scan_r + 1, (int)sd.w) - d.rx0, 0);
-    d.rh = max(min(g.scan_b, (int)sd.h) - d.ry0, 0);
-    if (d.rw == 0 || d.rh == 0) d.rw = d.rh = 0;
+  if (!g.empty && g.ntx > 0) {
+    // the whole scan rectangle (+ the column FindSpan's `+ 1` can reach), on the surface or not: HasClip() and
+    // nested clips see every span of a clip path (sw_canvas.cc:315-336)
+    d.rx0 = g.scan_l;
+    d.ry0 = g.scan_t;
+    d.rw = g.scan_r + 1 - g.scan_l;
+    d.rh = g.scan_b - g.scan_t;
+    if (d.rw <= 0 || d.rh <= 0) d.rw = d.rh = 0;
   }
   states[o.clip_out] = d;
   px_cnt[o.clip_out] = (uint32_t)(d.rw * d.rh);
@@ -657,13 +665,14 @@ struct ClipArgs {
 };
 
 // mode 0: build the clip states of nesting depth `level`; mode 1: rasterise the clipped draws.
-// A row is shared by several threads, SKB_CLIP_SEG pixels each (blockIdx.y = which run of pixels): every
-// thread but the first seeks the sweep state to its first pixel (clip_row_seek).
-#define SKB_CLIP_SEG 64
-__global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int level, int seg_px) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per row: every lane takes a run of consecutive pixels (at least SKB_CLIP_SEG_MIN) and, except the
+// first, seeks the sweep state to its first pixel (clip_row_seek).  Rows that are not this launch's business
+// cost one warp-uniform early exit.
+#define SKB_CLIP_SEG_MIN 8
+__global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int level) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= a.n_rows) return;
-  const int seg = (int)blockIdx.y;
+  const int seg = (int)(threadIdx.x & 31);
   const CoverArgs& c = a.c;
   const uint32_t op = find_interval(c.row_base, c.n_ops, r);
   const skb_dl_op o = c.ops[op];
@@ -676,7 +685,7 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   if (g.empty || g.ntx == 0) return;
   const SurfDesc sd = c.surfs[o.surface];
   const int y = g.ty0 * SKB_TILE + (int)(r - c.row_base[op]);
-  if (y < g.scan_t || y >= g.scan_b || y >= (int)sd.h) return;
+  if (y < g.scan_t || y >= g.scan_b || (mode == 1 && y >= (int)sd.h)) return;
   const uint2 row = c.rows[r];
   if (row.y == 0) return;
 
@@ -714,10 +723,13 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     x_first = max(x_first, lo);
     x_last = min(x_last, hi);
   }
-  x_last = min(x_last, (int)sd.w - 1);
+  if (mode == 1) x_last = min(x_last, (int)sd.w - 1);
+  // clipped draws store the pixels of the surface only; those left of it merely feed the sweep state
+  const int x_out = mode == 1 ? max(x_first, 0) : x_first;
   if (st.n_prep >= 0) {
-    // pixels left of the surface only feed the sweep state: the runs are laid out from x = 0
-    const int x0 = max(x_first, 0) + seg * seg_px;
+    const int width = x_last - x_out + 1;
+    const int seg_px = max(SKB_CLIP_SEG_MIN, (width + 31) / 32);
+    const int x0 = x_out + seg * seg_px;
     if (x0 > x_last) return;
     clip_row_seek(st, c.pool, row, x_first, x0);
     x_first = x0;
@@ -731,13 +743,23 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   for (int x = x_first; x <= x_last; x++) {
     SpanSide ld, od, la, oa;
     clip_row_step(st, c.pool, row, x, ld, od, la, oa);
-    if (x < 0) continue;
-    if ((ld.cover | od.cover | la.cover | oa.cover) == 0) continue;
+    if (x < x_out) continue;
+    if ((ld.cover | od.cover | la.cover | oa.cover) == 0 && !(mode == 0 && st.cur_zero_d)) continue;
     const uint32_t* clist = nullptr;
     int n_c = 0;
     if (c_row && x >= par.rx0 && x < par.rx0 + par.rw) {
       clist = c_row + (size_t)(x - par.rx0) * SKB_CLIP_MAXE;
       while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
+    }
+    if (mode == 0 && !wrote) {  // spans that cover nothing but still make the state count as a clip
+      const uint32_t* cprev = nullptr;
+      int n_p = 0;
+      if (c_row && x - 1 >= par.rx0 && x - 1 < par.rx0 + par.rw) {
+        cprev = c_row + (size_t)(x - 1 - par.rx0) * SKB_CLIP_MAXE;
+        while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
+      }
+      const bool starts = (od.cover && od.start == x) || (oa.cover && oa.start == x);
+      wrote = clip_ghost_span(st.cur_zero_d, starts, clipped, cprev, n_p, clist, n_c);
     }
     ClipOut out;
     clip_combine(ld, od, la, oa, clist, n_c, clipped, cap, out);
@@ -1512,14 +1534,20 @@ static skb_result run_frame(skb_surface s) {
       // ---- stage 2: setup
       SKB_CUDA(cudaMemsetAsync(row_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(item_base + n_ops, 0, 4, st));
-      k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base);
+      SKB_CUDA(cudaMemsetAsync(counters + 6, 0, 4, st));
+      k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base, counters + 6);
       launches++;
       SKB_TRY(scan_exclusive(s, row_base, n_ops + 1, &launches));
       SKB_TRY(scan_exclusive(s, item_base, n_ops + 1, &launches));
-      uint32_t tot[2] = {0, 0};
+      uint32_t tot[2] = {0, 0}, too_big = 0;
       SKB_TRY(fetch_words(s, &tot[0], row_base + n_ops, 1));
       SKB_TRY(fetch_words(s, &tot[1], item_base + n_ops, 1));
-      launches += 2;
+      SKB_TRY(fetch_words(s, &too_big, counters + 6, 1));
+      launches += 3;
+      if (too_big) {
+        set_error("the scan rectangle of a clip path exceeds 2^28 pixels (it reaches far beyond the surface)");
+        return SKB_ERROR_UNSUPPORTED;
+      }
       n_rows = tot[0];
       n_items = tot[1];
       S.n_rows = n_rows;
@@ -1675,17 +1703,13 @@ static skb_result run_frame(skb_surface s) {
     cl.op_depth = (const uint8_t*)s->op_depth.p;
     cl.overflow = counters + 2;
     cl.n_rows = (uint32_t)n_rows;
-    uint32_t max_w = 0;
-    for (const SurfDesc& d : surfs) max_w = std::max(max_w, d.w);
-    int seg_px = SKB_CLIP_SEG;
-    if (getenv("SKB_CLIP_SEG")) seg_px = std::max(1, atoi(getenv("SKB_CLIP_SEG")));
-    const dim3 clip_grid(cdiv(n_rows, 128), cdiv(max_w + 1, (uint32_t)seg_px));
-    for (int level = 1; level <= max_depth; level++) {
-      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level, seg_px);
+    const uint32_t clip_grid = cdiv(n_rows * 32, 128);
+    for (int level = 1; level <= max_depth && clip_grid; level++) {
+      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level);
       launches++;
     }
-    if (has_clipped_fills) {
-      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0, seg_px);
+    if (has_clipped_fills && clip_grid && n_items) {
+      k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0);
       launches++;
       k_clip_classify<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
       launches++;

@@ -26,7 +26,7 @@ namespace skb {
 
 #define SKB_CLIP_MAXE 8          // spans of a clip state that may cover one pixel
 #define SKB_CLIP_PLANES 8        // coverage planes of a clipped draw
-#define SKB_CLIP_RMAX 20         // prepared records per row kept in thread-local memory; rows with more are swept
+#define SKB_CLIP_RMAX 48         // prepared records per row kept in thread-local memory; rows with more are swept
                                  // by one thread that re-reads the records for every pixel
 #define SKB_CLIP_START_BIAS (1 << 22)
 
@@ -84,6 +84,24 @@ SKB_HDN void clip_combine(const SpanSide& left_d, const SpanSide& own_d, const S
   }
 }
 
+// Clip spans that cover nothing still count for SWCanvas::State::HasClip() (a non-empty span list,
+// sw_canvas.hpp), i.e. they decide whether later draws are clipped at all.  Two kinds arise at a pixel x while a
+// clip state is built: a directly emitted span of coverage 0 (kept by FindSpan with cover min(.., 0)), and the
+// zero-length sub-span FindSpan makes when a parent span ends exactly where an own span starts
+// (`clip.x + clip.len == span.x`, sw_canvas.cc:228-241).  `c_prev` / `c_cur` are the parent entries of pixels
+// x - 1 and x.
+SKB_HDN bool clip_ghost_span(bool zero_d, bool own_starts_here, bool clipped, const uint32_t* c_prev, int n_prev,
+                             const uint32_t* c_cur, int n_cur) {
+  if (zero_d && (!clipped || n_cur > 0)) return true;
+  if (!clipped || !own_starts_here) return false;
+  for (int i = 0; i < n_prev; i++) {
+    bool continues = false;
+    for (int j = 0; j < n_cur; j++) continues |= c_cur[j] == c_prev[i];
+    if (!continues) return true;
+  }
+  return false;
+}
+
 // Sweep state of one row.
 struct ClipRowState {
   TrapPrep prep[SKB_CLIP_RMAX];
@@ -92,6 +110,8 @@ struct ClipRowState {
   uint32_t prev_d, prev_a;
   int prev_d_start, prev_a_start;
   bool prev_d_ends;  // the direct span covering the previous pixel ends at the current pixel
+  bool cur_zero_d;   // the current pixel carries a directly emitted span whose coverage is 0 (it covers nothing,
+                     // but as a clip span it still makes HasClip() true)
 };
 
 // S side of pixel x of a row given its trapezoid records; advances the sweep state.
@@ -101,6 +121,7 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
   uint32_t d = 0, acc = 0;
   int d_start = x;
   bool d_ends_next = true;
+  bool d_touched = false;
   if (st.n_prep >= 0) {
     for (int k = 0; k < st.n_prep; k++) {
       const TrapPrep& p = st.prep[k];
@@ -108,6 +129,7 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
       if (!trap_prep_alpha(p, x, &v)) continue;
       if (!p.accum) {
         d = v;
+        d_touched = true;
         if (p.mode == 1 && x >= p.jl && x < p.jr) {  // interior of a direct row: one long span
           d_start = p.jl;
           d_ends_next = (x + 1 == p.jr);
@@ -132,6 +154,7 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
       if (!trap_prep_alpha(p, x, &v)) continue;
       if (!p.accum) {
         d = v;
+        d_touched = true;
         if (p.mode == 1 && x >= p.jl && x < p.jr) {
           d_start = p.jl;
           d_ends_next = (x + 1 == p.jr);
@@ -162,6 +185,7 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
   st.prev_d_ends = d != 0 ? d_ends_next : false;
   st.prev_a = a;
   st.prev_a_start = own_a.start;
+  st.cur_zero_d = d_touched && d == 0;
 }
 
 // Accumulated coverage of pixel x from the prepared records (saturated), without touching the sweep state.
@@ -215,6 +239,7 @@ SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
   st.prev_d = st.prev_a = 0;
   st.prev_d_start = st.prev_a_start = 0;
   st.prev_d_ends = false;
+  st.cur_zero_d = false;
   if (row.y > (uint32_t)SKB_CLIP_RMAX) {
     st.n_prep = -1;
     return;

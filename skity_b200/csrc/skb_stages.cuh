@@ -64,7 +64,10 @@ SKB_HD uint32_t f2u_wrap(float f) {
 // floor/ceil'd; empty test; WalkEdges arguments.  surf_w/h bound the tile rectangle.
 // extra_right = 1 for ops that go through the clip stage: FindSpan's `+ 1` can reach the pixel just right of
 // the scan rectangle, so their tile rectangle is one pixel wider.
-SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t surf_h, bool have_points, int extra_right = 0) {
+// unbounded = 1 for clip paths: their spans count wherever they fall (HasClip(), nested clips), so the tile
+// rectangle is the whole scan rectangle, on the surface or not.
+SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t surf_h, bool have_points, int extra_right = 0,
+                      int unbounded = 0) {
   g.empty = 1;
   g.ntx = g.nty = 0;
   g.tx0 = g.ty0 = 0;
@@ -89,13 +92,18 @@ SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t 
   g.right_clip = (fx)(f2u_wrap(sr) << 16);
   g.empty = 0;
   // tiles: scan rectangle ∩ surface (SWSpanBrush::Brush clips spans to the bitmap, sw_span_brush.cc:80-99)
-  int x0 = g.scan_l < 0 ? 0 : g.scan_l, y0 = g.scan_t < 0 ? 0 : g.scan_t;
-  int x1 = g.scan_r + extra_right > (int)surf_w ? (int)surf_w : g.scan_r + extra_right, y1 = g.scan_b > (int)surf_h ? (int)surf_h : g.scan_b;
+  int x0 = g.scan_l, y0 = g.scan_t, x1 = g.scan_r + extra_right, y1 = g.scan_b;
+  if (!unbounded) {
+    x0 = x0 < 0 ? 0 : x0;
+    y0 = y0 < 0 ? 0 : y0;
+    x1 = x1 > (int)surf_w ? (int)surf_w : x1;
+    y1 = y1 > (int)surf_h ? (int)surf_h : y1;
+  }
   if (x0 >= x1 || y0 >= y1) return;  // rasterised but entirely off-surface: no tiles
-  g.tx0 = x0 / SKB_TILE;
-  g.ty0 = y0 / SKB_TILE;
-  g.ntx = (x1 + SKB_TILE - 1) / SKB_TILE - g.tx0;
-  g.nty = (y1 + SKB_TILE - 1) / SKB_TILE - g.ty0;
+  g.tx0 = x0 >> 4;  // floor division by SKB_TILE, also for negative coordinates
+  g.ty0 = y0 >> 4;
+  g.ntx = ((x1 + SKB_TILE - 1) >> 4) - g.tx0;
+  g.nty = ((y1 + SKB_TILE - 1) >> 4) - g.ty0;
 }
 
 // Flatten one lowered primitive (line or quad, already transformed) into its 0..2 edges

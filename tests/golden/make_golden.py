@@ -90,6 +90,11 @@ def golden_scenes():
     out["filters_channel_carry_283"] = scene.scene_filters(5107, size=283)
     # found by the GPU fuzz: a pixel with a zero-coverage direct span AND an accumulated span under kSrcIn / kScreen
     out["blend_zero_then_accum_418"] = scene.scene_blend_modes(5016, size=418)
+    # found by the GPU fuzz: a clip path whose spans all lie off the surface still clips (HasClip() is a non-empty
+    # span list), and so does a nested clip whose only span is the zero-length one FindSpan makes when a parent
+    # span ends exactly where an own span starts
+    out["clip_spans_off_surface_75"] = scene.scene_fuzz(9002)[0]
+    out["clip_zero_length_span_532"] = scene.scene_fuzz(11012)[0]
     return out
 
 

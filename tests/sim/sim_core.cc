@@ -220,24 +220,25 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
       target = &states[o.clip_out];
       if (so.ok) {
         const OpGeom& g = so.g;
-        target->rx0 = g.scan_l < 0 ? 0 : g.scan_l;
-        target->ry0 = g.scan_t < 0 ? 0 : g.scan_t;
-        int x1 = g.scan_r + 1 > W ? W : g.scan_r + 1, y1 = g.scan_b > H ? H : g.scan_b;
-        target->rw = x1 > target->rx0 ? x1 - target->rx0 : 0;
-        target->rh = y1 > target->ry0 ? y1 - target->ry0 : 0;
+        // the whole scan rectangle, on the surface or not: HasClip() and nested clips see every span
+        target->rx0 = g.scan_l;
+        target->ry0 = g.scan_t;
+        target->rw = g.scan_r + 1 - g.scan_l;
+        target->rh = g.scan_b - g.scan_t;
         target->entries.assign((size_t)target->rw * target->rh * SKB_CLIP_MAXE, 0u);
       }
     }
     if (!so.ok) continue;
     const OpGeom& g = so.g;
     const skb_dl_paint* paint = o.kind == SKB_OP_FILL ? &paints[o.paint] : nullptr;
+    const bool is_clip = o.kind == SKB_OP_CLIP;
     for (int y = g.scan_t; y < g.scan_b; y++) {
-      if (y < 0 || y >= H) continue;
+      if (!is_clip && (y < 0 || y >= H)) continue;
       uint2 row = so.rows[(size_t)(y - g.scan_t)];
       if (row.y == 0) continue;
       ClipRowState st;
       clip_row_begin(st, so.pool.data(), row);
-      for (int x = g.scan_l; x <= g.scan_r && x < W; x++) {
+      for (int x = g.scan_l; x <= g.scan_r && (is_clip || x < W); x++) {
         SpanSide ld, od, la, oa;
         // the GPU lets several threads share a row: a thread entering at x must reconstruct this very state
         if (st.n_prep >= 0 && x > g.scan_l && (x - g.scan_l) % 7 == 0) {
@@ -252,12 +253,22 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
           if (!same) stats[3]++;
         }
         clip_row_step(st, so.pool.data(), row, x, ld, od, la, oa);
-        if (x < 0) continue;
+        if (!is_clip && x < 0) continue;
         const uint32_t* clist = nullptr;
         int n_c = 0;
         if (clipped && x >= parent->rx0 && x < parent->rx0 + parent->rw && y >= parent->ry0 && y < parent->ry0 + parent->rh) {
           clist = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - parent->rx0)) * SKB_CLIP_MAXE];
           while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
+        }
+        if (is_clip && !target->nonempty) {
+          const uint32_t* cprev = nullptr;
+          int n_p = 0;
+          if (clipped && x - 1 >= parent->rx0 && x - 1 < parent->rx0 + parent->rw && y >= parent->ry0 && y < parent->ry0 + parent->rh) {
+            cprev = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - 1 - parent->rx0)) * SKB_CLIP_MAXE];
+            while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
+          }
+          const bool starts = (od.cover && od.start == x) || (oa.cover && oa.start == x);
+          if (clip_ghost_span(st.cur_zero_d, starts, clipped, cprev, n_p, clist, n_c)) target->nonempty = true;
         }
         ClipOut out;
         clip_combine(ld, od, la, oa, clist, n_c, clipped, o.kind == SKB_OP_CLIP ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, out);

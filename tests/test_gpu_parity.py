@@ -58,11 +58,12 @@ def test_golden_bit_exact(dev, name):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("name", ["c2_gradients_90_512", "conical_512"])
+@pytest.mark.parametrize("name", ["c2_gradients_90_512", "conical_512", "clip_spans_off_surface_75",
+                                  "clip_zero_length_span_532"])
 def test_golden_gradients_within_tolerance(dev, name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     want = z["rgba"]
-    got = render(dev, z["dl"].tobytes(), 512, 512)
+    got = render(dev, z["dl"].tobytes(), want.shape[1], want.shape[0])
     assert_within_tolerance(got, want)
     print(name, "pixels differing from the reference:", int((got != want).any(axis=2).sum()))
 
