@@ -32,7 +32,8 @@ import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this
 # workload (profiles/r01_ncu_top3_c1.txt); None where no capture exists
-NCU_TRAFFIC = {("c1", "k_walk"): 35013120 + 118759680, ("c1", "k_cover"): 146969856 + 129862912}
+NCU_TRAFFIC = {("c1", "k_walk"): 33462272 + 116994304, ("c1", "k_cover"): 146301696 + 123251456,
+               ("c1", "k_fine"): 235771648 + 47252224}
 
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
