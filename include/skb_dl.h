@@ -128,6 +128,18 @@ enum skb_dl_paint_type {
                            r0/|c1-c0|, transform sx kx tx ky sy ty, r1, r1^2, f */
 };
 
+/* Colour-filter block in the float pool (raw 32-bit words), applied to the coverage-scaled source colour before
+ * the blend (SWSpanBrush::BrushH, sw_span_brush.cc:108-133; src/effect/color_filter.cc:123-197):
+ *   word 0 type: SKB_CF_BLEND   word 1 = skity::BlendMode, word 2 = the filter's premultiplied colour A<<24|R<<16|G<<8|B
+ *                SKB_CF_MATRIX  words 4-13 = the 4x5 matrix as int16 (row-major, MatrixColorFilter::matrix_i16_)
+ *                SKB_CF_TABLE   words 4-67 = 256 bytes: per-channel look-up of the unpremultiplied colour
+ *                               (SRGBGammaColorFilter, either direction) */
+#define SKB_CF_BLEND 1u
+#define SKB_CF_MATRIX 2u
+#define SKB_CF_TABLE 3u
+#define SKB_PAINT_HAS_STOPS(p) ((p).has_stops & 1u)
+#define SKB_PAINT_CF_OFFSET(p) ((p).has_stops >> 8) /* 0 = none, else 1 + word offset */
+
 /* IMAGE paints: the sampled surface holds unpremultiplied pixels (PixmapBrush premultiplies after sampling,
  * sw_span_brush.cc:573-576) — ORed into tile_mode */
 #define SKB_PAINT_IMAGE_UNPREMUL 0x100u
@@ -140,7 +152,8 @@ typedef struct skb_dl_paint {
                          — sx kx tx ky sy ty, as GenerateBrush builds it (sw_canvas.cc:727-795) */
   uint32_t stop_off;  /* float offset into the stop pool: n_colors*4 colour floats then n_colors stops */
   uint32_t n_colors;
-  uint32_t has_stops; /* 0: implicit i/(n-1) */
+  uint32_t has_stops; /* bit 0: explicit stops (else implicit i/(n-1)); bits 8-31: 1 + word offset in the float pool
+                         of a colour-filter block (0 = no filter), see SKB_CF_* */
   float bias;         /* SWEEP: info.radius[0] */
   float scale;        /* SWEEP: info.radius[1] */
   uint32_t image_surface; /* IMAGE: source surface id */

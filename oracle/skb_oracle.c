@@ -1091,6 +1091,33 @@ static inline void blend_pixel(uint8_t* px, uint32_t src, uint32_t mode) {
   px[3] = (uint8_t)(r >> 24);
 }
 
+/* ColorFilter::FilterColor — src/effect/color_filter.cc:123-197 ; PMColorToColor / ColorToPMColor —
+ * src/graphic/color_priv.cc:85-108 (UnPreMultiply scale = round(255 * 2^24 / alpha)) */
+static uint32_t apply_color_filter(const uint32_t* blk, uint32_t c) {
+  uint32_t type = blk[0];
+  if (type == SKB_CF_BLEND) return porter_duff(blk[2], c, blk[1]);
+  uint32_t a = c >> 24;
+  uint32_t scale = a ? (uint32_t)((0xFF000000u + a / 2) / a) : 0u;
+  uint32_t ch[4], o[4];
+  ch[0] = (uint32_t)(((uint64_t)scale * ((c >> 16) & 0xFF) + (1u << 23)) >> 24);
+  ch[1] = (uint32_t)(((uint64_t)scale * ((c >> 8) & 0xFF) + (1u << 23)) >> 24);
+  ch[2] = (uint32_t)(((uint64_t)scale * (c & 0xFF) + (1u << 23)) >> 24);
+  ch[3] = a;
+  if (type == SKB_CF_MATRIX) {
+    const int16_t* m = (const int16_t*)(blk + 4);
+    for (int i = 0; i < 4; i++) {
+      int32_t mul = (int32_t)ch[0] * m[5 * i] + (int32_t)ch[1] * m[5 * i + 1] + (int32_t)ch[2] * m[5 * i + 2] + (int32_t)ch[3] * m[5 * i + 3];
+      int32_t v = mul / 255 + m[5 * i + 4];
+      o[i] = (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  } else {
+    const uint8_t* t = (const uint8_t*)(blk + 4);
+    for (int i = 0; i < 3; i++) o[i] = t[ch[i]];
+    o[3] = a;
+  }
+  return color_to_pm((o[3] << 24) | (o[0] << 16) | (o[1] << 8) | o[2]);
+}
+
 typedef struct surface { uint32_t w, h; uint8_t* px; } surface;
 
 /* GradientColorBrush::LerpColor — sw_span_brush.cc:21-32,239-299 */
@@ -1109,11 +1136,11 @@ static void lerp_color(const skb_dl_paint* p, const float* pool, float t, float 
   }
   int n = (int)p->n_colors;
   float step = 1.f / (n - 1);
-  if (p->has_stops && t <= stops[0]) { memcpy(out, colors, 16); return; }
+  if ((p->has_stops & 1u) && t <= stops[0]) { memcpy(out, colors, 16); return; }
   int i, si = 0, ei = 1;
   float start = 0.f, end = 0.f;
   for (i = 0; i < n - 1; i++) {
-    if (p->has_stops) { start = stops[i]; end = stops[i + 1]; }
+    if (p->has_stops & 1u) { start = stops[i]; end = stops[i + 1]; }
     else { start = step * i; end = step * (i + 1); }
     if (t >= start && t <= end) { si = i; ei = i + 1; break; }
   }
@@ -1224,6 +1251,7 @@ static void brush_spans(surface* dst, const skbo_span* spans, size_t n, const sk
     for (int l = 0; l < len; l++) {
       uint32_t color = paint_color(p, pool, surfs, x + l, y);
       if (alpha != 255) color = alpha_mul_q(color, alpha);
+      if (p->has_stops >> 8) color = apply_color_filter((const uint32_t*)pool + ((p->has_stops >> 8) - 1), color);
       blend_pixel(dst->px + ((size_t)y * dst->w + (x + l)) * 4, color, mode);
     }
   }

@@ -242,7 +242,7 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
       const skb_dl_paint pt = t.paints[o.paint];
       // kept in the order the fine pass blends in (swap_rb)
       g.color = pt.type == SKB_PAINT_SOLID ? swap_rb(color4f_to_pm_word(pt.color[0], pt.color[1], pt.color[2], pt.color[3])) : 0u;
-      g.fast_solid = (pt.type == SKB_PAINT_SOLID && pt.blend == 0) ? 1u : 0u;
+      g.fast_solid = (pt.type == SKB_PAINT_SOLID && pt.blend == 0 && SKB_PAINT_CF_OFFSET(pt) == 0) ? 1u : 0u;
     }
     geom[op] = g;
   }
@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(COVER_WARPS * 32) k_cover(CoverArgs c) {
   const int xmax = min(g.scan_r, (int)sd.w);
   const int xmin = max(g.scan_l, 0);
   // blend modes that change the destination under a zero source: remember which pixels a direct span touched
-  const bool zmode = c.zmask != nullptr && blend_zero_src_matters(paint_blend_mode(c.paints[o.paint]));
+  const bool zmode = c.zmask != nullptr && (blend_zero_src_matters(paint_blend_mode(c.paints[o.paint])) ||
+                                            SKB_PAINT_CF_OFFSET(c.paints[o.paint]) != 0);
   // lanes 0..15 own the row table entries of the 16 pixel rows
   uint2 row = make_uint2(0u, 0u);
   {
@@ -962,13 +963,21 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
       }
 #pragma unroll 1
       const uint32_t mode = paint_blend_mode(pt);
-      const bool zmode = blend_zero_src_matters(mode);
+      // a colour filter can turn a zero source into something: then zero-coverage pixels matter as well
+      const uint32_t* cf = SKB_PAINT_CF_OFFSET(pt) ? reinterpret_cast<const uint32_t*>(a.stops) + (SKB_PAINT_CF_OFFSET(pt) - 1) : nullptr;
+      const bool zmode = blend_zero_src_matters(mode) || cf != nullptr;
       for (int j = 0; j < 8; j++) {
         uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
         // a span reaches the pixel when its coverage is non-zero, or zero on a direct span (zmask)
         const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
         cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
-        if (cv || (touched && zmode)) dst[j] = blend_cover_mode(dst[j], swap_rb(paint_color(pt, a.stops, img, x0 + j, y)), cv, mode);
+        if (cv || (touched && zmode)) {
+          // BrushH: colour, scaled by the coverage, colour filter, blend (sw_span_brush.cc:108-133)
+          uint32_t src = swap_rb(paint_color(pt, a.stops, img, x0 + j, y));
+          if (cv != 255) src = alpha_mul_q(src, cv);
+          if (cf) src = apply_color_filter(cf, src);
+          dst[j] = porter_duff(src, dst[j], mode);
+        }
       }
     }
   }
@@ -1385,7 +1394,16 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
           set_error("display list: blend mode outside what SWRenderTarget implements (kClear..kScreen, kSoftLight)");
           return SKB_ERROR_BAD_DISPLAY_LIST;
         }
-        if (o.clip_in != 0 && pt.blend && blend_zero_src_matters(pt.blend - 1)) {
+        if (SKB_PAINT_CF_OFFSET(pt)) {
+          const uint64_t off = SKB_PAINT_CF_OFFSET(pt) - 1;
+          const uint32_t* blk = (const uint32_t*)(dl + h.off_stops) + off;
+          if (off + 4 > h.n_stop_floats || blk[0] < SKB_CF_BLEND || blk[0] > SKB_CF_TABLE ||
+              off + (blk[0] == SKB_CF_TABLE ? 68u : 16u) > h.n_stop_floats || (blk[0] == SKB_CF_BLEND && blk[1] > 21)) {
+            set_error("display list: bad colour filter block");
+            return SKB_ERROR_BAD_DISPLAY_LIST;
+          }
+        }
+        if (o.clip_in != 0 && ((pt.blend && blend_zero_src_matters(pt.blend - 1)) || SKB_PAINT_CF_OFFSET(pt))) {
           set_error("blend modes that act on zero-coverage pixels are not implemented under a path clip");
           return SKB_ERROR_UNSUPPORTED;
         }
@@ -2039,7 +2057,7 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
   {
     const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
     for (uint32_t i = 0; i < h.n_paints; i++)
-      if (paints[i].blend && blend_zero_src_matters(paints[i].blend - 1)) s->zero_blend = true;
+      if ((paints[i].blend && blend_zero_src_matters(paints[i].blend - 1)) || SKB_PAINT_CF_OFFSET(paints[i])) s->zero_blend = true;
   }
   SKB_TRY(buf_reserve(s->dl, h.total_bytes));
   SKB_CUDA(cudaMemcpyAsync(s->dl.p, dl, h.total_bytes, cudaMemcpyHostToDevice, s->stream));

@@ -858,6 +858,45 @@ SKB_HD uint32_t blend_cover_mode(uint32_t dst, uint32_t color, uint32_t cover, u
   return porter_duff(color, dst, mode);
 }
 
+// ColorFilter::FilterColor on a premultiplied colour in the reference's register order A<<24|R<<16|G<<8|B
+// (src/effect/color_filter.cc:123-197; PMColorToColor / ColorToPMColor src/graphic/color_priv.cc:85-108, the
+// unpremultiply scale table is round(255 * 2^24 / alpha)).
+SKB_HDN uint32_t apply_color_filter(const uint32_t* blk, uint32_t c) {
+  const uint32_t type = blk[0];
+  if (type == SKB_CF_BLEND) return porter_duff(blk[2], c, blk[1]);  // PorterDuffBlend(filter colour, src, mode)
+  // unpremultiply
+  const uint32_t a = c >> 24;
+  const uint32_t scale = a ? (uint32_t)((0xFF000000u + a / 2) / a) : 0u;
+  uint32_t ch[4];  // r g b a
+  ch[0] = (uint32_t)(((uint64_t)scale * ((c >> 16) & 0xFF) + (1u << 23)) >> 24);
+  ch[1] = (uint32_t)(((uint64_t)scale * ((c >> 8) & 0xFF) + (1u << 23)) >> 24);
+  ch[2] = (uint32_t)(((uint64_t)scale * (c & 0xFF) + (1u << 23)) >> 24);
+  ch[3] = a;
+  uint32_t o[4];
+  if (type == SKB_CF_MATRIX) {
+    for (int i = 0; i < 4; i++) {
+      int32_t m[5];
+      for (int j = 0; j < 5; j++) {
+        const int k = 5 * i + j;
+        m[j] = (int32_t)(int16_t)((blk[4 + (k >> 1)] >> (16 * (k & 1))) & 0xFFFF);
+      }
+      int32_t mul = (int32_t)ch[0] * m[0] + (int32_t)ch[1] * m[1] + (int32_t)ch[2] * m[2] + (int32_t)ch[3] * m[3];
+      int32_t v = mul / 255 + m[4];
+      o[i] = (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+  } else {  // SKB_CF_TABLE
+    for (int i = 0; i < 3; i++) o[i] = (blk[4 + (ch[i] >> 2)] >> (8 * (ch[i] & 3))) & 0xFF;
+    o[3] = a;
+  }
+  // ColorToPMColor
+  if (o[3] != 255) {
+    o[0] = mul_div_255_round(o[0], o[3]);
+    o[1] = mul_div_255_round(o[1], o[3]);
+    o[2] = mul_div_255_round(o[2], o[3]);
+  }
+  return (o[3] << 24) | (o[0] << 16) | (o[1] << 8) | o[2];
+}
+
 // GradientColorBrush::LerpColor (sw_span_brush.cc:21-32,239-299) -> premultiplied pixel word
 SKB_HDN uint32_t gradient_color(const skb_dl_paint& p, const float* pool, float t) {
   const float* colors = pool + p.stop_off;
@@ -878,10 +917,11 @@ SKB_HDN uint32_t gradient_color(const skb_dl_paint& p, const float* pool, float 
   int si = 0, ei = 1;
   float start = 0.f, end = 0.f;
   int i = 0;
-  bool first = p.has_stops && t <= stops[0];
+  const bool has_stops = SKB_PAINT_HAS_STOPS(p) != 0;
+  bool first = has_stops && t <= stops[0];
   if (!first) {
     for (i = 0; i < n - 1; i++) {
-      if (p.has_stops) { start = stops[i]; end = stops[i + 1]; }
+      if (has_stops) { start = stops[i]; end = stops[i + 1]; }
       else { start = step * i; end = step * (i + 1); }
       if (t >= start && t <= end) { si = i; ei = i + 1; break; }
     }

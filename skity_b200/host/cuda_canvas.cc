@@ -1,6 +1,8 @@
 #include "skity_b200/host/cuda_canvas.hpp"
 
+#include "src/effect/color_filter_base.hpp"
 #include "src/effect/image_filter_base.hpp"
+#include "src/graphic/color_priv.hpp"
 
 #include <cmath>
 #include <cstring>
@@ -395,6 +397,51 @@ static bool BlendNeedsZeroCoverage(uint32_t encoded) {
   }
 }
 
+// Encodes paint.GetColorFilter() as a block of the float pool (include/skb_dl.h, SKB_CF_*) and returns the bits to
+// OR into skb_dl_paint::has_stops.  What each filter computes: src/effect/color_filter.cc:123-197.
+uint32_t CudaCanvas::EncodeColorFilter(const Paint& paint) {
+  auto filter = paint.GetColorFilter();
+  if (!filter) return 0;
+  const ColorFilterBase* base = As_CFB(filter.get());
+  uint32_t blk[68] = {};
+  uint32_t n_words = 16;
+  switch (base->GetType()) {
+    case ColorFilterType::kBlend: {
+      auto* f = static_cast<const BlendColorFilter*>(base);
+      blk[0] = SKB_CF_BLEND;
+      uint32_t mode = EncodeBlend(f->GetBlendMode());  // same fall-back to kSrcOver as a draw's blend mode
+      blk[1] = mode ? mode - 1 : static_cast<uint32_t>(BlendMode::kSrcOver);
+      blk[2] = ColorToPMColor(f->GetColor());
+    } break;
+    case ColorFilterType::kMatrix: {
+      auto* f = const_cast<MatrixColorFilter*>(static_cast<const MatrixColorFilter*>(base));
+      auto [mul, add] = f->GetMatrix();  // column i of `mul` = coefficients of input channel i
+      blk[0] = SKB_CF_MATRIX;
+      int16_t m16[20];
+      for (int r = 0; r < 4; r++) {
+        for (int c = 0; c < 4; c++) m16[5 * r + c] = static_cast<int16_t>(mul.Get(r, c) * 255);
+        m16[5 * r + 4] = static_cast<int16_t>(add[r] * 255);
+      }
+      std::memcpy(blk + 4, m16, sizeof(m16));
+    } break;
+    case ColorFilterType::kLinearToSRGBGamma:
+    case ColorFilterType::kSRGBToLinearGamma: {
+      // the per-channel table is read off the filter itself: an opaque grey goes through unchanged except for the look-up
+      blk[0] = SKB_CF_TABLE;
+      uint8_t* table = reinterpret_cast<uint8_t*>(blk + 4);
+      for (uint32_t v = 0; v < 256; v++) table[v] = static_cast<uint8_t>(ColorGetR(filter->FilterColor(ColorSetARGB(255, v, v, v))));
+      n_words = 68;
+    } break;
+    case ColorFilterType::kCompose:
+      return 0;  // ComposeColorFilter::OnFilterColor returns its input (color_filter.cc:194-197)
+    default:
+      NoteUnsupported("colour filter type");
+      return 0;
+  }
+  uint32_t off = builder_->AddWords(blk, n_words);
+  return (off + 1) << 8;
+}
+
 uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
   skb_dl_paint p{};
   p.global_alpha = 255;
@@ -403,7 +450,12 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
     NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
     p.blend = 0;
   }
-  if (paint.GetColorFilter()) NoteUnsupported("color filter");
+  uint32_t cf_bits = 0;
+  if (paint.GetColorFilter()) {
+    if (state_stack_.back().clip_id != 0) NoteUnsupported("colour filter under a path clip");
+    else cf_bits = EncodeColorFilter(paint);
+  }
+  p.has_stops = cf_bits;
   auto shader = paint.GetShader();
   if (shader) {
     Shader::GradientInfo info{};
@@ -422,7 +474,7 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
                                                                   : (type == Shader::kSweep ? SKB_PAINT_SWEEP : SKB_PAINT_CONICAL));
       p.tile_mode = static_cast<uint32_t>(info.tile_mode);
       p.n_colors = static_cast<uint32_t>(info.colors.size());
-      p.has_stops = info.color_offsets.empty() ? 0u : 1u;
+      p.has_stops = cf_bits | (info.color_offsets.empty() ? 0u : 1u);
       std::vector<float> cols(4 * info.colors.size());
       for (size_t i = 0; i < info.colors.size(); i++) {
         cols[4 * i + 0] = info.colors[i].x;
@@ -691,7 +743,10 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
     NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
     p.blend = 0;
   }
-  if (paint.GetColorFilter()) NoteUnsupported("color filter");
+  if (paint.GetColorFilter()) {
+    if (state_stack_.back().clip_id != 0) NoteUnsupported("colour filter under a path clip");
+    else p.has_stops = EncodeColorFilter(paint);
+  }
   uint32_t paint_index = builder_->AddPaint(p);
   EmitFill(path, CurrentTransform(), paint_index);
 }

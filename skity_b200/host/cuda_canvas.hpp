@@ -77,6 +77,7 @@ class CudaCanvas : public Canvas {
   void FillPath(const Path& path, const Paint& paint, bool stroke);
   void EmitFill(const Path& path, const Matrix& ctm, uint32_t paint_index);
   uint32_t MakeBrush(const Paint& paint, bool stroke);
+  uint32_t EncodeColorFilter(const Paint& paint);
   void HandleFilter(const Path& path, const Paint& paint);
   void DrawSurfaceImage(uint32_t src_surface, uint32_t w, uint32_t h, const Rect& dst,
                         const Paint& paint, bool unpremul);

@@ -70,6 +70,14 @@ class DlBuilder {
   // appends to the float pool (directly behind the block AddStops just returned)
   void AddFloats(const float* v, uint32_t n) { stops_.insert(stops_.end(), v, v + n); }
 
+  // raw 32-bit words in the float pool (colour-filter blocks); returns their word offset
+  uint32_t AddWords(const uint32_t* v, uint32_t n) {
+    uint32_t off = static_cast<uint32_t>(stops_.size());
+    stops_.resize(stops_.size() + n);
+    std::memcpy(stops_.data() + off, v, 4 * static_cast<size_t>(n));
+    return off;
+  }
+
   void AddOp(const skb_dl_op& op) { ops_.push_back(op); }
 
   size_t OpCount() const { return ops_.size(); }

@@ -19,13 +19,16 @@
 //             f32 local[6] (sx kx tx ky sy ty), f32 rgba[4*n_colors], f32 stops[n_stops]]
 //            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode),
 //             u32 image_filter (0 none, 1 ImageFilters::Blur, 2 ImageFilters::DropShadow),
-//             f32 dx, f32 dy, f32 sigma_x, f32 sigma_y, u32 shadow colour (A<<24|R<<16|G<<8|B)
+//             f32 dx, f32 dy, f32 sigma_x, f32 sigma_y, u32 shadow colour (A<<24|R<<16|G<<8|B),
+//             u32 colour_filter (0 none, 1 ColorFilters::Blend, 2 Matrix, 3 LinearToSRGBGamma, 4 SRGBToLinearGamma),
+//             u32 filter colour, u32 filter blend mode, f32 matrix[20]
 #ifndef SKITY_B200_HOST_SCENE_PLAYER_HPP
 #define SKITY_B200_HOST_SCENE_PLAYER_HPP
 
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <skity/effect/color_filter.hpp>
 #include <skity/effect/image_filter.hpp>
 #include <skity/effect/mask_filter.hpp>
 #include <skity/effect/shader.hpp>
@@ -226,6 +229,14 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
     paint->SetBlendMode(static_cast<skity::BlendMode>(blend));
     if (filter == 1) paint->SetImageFilter(skity::ImageFilters::Blur(f[2], f[3]));
     if (filter == 2) paint->SetImageFilter(skity::ImageFilters::DropShadow(f[0], f[1], f[2], f[3], shadow, nullptr));
+    uint32_t cf = r.U32(), cf_color = r.U32(), cf_mode = r.U32();
+    float cm[20];
+    r.Get(cm, 80);
+    if (!r.ok() || cf > 4 || cf_mode > static_cast<uint32_t>(skity::BlendMode::kLastMode)) return false;
+    if (cf == 1) paint->SetColorFilter(skity::ColorFilters::Blend(cf_color, static_cast<skity::BlendMode>(cf_mode)));
+    if (cf == 2) paint->SetColorFilter(skity::ColorFilters::Matrix(cm));
+    if (cf == 3) paint->SetColorFilter(skity::ColorFilters::LinearToSRGBGamma());
+    if (cf == 4) paint->SetColorFilter(skity::ColorFilters::SRGBToLinearGamma());
   }
   return true;
 }

@@ -76,17 +76,19 @@ class PathData:
 class Paint:
     def __init__(self, style=FILL, fill=(0, 0, 0, 1), stroke=(0, 0, 0, 1), stroke_width=1.0, miter=4.0,
                  cap=BUTT, join=MITER, blur_radius=0.0, blur_style=1, shader=None, blend=None,
-                 image_filter=None):
+                 image_filter=None, color_filter=None):
         self.style, self.fill, self.stroke = style, fill, stroke
         self.stroke_width, self.miter, self.cap, self.join = stroke_width, miter, cap, join
         self.blur_radius, self.blur_style = blur_radius, blur_style
         self.blend = blend    # skity::BlendMode value, None = default (kSrcOver)
         # None | dict(type=1, sigma=(sx, sy)) ImageFilters::Blur | dict(type=2, offset=(dx, dy), sigma=(sx, sy), color=0xAARRGGBB)
         self.image_filter = image_filter
+        # None | dict(type=1, color=0xAARRGGBB, mode=BlendMode) | dict(type=2, matrix=[20 floats]) | dict(type=3) | dict(type=4)
+        self.color_filter = color_filter
         self.shader = shader  # dict(type=1|2|3, p=(..4), tile=, colors=[(r,g,b,a)..], stops=[..]|None, local=None|6)
 
     def encode(self):
-        extras = self.blend is not None or self.image_filter is not None
+        extras = self.blend is not None or self.image_filter is not None or self.color_filter is not None
         out = struct.pack("<I2f2I", self.style | (0x100 if extras else 0), self.stroke_width, self.miter, self.cap, self.join)
         out += np.asarray(self.fill, dtype=np.float32).tobytes()
         out += np.asarray(self.stroke, dtype=np.float32).tobytes()
@@ -101,6 +103,9 @@ class Paint:
             sx, sy = f.get("sigma", (0.0, 0.0))
             out += struct.pack("<2I4fI", 3 if self.blend is None else self.blend, f.get("type", 0), dx, dy, sx, sy,
                                f.get("color", 0))
+            c = self.color_filter or {}
+            out += struct.pack("<3I", c.get("type", 0), c.get("color", 0), c.get("mode", 3))
+            out += np.asarray(c.get("matrix", [0.0] * 20), dtype=np.float32).tobytes()
         return out
 
     def _encode_shader(self):
@@ -617,3 +622,35 @@ def scene_fuzz(seed):
     while depth:
         s.restore(); depth -= 1
     return s, True
+
+
+def scene_color_filters(seed=66, size=512):
+    """Paint colour filters (src/effect/color_filter.cc): ColorFilters::Blend with several modes, Matrix (saturation,
+    channel swap, alpha-changing), both sRGB gamma tables; on solid, gradient, translucent and blurred draws, combined
+    with non-default blend modes."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.85, 0.9, 0.95, 1.0)))
+    for i in range(5):
+        p = _random_closed_path(rng, rng.uniform(0, size), rng.uniform(0, size), 260.0, i)
+        s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (rng.uniform(0.4, 1.0),)))
+    sat = [0.3, 0.6, 0.1, 0, 0, 0.3, 0.6, 0.1, 0, 0, 0.3, 0.6, 0.1, 0, 0, 0, 0, 0, 1, 0]
+    swap = [0, 0, 1, 0, 0, 0, 1, 0, 0, 0.1, 1, 0, 0, 0, -0.1, 0, 0, 0, 0.8, 0.1]
+    wild = [1.5, -0.5, 0, 0, 0.2, 0, 1.2, 0, 0.3, -0.2, 0.4, 0.4, 0.4, 0, 0, 0.2, 0.2, 0.2, 0.5, 0]
+    filters = [dict(type=1, color=0x80FF2010, mode=3), dict(type=1, color=0xFF2040C0, mode=13), dict(type=1, color=0x6010A020, mode=5),
+               dict(type=1, color=0xC0C0C000, mode=14), dict(type=1, color=0xFF808080, mode=1), dict(type=1, color=0x40FFFFFF, mode=12),
+               dict(type=2, matrix=sat), dict(type=2, matrix=swap), dict(type=2, matrix=wild), dict(type=3), dict(type=4),
+               dict(type=1, color=0x90003366, mode=9)]
+    cell = size / 4
+    for k, cf in enumerate(filters):
+        cx, cy = (k % 4 + 0.5) * cell, (k // 4 + 0.5) * cell
+        p = _random_closed_path(rng, cx, cy, cell * 1.05, k)
+        alpha = 1.0 if k % 2 == 0 else float(rng.uniform(0.3, 0.9))
+        if k % 3 == 1:
+            sh = dict(type=2, p=(cx, cy, cell * 0.6, 0), tile=MIRROR, colors=[(1, 0.2, 0, 1), (0, 0.8, 0.3, 0.4), (0.1, 0, 1, 1)], stops=None)
+            s.draw_path(p, Paint(shader=sh, color_filter=cf, blend=14 if k % 2 else None))
+        elif k % 3 == 2:
+            s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), color_filter=cf, blur_radius=4.0, blur_style=1))
+        else:
+            s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), color_filter=cf))
+    return s

@@ -285,7 +285,12 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
             uint32_t cv = clip_entry_cover(out.e[k]);
             uint32_t galpha = paint->type == SKB_PAINT_IMAGE ? (paint->global_alpha & 0xFF) : 0xFFu;
             cv &= galpha;
-            if (cv) canvas[(size_t)y * W + x] = swap_rb(blend_cover_mode(swap_rb(canvas[(size_t)y * W + x]), swap_rb(paint_color(*paint, pool, none, x, y)), cv, paint_blend_mode(*paint)));
+            if (cv) {
+              uint32_t src = swap_rb(paint_color(*paint, pool, none, x, y));
+              if (cv != 255) src = alpha_mul_q(src, cv);
+              if (SKB_PAINT_CF_OFFSET(*paint)) src = apply_color_filter((const uint32_t*)pool + (SKB_PAINT_CF_OFFSET(*paint) - 1), src);
+              canvas[(size_t)y * W + x] = swap_rb(porter_duff(src, swap_rb(canvas[(size_t)y * W + x]), paint_blend_mode(*paint)));
+            }
           }
         }
       }
