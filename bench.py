@@ -35,6 +35,7 @@ import numpy as np  # noqa: E402
 NCU_TRAFFIC = {("c1", "k_walk"): 33462272 + 116994304, ("c1", "k_cover"): 146301696 + 123251456,
                ("c1", "k_fine"): 235771648 + 47252224}
 
+E2E_LANES = 4      # surfaces (and host threads) the end-to-end loop keeps in flight
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
 
@@ -189,50 +190,72 @@ def run_ours(args):
     barrier()
     ms_e2e_serial = f0.elapsed_time(f1) / args.steps
 
-    # ---- end to end with two frames in flight: every step still uploads its display list from
-    # pinned memory, renders, and reads its canvas back to pinned memory, but frames alternate
-    # between two surfaces (two streams), so the read-back of frame i overlaps the rendering of
-    # frame i+1 — what an application streaming frames through the backend does
-    surf_b = dev.create_surface(W, H)
-    stream_b = torch.cuda.ExternalStream(surf_b.stream(), device=torch.device("cuda", local_rank))
-    out_b = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-    lanes = [(surf, out_np), (surf_b, out_b.numpy())]
+    # ---- end to end with several frames in flight: every step still uploads its display list from pinned
+    # memory, renders, and reads its canvas back to pinned memory, but steps are dealt round-robin to E2E_LANES
+    # surfaces, each driven by its own host thread on its own stream, so that the read-back of one frame
+    # overlaps the rendering of others and the latency-bound sweep of one frame shares the SMs with the
+    # coverage / fine passes of another — what an application streaming frames through the backend does
+    import threading
+    lanes = [(surf, out_np)]
+    for _ in range(E2E_LANES - 1):
+        sf = dev.create_surface(W, H)
+        lanes.append((sf, torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy()))
+    lane_streams = [torch.cuda.ExternalStream(sf.stream(), device=torch.device("cuda", local_rank)) for sf, _ in lanes]
 
-    def upload(i):
-        sf, _ = lanes[i & 1]
-        sf.begin(True)                              # stream-ordered after that surface's previous read-back
-        sf.encode((dl_pinned.data_ptr(), len(dl)))
+    def run_e2e_lanes(n_steps, host_buffers=True):
+        def work(t):
+            sf, out = lanes[t]
+            for _ in range(t, n_steps, E2E_LANES):
+                sf.begin(True)
+                if host_buffers:
+                    sf.encode((dl_pinned.data_ptr(), len(dl)))
+                sf.flush()
+                if host_buffers:
+                    sf.read_pixels_async(out)   # stream-ordered: the next begin() on this surface waits for it
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(E2E_LANES)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
 
-    def step_e2e_pipelined(i):
-        upload(i + 1)                               # next frame's display list goes up while this one renders
-        sf, out = lanes[i & 1]
-        sf.flush()
-        sf.read_pixels_async(out)
-
-    upload(0)
-    for i in range(4):
-        step_e2e_pipelined(i)
-    surf.sync()
-    surf_b.sync()
+    run_e2e_lanes(2 * E2E_LANES)
+    for sf, _ in lanes:
+        sf.sync()
     barrier()
-    p0, p1, pb = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event())
-    p0.record(stream)
-    for i in range(4, 4 + args.steps):
-        step_e2e_pipelined(i)
-    pb.record(stream_b)
-    stream.wait_event(pb)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)                               # every stream is idle here
+    run_e2e_lanes(args.steps)
+    for st_ in lane_streams[1:]:                    # p1 after the last frame of every lane
+        ev = torch.cuda.Event()
+        ev.record(st_)
+        stream.wait_event(ev)
     p1.record(stream)
     barrier()
     ms_e2e = p0.elapsed_time(p1) / args.steps
-    if not np.array_equal(lanes[0][1], lanes[1][1]):
-        raise SystemExit("pipelined frames differ")
-    surf_b.close()
+    # the same lanes with the display list resident and no read-back (for comparison with `value`, which is
+    # measured one frame at a time so that its per-stage timings mean something)
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for sf, _ in lanes:
+        sf.sync()
+    q0.record(stream)
+    run_e2e_lanes(args.steps, host_buffers=False)
+    for st_ in lane_streams[1:]:
+        ev = torch.cuda.Event()
+        ev.record(st_)
+        stream.wait_event(ev)
+    q1.record(stream)
+    barrier()
+    ms_resident_lanes = q0.elapsed_time(q1) / args.steps
+    for sf, out in lanes[1:]:
+        if not np.array_equal(out, lanes[0][1]):
+            raise SystemExit("frames rendered on different surfaces differ")
+        sf.close()
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
-        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_serial], device="cuda")
+        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_serial, ms_resident_lanes], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_resident, ms_e2e, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2])
+        ms_resident, ms_e2e, ms_e2e_serial, ms_resident_lanes = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         mpix = W * H / 1e6
@@ -255,10 +278,14 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc, "canvases_per_step": world, "paths_per_canvas": n_paths,
                        "l2": "working set per step (records + A8 masks + canvas, ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
-                       "partition": "by canvas" if world > 1 else "single"},
+                       "partition": "by canvas" if world > 1 else "single",
+                       "frames_in_flight": "value: 1 (so that the per-stage timings are those of a frame); e2e: %d" % E2E_LANES},
+            "resident_frames_in_flight": {"frames_in_flight": E2E_LANES, "ms_per_step": round(ms_resident_lanes, 4),
+                                          "value": round(world * W * H / 1e6 / (ms_resident_lanes / 1e3), 2)},
             "paths_per_s": round(world * n_paths / (ms_resident / 1e3), 1),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": len(dl),
-                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(ms_e2e, 4), "frames_in_flight": 2,
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(ms_e2e, 4), "frames_in_flight": E2E_LANES,
+                    "host_threads": E2E_LANES,
                     "one_frame_at_a_time": {"value": round(world * mpix / (ms_e2e_serial / 1e3), 2),
                                             "ms_per_step": round(ms_e2e_serial, 4)}},
             "gpu_launches": int(launches),

@@ -23,8 +23,9 @@
  *
  * Pixels are premultiplied RGBA8 (bytes R,G,B,A), the configuration the
  * reference's Bitmap(AlphaType::kPremul_AlphaType, ColorType::kRGBA) has.
- * Threading: like GPUContext, one thread drives a device and its surfaces
- * (include/skity/gpu/gpu_context.hpp:65,101).
+ * Threading: like GPUContext (include/skity/gpu/gpu_context.hpp:65,101) a surface is driven by one thread at a
+ * time; different surfaces of a device may be driven by different threads (each has its own stream and arenas,
+ * the last-error string is per thread).
  */
 #ifndef SKB_H
 #define SKB_H
