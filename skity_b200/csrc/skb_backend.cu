@@ -745,25 +745,20 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     SpanSide ld, od, la, oa;
     clip_row_step(st, c.pool, row, x, ld, od, la, oa);
     if (x < x_out) continue;
-    if ((ld.cover | od.cover | la.cover | oa.cover) == 0 && !(mode == 0 && st.cur_zero_d)) continue;
+    if (mode == 0 ? !(ld.present | od.present | la.present | oa.present) : (ld.cover | od.cover | la.cover | oa.cover) == 0) continue;
     const uint32_t* clist = nullptr;
-    int n_c = 0;
+    const uint32_t* cprev = nullptr;
+    int n_c = 0, n_p = 0;
     if (c_row && x >= par.rx0 && x < par.rx0 + par.rw) {
       clist = c_row + (size_t)(x - par.rx0) * SKB_CLIP_MAXE;
       while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
     }
-    if (mode == 0 && !wrote) {  // spans that cover nothing but still make the state count as a clip
-      const uint32_t* cprev = nullptr;
-      int n_p = 0;
-      if (c_row && x - 1 >= par.rx0 && x - 1 < par.rx0 + par.rw) {
-        cprev = c_row + (size_t)(x - 1 - par.rx0) * SKB_CLIP_MAXE;
-        while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
-      }
-      const bool starts = (od.cover && od.start == x) || (oa.cover && oa.start == x);
-      wrote = clip_ghost_span(st.cur_zero_d, starts, clipped, cprev, n_p, clist, n_c);
+    if (mode == 0 && c_row && x - 1 >= par.rx0 && x - 1 < par.rx0 + par.rw) {  // parent spans ending here (zero-length sub-spans)
+      cprev = c_row + (size_t)(x - 1 - par.rx0) * SKB_CLIP_MAXE;
+      while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
     }
     ClipOut out;
-    clip_combine(ld, od, la, oa, clist, n_c, clipped, cap, out);
+    clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, cap, mode == 0, out);
     over |= out.overflow;
     if (out.n == 0) continue;
     if (mode == 0) {

@@ -30,14 +30,24 @@ namespace skb {
                                  // by one thread that re-reads the records for every pixel
 #define SKB_CLIP_START_BIAS (1 << 22)
 
-// A clip-state entry: coverage (bits 0-7, never 0) | (span start x + bias) << 8.  0 = no entry.
+// A clip-state entry: coverage (bits 0-7) | (span start x + bias) << 8 | marker flag (bit 31).  0 = no entry.
+// Besides the spans that clip something, a state keeps the spans the reference keeps although they cover nothing —
+// they make HasClip() true (a non-empty span list) and they breed more of their kind in nested clips:
+//   * spans of coverage 0 (a directly emitted span whose coverage came out as 0; FindSpan keeps min(.., 0)),
+//     stored like any span;
+//   * zero-LENGTH spans, which FindSpan makes when a parent span ends exactly where an own span starts
+//     (`clip.x + clip.len == span.x`, sw_canvas.cc:228-241) and which it hands down whenever an own span covers or
+//     ends at their position: stored as a MARKER entry at that pixel.
+#define SKB_CLIP_MARKER 0x80000000u
 SKB_HD uint32_t clip_entry(int start, uint32_t cover) { return cover | ((uint32_t)(start + SKB_CLIP_START_BIAS) << 8); }
-SKB_HD int clip_entry_start(uint32_t e) { return (int)(e >> 8) - SKB_CLIP_START_BIAS; }
+SKB_HD int clip_entry_start(uint32_t e) { return (int)((e & ~SKB_CLIP_MARKER) >> 8) - SKB_CLIP_START_BIAS; }
 SKB_HD uint32_t clip_entry_cover(uint32_t e) { return e & 0xFF; }
+SKB_HD bool clip_entry_is_marker(uint32_t e) { return (e & SKB_CLIP_MARKER) != 0; }
 
 struct SpanSide {   // one span on the S side at the current pixel
-  uint32_t cover;   // 0 = absent
+  uint32_t cover;   // may be 0 for a directly emitted span (see above)
   int start;
+  bool present;
 };
 
 // Ordered output of one pixel.
@@ -47,59 +57,58 @@ struct ClipOut {
   bool overflow;
 };
 
-SKB_HD void clip_out_push(ClipOut& o, int cap, int start, uint32_t cover) {
-  if (cover == 0) return;  // zero coverage never changes a pixel
+// keep_ghosts: building a clip state (spans that cover nothing are kept); otherwise a clipped draw (dropped).
+SKB_HD void clip_out_push(ClipOut& o, int cap, bool keep_ghosts, int start, uint32_t cover, bool marker) {
+  if (!keep_ghosts && (cover == 0 || marker)) return;
   if (o.n >= cap) { o.overflow = true; return; }
-  o.e[o.n++] = clip_entry(start, cover);
+  o.e[o.n++] = clip_entry(start, cover) | (marker ? SKB_CLIP_MARKER : 0u);
 }
 
-// Combine the S side of a pixel with the clip spans covering it (FindSpan, all three cases).
+// Combine the S side of pixel x with the clip spans covering it (FindSpan, all three cases).
 //   own   : S contains the pixel            -> every C gives min(cover), sub-span starts at max(S.x, C.x)
 //   left  : S ends exactly at the pixel     -> only C with C.x > S.x (the `+ 1`), sub-span starts at C.x
+//   C a zero-length marker here             -> a marker again, for an own and for a left S alike
+//   C ends exactly here, S starts here      -> a new marker (c_prev = entries of pixel x - 1)
 // Order: spans in emission order (direct before accumulated, left before own), C in list order.
-SKB_HDN void clip_combine(const SpanSide& left_d, const SpanSide& own_d, const SpanSide& left_a, const SpanSide& own_a,
-                          const uint32_t* clist, int n_c, bool clipped, int cap, ClipOut& out) {
+SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, const SpanSide& left_a, const SpanSide& own_a,
+                          const uint32_t* clist, int n_c, const uint32_t* c_prev, int n_prev, bool clipped, int cap,
+                          bool keep_ghosts, ClipOut& out) {
   out.n = 0;
   out.overflow = false;
   if (!clipped) {  // HasClip() false: the raster spans themselves
-    clip_out_push(out, cap, own_d.start, own_d.cover);
-    clip_out_push(out, cap, own_a.start, own_a.cover);
+    if (own_d.present) clip_out_push(out, cap, keep_ghosts, own_d.start, own_d.cover, false);
+    if (own_a.present) clip_out_push(out, cap, keep_ghosts, own_a.start, own_a.cover, false);
     return;
   }
   const SpanSide* seq[4] = {&left_d, &own_d, &left_a, &own_a};
   for (int k = 0; k < 4; k++) {
     const SpanSide& s = *seq[k];
-    if (s.cover == 0) continue;
+    if (!s.present) continue;
     const bool is_left = (k & 1) == 0;
+    if (!is_left && keep_ghosts && s.start == x) {
+      // parent spans that end exactly where this span starts
+      for (int i = 0; i < n_prev; i++) {
+        if (clip_entry_is_marker(c_prev[i])) continue;
+        bool continues = false;
+        for (int j = 0; j < n_c; j++) continues |= clist[j] == c_prev[i];
+        if (continues) continue;
+        const uint32_t pc = clip_entry_cover(c_prev[i]);
+        clip_out_push(out, cap, true, x, pc < s.cover ? pc : s.cover, true);
+      }
+    }
     for (int i = 0; i < n_c; i++) {
       const int cstart = clip_entry_start(clist[i]);
       const uint32_t ccover = clip_entry_cover(clist[i]);
       const uint32_t m = ccover < s.cover ? ccover : s.cover;
-      if (is_left) {
-        if (cstart > s.start) clip_out_push(out, cap, cstart, m);
+      if (clip_entry_is_marker(clist[i])) {
+        clip_out_push(out, cap, keep_ghosts, cstart, m, true);
+      } else if (is_left) {
+        if (cstart > s.start) clip_out_push(out, cap, keep_ghosts, cstart, m, false);
       } else {
-        clip_out_push(out, cap, cstart > s.start ? cstart : s.start, m);
+        clip_out_push(out, cap, keep_ghosts, cstart > s.start ? cstart : s.start, m, false);
       }
     }
   }
-}
-
-// Clip spans that cover nothing still count for SWCanvas::State::HasClip() (a non-empty span list,
-// sw_canvas.hpp), i.e. they decide whether later draws are clipped at all.  Two kinds arise at a pixel x while a
-// clip state is built: a directly emitted span of coverage 0 (kept by FindSpan with cover min(.., 0)), and the
-// zero-length sub-span FindSpan makes when a parent span ends exactly where an own span starts
-// (`clip.x + clip.len == span.x`, sw_canvas.cc:228-241).  `c_prev` / `c_cur` are the parent entries of pixels
-// x - 1 and x.
-SKB_HDN bool clip_ghost_span(bool zero_d, bool own_starts_here, bool clipped, const uint32_t* c_prev, int n_prev,
-                             const uint32_t* c_cur, int n_cur) {
-  if (zero_d && (!clipped || n_cur > 0)) return true;
-  if (!clipped || !own_starts_here) return false;
-  for (int i = 0; i < n_prev; i++) {
-    bool continues = false;
-    for (int j = 0; j < n_cur; j++) continues |= c_cur[j] == c_prev[i];
-    if (!continues) return true;
-  }
-  return false;
 }
 
 // Sweep state of one row.
@@ -110,8 +119,6 @@ struct ClipRowState {
   uint32_t prev_d, prev_a;
   int prev_d_start, prev_a_start;
   bool prev_d_ends;  // the direct span covering the previous pixel ends at the current pixel
-  bool cur_zero_d;   // the current pixel carries a directly emitted span whose coverage is 0 (it covers nothing,
-                     // but as a clip span it still makes HasClip() true)
 };
 
 // S side of pixel x of a row given its trapezoid records; advances the sweep state.
@@ -169,23 +176,26 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
   }
   const uint32_t a = acc > 255u ? 255u : acc;
   // spans ending at this pixel
+  left_d.present = st.prev_d_ends;
   left_d.cover = st.prev_d_ends ? st.prev_d : 0u;
   left_d.start = st.prev_d_start;
   const bool a_run_continues = a != 0 && a == st.prev_a;
   left_a.cover = (st.prev_a != 0 && !a_run_continues) ? st.prev_a : 0u;
+  left_a.present = left_a.cover != 0;
   left_a.start = st.prev_a_start;
   // spans covering this pixel
   own_d.cover = d;
+  own_d.present = d_touched;   // a directly emitted span exists here even when its coverage came out as 0
   own_d.start = d_start;
   own_a.cover = a;
+  own_a.present = a != 0;
   own_a.start = a_run_continues ? st.prev_a_start : x;
   // advance
   st.prev_d = d;
   st.prev_d_start = d_start;
-  st.prev_d_ends = d != 0 ? d_ends_next : false;
+  st.prev_d_ends = d_touched ? d_ends_next : false;
   st.prev_a = a;
   st.prev_a_start = own_a.start;
-  st.cur_zero_d = d_touched && d == 0;
 }
 
 // Accumulated coverage of pixel x from the prepared records (saturated), without touching the sweep state.
@@ -239,7 +249,6 @@ SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
   st.prev_d = st.prev_a = 0;
   st.prev_d_start = st.prev_a_start = 0;
   st.prev_d_ends = false;
-  st.cur_zero_d = false;
   if (row.y > (uint32_t)SKB_CLIP_RMAX) {
     st.n_prep = -1;
     return;

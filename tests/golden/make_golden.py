@@ -96,6 +96,9 @@ def golden_scenes():
     # span ends exactly where an own span starts
     out["clip_spans_off_surface_75"] = scene.scene_fuzz(9002)[0]
     out["clip_zero_length_span_532"] = scene.scene_fuzz(11012)[0]
+    # ... and such spans are handed down: here a third-level clip consists of one zero-length span inherited from
+    # the zero-length / zero-coverage spans of the second level
+    out["clip_inherited_ghost_span_354"] = scene.scene_fuzz(22152)[0]
     return out
 
 

@@ -260,18 +260,14 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
           clist = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - parent->rx0)) * SKB_CLIP_MAXE];
           while (n_c < SKB_CLIP_MAXE && clist[n_c]) n_c++;
         }
-        if (is_clip && !target->nonempty) {
-          const uint32_t* cprev = nullptr;
-          int n_p = 0;
-          if (clipped && x - 1 >= parent->rx0 && x - 1 < parent->rx0 + parent->rw && y >= parent->ry0 && y < parent->ry0 + parent->rh) {
-            cprev = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - 1 - parent->rx0)) * SKB_CLIP_MAXE];
-            while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
-          }
-          const bool starts = (od.cover && od.start == x) || (oa.cover && oa.start == x);
-          if (clip_ghost_span(st.cur_zero_d, starts, clipped, cprev, n_p, clist, n_c)) target->nonempty = true;
+        const uint32_t* cprev = nullptr;
+        int n_p = 0;
+        if (is_clip && clipped && x - 1 >= parent->rx0 && x - 1 < parent->rx0 + parent->rw && y >= parent->ry0 && y < parent->ry0 + parent->rh) {
+          cprev = &parent->entries[((size_t)(y - parent->ry0) * parent->rw + (x - 1 - parent->rx0)) * SKB_CLIP_MAXE];
+          while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
         }
         ClipOut out;
-        clip_combine(ld, od, la, oa, clist, n_c, clipped, o.kind == SKB_OP_CLIP ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, out);
+        clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, is_clip ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, is_clip, out);
         if (out.overflow) stats[0]++;
         if (out.n > stats[1]) stats[1] = out.n;
         if (o.kind == SKB_OP_CLIP) {
