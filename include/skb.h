@@ -106,6 +106,13 @@ SKB_API skb_result skb_surface_write_pixels(skb_surface surface, uint32_t x, uin
  * (SKB_SURFACE_CANVAS in include/skb_dl.h).  Valid until the next skb_frame_flush. */
 SKB_API skb_result skb_frame_read_surface(skb_surface surface, uint32_t index, void* dst, size_t stride);
 SKB_API skb_result skb_surface_device_ptr(skb_surface surface, void** out_ptr, size_t* out_pitch_bytes);
+/* One canvas rendered by several GPUs (bands, skb_surface_set_band) with the gather fused into the fine pass: the
+ * gathering process exports its canvas as a 64-byte CUDA IPC handle; every other process (one per GPU, same
+ * surface size) opens it, after which its fine pass stores the finished pixels of its band straight into the
+ * gathering GPU's canvas over NVLink (peer memory) instead of its own — no copy, no collective, only a barrier
+ * before the read-back.  NULL restores local stores. */
+SKB_API skb_result skb_surface_export_canvas(skb_surface surface, void* out_handle64);
+SKB_API skb_result skb_surface_set_remote_canvas(skb_surface surface, const void* handle64);
 SKB_API skb_result skb_surface_stream(skb_surface surface, void** out_cuda_stream);
 
 SKB_API skb_result skb_frame_get_stats(skb_surface surface, skb_frame_stats* out_stats);

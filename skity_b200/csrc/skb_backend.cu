@@ -48,6 +48,8 @@ struct SurfDesc {
   uint32_t row0, row1;  // rows this device renders (band), whole surface for temporaries
   uint32_t level;       // pass in which the surface is composited: after every surface its draws sample or are blurred from
   uint32_t pad;
+  uint8_t* px_out;      // where the fine pass stores the finished pixels: px, or the same canvas on ANOTHER GPU (peer
+                        // memory over NVLink) when the bands of one canvas are rendered by several devices
 };
 
 #define SKB_CMD_SOLID 0x80000000u
@@ -976,8 +978,9 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
       }
     }
   }
-  reinterpret_cast<uint4*>(prow)[0] = make_uint4(swap_rb(dst[0]), swap_rb(dst[1]), swap_rb(dst[2]), swap_rb(dst[3]));
-  reinterpret_cast<uint4*>(prow)[1] = make_uint4(swap_rb(dst[4]), swap_rb(dst[5]), swap_rb(dst[6]), swap_rb(dst[7]));
+  uint32_t* orow = reinterpret_cast<uint32_t*>(sd.px_out + (size_t)y * sd.pitch) + x0;
+  reinterpret_cast<uint4*>(orow)[0] = make_uint4(swap_rb(dst[0]), swap_rb(dst[1]), swap_rb(dst[2]), swap_rb(dst[3]));
+  reinterpret_cast<uint4*>(orow)[1] = make_uint4(swap_rb(dst[4]), swap_rb(dst[5]), swap_rb(dst[6]), swap_rb(dst[7]));
 }
 
 // -------------------------------------------------------------------- stage 7: blur
@@ -1234,6 +1237,7 @@ struct skb_surface_s {
   uint32_t* mapped_dev = nullptr;
   // canvas pixels (persistent)
   uint8_t* canvas = nullptr;
+  uint8_t* remote_canvas = nullptr;  // peer mapping of the same canvas on the gathering device (cudaIpcOpenMemHandle)
   uint32_t pitch = 0, tiles_x = 0, tiles_y = 0;
   // frame
   std::vector<uint8_t> host_dl;
@@ -1477,6 +1481,8 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->temp_px, temp_bytes + 256));
   surfs[0].px = s->canvas;
   for (uint32_t i = 1; i < h.n_surfaces; i++) surfs[i].px = (uint8_t*)s->temp_px.p + temp_off[i];
+  for (uint32_t i = 0; i < h.n_surfaces; i++) surfs[i].px_out = surfs[i].px;
+  if (s->remote_canvas) surfs[0].px_out = s->remote_canvas;
   if (temp_bytes) SKB_CUDA(cudaMemsetAsync(s->temp_px.p, 0, temp_bytes, st));
   const uint32_t n_tiles = tile_base[h.n_surfaces];
   S.n_tiles = n_tiles;
@@ -1975,6 +1981,7 @@ void skb_surface_destroy(skb_surface s) {
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
   for (Buf* b : bufs) buf_free(*b);
+  if (s->remote_canvas) cudaIpcCloseMemHandle(s->remote_canvas);
   if (s->canvas) cudaFree(s->canvas);
   if (s->mapped_host) cudaFreeHost(s->mapped_host);
   for (int i = 0; i < 12; i++)
@@ -2092,6 +2099,33 @@ skb_result skb_surface_read_pixels_async(skb_surface s, uint32_t x, uint32_t y, 
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
                              cudaMemcpyDeviceToHost, s->stream));
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_export_canvas(skb_surface s, void* handle64) {
+  if (!s || !handle64) return SKB_ERROR_INVALID_ARGUMENT;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI hands the IPC handle over as 64 bytes");
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  cudaIpcMemHandle_t hdl;
+  SKB_CUDA(cudaIpcGetMemHandle(&hdl, s->canvas));
+  memcpy(handle64, &hdl, 64);
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_set_remote_canvas(skb_surface s, const void* handle64) {
+  if (!s) return SKB_ERROR_INVALID_ARGUMENT;
+  SKB_CUDA(cudaSetDevice(s->dev->ordinal));
+  SKB_CUDA(cudaStreamSynchronize(s->stream));
+  if (s->remote_canvas) {
+    SKB_CUDA(cudaIpcCloseMemHandle(s->remote_canvas));
+    s->remote_canvas = nullptr;
+  }
+  if (!handle64) return SKB_SUCCESS;
+  cudaIpcMemHandle_t hdl;
+  memcpy(&hdl, handle64, 64);
+  void* p = nullptr;
+  SKB_CUDA(cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess));
+  s->remote_canvas = (uint8_t*)p;
   return SKB_SUCCESS;
 }
 

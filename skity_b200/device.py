@@ -64,6 +64,8 @@ def lib():
         L.skb_surface_write_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_frame_read_surface.argtypes = [vp, u32, vp, sz]
         L.skb_surface_device_ptr.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(sz)]
+        L.skb_surface_export_canvas.argtypes = [vp, ctypes.c_char_p]
+        L.skb_surface_set_remote_canvas.argtypes = [vp, ctypes.c_char_p]
         L.skb_surface_stream.argtypes = [vp, ctypes.POINTER(vp)]
         L.skb_frame_get_stats.argtypes = [vp, ctypes.POINTER(FrameStats)]
         L.skb_debug_read_coverage.argtypes = [vp, u32, i32, i32, u32, u32, vp, vp]
@@ -158,6 +160,16 @@ class Surface:
             out = np.empty((height, width, 4), dtype=np.uint8)
         _check(lib().skb_frame_read_surface(self._h, index, out.ctypes.data, width * 4), "skb_frame_read_surface")
         return out
+
+    def export_canvas(self):
+        """64-byte CUDA IPC handle of the canvas, for the other GPUs' fine passes to store their bands into."""
+        buf = ctypes.create_string_buffer(64)
+        _check(lib().skb_surface_export_canvas(self._h, buf), "skb_surface_export_canvas")
+        return buf.raw
+
+    def set_remote_canvas(self, handle):
+        """Store this surface's finished band into the canvas `handle` names (None: back to local stores)."""
+        _check(lib().skb_surface_set_remote_canvas(self._h, handle), "skb_surface_set_remote_canvas")
 
     def device_ptr(self):
         p, pitch = ctypes.c_void_p(), ctypes.c_size_t()

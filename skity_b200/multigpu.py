@@ -76,3 +76,13 @@ def host_band_tensor_factory(image):
     def f(y0, y1):
         return flat[y0 * row:y1 * row]
     return f
+
+
+def fuse_gather_into_fine_pass(surface, rank, dist, root=0):
+    """Band split with the gather fused into the fine pass: `root` exports its canvas, every other rank maps it
+    (CUDA IPC, peer memory over NVLink) and from then on stores the finished pixels of its band there.  After each
+    frame a barrier is all that is left of the gather.  Collective: every rank must call it."""
+    box = [surface.export_canvas() if rank == root else None]
+    dist.broadcast_object_list(box, src=root)
+    if rank != root:
+        surface.set_remote_canvas(box[0])

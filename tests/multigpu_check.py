@@ -67,5 +67,30 @@ if rank == 0:
           f"gather {min(gather):.2f} ms ({(H - bands[0][1]) * surf.device_ptr()[1] / 1e6 / min(gather):.1f} GB/s into rank 0) "
           f"bands==single-GPU: {ok}", flush=True)
     assert ok
+# ---- the same split with the gather fused into the fine pass (peer-memory stores, no copy)
+dist.barrier()
+surf.begin(True)            # rank 0's canvas is cleared by rank 0; the others' clears are local
+surf.sync()
+dist.barrier()
+multigpu.fuse_gather_into_fine_pass(surf, rank, dist)
+fused = []
+for it in range(4):
+    surf.begin(True)
+    surf.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    surf.flush()
+    surf.sync()
+    dist.barrier()          # all bands are in rank 0's canvas
+    fused.append((time.perf_counter() - t0) * 1e3)
+if rank == 0:
+    got2 = surf.read_pixels()
+    ok2 = bool(np.array_equal(got2, want))
+    print(f"fused gather: frame + barrier {min(fused[1:]):.2f} ms wall (separate: render {render_ms:.2f} + gather {min(gather):.2f}), "
+          f"canvas==single-GPU: {ok2}", flush=True)
+    assert ok2
+if rank != 0:
+    surf.set_remote_canvas(None)
 dist.barrier()
 dist.destroy_process_group()
