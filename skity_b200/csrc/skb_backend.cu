@@ -300,7 +300,10 @@ __device__ __forceinline__ void walk_setup_sink(const WalkArgs& a, uint32_t op, 
   sink_init(sink);
 }
 
-__global__ void __launch_bounds__(64) k_walk(WalkArgs a, int lane_stride) {
+#ifndef WALK_BLOCK
+#define WALK_BLOCK 64
+#endif
+__global__ void __launch_bounds__(WALK_BLOCK) k_walk(WalkArgs a, int lane_stride) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid % (uint32_t)lane_stride) return;
   const uint32_t i = tid / (uint32_t)lane_stride;
@@ -347,10 +350,18 @@ struct CoverArgs {
 #define SKB_ITEM_ZERO 512u
 #define SKB_ITEM_PLANE_MASK 255u
 
-#define COVER_WARPS 4
+#ifndef COVER_WARPS
+#define COVER_WARPS 1
+#endif
+#ifndef COVER_CW
 #define COVER_CW 128                 // pixels per chunk of a tile row (8 tiles) held in shared memory
-#define COVER_ND 128                 // trapezoid records summarised per pass
-#define COVER_UNIT 4                 // edge pixels evaluated per work unit
+#endif
+#ifndef COVER_ND
+#define COVER_ND 64                  // trapezoid records summarised per pass
+#endif
+#ifndef COVER_UNIT
+#define COVER_UNIT 2                 // edge pixels evaluated per work unit
+#endif
 
 struct alignas(16) CoverWarpSmem {
   uint32_t D[16][COVER_CW / 4];      // directly emitted coverage, one byte per pixel
@@ -852,7 +863,9 @@ struct FineArgs {
   const uint8_t* mask[SKB_CLIP_PLANES];
   const uint8_t* zmask;
 };
-#define FINE_WARPS 4
+#ifndef FINE_WARPS
+#define FINE_WARPS 2
+#endif
 #define FINE_SORT_CAP 256
 
 __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
@@ -1613,7 +1626,7 @@ static skb_result run_frame(skb_surface s) {
       const uint64_t want_threads = (uint64_t)s->dev->sm_count * 32 * 32;
       while (lane_stride < 8 && (uint64_t)n_ops * lane_stride * 2 <= want_threads) lane_stride *= 2;
       if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
-      k_walk<<<cdiv((uint64_t)n_ops * lane_stride, 64), 64, 0, st>>>(wa, lane_stride);
+      k_walk<<<cdiv((uint64_t)n_ops * lane_stride, WALK_BLOCK), WALK_BLOCK, 0, st>>>(wa, lane_stride);
       launches++;
     }
     uint32_t hc[2];
