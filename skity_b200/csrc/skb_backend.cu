@@ -1032,12 +1032,27 @@ __global__ void k_blur_style(SurfDesc raw, SurfDesc dst, uint32_t style, uint32_
 }
 
 
-// Horizontal pass: one CTA per (job, row).  The extended row (n + 2m + 1 samples x 4 channels)
-// lives in shared memory; two block-wide scans produce U.
-__global__ void __launch_bounds__(256) k_blur_h(const BlurJob* jobs, const uint32_t* job_row_base, uint32_t n_jobs,
-                                                const SurfDesc* surfs, uint32_t first_row) {
-  extern __shared__ uint32_t sm[];  // [4][len] then per-thread partials
-  const uint32_t grow = first_row + blockIdx.x;
+// Horizontal pass: one WARP per (job, row).  Each lane owns a run of consecutive samples of the extended row
+// (n + 2m + 1 samples): it sums them (T), the lane totals are scanned with shuffles, it then builds its part of U
+// (prefix of T) in shared memory, the totals are scanned again; the output loop reads U at the three positions.
+// No block-wide barrier: a block is BLUR_H_WARPS independent warps sharing the dynamic shared memory.
+#define BLUR_H_WARPS 2
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  return inc - v;
+}
+__global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* jobs, const uint32_t* job_row_base, uint32_t n_jobs,
+                                                              const SurfDesc* surfs, uint32_t first_row, uint32_t end_row,
+                                                              uint32_t max_len) {
+  extern __shared__ uint32_t sm[];  // per warp: U[4][max_len]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t grow = first_row + blockIdx.x * BLUR_H_WARPS + wib;
+  if (grow >= end_row) return;
   const uint32_t job = find_interval(job_row_base, n_jobs, grow);
   const BlurJob jb = jobs[job];
   const SurfDesc S = surfs[jb.src], D = surfs[jb.dst];
@@ -1047,86 +1062,60 @@ __global__ void __launch_bounds__(256) k_blur_h(const BlurJob* jobs, const uint3
   uint32_t* drow = reinterpret_cast<uint32_t*>(D.px + (size_t)y * D.pitch);
   int r = jb.radius > 254 ? 254 : jb.radius;
   if (r <= 1) {
-    for (int x = threadIdx.x; x < n; x += blockDim.x) drow[x] = srow[x];
+    for (int x = lane; x < n; x += 32) drow[x] = srow[x];
     return;
   }
   const int m = r + 1;
   const int len = n + 2 * m + 1;  // extended index j = k - m for k in [0, len): j in [-m, n+m]
-  uint32_t* U = sm;                // U[c*len + k], exclusive double prefix
-  __shared__ uint32_t part[4][256];
-  const int T = blockDim.x;
-  const int chunk = (len + T - 1) / T;
-  const int k0 = min((int)threadIdx.x * chunk, len), k1 = min(k0 + chunk, len);
-  // pass 1: T (exclusive prefix of e) into U[]
-  uint32_t acc[4] = {0, 0, 0, 0};
-  for (int k = k0; k < k1; k++) {
+  uint4* U = reinterpret_cast<uint4*>(sm) + (size_t)wib * max_len;  // U[k] = the four channels' exclusive double prefix
+  const int chunk = (len + 31) / 32;
+  const int k0 = min(lane * chunk, len), k1 = min(k0 + chunk, len);
+  auto sample = [&](int k) -> uint32_t {
     int j = k - m;
     j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
-    uint32_t px = srow[j];
+    return srow[j];
+  };
+  // T: totals of my run, scanned
+  uint32_t acc[4] = {0, 0, 0, 0};
+  for (int k = k0; k < k1; k++) {
+    const uint32_t px = sample(k);
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] += (px >> (8 * c)) & 0xFF;
+  }
+  uint32_t t_off[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) t_off[c] = warp_excl_scan(acc[c], lane);
+  // U: exclusive prefix of T over my run, totals scanned, offsets added
+  uint32_t tv[4], ua[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int c = 0; c < 4; c++) tv[c] = t_off[c];
+  for (int k = k0; k < k1; k++) {
+    const uint32_t px = sample(k);
+    U[k] = make_uint4(ua[0], ua[1], ua[2], ua[3]);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      U[c * len + k] = acc[c];
-      acc[c] += (px >> (8 * c)) & 0xFF;
+      ua[c] += tv[c];                       // U[k+1] = U[k] + T[k]
+      tv[c] += (px >> (8 * c)) & 0xFF;      // T[k+1] = T[k] + e[k]
     }
   }
-  for (int pass = 0; pass < 2; pass++) {
+  uint32_t u_off[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) part[c][threadIdx.x] = acc[c];
-    __syncthreads();
-    // exclusive scan of the per-thread totals (256 values per channel) by warp 0..3, one channel each
-    if (threadIdx.x < 128) {
-      const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      uint32_t carry = 0;
-      for (int base = 0; base < T; base += 32) {
-        uint32_t v = part[c][base + lane];
-        uint32_t inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += t;
-        }
-        part[c][base + lane] = carry + inc - v;
-        carry += __shfl_sync(0xffffffffu, inc, 31);
-      }
-    }
-    __syncthreads();
-    uint32_t off[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) off[c] = part[c][threadIdx.x];
-    __syncthreads();
-    if (pass == 0) {
-      // finalise T, then turn it into U (exclusive prefix of T) chunk-locally
-#pragma unroll
-      for (int c = 0; c < 4; c++) acc[c] = 0;
-      for (int k = k0; k < k1; k++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          uint32_t tv = U[c * len + k] + off[c];
-          U[c * len + k] = acc[c];
-          acc[c] += tv;
-        }
-      }
-    } else {
-      for (int k = k0; k < k1; k++) {
-#pragma unroll
-        for (int c = 0; c < 4; c++) U[c * len + k] += off[c];
-      }
-    }
+  for (int c = 0; c < 4; c++) u_off[c] = warp_excl_scan(ua[c], lane);
+  for (int k = k0; k < k1; k++) {
+    uint4 v = U[k];
+    U[k] = make_uint4(v.x + u_off[0], v.y + u_off[1], v.z + u_off[2], v.w + u_off[3]);
   }
-  __syncthreads();
+  __syncwarp();
   uint32_t mul;
   int shr;
   blur_mul_shr(r, &mul, &shr);
-  for (int x = threadIdx.x; x < n; x += blockDim.x) {
+  for (int x = lane; x < n; x += 32) {
     // extended index j maps to k = j + m;  U[j] here means prefix over samples < j
-    uint32_t out = 0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const uint32_t* Uc = U + c * len;
-      uint32_t sum = Uc[x + m + 1 + m] - 2u * Uc[x + 1 + m] + Uc[x - m + 1 + m];
-      out |= (uint32_t)(uint8_t)(((uint64_t)sum * mul) >> shr) << (8 * c);
-    }
-    drow[x] = out;
+    const uint4 ul = U[x + m + 1 + m], um = U[x + 1 + m], ug = U[x - m + 1 + m];
+    const uint32_t s0 = ul.x - 2u * um.x + ug.x, s1 = ul.y - 2u * um.y + ug.y;
+    const uint32_t s2 = ul.z - 2u * um.z + ug.z, s3 = ul.w - 2u * um.w + ug.w;
+    drow[x] = (uint32_t)(uint8_t)(((uint64_t)s0 * mul) >> shr) | ((uint32_t)(uint8_t)(((uint64_t)s1 * mul) >> shr) << 8) |
+              ((uint32_t)(uint8_t)(((uint64_t)s2 * mul) >> shr) << 16) | ((uint32_t)(uint8_t)(((uint64_t)s3 * mul) >> shr) << 24);
   }
 }
 
@@ -1805,6 +1794,7 @@ static skb_result run_frame(skb_surface s) {
   std::vector<uint32_t> rowb(nj + 1, 0), colb(nj + 1, 0);
   std::vector<const uint8_t*> tmp_ptrs(nj);
   size_t blur_smem = 0;
+  uint32_t blur_max_len = 0;
   if (nj) {
     size_t max_len = 0, tmp_bytes = 0;
     std::vector<size_t> tmp_off(nj);
@@ -1817,7 +1807,8 @@ static skb_result run_frame(skb_surface s) {
       tmp_off[i] = tmp_bytes;
       tmp_bytes += (size_t)d.pitch * d.tiles_y * SKB_TILE;
     }
-    blur_smem = max_len * 16;
+    blur_max_len = (uint32_t)max_len;
+    blur_smem = max_len * 16 * BLUR_H_WARPS;
     if (blur_smem > 200 * 1024) {
       set_error("blur: surface too wide for the shared-memory row scan");
       return SKB_ERROR_UNSUPPORTED;
@@ -1859,8 +1850,9 @@ static skb_result run_frame(skb_surface s) {
     uint32_t j1 = j0;
     while (j1 < nj && surfs[jobs[j1].dst].level == level) j1++;
     if (j1 > j0) {
-      k_blur_h<<<rowb[j1] - rowb[j0], 256, blur_smem, st>>>((const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj,
-                                                             (const SurfDesc*)s->scan_tmp.p, rowb[j0]);
+      k_blur_h<<<cdiv(rowb[j1] - rowb[j0], BLUR_H_WARPS), BLUR_H_WARPS * 32, blur_smem, st>>>(
+          (const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj, (const SurfDesc*)s->scan_tmp.p, rowb[j0], rowb[j1],
+          blur_max_len);
       launches++;
       // radius <= 1: the H kernel copied src into scratch; finish with a plain copy into dst
       for (uint32_t i = j0; i < j1; i++) {
