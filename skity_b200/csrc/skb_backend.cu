@@ -870,6 +870,9 @@ struct FineArgs {
 
 __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
   __shared__ uint2 s_cmd[FINE_WARPS][FINE_SORT_CAP];
+  __shared__ uint8_t s_requant[256];  // the nearest sampler's u8 -> float -> u8 round trip, tabulated once per block
+  for (int i = threadIdx.x; i < 256; i += FINE_WARPS * 32) s_requant[i] = (uint8_t)requant((uint32_t)i);
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tile = a.tile_begin + blockIdx.x * FINE_WARPS + warp;
   if (tile >= a.tile_end) return;
@@ -983,7 +986,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
         cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
         if (cv || (touched && zmode)) {
           // BrushH: colour, scaled by the coverage, colour filter, blend (sw_span_brush.cc:108-133)
-          uint32_t src = swap_rb(paint_color(pt, a.stops, img, x0 + j, y));
+          uint32_t src = swap_rb(paint_color(pt, a.stops, img, x0 + j, y, s_requant));
           if (cv != 255) src = alpha_mul_q(src, cv);
           if (cf) src = apply_color_filter(cf, src);
           dst[j] = porter_duff(src, dst[j], mode);

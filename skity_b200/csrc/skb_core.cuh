@@ -951,7 +951,9 @@ struct SurfaceView { const uint8_t* px; uint32_t w, h, pitch; };  // pitch in by
 // Solid sw_span_brush.cc:140-152, Linear :312-320, Sweep :337-354, Radial :371-379,
 // Pixmap :569-579 + bitmap_sampler.cc:26-40,85-108.
 // `img` is the surface an IMAGE paint samples (ignored by the other paint types).
-SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const SurfaceView& img, int x, int y) {
+// `requant_lut` (optional): requant() of every byte, tabulated by the caller.
+SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const SurfaceView& img, int x, int y,
+                             const uint8_t* requant_lut = nullptr) {
   if (p.type == SKB_PAINT_SOLID) return color4f_to_pm_word(p.color[0], p.color[1], p.color[2], p.color[3]);
   float fxc = x + 0.5f, fyc = y + 0.5f;
   float u = fxc * p.m[0] + fyc * p.m[1] + p.m[2];
@@ -1018,8 +1020,18 @@ SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const Sur
       if (ix > s.w - 1) ix = s.w - 1;
       if (iy > s.h - 1) iy = s.h - 1;
       const uint8_t* t = s.px + (size_t)iy * s.pitch + (size_t)ix * 4;
-      uint32_t r = requant(t[0]), g = requant(t[1]), b = requant(t[2]);
-      const uint32_t a = requant(t[3]);
+      uint32_t r, g, b, a;
+      if (requant_lut) {
+        r = requant_lut[t[0]];
+        g = requant_lut[t[1]];
+        b = requant_lut[t[2]];
+        a = requant_lut[t[3]];
+      } else {
+        r = requant(t[0]);
+        g = requant(t[1]);
+        b = requant(t[2]);
+        a = requant(t[3]);
+      }
       // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
       if ((p.tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
         r = mul_div_255_round(r, a);
