@@ -7,7 +7,9 @@
  * load it.  It is PINNED: tests/test_oracle_pinning.py checks it bit-for-bit
  * against the reference's own compiled backend (oracle/_ref, built from the
  * unmodified sources by oracle/build_ref.py) on spans, pixels and blur, and
- * against the golden vectors committed under tests/golden/.
+ * against the golden vectors committed under tests/golden/.  One exception: ClipOp::kDifference (spans_subtract,
+ * the merge in clip_refine) is restated but UNPINNED — the reference's result depends on std::sort's order of
+ * equal keys, qsort's differs on some scenes; the CUDA backend refuses difference clips.
  *
  * Every function cites the reference file:line it restates (paths relative to
  * the reference root).  Arithmetic notes that matter for bit-exactness:
