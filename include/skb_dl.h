@@ -53,6 +53,11 @@ typedef struct skb_dl_header {
  * 1..N: all canvases share every launch, which is what makes many small canvases efficient. */
 #define SKB_SURFACE_CANVAS 1u
 
+/* skb_dl_surface.flags */
+#define SKB_SURFACE_IMAGE 2u  /* an application image (Image::MakeImage of a Pixmap): its pixels travel in the display
+                                 list, `reserved` = byte offset from the start of the list of width*height RGBA8 pixels
+                                 (the Colors Bitmap::GetPixel returns, src/graphic/bitmap.cc:25-50, as R,G,B,A bytes) */
+
 typedef struct skb_dl_surface {
   uint32_t width;
   uint32_t height;
@@ -140,9 +145,15 @@ enum skb_dl_paint_type {
 #define SKB_PAINT_HAS_STOPS(p) ((p).has_stops & 1u)
 #define SKB_PAINT_CF_OFFSET(p) ((p).has_stops >> 8) /* 0 = none, else 1 + word offset */
 
-/* IMAGE paints: the sampled surface holds unpremultiplied pixels (PixmapBrush premultiplies after sampling,
- * sw_span_brush.cc:573-576) — ORed into tile_mode */
+/* IMAGE paints, ORed into tile_mode (whose low nibble is the x tile mode):
+ *   UNPREMUL  the sampled surface holds unpremultiplied pixels (PixmapBrush premultiplies after sampling,
+ *             sw_span_brush.cc:573-576)
+ *   LINEAR    FilterMode::kLinear (BitmapSampler::SampleUnitLinear, bitmap_sampler.cc:44-83); cubic resampling
+ *             falls back to it in the reference (:96-99)
+ *   YMODE     bits 4-7 hold the y tile mode (otherwise it equals the x mode) */
 #define SKB_PAINT_IMAGE_UNPREMUL 0x100u
+#define SKB_PAINT_IMAGE_LINEAR 0x200u
+#define SKB_PAINT_IMAGE_YMODE 0x400u
 
 typedef struct skb_dl_paint {
   uint32_t type;

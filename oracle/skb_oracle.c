@@ -1162,6 +1162,54 @@ static inline uint32_t requant(uint32_t c) {
 
 /* SWSpanBrush colour for one pixel (premultiplied, register layout) —
  * Solid :140-152, Linear :312-320, Sweep :337-354, Radial :371-379, Pixmap :569-579 + bitmap_sampler.cc:26-40,85-108 */
+/* BitmapSampler::GetColor — src/graphic/bitmap_sampler.cc:11-108 ; PixmapBrush::CalculateColor —
+ * sw_span_brush.cc:569-579 */
+static float remap_tile(float t, uint32_t mode) { /* RemapFloatTile :12-23 */
+  if (mode == 0) t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+  else if (mode == 1) t = t - floorf(t);
+  else if (mode == 2) {
+    float t1 = t - 1;
+    float t2 = t1 - 2 * floor(t1 * 0.5) - 1;
+    t = fabsf(t2);
+  }
+  return t;
+}
+static const uint8_t* image_texel(const surface* s, float fx_, float fy_) { /* SampleXY :26-34 */
+  uint32_t ix = (uint32_t)(long long)fx_, iy = (uint32_t)(long long)fy_; /* glm::clamp<uint32_t>(float, ...) on x86-64 */
+  if (ix > s->w - 1) ix = s->w - 1;
+  if (iy > s->h - 1) iy = s->h - 1;
+  return s->px + ((size_t)iy * s->w + ix) * 4;
+}
+static uint32_t sample_image(const skb_dl_paint* p, const surface* s, float u, float v) {
+  uint32_t xmode = p->tile_mode & 0xF;
+  uint32_t ymode = (p->tile_mode & SKB_PAINT_IMAGE_YMODE) ? ((p->tile_mode >> 4) & 0xF) : xmode;
+  if ((xmode == 3 && (u < 0.0 || u >= 1.0)) || (ymode == 3 && (v < 0.0 || v >= 1.0))) return 0;
+  u = remap_tile(u, xmode);
+  v = remap_tile(v, ymode);
+  float c4[4]; /* r g b a */
+  if (!(p->tile_mode & SKB_PAINT_IMAGE_LINEAR)) {
+    const uint8_t* t = image_texel(s, u * s->w, v * s->h);
+    for (int k = 0; k < 4; k++) c4[k] = t[k] / 255.f;
+  } else { /* SampleUnitLinear :44-83 */
+    float w = (float)s->w, h = (float)s->h;
+    float x = u * w, y = v * h;
+    float i0 = floorf(x - 0.5f), j0 = floorf(y - 0.5f);
+    if (xmode == 1) i0 = i0 - w * floorf(i0 / w);
+    if (ymode == 1) j0 = j0 - h * floorf(j0 / h);
+    float i1 = i0 + 1.0f, j1 = j0 + 1.0f;
+    if (xmode == 1) i1 = i1 - w * floorf(i1 / w);
+    if (ymode == 1) j1 = j1 - h * floorf(j1 / h);
+    float a = (x - 0.5f) - floorf(x - 0.5f), b = (y - 0.5f) - floorf(y - 0.5f);
+    const uint8_t *t00 = image_texel(s, i0, j0), *t10 = image_texel(s, i1, j0), *t01 = image_texel(s, i0, j1),
+                  *t11 = image_texel(s, i1, j1);
+    float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+    for (int k = 0; k < 4; k++)
+      c4[k] = ((w00 * (t00[k] / 255.f) + w10 * (t10[k] / 255.f)) + w01 * (t01[k] / 255.f)) + w11 * (t11[k] / 255.f);
+  }
+  uint32_t c = color4f_to_color(c4);
+  return (p->tile_mode & SKB_PAINT_IMAGE_UNPREMUL) ? color_to_pm(c) : c;
+}
+
 static uint32_t paint_color(const skb_dl_paint* p, const float* pool, const surface* surfs, int x, int y) {
   float fx_ = x + 0.5f, fy_ = y + 0.5f;
   float u = fx_ * p->m[0] + fy_ * p->m[1] + p->m[2];
@@ -1220,18 +1268,8 @@ static uint32_t paint_color(const skb_dl_paint* p, const float* pool, const surf
       lerp_color(p, pool, t, c);
       return color_to_pm(color4f_to_color(c));
     }
-    case SKB_PAINT_IMAGE: {
-      const surface* s = &surfs[p->image_surface];
-      if (u < 0.0 || u >= 1.0 || v < 0.0 || v >= 1.0) return 0; /* decal/decal */
-      float px = u * s->w, py = v * s->h;
-      uint32_t ix = (uint32_t)px, iy = (uint32_t)py; /* glm::clamp<uint32_t>(float,...) */
-      if (ix > s->w - 1) ix = s->w - 1;
-      if (iy > s->h - 1) iy = s->h - 1;
-      const uint8_t* t = s->px + ((size_t)iy * s->w + ix) * 4;
-      uint32_t c = (requant(t[3]) << 24) | (requant(t[0]) << 16) | (requant(t[1]) << 8) | requant(t[2]);
-      /* an unpremultiplied texture is premultiplied after sampling — sw_span_brush.cc:573-576 */
-      return (p->tile_mode & SKB_PAINT_IMAGE_UNPREMUL) ? color_to_pm(c) : c;
-    }
+    case SKB_PAINT_IMAGE:
+      return sample_image(p, &surfs[p->image_surface], u, v);
   }
   return 0;
 }
@@ -1444,15 +1482,21 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
   const skb_dl_paint* paints = (const skb_dl_paint*)dl_section(dl, h->off_paints);
   const float* pool = (const float*)dl_section(dl, h->off_stops);
   surface* surfs = (surface*)calloc(h->n_surfaces ? h->n_surfaces : 1, sizeof(surface));
+  int rc_images = 0;
   for (uint32_t i = 0; i < h->n_surfaces; i++) {
     surfs[i].w = sdesc[i].width;
     surfs[i].h = sdesc[i].height;
     surfs[i].px = (uint8_t*)calloc((size_t)surfs[i].w * surfs[i].h * 4 + 4, 1);
+    if (sdesc[i].flags & SKB_SURFACE_IMAGE) { /* an application image: its pixels come with the display list */
+      size_t nb = (size_t)surfs[i].w * surfs[i].h * 4;
+      if ((size_t)sdesc[i].reserved + nb > bytes) { rc_images = -6; continue; }
+      memcpy(surfs[i].px, dl + sdesc[i].reserved, nb);
+    }
   }
   if (initial && h->n_surfaces) memcpy(surfs[0].px, initial, (size_t)surfs[0].w * surfs[0].h * 4);
   clip_state* clips = (clip_state*)calloc((size_t)h->n_clip_states + 1, sizeof(clip_state));
   spanvec spans = {0, 0, 0}, clipped = {0, 0, 0};
-  int rc = 0;
+  int rc = rc_images;
   for (uint32_t i = 0; i < h->n_ops && rc == 0; i++) {
     const skb_dl_op* op = &ops[i];
     switch (op->kind) {

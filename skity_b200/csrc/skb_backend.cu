@@ -1371,8 +1371,20 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
   const skb_dl_op* ops = (const skb_dl_op*)(dl + h.off_ops);
   const skb_dl_path* paths = (const skb_dl_path*)(dl + h.off_paths);
   const skb_dl_paint* paints = (const skb_dl_paint*)(dl + h.off_paints);
+  const skb_dl_surface* vsurfs = (const skb_dl_surface*)(dl + h.off_surfaces);
+  for (uint32_t i = 0; i < h.n_surfaces; i++) {
+    if (!(vsurfs[i].flags & SKB_SURFACE_IMAGE)) continue;
+    if (i == 0 || (uint64_t)vsurfs[i].reserved + (uint64_t)vsurfs[i].width * vsurfs[i].height * 4 > h.total_bytes) {
+      set_error("display list: image pixels out of range");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
+  }
   for (uint32_t i = 0; i < h.n_ops; i++) {
     const skb_dl_op& o = ops[i];
+    if (o.surface < h.n_surfaces && (vsurfs[o.surface].flags & SKB_SURFACE_IMAGE)) {
+      set_error("display list: an image surface is read-only");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
     if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
       if (o.path >= h.n_paths || o.surface >= h.n_surfaces || (o.kind == SKB_OP_FILL && o.paint >= h.n_paints) ||
           o.clip_in > h.n_clip_states) {
@@ -1489,6 +1501,11 @@ static skb_result run_frame(skb_surface s) {
   for (uint32_t i = 0; i < h.n_surfaces; i++) surfs[i].px_out = surfs[i].px;
   if (s->remote_canvas) surfs[0].px_out = s->remote_canvas;
   if (temp_bytes) SKB_CUDA(cudaMemsetAsync(s->temp_px.p, 0, temp_bytes, st));
+  for (uint32_t i = 1; i < h.n_surfaces; i++) {  // application images: their pixels came with the display list
+    if (hs[i].flags & SKB_SURFACE_IMAGE)
+      SKB_CUDA(cudaMemcpy2DAsync(surfs[i].px, surfs[i].pitch, (const uint8_t*)s->dl.p + hs[i].reserved, (size_t)surfs[i].w * 4,
+                                 (size_t)surfs[i].w * 4, surfs[i].h, cudaMemcpyDeviceToDevice, st));
+  }
   const uint32_t n_tiles = tile_base[h.n_surfaces];
   S.n_tiles = n_tiles;
   SKB_TRY(buf_reserve(s->surfs, surfs.size() * sizeof(SurfDesc)));

@@ -947,6 +947,78 @@ SKB_HD uint32_t requant(uint32_t c) {
 
 struct SurfaceView { const uint8_t* px; uint32_t w, h, pitch; };  // pitch in bytes
 
+// float -> int the way x86-64 does for (int)f and static_cast<uint32_t>(f) (via 64-bit truncation)
+SKB_HD int32_t f2i_trunc(float f) { return f2i(f); }
+SKB_HD uint32_t f2u_wrap(float f) {
+  if (!(f > -9.2233720e18f && f < 9.2233720e18f)) return 0u;
+  return (uint32_t)(long long)f;
+}
+
+// BitmapSampler::GetColor (src/graphic/bitmap_sampler.cc:11-108) + PixmapBrush::CalculateColor
+// (sw_span_brush.cc:569-579): decal test, tile remap, nearest or bilinear sample, byte round trip, premultiply.
+SKB_HD float remap_tile(float t, uint32_t mode) {  // RemapFloatTile (:12-23)
+  if (mode == 0) {
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+  } else if (mode == 1) {
+    t = t - floorf(t);
+  } else if (mode == 2) {
+    float t1 = t - 1;
+    float t2 = (float)((double)t1 - 2 * floor((double)t1 * 0.5) - 1);
+    t = fabsf(t2);
+  }
+  return t;
+}
+SKB_HD uint32_t image_texel(const SurfaceView& s, float fx_, float fy_) {  // SampleXY: glm::clamp<uint32_t>(float, 0, n-1)
+  uint32_t ix = f2u_wrap(fx_), iy = f2u_wrap(fy_);
+  if (ix > s.w - 1) ix = s.w - 1;
+  if (iy > s.h - 1) iy = s.h - 1;
+  return *reinterpret_cast<const uint32_t*>(s.px + (size_t)iy * s.pitch + (size_t)ix * 4);  // R | G<<8 | B<<16 | A<<24
+}
+SKB_HDN uint32_t sample_image(const skb_dl_paint& p, const SurfaceView& s, float u, float v, const uint8_t* requant_lut) {
+  const uint32_t xmode = p.tile_mode & 0xF;
+  const uint32_t ymode = (p.tile_mode & SKB_PAINT_IMAGE_YMODE) ? ((p.tile_mode >> 4) & 0xF) : xmode;
+  if ((xmode == 3 && (u < 0.0f || u >= 1.0f)) || (ymode == 3 && (v < 0.0f || v >= 1.0f))) return 0;
+  u = remap_tile(u, xmode);
+  v = remap_tile(v, ymode);
+  uint32_t r, g, b, a;
+  if (!(p.tile_mode & SKB_PAINT_IMAGE_LINEAR)) {
+    const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h);
+    const uint32_t t0 = t & 0xFF, t1 = (t >> 8) & 0xFF, t2 = (t >> 16) & 0xFF, t3 = t >> 24;
+    if (requant_lut) {
+      r = requant_lut[t0]; g = requant_lut[t1]; b = requant_lut[t2]; a = requant_lut[t3];
+    } else {
+      r = requant(t0); g = requant(t1); b = requant(t2); a = requant(t3);
+    }
+  } else {  // SampleUnitLinear (:44-83)
+    const float w = (float)s.w, h = (float)s.h;
+    float x = u * w, y = v * h;
+    float i0 = floorf(x - 0.5f), j0 = floorf(y - 0.5f);
+    if (xmode == 1) i0 = i0 - w * floorf(i0 / w);  // glm::mod
+    if (ymode == 1) j0 = j0 - h * floorf(j0 / h);
+    float i1 = i0 + 1.0f, j1 = j0 + 1.0f;
+    if (xmode == 1) i1 = i1 - w * floorf(i1 / w);
+    if (ymode == 1) j1 = j1 - h * floorf(j1 / h);
+    const float fa = (x - 0.5f) - floorf(x - 0.5f), fb = (y - 0.5f) - floorf(y - 0.5f);  // glm::fract
+    const uint32_t t00 = image_texel(s, i0, j0), t10 = image_texel(s, i1, j0), t01 = image_texel(s, i0, j1),
+                   t11 = image_texel(s, i1, j1);
+    const float w00 = (1 - fa) * (1 - fb), w10 = fa * (1 - fb), w01 = (1 - fa) * fb, w11 = fa * fb;
+    uint32_t o[4];
+    for (int c = 0; c < 4; c++) {
+      const float c00 = (float)((t00 >> (8 * c)) & 0xFF) / 255.f, c10 = (float)((t10 >> (8 * c)) & 0xFF) / 255.f;
+      const float c01 = (float)((t01 >> (8 * c)) & 0xFF) / 255.f, c11 = (float)((t11 >> (8 * c)) & 0xFF) / 255.f;
+      o[c] = unit_to_byte(((w00 * c00 + w10 * c10) + w01 * c01) + w11 * c11);
+    }
+    r = o[0]; g = o[1]; b = o[2]; a = o[3];
+  }
+  // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
+  if ((p.tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
+    r = mul_div_255_round(r, a);
+    g = mul_div_255_round(g, a);
+    b = mul_div_255_round(b, a);
+  }
+  return r | (g << 8) | (b << 16) | (a << 24);
+}
+
 // Source colour of paint `p` at pixel centre (x+.5, y+.5): premultiplied pixel word.
 // Solid sw_span_brush.cc:140-152, Linear :312-320, Sweep :337-354, Radial :371-379,
 // Pixmap :569-579 + bitmap_sampler.cc:26-40,85-108.
@@ -1012,34 +1084,8 @@ SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const Sur
       }
       return gradient_color(p, pool, t);
     }
-    case SKB_PAINT_IMAGE: {
-      const SurfaceView& s = img;
-      if (u < 0.0f || u >= 1.0f || v < 0.0f || v >= 1.0f) return 0;
-      float px = u * (float)s.w, py = v * (float)s.h;
-      uint32_t ix = (uint32_t)px, iy = (uint32_t)py;
-      if (ix > s.w - 1) ix = s.w - 1;
-      if (iy > s.h - 1) iy = s.h - 1;
-      const uint8_t* t = s.px + (size_t)iy * s.pitch + (size_t)ix * 4;
-      uint32_t r, g, b, a;
-      if (requant_lut) {
-        r = requant_lut[t[0]];
-        g = requant_lut[t[1]];
-        b = requant_lut[t[2]];
-        a = requant_lut[t[3]];
-      } else {
-        r = requant(t[0]);
-        g = requant(t[1]);
-        b = requant(t[2]);
-        a = requant(t[3]);
-      }
-      // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
-      if ((p.tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
-        r = mul_div_255_round(r, a);
-        g = mul_div_255_round(g, a);
-        b = mul_div_255_round(b, a);
-      }
-      return r | (g << 8) | (b << 16) | (a << 24);
-    }
+    case SKB_PAINT_IMAGE:
+      return sample_image(p, img, u, v, requant_lut);
     default:
       return 0;
   }

@@ -53,13 +53,6 @@ struct OpGeom {
 };
 static_assert(offsetof(OpGeom, color) % 8 == 0 && sizeof(OpGeom) % 8 == 0, "the fine pass loads (color, fast_solid) as one 64-bit word");
 
-// float -> int the way x86-64 does for (int)f and static_cast<uint32_t>(f) (via 64-bit truncation)
-SKB_HD int32_t f2i_trunc(float f) { return f2i(f); }
-SKB_HD uint32_t f2u_wrap(float f) {
-  if (!(f > -9.2233720e18f && f < 9.2233720e18f)) return 0u;
-  return (uint32_t)(long long)f;
-}
-
 // Second half of RastePath's prologue: bounds_ = floor/ceil(path bounds); scan = bounds ∩ clip,
 // floor/ceil'd; empty test; WalkEdges arguments.  surf_w/h bound the tile rectangle.
 // extra_right = 1 for ops that go through the clip stage: FindSpan's `+ 1` can reach the pixel just right of

@@ -2,6 +2,7 @@
 
 #include "src/effect/color_filter_base.hpp"
 #include "src/effect/image_filter_base.hpp"
+#include "src/effect/pixmap_shader.hpp"
 #include "src/graphic/color_priv.hpp"
 
 #include <cmath>
@@ -11,6 +12,8 @@
 #include <skity/effect/path_effect.hpp>
 #include <skity/effect/shader.hpp>
 #include <skity/geometry/stroke.hpp>
+#include <skity/graphic/bitmap.hpp>
+#include <skity/graphic/image.hpp>
 #include <skity/graphic/paint.hpp>
 #include <skity/graphic/path.hpp>
 
@@ -531,7 +534,52 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
       }
       return builder_->AddPaint(p);
     }
-    if (shader->AsImage()) NoteUnsupported("image shader");
+    if (const auto* image_ptr = shader->AsImage()) {
+      // GenerateBrush, image branch (sw_canvas.cc:755-787) + PixmapBrush (sw_span_brush.cc:555-579)
+      const auto& image = *image_ptr;
+      const std::shared_ptr<Pixmap>* pm = image ? image->GetPixmap() : nullptr;
+      if (!pm || !*pm || (*pm)->Width() == 0 || (*pm)->Height() == 0) {
+        NoteUnsupported("image shader without CPU pixels (texture-backed image)");
+      } else {
+        auto pixmap_shader = std::static_pointer_cast<PixmapShader>(shader);
+        const std::shared_ptr<Pixmap>& pixmap = *pm;
+        uint32_t iw = pixmap->Width(), ih = pixmap->Height();
+        // the Colors Bitmap::GetPixel hands the sampler, whatever the pixmap's colour type
+        std::vector<uint8_t> rgba(static_cast<size_t>(iw) * ih * 4);
+        {
+          Bitmap bm(pixmap, true);
+          for (uint32_t yy = 0; yy < ih; yy++) {
+            for (uint32_t xx = 0; xx < iw; xx++) {
+              Color c = bm.GetPixel(xx, yy);
+              uint8_t* d = &rgba[(static_cast<size_t>(yy) * iw + xx) * 4];
+              d[0] = ColorGetR(c);
+              d[1] = ColorGetG(c);
+              d[2] = ColorGetB(c);
+              d[3] = ColorGetA(c);
+            }
+          }
+        }
+        uint32_t sid = builder_->AddImageSurface(pixmap.get(), iw, ih, rgba.data());
+        Matrix inverse;
+        shader->GetLocalMatrix().Invert(&inverse);
+        Matrix matrix = Matrix::Scale(1.f / iw, 1.f / ih) * inverse;
+        Matrix layer_to_local;
+        CurrentTransform().Invert(&layer_to_local);
+        matrix = matrix * layer_to_local;
+        StoreAffine(matrix, p.m);
+        const SamplingOptions& sampling = *pixmap_shader->GetSamplingOptions();
+        const bool linear = sampling.UseCubic() || sampling.filter == FilterMode::kLinear;
+        p.type = SKB_PAINT_IMAGE;
+        p.tile_mode = static_cast<uint32_t>(pixmap_shader->GetXTileMode()) |
+                      (static_cast<uint32_t>(pixmap_shader->GetYTileMode()) << 4) | SKB_PAINT_IMAGE_YMODE |
+                      (linear ? SKB_PAINT_IMAGE_LINEAR : 0u) |
+                      (pixmap->GetAlphaType() == kUnpremul_AlphaType ? SKB_PAINT_IMAGE_UNPREMUL : 0u);
+        p.image_surface = sid;
+        // SWSpanBrush converts the float alpha to its byte with a plain cast (sw_span_brush.hpp:29-35)
+        p.global_alpha = static_cast<uint8_t>(255 * paint.GetAlphaF());
+        return builder_->AddPaint(p);
+      }
+    }
   }
   Color4f color = stroke ? paint.GetStrokeColor() : paint.GetFillColor();
   p.type = SKB_PAINT_SOLID;
@@ -813,9 +861,21 @@ void CudaCanvas::OnDrawGlyphs(uint32_t, const GlyphID*, const float*, const floa
   NoteUnsupported("text");
 }
 
-void CudaCanvas::OnDrawImageRect(std::shared_ptr<Image>, const Rect&, const Rect&, const SamplingOptions&,
-                                 Paint const*) {
-  NoteUnsupported("DrawImage of a host image");
+// SWCanvas::OnDrawImageRect (sw_canvas.cc:641-677): the image becomes a decal shader over the destination rectangle
+void CudaCanvas::OnDrawImageRect(std::shared_ptr<Image> image, const Rect& src, const Rect& dst, const SamplingOptions& sampling,
+                                 Paint const* paint) {
+  if (!image) return;
+  if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
+  Paint work_paint = (paint == nullptr) ? Paint() : *paint;
+  work_paint.SetStyle(Paint::kFill_Style);
+  Matrix local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
+                        Matrix::Scale(dst.Width() / src.Width(), dst.Height() / src.Height()) *
+                        Matrix::Translate(-src.Left(), -src.Top());
+  auto shader = Shader::MakeShader(std::move(image), sampling, TileMode::kDecal, TileMode::kDecal, local_matrix);
+  work_paint.SetShader(std::move(shader));
+  Path path;
+  path.AddRect(dst);
+  this->OnDrawPath(path, work_paint);
 }
 
 }  // namespace skity

@@ -21,6 +21,7 @@ class DlBuilder {
 
   void Reset(uint32_t canvas_w, uint32_t canvas_h) {
     surfaces_.clear();
+    images_.clear();
     ops_.clear();
     paths_.clear();
     segs_.clear();
@@ -37,6 +38,20 @@ class DlBuilder {
     s.flags = flags;
     surfaces_.push_back(s);
     return static_cast<uint32_t>(surfaces_.size() - 1);
+  }
+
+  // An application image: RGBA8 pixels (width*height*4 bytes) carried in the display list.  `key` identifies the
+  // source pixmap so that one image drawn many times is stored once.
+  uint32_t AddImageSurface(const void* key, uint32_t w, uint32_t h, const uint8_t* rgba) {
+    for (const auto& im : images_)
+      if (im.key == key && surfaces_[im.surface].width == w && surfaces_[im.surface].height == h) return im.surface;
+    uint32_t id = AddSurface(w, h, SKB_SURFACE_IMAGE);
+    ImageBlob b;
+    b.key = key;
+    b.surface = id;
+    b.pixels.assign(rgba, rgba + static_cast<size_t>(w) * h * 4);
+    images_.push_back(std::move(b));
+    return id;
   }
 
   uint32_t NewClipState() { return ++n_clip_states_; }
@@ -108,13 +123,19 @@ class DlBuilder {
     off = align16(off + paints_.size() * sizeof(skb_dl_paint));
     h.off_stops = static_cast<uint32_t>(off);
     off = align16(off + stops_.size() * sizeof(float));
+    std::vector<skb_dl_surface> surfaces = surfaces_;
+    for (const auto& im : images_) {  // image pixels go last
+      surfaces[im.surface].reserved = static_cast<uint32_t>(off);
+      off = align16(off + im.pixels.size());
+    }
     h.total_bytes = static_cast<uint32_t>(off);
     std::vector<uint8_t> out(off, 0);
     std::memcpy(out.data(), &h, sizeof(h));
     auto put = [&](uint32_t o, const void* p, size_t n) {
       if (n) std::memcpy(out.data() + o, p, n);
     };
-    put(h.off_surfaces, surfaces_.data(), surfaces_.size() * sizeof(skb_dl_surface));
+    put(h.off_surfaces, surfaces.data(), surfaces.size() * sizeof(skb_dl_surface));
+    for (const auto& im : images_) put(surfaces[im.surface].reserved, im.pixels.data(), im.pixels.size());
     put(h.off_ops, ops_.data(), ops_.size() * sizeof(skb_dl_op));
     put(h.off_paths, paths_.data(), paths_.size() * sizeof(skb_dl_path));
     put(h.off_segs, segs_.data(), segs_.size() * sizeof(skb_dl_seg));
@@ -124,7 +145,13 @@ class DlBuilder {
   }
 
  private:
+  struct ImageBlob {
+    const void* key;
+    uint32_t surface;
+    std::vector<uint8_t> pixels;
+  };
   std::vector<skb_dl_surface> surfaces_;
+  std::vector<ImageBlob> images_;
   std::vector<skb_dl_op> ops_;
   std::vector<skb_dl_path> paths_;
   std::vector<skb_dl_seg> segs_;

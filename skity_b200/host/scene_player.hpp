@@ -33,7 +33,10 @@
 #include <skity/effect/mask_filter.hpp>
 #include <skity/effect/shader.hpp>
 #include <skity/geometry/matrix.hpp>
+#include <skity/graphic/bitmap.hpp>
+#include <skity/graphic/image.hpp>
 #include <skity/graphic/paint.hpp>
+#include <skity/graphic/sampling_options.hpp>
 #include <skity/graphic/path.hpp>
 #include <skity/render/canvas.hpp>
 #include <vector>
@@ -52,6 +55,7 @@ enum Op : uint32_t {
   kDrawPath = 9,
   kDrawRect = 10,
   kSaveLayer = 11,  // f32 ltrb[4], paint -> Canvas::SaveLayer(bounds, paint); closed by kRestore
+  kDrawImageRect = 12,  // u32 w, h, seed, unpremul (test image), f32 src[4], f32 dst[4], u32 filter, paint
 };
 
 constexpr uint32_t kMagic = 0x43534B53u;  // "SKSC"
@@ -150,6 +154,32 @@ inline bool ReadPath(Reader& r, skity::Path* path) {
   return true;
 }
 
+// A deterministic test image: a smooth colour field with hard-edged translucent blocks, so that nearest and bilinear
+// sampling, tiling and both alpha types all show.  Pixels are valid premultiplied colours when `unpremul` is 0.
+inline std::shared_ptr<skity::Image> MakeTestImage(uint32_t w, uint32_t h, uint32_t seed, uint32_t unpremul) {
+  skity::Bitmap bm(w, h, unpremul ? skity::AlphaType::kUnpremul_AlphaType : skity::AlphaType::kPremul_AlphaType);
+  uint32_t state = seed * 2654435761u + 12345u;
+  for (uint32_t y = 0; y < h; y++) {
+    for (uint32_t x = 0; x < w; x++) {
+      uint32_t r = (x * 255u) / (w > 1 ? w - 1 : 1), g = (y * 255u) / (h > 1 ? h - 1 : 1);
+      uint32_t b = ((x ^ y) * 37u + seed * 11u) & 0xFF;
+      uint32_t a = 255;
+      if (((x / 5) + (y / 3) + seed) % 4 == 0) {
+        state = state * 1664525u + 1013904223u;
+        a = (state >> 24) & 0xFF;
+      }
+      if (!unpremul) {
+        r = r * a / 255u;
+        g = g * a / 255u;
+        b = b * a / 255u;
+      }
+      bm.SetPixel(x, y, skity::ColorSetARGB(static_cast<uint8_t>(a), static_cast<uint8_t>(r), static_cast<uint8_t>(g),
+                                            static_cast<uint8_t>(b)));
+    }
+  }
+  return skity::Image::MakeImage(bm.GetPixmap());
+}
+
 inline skity::Matrix Affine(const float m[6]) {
   // m = sx kx tx ky sy ty (row-major 2x3)
   return skity::Matrix(m[0], m[1], m[2], m[3], m[4], m[5], 0.f, 0.f, 1.f);
@@ -213,6 +243,17 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
       if (!r.ok()) return false;
       sh = skity::Shader::MakeTwoPointConical(skity::Point{p[0], p[1], 0.f, 1.f}, rr[0], skity::Point{p[2], p[3], 0.f, 1.f},
                                               rr[1], colors.data(), pos, static_cast<int>(nc), tm);
+    } else if (shader == 5) {  // image shader: p = width, height, seed, unpremul; y tile mode and filter follow the stops
+      uint32_t ymode = r.U32(), filter = r.U32();
+      if (!r.ok() || ymode > 3 || filter > 2 || p[0] < 1 || p[1] < 1 || p[0] > 4096 || p[1] > 4096) return false;
+      skity::SamplingOptions so;
+      so.filter = filter == 0 ? skity::FilterMode::kNearest : skity::FilterMode::kLinear;
+      if (filter == 2) so.cubic = skity::CubicResampler{1 / 3.0f, 1 / 3.0f};
+      sh = skity::Shader::MakeShader(MakeTestImage(static_cast<uint32_t>(p[0]), static_cast<uint32_t>(p[1]),
+                                                   static_cast<uint32_t>(p[2]), static_cast<uint32_t>(p[3])),
+                                     so, tm, static_cast<skity::TileMode>(ymode),
+                                     has_local ? Affine(local) : skity::Matrix());
+      has_local = 0;
     } else {
       return false;
     }
@@ -301,6 +342,20 @@ inline int Play(const uint8_t* data, size_t n, skity::Canvas* canvas) {
         skity::Paint paint;
         if (!ReadPaint(r, &paint)) return -3;
         canvas->DrawRect(skity::Rect::MakeLTRB(q[0], q[1], q[2], q[3]), paint);
+      } break;
+      case kDrawImageRect: {
+        uint32_t iw = r.U32(), ih = r.U32(), seed = r.U32(), unpremul = r.U32();
+        float sq[4], dq[4];
+        r.Get(sq, 16);
+        r.Get(dq, 16);
+        uint32_t filter = r.U32();
+        skity::Paint paint;
+        if (!ReadPaint(r, &paint) || iw < 1 || ih < 1 || iw > 4096 || ih > 4096 || filter > 2) return -3;
+        skity::SamplingOptions so;
+        so.filter = filter == 0 ? skity::FilterMode::kNearest : skity::FilterMode::kLinear;
+        if (filter == 2) so.cubic = skity::CubicResampler{1 / 3.0f, 1 / 3.0f};
+        canvas->DrawImageRect(MakeTestImage(iw, ih, seed, unpremul), skity::Rect::MakeLTRB(sq[0], sq[1], sq[2], sq[3]),
+                              skity::Rect::MakeLTRB(dq[0], dq[1], dq[2], dq[3]), so, &paint);
       } break;
       case kSaveLayer: {
         float q[4];

@@ -23,7 +23,7 @@ CLAMP, REPEAT, MIRROR, DECAL = 0, 1, 2, 3
 WINDING, EVEN_ODD = 0, 1
 
 OP_SAVE, OP_RESTORE, OP_TRANSLATE, OP_SCALE, OP_ROTATE, OP_CONCAT = 1, 2, 3, 4, 5, 6
-OP_CLIP_RECT, OP_CLIP_PATH, OP_DRAW_PATH, OP_DRAW_RECT, OP_SAVE_LAYER = 7, 8, 9, 10, 11
+OP_CLIP_RECT, OP_CLIP_PATH, OP_DRAW_PATH, OP_DRAW_RECT, OP_SAVE_LAYER, OP_DRAW_IMAGE_RECT = 7, 8, 9, 10, 11, 12
 
 
 class PathData:
@@ -124,6 +124,8 @@ class Paint:
         out += colors.tobytes() + stops.tobytes()
         if sh["type"] == 4:
             out += struct.pack("<2f", *sh["radii"])
+        if sh["type"] == 5:   # image shader: p = (w, h, seed, unpremul); tile = x mode
+            out += struct.pack("<2I", sh.get("tile_y", sh.get("tile", CLAMP)), sh.get("filter", 0))
         return out
 
 
@@ -142,6 +144,12 @@ class Scene:
 
     def restore(self):
         self._op(OP_RESTORE)
+
+    def draw_image_rect(self, image, src, dst, paint, filter=0):
+        """Canvas::DrawImageRect of the procedural test image `image` = (w, h, seed, unpremul)."""
+        self._op(OP_DRAW_IMAGE_RECT, struct.pack("<4I", *image) + struct.pack("<8f", *src, *dst) + struct.pack("<I", filter) +
+                 paint.encode())
+        self.n_draws += 1
 
     def save_layer(self, l, t, r, b, paint):
         """Canvas::SaveLayer(bounds, paint); the matching restore() composites the layer with `paint`."""
@@ -653,4 +661,45 @@ def scene_color_filters(seed=66, size=512):
             s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), color_filter=cf, blur_radius=4.0, blur_style=1))
         else:
             s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (alpha,), color_filter=cf))
+    return s
+
+
+def scene_images(seed=77, size=512):
+    """Application images (Canvas::DrawImageRect and image shaders, src/render/sw/sw_canvas.cc:641-677,755-787;
+    BitmapSampler, src/graphic/bitmap_sampler.cc): premultiplied and unpremultiplied pixels, nearest / bilinear /
+    cubic-as-bilinear sampling, all tile modes per axis, scaled and rotated, sub-rectangles, translucent paints,
+    a blend mode and a path clip."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.9, 0.9, 0.85, 1.0)))
+    img_a, img_b = (37, 29, seed, 0), (16, 23, seed + 1, 1)
+    s.draw_image_rect(img_a, (0, 0, 37, 29), (10, 10, 158, 126), Paint(), filter=0)
+    s.draw_image_rect(img_a, (0, 0, 37, 29), (170, 10.5, 318.25, 126), Paint(fill=(0, 0, 0, 0.7)), filter=1)
+    s.draw_image_rect(img_b, (2, 3, 14, 20), (330, 10, 500, 126), Paint(), filter=2)
+    s.draw_image_rect(img_b, (0, 0, 16, 23), (340.5, 20.5, 356.5, 43.5), Paint(), filter=0)      # 1:1 on half pixels
+    s.save()
+    s.translate(100, 230)
+    s.rotate(25)
+    s.scale(1.3, 0.8)
+    s.draw_image_rect(img_a, (5, 4, 30, 25), (-60, -50, 70, 60), Paint(fill=(0, 0, 0, 0.9), blend=14), filter=1)
+    s.restore()
+    k = 0
+    for tx in (CLAMP, REPEAT, MIRROR, DECAL):
+        for flt in (0, 1):
+            x0, y0 = 200 + (k % 4) * 78, 150 + (k // 4) * 90
+            sh = dict(type=5, p=(img_a[0], img_a[1], img_a[2], img_a[3]) if k % 2 else (img_b[0], img_b[1], img_b[2], img_b[3]),
+                      tile=tx, tile_y=(tx + 1) % 4, filter=flt, colors=[(0, 0, 0, 1), (1, 1, 1, 1)], stops=None,
+                      local=(1.5, 0.2, x0 + 10.0, -0.1, 1.2, y0 + 8.0))
+            s.draw_rect(x0, y0, x0 + 72, y0 + 84, Paint(shader=sh))
+            k += 1
+    s.save()
+    s.clip_path(star_path_small(90.0).translate(110, 410) if hasattr(PathData, "translate") else _random_closed_path(rng, 110, 410, 200.0, 1))
+    sh = dict(type=5, p=img_a, tile=MIRROR, tile_y=REPEAT, filter=1, colors=[(0, 0, 0, 1), (1, 1, 1, 1)], stops=None,
+              local=(2.0, 0, 0, 0, 2.0, 0))
+    s.draw_rect(0, 300, 230, 512, Paint(shader=sh, fill=(0, 0, 0, 0.8)))
+    s.restore()
+    sh = dict(type=5, p=img_b, tile=REPEAT, tile_y=MIRROR, filter=0, colors=[(0, 0, 0, 1), (1, 1, 1, 1)], stops=None,
+              local=(3.0, 0.5, 250.0, -0.5, 3.0, 340.0))
+    s.draw_path(_random_closed_path(rng, 380, 420, 230.0, 2), Paint(shader=sh))
+    s.draw_path(_random_closed_path(rng, 380, 420, 200.0, 3), Paint(style=STROKE, shader=sh, stroke=(0, 0, 0, 0.5), stroke_width=9.0))
     return s

@@ -58,7 +58,7 @@ def test_golden_bit_exact(dev, name):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("name", ["c2_gradients_90_512", "conical_512", "color_filters_512", "clip_spans_off_surface_75",
+@pytest.mark.parametrize("name", ["c2_gradients_90_512", "conical_512", "color_filters_512", "images_512", "clip_spans_off_surface_75",
                                   "clip_zero_length_span_532", "clip_inherited_ghost_span_354"])
 def test_golden_gradients_within_tolerance(dev, name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
