@@ -576,6 +576,10 @@ def scene_fuzz(seed):
     rng = np.random.RandomState(seed)
     kind = seed % 10
     w, h = int(rng.randint(40, 700)), int(rng.randint(40, 700))
+    if seed >= 1000000:  # later additions (seeds below keep their meaning: some are golden fixtures)
+        if seed % 2:
+            return scene_images(seed, size=int(rng.randint(200, 600))), False
+        return scene_color_filters(seed, size=int(rng.randint(200, 600))), False
     if kind == 0:
         return scene_random_fills(int(rng.randint(5, 150)), 0, seed, box=float(rng.uniform(20, 500)), width=w, height=h), True
     if kind == 1:
