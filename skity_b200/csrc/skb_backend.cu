@@ -341,6 +341,7 @@ struct CoverArgs {
   uint32_t* tile_cnt;
   const skb_dl_paint* paints;
   uint8_t* zmask;  // n_items * 256, only with blend modes that act on zero-coverage pixels: 1 = touched by a direct span
+  uint8_t* zplane[SKB_CLIP_PLANES];  // the same per coverage plane, for clipped draws ([0] = zmask)
 };
 // item flags (u16): bit k = coverage plane k present (k < SKB_CLIP_PLANES = 8), bit 8 = plane 0 is solid 255,
 // bit 9 = zmask holds this item's zero-coverage map
@@ -752,13 +753,19 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     return;  // a row with more records than the state holds is swept by one thread
   }
   const int cap = mode == 0 ? SKB_CLIP_MAXE : SKB_CLIP_PLANES;
+  // a clipped draw whose blend mode / colour filter acts on zero-coverage pixels keeps the spans of coverage 0
+  bool zm = false;
+  if (mode == 1 && c.zplane[1] != nullptr) {
+    const skb_dl_paint pt = c.paints[o.paint];
+    zm = blend_zero_src_matters(paint_blend_mode(pt)) || SKB_PAINT_CF_OFFSET(pt) != 0;
+  }
   const uint32_t item_row = c.item_base[op] + (uint32_t)((y / SKB_TILE) - g.ty0) * (uint32_t)g.ntx;
   bool wrote = false, over = false;
   for (int x = x_first; x <= x_last; x++) {
     SpanSide ld, od, la, oa;
     clip_row_step(st, c.pool, row, x, ld, od, la, oa);
     if (x < x_out) continue;
-    if (mode == 0 ? !(ld.present | od.present | la.present | oa.present) : (ld.cover | od.cover | la.cover | oa.cover) == 0) continue;
+    if ((mode == 0 || zm) ? !(ld.present | od.present | la.present | oa.present) : (ld.cover | od.cover | la.cover | oa.cover) == 0) continue;
     const uint32_t* clist = nullptr;
     const uint32_t* cprev = nullptr;
     int n_c = 0, n_p = 0;
@@ -771,7 +778,7 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
       while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
     }
     ClipOut out;
-    clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, cap, mode == 0, out);
+    clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, cap, mode == 0 ? 2 : (zm ? 1 : 0), out);
     over |= out.overflow;
     if (out.n == 0) continue;
     if (mode == 0) {
@@ -784,7 +791,10 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
       const int tx = x / SKB_TILE;
       if (tx < g.tx0 || tx >= g.tx0 + g.ntx) continue;
       const size_t at = (size_t)(item_row + (uint32_t)(tx - g.tx0)) * 256 + (size_t)(y % SKB_TILE) * SKB_TILE + (x % SKB_TILE);
-      for (int k = 0; k < out.n; k++) c.mask[k][at] = (uint8_t)clip_entry_cover(out.e[k]);
+      for (int k = 0; k < out.n; k++) {
+        c.mask[k][at] = (uint8_t)clip_entry_cover(out.e[k]);
+        if (zm) c.zplane[k][at] = 1;  // a span reaches the pixel, whatever its coverage
+      }
     }
   }
   if (wrote) a.states[o.clip_out].nonempty = 1;
@@ -799,17 +809,27 @@ __global__ void __launch_bounds__(128) k_clip_classify(CoverArgs c) {
   const uint32_t op = find_interval(c.item_base, c.n_ops, item);
   const skb_dl_op o = c.ops[op];
   if (o.kind != SKB_OP_FILL || o.clip_in == 0) return;
+  bool zm = false;
+  if (c.zplane[1] != nullptr) {
+    const skb_dl_paint pt = c.paints[o.paint];
+    zm = blend_zero_src_matters(paint_blend_mode(pt)) || SKB_PAINT_CF_OFFSET(pt) != 0;
+  }
   uint32_t flags = 0;
   bool solid = true;
 #pragma unroll
   for (int k = 0; k < SKB_CLIP_PLANES; k++) {
     const uint2 v = reinterpret_cast<const uint2*>(c.mask[k] + (size_t)item * 256)[lane];
-    const bool nz = (v.x | v.y) != 0;
+    bool nz = (v.x | v.y) != 0;
+    if (zm) {
+      const uint2 z = reinterpret_cast<const uint2*>(c.zplane[k] + (size_t)item * 256)[lane];
+      nz |= (z.x | z.y) != 0;
+    }
     if (__any_sync(0xffffffffu, nz)) flags |= 1u << k;
     if (k == 0) solid = (v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu);
   }
   solid = __all_sync(0xffffffffu, solid) && flags == 1u;
   if (solid) flags |= SKB_ITEM_SOLID;
+  if (zm && flags) flags |= SKB_ITEM_ZERO;
   if (lane == 0) {
     c.item_flags[item] = (uint16_t)flags;
     if (flags) {
@@ -842,7 +862,7 @@ __global__ void k_scatter(CoverArgs c, const uint32_t* tile_off, uint32_t* tile_
   for (uint32_t k = 0; k < SKB_CLIP_PLANES; k++) {
     if (!((flags >> k) & 1u)) continue;
     cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u) |
-                                                ((k == 0 && (flags & SKB_ITEM_ZERO)) ? SKB_CMD_ZERO : 0u));
+                                                (((flags & SKB_ITEM_ZERO) && (k == 0 || c.ops[op].clip_in != 0)) ? SKB_CMD_ZERO : 0u));
   }
 }
 
@@ -862,6 +882,7 @@ struct FineArgs {
   const float* stops;
   const uint8_t* mask[SKB_CLIP_PLANES];
   const uint8_t* zmask;
+  const uint8_t* zplane[SKB_CLIP_PLANES];  // [0] = zmask
 };
 #ifndef FINE_WARPS
 #define FINE_WARPS 2
@@ -955,7 +976,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
     } else {
       uint32_t zlo = 0, zhi = 0;
       if (cmd.y & SKB_CMD_ZERO) {
-        uint2 zv = reinterpret_cast<const uint2*>(a.zmask + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256)[lane];
+        uint2 zv = reinterpret_cast<const uint2*>(a.zplane[cmd.x & 7u] + (size_t)(cmd.y & SKB_CMD_ITEM_MASK) * 256)[lane];
         zlo = zv.x;
         zhi = zv.y;
       }
@@ -1256,7 +1277,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, zmask, item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -1418,10 +1439,6 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
             set_error("display list: bad colour filter block");
             return SKB_ERROR_BAD_DISPLAY_LIST;
           }
-        }
-        if (o.clip_in != 0 && ((pt.blend && blend_zero_src_matters(pt.blend - 1)) || SKB_PAINT_CF_OFFSET(pt))) {
-          set_error("blend modes that act on zero-coverage pixels are not implemented under a path clip");
-          return SKB_ERROR_UNSUPPORTED;
         }
       }
       if (o.kind == SKB_OP_CLIP && (o.clip_out == 0 || o.clip_out > h.n_clip_states)) {
@@ -1675,9 +1692,11 @@ static skb_result run_frame(skb_surface s) {
   ca.tile_cnt = (uint32_t*)s->tile_cnt.p;
   ca.paints = t.paints;
   ca.zmask = nullptr;
+  for (int k = 0; k < SKB_CLIP_PLANES; k++) ca.zplane[k] = nullptr;
   if (s->zero_blend) {
     SKB_TRY(buf_reserve(s->zmask, (n_items + 1) * 256));
     ca.zmask = (uint8_t*)s->zmask.p;
+    ca.zplane[0] = ca.zmask;
   }
   // clip structure of the frame (host side): nesting depth of every clip state, clipped draws present?
   bool has_clip_ops = false, has_clipped_fills = false;
@@ -1709,6 +1728,13 @@ static skb_result run_frame(skb_surface s) {
     }
     // clipped draws write single bytes of their planes: start from zero
     for (int k = 0; k < SKB_CLIP_PLANES; k++) SKB_CUDA(cudaMemsetAsync(ca.mask[k], 0, n_items * 256, st));
+    if (s->zero_blend) {  // ... and of the per-plane "a span reaches this pixel" maps, when some paint needs them
+      for (int k = 1; k < SKB_CLIP_PLANES; k++) {
+        SKB_TRY(buf_reserve(s->zplane_extra[k - 1], (n_items + 1) * 256));
+        ca.zplane[k] = (uint8_t*)s->zplane_extra[k - 1].p;
+      }
+      for (int k = 0; k < SKB_CLIP_PLANES; k++) SKB_CUDA(cudaMemsetAsync(ca.zplane[k], 0, n_items * 256, st));
+    }
   }
   SKB_CUDA(cudaMemsetAsync(s->tile_cnt.p, 0, (size_t)(n_tiles + 1) * 4, st));
   SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
@@ -1792,6 +1818,7 @@ static skb_result run_frame(skb_surface s) {
   fa.stops = t.stops;
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.mask[k] = ca.mask[k];
   fa.zmask = ca.zmask;
+  for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.zplane[k] = ca.zplane[k];
   // blur jobs of the whole frame, sorted by the level of their destination
   std::vector<BlurJob> jobs;
   for (uint32_t i = 0; i < n_ops; i++) {
@@ -2002,7 +2029,7 @@ void skb_surface_destroy(skb_surface s) {
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
   Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
-                 &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
+                 &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
   for (Buf* b : bufs) buf_free(*b);

@@ -57,9 +57,11 @@ struct ClipOut {
   bool overflow;
 };
 
-// keep_ghosts: building a clip state (spans that cover nothing are kept); otherwise a clipped draw (dropped).
-SKB_HD void clip_out_push(ClipOut& o, int cap, bool keep_ghosts, int start, uint32_t cover, bool marker) {
-  if (!keep_ghosts && (cover == 0 || marker)) return;
+// keep: 2 = building a clip state (spans that cover nothing are kept, zero-length markers included); 1 = a clipped draw
+// whose blend mode or colour filter acts on zero-coverage pixels (spans of coverage 0 kept, markers dropped: they
+// have no pixel); 0 = any other clipped draw (both dropped).
+SKB_HD void clip_out_push(ClipOut& o, int cap, int keep, int start, uint32_t cover, bool marker) {
+  if (marker ? keep < 2 : (cover == 0 && keep < 1)) return;
   if (o.n >= cap) { o.overflow = true; return; }
   o.e[o.n++] = clip_entry(start, cover) | (marker ? SKB_CLIP_MARKER : 0u);
 }
@@ -72,7 +74,7 @@ SKB_HD void clip_out_push(ClipOut& o, int cap, bool keep_ghosts, int start, uint
 // Order: spans in emission order (direct before accumulated, left before own), C in list order.
 SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, const SpanSide& left_a, const SpanSide& own_a,
                           const uint32_t* clist, int n_c, const uint32_t* c_prev, int n_prev, bool clipped, int cap,
-                          bool keep_ghosts, ClipOut& out) {
+                          int keep_ghosts, ClipOut& out) {
   out.n = 0;
   out.overflow = false;
   if (!clipped) {  // HasClip() false: the raster spans themselves
@@ -85,7 +87,7 @@ SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, 
     const SpanSide& s = *seq[k];
     if (!s.present) continue;
     const bool is_left = (k & 1) == 0;
-    if (!is_left && keep_ghosts && s.start == x) {
+    if (!is_left && keep_ghosts == 2 && s.start == x) {
       // parent spans that end exactly where this span starts
       for (int i = 0; i < n_prev; i++) {
         if (clip_entry_is_marker(c_prev[i])) continue;
@@ -93,7 +95,7 @@ SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, 
         for (int j = 0; j < n_c; j++) continues |= clist[j] == c_prev[i];
         if (continues) continue;
         const uint32_t pc = clip_entry_cover(c_prev[i]);
-        clip_out_push(out, cap, true, x, pc < s.cover ? pc : s.cover, true);
+        clip_out_push(out, cap, 2, x, pc < s.cover ? pc : s.cover, true);
       }
     }
     for (int i = 0; i < n_c; i++) {

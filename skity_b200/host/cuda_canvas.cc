@@ -390,16 +390,6 @@ static uint32_t EncodeBlend(BlendMode mode) {
   return mode == BlendMode::kSrcOver ? 0u : static_cast<uint32_t>(m) + 1u;
 }
 
-// include/skb_dl.h: these modes change the destination even where a span's coverage is 0
-static bool BlendNeedsZeroCoverage(uint32_t encoded) {
-  switch (encoded) {
-    case 1: case 2: case 6: case 7: case 8: case 11: case 14: case 22:
-      return true;
-    default:
-      return false;
-  }
-}
-
 // Encodes paint.GetColorFilter() as a block of the float pool (include/skb_dl.h, SKB_CF_*) and returns the bits to
 // OR into skb_dl_paint::has_stops.  What each filter computes: src/effect/color_filter.cc:123-197.
 uint32_t CudaCanvas::EncodeColorFilter(const Paint& paint) {
@@ -449,14 +439,9 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
   skb_dl_paint p{};
   p.global_alpha = 255;
   p.blend = EncodeBlend(paint.GetBlendMode());
-  if (BlendNeedsZeroCoverage(p.blend) && state_stack_.back().clip_id != 0) {
-    NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
-    p.blend = 0;
-  }
   uint32_t cf_bits = 0;
   if (paint.GetColorFilter()) {
-    if (state_stack_.back().clip_id != 0) NoteUnsupported("colour filter under a path clip");
-    else cf_bits = EncodeColorFilter(paint);
+    cf_bits = EncodeColorFilter(paint);
   }
   p.has_stops = cf_bits;
   auto shader = paint.GetShader();
@@ -787,13 +772,8 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
   // work_paint.SetStyle(kFill) precedes GetAlphaF() in the reference (sw_canvas.cc:656,784)
   p.global_alpha = static_cast<uint8_t>(255 * paint.GetFillColor().a);
   p.blend = EncodeBlend(paint.GetBlendMode());
-  if (BlendNeedsZeroCoverage(p.blend) && state_stack_.back().clip_id != 0) {
-    NoteUnsupported("blend mode that acts on zero-coverage pixels under a path clip");
-    p.blend = 0;
-  }
   if (paint.GetColorFilter()) {
-    if (state_stack_.back().clip_id != 0) NoteUnsupported("colour filter under a path clip");
-    else p.has_stops = EncodeColorFilter(paint);
+    p.has_stops = EncodeColorFilter(paint);
   }
   uint32_t paint_index = builder_->AddPaint(p);
   EmitFill(path, CurrentTransform(), paint_index);

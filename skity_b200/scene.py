@@ -577,8 +577,10 @@ def scene_fuzz(seed):
     kind = seed % 10
     w, h = int(rng.randint(40, 700)), int(rng.randint(40, 700))
     if seed >= 1000000:  # later additions (seeds below keep their meaning: some are golden fixtures)
-        if seed % 2:
+        if seed % 3 == 1:
             return scene_images(seed, size=int(rng.randint(200, 600))), False
+        if seed % 3 == 2:
+            return scene_clipped_blends(seed, size=int(rng.randint(150, 500))), True
         return scene_color_filters(seed, size=int(rng.randint(200, 600))), False
     if kind == 0:
         return scene_random_fills(int(rng.randint(5, 150)), 0, seed, box=float(rng.uniform(20, 500)), width=w, height=h), True
@@ -706,4 +708,36 @@ def scene_images(seed=77, size=512):
               local=(3.0, 0.5, 250.0, -0.5, 3.0, 340.0))
     s.draw_path(_random_closed_path(rng, 380, 420, 230.0, 2), Paint(shader=sh))
     s.draw_path(_random_closed_path(rng, 380, 420, 200.0, 3), Paint(style=STROKE, shader=sh, stroke=(0, 0, 0, 0.5), stroke_width=9.0))
+    return s
+
+
+def scene_clipped_blends(seed=88, size=400):
+    """Blend modes that act on zero-coverage pixels (kClear, kSrc, kSrcIn, kDstIn, kSrcOut, kDstATop, kModulate,
+    kSoftLight) and colour filters on draws UNDER nested path clips: the clipped sub-spans of coverage 0 still
+    blend (FindSpan keeps min(clip, span) = 0, sw_canvas.cc:219-265)."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.8, 0.85, 0.6, 1.0)))
+    for i in range(6):
+        p = _random_closed_path(rng, rng.uniform(0, size), rng.uniform(0, size), 240.0, i)
+        s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (rng.uniform(0.4, 1.0),)))
+    modes = [0, 1, 5, 6, 7, 10, 13, 21, 3, 14]
+    s.save()
+    s.clip_path(_random_closed_path(rng, size * 0.5, size * 0.5, size * 0.95, 1))
+    for k, mode in enumerate(modes):
+        if k == 5:
+            s.save()
+            s.clip_path(_random_closed_path(rng, size * 0.55, size * 0.5, size * 0.7, 2))
+        p = _random_closed_path(rng, rng.uniform(0.2, 0.8) * size, rng.uniform(0.2, 0.8) * size, 170.0, k)
+        cf = None
+        if k % 3 == 2:
+            cf = dict(type=1, color=0x9020C040, mode=1 if k % 2 else 5)
+        elif k % 3 == 1:
+            cf = dict(type=3)
+        col = tuple(rng.uniform(0, 1, 3)) + ((1.0,) if k % 2 else (float(rng.uniform(0.4, 0.9)),))
+        s.draw_path(p, Paint(fill=col, blend=mode, color_filter=cf))
+        if k % 4 == 3:
+            s.draw_path(p, Paint(style=STROKE, stroke=col[::-1][1:] + (0.8,), stroke_width=5.0, blend=mode, color_filter=cf))
+    s.restore()
+    s.restore()
     return s

@@ -87,6 +87,7 @@ def golden_scenes():
     out["conical_512"] = scene.scene_conical()
     out["color_filters_512"] = scene.scene_color_filters()
     out["images_512"] = scene.scene_images()
+    out["clipped_blends_400"] = scene.scene_clipped_blends()
     # found by the GPU fuzz: StackBlur's seeding quirk yields pixels that are not valid premultiplied colours, whose
     # SrcOver sum overflows a channel and carries into the next one up in the reference's A|R|G|B registers
     out["filters_channel_carry_283"] = scene.scene_filters(5107, size=283)

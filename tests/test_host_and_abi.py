@@ -88,9 +88,10 @@ def test_display_list_structure_for_blur_and_strokes():
 @needs_host
 def test_unsupported_features_are_reported_not_approximated():
     s = Scene(64, 64)
-    s.clip_path(scene.star_path())
-    # kClear also acts on the zero-coverage pixels of a span; under a path clip that is not implemented
-    s.draw_rect(0, 0, 64, 64, Paint(blend=0))
+    # a layer whose paint carries a mask filter would need the layer drawn as a blurred image shader: not implemented
+    s.save_layer(4, 4, 60, 60, Paint(blur_radius=3.0, blur_style=1))
+    s.draw_rect(10, 10, 40, 40, Paint())
+    s.restore()
     with pytest.raises(RuntimeError):
         hostlib.encode_scene(s.encode())
 
