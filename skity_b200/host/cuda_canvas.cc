@@ -6,6 +6,7 @@
 #include "src/graphic/color_priv.hpp"
 
 #include <cmath>
+#include <functional>
 #include <cstring>
 #include <skity/effect/image_filter.hpp>
 #include <skity/effect/mask_filter.hpp>
@@ -659,6 +660,12 @@ void CudaCanvas::OnDrawPaint(const Paint& paint) {
 // path is drawn into an offscreen surface, blurred into a second one, post-processed per pixel for the
 // blur styles / the shadow colour, and composited back as an image.
 void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
+  HandleFilterOf(path.GetBounds(), paint, [&](CudaCanvas& temp_canvas, const Paint& work_paint) { temp_canvas.DrawPath(path, work_paint); });
+}
+
+// `draw_source` draws what is to be filtered (a path, or an image that lives on the device) into the temporary canvas.
+void CudaCanvas::HandleFilterOf(const Rect& source_bounds, const Paint& paint,
+                                const std::function<void(CudaCanvas&, const Paint&)>& draw_source) {
   Paint work_paint = paint;
   work_paint.SetMaskFilter(nullptr);
   work_paint.SetImageFilter(nullptr);
@@ -672,7 +679,7 @@ void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
       return;
     }
   }
-  Rect bounds = ComputeBoundsIfStroke(path.GetBounds(), paint);
+  Rect bounds = ComputeBoundsIfStroke(source_bounds, paint);
   float radius_x = mask_filter ? mask_filter->GetBlurRadius() : image_filter->GetRadiusX();
   float radius_y = mask_filter ? mask_filter->GetBlurRadius() : image_filter->GetRadiusY();
   Rect fb = Rect::MakeLTRB(std::floor(bounds.Left() - radius_x), std::floor(bounds.Top() - radius_y),
@@ -685,7 +692,7 @@ void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
   {
     CudaCanvas temp_canvas(builder_, temp, w, h);
     temp_canvas.Translate(-fb.Left(), -fb.Top());
-    temp_canvas.DrawPath(path, work_paint);
+    draw_source(temp_canvas, work_paint);
     if (!temp_canvas.Unsupported().empty()) NoteUnsupported(temp_canvas.Unsupported().c_str());
   }
   uint32_t blurred = builder_->AddSurface(w, h);
@@ -723,31 +730,41 @@ void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
 // Canvas::DrawImage(image, rect, paint) -> SWCanvas::OnDrawImageRect (sw_canvas.cc:641-677)
 // -> GenerateBrush image branch (sw_canvas.cc:755-787), for an image that lives on the device.
 void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih, const Rect& dst,
-                                  const Paint& paint, bool unpremul) {
+                                  const Paint& paint, bool unpremul, const Matrix* shader_local) {
   Rect src = Rect::MakeWH(iw, ih);
   if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
   if (PeekLayerStack()) {  // OnDrawImageRect ends in OnDrawPath, which an open layer takes over (sw_canvas.cc:360-363)
-    PeekLayerStack()->canvas->DrawSurfaceImage(src_surface, iw, ih, dst, paint, unpremul);
-    return;
-  }
-  if (paint.GetMaskFilter() || paint.GetImageFilter()) {
-    NoteUnsupported("mask / image filter on an image or layer composite");
+    PeekLayerStack()->canvas->DrawSurfaceImage(src_surface, iw, ih, dst, paint, unpremul, shader_local);
     return;
   }
   Path path;
   path.AddRect(dst);
+  // the image shader's local matrix as OnDrawImageRect builds it (sw_canvas.cc:657-667) — unless the caller is a
+  // filter's temporary canvas replaying a shader that was built elsewhere
   Matrix local_matrix;
-  if (IsDrawingLayer()) {
+  if (shader_local) {
+    local_matrix = *shader_local;
+  } else if (IsDrawingLayer()) {
     local_matrix = Matrix::Scale(1.f / src.Width(), 1.f / src.Height()) * Matrix::Translate(-src.Left(), -src.Top());
   } else {
     local_matrix = Matrix::Translate(dst.Left(), dst.Top()) *
                    Matrix::Scale(dst.Width() / src.Width(), dst.Height() / src.Height()) *
                    Matrix::Translate(-src.Left(), -src.Top());
   }
+  if (paint.GetMaskFilter() || paint.GetImageFilter()) {
+    // OnDrawImageRect -> OnDrawPath(rect, image shader + filter) -> HandleFilter (sw_canvas.cc:656-676,365-369): the image
+    // is resampled into the temporary canvas, filtered, and the result drawn back
+    Paint fill_paint = paint;
+    fill_paint.SetStyle(Paint::kFill_Style);
+    HandleFilterOf(path.GetBounds(), fill_paint, [&](CudaCanvas& temp_canvas, const Paint& work_paint) {
+      temp_canvas.DrawSurfaceImage(src_surface, iw, ih, dst, work_paint, unpremul, &local_matrix);
+    });
+    return;
+  }
   Matrix inverse;
   local_matrix.Invert(&inverse);
   Matrix matrix = Matrix::Scale(1.f / iw, 1.f / ih) * inverse;
-  if (IsDrawingLayer()) {
+  if (IsDrawingLayer()) {  // (a filter's temporary canvas is a canvas of its own: never "drawing a layer")
     // GenerateBrush maps the raster bounds of the drawn rectangle onto the layer (sw_canvas.cc:772-776);
     // the bounds are SWRaster::RastePath's (sw_raster.cc:737-745)
     Paint plain;

@@ -11,6 +11,7 @@
 #ifndef SKITY_B200_HOST_CUDA_CANVAS_HPP
 #define SKITY_B200_HOST_CUDA_CANVAS_HPP
 
+#include <functional>
 #include <memory>
 #include <skity/render/canvas.hpp>
 #include <string>
@@ -79,8 +80,10 @@ class CudaCanvas : public Canvas {
   uint32_t MakeBrush(const Paint& paint, bool stroke);
   uint32_t EncodeColorFilter(const Paint& paint);
   void HandleFilter(const Path& path, const Paint& paint);
+  void HandleFilterOf(const Rect& source_bounds, const Paint& paint,
+                      const std::function<void(CudaCanvas&, const Paint&)>& draw_source);
   void DrawSurfaceImage(uint32_t src_surface, uint32_t w, uint32_t h, const Rect& dst,
-                        const Paint& paint, bool unpremul);
+                        const Paint& paint, bool unpremul, const Matrix* shader_local = nullptr);
   LayerState* PeekLayerStack() { return layer_stack_.empty() ? nullptr : layer_stack_.back().get(); }
   void OnLayerRestore();
   bool IsDrawingLayer() const { return parent_canvas_ ? parent_canvas_->drawing_layer_ : drawing_layer_; }

@@ -741,3 +741,30 @@ def scene_clipped_blends(seed=88, size=400):
     s.restore()
     s.restore()
     return s
+
+
+def scene_filtered_layers(seed=99, size=384):
+    """SaveLayer whose paint carries a mask filter or an image filter: the layer is drawn back through HandleFilter
+    (resampled into a temporary, blurred / shadowed, composited), src/render/sw/sw_canvas.cc:891-902,365-369."""
+    rng = np.random.RandomState(seed)
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.93, 0.93, 0.9, 1.0)))
+    s.save_layer(30.5, 20.25, 200, 180, Paint(fill=(0, 0, 0, 0.8), blur_radius=5.0, blur_style=1))
+    s.draw_rect(50, 40, 170, 150, Paint(fill=(0.9, 0.2, 0.1, 1.0)))
+    s.draw_path(_random_closed_path(rng, 120, 100, 130.0, 1), Paint(fill=(0.1, 0.6, 0.9, 0.9)))
+    s.restore()
+    s.save()
+    s.translate(280, 110)
+    s.rotate(-15)
+    s.save_layer(-80, -70, 90, 80, Paint(image_filter=dict(type=2, offset=(7.0, 6.0), sigma=(3.0, 3.0), color=0xA0000000)))
+    s.draw_path(_random_closed_path(rng, 0, 0, 140.0, 2), Paint(fill=(0.2, 0.8, 0.3, 1.0)))
+    s.draw_rect(-40, -30, 30, 20, Paint(style=STROKE, stroke=(0.1, 0.1, 0.5, 1.0), stroke_width=6.0))
+    s.restore()
+    s.restore()
+    s.save_layer(60, 220, 340, 370, Paint(fill=(0, 0, 0, 0.9), blur_radius=3.0, blur_style=2, blend=14))
+    s.draw_path(_random_closed_path(rng, 200, 295, 190.0, 3), Paint(fill=(0.8, 0.7, 0.1, 1.0)))
+    s.save_layer(120, 240, 300, 350, Paint(image_filter=dict(type=1, sigma=(2.5, 4.0))))
+    s.draw_rect(140, 260, 280, 330, Paint(fill=(0.5, 0.1, 0.7, 0.8)))
+    s.restore()
+    s.restore()
+    return s

@@ -84,6 +84,7 @@ def golden_scenes():
     out["blend_modes_480"] = scene.scene_blend_modes()
     out["filters_512"] = scene.scene_filters()
     out["layers_512"] = scene.scene_layers()
+    out["filtered_layers_384"] = scene.scene_filtered_layers()
     out["conical_512"] = scene.scene_conical()
     out["color_filters_512"] = scene.scene_color_filters()
     out["images_512"] = scene.scene_images()
