@@ -528,19 +528,26 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
         prev_right = fx_ceil_i(fx_max(right, c.x));
       }
       const int next = c.next;
+      bool chord = false;
       while (c.lower_y <= next_y) {
         if (edge_count(c) > 0) {
           QuadState& q = Q[cur];
           q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
           q.snapped_y = c.y;
+          chord = true;
           if (!update_quad(c, q)) break;
         } else {
           break;
         }
       }
-      // write back what changed (the links are edited in place below)
-      E[cur].x = c.x; E[cur].y = c.y; E[cur].dx = c.dx; E[cur].dy = c.dy;
-      E[cur].upper_x = c.upper_x; E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
+      // write back what changed (the links are edited in place below): x and y always, the rest only when the
+      // edge took its next chord
+      E[cur].x = c.x;
+      E[cur].y = c.y;
+      if (chord) {
+        E[cur].dx = c.dx; E[cur].dy = c.dy;
+        E[cur].upper_x = c.upper_x; E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
+      }
       if (c.lower_y <= next_y) {
         remove_edge(E, cur);
       } else {

@@ -4,6 +4,7 @@
 // Test infrastructure only; built by tests/simlib.py with g++.
 #include <climits>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -267,7 +268,15 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
           while (n_p < SKB_CLIP_MAXE && cprev[n_p]) n_p++;
         }
         ClipOut out;
-        clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, is_clip ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, is_clip, out);
+        clip_combine(x, ld, od, la, oa, clist, n_c, cprev, n_p, clipped, is_clip ? SKB_CLIP_MAXE : SKB_CLIP_PLANES, is_clip ? 2 : 0, out);
+        if (getenv("SKB_SIM_DEBUG_XY")) {
+          int dx_ = 0, dy_ = 0;
+          sscanf(getenv("SKB_SIM_DEBUG_XY"), "%d,%d", &dx_, &dy_);
+          if (y == dy_ && x >= dx_ - 2 && x <= dx_ + 2)
+            fprintf(stderr, "op %u kind %u x %d y %d: ld(%d,%u,%d) od(%d,%u,%d) la(%d,%u,%d) oa(%d,%u,%d) clipped %d n_c %d n_p %d out.n %d\n", i, o.kind, x, y,
+                    (int)ld.present, ld.cover, ld.start, (int)od.present, od.cover, od.start, (int)la.present, la.cover, la.start,
+                    (int)oa.present, oa.cover, oa.start, (int)clipped, n_c, n_p, out.n);
+        }
         if (out.overflow) stats[0]++;
         if (out.n > stats[1]) stats[1] = out.n;
         if (o.kind == SKB_OP_CLIP) {

@@ -104,3 +104,15 @@ def test_sim_clip_rows_shared_between_threads(seed):
     got, stats = simlib.render_dl(dl)
     assert stats[0] == 0 and stats[3] == 0
     assert np.array_equal(got, port.render(dl))
+
+
+@pytest.mark.parametrize("name", ["clip_spans_off_surface_75", "clip_zero_length_span_532", "clip_inherited_ghost_span_354"])
+def test_sim_clip_fixtures_found_by_fuzzing(name):
+    """The clip-stack corner cases the GPU fuzz found (spans off the surface, spans that cover nothing), through the
+    CPU build of the same stage code, against the compiled reference's pixels."""
+    import os
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    got, stats = simlib.render_dl(z["dl"].tobytes())
+    assert stats[0] == 0 and stats[3] == 0
+    assert np.array_equal(got, z["rgba"])
