@@ -71,7 +71,9 @@ enum skb_dl_op_kind {
   SKB_OP_BLUR = 3  /* SWStackBlur: surface aux -> surface `surface`, radius in clip_bounds[0]; fill_type = what is
                       then done to the blurred pixels with the unblurred ones at hand: 0 nothing (BlurStyle::kNormal,
                       ImageFilters::Blur), 2 kSolid, 3 kOuter, 4 kInner (src/effect/mask_filter.cc:64-100),
-                      5 drop shadow (src/effect/image_filter.cc:222-233) with the colour in `paint` */
+                      5 drop shadow (src/effect/image_filter.cc:222-233) with the colour in `paint`;
+                      6 / 7: no blur at all but ImageFilters::Dilate / Erode (MorphologyImageFilter::OnFilter,
+                      image_filter.cc:294-385): clip_bounds[0], [1] = the filter's radius_x, radius_y */
 };
 
 typedef struct skb_dl_op {

@@ -1402,6 +1402,26 @@ static void clip_refine(const clip_state* parent, const spanvec* fresh, int op, 
   }
 }
 
+/* morph<type, direction> — image_filter.cc:294-340: per channel max (dilate) / min (erode) over the window
+ * [i - radius, i + radius] clamped to the line, along x (dir 0) or y (dir 1); radius = min(radius, n - 1) */
+static void morph_pass(const uint8_t* src, uint8_t* dst, int w, int h, int radius, int dir, int erode) {
+  int n = dir == 0 ? w : h;
+  if (radius > n - 1) radius = n - 1;
+  for (int y = 0; y < h; y++) {
+    for (int x = 0; x < w; x++) {
+      int i = dir == 0 ? x : y;
+      int lo = i - radius < 0 ? 0 : i - radius, hi = i + radius > n - 1 ? n - 1 : i + radius;
+      int v[4] = {erode ? 255 : 0, erode ? 255 : 0, erode ? 255 : 0, erode ? 255 : 0};
+      for (int k = lo; k <= hi; k++) {
+        const uint8_t* p = src + ((size_t)(dir == 0 ? y : k) * w + (dir == 0 ? k : x)) * 4;
+        for (int c = 0; c < 4; c++) v[c] = erode ? (p[c] < v[c] ? p[c] : v[c]) : (p[c] > v[c] ? p[c] : v[c]);
+      }
+      uint8_t* o = dst + ((size_t)y * w + x) * 4;
+      for (int c = 0; c < 4; c++) o[c] = (uint8_t)v[c];
+    }
+  }
+}
+
 /* --------------------------------------------------------------- stack blur */
 /* SWStackBlur::GetMulSum/GetShrSum — sw_stack_blur.cc:286-338.  The two 255-entry
  * tables are the classic StackBlur reciprocal tables: shr = the largest s with
@@ -1523,6 +1543,21 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
         surface* d = &surfs[op->surface];
         surface* s = &surfs[op->aux];
         if (d->w != s->w || d->h != s->h) { rc = -3; break; }
+        if (op->fill_type == 6 || op->fill_type == 7) { /* MorphologyImageFilter::OnFilter — image_filter.cc:294-385 */
+          float rxf = op->clip_bounds[0], ryf = op->clip_bounds[1];
+          int erode = op->fill_type == 7, w_ = (int)s->w, h_ = (int)s->h;
+          if (rxf > 0 && ryf > 0) {
+            uint8_t* tmp = (uint8_t*)calloc((size_t)w_ * h_ * 4 + 4, 1);
+            morph_pass(s->px, tmp, w_, h_, (int)rxf, 0, erode);
+            morph_pass(tmp, d->px, w_, h_, (int)ryf, 1, erode);
+            free(tmp);
+          } else if (rxf > 0) {
+            morph_pass(s->px, d->px, w_, h_, (int)rxf, 0, erode);
+          } else if (ryf > 0) {
+            morph_pass(s->px, d->px, w_, h_, (int)ryf, 1, erode);
+          }
+          break;
+        }
         stack_blur(s->px, d->px, (int)s->w, (int)s->h, (int)op->clip_bounds[0]);
         /* MaskFilterOnFilter styles — src/effect/mask_filter.cc:64-100 ; DropShadowImageFilter::OnFilter —
          * src/effect/image_filter.cc:222-233 (pixels are R,G,B,A bytes) */

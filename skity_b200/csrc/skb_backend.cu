@@ -1029,8 +1029,10 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) k_fine(FineArgs a) {
 struct BlurJob {
   uint32_t src, dst;  // surface ids
   int32_t radius;
-  uint32_t style;     // 0 plain blur; BlurStyle kSolid 2 / kOuter 3 / kInner 4 (mask_filter.cc:64-100); 5 drop shadow
+  uint32_t style;     // 0 plain blur; BlurStyle kSolid 2 / kOuter 3 / kInner 4 (mask_filter.cc:64-100); 5 drop shadow;
+                      // 6 dilate, 7 erode
   uint32_t color;     // style 5: the shadow colour (unpremultiplied A<<24|R<<16|G<<8|B)
+  float morph_rx, morph_ry;  // styles 6 / 7 (dilate / erode): the filter's radii, no blur
 };
 
 // What MaskFilterOnFilter / DropShadowImageFilter::OnFilter do to the blurred bitmap with the unblurred
@@ -1055,6 +1057,24 @@ __global__ void k_blur_style(SurfDesc raw, SurfDesc dst, uint32_t style, uint32_
   }
 }
 
+
+// morph<type, direction> (src/effect/image_filter.cc:294-340): per channel max (dilate) or min (erode) over the window
+// [i - radius, i + radius] clamped to the line, along x (dir 0) or y (dir 1).  One thread per pixel.
+__global__ void k_morph(const uint8_t* src, uint32_t src_pitch, uint8_t* dst, uint32_t dst_pitch, int w, int h, int radius,
+                        int dir, int erode) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)w * h) return;
+  const int x = (int)(i % (uint32_t)w), y = (int)(i / (uint32_t)w);
+  const int n = dir == 0 ? w : h, at = dir == 0 ? x : y;
+  radius = min(radius, n - 1);
+  const int lo = max(at - radius, 0), hi = min(at + radius, n - 1);
+  uint32_t acc = erode ? 0xFFFFFFFFu : 0u;
+  for (int k = lo; k <= hi; k++) {
+    const uint32_t p = *reinterpret_cast<const uint32_t*>(src + (size_t)(dir == 0 ? y : k) * src_pitch + (size_t)(dir == 0 ? k : x) * 4);
+    acc = erode ? __vminu4(acc, p) : __vmaxu4(acc, p);
+  }
+  *reinterpret_cast<uint32_t*>(dst + (size_t)y * dst_pitch + (size_t)x * 4) = acc;
+}
 
 // Horizontal pass: one WARP per (job, row).  Each lane owns a run of consecutive samples of the extended row
 // (n + 2m + 1 samples): it sums them (T), the lane totals are scanned with shuffles, it then builds its part of U
@@ -1084,6 +1104,7 @@ __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* job
   const int n = (int)S.w;
   const uint32_t* srow = reinterpret_cast<const uint32_t*>(S.px + (size_t)y * S.pitch);
   uint32_t* drow = reinterpret_cast<uint32_t*>(D.px + (size_t)y * D.pitch);
+  if (jb.style >= 6) return;  // dilate / erode: k_morph
   int r = jb.radius > 254 ? 254 : jb.radius;
   if (r <= 1) {
     for (int x = lane; x < n; x += 32) drow[x] = srow[x];
@@ -1156,6 +1177,7 @@ __global__ void __launch_bounds__(128) k_blur_v(const BlurJob* jobs, const uint3
   const uint32_t job = find_interval(job_col_base, n_jobs, gcol);
   const BlurJob jb = jobs[job];
   const SurfDesc D = surfs[jb.dst];
+  if (jb.style >= 6) return;
   int r = jb.radius > 254 ? 254 : jb.radius;
   if (r <= 1) return;  // the horizontal kernel already copied
   const int x = (int)(gcol - job_col_base[job]);
@@ -1454,7 +1476,7 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
         set_error("display list: blur surface out of range");
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
-      if (o.fill_type == 1 || o.fill_type > 5) {
+      if (o.fill_type == 1 || o.fill_type > 7) {
         set_error("display list: unknown blur style");
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
@@ -1829,6 +1851,8 @@ static skb_result run_frame(skb_surface s) {
       j.radius = (int32_t)hops[i].clip_bounds[0];
       j.style = hops[i].fill_type;
       j.color = hops[i].paint;
+      j.morph_rx = hops[i].clip_bounds[0];
+      j.morph_ry = hops[i].clip_bounds[1];
       if (surfs[j.src].w != surfs[j.dst].w || surfs[j.src].h != surfs[j.dst].h) {
         set_error("blur: source and destination surfaces differ in size");
         return SKB_ERROR_BAD_DISPLAY_LIST;
@@ -1904,7 +1928,7 @@ static skb_result run_frame(skb_surface s) {
       // radius <= 1: the H kernel copied src into scratch; finish with a plain copy into dst
       for (uint32_t i = j0; i < j1; i++) {
         int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
-        if (r <= 1) {
+        if (r <= 1 && jobs[i].style < 6) {
           const SurfDesc& d = surfs[jobs[i].dst];
           SKB_CUDA(cudaMemcpyAsync(d.px, tmp_ptrs[i], (size_t)d.pitch * d.h, cudaMemcpyDeviceToDevice, st));
         }
@@ -1914,7 +1938,27 @@ static skb_result run_frame(skb_surface s) {
                                                                  (const uint8_t* const*)s->blur_tmp_ptrs.p, colb[j0], colb[j1]);
       launches++;
       for (uint32_t i = j0; i < j1; i++) {
-        if (jobs[i].style == 0) continue;
+        if (jobs[i].style < 6) continue;
+        // MorphologyImageFilter::OnFilter (image_filter.cc:342-385): x then y when both radii are positive, else the one
+        const SurfDesc& sdesc = surfs[jobs[i].src];
+        const SurfDesc& d = surfs[jobs[i].dst];
+        const int erode = jobs[i].style == 7, mw = (int)d.w, mh = (int)d.h;
+        const uint32_t mgrid = cdiv((uint64_t)mw * mh, 256);
+        const float rxf = jobs[i].morph_rx, ryf = jobs[i].morph_ry;
+        if (rxf > 0 && ryf > 0) {
+          k_morph<<<mgrid, 256, 0, st>>>(sdesc.px, sdesc.pitch, (uint8_t*)tmp_ptrs[i], d.pitch, mw, mh, (int)rxf, 0, erode);
+          k_morph<<<mgrid, 256, 0, st>>>(tmp_ptrs[i], d.pitch, d.px, d.pitch, mw, mh, (int)ryf, 1, erode);
+          launches += 2;
+        } else if (rxf > 0) {
+          k_morph<<<mgrid, 256, 0, st>>>(sdesc.px, sdesc.pitch, d.px, d.pitch, mw, mh, (int)rxf, 0, erode);
+          launches++;
+        } else if (ryf > 0) {
+          k_morph<<<mgrid, 256, 0, st>>>(sdesc.px, sdesc.pitch, d.px, d.pitch, mw, mh, (int)ryf, 1, erode);
+          launches++;
+        }
+      }
+      for (uint32_t i = j0; i < j1; i++) {
+        if (jobs[i].style == 0 || jobs[i].style >= 6) continue;
         const SurfDesc& d = surfs[jobs[i].dst];
         k_blur_style<<<cdiv((uint64_t)d.w * d.h, 256), 256, 0, st>>>(surfs[jobs[i].src], d, jobs[i].style, jobs[i].color);
         launches++;

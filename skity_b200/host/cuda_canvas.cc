@@ -674,8 +674,9 @@ void CudaCanvas::HandleFilterOf(const Rect& source_bounds, const Paint& paint,
   auto image_filter = As_IFB(paint.GetImageFilter().get());
   if (!mask_filter) {
     auto type = image_filter->GetType();
-    if (type != ImageFilterType::kBlur && type != ImageFilterType::kDropShadow) {
-      NoteUnsupported("image filter other than Blur / DropShadow");
+    if (type != ImageFilterType::kBlur && type != ImageFilterType::kDropShadow && type != ImageFilterType::kDilate &&
+        type != ImageFilterType::kErode) {
+      NoteUnsupported("image filter other than Blur / DropShadow / Dilate / Erode");  // the SW backend has no OnFilter for them either
       return;
     }
   }
@@ -715,6 +716,15 @@ void CudaCanvas::HandleFilterOf(const Rect& source_bounds, const Paint& paint,
   if (image_filter->GetType() == ImageFilterType::kBlur) {
     builder_->AddOp(b);
     DrawSurfaceImage(blurred, w, h, fb, work_paint, false);
+    return;
+  }
+  if (image_filter->GetType() == ImageFilterType::kDilate || image_filter->GetType() == ImageFilterType::kErode) {
+    // MorphologyImageFilter::OnFilter (image_filter.cc:342-385): the result bitmap is of the default (unpremultiplied) type
+    b.fill_type = image_filter->GetType() == ImageFilterType::kDilate ? 6 : 7;
+    b.clip_bounds[0] = radius_x;
+    b.clip_bounds[1] = radius_y;
+    builder_->AddOp(b);
+    DrawSurfaceImage(blurred, w, h, fb, work_paint, true);
     return;
   }
   // drop shadow: the blurred alpha tinted with the (unpremultiplied) shadow colour, offset, then the shape

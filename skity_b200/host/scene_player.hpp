@@ -18,7 +18,8 @@
 //            [shader: f32 p[4], u32 tile_mode, u32 n_colors, u32 n_stops, u32 has_local,
 //             f32 local[6] (sx kx tx ky sy ty), f32 rgba[4*n_colors], f32 stops[n_stops]]
 //            style bit 8 set => extras follow the shader block: u32 blend_mode (skity::BlendMode),
-//             u32 image_filter (0 none, 1 ImageFilters::Blur, 2 ImageFilters::DropShadow, 3 ImageFilters::Dilate),
+//             u32 image_filter (0 none, 1 ImageFilters::Blur, 2 ImageFilters::DropShadow, 3 ImageFilters::Dilate, 4 Erode: radii in sigma_x/y,
+//             5 ImageFilters::MatrixTransform(Translate(dx, dy))),
 //             f32 dx, f32 dy, f32 sigma_x, f32 sigma_y, u32 shadow colour (A<<24|R<<16|G<<8|B),
 //             u32 colour_filter (0 none, 1 ColorFilters::Blend, 2 Matrix, 3 LinearToSRGBGamma, 4 SRGBToLinearGamma),
 //             u32 filter colour, u32 filter blend mode, f32 matrix[20]
@@ -266,11 +267,13 @@ inline bool ReadPaint(Reader& r, skity::Paint* paint) {
     float f[4];
     r.Get(f, 16);
     uint32_t shadow = r.U32();
-    if (!r.ok() || blend > static_cast<uint32_t>(skity::BlendMode::kLastMode) || filter > 3) return false;
+    if (!r.ok() || blend > static_cast<uint32_t>(skity::BlendMode::kLastMode) || filter > 5) return false;
     paint->SetBlendMode(static_cast<skity::BlendMode>(blend));
     if (filter == 1) paint->SetImageFilter(skity::ImageFilters::Blur(f[2], f[3]));
     if (filter == 2) paint->SetImageFilter(skity::ImageFilters::DropShadow(f[0], f[1], f[2], f[3], shadow, nullptr));
     if (filter == 3) paint->SetImageFilter(skity::ImageFilters::Dilate(f[2], f[3]));
+    if (filter == 4) paint->SetImageFilter(skity::ImageFilters::Erode(f[2], f[3]));
+    if (filter == 5) paint->SetImageFilter(skity::ImageFilters::MatrixTransform(skity::Matrix::Translate(f[0], f[1])));
     uint32_t cf = r.U32(), cf_color = r.U32(), cf_mode = r.U32();
     float cm[20];
     r.Get(cm, 80);

@@ -465,6 +465,12 @@ def scene_filters(seed=33, size=512):
                      sigma=(float(rng.uniform(1, 5)), float(rng.uniform(1, 5))), color=0xC0102060 if j == 2 else 0xFF203010)
         s.draw_path(p, Paint(fill=col, image_filter=f))
         k += 1
+    if seed == 34:  # morphology image filters (a later addition: other seeds keep their committed fixtures)
+        for j, f in enumerate([dict(type=3, sigma=(3.0, 2.0)), dict(type=4, sigma=(2.0, 3.0)), dict(type=3, sigma=(4.0, 0.0)),
+                               dict(type=4, sigma=(0.0, 2.5)), dict(type=3, sigma=(0.5, 0.5))]):
+            p = _random_closed_path(rng, (j + 0.5) * size / 5, size * 0.5, size / 5.5, j)
+            s.draw_path(p, Paint(fill=tuple(rng.uniform(0, 1, 3)) + (float(rng.uniform(0.5, 1.0)),), image_filter=f))
+            s.draw_path(p, Paint(style=STROKE, stroke=(0.1, 0.1, 0.1, 0.8), stroke_width=3.0, image_filter=f))
     s.save()
     s.translate(size * 0.5, size * 0.85)
     s.rotate(-12)

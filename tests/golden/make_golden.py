@@ -83,6 +83,7 @@ def golden_scenes():
     out["golden_canonical_edges_192x144"] = s
     out["blend_modes_480"] = scene.scene_blend_modes()
     out["filters_512"] = scene.scene_filters()
+    out["filters_morphology_512"] = scene.scene_filters(34)
     out["layers_512"] = scene.scene_layers()
     out["filtered_layers_384"] = scene.scene_filtered_layers()
     out["conical_512"] = scene.scene_conical()

@@ -88,8 +88,8 @@ def test_display_list_structure_for_blur_and_strokes():
 @needs_host
 def test_unsupported_features_are_reported_not_approximated():
     s = Scene(64, 64)
-    # morphology image filters (ImageFilters::Dilate / Erode) are not implemented on the device
-    s.draw_rect(10, 10, 40, 40, Paint(image_filter=dict(type=3, sigma=(2.0, 2.0))))
+    # a matrix-transform image filter has no software implementation in the reference either (no OnFilter): refused
+    s.draw_rect(10, 10, 40, 40, Paint(image_filter=dict(type=5, offset=(3.0, 2.0))))
     with pytest.raises(RuntimeError):
         hostlib.encode_scene(s.encode())
 
