@@ -35,7 +35,7 @@ import numpy as np  # noqa: E402
 NCU_TRAFFIC = {("c1", "k_walk"): 33402624 + 120184576, ("c1", "k_cover"): 146342656 + 122601728,
                ("c1", "k_fine"): 235946240 + 47422208}
 
-E2E_LANES = 4      # surfaces (and host threads) the end-to-end loop keeps in flight
+E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # surfaces (and host threads) the end-to-end loop keeps in flight
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
 
