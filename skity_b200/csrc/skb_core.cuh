@@ -897,6 +897,87 @@ SKB_HDN uint32_t apply_color_filter(const uint32_t* blk, uint32_t c) {
   return (o[3] << 24) | (o[0] << 16) | (o[1] << 8) | o[2];
 }
 
+// atan2f as glibc 2.39 computes it (the fdlibm single-precision algorithm: e_atan2f.c / s_atanf.c, plain float
+// operations, no FMA): the sweep gradient's angle has to come out bit-identical to the reference's, because at a
+// hard colour stop or at the wrap of a repeating gradient the last bit of the angle decides which colour a pixel
+// takes.  CUDA's own atan2f differs in the last place.  Verified against the C library on 2*10^7 random inputs spanning 80 binades
+// (tests/test_sim_stages.py checks a sample on every run).  Special values follow the same branches.
+SKB_HD uint32_t f_bits(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+SKB_HDN float skb_atanf(float x) {
+  const float atanhi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+  const float atanlo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+  const float aT[11] = {3.3333334327e-01f, -2.0000000298e-01f, 1.4285714924e-01f, -1.1111110449e-01f,
+                        9.0908870101e-02f, -7.6918758452e-02f, 6.6610731184e-02f, -5.8335702866e-02f,
+                        4.9768779427e-02f, -3.6531571299e-02f, 1.6285819933e-02f};
+  const int32_t hx = (int32_t)f_bits(x), ix = hx & 0x7fffffff;
+  int id;
+  if (ix >= 0x4c800000) {  // |x| >= 2^26
+    if (ix > 0x7f800000) return x + x;
+    return hx > 0 ? atanhi[3] + atanlo[3] : -atanhi[3] - atanlo[3];
+  }
+  if (ix < 0x3ee00000) {  // |x| < 0.4375
+    if (ix < 0x31000000) return x;
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000) {  // |x| < 1.1875
+      if (ix < 0x3f300000) {
+        id = 0;
+        x = (2.0f * x - 1.0f) / (2.0f + x);
+      } else {
+        id = 1;
+        x = (x - 1.0f) / (x + 1.0f);
+      }
+    } else if (ix < 0x401c0000) {  // |x| < 2.4375
+      id = 2;
+      x = (x - 1.5f) / (1.0f + 1.5f * x);
+    } else {
+      id = 3;
+      x = -1.0f / x;
+    }
+  }
+  const float z = x * x, w = z * z;
+  const float s1 = z * (aT[0] + w * (aT[2] + w * (aT[4] + w * (aT[6] + w * (aT[8] + w * aT[10])))));
+  const float s2 = w * (aT[1] + w * (aT[3] + w * (aT[5] + w * (aT[7] + w * aT[9]))));
+  if (id < 0) return x - x * (s1 + s2);
+  const float r = atanhi[id] - ((x * (s1 + s2) - atanlo[id]) - x);
+  return hx < 0 ? -r : r;
+}
+SKB_HDN float skb_atan2f(float y, float x) {
+  const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+              pi_lo = -8.7422776573e-08f;
+  const int32_t hx = (int32_t)f_bits(x), ix = hx & 0x7fffffff, hy = (int32_t)f_bits(y), iy = hy & 0x7fffffff;
+  if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+  if (hx == 0x3f800000) return skb_atanf(y);
+  const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+  if (iy == 0) return m < 2 ? y : (m == 2 ? pi + tiny : -pi - tiny);
+  if (ix == 0) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  if (ix == 0x7f800000) {
+    if (iy == 0x7f800000) return m == 0 ? pi_o_4 + tiny : (m == 1 ? -pi_o_4 - tiny : (m == 2 ? 3.0f * pi_o_4 + tiny : -3.0f * pi_o_4 - tiny));
+    return m == 0 ? 0.0f : (m == 1 ? -0.0f : (m == 2 ? pi + tiny : -pi - tiny));
+  }
+  if (iy == 0x7f800000) return hy < 0 ? -pi_o_2 - tiny : pi_o_2 + tiny;
+  const int32_t k = (iy - ix) >> 23;
+  float z;
+  if (k > 24) z = pi_o_2 + 0.5f * pi_lo;       // |y/x| > 2^24
+  else if (hx < 0 && k < -26) z = 0.0f;        // |y|/x < -2^26
+  else z = skb_atanf(fabsf(y / x));
+  switch (m) {
+    case 0: return z;
+    case 1: return -z;
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+  }
+}
+
 // GradientColorBrush::LerpColor (sw_span_brush.cc:21-32,239-299) -> premultiplied pixel word
 SKB_HDN uint32_t gradient_color(const skb_dl_paint& p, const float* pool, float t) {
   const float* colors = pool + p.stop_off;
@@ -1036,7 +1117,7 @@ SKB_HDN uint32_t paint_color(const skb_dl_paint& p, const float* pool, const Sur
     case SKB_PAINT_RADIAL:
       return gradient_color(p, pool, sqrtf(u * u + v * v));
     case SKB_PAINT_SWEEP: {
-      float angle = atan2f(-v, -u);
+      float angle = skb_atan2f(-v, -u);  // glibc's, bit for bit
       const float k1Over2Pi = 0.1591549430918f;
       float t = (float)(((double)(angle * k1Over2Pi) + 0.5 + (double)p.bias) * (double)p.scale);
       return gradient_color(p, pool, t);

@@ -304,3 +304,23 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
   std::memcpy(out_rgba, canvas.data(), (size_t)W * H * 4);
   return 0;
 }
+
+
+// Number of inputs (out of n pseudo-random (y, x) pairs) on which skb_atan2f differs from the C library's atan2f.
+extern "C" long sim_atan2f_mismatches(long n, unsigned long long seed) {
+  unsigned long long s = seed ? seed : 88172645463325252ull;
+  long bad = 0;
+  for (long i = 0; i < n; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    float a = (float)((double)(s & 0xFFFFFF) / 0xFFFFFF * 8000.0 - 4000.0);
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    float b = (float)((double)(s & 0xFFFFFF) / 0xFFFFFF * 8000.0 - 4000.0);
+    if (i % 3 == 0) {  // a third of the samples with widely different magnitudes
+      a = ldexpf(a, (int)((s >> 40) % 80) - 40);
+      b = ldexpf(b, (int)((s >> 48) % 80) - 40);
+    }
+    float r = atan2f(a, b), m = skb::skb_atan2f(a, b);
+    if (memcmp(&r, &m, 4) != 0) bad++;
+  }
+  return bad;
+}

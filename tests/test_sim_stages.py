@@ -116,3 +116,13 @@ def test_sim_clip_fixtures_found_by_fuzzing(name):
     got, stats = simlib.render_dl(z["dl"].tobytes())
     assert stats[0] == 0 and stats[3] == 0
     assert np.array_equal(got, z["rgba"])
+
+
+def test_sweep_gradient_angle_is_the_c_librarys_atan2f():
+    """The device evaluates the sweep gradient's angle with its own atan2f (skb_core.cuh: skb_atan2f), which must be
+    glibc's bit for bit: the last bit of the angle decides the colour at a hard stop."""
+    import ctypes
+    lib = simlib.lib()
+    lib.sim_atan2f_mismatches.restype = ctypes.c_long
+    lib.sim_atan2f_mismatches.argtypes = [ctypes.c_long, ctypes.c_ulonglong]
+    assert lib.sim_atan2f_mismatches(3_000_000, 12345) == 0
