@@ -158,31 +158,30 @@ SKB_HDN int update_quad(Edge& e, QuadState& q) {
   fx newx = 0, newy = 0, nsx = 0, nsy = 0;
   const int shift = edge_shift(e);
   do {
-    fx slope;
+    // The three cases of the reference (a chord stepping >= 2 px in y snaps to whole pixels and moves x along
+    // the chord, a shorter one snaps to quarter pixels, the last chord ends on the curve's end point) differ
+    // only in which y the slope is taken to and in how the snapped end is formed, so they share ONE division:
+    // lanes of a warp that are in different cases stay converged through the expensive part.
+    bool steep = false;
+    fx slope_y;
     if (--count > 0) {
+      const fx sdy = dy >> shift;
       newx = fx_add(oldx, dx >> shift);
-      newy = fx_add(oldy, dy >> shift);
-      if (fx_abs(dy >> shift) >= SKB_FX1 * 2) {
-        fx diffy = fx_sub(newy, q.snapped_y) >> 10;
-        slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
-        nsy = fx_min(q.q_last_y, fx_round_fx(newy));
-        nsx = fx_sub(newx, fx_mul(slope, fx_sub(newy, nsy)));
-      } else {
-        nsy = fx_min(q.q_last_y, snap_y(newy));
-        nsx = newx;
-        fx diffy = fx_sub(nsy, q.snapped_y) >> 10;
-        slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
-      }
+      newy = fx_add(oldy, sdy);
+      steep = fx_abs(sdy) >= SKB_FX1 * 2;
+      nsy = fx_min(q.q_last_y, steep ? fx_round_fx(newy) : snap_y(newy));
+      slope_y = steep ? newy : nsy;
       dx = fx_add(dx, q.qddx);
       dy = fx_add(dy, q.qddy);
     } else {
       newx = q.q_last_x;
       newy = q.q_last_y;
       nsy = newy;
-      nsx = newx;
-      fx diffy = fx_sub(newy, q.snapped_y) >> 10;
-      slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+      slope_y = newy;
     }
+    const fx diffy = fx_sub(slope_y, q.snapped_y) >> 10;
+    const fx slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+    nsx = steep ? fx_sub(newx, fx_mul(slope, fx_sub(newy, nsy))) : newx;
     if (slope < SKB_FX_MAX) success = update_line(e, q.snapped_x, q.snapped_y, nsx, nsy, slope);
     oldx = newx;
     oldy = newy;

@@ -1,7 +1,8 @@
-"""Per-source-line summary of an ncu report (manual tool): python tests/ncu_lines.py rep.ncu-rep [top]"""
+"""Per-source-line summary of an ncu report (manual tool): python tests/ncu_lines.py rep.ncu-rep [top [kernel-regex]]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["-k", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
 hdr = rows[hi]
