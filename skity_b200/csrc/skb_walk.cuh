@@ -489,12 +489,20 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
       y_shift = 1;                                                              \
     }                                                                           \
     full = (uint32_t)(uint8_t)fx_round_i((fx)(0xFF * fx_sub(next_y, y)));       \
+    cur_upper = E[cur].upper_y;                                                 \
+    lk_real = false;                                                            \
   } while (0)
+  // cur_upper = E[cur].upper_y, loaded one iteration ahead (nothing an iteration does changes the upper_y of the
+  // edge after it).  lk_*: the edge that sits right before the not-yet-visited part of the list — the last visited
+  // edge that stayed where it was — as registers: its x + dx is all check_intersection needs of it.
+  fx cur_upper = 0, lk_sum = 0;
+  bool lk_real = false;
   SKB_BEGIN_BAND();
   bool done = false;
   while (!done) {
-    if (E[cur].upper_y <= y) {
+    if (cur_upper <= y) {
       Edge c = E[cur];
+      const fx next_upper = E[c.next].upper_y;
       w += edge_winding(c);
       const bool prev_in = in_interval;
       in_interval = (w & mask) != 0;
@@ -552,13 +560,26 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
         remove_edge(E, cur);
       } else {
         upd_nny(c.lower_y, next_y, &nny);
-        if (c.x < prev_x) backward_insert_on_x(E, cur);
-        else prev_x = c.x;
-        check_intersection(E, cur, next_y, &nny);
+        const fx sum = fx_add(c.x, c.dx);
+        if (c.x < prev_x) {
+          backward_insert_on_x(E, cur);
+          check_intersection(E, cur, next_y, &nny);
+          if (E[cur].next == next) {  // not moved (only the head was before it)
+            lk_real = true;
+            lk_sum = sum;
+          }
+        } else {
+          prev_x = c.x;
+          // check_intersection with the previous edge's x + dx at hand
+          if (lk_real && lk_sum > sum) nny = fx_add(next_y, SKB_FX1 >> 2);
+          lk_real = true;
+          lk_sum = sum;
+        }
       }
       cur = next;
+      cur_upper = next_upper;
     }
-    if (E[cur].upper_y > y) {
+    if (cur_upper > y) {
       if (in_interval) {
         TrapRec r;
         r.y = y >> 16;
