@@ -258,11 +258,18 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
 // thread slots, the paths are therefore SPREAD: only every (32/lanes)-th lane of a warp carries a
 // path, which cuts the divergence per warp and multiplies the number of warps the schedulers can
 // interleave.  k_walk_list first compacts the non-empty ops into a list.
-__global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, uint32_t* list) {
+// Also writes the owner of every tile row (trow_op): the coverage and clip stages start from a tile row or a
+// pixel row and would otherwise find its op by a binary search over row_base — 20 dependent loads at 1M ops.
+__global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, uint32_t* list, const uint32_t* row_base,
+                            uint32_t* trow_op) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const OpGeom g = geom[op];
   if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  {
+    uint32_t* o = trow_op + row_base[op] / SKB_TILE;
+    for (int r = 0; r < g.nty; r++) o[r] = op;
+  }
   // warp-aggregated append
   const unsigned m = __activemask();
   const int lane = threadIdx.x & 31;
@@ -334,6 +341,7 @@ struct CoverArgs {
   const OpGeom* geom;
   const uint32_t* item_base;  // n_ops + 1
   const uint32_t* row_base;
+  const uint32_t* trow_op;    // owner of every tile row (n_trows)
   uint32_t n_ops, n_items, n_trows;
   const skb_dl_op* ops;
   const SurfDesc* surfs;
@@ -404,7 +412,7 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
   const int lane = threadIdx.x & 31;
   if (trow >= c.n_trows) return;
   CoverWarpSmem& sm = sm_all[wib];
-  const uint32_t op = find_interval(c.row_base, c.n_ops, trow * SKB_TILE);
+  const uint32_t op = c.trow_op[trow];
   const OpGeom g = c.geom[op];
   const uint32_t tr = trow - c.row_base[op] / SKB_TILE;
   const int ty = g.ty0 + (int)tr;
@@ -463,11 +471,11 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
         int units = 0;
         if (p < npass) {
           const int P = pbase + p;
-          int rr_ = 0;  // the row that owns record P: the last row with records whose prefix is <= P
-#pragma unroll
-          for (int r = 0; r < 16; r++) {
-            if (sm.r_cnt[r] > 0 && sm.r_pre[r] <= P) rr_ = r;
-          }
+          // the row that owns record P: the last row whose prefix is <= P (it has records: the next prefix is > P)
+          int rr_ = sm.r_pre[8] <= P ? 8 : 0;
+          rr_ += sm.r_pre[rr_ + 4] <= P ? 4 : 0;
+          rr_ += sm.r_pre[rr_ + 2] <= P ? 2 : 0;
+          rr_ += sm.r_pre[rr_ + 1] <= P ? 1 : 0;
           const uint32_t first = sm.r_first[rr_];
           // k-th record of the row: consecutive slots, the last slot of every chunk links to the next chunk
           uint32_t pos = (first & (SKB_CHUNK - 1)) + (uint32_t)(P - sm.r_pre[rr_]);
@@ -699,7 +707,7 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   if (r >= a.n_rows) return;
   const int seg = (int)(threadIdx.x & 31);
   const CoverArgs& c = a.c;
-  const uint32_t op = find_interval(c.row_base, c.n_ops, r);
+  const uint32_t op = c.trow_op[r / SKB_TILE];
   const skb_dl_op o = c.ops[op];
   if (mode == 0) {
     if (o.kind != SKB_OP_CLIP || a.op_depth[op] != (uint8_t)level) return;
@@ -1343,7 +1351,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -1355,6 +1363,14 @@ namespace skb {
 
 __global__ void k_fetch_words(uint32_t* dst, const uint32_t* src, int n) {
   if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+}
+
+__global__ void k_gather3(uint32_t* dst, const uint32_t* a, const uint32_t* b, const uint32_t* c) {
+  if (threadIdx.x == 0) {
+    dst[0] = *a;
+    dst[1] = *b;
+    dst[2] = *c;
+  }
 }
 
 // Brings n (<= 16) device words to the host and waits for them.
@@ -1663,11 +1679,11 @@ static skb_result run_frame(skb_surface s) {
       launches++;
       SKB_TRY(scan_exclusive(s, row_base, n_ops + 1, &launches));
       SKB_TRY(scan_exclusive(s, item_base, n_ops + 1, &launches));
-      uint32_t tot[2] = {0, 0}, too_big = 0;
-      SKB_TRY(fetch_words(s, &tot[0], row_base + n_ops, 1));
-      SKB_TRY(fetch_words(s, &tot[1], item_base + n_ops, 1));
-      SKB_TRY(fetch_words(s, &too_big, counters + 6, 1));
-      launches += 3;
+      uint32_t tot[3] = {0, 0, 0};  // one round trip for the three words
+      k_gather3<<<1, 32, 0, st>>>(counters + 8, row_base + n_ops, item_base + n_ops, counters + 6);
+      SKB_TRY(fetch_words(s, tot, counters + 8, 3));
+      const uint32_t too_big = tot[2];
+      launches += 2;
       if (too_big) {
         set_error("the scan rectangle of a clip path exceeds 2^28 pixels (it reaches far beyond the surface)");
         return SKB_ERROR_UNSUPPORTED;
@@ -1681,6 +1697,7 @@ static skb_result run_frame(skb_surface s) {
       if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
       pool_cap = (uint32_t)want;
       SKB_TRY(buf_reserve(s->rows, (n_rows + 1) * sizeof(uint2)));
+      SKB_TRY(buf_reserve(s->trow_op, (n_rows / SKB_TILE + 1) * 4));
       SKB_TRY(buf_reserve(s->mask0, (n_items + 1) * 256));
       SKB_TRY(buf_reserve(s->mask1, (n_items + 1) * 256));
       SKB_TRY(buf_reserve(s->item_flags, 2 * n_items + 16));
@@ -1696,7 +1713,8 @@ static skb_result run_frame(skb_surface s) {
     if (n_rows) SKB_CUDA(cudaMemsetAsync(s->rows.p, 0, n_rows * sizeof(uint2), st));
     {
       // counters: [0] pool_next, [1] overflow, [4] number of ops to sweep
-      k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p);
+      k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p, row_base,
+                                                    (uint32_t*)s->trow_op.p);
       launches++;
       WalkArgs wa;
       wa.t = t;
@@ -1742,6 +1760,7 @@ static skb_result run_frame(skb_surface s) {
   ca.geom = geom;
   ca.item_base = item_base;
   ca.row_base = row_base;
+  ca.trow_op = (const uint32_t*)s->trow_op.p;
   ca.n_ops = n_ops;
   ca.n_items = (uint32_t)n_items;
   ca.n_trows = (uint32_t)(n_rows / SKB_TILE);
@@ -2116,7 +2135,7 @@ void skb_surface_destroy(skb_surface s) {
   if (!s) return;
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->pool,
+  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
