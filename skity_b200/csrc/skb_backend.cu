@@ -1047,11 +1047,37 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
         img.h = is.h;
         img.pitch = is.pitch;
       }
-#pragma unroll 1
       const uint32_t mode = paint_blend_mode(pt);
       // a colour filter can turn a zero source into something: then zero-coverage pixels matter as well
       const uint32_t* cf = SKB_PAINT_CF_OFFSET(pt) ? reinterpret_cast<const uint32_t*>(a.stops) + (SKB_PAINT_CF_OFFSET(pt) - 1) : nullptr;
       const bool zmode = blend_zero_src_matters(mode) || cf != nullptr;
+      if (ptype == SKB_PAINT_IMAGE && !(pt.tile_mode & SKB_PAINT_IMAGE_LINEAR)) {
+        // Nearest-sampled image (blurred temporaries, layers, DrawImage): the same per-pixel work as the general
+        // loop below with what is constant over the tile kept in registers — paint_color()'s matrix row for this
+        // pixel row, the tile modes, the blend mode (SrcOver inline).
+        const float fyc = y + 0.5f;
+        const float uy = fyc * pt.m[1], vy = fyc * pt.m[4];
+        const float m0 = pt.m[0], m2 = pt.m[2], m3 = pt.m[3], m5 = pt.m[5];
+        const uint32_t tmode = pt.tile_mode;
+#pragma unroll 2
+        for (int j = 0; j < 8; j++) {
+          uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
+          const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
+          cv &= galpha;
+          if (cv || (touched && zmode)) {
+            const float fxc = (x0 + j) + 0.5f;
+            const float u = fxc * m0 + uy + m2;  // paint_color: fxc * m[0] + fyc * m[1] + m[2], same order
+            const float v = fxc * m3 + vy + m5;
+            uint32_t src = swap_rb(sample_image_nearest(tmode, img, u, v, s_requant));
+            if (cv != 255) src = alpha_mul_q(src, cv);
+            if (cf) src = apply_color_filter(cf, src);
+            if (mode == SKB_BLEND_SRC_OVER) dst[j] = (src >> 24) == 0 ? dst[j] : src + alpha_mul_q(dst[j], 256 - (src >> 24));
+            else dst[j] = porter_duff(src, dst[j], mode);
+          }
+        }
+        continue;
+      }
+#pragma unroll 1
       for (int j = 0; j < 8; j++) {
         uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
         // a span reaches the pixel when its coverage is non-zero, or zero on a direct span (zmask)

@@ -1054,22 +1054,39 @@ SKB_HD uint32_t image_texel(const SurfaceView& s, float fx_, float fy_) {  // Sa
   if (iy > s.h - 1) iy = s.h - 1;
   return *reinterpret_cast<const uint32_t*>(s.px + (size_t)iy * s.pitch + (size_t)ix * 4);  // R | G<<8 | B<<16 | A<<24
 }
+// The nearest sampler on its own (forced inline: the fine pass runs it in a loop specialised for image paints, with
+// `tile_mode` in a register).
+SKB_HD uint32_t sample_image_nearest(uint32_t tile_mode, const SurfaceView& s, float u, float v, const uint8_t* requant_lut) {
+  const uint32_t xmode = tile_mode & 0xF;
+  const uint32_t ymode = (tile_mode & SKB_PAINT_IMAGE_YMODE) ? ((tile_mode >> 4) & 0xF) : xmode;
+  if ((xmode == 3 && (u < 0.0f || u >= 1.0f)) || (ymode == 3 && (v < 0.0f || v >= 1.0f))) return 0;
+  u = remap_tile(u, xmode);
+  v = remap_tile(v, ymode);
+  uint32_t r, g, b, a;
+  const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h);
+  const uint32_t t0 = t & 0xFF, t1 = (t >> 8) & 0xFF, t2 = (t >> 16) & 0xFF, t3 = t >> 24;
+  if (requant_lut) {
+    r = requant_lut[t0]; g = requant_lut[t1]; b = requant_lut[t2]; a = requant_lut[t3];
+  } else {
+    r = requant(t0); g = requant(t1); b = requant(t2); a = requant(t3);
+  }
+  // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
+  if ((tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
+    r = mul_div_255_round(r, a);
+    g = mul_div_255_round(g, a);
+    b = mul_div_255_round(b, a);
+  }
+  return r | (g << 8) | (b << 16) | (a << 24);
+}
 SKB_HDN uint32_t sample_image(const skb_dl_paint& p, const SurfaceView& s, float u, float v, const uint8_t* requant_lut) {
+  if (!(p.tile_mode & SKB_PAINT_IMAGE_LINEAR)) return sample_image_nearest(p.tile_mode, s, u, v, requant_lut);
   const uint32_t xmode = p.tile_mode & 0xF;
   const uint32_t ymode = (p.tile_mode & SKB_PAINT_IMAGE_YMODE) ? ((p.tile_mode >> 4) & 0xF) : xmode;
   if ((xmode == 3 && (u < 0.0f || u >= 1.0f)) || (ymode == 3 && (v < 0.0f || v >= 1.0f))) return 0;
   u = remap_tile(u, xmode);
   v = remap_tile(v, ymode);
   uint32_t r, g, b, a;
-  if (!(p.tile_mode & SKB_PAINT_IMAGE_LINEAR)) {
-    const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h);
-    const uint32_t t0 = t & 0xFF, t1 = (t >> 8) & 0xFF, t2 = (t >> 16) & 0xFF, t3 = t >> 24;
-    if (requant_lut) {
-      r = requant_lut[t0]; g = requant_lut[t1]; b = requant_lut[t2]; a = requant_lut[t3];
-    } else {
-      r = requant(t0); g = requant(t1); b = requant(t2); a = requant(t3);
-    }
-  } else {  // SampleUnitLinear (:44-83)
+  {  // SampleUnitLinear (:44-83)
     const float w = (float)s.w, h = (float)s.h;
     float x = u * w, y = v * h;
     float i0 = floorf(x - 0.5f), j0 = floorf(y - 0.5f);

@@ -529,7 +529,7 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
         if (full == 0xFF) {
           const int nx = c.next;  // too_close_edges(cur, cur->next, next_y) with cur's advanced x
           no_real = (prev_right > fx_floor_i(left) || prev_right > fx_floor_i(le_x)) ||
-                    (E[nx].upper_y < next_y && fx_add(c.x, SKB_FX1) >= fx_sub(E[nx].x, fx_abs(E[nx].dx)));
+                    (next_upper < next_y && fx_add(c.x, SKB_FX1) >= fx_sub(E[nx].x, fx_abs(E[nx].dx)));
         }
         r.flags = full | (no_real ? 0x100u : 0u);
         sink_emit(sink, r);
@@ -548,10 +548,9 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
           break;
         }
       }
-      // write back what changed (the links are edited in place below): x and y always, the rest only when the
-      // edge took its next chord
+      // write back what changed (the links are edited in place below): x always, the rest only when the edge took
+      // its next chord (y is not read again: this loop sets it to next_y whenever it loads an edge)
       E[cur].x = c.x;
-      E[cur].y = c.y;
       if (chord) {
         E[cur].dx = c.dx; E[cur].dy = c.dy;
         E[cur].upper_x = c.upper_x; E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
