@@ -1154,26 +1154,52 @@ __global__ void k_morph(const uint8_t* src, uint32_t src_pitch, uint8_t* dst, ui
   *reinterpret_cast<uint32_t*>(dst + (size_t)y * dst_pitch + (size_t)x * 4) = acc;
 }
 
-// Horizontal pass: one WARP per (job, row).  Each lane owns a run of consecutive samples of the extended row
-// (n + 2m + 1 samples): it sums them (T), the lane totals are scanned with shuffles, it then builds its part of U
-// (prefix of T) in shared memory, the totals are scanned again; the output loop reads U at the three positions.
-// No block-wide barrier: a block is BLUR_H_WARPS independent warps sharing the dynamic shared memory.
+// Horizontal pass: one BLOCK of BLUR_H_WARPS warps per (job, row).  The source row comes into shared memory with one
+// bulk copy (TMA, cp.async.bulk + mbarrier).  Each thread owns a run of consecutive samples of the extended row
+// (n + 2m + 1 samples): it sums them (T), the thread totals are scanned (shuffles, then across the warps), it then
+// builds its part of U (prefix of T) in shared memory, the totals are scanned again; the output loop reads U at the
+// three positions.  Measured on C3 (2k paths, 8192^2; the H pass alone): runs read from global memory, even run
+// length 5.9 ms; odd run length (no bank conflicts on U) 5.0 ms; row staged by TMA 4.7 ms; two warps per row instead
+// of one (the shared memory a row needs limits the rows in flight, so more threads per row) see DESIGN.md.
+#ifndef BLUR_H_WARPS
 #define BLUR_H_WARPS 2
-__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane) {
-  uint32_t inc = v;
+#endif
+#ifndef BLUR_H_TMA
+#define BLUR_H_TMA 1
+#endif
+// exclusive scan of one value per thread over the block's threads (in thread order), four channels at once
+__device__ __forceinline__ void blur_row_scan(const uint32_t v[4], uint32_t off[4], int lane, int wib, uint32_t (*tot)[4]) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= d) inc += t;
+  for (int c = 0; c < 4; c++) {
+    uint32_t inc = v[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    off[c] = inc - v[c];
+    if (BLUR_H_WARPS > 1 && lane == 31) tot[wib][c] = inc;
   }
-  return inc - v;
+  if (BLUR_H_WARPS > 1) {
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < BLUR_H_WARPS - 1; w++) {
+      if (w < wib) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) off[c] += tot[w][c];
+      }
+    }
+    __syncthreads();
+  }
 }
 __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* jobs, const uint32_t* job_row_base, uint32_t n_jobs,
                                                               const SurfDesc* surfs, uint32_t first_row, uint32_t end_row,
                                                               uint32_t max_len) {
-  extern __shared__ uint32_t sm[];  // per warp: U[4][max_len]
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t grow = first_row + blockIdx.x * BLUR_H_WARPS + wib;
+  // U[max_len] (uint4), the source row (max_len words), the warps' scan totals, one mbarrier
+  extern __shared__ __align__(16) uint32_t sm[];
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int NT = BLUR_H_WARPS * 32;
+  const uint32_t grow = first_row + blockIdx.x;
   if (grow >= end_row) return;
   const uint32_t job = find_interval(job_row_base, n_jobs, grow);
   const BlurJob jb = jobs[job];
@@ -1185,18 +1211,50 @@ __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* job
   if (jb.style >= 6) return;  // dilate / erode: k_morph
   int r = jb.radius > 254 ? 254 : jb.radius;
   if (r <= 1) {
-    for (int x = lane; x < n; x += 32) drow[x] = srow[x];
+    for (int x = tid; x < n; x += NT) drow[x] = srow[x];
     return;
   }
   const int m = r + 1;
   const int len = n + 2 * m + 1;  // extended index j = k - m for k in [0, len): j in [-m, n+m]
-  uint4* U = reinterpret_cast<uint4*>(sm) + (size_t)wib * max_len;  // U[k] = the four channels' exclusive double prefix
-  const int chunk = (len + 31) / 32;
-  const int k0 = min(lane * chunk, len), k1 = min(k0 + chunk, len);
+  uint4* U = reinterpret_cast<uint4*>(sm);  // U[k] = the four channels' exclusive double prefix
+  uint32_t* rowbuf = reinterpret_cast<uint32_t*>(U + max_len);
+  uint32_t(*tot)[4] = reinterpret_cast<uint32_t(*)[4]>(rowbuf + max_len);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tot + BLUR_H_WARPS);
+#if BLUR_H_TMA
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+  if (tid == 0) {
+    const uint32_t bytes = ((uint32_t)n * 4u + 15u) & ~15u;  // the pitch is padded to whole tiles: reading on is safe
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(rowbuf)),
+                 "l"(srow), "r"(bytes), "r"(bar_a)
+                 : "memory");
+  }
+  if (BLUR_H_WARPS > 1) __syncthreads();  // the barrier word is initialised before anyone waits on it
+  else __syncwarp();
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "BLUR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra BLUR_DONE;\n"
+      "bra BLUR_WAIT;\n"
+      "BLUR_DONE:\n"
+      "}" ::"r"(bar_a)
+      : "memory");
+  const uint32_t* rsrc = rowbuf;
+#else
+  const uint32_t* rsrc = srow;
+#endif
+  // an odd run length keeps the threads' 128-bit accesses to U (and their reads of the staged row) on different banks
+  const int chunk = ((len + NT - 1) / NT) | 1;
+  const int k0 = min(tid * chunk, len), k1 = min(k0 + chunk, len);
   auto sample = [&](int k) -> uint32_t {
     int j = k - m;
     j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
-    return srow[j];
+    return rsrc[j];
   };
   // T: totals of my run, scanned
   uint32_t acc[4] = {0, 0, 0, 0};
@@ -1206,8 +1264,7 @@ __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* job
     for (int c = 0; c < 4; c++) acc[c] += (px >> (8 * c)) & 0xFF;
   }
   uint32_t t_off[4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) t_off[c] = warp_excl_scan(acc[c], lane);
+  blur_row_scan(acc, t_off, lane, wib, tot);
   // U: exclusive prefix of T over my run, totals scanned, offsets added
   uint32_t tv[4], ua[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -1222,17 +1279,17 @@ __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* job
     }
   }
   uint32_t u_off[4];
-#pragma unroll
-  for (int c = 0; c < 4; c++) u_off[c] = warp_excl_scan(ua[c], lane);
+  blur_row_scan(ua, u_off, lane, wib, tot);
   for (int k = k0; k < k1; k++) {
     uint4 v = U[k];
     U[k] = make_uint4(v.x + u_off[0], v.y + u_off[1], v.z + u_off[2], v.w + u_off[3]);
   }
-  __syncwarp();
+  if (BLUR_H_WARPS > 1) __syncthreads();
+  else __syncwarp();
   uint32_t mul;
   int shr;
   blur_mul_shr(r, &mul, &shr);
-  for (int x = lane; x < n; x += 32) {
+  for (int x = tid; x < n; x += NT) {
     // extended index j maps to k = j + m;  U[j] here means prefix over samples < j
     const uint4 ul = U[x + m + 1 + m], um = U[x + 1 + m], ug = U[x - m + 1 + m];
     const uint32_t s0 = ul.x - 2u * um.x + ug.x, s1 = ul.y - 2u * um.y + ug.y;
@@ -1968,7 +2025,9 @@ static skb_result run_frame(skb_surface s) {
       tmp_bytes += (size_t)d.pitch * d.tiles_y * SKB_TILE;
     }
     blur_max_len = (uint32_t)max_len;
-    blur_smem = max_len * 16 * BLUR_H_WARPS;
+    max_len = (max_len + 3) & ~(size_t)3;
+    blur_max_len = (uint32_t)max_len;
+    blur_smem = max_len * 16 + max_len * 4 + 16 * BLUR_H_WARPS + 16;
     if (blur_smem > 200 * 1024) {
       set_error("blur: surface too wide for the shared-memory row scan");
       return SKB_ERROR_UNSUPPORTED;
@@ -2010,7 +2069,7 @@ static skb_result run_frame(skb_surface s) {
     uint32_t j1 = j0;
     while (j1 < nj && surfs[jobs[j1].dst].level == level) j1++;
     if (j1 > j0) {
-      k_blur_h<<<cdiv(rowb[j1] - rowb[j0], BLUR_H_WARPS), BLUR_H_WARPS * 32, blur_smem, st>>>(
+      k_blur_h<<<rowb[j1] - rowb[j0], BLUR_H_WARPS * 32, blur_smem, st>>>(
           (const BlurJob*)s->blur_jobs.p, (const uint32_t*)s->blur_rows.p, nj, (const SurfDesc*)s->scan_tmp.p, rowb[j0], rowb[j1],
           blur_max_len);
       launches++;
