@@ -507,7 +507,11 @@ SKB_HD uint8_t alpha_above_at(int j, fx l, fx r, fx dY, uint32_t full) {
 
 // blit_aaa_trapezoid_row at pixel x (sw_raster.cc:370-455). `accum` = the row goes through the
 // accumulating SpanBuilder (partial-height band or "too close"), which scales single alphas.
-SKB_HDN bool aaa_row_at(int x, fx ul, fx ur, fx ll, fx lr, fx lDY, fx rDY, uint32_t full, bool accum, uint8_t* out) {
+// `side` (a compile-time constant at every call): 0 = both slanted sides; 1 / 2 = only the left / right one, for the
+// calls whose other side is the vertical join line — there its two tests (`u + 2 == l`, `x` beyond it) cannot hold for
+// a pixel of the zone, so leaving them out changes nothing but the code the compiler has to schedule.
+SKB_HD bool aaa_row_at(int x, fx ul, fx ur, fx ll, fx lr, fx lDY, fx rDY, uint32_t full, bool accum, uint8_t* out,
+                       const int side = 0) {
   int L = fx_floor_i(ul), R = fx_ceil_i(lr);
   int len = R - L;
   if (x < L || x >= R) return false;
@@ -519,7 +523,8 @@ SKB_HDN bool aaa_row_at(int x, fx ul, fx ur, fx ll, fx lr, fx lDY, fx rDY, uint3
   int i = x - L;
   uint32_t a = full;
   int uL = L, lL = fx_ceil_i(ll);
-  if (uL + 2 == lL) {
+  if (side == 2) {
+  } else if (uL + 2 == lL) {
     fx first = fx_sub(fx_add(i_to_fx(uL), SKB_FX1), ul);
     fx second = fx_sub(fx_sub(ll, ul), first);
     if (i == 0) {
@@ -534,7 +539,8 @@ SKB_HDN bool aaa_row_at(int x, fx ul, fx ur, fx ll, fx lr, fx lDY, fx rDY, uint3
     a = a > t ? a - t : 0;
   }
   int uR = fx_floor_i(ur), lR = R;
-  if (uR + 2 == lR) {
+  if (side == 1) {
+  } else if (uR + 2 == lR) {
     fx first = fx_sub(fx_add(i_to_fx(uR), SKB_FX1), ur);
     fx second = fx_sub(fx_sub(lr, ur), first);
     if (i == len - 2) {
@@ -713,7 +719,7 @@ SKB_HDN bool trap_prep_alpha(const TrapPrep& p, int x, uint8_t* out) {
       *out = x == p.L ? partial_triangle_to_alpha(first, p.ldy) : (uint8_t)(p.full - partial_triangle_to_alpha(second, p.ldy));
       return true;
     }
-    return aaa_row_at(x, p.ul, p.join_left, p.ll, p.join_left, p.ldy, SKB_FX_MAX, p.full, p.accum, out);
+    return aaa_row_at(x, p.ul, p.join_left, p.ll, p.join_left, p.ldy, SKB_FX_MAX, p.full, p.accum, out, 1);
   }
   int len = p.R - p.jr;
   if (len == 1) {
@@ -727,7 +733,7 @@ SKB_HDN bool trap_prep_alpha(const TrapPrep& p, int x, uint8_t* out) {
     *out = x == p.jr ? (uint8_t)(p.full - partial_triangle_to_alpha(first, p.rdy)) : partial_triangle_to_alpha(second, p.rdy);
     return true;
   }
-  return aaa_row_at(x, p.join_rite, p.ur, p.join_rite, p.lr, SKB_FX_MAX, p.rdy, p.full, p.accum, out);
+  return aaa_row_at(x, p.join_rite, p.ur, p.join_rite, p.lr, SKB_FX_MAX, p.rdy, p.full, p.accum, out, 2);
 }
 
 // ------------------------------------------------------------- colour and blend
