@@ -376,6 +376,9 @@ struct CoverArgs {
 #ifndef COVER_UNIT
 #define COVER_UNIT 2                 // edge pixels evaluated per work unit
 #endif
+#ifndef COVER_INLINE_PX
+#define COVER_INLINE_PX 8            // records with at most this many edge-zone pixels are evaluated by the lane that summarised them
+#endif
 
 struct alignas(16) CoverWarpSmem {
   uint32_t D[16][COVER_CW / 4];      // directly emitted coverage, one byte per pixel
@@ -500,7 +503,24 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
           sm.z_jl[p] = (int16_t)(jl - cx);
           sm.z_jr[p] = (int16_t)(jr - cx);
           sm.z_fa[p] = (uint16_t)(pr.full | (pr.accum ? 0x100u : 0u) | ((uint32_t)rr_ << 12));
-          units = (jl - L + COVER_UNIT - 1) / COVER_UNIT + (R - jr + COVER_UNIT - 1) / COVER_UNIT;
+          if ((jl - L) + (R - jr) <= COVER_INLINE_PX) {
+            // short edge zones (steep edges: a pixel or two per side) are evaluated right here, while the prepared
+            // record is in registers; only the long ones go to the unit queue, where all lanes share them
+            for (int xr = L - cx; xr < R - cx; xr++) {
+              if (xr == jl - cx) xr = jr - cx;
+              if (xr >= R - cx) break;
+              uint8_t v = 0;
+              if (!trap_prep_alpha(pr, cx + xr, &v)) continue;
+              if (v == 0) {
+                if (zmode && !pr.accum) atomicAdd(&Aw[(rr_ * COVER_CW + xr) >> 1], 0x8000u << (16 * (xr & 1)));
+                continue;
+              }
+              if (pr.accum) atomicAdd(&Aw[(rr_ * COVER_CW + xr) >> 1], (uint32_t)v << (16 * (xr & 1)));
+              else Db[rr_ * COVER_CW + xr] = v;
+            }
+          } else {
+            units = (jl - L + COVER_UNIT - 1) / COVER_UNIT + (R - jr + COVER_UNIT - 1) / COVER_UNIT;
+          }
         }
         sm.z_base[p] = units;
       }
