@@ -1007,7 +1007,23 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   uint32_t dst[8] = {swap_rb(q0.x), swap_rb(q0.y), swap_rb(q0.z), swap_rb(q0.w),
                      swap_rb(q1.x), swap_rb(q1.y), swap_rb(q1.z), swap_rb(q1.w)};
 
-  for (uint32_t i = 0; i < n; i++) {
+  // A command that covers the whole tile with an opaque solid colour (SrcOver) leaves nothing of what was blended
+  // before it: start at the last such command.
+  uint32_t first = 0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + (uint32_t)lane;
+    bool opaque = false;
+    if (i < n) {
+      const uint2 cmd = list[i];
+      if (cmd.y & SKB_CMD_SOLID) {
+        const uint2 gc = *reinterpret_cast<const uint2*>(&a.geom[cmd.x >> 3].color);  // color, fast_solid
+        opaque = gc.y != 0 && (gc.x >> 24) == 255u;
+      }
+    }
+    const uint32_t b = __ballot_sync(0xffffffffu, opaque);
+    if (b) first = base + 31u - (uint32_t)__clz((int)b);
+  }
+  for (uint32_t i = first; i < n; i++) {
     const uint2 cmd = list[i];
     const uint32_t op = cmd.x >> 3;
     uint32_t lo, hi;

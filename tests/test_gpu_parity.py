@@ -95,6 +95,22 @@ def test_random_fills_bit_exact_vs_port(dev, n, size, seed):
     assert np.array_equal(render(dev, dl, size, size), port.render(dl))
 
 
+def test_opaque_fills_hide_what_is_under_them(dev):
+    """The fine pass starts a tile at its last whole-tile opaque command: large opaque and translucent paths mixed,
+    over existing content, must still give the reference's bytes."""
+    size = 1024
+    rng = np.random.RandomState(77)
+    s = Scene(size, size)
+    for i in range(400):
+        cx, cy = rng.uniform(0, size), rng.uniform(0, size)
+        path = scene._random_closed_path(rng, cx, cy, 700.0 if i % 3 else 150.0, i)
+        alpha = 1.0 if i % 2 == 0 else rng.uniform(0.3, 1.0)
+        col = (rng.uniform(), rng.uniform(), rng.uniform(), alpha)
+        s.draw_path(path, Paint(fill=tuple(np.float32(c) for c in col)))
+    dl = hostlib.encode_scene(s.encode())
+    assert np.array_equal(render(dev, dl, size, size), port.render(dl))
+
+
 def test_ragged_surface_sizes(dev):
     for (w, h) in [(801, 599), (17, 33), (1, 1), (250, 16)]:
         s = scene.scene_random_fills(40, 0, 40 + w, box=200.0, width=w, height=h)
