@@ -2178,7 +2178,7 @@ static skb_result run_frame(skb_surface s) {
   uint64_t band_px = (uint64_t)(surfs[0].row1 - surfs[0].row0) * s->w;
   S.bytes_fine = band_px * 8 + (uint64_t)n_cmds * (8 + 256);
   S.bytes_cover = S.n_records * 32 + (uint64_t)n_cmds * 256;
-  S.bytes_walk = (uint64_t)S.n_edges_slots * 80 + S.n_records * 32 + S.n_rows * 8;
+  S.bytes_walk = (uint64_t)S.n_edges_slots * (sizeof(Edge) + sizeof(QuadState)) + S.n_records * 32 + S.n_rows * 8;
   s->flushed = true;
   return SKB_SUCCESS;
 }

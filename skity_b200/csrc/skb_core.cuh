@@ -91,12 +91,16 @@ SKB_HD int32_t f2i(float v) {
 
 // ------------------------------------------------------------------------ edges
 // One edge of the scan converter, split by access frequency:
-//   Edge      (SWEdge, sw_edge.hpp:18-63)  — touched for every band; 40 bytes, small enough to keep
+//   Edge      (SWEdge, sw_edge.hpp:18-63)  — touched for every band; 32 bytes, small enough to keep
 //                                            a whole path's active list in shared memory
 //   QuadState (SWQuadEdge, sw_edge.hpp:65-81) — forward-difference state, touched only when an edge
 //                                            steps to its next chord; stays in global memory
-struct alignas(8) Edge {
-  fx x, y, dx, dy, upper_x, upper_y, lower_y;
+// SWEdge's y and upper_x are not kept: until the sweep reaches an edge they equal upper_y and x (UpdateLine sets the
+// four together) — which is all SWEdge::GoY reads of them (sw_edge.hpp:43-51) — and afterwards the sweep itself knows
+// the y it has brought the edge to.  32 bytes: one sector, two 128-bit accesses.
+struct alignas(16) Edge {
+  fx x, dx, dy, upper_y;
+  fx lower_y;
   int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24 | quadratic << 25
   int32_t prev, next;
 };
@@ -126,10 +130,8 @@ SKB_HD int update_line(Edge& e, fx x0, fx y0, fx x1, fx y1, fx slope) {
   fx y0y1 = fx_sub(y1, y0) >> 10;
   if (y0y1 == 0) return 0;
   e.x = x0;
-  e.y = y0;
   e.dx = slope;
   e.dy = (x0x1 == 0 || slope == 0) ? SKB_FX_MAX : fx_abs(fx_div(y0y1, x0x1));
-  e.upper_x = x0;
   e.upper_y = y0;
   e.lower_y = y1;
   return 1;
@@ -241,7 +243,7 @@ SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* las
   *last_y = q.q_last_y;
   q.snapped_x = q.qx;
   q.snapped_y = q.qy;
-  e.x = e.y = e.dx = e.dy = e.upper_x = e.upper_y = e.lower_y = 0;
+  e.x = e.dx = e.dy = e.upper_y = e.lower_y = 0;
   update_quad(e, q);
   return 1;
 }

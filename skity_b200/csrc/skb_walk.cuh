@@ -330,25 +330,21 @@ SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f,
   Edge& T = E[SKB_TAIL];
   H.prev = -1; H.next = ord[0];
   H.upper_y = H.lower_y = SKB_FX_MIN; H.dx = 0; H.dy = SKB_FX_MAX;
-  H.curve = 0; H.y = 0;
+  H.curve = 0;
   T.prev = ord[n - 1]; T.next = -1;
   T.upper_y = T.lower_y = SKB_FX_MAX; T.dx = 0; T.dy = SKB_FX_MAX;
-  T.curve = 0; T.y = 0;
+  T.curve = 0;
   // WalkEdges (sw_raster.cc:546-677)
-  H.x = H.upper_x = left_clip;
-  T.x = T.upper_x = right_clip;
+  H.x = left_clip;
+  T.x = right_clip;
   fx y = fx_max(E[H.next].upper_y, i_to_fx(start_y));
   fx nny = SKB_FX_MAX;
   int e;
   for (e = H.next; E[e].upper_y <= y; e = E[e].next) {
-    Edge& q = E[e];  // SWEdge::GoY(dst) (sw_edge.hpp:43-51)
-    if (y == fx_add(q.y, SKB_FX1)) {
-      q.x = fx_add(q.x, q.dx);
-      q.y = y;
-    } else if (q.y != y) {
-      q.x = fx_add(q.upper_x, fx_mul(q.dx, fx_sub(q.y, q.upper_y)));
-      q.y = y;
-    }
+    Edge& q = E[e];
+    // SWEdge::GoY(dst) (sw_edge.hpp:43-51) with y == upper_y and upper_x == x, as they are before the sweep: one row
+    // below the top the edge takes a dx step; anywhere else GoY computes upper_x + dx * (y - upper_y) = x
+    if (y == fx_add(q.upper_y, SKB_FX1)) q.x = fx_add(q.x, q.dx);
     upd_nny(q.lower_y, y, &nny);
   }
   upd_nny(E[e].upper_y, y, &nny);
@@ -391,11 +387,9 @@ SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, Walk
         left = fx_max(c.x, left_clip);
         left_dy = c.dy;
         left_edge = cur;
-        c.y = next_y;
         c.x = fx_add(c.x, c.dx >> y_shift);
       } else if (is_right) {
         fx right = fx_min(right_clip, c.x);
-        c.y = next_y;
         c.x = fx_add(c.x, c.dx >> y_shift);
         TrapRec r;
         r.y = y >> 16;
@@ -411,7 +405,6 @@ SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, Walk
         sink_emit(sink, r);
         prev_right = fx_ceil_i(fx_max(right, c.x));
       } else {
-        c.y = next_y;
         c.x = fx_add(c.x, c.dx >> y_shift);
       }
       int next = c.next;
@@ -419,7 +412,7 @@ SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, Walk
         if (edge_count(c) > 0) {
           QuadState& q = Q[qmap ? (int)qmap[cur] : cur];
           q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
-          q.snapped_y = c.y;
+          q.snapped_y = next_y;
           if (!update_quad(c, q)) break;
         } else {
           break;
@@ -508,7 +501,6 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
       in_interval = (w & mask) != 0;
       const bool is_left = in_interval && !prev_in, is_right = !in_interval && prev_in;
       const fx old_x = c.x;
-      c.y = next_y;
       c.x = fx_add(c.x, c.dx >> y_shift);
       if (is_left) {
         left = fx_max(old_x, left_clip);
@@ -541,7 +533,7 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
         if (edge_count(c) > 0) {
           QuadState& q = Q[cur];
           q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
-          q.snapped_y = c.y;
+          q.snapped_y = next_y;
           chord = true;
           if (!update_quad(c, q)) break;
         } else {
@@ -549,11 +541,11 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
         }
       }
       // write back what changed (the links are edited in place below): x always, the rest only when the edge took
-      // its next chord (y is not read again: this loop sets it to next_y whenever it loads an edge)
+      // its next chord
       E[cur].x = c.x;
       if (chord) {
         E[cur].dx = c.dx; E[cur].dy = c.dy;
-        E[cur].upper_x = c.upper_x; E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
+        E[cur].upper_y = c.upper_y; E[cur].lower_y = c.lower_y; E[cur].curve = c.curve;
       }
       if (c.lower_y <= next_y) {
         remove_edge(E, cur);
