@@ -104,8 +104,10 @@ struct alignas(16) Edge {
   int32_t curve;  // curve_count | curve_shift << 8 | (winding & 0xFF) << 16 | valid << 24 | quadratic << 25
   int32_t prev, next;
 };
-struct alignas(8) QuadState {
-  fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y, snapped_x, snapped_y;
+// SWQuadEdge's snapped_x / snapped_y are arguments of update_quad instead of state: every caller sets them right
+// before the call (KeepContinuous) and nothing reads what UpdateQuad leaves in them.  32 bytes: one sector.
+struct alignas(16) QuadState {
+  fx qx, qy, qdx, qdy, qddx, qddy, q_last_x, q_last_y;
 };
 SKB_HD int edge_count(const Edge& e) { return e.curve & 0xFF; }
 SKB_HD int edge_shift(const Edge& e) { return (e.curve >> 8) & 0xFF; }
@@ -153,7 +155,7 @@ SKB_HD int set_line(Edge& e, float x0f, float y0f, float x1f, float y1f) {
 }
 
 // SWQuadEdge::UpdateQuad (sw_edge.cc:233-292)
-SKB_HDN int update_quad(Edge& e, QuadState& q) {
+SKB_HDN int update_quad(Edge& e, QuadState& q, const fx snapped_x, const fx snapped_y) {
   int success = 0;
   int count = edge_count(e);
   fx oldx = q.qx, oldy = q.qy, dx = q.qdx, dy = q.qdy;
@@ -181,10 +183,10 @@ SKB_HDN int update_quad(Edge& e, QuadState& q) {
       nsy = newy;
       slope_y = newy;
     }
-    const fx diffy = fx_sub(slope_y, q.snapped_y) >> 10;
-    const fx slope = diffy ? fx_div(fx_sub(newx, q.snapped_x) >> 10, diffy) : SKB_FX_MAX;
+    const fx diffy = fx_sub(slope_y, snapped_y) >> 10;
+    const fx slope = diffy ? fx_div(fx_sub(newx, snapped_x) >> 10, diffy) : SKB_FX_MAX;
     nsx = steep ? fx_sub(newx, fx_mul(slope, fx_sub(newy, nsy))) : newx;
-    if (slope < SKB_FX_MAX) success = update_line(e, q.snapped_x, q.snapped_y, nsx, nsy, slope);
+    if (slope < SKB_FX_MAX) success = update_line(e, snapped_x, snapped_y, nsx, nsy, slope);
     oldx = newx;
     oldy = newy;
   } while (count > 0 && !success);
@@ -192,8 +194,6 @@ SKB_HDN int update_quad(Edge& e, QuadState& q) {
   q.qy = newy;
   q.qdx = dx;
   q.qdy = dy;
-  q.snapped_x = nsx;
-  q.snapped_y = nsy;
   edge_set_count(e, count);
   return success;
 }
@@ -241,10 +241,8 @@ SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* las
   q.q_last_y = snap_y(shl(y2, 10) >> 2);
   *first_y = q.qy;
   *last_y = q.q_last_y;
-  q.snapped_x = q.qx;
-  q.snapped_y = q.qy;
   e.x = e.dx = e.dy = e.upper_y = e.lower_y = 0;
-  update_quad(e, q);
+  update_quad(e, q, q.qx, q.qy);
   return 1;
 }
 

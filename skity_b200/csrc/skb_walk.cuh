@@ -411,9 +411,8 @@ SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, Walk
       while (c.lower_y <= next_y) {
         if (edge_count(c) > 0) {
           QuadState& q = Q[qmap ? (int)qmap[cur] : cur];
-          q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
-          q.snapped_y = next_y;
-          if (!update_quad(c, q)) break;
+          // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297): the next chord starts where the sweep has brought the edge
+          if (!update_quad(c, q, c.x, next_y)) break;
         } else {
           break;
         }
@@ -532,10 +531,9 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
       while (c.lower_y <= next_y) {
         if (edge_count(c) > 0) {
           QuadState& q = Q[cur];
-          q.snapped_x = c.x;  // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297)
-          q.snapped_y = next_y;
           chord = true;
-          if (!update_quad(c, q)) break;
+          // SWQuadEdge::KeepContinuous (sw_edge.cc:294-297): the next chord starts where the sweep has brought the edge
+          if (!update_quad(c, q, c.x, next_y)) break;
         } else {
           break;
         }
