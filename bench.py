@@ -35,7 +35,9 @@ import numpy as np  # noqa: E402
 NCU_TRAFFIC = {("c1", "k_walk"): 33357312 + 118208000, ("c1", "k_cover"): 146814464 + 123073792,
                ("c1", "k_fine"): 235789568 + 51493376}
 
-E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # surfaces (and host threads) the end-to-end loop keeps in flight
+E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # host threads the end-to-end loop drives frames with
+E2E_SURFACES = int(os.environ.get("SKB_BENCH_SURFACES_PER_LANE", "1"))  # surfaces a thread alternates between: the
+                                                             # read-back of its last frame overlaps its next frame
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
 
@@ -197,15 +199,16 @@ def run_ours(args):
     # coverage / fine passes of another — what an application streaming frames through the backend does
     import threading
     lanes = [(surf, out_np)]
-    for _ in range(E2E_LANES - 1):
+    for _ in range(E2E_LANES * E2E_SURFACES - 1):
         sf = dev.create_surface(W, H)
         lanes.append((sf, torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy()))
     lane_streams = [torch.cuda.ExternalStream(sf.stream(), device=torch.device("cuda", local_rank)) for sf, _ in lanes]
 
     def run_e2e_lanes(n_steps, host_buffers=True):
         def work(t):
-            sf, out = lanes[t]
-            for _ in range(t, n_steps, E2E_LANES):
+            mine = lanes[t * E2E_SURFACES:(t + 1) * E2E_SURFACES]
+            for k, _ in enumerate(range(t, n_steps, E2E_LANES)):
+                sf, out = mine[k % E2E_SURFACES]
                 sf.begin(True)
                 if host_buffers:
                     sf.encode((dl_pinned.data_ptr(), len(dl)))
@@ -218,7 +221,7 @@ def run_ours(args):
         for th in threads:
             th.join()
 
-    run_e2e_lanes(2 * E2E_LANES)
+    run_e2e_lanes(2 * E2E_LANES * E2E_SURFACES)
     for sf, _ in lanes:
         sf.sync()
     barrier()
@@ -279,13 +282,13 @@ def run_ours(args):
             "config": {"workload": desc, "canvases_per_step": world, "paths_per_canvas": n_paths,
                        "l2": "working set per step (records + A8 masks + canvas, ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "partition": "by canvas" if world > 1 else "single",
-                       "frames_in_flight": "value: 1 (so that the per-stage timings are those of a frame); e2e: %d" % E2E_LANES},
+                       "frames_in_flight": "value: 1 (so that the per-stage timings are those of a frame); e2e: %d host threads x %d surfaces" % (E2E_LANES, E2E_SURFACES)},
             "resident_frames_in_flight": {"frames_in_flight": E2E_LANES, "ms_per_step": round(ms_resident_lanes, 4),
                                           "value": round(world * W * H / 1e6 / (ms_resident_lanes / 1e3), 2)},
             "paths_per_s": round(world * n_paths / (ms_resident / 1e3), 1),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": len(dl),
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(ms_e2e, 4), "frames_in_flight": E2E_LANES,
-                    "host_threads": E2E_LANES,
+                    "host_threads": E2E_LANES, "surfaces_per_thread": E2E_SURFACES,
                     "one_frame_at_a_time": {"value": round(world * mpix / (ms_e2e_serial / 1e3), 2),
                                             "ms_per_step": round(ms_e2e_serial, 4)}},
             "gpu_launches": int(launches),
