@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this
 # workload (profiles/r01_ncu_top3_c1.txt); None where no capture exists
-NCU_TRAFFIC = {("c1", "k_walk"): 33357312 + 118208000, ("c1", "k_cover"): 146814464 + 123073792,
-               ("c1", "k_fine"): 235789568 + 51493376}
+NCU_TRAFFIC = {("c1", "k_walk"): 29027328 + 110708224, ("c1", "k_cover"): 146852352 + 123882752,
+               ("c1", "k_fine"): 235789056 + 48016640}
 
 E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # host threads the end-to-end loop drives frames with
 E2E_SURFACES = int(os.environ.get("SKB_BENCH_SURFACES_PER_LANE", "1"))  # surfaces a thread alternates between: the

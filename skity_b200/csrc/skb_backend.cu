@@ -186,7 +186,7 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
   Edge slot[2];
   QuadState qslot[2];
   flatten_prim(np, p, slot, qslot);
-  // Each path owns one contiguous region of 80 bytes per slot: its Edge array followed by its
+  // Each path owns one contiguous region of 64 bytes per slot: its Edge array followed by its
   // QuadState array, so the sweep's working set per path stays within a few cache lines.
   const skb_dl_path pa = t.paths[t.ops[op].path];
   const uint32_t first_prim = prim_off[pa.seg_off];
