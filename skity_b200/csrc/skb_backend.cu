@@ -787,6 +787,7 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     clip_row_seek(st, c.pool, row, x_first, x0);
     x_first = x0;
     x_last = min(x_last, x0 + seg_px - 1);
+    clip_row_focus(st, x_first, x_last);
   } else if (seg != 0) {
     return;  // a row with more records than the state holds is swept by one thread
   }

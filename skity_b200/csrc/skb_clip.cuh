@@ -117,6 +117,10 @@ SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, 
 struct ClipRowState {
   TrapPrep prep[SKB_CLIP_RMAX];
   int n_prep;      // records prepared (row has at most SKB_CLIP_RMAX) or -1: evaluate generically
+  // the records clip_row_step looks at, in record order: all of them, or (clip_row_focus) those that reach the
+  // pixels the caller is going to step through
+  uint8_t act[SKB_CLIP_RMAX];
+  int n_act;
   // previous pixel
   uint32_t prev_d, prev_a;
   int prev_d_start, prev_a_start;
@@ -132,8 +136,8 @@ SKB_HDN void clip_row_step(ClipRowState& st, const TrapRec* pool, uint2 row, int
   bool d_ends_next = true;
   bool d_touched = false;
   if (st.n_prep >= 0) {
-    for (int k = 0; k < st.n_prep; k++) {
-      const TrapPrep& p = st.prep[k];
+    for (int i = 0; i < st.n_act; i++) {
+      const TrapPrep& p = st.prep[st.act[i]];
       uint8_t v;
       if (!trap_prep_alpha(p, x, &v)) continue;
       if (!p.accum) {
@@ -256,6 +260,7 @@ SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
     return;
   }
   st.n_prep = (int)row.y;
+  st.n_act = (int)row.y;
   uint32_t idx = row.x;
   for (uint32_t k = 0; k < row.y; k++, idx++) {
     TrapRec r = pool[idx];
@@ -264,7 +269,27 @@ SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
       r = pool[idx];
     }
     st.prep[k] = trap_prepare(r);
+    st.act[k] = (uint8_t)k;
   }
+}
+
+SKB_HD void clip_row_unfocus(ClipRowState& st) {
+  for (int k = 0; k < st.n_prep; k++) st.act[k] = (uint8_t)k;
+  st.n_act = st.n_prep > 0 ? st.n_prep : 0;
+}
+
+// From here on clip_row_step is only called for pixels xa..xb: keep the records that give one of them a value (a
+// record gives nothing outside [L, R)).  A thread that shares a row with others steps through a run of a few pixels
+// and most of the row's records do not reach it.
+SKB_HDN void clip_row_focus(ClipRowState& st, int xa, int xb) {
+  if (st.n_prep < 0) return;
+  int n = 0;
+  for (int k = 0; k < st.n_prep; k++) {
+    const TrapPrep& p = st.prep[k];
+    if (p.mode == 0 || p.R <= xa || p.L > xb) continue;
+    st.act[n++] = (uint8_t)k;
+  }
+  st.n_act = n;
 }
 
 }  // namespace skb

@@ -242,8 +242,11 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
       for (int x = g.scan_l; x <= g.scan_r && (is_clip || x < W); x++) {
         SpanSide ld, od, la, oa;
         // the GPU lets several threads share a row: a thread entering at x must reconstruct this very state
+        // ... and looks only at the records that reach its run of pixels (clip_row_focus): here runs of 7
+        if (st.n_prep >= 0 && (x - g.scan_l) % 7 == 0) clip_row_focus(st, x, x + 6);
         if (st.n_prep >= 0 && x > g.scan_l && (x - g.scan_l) % 7 == 0) {
           ClipRowState t = st;
+          clip_row_unfocus(t);
           t.prev_d = t.prev_a = 0xDEAD;
           t.prev_d_start = t.prev_a_start = -12345;
           t.prev_d_ends = true;
