@@ -762,8 +762,11 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     own_row = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
   }
 
+  // the row's prepared records: one array per warp in shared memory, every lane prepares its share
+  __shared__ TrapPrep s_prep[4][SKB_CLIP_RMAX];
   ClipRowState st;
-  clip_row_begin(st, c.pool, row);
+  clip_row_begin(st, c.pool, row, s_prep[threadIdx.x >> 5], seg, 32);
+  __syncwarp();
   int x_first = g.scan_l, x_last = g.scan_r;  // inclusive: the pixel after the last span can receive the `+ 1`
   if (st.n_prep >= 0) {
     int lo = INT_MAX, hi = INT_MIN;

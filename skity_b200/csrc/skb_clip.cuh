@@ -115,7 +115,8 @@ SKB_HDN void clip_combine(int x, const SpanSide& left_d, const SpanSide& own_d, 
 
 // Sweep state of one row.
 struct ClipRowState {
-  TrapPrep prep[SKB_CLIP_RMAX];
+  TrapPrep* prep;  // SKB_CLIP_RMAX prepared records, storage given by the caller: the threads that share a row on the
+                   // GPU share ONE array in shared memory (each prepares a part of it)
   int n_prep;      // records prepared (row has at most SKB_CLIP_RMAX) or -1: evaluate generically
   // the records clip_row_step looks at, in record order: all of them, or (clip_row_focus) those that reach the
   // pixels the caller is going to step through
@@ -251,10 +252,14 @@ SKB_HDN void clip_row_seek(ClipRowState& st, const TrapRec* pool, uint2 row, int
   st.prev_a_start = cur;
 }
 
-SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
+// `storage`: SKB_CLIP_RMAX entries.  `part` / `n_parts`: this caller prepares the records k with k % n_parts == part
+// (1 part = all of them); callers that share the storage synchronise before they step.
+SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row, TrapPrep* storage, int part = 0, int n_parts = 1) {
+  st.prep = storage;
   st.prev_d = st.prev_a = 0;
   st.prev_d_start = st.prev_a_start = 0;
   st.prev_d_ends = false;
+  st.n_act = 0;
   if (row.y > (uint32_t)SKB_CLIP_RMAX) {
     st.n_prep = -1;
     return;
@@ -263,12 +268,8 @@ SKB_HDN void clip_row_begin(ClipRowState& st, const TrapRec* pool, uint2 row) {
   st.n_act = (int)row.y;
   uint32_t idx = row.x;
   for (uint32_t k = 0; k < row.y; k++, idx++) {
-    TrapRec r = pool[idx];
-    if (r.flags & SKB_REC_LINK) {
-      idx = (uint32_t)r.y;
-      r = pool[idx];
-    }
-    st.prep[k] = trap_prepare(r);
+    if (pool[idx].flags & SKB_REC_LINK) idx = (uint32_t)pool[idx].y;
+    if ((int)(k % (uint32_t)n_parts) == part) st.prep[k] = trap_prepare(pool[idx]);
     st.act[k] = (uint8_t)k;
   }
 }

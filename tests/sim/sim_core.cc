@@ -238,7 +238,8 @@ extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba,
       uint2 row = so.rows[(size_t)(y - g.scan_t)];
       if (row.y == 0) continue;
       ClipRowState st;
-      clip_row_begin(st, so.pool.data(), row);
+      TrapPrep prep_storage[SKB_CLIP_RMAX];
+      clip_row_begin(st, so.pool.data(), row, prep_storage);
       for (int x = g.scan_l; x <= g.scan_r && (is_clip || x < W); x++) {
         SpanSide ld, od, la, oa;
         // the GPU lets several threads share a row: a thread entering at x must reconstruct this very state
