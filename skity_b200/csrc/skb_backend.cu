@@ -1389,19 +1389,31 @@ __global__ void __launch_bounds__(128) k_blur_v(const BlurJob* jobs, const uint3
   int shr;
   blur_mul_shr(r, &mul, &shr);
   uint8_t* dcol = D.px + (size_t)x * 4;
+  // From here on only S = Ul - 2 Um + Ug and its first difference Dd = Tl - 2 Tm + Tg are carried (U' = U + T and
+  // T' = T + e give S' = S + Dd and Dd' = Dd + e[y+m+1] - 2 e[y+1] + e[y-m+1], all mod 2^32): 8 running values and
+  // 7 operations per channel and row instead of 24 and 12.
+  uint32_t S[4], Dd[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    S[c] = Ul[c] - 2u * Um[c] + Ug[c];
+    Dd[c] = Tl[c] - 2u * Tm[c] + Tg[c];
+  }
   for (int y = 0; y < h; y++) {
     uint32_t out = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      uint64_t sum = (uint64_t)(uint32_t)(Ul[c] - 2u * Um[c] + Ug[c]);
+      uint64_t sum = (uint64_t)S[c];
       if (c == 0) sum -= (uint64_t)y * drift0;
       if (c == 3) sum -= (uint64_t)y * drift3;
       out |= (uint32_t)(uint8_t)((sum * (uint64_t)mul) >> shr) << (8 * c);
     }
     *reinterpret_cast<uint32_t*>(dcol + (size_t)y * pitch) = out;
-    advance(Tl, Ul, y + m + 1);
-    advance(Tm, Um, y + 1);
-    advance(Tg, Ug, y - m + 1);
+    const uint32_t pl = sample(y + m + 1), pm = sample(y + 1), pg = sample(y - m + 1);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      S[c] += Dd[c];
+      Dd[c] += ((pl >> (8 * c)) & 0xFF) - 2u * ((pm >> (8 * c)) & 0xFF) + ((pg >> (8 * c)) & 0xFF);
+    }
   }
 }
 
