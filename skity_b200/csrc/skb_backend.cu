@@ -1378,11 +1378,22 @@ __global__ void __launch_bounds__(128) k_blur_v(const BlurJob* jobs, const uint3
       Tt[c] += (px >> (8 * c)) & 0xFF;
     }
   };
-  // all three start at extended index -m (T = U = 0); bring them to y=0 positions
-  for (int j = -m; j < m + 1; j++) advance(Tl, Ul, j);      // -> index m+1
-  for (int j = -m; j < 1; j++) advance(Tm, Um, j);          // -> index 1
-  for (int j = -m; j < -m + 1; j++) advance(Tg, Ug, j);     // -> index -m+1
+  // all three start at extended index -m (T = U = 0) and are brought to their y = 0 positions: m+1, 1 and -m+1.
+  // The samples above the top row are the top row (clamp), so after k of them T = k p0 and U = p0 k (k-1) / 2: only
+  // the leading pair has real rows (0..m) to walk through.
   const uint32_t p0 = sample(0);
+  const uint32_t um = (uint32_t)m, tri_m = um * (um - 1u) / 2u, tri_m1 = (um + 1u) * um / 2u;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint32_t e0 = (p0 >> (8 * c)) & 0xFF;
+    Tl[c] = um * e0;
+    Ul[c] = e0 * tri_m;
+    Tm[c] = (um + 1u) * e0;
+    Um[c] = e0 * tri_m1;
+    Tg[c] = e0;
+    Ug[c] = 0u;
+  }
+  for (int j = 0; j < m + 1; j++) advance(Tl, Ul, j);       // -> index m+1
   const uint64_t g0 = (p0 >> 8) & 0xFF, b0 = p0 & 0xFF, a0 = (p0 >> 24) & 0xFF;
   const uint64_t drift0 = (uint64_t)m * (g0 - b0), drift3 = (uint64_t)m * (g0 - a0);
   uint32_t mul;
