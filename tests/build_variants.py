@@ -1,7 +1,10 @@
-"""Builds variant CUDA libraries (one nvcc call each) into gpurun_variants/<name>.so"""
+"""Manual tool: builds variant CUDA libraries (one nvcc call each, -D flags per variant) into the untracked
+gpurun_variants/<name>.so, to be compared on the GPU with SKB_LIB=... python tests/perf_probe.py.
+Usage: python tests/build_variants.py base="" f16="-DFINE_MINB=16" ..."""
 import subprocess, sys, os, concurrent.futures as cf
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from skity_b200 import build as b
+os.makedirs(os.path.join(b.REPO, 'gpurun_variants'), exist_ok=True)
 V = dict(a.split('=', 1) for a in sys.argv[1:])   # name="-DX=1 -DY=2"
 def one(kv):
     name, flags = kv
