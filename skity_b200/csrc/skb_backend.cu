@@ -1298,33 +1298,32 @@ __global__ void __launch_bounds__(BLUR_H_WARPS * 32) k_blur_h(const BlurJob* job
     j = j < 0 ? 0 : (j > n - 1 ? n - 1 : j);
     return rsrc[j];
   };
-  // T: totals of my run, scanned
-  uint32_t acc[4] = {0, 0, 0, 0};
-  for (int k = k0; k < k1; k++) {
-    const uint32_t px = sample(k);
-#pragma unroll
-    for (int c = 0; c < 4; c++) acc[c] += (px >> (8 * c)) & 0xFF;
-  }
-  uint32_t t_off[4];
-  blur_row_scan(acc, t_off, lane, wib, tot);
-  // U: exclusive prefix of T over my run, totals scanned, offsets added
-  uint32_t tv[4], ua[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int c = 0; c < 4; c++) tv[c] = t_off[c];
+  // One pass over my run builds T and U relative to the run's start (T_rel = sum of the run's samples so far, U_rel =
+  // sum of T_rel so far) and leaves U_rel in shared memory; the run totals are scanned over the row; with t_off = T at
+  // the run's start the true values are T = t_off + T_rel and U[k] = u_off + (k - k0) t_off + U_rel[k], where u_off
+  // is the scan of the runs' sums of T = n_run t_off + U_rel(end).
+  uint32_t tv[4] = {0, 0, 0, 0}, ua[4] = {0, 0, 0, 0};
   for (int k = k0; k < k1; k++) {
     const uint32_t px = sample(k);
     U[k] = make_uint4(ua[0], ua[1], ua[2], ua[3]);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      ua[c] += tv[c];                       // U[k+1] = U[k] + T[k]
-      tv[c] += (px >> (8 * c)) & 0xFF;      // T[k+1] = T[k] + e[k]
+      ua[c] += tv[c];                       // U_rel[k+1] = U_rel[k] + T_rel[k]
+      tv[c] += (px >> (8 * c)) & 0xFF;      // T_rel[k+1] = T_rel[k] + e[k]
     }
   }
+  uint32_t t_off[4];
+  blur_row_scan(tv, t_off, lane, wib, tot);
+  const uint32_t n_run = (uint32_t)(k1 - k0);
+#pragma unroll
+  for (int c = 0; c < 4; c++) ua[c] += n_run * t_off[c];
   uint32_t u_off[4];
   blur_row_scan(ua, u_off, lane, wib, tot);
   for (int k = k0; k < k1; k++) {
     uint4 v = U[k];
     U[k] = make_uint4(v.x + u_off[0], v.y + u_off[1], v.z + u_off[2], v.w + u_off[3]);
+#pragma unroll
+    for (int c = 0; c < 4; c++) u_off[c] += t_off[c];   // (k - k0) t_off, one step at a time
   }
   if (BLUR_H_WARPS > 1) __syncthreads();
   else __syncwarp();
