@@ -1054,8 +1054,17 @@ SKB_HD float remap_tile(float t, uint32_t mode) {  // RemapFloatTile (:12-23)
   }
   return t;
 }
-SKB_HD uint32_t image_texel(const SurfaceView& s, float fx_, float fy_) {  // SampleXY: glm::clamp<uint32_t>(float, 0, n-1)
-  uint32_t ix = f2u_wrap(fx_), iy = f2u_wrap(fy_);
+// f2u_wrap for an argument known to be >= 0 (or NaN) and below 2^31 — a remapped unit coordinate times the image
+// size: one saturating conversion (NaN -> 0, like f2u_wrap) instead of range tests and a 64-bit one.
+SKB_HD uint32_t f2u_nonneg(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float2uint_rz(f);
+#else
+  return f2u_wrap(f);
+#endif
+}
+SKB_HD uint32_t image_texel(const SurfaceView& s, float fx_, float fy_, const bool nonneg = false) {  // SampleXY: glm::clamp<uint32_t>(float, 0, n-1)
+  uint32_t ix = nonneg ? f2u_nonneg(fx_) : f2u_wrap(fx_), iy = nonneg ? f2u_nonneg(fy_) : f2u_wrap(fy_);
   if (ix > s.w - 1) ix = s.w - 1;
   if (iy > s.h - 1) iy = s.h - 1;
   return *reinterpret_cast<const uint32_t*>(s.px + (size_t)iy * s.pitch + (size_t)ix * 4);  // R | G<<8 | B<<16 | A<<24
@@ -1069,7 +1078,8 @@ SKB_HD uint32_t sample_image_nearest(uint32_t tile_mode, const SurfaceView& s, f
   u = remap_tile(u, xmode);
   v = remap_tile(v, ymode);
   uint32_t r, g, b, a;
-  const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h);
+  // after the decal test and the remap u and v are in [0, 1] (or NaN)
+  const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h, true);
   const uint32_t t0 = t & 0xFF, t1 = (t >> 8) & 0xFF, t2 = (t >> 16) & 0xFF, t3 = t >> 24;
   if (requant_lut) {
     r = requant_lut[t0]; g = requant_lut[t1]; b = requant_lut[t2]; a = requant_lut[t3];
