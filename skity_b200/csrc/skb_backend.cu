@@ -943,11 +943,8 @@ struct FineArgs {
 #endif
 __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   __shared__ uint2 s_cmd[FINE_WARPS][FINE_SORT_CAP];
-  // the nearest sampler's u8 -> float -> u8 round trip, tabulated per warp when its tile first meets an image paint
-  __shared__ uint8_t s_requant_all[FINE_WARPS][256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* const s_requant = s_requant_all[warp];
-  bool requant_ready = false;
+  const uint8_t* const s_requant = nullptr;  // the sampler's byte round trip is the identity (skb_core.cuh)
   const uint32_t tile = a.tile_begin + blockIdx.x * FINE_WARPS + warp;
   if (tile >= a.tile_end) return;
   const uint32_t c0 = a.tile_off[tile];
@@ -1071,11 +1068,6 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
       }
       const uint32_t pidx = a.ops[op].paint;
       const uint32_t ptype = a.paints[pidx].type;
-      if (ptype == SKB_PAINT_IMAGE && !requant_ready) {  // warp-uniform
-        for (int k = lane; k < 256; k += 32) s_requant[k] = (uint8_t)requant((uint32_t)k);
-        __syncwarp();
-        requant_ready = true;
-      }
       if ((lo | hi | zlo | zhi) == 0) continue;
       const skb_dl_paint pt = a.paints[pidx];
       const uint32_t galpha = ptype == SKB_PAINT_IMAGE ? (pt.global_alpha & 0xFF) : 0xFFu;

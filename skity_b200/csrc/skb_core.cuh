@@ -1081,11 +1081,11 @@ SKB_HD uint32_t sample_image_nearest(uint32_t tile_mode, const SurfaceView& s, f
   // after the decal test and the remap u and v are in [0, 1] (or NaN)
   const uint32_t t = image_texel(s, u * (float)s.w, v * (float)s.h, true);
   const uint32_t t0 = t & 0xFF, t1 = (t >> 8) & 0xFF, t2 = (t >> 16) & 0xFF, t3 = t >> 24;
-  if (requant_lut) {
-    r = requant_lut[t0]; g = requant_lut[t1]; b = requant_lut[t2]; a = requant_lut[t3];
-  } else {
-    r = requant(t0); g = requant(t1); b = requant(t2); a = requant(t3);
-  }
+  // The sampler's u8 -> float -> u8 round trip (requant(): Color4fFromColor, Color4fToColor) gives every byte back
+  // unchanged under IEEE single-precision division and multiplication — all 256 values are checked by
+  // tests/test_sim_stages.py::test_sampler_round_trip_is_identity — so the bytes are used as they are.
+  (void)requant_lut;
+  r = t0; g = t1; b = t2; a = t3;
   // an unpremultiplied texture is premultiplied after sampling (sw_span_brush.cc:573-576)
   if ((tile_mode & SKB_PAINT_IMAGE_UNPREMUL) && a != 255) {
     r = mul_div_255_round(r, a);

@@ -190,6 +190,14 @@ struct SimClipState {
 
 }  // namespace
 
+// How many bytes the sampler's u8 -> float -> u8 round trip changes (requant in skb_core.cuh): must be 0, the device
+// code relies on it.
+extern "C" int sim_requant_changes() {
+  int bad = 0;
+  for (uint32_t c = 0; c < 256; c++) bad += requant(c) != c;
+  return bad;
+}
+
 extern "C" int sim_render_dl(const uint8_t* dl, size_t bytes, uint8_t* out_rgba, int64_t* stats) {
   (void)bytes;
   const skb_dl_header* h = (const skb_dl_header*)dl;

@@ -49,6 +49,16 @@ def check_scene(s):
     return both
 
 
+def test_sampler_round_trip_is_identity():
+    """BitmapSampler's nearest path converts a texel to floats and back (Color4fFromColor / Color4fToColor,
+    src/graphic/color.cc:44-59): with IEEE single precision that is the identity on all 256 byte values, which the
+    device sampler relies on (it uses the texel bytes as they are)."""
+    assert simlib.lib().sim_requant_changes() == 0
+    c = np.arange(256, dtype=np.float32)
+    back = np.clip((c / np.float32(255.0)).astype(np.float32) * np.float32(255.0), 0, 255).astype(np.uint8)
+    assert np.array_equal(back, np.arange(256, dtype=np.uint8))
+
+
 def test_sim_star_and_fills():
     check_scene(scene.scene_c0(blur=False))
     check_scene(scene.scene_random_fills(40, 320, 1, box=200.0))
