@@ -32,8 +32,8 @@ import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this
 # workload (profiles/r01_ncu_top3_c1.txt); None where no capture exists
-NCU_TRAFFIC = {("c1", "k_walk"): 28995584 + 110497792, ("c1", "k_cover"): 146844672 + 124187392,
-               ("c1", "k_fine"): 235950848 + 49722368}
+NCU_TRAFFIC = {("c1", "k_walk"): 29028352 + 112788480, ("c1", "k_cover"): 146949632 + 124314624,
+               ("c1", "k_fine"): 235782912 + 49222656}
 
 E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # host threads the end-to-end loop drives frames with
 E2E_SURFACES = int(os.environ.get("SKB_BENCH_SURFACES_PER_LANE", "1"))  # surfaces a thread alternates between: the
