@@ -81,6 +81,19 @@ SKB_API void skb_surface_destroy(skb_surface surface);
  * Used to split one canvas across GPUs; y1 = 0 resets to the whole surface. */
 SKB_API skb_result skb_surface_set_band(skb_surface surface, uint32_t y0, uint32_t y1);
 
+/* How float coordinates become 16.16 fixed point.  The reference converts through 26.6 with `x << 10` in int32
+ * (SWFDot6ToFixed, src/render/sw/sw_subpixel.hpp:43, used by SWEdge::SetLine / SWQuadEdge::SetQuad,
+ * src/render/sw/sw_edge.cc:22-29,124-130,207-215): at 8192 px the shift overflows and the coordinate wraps, so
+ * on canvases larger than 8192 px geometry beyond that line lands elsewhere (the reference's own numeric range).
+ *   SKB_COORD_REFERENCE  the reference's arithmetic, wrap included (bit-exact with it for every input)
+ *   SKB_COORD_WIDE       the same conversion without the overflow: identical results wherever the reference does
+ *                        not wrap, coordinates valid up to +-32767 px
+ *   SKB_COORD_AUTO       (default) WIDE for surfaces wider or taller than 8192 px, REFERENCE otherwise */
+#define SKB_COORD_AUTO 0
+#define SKB_COORD_REFERENCE 1
+#define SKB_COORD_WIDE 2
+SKB_API skb_result skb_surface_set_coord_mode(skb_surface surface, int mode);
+
 /* clear != 0 zeroes the surface (transparent black), like LockCanvas(true). */
 SKB_API skb_result skb_frame_begin(skb_surface surface, int clear);
 /* Copies the display list to the device (host -> device, asynchronous on the surface's stream

@@ -35,6 +35,8 @@ def lib():
         _lib.skbo_raster_path.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
         _lib.skbo_raster_path.restype = ctypes.c_long
+        _lib.skbo_set_coord_mode.argtypes = [ctypes.c_int]
+        _lib.skbo_set_row_band.argtypes = [ctypes.c_int, ctypes.c_int]
         _lib.skbo_stack_blur.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return _lib
 
@@ -44,6 +46,45 @@ def dl_header(dl):
              "n_stop_floats", "n_clip_states", "reserved0", "off_surfaces", "off_ops", "off_paths", "off_segs",
              "off_paints", "off_stops"]
     return dict(zip(names, struct.unpack_from("<18I", dl, 0)))
+
+
+def set_coord_mode(mode):
+    """0 auto (wide above 8192 px, the device's default), 1 the reference's int32 arithmetic, 2 wide."""
+    lib().skbo_set_coord_mode(int(mode))
+
+
+def set_row_band(y0, y1):
+    """Render only the canvas rows [y0, y1) (y1 <= y0: all rows) — lets several processes share a very large frame."""
+    lib().skbo_set_row_band(int(y0), int(y1))
+
+
+def render_parallel(dl, procs=None):
+    """port.render() of a large frame by `procs` forked processes, each producing a band of rows."""
+    import multiprocessing as mp
+    h = dl_header(dl)
+    w, hh = struct.unpack_from("<2I", dl, h["off_surfaces"])
+    procs = procs or os.cpu_count() or 1
+    bands = [(hh * i // procs, hh * (i + 1) // procs) for i in range(procs)]
+    out = np.zeros((hh, w, 4), dtype=np.uint8)
+    global _pr_dl
+    _pr_dl = dl
+    with mp.get_context("fork").Pool(procs) as pool:
+        for (y0, y1), rows in zip(bands, pool.imap(_render_band, bands)):
+            out[y0:y1] = rows
+    _pr_dl = None
+    return out
+
+
+_pr_dl = None
+
+
+def _render_band(band):
+    y0, y1 = band
+    set_row_band(y0, y1)
+    try:
+        return render(_pr_dl)[y0:y1].copy()
+    finally:
+        set_row_band(0, 0)
 
 
 def render(dl, initial=None):

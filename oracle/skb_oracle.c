@@ -99,8 +99,17 @@ static int update_line(edge* e, fx x0, fx y0, fx x1, fx y1, fx slope) {
   return 1;
 }
 
-/* SWEdge::SetLine — sw_edge.cc:18-42.  trunc(v*4*64) << 10 >> 2 with int32 wrap. */
-static inline fx line_coord(float v) { return shl(f2i((v * 4) * 64), 10) >> 2; }
+/* SWEdge::SetLine — sw_edge.cc:18-42.  trunc(v*4*64) << 10 >> 2 with int32 wrap.
+ * g_wide: the backend's wide-coordinate mode (include/skb.h SKB_COORD_WIDE) — the same 24.8 -> 16.16 conversion
+ * without the int32 overflow of SWFDot6ToFixed (sw_subpixel.hpp:43), i.e. `<< 8`.  The ONE deliberate deviation from
+ * the reference in this file; identical to it wherever the reference does not wrap (|coordinate| < 8192 px).  The
+ * compiled reference cannot serve as the checker there: it has no such mode, and rendering a large canvas as
+ * translated windows is not the same function either (ChopQuadAtYExtrema interpolates in device space in fp32,
+ * geometry.cc:323-349, so the reference's own output changes by up to a quarter-pixel snap under a whole-pixel
+ * translation — measured by tests/test_oracle_pinning.py::test_reference_is_not_translation_invariant). */
+static int g_wide = 0;
+static inline fx fx_from_24_8(fx t) { return g_wide ? shl(t, 8) : (shl(t, 10) >> 2); }
+static inline fx line_coord(float v) { return fx_from_24_8(f2i((v * 4) * 64)); }
 static int set_line(edge* e, float x0f, float y0f, float x1f, float y1f) {
   fx x0 = line_coord(x0f), y0 = snap_y(line_coord(y0f));
   fx x1 = line_coord(x1f), y1 = snap_y(line_coord(y1f));
@@ -208,6 +217,9 @@ static int set_quad(edge* e, const float* p) {
   e->q_last_y = shl(y2, 10);
   e->qx >>= 2; e->qy >>= 2; e->qdx >>= 2; e->qdy >>= 2;
   e->qddx >>= 2; e->qddy >>= 2; e->q_last_x >>= 2; e->q_last_y >>= 2;
+  if (g_wide) {  /* the end points without the overflow of `<< 10` (see line_coord) */
+    e->qx = shl(x0, 8); e->qy = shl(y0, 8); e->q_last_x = shl(x2, 8); e->q_last_y = shl(y2, 8);
+  }
   e->qy = snap_y(e->qy);
   e->q_last_y = snap_y(e->q_last_y);
   e->q_first_y = e->qy;
@@ -919,6 +931,12 @@ static void sort_edges(edge* first, size_t n) {
   }
 }
 
+/* Test-harness aid, not part of the reference: restrict the canvas (surface 0) to the pixel rows [g_band_y0, g_band_y1)
+ * so that a very large frame can be produced by several processes.  Spans of different rows are independent, so the
+ * rows a process keeps are exactly those of the whole frame: paths whose bounds miss the band are skipped before the
+ * sweep (g_band_skip, set per op by skbo_render), spans outside it are dropped before the brush. */
+static int g_band_y0 = 0, g_band_y1 = 0, g_band_skip = 0;
+
 /* SWRaster::RastePath — sw_raster.cc:731-786.  Appends spans to `out`; bounds4 = raster bounds_. */
 static void raster_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, const float* clip, int even_odd,
                         spanvec* out, float* bounds4) {
@@ -928,6 +946,7 @@ static void raster_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ct
   float sl = pb.have ? pb.l : 0, st = pb.have ? pb.t : 0, sr = pb.have ? pb.r : 0, sbm = pb.have ? pb.b : 0;
   float bl = floorf(sl), bt = floorf(st), br = ceilf(sr), bb = ceilf(sbm);
   if (bounds4) { bounds4[0] = bl; bounds4[1] = bt; bounds4[2] = br; bounds4[3] = bb; }
+  if (g_band_skip && (bb <= (float)g_band_y0 || bt >= (float)g_band_y1)) { free(pb.v); return; }
   { /* Rect::Intersect — rect.cc:160-172 */
     float l = sl > clip[0] ? sl : clip[0], r = sr < clip[2] ? sr : clip[2];
     float t = st > clip[1] ? st : clip[1], b = sbm < clip[3] ? sbm : clip[3];
@@ -1491,11 +1510,19 @@ static const void* dl_section(const uint8_t* dl, uint32_t off) { return dl + off
 /* Executes a whole display list.  Surfaces are allocated zeroed (Bitmap calloc,
  * src/io/pixmap.cc:77); surface 0 is copied to canvas_rgba (w*h*4).  If
  * `initial` is non-NULL surface 0 starts from those pixels.  Returns 0 / <0. */
+/* 0 = auto (wide for canvases wider or taller than 8192 px, like skb_surface_set_coord_mode's default),
+ * 1 = the reference's int32 arithmetic, 2 = wide.  See line_coord. */
+static int g_coord_mode = 0;
+SKBO_API void skbo_set_coord_mode(int mode) { g_coord_mode = mode; g_wide = mode == 2; }
+/* rows [y0, y1) of the canvas only (y1 <= y0: the whole canvas); see g_band_y0 */
+SKBO_API void skbo_set_row_band(int y0, int y1) { g_band_y0 = y0; g_band_y1 = y1; }
+
 SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial, uint8_t* canvas_rgba) {
   if (bytes < sizeof(skb_dl_header)) return -1;
   const skb_dl_header* h = (const skb_dl_header*)dl;
   if (h->magic != SKB_DL_MAGIC || h->version != SKB_DL_VERSION || h->total_bytes > bytes) return -1;
   const skb_dl_surface* sdesc = (const skb_dl_surface*)dl_section(dl, h->off_surfaces);
+  g_wide = g_coord_mode == 2 || (g_coord_mode == 0 && h->n_surfaces && (sdesc[0].width > 8192 || sdesc[0].height > 8192));
   const skb_dl_op* ops = (const skb_dl_op*)dl_section(dl, h->off_ops);
   const skb_dl_path* paths = (const skb_dl_path*)dl_section(dl, h->off_paths);
   const skb_dl_seg* segs = (const skb_dl_seg*)dl_section(dl, h->off_segs);
@@ -1523,7 +1550,16 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
       case SKB_OP_FILL: {
         const skb_dl_path* p = &paths[op->path];
         spans.n = 0;
+        const int banded = g_band_y1 > g_band_y0 && op->surface == 0 && !op->clip_in;
+        g_band_skip = banded;
         raster_path(segs + p->seg_off, p->n_segs, op->ctm, op->clip_bounds, (int)op->fill_type, &spans, NULL);
+        g_band_skip = 0;
+        if (banded) {
+          size_t k = 0;
+          for (size_t j = 0; j < spans.n; j++)
+            if (spans.v[j].y >= g_band_y0 && spans.v[j].y < g_band_y1) spans.v[k++] = spans.v[j];
+          spans.n = k;
+        }
         const spanvec* use = &spans;
         if (op->clip_in && clip_has(&clips[op->clip_in])) {
           clipped.n = 0;

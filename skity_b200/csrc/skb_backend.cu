@@ -131,6 +131,7 @@ struct FrameTables {
   const skb_dl_paint* paints;
   const float* stops;
   uint32_t n_ops, n_segs;
+  uint32_t wide;  // wide-coordinate mode (skb_surface_set_coord_mode): 24.8 -> 16.16 without the reference's int32 wrap
 };
 
 __global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op) {
@@ -185,7 +186,7 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
   }
   Edge slot[2];
   QuadState qslot[2];
-  flatten_prim(np, p, slot, qslot);
+  flatten_prim(np, p, slot, qslot, (int)t.wide);
   // Each path owns one contiguous region of 64 bytes per slot: its Edge array followed by its
   // QuadState array, so the sweep's working set per path stays within a few cache lines.
   const skb_dl_path pa = t.paths[t.ops[op].path];
@@ -331,7 +332,7 @@ __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   Edge* E = reinterpret_cast<Edge*>(region);
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
   walk_path(E, Q, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
-            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink, 1);
+            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink, 1, (int)a.t.wide);
 }
 
 // ---------------------------------------------------------------- stage 4: coverage
@@ -1468,6 +1469,7 @@ struct skb_surface_s {
   skb_device dev = nullptr;
   uint32_t w = 0, h = 0;
   uint32_t band_y0 = 0, band_y1 = 0;
+  int coord_mode = SKB_COORD_AUTO;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[12] = {};
   // host-mapped words the device writes counts into: reading them does not queue behind another
@@ -1760,6 +1762,7 @@ static skb_result run_frame(skb_surface s) {
   t.stops = (const float*)(ddl + h.off_stops);
   t.n_ops = h.n_ops;
   t.n_segs = h.n_segs;
+  t.wide = s->coord_mode == SKB_COORD_WIDE || (s->coord_mode == SKB_COORD_AUTO && (s->w > 8192 || s->h > 8192)) ? 1u : 0u;
   const uint32_t n_ops = h.n_ops, n_segs = h.n_segs;
   s->n_ops = n_ops;
   if (n_ops == 0) {
@@ -2304,6 +2307,12 @@ skb_result skb_surface_set_band(skb_surface s, uint32_t y0, uint32_t y1) {
   }
   s->band_y0 = y0;
   s->band_y1 = y1;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_set_coord_mode(skb_surface s, int mode) {
+  if (!s || mode < SKB_COORD_AUTO || mode > SKB_COORD_WIDE) return SKB_ERROR_INVALID_ARGUMENT;
+  s->coord_mode = mode;
   return SKB_SUCCESS;
 }
 

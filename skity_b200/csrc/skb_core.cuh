@@ -139,13 +139,18 @@ SKB_HD int update_line(Edge& e, fx x0, fx y0, fx x1, fx y1, fx slope) {
   return 1;
 }
 
-// float pixel coordinate -> 16.16 as SetLine does: trunc(v*4*64) << 10 >> 2 (sw_edge.cc:22-29)
-SKB_HD fx line_coord(float v) { return shl(f2i((v * 4.0f) * 64.0f), 10) >> 2; }
+// float pixel coordinate -> 16.16 as SetLine does: trunc(v*4*64) << 10 >> 2 (sw_edge.cc:22-29).
+// SWFDot6ToFixed is `x << 10` in int32 (sw_subpixel.hpp:43): at 8192 px the shift leaves the int32 range and the
+// coordinate wraps.  `wide` selects the wide-coordinate mode of this backend (include/skb.h, skb_surface_set_coord_mode):
+// the same conversion carried out without the overflow (24.8 -> 16.16 is `<< 8`), equal to the reference wherever the
+// reference does not wrap and valid up to +-32767 px (what 16.16 holds).
+SKB_HD fx fx_from_24_8(int32_t t, int wide) { return wide ? (fx)((uint32_t)t << 8) : (shl(t, 10) >> 2); }
+SKB_HD fx line_coord(float v, int wide = 0) { return fx_from_24_8(f2i((v * 4.0f) * 64.0f), wide); }
 
 // SWEdge::SetLine (sw_edge.cc:18-42)
-SKB_HD int set_line(Edge& e, float x0f, float y0f, float x1f, float y1f) {
-  fx x0 = line_coord(x0f), y0 = snap_y(line_coord(y0f));
-  fx x1 = line_coord(x1f), y1 = snap_y(line_coord(y1f));
+SKB_HD int set_line(Edge& e, float x0f, float y0f, float x1f, float y1f, int wide = 0) {
+  fx x0 = line_coord(x0f, wide), y0 = snap_y(line_coord(y0f, wide));
+  fx x1 = line_coord(x1f, wide), y1 = snap_y(line_coord(y1f, wide));
   edge_set_curve(e, 0, 0, 1);
   fx y0y1 = fx_sub(y1, y0) >> 10;
   if (y0y1 == 0) return 0;
@@ -209,7 +214,7 @@ SKB_HD int diff_to_shift(fx dx, fx dy) {
 
 // SWQuadEdge::SetQuad (sw_edge.cc:121-231). p = x0 y0 x1 y1 x2 y2 of a y-monotone quad.
 // On success *first_y / *last_y receive q_first_y / q_last_y (used by CanBeIgnored).
-SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* last_y) {
+SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* last_y, int wide = 0) {
   fx x0 = f2i(p[0] * 256.0f), y0 = f2i(p[1] * 256.0f);
   fx x1 = f2i(p[2] * 256.0f), y1 = f2i(p[3] * 256.0f);
   fx x2 = f2i(p[4] * 256.0f), y2 = f2i(p[5] * 256.0f);
@@ -229,16 +234,16 @@ SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* las
   edge_set_curve(e, 1 << shift, shift - 1, w);
   fx A = shl(fx_add(fx_sub(fx_sub(x0, x1), x1), x2), 9);
   fx B = shl(fx_sub(x1, x0), 10);
-  q.qx = shl(x0, 10) >> 2;
+  q.qx = fx_from_24_8(x0, wide);
   q.qdx = fx_add(B, A >> shift) >> 2;
   q.qddx = (A >> (shift - 1)) >> 2;
   A = shl(fx_add(fx_sub(fx_sub(y0, y1), y1), y2), 9);
   B = shl(fx_sub(y1, y0), 10);
-  q.qy = snap_y(shl(y0, 10) >> 2);
+  q.qy = snap_y(fx_from_24_8(y0, wide));
   q.qdy = fx_add(B, A >> shift) >> 2;
   q.qddy = (A >> (shift - 1)) >> 2;
-  q.q_last_x = shl(x2, 10) >> 2;
-  q.q_last_y = snap_y(shl(y2, 10) >> 2);
+  q.q_last_x = fx_from_24_8(x2, wide);
+  q.q_last_y = snap_y(fx_from_24_8(y2, wide));
   *first_y = q.qy;
   *last_y = q.q_last_y;
   e.x = e.dx = e.dy = e.upper_y = e.lower_y = 0;
@@ -247,9 +252,9 @@ SKB_HDN int set_quad(Edge& e, QuadState& q, const float* p, fx* first_y, fx* las
 }
 
 // SWEdge::CanBeIgnored (sw_edge.cc:72-88)
-SKB_HD int can_be_ignored(float scan_top, float scan_bottom, fx y0, fx y1) {
-  fx start_y = snap_y(line_coord(scan_top));
-  fx stop_y = snap_y(line_coord(scan_bottom));
+SKB_HD int can_be_ignored(float scan_top, float scan_bottom, fx y0, fx y1, int wide = 0) {
+  fx start_y = snap_y(line_coord(scan_top, wide));
+  fx stop_y = snap_y(line_coord(scan_bottom, wide));
   return (y0 >= stop_y || y1 <= start_y);
 }
 

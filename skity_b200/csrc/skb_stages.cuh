@@ -103,14 +103,14 @@ SKB_HDN void op_setup(OpGeom& g, const float clip[4], uint32_t surf_w, uint32_t 
 // (SWEdgeBuilder::AddLine / ChopQuadAtYExtrema + AddQuad, sw_edge.cc:299-336).  Edges go to
 // slot[0], slot[1]; the valid bit (24) tells the walker which are live, bit 25 marks quadratics
 // whose cull extent (q_first_y, q_last_y) is parked in prev/next.
-SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2], QuadState qslot[2]) {
+SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2], QuadState qslot[2], int wide = 0) {
   slot[0].curve = 0;
   slot[1].curve = 0;
   if (npts == 2) {
     Edge e;
     e.curve = 0;
     e.prev = e.next = -1;
-    if (set_line(e, p[0].x, p[0].y, p[1].x, p[1].y)) {
+    if (set_line(e, p[0].x, p[0].y, p[1].x, p[1].y, wide)) {
       e.curve |= 1 << 24;
       slot[0] = e;
     }
@@ -123,7 +123,7 @@ SKB_HDN void flatten_prim(int npts, const V2 p[3], Edge slot[2], QuadState qslot
       e.curve = 0;
       float q[6] = {mono[2 * j].x, mono[2 * j].y, mono[2 * j + 1].x, mono[2 * j + 1].y, mono[2 * j + 2].x, mono[2 * j + 2].y};
       fx fy, ly;
-      if (set_quad(e, qs, q, &fy, &ly)) {
+      if (set_quad(e, qs, q, &fy, &ly, wide)) {
         e.curve |= (1 << 24) | (1 << 25);
         e.prev = fy;
         e.next = ly;

@@ -308,7 +308,7 @@ struct WalkState {
 // SWEdgeBuilder culling (sw_edge.cc:322-336) + SortEdges + ProcessEdges (sw_raster.cc:679-729) and
 // the prologue of WalkEdges (:549-563).  Returns false when the path has no edge to sweep.
 SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
-                           fx left_clip, fx right_clip, WalkState& ws) {
+                           fx left_clip, fx right_clip, WalkState& ws, int wide = 0) {
   int n = 0;
   for (int i = 2; i < n_slots; i++) {
     if (!((E[i].curve >> 24) & 1)) continue;
@@ -317,7 +317,7 @@ SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f,
     const bool quad = (E[i].curve >> 25) & 1;
     fx y0 = quad ? E[i].prev : E[i].upper_y;
     fx y1 = quad ? E[i].next : E[i].lower_y;
-    if (can_be_ignored(scan_top_f, scan_bottom_f, y0, y1)) continue;
+    if (can_be_ignored(scan_top_f, scan_bottom_f, y0, y1, wide)) continue;
     ord[n++] = i;
   }
   if (n == 0) return false;
@@ -598,10 +598,10 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
 // mode: 0 = nested loops (the reference's shape, kept as a cross-check), 1 = flat loop (what the GPU runs)
 SKB_HDN void walk_path(Edge* E, QuadState* Q, const uint16_t* qmap, int n_slots, int32_t* ord, float scan_top_f,
                        float scan_bottom_f, int start_y, int stop_y, fx left_clip, fx right_clip, int even_odd,
-                       RecSink& sink, int mode = 1) {
+                       RecSink& sink, int mode = 1, int wide = 0) {
   const int flat = mode != 0;
   WalkState ws;
-  if (!walk_prologue(E, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws)) return;
+  if (!walk_prologue(E, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws, wide)) return;
   if (flat && !qmap) walk_bands_flat(E, Q, ws, stop_y, left_clip, right_clip, even_odd, sink);
   else walk_bands_nested(E, Q, qmap, ws, stop_y, left_clip, right_clip, even_odd, sink);
 }

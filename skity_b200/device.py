@@ -55,6 +55,7 @@ def lib():
         L.skb_surface_destroy.argtypes = [vp]
         L.skb_surface_destroy.restype = None
         L.skb_surface_set_band.argtypes = [vp, u32, u32]
+        L.skb_surface_set_coord_mode.argtypes = [vp, ctypes.c_int]
         L.skb_frame_begin.argtypes = [vp, ctypes.c_int]
         L.skb_frame_encode.argtypes = [vp, vp, sz]
         L.skb_frame_flush.argtypes = [vp]
@@ -115,6 +116,10 @@ class Surface:
 
     def set_band(self, y0, y1):
         _check(lib().skb_surface_set_band(self._h, y0, y1), "skb_surface_set_band")
+
+    def set_coord_mode(self, mode):
+        """0 auto (wide above 8192 px), 1 the reference's int32 arithmetic (wraps at 8192 px), 2 wide."""
+        _check(lib().skb_surface_set_coord_mode(self._h, int(mode)), "skb_surface_set_coord_mode")
 
     def begin(self, clear=True):
         _check(lib().skb_frame_begin(self._h, 1 if clear else 0), "skb_frame_begin")

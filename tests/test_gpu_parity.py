@@ -278,10 +278,12 @@ def test_batch_of_canvases_in_one_display_list(dev):
 
 
 def test_large_canvas_band_split_and_determinism(dev):
-    """16384 x 16384 (BASELINE config 4a's canvas): four tile bands reproduce the whole frame."""
+    """16384 x 16384 (BASELINE config 4a's canvas) in the REFERENCE coordinate mode: four tile bands reproduce the
+    whole frame (the wide mode is covered by test_config_c4a_full_size_vs_wide_oracle)."""
     s = scene.scene_random_fills_fast(40000, 16384, 4, box=128.0)
     dl = hostlib.encode_scene(s.encode())
     surf = dev.create_surface(16384, 16384)
+    surf.set_coord_mode(1)
     surf.begin(True)
     surf.encode(dl)
     surf.flush()
@@ -320,3 +322,84 @@ def test_two_surfaces_in_flight_with_async_read_back(dev):
     finally:
         for sf, _ in lanes:
             sf.close()
+
+
+# ---- the BASELINE.json configs at their NAMED sizes, against the digests of the reference's frames ----------------
+def _digest_store():
+    return np.load(os.path.join(GOLDEN, "config_digests.npz"))
+
+
+def _check_config(dev, name, sc, exact=True):
+    import config_digest
+    dl = hostlib.encode_scene(sc.encode())
+    surf = dev.create_surface(sc.width, sc.height)
+    try:
+        got = surf.render(dl)
+        st = surf.stats()
+    finally:
+        surf.close()
+    assert st["n_launches"] > 0
+    ok, msg = config_digest.compare(_digest_store(), name, got)
+    assert ok, msg
+    return st
+
+
+def test_config_c2_full_size_vs_reference(dev):
+    """C2 as BASELINE names it: 20k stroked+filled gradient paths with the nested clip stack, 4096^2 — every byte equal
+    to the frame of the compiled reference (digest made by tests/golden/make_config_digests.py)."""
+    _check_config(dev, "c2", scene.scene_c2(20000, 4096, 2))
+
+
+def test_config_c3_full_size_vs_reference(dev):
+    """C3: 2k blurred paths, 8192^2 (2000 blur temporaries composited level by level)."""
+    _check_config(dev, "c3", scene.scene_c3(2000, 8192, 3))
+
+
+def test_config_c4b_64_canvases_vs_reference(dev):
+    """C4b: 64 of the 1920x1080 canvases (1000 paths each), rendered as ONE display list batch."""
+    import config_digest
+    store = _digest_store()
+    n = 64
+    blobs = [scene.scene_c4b(i).encode() for i in range(n)]
+    dl, ids = hostlib.encode_scene_batch(blobs)
+    surf = dev.create_surface(16, 16)
+    try:
+        surf.begin(True)
+        surf.encode(dl)
+        surf.flush()
+        for i in range(n):
+            got = surf.read_batch_canvas(ids[i], 1920, 1080)
+            ok, msg = config_digest.compare(store, f"c4b_{i}", got)
+            assert ok, msg
+    finally:
+        surf.close()
+
+
+def test_config_c4a_full_size_vs_wide_oracle(dev):
+    """C4a: 1M paths on 16384^2 in the wide-coordinate mode (the default above 8192 px), whole frame and as four tile
+    bands, against the digest of the pinned port in the same mode (the compiled reference wraps at 8192 px and cannot
+    render this config; tests/golden/make_config_digests.py has the details and the windowed second opinion)."""
+    import config_digest
+    from skity_b200 import multigpu
+    store = _digest_store()
+    sc = scene.scene_c4a()
+    dl = hostlib.encode_scene(sc.encode())
+    surf = dev.create_surface(16384, 16384)
+    try:
+        got = surf.render(dl)
+        st = surf.stats()
+        ok, msg = config_digest.compare(store, "c4a", got)
+        assert ok, msg
+        # all four quadrants carry geometry: the command count is in line with C1's share of its work items
+        assert st["n_cmds"] > 0.25 * st["n_items"]
+        lower = int(got[8192:].astype(np.uint64).sum())
+        assert lower > 0
+        bands = multigpu.band_ranges(16384, 4)
+        for (y0, y1) in bands:
+            surf.set_band(y0, y1)
+            surf.begin(True)
+            surf.flush()
+            rows = surf.read_pixels(0, y0, 16384, y1 - y0)
+            assert np.array_equal(rows, got[y0:y1])
+    finally:
+        surf.close()
