@@ -4,16 +4,22 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU backend on the host cores
 
-A "step" is one frame: clear the canvas and rasterise the whole synthetic scene (flatten, walk,
-coverage, bin, fine [, blur]).  Workload at N=1: BASELINE.json configs[1] — 10k random quad/cubic
-paths, mixed nonzero/even-odd, solid fill, 4096x4096 (seed 1).  At N>1 every rank renders its own
-canvas of that workload (seed 1+rank): the "batch of independent canvases split by canvas"
-partition, no data-path collective, weak scaling.
+Default workload = the configuration BASELINE.json's metric is quoted on ("at 1/2/4/8 B200"): config 4a,
+1M random quad/cubic paths on ONE 16384x16384 canvas (seed 4), which fits one GPU.  At N > 1 the canvas is
+partitioned into N contiguous bands of tile rows (STRONG scaling: the same frame, N times the hardware): the
+display list is replicated, every rank culls the draws that cannot reach its band before flattening, renders
+its band, and its fine pass stores the finished pixels straight into rank 0's canvas over NVLink peer memory
+(skb_surface_set_remote_canvas) — the gather of the north star fused into the producing kernel.  The same
+gather done by NCCL send/recv after the frame is timed beside it (`gather`).
 
-  value  Mpix/s of canvas filled, whole job, display list already resident in HBM, timed with CUDA
-         events on the surface's stream over exactly K steps, max over ranks.
-  e2e    same metric through the C ABI with HOST buffers: every step copies the display list from
-         pinned host memory (H2D) and reads the finished canvas back (D2H) inside the timed region.
+A "step" is one frame: clear, flatten, setup, walk, coverage, bin, fine — all paths, all pixels.
+  value  Mpix/s of canvas filled, whole job, display list resident in HBM, CUDA events on the surface's stream
+         over exactly K steps, max over ranks.
+  e2e    the same metric through the C ABI with HOST buffers: every step uploads the display list from pinned
+         host memory on every rank (H2D), renders, and rank 0 reads the gathered canvas back into pinned host
+         memory (D2H) — all inside the timed region.
+Other workloads (--workload): c1 (10k paths 4096^2; at N > 1 one canvas per rank, weak scaling), c4b (batch
+of 1920x1080 canvases split by canvas, 64 per display list), c2, c3.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -30,28 +36,40 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of this
-# workload (profiles/r01_ncu_top3_c1.txt); None where no capture exists
-NCU_TRAFFIC = {("c1", "k_walk"): 29028352 + 112788480, ("c1", "k_cover"): 146949632 + 124314624,
-               ("c1", "k_fine"): 235782912 + 49222656}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures (profiles/); None where
+# no capture of that (workload, kernel) exists.  Filled in from profiles/r02_*.
+NCU_TRAFFIC = {}
+try:
+    NCU_TRAFFIC = {tuple(k.split("/")): v for k, v in json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).items()}
+except Exception:
+    pass
 
-E2E_LANES = int(os.environ.get("SKB_BENCH_LANES", "4"))      # host threads the end-to-end loop drives frames with
-E2E_SURFACES = int(os.environ.get("SKB_BENCH_SURFACES_PER_LANE", "1"))  # surfaces a thread alternates between: the
-                                                             # read-back of its last frame overlaps its next frame
 METRIC = "canvas_mpix_per_s"
 UNIT = "Mpix/s"
+C4B_BATCH = 64          # canvases per display list (one launch sequence renders all of them)
+C4B_TOTAL = 1024
 
 
-def workload(name, rank):
+def workload(name, rank, world):
+    """-> (scene or list of scenes, description, partition, scaling)"""
     from skity_b200 import scene
+    if name == "c4a":
+        return scene.scene_c4a(), "c4a: 1M random quad/cubic paths (128 px), solid fill, ONE 16384x16384 canvas", "bands", "strong"
+    if name == "c4a-small":
+        return scene.scene_random_fills_fast(20000, 4096, 4, 128.0), "c4a-small: 20k paths 4096x4096 (smoke size)", "bands", "strong"
     if name == "c1":
-        return scene.scene_c1(10000, 4096, 1 + rank), "c1: 10k random quad/cubic paths, mixed nonzero/even-odd, solid fill, 4096x4096"
+        return scene.scene_c1(10000, 4096, 1 + rank), "c1: 10k random quad/cubic paths, mixed nonzero/even-odd, solid fill, 4096x4096", "canvas", "weak"
     if name == "c1-small":
-        return scene.scene_c1(1000, 1024, 1 + rank), "c1-small: 1k paths 1024x1024 (smoke size)"
+        return scene.scene_c1(1000, 1024, 1 + rank), "c1-small: 1k paths 1024x1024 (smoke size)", "canvas", "weak"
     if name == "c3":
-        return scene.scene_c3(2000, 8192, 3 + rank), "c3: 2k blurred paths (sigma 4-64) 8192x8192"
+        return scene.scene_c3(2000, 8192, 3 + rank), "c3: 2k blurred paths (sigma 4-64) 8192x8192", "canvas", "weak"
     if name == "c2":
-        return scene.scene_c2(20000, 4096, 2 + rank, clip_every=0), "c2 (no clip stack): 20k stroked+filled gradient paths 4096x4096"
+        return scene.scene_c2(20000, 4096, 2 + rank), "c2: 20k stroked+filled gradient paths with the nested clip stack 4096x4096", "canvas", "weak"
+    if name == "c4b":
+        per_rank = C4B_TOTAL // world
+        mine = [scene.scene_c4b(i) for i in range(rank * per_rank, rank * per_rank + min(per_rank, C4B_BATCH))]
+        return mine, (f"c4b: batch of {C4B_TOTAL} independent 1920x1080 canvases x 1000 paths split by canvas; each step renders "
+                      f"{len(mine)} canvases per rank as one display list"), "batch", "weak"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -116,7 +134,7 @@ def measured_peak():
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from skity_b200 import device, hostlib
+    from skity_b200 import device, hostlib, multigpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -127,235 +145,319 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    sc, desc = workload(args.workload, rank)
-    W, H = sc.width, sc.height
-    n_paths = sc.n_draws
-    blob = sc.encode()
-    dl = hostlib.encode_scene(blob)                 # host-side encode (CudaCanvas), outside every timed region
+    sc, desc, partition, scaling = workload(args.workload, rank, world)
+    t_enc = time.perf_counter()
+    if partition == "batch":
+        blobs = [s.encode() for s in sc]
+        dl, canvas_ids = hostlib.encode_scene_batch(blobs)
+        W, H, n_canvases = 1920, 1080, len(sc)
+        n_paths = sum(s.n_draws for s in sc)
+        surf_w = surf_h = 16
+        blob = blobs[0]
+    else:
+        blob = sc.encode()
+        dl = hostlib.encode_scene(blob)             # host-side encode (CudaCanvas), outside every timed region
+        W, H, n_canvases = sc.width, sc.height, 1
+        n_paths = sc.n_draws
+        surf_w, surf_h = W, H
+    host_encode_s = time.perf_counter() - t_enc
     dl_pinned = torch.empty(len(dl), dtype=torch.uint8).pin_memory()
     dl_pinned.copy_(torch.frombuffer(bytearray(dl), dtype=torch.uint8))
-    out_pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
-    out_np = out_pinned.numpy()
+    del dl
+    n_dl = dl_pinned.numel()
 
     dev = device.Device(local_rank)
-    surf = dev.create_surface(W, H)
+    surf = dev.create_surface(surf_w, surf_h)
     stream = torch.cuda.ExternalStream(surf.stream(), device=torch.device("cuda", local_rank))
+    bands = multigpu.band_ranges(H, world) if partition == "bands" else None
+    banded = partition == "bands" and world > 1
+    if banded:
+        surf.set_band(*bands[rank])
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # what rank 0 reads back per step
+    if partition == "batch":
+        out_pinned = torch.empty((n_canvases, H, W, 4), dtype=torch.uint8).pin_memory()
+    elif rank == 0 or not banded:
+        out_pinned = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    else:
+        out_pinned = None
+    out_np = out_pinned.numpy() if out_pinned is not None else None
+
+    def read_back():
+        if partition == "batch":
+            for i, sid in enumerate(canvas_ids):
+                surf.read_batch_canvas(sid, W, H, out=out_np[i])
+        elif out_np is not None:
+            surf.read_pixels(out=out_np)
+
+    # ---- upload once, warm up
+    surf.begin(True)
+    surf.encode((dl_pinned.data_ptr(), n_dl))
+    surf.flush()
+    surf.sync()
+    single_check = None
+    if banded:
+        # first the separate NCCL gather (bands rendered into each rank's own canvas), timed on its own ...
+        def band_tensor(a, b):
+            return multigpu.surface_band_tensor(surf, a, b)[0]
+        gather_ms = []
+        for _ in range(3):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            multigpu.gather_bands(band_tensor, bands, rank, world, dist)
+            g1.record()
+            torch.cuda.synchronize()
+            gather_ms.append(g0.elapsed_time(g1))
+        tg = torch.tensor([min(gather_ms)], device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        nccl_gather_ms = float(tg[0])
+        if rank == 0:
+            single_check = int(surf.read_pixels(0, bands[-1][0], W, min(64, bands[-1][1] - bands[-1][0])).astype(np.uint64).sum())
+        # ... then the gather fused into the fine pass: from here on every rank stores its band into rank 0's canvas
+        barrier()
+        multigpu.fuse_gather_into_fine_pass(surf, rank, dist)
+        barrier()
+
     def step_resident():
         surf.begin(True)
         surf.flush()
 
-    def step_e2e():
-        surf.begin(True)
-        surf.encode((dl_pinned.data_ptr(), len(dl)))
-        surf.flush()
-        surf.read_pixels(out=out_np)
-
-    # ---- device-resident throughput
-    surf.begin(True)
-    surf.encode((dl_pinned.data_ptr(), len(dl)))
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
+    if banded and rank == 0:
+        fused_check = int(surf.read_pixels(0, bands[-1][0], W, min(64, bands[-1][1] - bands[-1][0])).astype(np.uint64).sum())
+        if fused_check != single_check:
+            raise SystemExit("band stored over NVLink differs from the band gathered by NCCL")
+    barrier()
+
+    # ---- device-resident throughput
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms = np.zeros(8)
     launches = 0
-    bytes_fine = bytes_cover = bytes_walk = 0
+    st = None
     e0.record(stream)
     for _ in range(args.steps):
         step_resident()
         st = surf.stats()      # waits for the frame; per-stage CUDA-event timings of this step
         stage_ms += np.array(st["ms_stage"])
         launches += st["n_launches"]
-        bytes_fine, bytes_cover, bytes_walk = st["bytes_fine"], st["bytes_cover"], st["bytes_walk"]
     e1.record(stream)
     barrier()
     ms_resident = e0.elapsed_time(e1) / args.steps
 
-    # ---- end to end through the C ABI with host buffers, one frame at a time
-    for _ in range(2):
-        step_e2e()
+    # ---- end to end through the C ABI with host buffers: H2D of the display list on every rank, render, the bands
+    # land in rank 0's canvas (peer stores), rank 0 reads the canvas back; one frame at a time
+    def step_e2e():
+        surf.begin(True)
+        surf.encode((dl_pinned.data_ptr(), n_dl))
+        surf.flush()
+        if banded:
+            surf.sync()
+            dist.barrier()          # every band is in rank 0's canvas
+        read_back()
+        if banded:
+            dist.barrier()          # rank 0 has its copy: the canvas may be overwritten
+
+    step_e2e()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     f0.record(stream)
     for _ in range(args.steps):
         step_e2e()
     f1.record(stream)
     barrier()
-    ms_e2e_serial = f0.elapsed_time(f1) / args.steps
-
-    # ---- end to end with several frames in flight: every step still uploads its display list from pinned
-    # memory, renders, and reads its canvas back to pinned memory, but steps are dealt round-robin to E2E_LANES
-    # surfaces, each driven by its own host thread on its own stream, so that the read-back of one frame
-    # overlaps the rendering of others and the latency-bound sweep of one frame shares the SMs with the
-    # coverage / fine passes of another — what an application streaming frames through the backend does
-    import threading
-    lanes = [(surf, out_np)]
-    for _ in range(E2E_LANES * E2E_SURFACES - 1):
-        sf = dev.create_surface(W, H)
-        lanes.append((sf, torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy()))
-    lane_streams = [torch.cuda.ExternalStream(sf.stream(), device=torch.device("cuda", local_rank)) for sf, _ in lanes]
-
-    def run_e2e_lanes(n_steps, host_buffers=True):
-        def work(t):
-            mine = lanes[t * E2E_SURFACES:(t + 1) * E2E_SURFACES]
-            for k, _ in enumerate(range(t, n_steps, E2E_LANES)):
-                sf, out = mine[k % E2E_SURFACES]
-                sf.begin(True)
-                if host_buffers:
-                    sf.encode((dl_pinned.data_ptr(), len(dl)))
-                sf.flush()
-                if host_buffers:
-                    sf.read_pixels_async(out)   # stream-ordered: the next begin() on this surface waits for it
-        threads = [threading.Thread(target=work, args=(t,)) for t in range(E2E_LANES)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-
-    run_e2e_lanes(2 * E2E_LANES * E2E_SURFACES)
-    for sf, _ in lanes:
-        sf.sync()
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(stream)                               # every stream is idle here
-    run_e2e_lanes(args.steps)
-    for st_ in lane_streams[1:]:                    # p1 after the last frame of every lane
-        ev = torch.cuda.Event()
-        ev.record(st_)
-        stream.wait_event(ev)
-    p1.record(stream)
-    barrier()
-    ms_e2e = p0.elapsed_time(p1) / args.steps
-    # the same lanes with the display list resident and no read-back (for comparison with `value`, which is
-    # measured one frame at a time so that its per-stage timings mean something)
-    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for sf, _ in lanes:
-        sf.sync()
-    q0.record(stream)
-    run_e2e_lanes(args.steps, host_buffers=False)
-    for st_ in lane_streams[1:]:
-        ev = torch.cuda.Event()
-        ev.record(st_)
-        stream.wait_event(ev)
-    q1.record(stream)
-    barrier()
-    ms_resident_lanes = q0.elapsed_time(q1) / args.steps
-    for sf, out in lanes[1:]:
-        if not np.array_equal(out, lanes[0][1]):
-            raise SystemExit("frames rendered on different surfaces differ")
-        sf.close()
+    ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / args.steps
+    ms_e2e = max(f0.elapsed_time(f1) / args.steps, 0.0)
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the complete plug-in path (what a skity::Canvas user pays): CudaContextCreate'd surface -> LockCanvas ->
+    # Canvas calls (host encode) -> Flush -> ReadPixels, per step; N = 1 only
+    ms_canvas = None
+    if world == 1 and partition != "batch" and not args.no_canvas_e2e:
+        try:
+            n_c = max(1, min(args.steps, 3))
+            hostlib.render_scene_cuda(blob, local_rank)
+            t0 = time.perf_counter()
+            for _ in range(n_c):
+                hostlib.render_scene_cuda(blob, local_rank)
+            ms_canvas = (time.perf_counter() - t0) * 1e3 / n_c
+        except Exception as e:  # noqa: BLE001
+            ms_canvas = f"failed: {e}"
+
     if world > 1:
-        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_serial, ms_resident_lanes], device="cuda")
+        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_wall], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_resident, ms_e2e, ms_e2e_serial, ms_resident_lanes = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms_resident, ms_e2e, ms_e2e_wall = float(t[0]), float(t[1]), float(t[2])
+        ts = torch.tensor(stage_ms, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        stage_ms = ts.cpu().numpy()
+        tl = torch.tensor([launches], device="cuda")
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+        launches = int(tl[0])
 
     if rank == 0:
-        mpix = W * H / 1e6
-        value = world * mpix / (ms_resident / 1e3)
-        e2e_value = world * mpix / (ms_e2e / 1e3)
-        stage_ms /= args.steps
+        canvases = n_canvases * (world if partition in ("canvas", "batch") else 1)
+        mpix = canvases * W * H / 1e6
+        paths = n_paths * (world if partition in ("canvas", "batch") else 1)
+        value = mpix / (ms_resident / 1e3)
+        ms_e2e_used = ms_e2e_wall   # host copies are part of it: wall clock around the K steps, max over ranks
+        stage_ms = stage_ms / args.steps
         peak, peak_kind = measured_peak()
         names = device.STAGE_NAMES
-        # dominant kernel = the longest of the three data-facing stages, each a single kernel:
-        # k_walk (sweep), k_cover (coverage), k_fine (paint + blend)
-        cands = [("k_walk (edge sweep)", float(stage_ms[2]), bytes_walk),
-                 ("k_cover (coverage)", float(stage_ms[3]), bytes_cover),
-                 ("k_fine (paint+blend)", float(stage_ms[5]), bytes_fine)]
-        dom, dom_ms, dom_bytes = max(cands, key=lambda c: c[1])
-        achieved = dom_bytes / (dom_ms / 1e3) / 1e9 if dom_ms > 0 else 0.0
+        cands = [("k_walk", "sweep: edges -> trapezoid rows", float(stage_ms[2]), st["bytes_walk"]),
+                 ("k_cover", "coverage: trapezoid rows -> A8 tile masks", float(stage_ms[3]), st["bytes_cover"]),
+                 ("k_fine", "fine: paint + blend, RGBA8 tiles", float(stage_ms[5]), st["bytes_fine"])]
+        if stage_ms[6] > 0 and st.get("bytes_blur"):
+            cands.append(("k_blur", "blur: separable StackBlur, 2 passes", float(stage_ms[6]), st["bytes_blur"]))
+        dom = max(cands, key=lambda c: c[2])
+        achieved = dom[3] / (dom[2] / 1e3) / 1e9 if dom[2] > 0 else 0.0
+        wkey = args.workload
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_resident, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "i32 16.16 fixed point + u8 (fp32 for curve lowering)",
+            "scaling": scaling, "vs_baseline": None, "dtype": "i32 16.16 fixed point + u8 (fp32 for curve lowering)",
             "data": "synthetic",
-            "config": {"workload": desc, "canvases_per_step": world, "paths_per_canvas": n_paths,
-                       "l2": "working set per step (records + A8 masks + canvas, ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
-                       "partition": "by canvas" if world > 1 else "single",
-                       "frames_in_flight": "value: 1 (so that the per-stage timings are those of a frame); e2e: %d host threads x %d surfaces" % (E2E_LANES, E2E_SURFACES)},
-            "resident_frames_in_flight": {"frames_in_flight": E2E_LANES, "ms_per_step": round(ms_resident_lanes, 4),
-                                          "value": round(world * W * H / 1e6 / (ms_resident_lanes / 1e3), 2)},
-            "paths_per_s": round(world * n_paths / (ms_resident / 1e3), 1),
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": len(dl),
-                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": round(ms_e2e, 4), "frames_in_flight": E2E_LANES,
-                    "host_threads": E2E_LANES, "surfaces_per_thread": E2E_SURFACES,
-                    "one_frame_at_a_time": {"value": round(world * mpix / (ms_e2e_serial / 1e3), 2),
-                                            "ms_per_step": round(ms_e2e_serial, 4)}},
+            "config": {"workload": desc, "canvases_per_step": canvases, "paths_per_step": paths,
+                       "l2": "working set per step (display list, edges, records, A8 masks, canvas) is several GB at N=1, far above the 126 MB L2; no explicit flush",
+                       "partition": {"bands": f"tile-row bands of one canvas over {world} GPU(s), display list replicated, culled per band on the device, "
+                                              "bands stored into rank 0's canvas by the fine pass (NVLink peer memory)" if world > 1 else "single GPU, whole canvas",
+                                     "canvas": "one canvas per rank", "batch": "canvases dealt to ranks, one display list per rank"}[partition],
+                       "coord_mode": "wide (canvas > 8192 px: the reference's 16.16 conversion without its int32 wrap)" if max(W, H) > 8192 else "reference",
+                       "frames_in_flight": 1},
+            "paths_per_s": round(paths / (ms_resident / 1e3), 1),
+            "e2e": {"value": round(mpix / (ms_e2e_used / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(n_dl) * world,
+                    "d2h_bytes_per_step": int(canvases * W * H * 4), "ms_per_step": round(ms_e2e_used, 4),
+                    "what": "C ABI with host buffers: display list H2D from pinned memory on every rank, frame, "
+                            + ("bands into rank 0's canvas over NVLink, barrier, " if banded else "") + "canvas D2H into pinned memory; one frame at a time"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 5), "traffic": NCU_TRAFFIC.get((args.workload, dom.split()[0])),
-                         "peak_kind": peak_kind,
-                         "algorithmic_bytes_per_launch": int(dom_bytes), "ms_per_launch": round(dom_ms, 4)},
+            "roofline": {"bound": "hbm", "kernel": f"{dom[0]} ({dom[1]})", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 5), "traffic": NCU_TRAFFIC.get((wkey, dom[0])),
+                         "peak_kind": peak_kind, "algorithmic_bytes_per_launch": int(dom[3]), "ms_per_launch": round(dom[2], 4),
+                         "per_rank": world > 1},
+            "roofline_stages": {c[0]: {"ms": round(c[2], 4), "algorithmic_bytes": int(c[3]),
+                                       "achieved_gbs": round(c[3] / (c[2] / 1e3) / 1e9, 2) if c[2] > 0 else None,
+                                       "frac": round(c[3] / (c[2] / 1e3) / 1e9 / peak, 5) if c[2] > 0 else None,
+                                       "traffic": NCU_TRAFFIC.get((wkey, c[0]))} for c in cands},
             "stages_ms": {names[i]: round(float(stage_ms[i]), 4) for i in range(8)},
-            "stage_frac_of_hbm_roofline": {n: round(b / (m / 1e3) / 1e9 / peak, 5) if m > 0 else None for n, m, b in cands},
+            "frame_counters": {k: int(st[k]) for k in ("n_ops", "n_prims", "n_rows", "n_records", "n_items", "n_cmds", "n_retries")},
+            "host_encode_ms_outside_timed_region": round(host_encode_s * 1e3, 1),
             "clocks": clocks,
         }
+        if banded:
+            line["gather"] = {"fused_in_fine_pass": True, "nccl_send_recv_ms": round(nccl_gather_ms, 4),
+                              "bytes_into_rank0": int((H - bands[0][1]) * W * 4)}
+        if ms_canvas is not None:
+            line["e2e_canvas"] = ({"value": round(mpix / (ms_canvas / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms_canvas, 3),
+                                   "what": "skity plug-in API per step: GPUContext -> CreateSurface -> LockCanvas -> Canvas::DrawPath calls "
+                                           "(host encode) -> Flush -> ReadPixels, wall clock"}
+                                  if not isinstance(ms_canvas, str) else {"error": ms_canvas})
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(blob, dl, W, H)
+            line["cpu_baseline"] = cpu_baseline(args.workload, blob, W, H)
         print(json.dumps(line), flush=True)
     surf.close()
     dev.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(blob, dl, W, H):
-    """The reference's software backend (oracle/_ref) — or the oracle port where it is not built —
-    timed on one host core on the same scene (SWCanvas is single-threaded)."""
+def _c4a_window_blobs(blob, size):
+    from oracle import windows
+    rec = windows.fills_records(blob)
+    n = windows.n_windows(size)
+    return [windows.window_scene(blob, rec, ix, iy, size) for iy in range(n) for ix in range(n)]
+
+
+def cpu_baseline(name, blob, W, H):
+    """The reference's software backend (oracle/_ref) — or the oracle port where it is not built — on ONE host core
+    (SWCanvas is single-threaded), on a bounded sample of the workload."""
     from oracle import refsw, port
-    if refsw.available():
-        _, sec = refsw.render_scene(blob, return_seconds=True)
-        kind = "reference"
-    else:
+    from skity_b200 import hostlib
+    use_ref = refsw.available()
+    kind = "reference" if use_ref else "port"
+
+    def render_seconds(b):
+        if use_ref:
+            return refsw.render_scene(b, return_seconds=True)[1]
+        d = hostlib.encode_scene(b)
         t0 = time.perf_counter()
-        port.render(dl)
-        sec = time.perf_counter() - t0
-        kind = "port"
-    return {"value": round(W * H / 1e6 / sec, 3), "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "the full scene once (all paths), draw loop only", "seconds": round(sec, 3)}
+        port.render(d)
+        return time.perf_counter() - t0
+
+    if W > 8192 or H > 8192:
+        # beyond the reference's numeric range (coordinates wrap at 8192 px): one 4096^2 window of the canvas, rendered
+        # under a translation with the paths that touch it (oracle/windows.py) = 1/16 of the frame
+        sub, _, cnt = _c4a_window_blobs(blob, W)[5]
+        sec = render_seconds(sub)
+        px = 4096 * 4096
+        sample = f"one 4096x4096 window of the canvas (window (1,1) of 4x4, {cnt} paths), draw loop only"
+    else:
+        sec = render_seconds(blob)
+        px = W * H
+        sample = "the full scene once (all paths), draw loop only"
+    return {"value": round(px / 1e6 / sec, 3), "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "seconds": round(sec, 3)}
 
 
-def _ref_band_worker(q_in, q_out, blob, n_bands, band):
-    """Renders the scene under a whole-pixel ClipRect band (the SW fast path, sw_canvas.cc:305-312)."""
-    import struct
+def _ref_worker(q_in, q_out, blobs):
     from oracle import refsw
-    from skity_b200 import scene as sc
-    magic, ver, w, h, n_ops, _ = struct.unpack_from("<6I", blob, 0)
-    y0, y1 = h * band // n_bands, h * (band + 1) // n_bands
-    clip = struct.pack("<2I", sc.OP_CLIP_RECT, 20) + struct.pack("<4fI", 0.0, float(y0), float(w), float(y1), 1)
-    banded = struct.pack("<6I", magic, ver, w, h, n_ops + 1, 0) + clip + blob[24:]
     refsw.lib()
     while True:
         msg = q_in.get()
         if msg is None:
             break
-        _, sec = refsw.render_scene(banded, return_seconds=True)
+        sec = 0.0
+        for b in blobs:
+            sec += refsw.render_scene(b, return_seconds=True)[1]
         q_out.put(sec)
 
 
+def _band_blob(blob, n_bands, band):
+    """The scene under a whole-pixel ClipRect band (the SW fast path, sw_canvas.cc:305-312)."""
+    import struct
+    from skity_b200 import scene as sc
+    magic, ver, w, h, n_ops, _ = struct.unpack_from("<6I", blob, 0)
+    y0, y1 = h * band // n_bands, h * (band + 1) // n_bands
+    clip = struct.pack("<2I", sc.OP_CLIP_RECT, 20) + struct.pack("<4fI", 0.0, float(y0), float(w), float(y1), 1)
+    return struct.pack("<6I", magic, ver, w, h, n_ops + 1, 0) + clip + blob[24:]
+
+
 def run_reference(args):
+    """The reference's own software backend on all host cores.  Canvases within its numeric range: one whole-pixel
+    ClipRect band per core.  The 16384^2 canvas: the 16 translated 4096^2 windows (oracle/windows.py) dealt to the cores;
+    with fewer than 16 cores a step renders the first `cores` windows and says so (a bounded sample)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     from oracle import refsw
-    sc, desc = workload(args.workload, 0)
-    W, H = sc.width, sc.height
-    blob = sc.encode()
+    sc, desc, partition, scaling = workload(args.workload, 0, 1)
+    if partition == "batch":
+        sc_list = sc
+        W, H = 1920, 1080
+    else:
+        sc_list = None
+        W, H = sc.width, sc.height
+    cores = os.cpu_count() or 1
     if not refsw.available():
-        # the compiled reference is absent: fall back to the oracle port, single core
         from oracle import port
         from skity_b200 import hostlib
+        blob = (sc_list[0] if sc_list else sc).encode()
+        if W > 8192:
+            blob = _c4a_window_blobs(blob, W)[5][0]
+            px, sample = 4096 * 4096, "oracle port, one 4096x4096 window per step (compiled reference absent)"
+        else:
+            px, sample = W * H, "oracle port, whole scene per step (compiled reference absent)"
         dl = hostlib.encode_scene(blob)
         times = []
         for i in range(args.warmup + args.steps):
@@ -363,40 +465,67 @@ def run_reference(args):
             port.render(dl)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
-        sec, cores, kind = sum(times) / len(times), 1, "port"
+        sec, used, kind = sum(times) / len(times), 1, "port"
     else:
-        cores = os.cpu_count() or 1
+        kind = "reference"
+        if sc_list is not None:
+            per = [[] for _ in range(cores)]
+            for i, s in enumerate(sc_list):
+                per[i % cores].append(s.encode())
+            per = [p for p in per if p]
+            px = len(sc_list) * W * H
+            sample = f"each step renders {len(sc_list)} canvases, dealt to {len(per)} processes"
+        elif W > 8192 or H > 8192:
+            wins = [w[0] for w in _c4a_window_blobs(sc.encode(), W)]
+            n_used = len(wins) if cores >= len(wins) else cores
+            per = [[] for _ in range(min(cores, n_used))]
+            for i in range(n_used):
+                per[i % len(per)].append(wins[i])
+            px = n_used * 4096 * 4096
+            sample = (f"each step renders {n_used} of the canvas's 16 translated 4096x4096 windows (the reference wraps at 8192 px), "
+                      f"one process per window, {len(per)} processes")
+        else:
+            blob = sc.encode()
+            per = [[_band_blob(blob, cores, b)] for b in range(cores)]
+            px = W * H
+            sample = "each step renders the whole scene once, split into one whole-pixel ClipRect band per host core (every process walks the full display list)"
+        used = len(per)
         ctx = mp.get_context("fork")
         q_out = ctx.Queue()
         qs, procs = [], []
-        for b in range(cores):
+        for blobs in per:
             q = ctx.Queue()
-            p = ctx.Process(target=_ref_band_worker, args=(q, q_out, blob, cores, b), daemon=True)
+            p = ctx.Process(target=_ref_worker, args=(q, q_out, blobs), daemon=True)
             p.start()
             qs.append(q)
             procs.append(p)
         times = []
+        budget_end = time.perf_counter() + 240.0     # the whole run ends within a few minutes
+        n_timed = 0
         for i in range(args.warmup + args.steps):
+            if i >= min(args.warmup, 1) + 1 and time.perf_counter() > budget_end:
+                break
             t0 = time.perf_counter()
             for q in qs:
                 q.put(1)
             for _ in qs:
                 q_out.get()
-            if i >= args.warmup:
+            if i >= min(args.warmup, 1):
                 times.append(time.perf_counter() - t0)
+                n_timed += 1
         for q in qs:
             q.put(None)
         for p in procs:
             p.join(timeout=5)
-        sec, kind = sum(times) / len(times), "reference"
-    value = W * H / 1e6 / sec
+        sec = sum(times) / len(times)
+        if n_timed < args.steps:
+            sample += f"; {n_timed} timed steps fit the time budget"
+    value = px / 1e6 / sec
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "i32 16.16 fixed point + u8", "data": "synthetic",
-            "config": {"workload": desc, "canvases_per_step": 1},
-            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "each step renders the whole scene once, split into one whole-pixel ClipRect band per host core "
-                                       "(every process walks the full display list)"},
+            "scaling": scaling, "vs_baseline": None, "dtype": "i32 16.16 fixed point + u8", "data": "synthetic",
+            "config": {"workload": desc},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": used, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -404,11 +533,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1")
+    ap.add_argument("--workload", default="c4a")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-canvas-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,6 +68,9 @@ typedef struct skb_frame_stats {
   uint64_t bytes_fine;   /* algorithmic bytes of the fine pass (pixels + commands + masks) */
   uint64_t bytes_cover;  /* algorithmic bytes of the coverage pass (records in, masks out) */
   uint64_t bytes_walk;   /* algorithmic bytes of the sweep (edge slots in, records + row table out) */
+  uint64_t bytes_blur;   /* algorithmic bytes of the blur passes: 2 passes x (4 B read + 4 B write) per temp pixel */
+  uint32_t n_rw_retried;     /* paths whose row-parallel sweep was retried (tables not self-consistent at first) */
+  uint32_t n_rw_sequential;  /* paths swept by the sequential walker */
 } skb_frame_stats;
 
 SKB_API skb_result skb_device_create(int ordinal, skb_device* out_device);

@@ -627,7 +627,9 @@ static void blit_trapezoid_row(builder* b, int y, fx ul, fx ur, fx ll, fx lr, fx
     fx l1 = ul, r1 = ll, l2 = ur, r2 = lr;
     if (l1 > r1) { fx t = l1; l1 = r1; r1 = t; }
     if (l2 > r2) { fx t = l2; l2 = r2; r2 = t; }
-    ll = lr = fx_add(l1 > l2 ? l1 : l2, r1 < r2 ? r1 : r2) / 2;
+    /* 64-bit sum: equal to the reference's int32 sum wherever that does not overflow (every coordinate below 8192 px);
+     * at the right clip of a 16384-px canvas (wide mode) the int32 sum would reach 2^31 and flip sign */
+    ll = lr = (fx)(((int64_t)(l1 > l2 ? l1 : l2) + (int64_t)(r1 < r2 ? r1 : r2)) / 2);
   }
   if (ul == ur && ll == lr) return;
   if (ul > ll) { fx t = ul; ul = ll; ll = t; }

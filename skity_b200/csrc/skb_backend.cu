@@ -23,6 +23,7 @@
 #include "include/skb.h"
 #include "skity_b200/csrc/skb_clip.cuh"
 #include "skity_b200/csrc/skb_stages.cuh"
+#include "skity_b200/csrc/skb_rowwalk.cuh"
 
 namespace skb {
 
@@ -134,7 +135,12 @@ struct FrameTables {
   uint32_t wide;  // wide-coordinate mode (skb_surface_set_coord_mode): 24.8 -> 16.16 without the reference's int32 wrap
 };
 
-__global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op) {
+// Also culls, before anything is flattened, the draws that cannot reach the rows this device renders (band split of
+// one canvas over several GPUs, skb_surface_set_band): the control points of a path bound its lowered quads up to half
+// of their extent (a quad's control point from Cubic::ToQuads is (3(c1'+c2') - (p0'+p3'))/4 with all four inside the
+// control polygon's bounds), so a path whose control points' y range, widened by half its height plus 2 px, misses the
+// band gets no primitives at all (`culled`: k_seg_count counts 0 for its segments).  Clip paths are never culled.
+__global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op, const SurfDesc* surfs) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   OpGeom g;
@@ -145,30 +151,58 @@ __global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op) {
   const skb_dl_op o = t.ops[op];
   if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
     const skb_dl_path p = t.paths[o.path];
+    const SurfDesc sd = surfs[o.surface];
+    const bool banded = o.kind == SKB_OP_FILL && (sd.row0 > 0 || sd.row1 < sd.h);
+    float ymin = 3.0e38f, ymax = -3.0e38f;
+    bool all_finite = true;
     for (uint32_t i = 0; i < p.n_segs; i++) {
       uint32_t s = p.seg_off + i;
       seg_op[s] = op;
-      if ((t.segs[s].type_flags & SKB_SEG_TYPE_MASK) == SKB_SEG_POINT) {
+      const uint32_t type = t.segs[s].type_flags & SKB_SEG_TYPE_MASK;
+      if (banded) {
+        const skb_dl_seg& sg = t.segs[s];
+        int first = 1, last = 0;  // control points p[2*first .. 2*last+1]; p[0..1] repeats the start point
+        if (type == SKB_SEG_LINE || type == SKB_SEG_CLOSE) last = 1;
+        else if (type == SKB_SEG_QUAD || type == SKB_SEG_CONIC) last = 2;
+        else if (type == SKB_SEG_CUBIC) last = 3;
+        const V2 st = xform(o.ctm, seg_start_point(t.segs, s));
+        all_finite &= finite_f(st.y);
+        ymin = fminf(ymin, st.y); ymax = fmaxf(ymax, st.y);
+        for (int k = first; k <= last; k++) {
+          const V2 q = xform(o.ctm, v2(sg.p[2 * k], sg.p[2 * k + 1]));
+          all_finite &= finite_f(q.y);
+          ymin = fminf(ymin, q.y); ymax = fmaxf(ymax, q.y);
+        }
+      }
+      if (type == SKB_SEG_POINT) {
         V2 q = xform(o.ctm, seg_start_point(t.segs, s));
         int32_t kx = float_key(q.x), ky = float_key(q.y);
         g.bmin_x = min(g.bmin_x, kx); g.bmax_x = max(g.bmax_x, kx);
         g.bmin_y = min(g.bmin_y, ky); g.bmax_y = max(g.bmax_y, ky);
       }
     }
+    if (banded && all_finite && p.n_segs > 0) {
+      const float pad = 0.5f * (ymax - ymin) + 2.0f;
+      if (ymax + pad < (float)sd.row0 || ymin - pad > (float)sd.row1) {
+        g.culled = 1;
+        g.bmin_x = g.bmin_y = INT_MAX;   // no bounds: k_op_setup leaves the op empty
+        g.bmax_x = g.bmax_y = INT_MIN;
+      }
+    }
   }
   geom[op] = g;
 }
 
-__global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt) {
+__global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt, const uint32_t* seg_op, const OpGeom* geom) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= t.n_segs) return;
-  prim_cnt[s] = (uint32_t)seg_prim_count(t.segs[s]);
+  prim_cnt[s] = geom[seg_op[s]].culled ? 0u : (uint32_t)seg_prim_count(t.segs[s]);
 }
 
 // One thread per lowered primitive: resolve (segment, k) from the scanned counts, evaluate and
 // transform its control points, fold them into the path bounds, emit its 0..2 edges.
 __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_prims, const uint32_t* seg_op, OpGeom* geom,
-                          Edge* edges, QuadState* quads) {
+                          Edge* edges, QuadState* quads, uint32_t* chord_cap, uint32_t* slot_op) {
   uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
   if (prim >= n_prims) return;
   uint32_t seg = find_interval(prim_off, t.n_segs, prim);
@@ -201,11 +235,21 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
   E[at + 1] = slot[1];
   if ((slot[0].curve >> 25) & 1) Q[at] = qslot[0];
   if ((slot[1].curve >> 25) & 1) Q[at + 1] = qslot[1];
+  if (chord_cap) {
+    // row-parallel walk (skb_rowwalk.cuh): an upper bound of the chords each edge can give — a line is one, a
+    // quadratic its first chord plus one per remaining subdivision — and the op that owns the slot
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const bool valid = (slot[j].curve >> 24) & 1, quad = (slot[j].curve >> 25) & 1;
+      chord_cap[slot_base + at + j] = valid ? (quad ? 1u + (uint32_t)edge_count(slot[j]) : 1u) : 0u;
+      slot_op[slot_base + at + j] = op;
+    }
+  }
 }
 
 // ------------------------------------------------------------------- stage 2: setup
 __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom, const SurfDesc* surfs, uint32_t* row_cnt,
-                           uint32_t* item_cnt, uint32_t* too_big) {
+                           uint32_t* item_cnt, uint32_t* too_big, RwOp* rwops, uint32_t* wrow_cnt) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const skb_dl_op o = t.ops[op];
@@ -251,6 +295,32 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
   }
   row_cnt[op] = rows;
   item_cnt[op] = items;
+  if (rwops) {
+    // row-parallel walk: the rows the sweep covers, from WalkEdges' start_y (the top of the path's bounds — above the
+    // scan rectangle when the path is clipped at the top) to where the records stop being read
+    RwOp r;
+    r.wrow_base = 0;
+    r.n_wrows = 0;
+    r.origin_row = 0;
+    r.y0q = INT_MAX;
+    r.fail = 0;
+    r.rec_base = r.n_recs = r.pad = 0;
+    uint32_t wr = 0;
+    if (rows) {
+      const OpGeom g = geom[op];
+      const int stop = min(g.stop_y, (g.ty0 + g.nty) * SKB_TILE);
+      const int64_t n = (int64_t)stop - (int64_t)g.start_y;
+      r.origin_row = g.start_y;
+      if (n <= 0 || n * 4 > SKB_RW_MAXQ) {
+        r.fail = SKB_RWFAIL_HARD;   // taller than the chord table addresses: swept sequentially
+      } else {
+        r.n_wrows = (int32_t)n;
+        wr = ((uint32_t)n + 1u + 15u) & ~15u;   // + the table's end entry, in groups of 16 rows
+      }
+    }
+    rwops[op] = r;
+    wrow_cnt[op] = wr;
+  }
 }
 
 // -------------------------------------------------------------------- stage 3: walk
@@ -262,7 +332,7 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
 // Also writes the owner of every tile row (trow_op): the coverage and clip stages start from a tile row or a
 // pixel row and would otherwise find its op by a binary search over row_base — 20 dependent loads at 1M ops.
 __global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, uint32_t* list, const uint32_t* row_base,
-                            uint32_t* trow_op) {
+                            uint32_t* trow_op, RwOp* rwops, const uint32_t* wrow_base, uint32_t* wgrp_op) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const OpGeom g = geom[op];
@@ -270,6 +340,12 @@ __global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, 
   {
     uint32_t* o = trow_op + row_base[op] / SKB_TILE;
     for (int r = 0; r < g.nty; r++) o[r] = op;
+  }
+  if (rwops) {   // row-parallel walk: where the op's walk rows are, and who owns each group of 16 of them
+    const uint32_t wb = wrow_base[op], we = wrow_base[op + 1];
+    rwops[op].wrow_base = wb;
+    for (uint32_t gq = wb >> 4; gq < (we >> 4); gq++) wgrp_op[gq] = op;
+    return;   // the sequential sweep's list is made later, of the paths the row-parallel form gives up on
   }
   // warp-aggregated append
   const unsigned m = __activemask();
@@ -333,6 +409,246 @@ __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
   walk_path(E, Q, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
             g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink, 1, (int)a.t.wide);
+}
+
+// ------------------------------------------------- stage 3 (row-parallel form): skb_rowwalk.cuh
+// The sweep as short kernels whose threads own a slot, a path or a (path, pixel row):
+//   k_rw_events   slot      chords' y (forward differencing of y alone), events of every walk row, first y of the path
+//   k_rw_bands0   path      band tables from the events alone
+//   k_rw_chain    slot      chords with their x, walked through the bands of the tables
+//   k_rw_rows<0>  (path,row) the row swept under both hypotheses about its first band: forcing bits, masks, record counts
+//   k_rw_resolve  path      composes the rows' f_in -> f_out maps; final band tables, record offsets
+//   k_rw_chain    slot      again, with the final tables
+//   k_rw_rows<1>  (path,row) the row swept with the exact x: emits the records, re-derives every table entry; a
+//                            mismatch flags the path (retried once from its new tables with the sort ranks; what still
+//                            fails is swept by the sequential k_walk)
+struct RwArgs {
+  FrameTables t;
+  const OpGeom* geom;
+  const uint32_t* row_base;
+  uint8_t* edges;
+  RwOp* ops;
+  const uint32_t* wgrp_op;   // owner of every group of 16 walk rows
+  uint32_t n_wgrps;
+  const uint32_t* slot_op;
+  uint32_t n_slots_total;
+  const uint32_t* chord_base;   // scanned chord capacities, n_slots_total + 1
+  SlotInfo* slots;
+  Chord* chords;
+  uint32_t* ev_words;
+  RowBand* tab;
+  uint32_t* res;
+  uint32_t* rec_off;
+  uint32_t* rec_cnt;            // per op, scanned into the ops' first records
+  uint16_t* rank;
+  int32_t* ord;
+  TrapRec* pool;
+  uint32_t pool_cap;
+  uint32_t* pool_next;
+  uint32_t* overflow;
+  uint2* rows;
+  uint32_t* n_failed;           // statistics: [0] retried, [1] swept sequentially
+};
+
+__device__ __forceinline__ bool rw_op_active(uint32_t fail, int phase) {
+  return phase == 0 ? fail == 0 : (fail & (SKB_RWFAIL_RETRY | SKB_RWFAIL_HARD)) == SKB_RWFAIL_RETRY;
+}
+__device__ __forceinline__ const Edge* rw_op_edges(const RwArgs& a, const OpGeom& g) {
+  return reinterpret_cast<const Edge*>(a.edges + (size_t)g.slot_base * (sizeof(Edge) + sizeof(QuadState)));
+}
+
+__global__ void __launch_bounds__(128) k_rw_events(RwArgs a) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n_slots_total) return;
+  const uint32_t cbase = a.chord_base[s];
+  const uint32_t cap = a.chord_base[s + 1] - cbase;
+  SlotInfo si;
+  si.chord_base = cbase;
+  si.n_chords = 0;
+  si.q_first = si.q_last = 0;
+  if (cap) {
+    const uint32_t op = a.slot_op[s];
+    const RwOp ro = a.ops[op];
+    if (ro.fail == 0 && ro.n_wrows > 0) {
+      const OpGeom g = a.geom[op];
+      const Edge* E = rw_op_edges(a, g);
+      const QuadState* Q = reinterpret_cast<const QuadState*>(E + g.n_slots);
+      const uint32_t local = s - g.slot_base;
+      const Edge e = E[local];
+      const bool quad = (e.curve >> 25) & 1;
+      const fx y0 = quad ? e.prev : e.upper_y, y1 = quad ? e.next : e.lower_y;
+      if (!can_be_ignored(g.scan_top_f, g.scan_bottom_f, y0, y1, (int)a.t.wide)) {
+        QuadState q;
+        if (quad) q = Q[local];
+        const int n = rw_chain(e, q, ro.origin_row, ro.n_wrows * 4, nullptr, a.chords + cbase, (int)cap, a.ev_words + (ro.wrow_base >> 2));
+        if (n <= 0) {
+          atomicOr(&a.ops[op].fail, SKB_RWFAIL_HARD);
+        } else {
+          si.n_chords = (uint32_t)n;
+          si.q_first = chord_uq(a.chords[cbase].yy);
+          si.q_last = chord_lq(a.chords[cbase + n - 1].yy);
+          atomicMin(&a.ops[op].y0q, si.q_first);
+        }
+      }
+    }
+  }
+  a.slots[s] = si;
+}
+
+// phase 1 (retry): also the sort ranks, and the op's fail bits move from "soft" to "being retried"
+__global__ void __launch_bounds__(128) k_rw_bands0(RwArgs a, int phase) {
+  const uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= a.t.n_ops) return;
+  RwOp ro = a.ops[op];
+  if (phase == 1) {
+    if ((ro.fail & SKB_RWFAIL_HARD) || !(ro.fail & SKB_RWFAIL_SOFT)) return;
+    a.ops[op].fail = SKB_RWFAIL_RETRY;
+    atomicAdd(&a.n_failed[0], 1u);
+    const OpGeom g = a.geom[op];
+    {  // row entries the first attempt's final pass wrote before one of its rows failed
+      uint2* r = a.rows + a.row_base[op];
+      for (int i = 0; i < g.nty * SKB_TILE; i++) r[i] = make_uint2(0u, 0u);
+    }
+    rw_sort_ranks(rw_op_edges(a, g), (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, (int)a.t.wide, a.rank + g.slot_base);
+  } else if (ro.fail) {
+    return;
+  }
+  if (ro.n_wrows <= 0 || ro.y0q == INT_MAX) return;
+  rw_bands_from_events(reinterpret_cast<const uint8_t*>(a.ev_words) + ro.wrow_base, ro.n_wrows, ro.y0q, a.tab + ro.wrow_base);
+}
+
+__global__ void __launch_bounds__(128) k_rw_chain(RwArgs a, int phase) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.n_slots_total) return;
+  const SlotInfo si = a.slots[s];
+  if (si.n_chords == 0) return;
+  const uint32_t op = a.slot_op[s];
+  const RwOp ro = a.ops[op];
+  if (!rw_op_active(ro.fail, phase)) return;
+  const OpGeom g = a.geom[op];
+  const Edge* E = rw_op_edges(a, g);
+  const QuadState* Q = reinterpret_cast<const QuadState*>(E + g.n_slots);
+  const uint32_t local = s - g.slot_base;
+  const Edge e = E[local];
+  if (!((e.curve >> 25) & 1)) {   // a line: its one chord is the edge itself
+    Chord c = a.chords[si.chord_base];
+    c.x = e.x; c.dx = e.dx; c.dy = e.dy;
+    a.chords[si.chord_base] = c;
+    return;
+  }
+  const QuadState q = Q[local];
+  const int cap = (int)(a.chord_base[s + 1] - si.chord_base);
+  const int n = rw_chain(e, q, ro.origin_row, ro.n_wrows * 4, a.tab + ro.wrow_base, a.chords + si.chord_base, cap, nullptr);
+  if (n != (int)si.n_chords) atomicOr(&a.ops[op].fail, SKB_RWFAIL_HARD);
+}
+
+__device__ __forceinline__ void rw_fill_row_in(const RwArgs& a, const RwOp& ro, const OpGeom& g, uint32_t op, int row, int phase, RwRowIn& in) {
+  in.rank = phase == 1 ? a.rank + g.slot_base : nullptr;
+  in.slots = a.slots + g.slot_base;
+  in.n_slots = (int)g.n_slots;
+  in.chords = a.chords;
+  in.tab = a.tab + ro.wrow_base;
+  in.ev = reinterpret_cast<const uint8_t*>(a.ev_words) + ro.wrow_base;
+  in.row = row;
+  in.y0q = ro.y0q;
+  in.stop_q = ro.n_wrows * 4;
+  in.origin_fx = i_to_fx(ro.origin_row);
+  in.left_clip = g.left_clip;
+  in.right_clip = g.right_clip;
+  in.even_odd = (int)a.t.ops[op].fill_type;
+  in.exact = false;
+}
+
+#ifndef RW_ROWS_BLOCK
+#define RW_ROWS_BLOCK 64
+#endif
+template <int FINAL>
+__global__ void __launch_bounds__(RW_ROWS_BLOCK) k_rw_rows(RwArgs a, int phase) {
+  const uint32_t wr = blockIdx.x * blockDim.x + threadIdx.x;   // global walk row
+  // chunked records (retries, sequential sweeps) follow the linear ones, on a chunk boundary
+  if (FINAL && phase == 0 && wr == 0) *a.pool_next = (a.rec_cnt[a.t.n_ops] + SKB_CHUNK - 1) & ~(SKB_CHUNK - 1);
+  if ((wr >> 4) >= a.n_wgrps) return;
+  const uint32_t op = a.wgrp_op[wr >> 4];
+  const RwOp ro = a.ops[op];
+  if (!rw_op_active(ro.fail, phase)) return;
+  const int row = (int)(wr - ro.wrow_base);
+  if (row >= ro.n_wrows || ro.y0q == INT_MAX) return;
+  const OpGeom g = a.geom[op];
+  RwRowIn in;
+  rw_fill_row_in(a, ro, g, op, row, phase, in);
+  // rows above the first tile row of the op's scan rectangle are swept (they shape the tables) but emit nothing
+  const int rel = ro.origin_row + row - g.ty0 * SKB_TILE;
+  const bool emits = rel >= 0 && rel < g.nty * SKB_TILE;
+  if (!FINAL) {
+    RwRowOut o0, o1;
+    rw_row(in, false, nullptr, 0, o0);
+    rw_row(in, true, nullptr, 0, o1);
+    if (o0.n_recs > 255) o0.fail = SKB_RWF_EMIT;
+    if (o1.n_recs > 255) o1.fail = SKB_RWF_EMIT;
+    a.res[wr] = rw_pack(o0.f_ins, o0.f_surv, o1.f_surv, o0.mask, o1.mask, o0.fail != 0, o1.fail != 0, emits ? o0.n_recs & 255 : 0,
+                        emits ? o1.n_recs & 255 : 0);
+  } else {
+    const RowBand tb = in.tab[row];
+    in.exact = true;
+    const uint32_t first = ro.rec_base + a.rec_off[wr];
+    const int n_alloc = (int)((row + 1 < ro.n_wrows ? a.rec_off[wr + 1] : ro.n_recs) - a.rec_off[wr]);
+    RwRowOut o;
+    const bool room = (uint64_t)first + (uint64_t)n_alloc <= (uint64_t)a.pool_cap;
+    if (!room) *a.overflow = 1;
+    rw_row(in, (tb.fl & SKB_RB_FIN) != 0, (emits && room) ? a.pool + first : nullptr, n_alloc, o);
+    const bool in_rows = row * 4 + 4 > ro.y0q;
+    bool bad = o.fail != 0;
+    if (in_rows && (o.mask != tb.mask || o.f_surv != ((tb.fl & SKB_RB_FSURV) != 0) || o.f_ins != ((tb.fl & SKB_RB_FINS) != 0))) bad = true;
+    if (emits && o.n_recs != n_alloc) bad = true;
+    if (bad) {
+      atomicOr(&a.ops[op].fail, phase == 0 ? SKB_RWFAIL_SOFT : SKB_RWFAIL_HARD);
+    } else if (emits && n_alloc > 0 && room) {
+      a.rows[a.row_base[op] + (uint32_t)rel] = make_uint2(first, (uint32_t)n_alloc | SKB_ROW_LINEAR);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_rw_resolve(RwArgs a, int phase) {
+  const uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= a.t.n_ops) return;
+  if (phase == 0) a.rec_cnt[op] = 0;
+  const RwOp ro = a.ops[op];
+  if (!rw_op_active(ro.fail, phase) || ro.n_wrows <= 0 || ro.y0q == INT_MAX) return;
+  const uint32_t total = rw_bands_resolve(a.res + ro.wrow_base, ro.n_wrows, ro.y0q, a.tab + ro.wrow_base, a.rec_off + ro.wrow_base);
+  if (total == 0xFFFFFFFFu) {
+    a.ops[op].fail = phase == 0 ? SKB_RWFAIL_SOFT : SKB_RWFAIL_HARD;
+    return;
+  }
+  a.ops[op].n_recs = total;
+  if (phase == 0) {
+    a.rec_cnt[op] = total;
+  } else {
+    const uint32_t base = atomicAdd(a.pool_next, (total + SKB_CHUNK - 1) & ~(SKB_CHUNK - 1));   // keeps the sequential sweep's chunks aligned
+    if ((uint64_t)base + total > (uint64_t)a.pool_cap) *a.overflow = 1;
+    a.ops[op].rec_base = base;
+  }
+}
+
+// after the scan of rec_cnt: the ops' first records
+__global__ void __launch_bounds__(128) k_rw_rec_base(RwArgs a) {
+  const uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= a.t.n_ops) return;
+  a.ops[op].rec_base = a.rec_cnt[op];
+}
+
+// The paths the row-parallel form gave up on: their row entries are cleared (the final pass may have written some
+// before another row of the path failed) and they are listed for the sequential sweep.
+__global__ void __launch_bounds__(128) k_rw_fallback_list(RwArgs a, uint32_t* count, uint32_t* list) {
+  const uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= a.t.n_ops) return;
+  const uint32_t fail = a.ops[op].fail;
+  if (!(fail & (SKB_RWFAIL_HARD | SKB_RWFAIL_SOFT))) return;
+  const OpGeom g = a.geom[op];
+  if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  uint2* r = a.rows + a.row_base[op];
+  for (int i = 0; i < g.nty * SKB_TILE; i++) r[i] = make_uint2(0u, 0u);
+  atomicAdd(&a.n_failed[1], 1u);
+  list[atomicAdd(count, 1u)] = op;
 }
 
 // ---------------------------------------------------------------- stage 4: coverage
@@ -434,6 +750,9 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
     const int y = ty * SKB_TILE + lane;
     if (lane < 16 && y >= g.scan_t && y < g.scan_b && y < (int)sd.h) row = c.rows[c.row_base[op] + tr * SKB_TILE + (uint32_t)lane];
   }
+  // rows written by the row-parallel walk hold their records one after the other (no chunk links)
+  const uint32_t lin_mask = __ballot_sync(0xffffffffu, (row.y & SKB_ROW_LINEAR) != 0);
+  row.y &= ~SKB_ROW_LINEAR;
   int pre = (int)row.y;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -482,13 +801,18 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
           rr_ += sm.r_pre[rr_ + 1] <= P ? 1 : 0;
           const uint32_t first = sm.r_first[rr_];
           // k-th record of the row: consecutive slots, the last slot of every chunk links to the next chunk
-          uint32_t pos = (first & (SKB_CHUNK - 1)) + (uint32_t)(P - sm.r_pre[rr_]);
-          uint32_t cb = first & ~(SKB_CHUNK - 1);
-          while (pos >= SKB_CHUNK - 1) {
-            cb = (uint32_t)c.pool[cb | (SKB_CHUNK - 1)].y;
-            pos -= SKB_CHUNK - 1;
+          uint32_t idx;
+          if ((lin_mask >> rr_) & 1u) {
+            idx = first + (uint32_t)(P - sm.r_pre[rr_]);
+          } else {
+            uint32_t pos = (first & (SKB_CHUNK - 1)) + (uint32_t)(P - sm.r_pre[rr_]);
+            uint32_t cb = first & ~(SKB_CHUNK - 1);
+            while (pos >= SKB_CHUNK - 1) {
+              cb = (uint32_t)c.pool[cb | (SKB_CHUNK - 1)].y;
+              pos -= SKB_CHUNK - 1;
+            }
+            idx = cb + pos;
           }
-          const uint32_t idx = cb + pos;
           const TrapPrep pr = trap_prepare(c.pool[idx]);
           int L = max(pr.L, cl), R = min(pr.mode ? pr.R : pr.L, cr);
           if (R > L) {
@@ -742,7 +1066,8 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   const SurfDesc sd = c.surfs[o.surface];
   const int y = g.ty0 * SKB_TILE + (int)(r - c.row_base[op]);
   if (y < g.scan_t || y >= g.scan_b || (mode == 1 && y >= (int)sd.h)) return;
-  const uint2 row = c.rows[r];
+  uint2 row = c.rows[r];
+  row.y &= ~SKB_ROW_LINEAR;   // consecutive records simply contain no chunk link
   if (row.y == 0) return;
 
   // parent clip state (C side)
@@ -918,6 +1243,7 @@ struct FineArgs {
   uint2* cmds_sorted;  // scratch for tiles whose list does not fit the shared-memory sorter
   uint32_t tile_begin, tile_end;
   uint32_t level;  // which surfaces this launch composites
+  uint32_t remote_store;  // the canvas band is stored into another GPU's canvas: empty tiles are stored as well
   const SurfDesc* surfs;
   const uint32_t* surf_tile_base;  // n_surfaces + 1
   uint32_t n_surfaces;
@@ -950,7 +1276,7 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   if (tile >= a.tile_end) return;
   const uint32_t c0 = a.tile_off[tile];
   const uint32_t n = a.tile_off[tile + 1] - c0;
-  if (n == 0) return;
+  if (n == 0 && !a.remote_store) return;
   const uint32_t s = find_interval(a.surf_tile_base, a.n_surfaces, tile);
   const SurfDesc sd = a.surfs[s];
   if (sd.level != a.level) return;
@@ -958,6 +1284,17 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   const int tx = (int)(local % sd.tiles_x), ty = (int)(local / sd.tiles_x);
   const int y = ty * SKB_TILE + (lane >> 1);
   const int x0 = tx * SKB_TILE + (lane & 1) * 8;
+  if (n == 0) {
+    // The band's pixels are stored into another GPU's canvas (sd.px_out != sd.px): tiles nothing was drawn into are
+    // stored too, so that the gathering canvas needs no clear of its own for the rows other devices own.
+    if (sd.px_out != sd.px) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(sd.px + (size_t)y * sd.pitch) + x0);
+      uint4* dstp = reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(sd.px_out + (size_t)y * sd.pitch) + x0);
+      dstp[0] = src[0];
+      dstp[1] = src[1];
+    }
+    return;
+  }
 
   // order the tile's commands by (op, plane): draws must be composited in draw order
   const uint2* list;
@@ -1492,6 +1829,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
+  Buf rw_chord_cnt, rw_slot_op, rw_slots, rw_rank, rw_ops, rw_wrow_cnt, rw_rec_cnt, rw_chords, rw_wgrp_op, rw_ev, rw_tab, rw_res, rw_rec_off;
   Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
@@ -1506,11 +1844,13 @@ __global__ void k_fetch_words(uint32_t* dst, const uint32_t* src, int n) {
   if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
 }
 
-__global__ void k_gather3(uint32_t* dst, const uint32_t* a, const uint32_t* b, const uint32_t* c) {
+__global__ void k_gather5(uint32_t* dst, const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, const uint32_t* e) {
   if (threadIdx.x == 0) {
     dst[0] = *a;
     dst[1] = *b;
     dst[2] = *c;
+    dst[3] = d ? *d : 0u;
+    dst[4] = e ? *e : 0u;
   }
 }
 
@@ -1775,7 +2115,7 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->prim_cnt, (size_t)(n_segs + 1) * 4));
   SKB_TRY(buf_reserve(s->row_cnt, (size_t)(n_ops + 1) * 4));
   SKB_TRY(buf_reserve(s->item_cnt, (size_t)(n_ops + 1) * 4));
-  SKB_TRY(buf_reserve(s->counters, 64));
+  SKB_TRY(buf_reserve(s->counters, 128));
   OpGeom* geom = (OpGeom*)s->geom.p;
   uint32_t* seg_op = (uint32_t*)s->seg_op.p;
   uint32_t* prim_off = (uint32_t*)s->prim_cnt.p;
@@ -1785,12 +2125,13 @@ static skb_result run_frame(skb_surface s) {
 
   cudaEventRecord(s->ev[0], st);
   // ---- stage 1: flatten
-  k_op_init<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, seg_op);
+  SKB_CUDA(cudaMemsetAsync(seg_op, 0, (size_t)(n_segs + 1) * 4, st));  // segments no op refers to count as op 0's (validate_dl rejects such lists)
+  k_op_init<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, seg_op, (const SurfDesc*)s->surfs.p);
   launches++;
   uint32_t n_prims = 0;
   if (n_segs) {
     SKB_CUDA(cudaMemsetAsync(prim_off + n_segs, 0, 4, st));
-    k_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(t, prim_off);
+    k_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(t, prim_off, seg_op, geom);
     launches++;
     SKB_TRY(scan_exclusive(s, prim_off, n_segs + 1, &launches));
     SKB_TRY(fetch_words(s, &n_prims, prim_off + n_segs, 1));
@@ -1803,12 +2144,29 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->walk_lists, (size_t)n_ops * 4 + 16));
   SKB_TRY(buf_reserve(s->ord, n_slots * 4));
   Edge* edges = (Edge*)s->edges.p;
+  // stage 3 in its row-parallel form (skb_rowwalk.cuh) unless SKB_WALK_MODE=0 asks for the sequential sweep alone
+  const bool rowwalk = !(getenv("SKB_WALK_MODE") && atoi(getenv("SKB_WALK_MODE")) == 0);
+  uint32_t* chord_base = nullptr;
+  uint32_t* wrow_base = nullptr;
+  if (rowwalk) {
+    SKB_TRY(buf_reserve(s->rw_chord_cnt, (n_slots + 1) * 4));
+    SKB_TRY(buf_reserve(s->rw_slot_op, n_slots * 4));
+    SKB_TRY(buf_reserve(s->rw_slots, n_slots * sizeof(SlotInfo)));
+    SKB_TRY(buf_reserve(s->rw_rank, n_slots * 2));
+    SKB_TRY(buf_reserve(s->rw_ops, (size_t)n_ops * sizeof(RwOp)));
+    SKB_TRY(buf_reserve(s->rw_wrow_cnt, (size_t)(n_ops + 1) * 4));
+    SKB_TRY(buf_reserve(s->rw_rec_cnt, (size_t)(n_ops + 1) * 4));
+    chord_base = (uint32_t*)s->rw_chord_cnt.p;
+    wrow_base = (uint32_t*)s->rw_wrow_cnt.p;
+  }
 
-  uint64_t n_rows = 0, n_items = 0;
+  uint64_t n_rows = 0, n_items = 0, n_wrows = 0, n_chords = 0;
   uint32_t pool_cap = 0;
   for (int attempt = 0;; attempt++) {
     if (n_prims) {
-      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, nullptr);
+      if (rowwalk && attempt == 0) SKB_CUDA(cudaMemsetAsync(chord_base, 0, (n_slots + 1) * 4, st));
+      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, nullptr, (rowwalk && attempt == 0) ? chord_base : nullptr,
+                                                    (uint32_t*)s->rw_slot_op.p);
       launches++;
     }
     if (attempt == 0) {
@@ -1817,13 +2175,20 @@ static skb_result run_frame(skb_surface s) {
       SKB_CUDA(cudaMemsetAsync(row_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(item_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(counters + 6, 0, 4, st));
-      k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base, counters + 6);
+      if (rowwalk) SKB_CUDA(cudaMemsetAsync(wrow_base + n_ops, 0, 4, st));
+      k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base, counters + 6,
+                                                   rowwalk ? (RwOp*)s->rw_ops.p : nullptr, wrow_base);
       launches++;
       SKB_TRY(scan_exclusive(s, row_base, n_ops + 1, &launches));
       SKB_TRY(scan_exclusive(s, item_base, n_ops + 1, &launches));
-      uint32_t tot[3] = {0, 0, 0};  // one round trip for the three words
-      k_gather3<<<1, 32, 0, st>>>(counters + 8, row_base + n_ops, item_base + n_ops, counters + 6);
-      SKB_TRY(fetch_words(s, tot, counters + 8, 3));
+      if (rowwalk) {
+        SKB_TRY(scan_exclusive(s, wrow_base, n_ops + 1, &launches));
+        SKB_TRY(scan_exclusive(s, chord_base, (uint32_t)n_slots + 1, &launches));
+      }
+      uint32_t tot[5] = {0, 0, 0, 0, 0};  // one round trip for all the totals
+      k_gather5<<<1, 32, 0, st>>>(counters + 8, row_base + n_ops, item_base + n_ops, counters + 6, rowwalk ? wrow_base + n_ops : nullptr,
+                                  rowwalk ? chord_base + n_slots : nullptr);
+      SKB_TRY(fetch_words(s, tot, counters + 8, 5));
       const uint32_t too_big = tot[2];
       launches += 2;
       if (too_big) {
@@ -1832,10 +2197,13 @@ static skb_result run_frame(skb_surface s) {
       }
       n_rows = tot[0];
       n_items = tot[1];
+      n_wrows = tot[3];
+      n_chords = tot[4];
       S.n_rows = n_rows;
       S.n_items = n_items;
       s->n_items = (uint32_t)n_items;
       uint64_t want = 2 * n_rows + (uint64_t)SKB_CHUNK * 2 * n_ops + 4096;
+      if (rowwalk) want = 2 * n_rows + n_rows / 4 + 65536;   // linear records; chunks only for the few paths swept sequentially
       if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
       pool_cap = (uint32_t)want;
       SKB_TRY(buf_reserve(s->rows, (n_rows + 1) * sizeof(uint2)));
@@ -1845,6 +2213,14 @@ static skb_result run_frame(skb_surface s) {
       SKB_TRY(buf_reserve(s->item_flags, 2 * n_items + 16));
       SKB_TRY(buf_reserve(s->tile_cnt, (size_t)(n_tiles + 1) * 4));
       SKB_TRY(buf_reserve(s->tile_fill, (size_t)(n_tiles + 1) * 4));
+      if (rowwalk) {
+        SKB_TRY(buf_reserve(s->rw_chords, (n_chords + 1) * sizeof(Chord)));
+        SKB_TRY(buf_reserve(s->rw_wgrp_op, (n_wrows / 16 + 1) * 4));
+        SKB_TRY(buf_reserve(s->rw_ev, n_wrows + 64));
+        SKB_TRY(buf_reserve(s->rw_tab, (n_wrows + 1) * sizeof(RowBand)));
+        SKB_TRY(buf_reserve(s->rw_res, (n_wrows + 1) * 4));
+        SKB_TRY(buf_reserve(s->rw_rec_off, (n_wrows + 2) * 4));
+      }
       cudaEventRecord(s->ev[2], st);
     }
     SKB_TRY(buf_reserve(s->pool, (size_t)pool_cap * sizeof(TrapRec)));
@@ -1853,38 +2229,96 @@ static skb_result run_frame(skb_surface s) {
     // ---- stage 3: walk
     SKB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
     if (n_rows) SKB_CUDA(cudaMemsetAsync(s->rows.p, 0, n_rows * sizeof(uint2), st));
-    {
-      // counters: [0] pool_next, [1] overflow, [4] number of ops to sweep
-      k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p, row_base,
-                                                    (uint32_t*)s->trow_op.p);
-      launches++;
-      WalkArgs wa;
-      wa.t = t;
-      wa.geom = geom;
-      wa.row_base = row_base;
-      wa.edges = edges;
-      wa.quads = nullptr;
-      wa.ord = (int32_t*)s->ord.p;
-      wa.pool = (TrapRec*)s->pool.p;
-      wa.pool_next = counters;
-      wa.pool_cap = pool_cap;
-      wa.overflow = counters + 1;
-      wa.rows = (uint2*)s->rows.p;
-      wa.list = (const uint32_t*)s->walk_lists.p;
-      wa.count = counters + 4;
-      // spread paths over warps while the GPU has spare thread slots (about 32 warps per SM wanted;
-      // measured on C1: stride 1 5.2 ms, 4 2.6 ms, 8 2.0 ms, 32 2.6 ms)
-      int lane_stride = 1;
-      const uint64_t want_threads = (uint64_t)s->dev->sm_count * 32 * 32;
-      while (lane_stride < 8 && (uint64_t)n_ops * lane_stride * 2 <= want_threads) lane_stride *= 2;
-      if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
-      k_walk<<<cdiv((uint64_t)n_ops * lane_stride, WALK_BLOCK), WALK_BLOCK, 0, st>>>(wa, lane_stride);
+    WalkArgs wa;
+    wa.t = t;
+    wa.geom = geom;
+    wa.row_base = row_base;
+    wa.edges = edges;
+    wa.quads = nullptr;
+    wa.ord = (int32_t*)s->ord.p;
+    wa.pool = (TrapRec*)s->pool.p;
+    wa.pool_next = counters;
+    wa.pool_cap = pool_cap;
+    wa.overflow = counters + 1;
+    wa.rows = (uint2*)s->rows.p;
+    wa.list = (const uint32_t*)s->walk_lists.p;
+    wa.count = counters + 4;
+    // counters: [0] pool_next, [1] overflow, [4] number of ops to sweep sequentially, [10] retried, [11] swept sequentially
+    k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p, row_base, (uint32_t*)s->trow_op.p,
+                                                  (rowwalk && attempt == 0) ? (RwOp*)s->rw_ops.p : nullptr, wrow_base, (uint32_t*)s->rw_wgrp_op.p);
+    launches++;
+    uint32_t n_seq = n_ops;   // upper bound of the paths the sequential sweep gets
+    if (rowwalk && n_wrows && attempt == 0) {
+      RwArgs ra;
+      ra.t = t;
+      ra.geom = geom;
+      ra.row_base = row_base;
+      ra.edges = (uint8_t*)edges;
+      ra.ops = (RwOp*)s->rw_ops.p;
+      ra.wgrp_op = (const uint32_t*)s->rw_wgrp_op.p;
+      ra.n_wgrps = (uint32_t)(n_wrows / 16);
+      ra.slot_op = (const uint32_t*)s->rw_slot_op.p;
+      ra.n_slots_total = (uint32_t)n_slots;
+      ra.chord_base = chord_base;
+      ra.slots = (SlotInfo*)s->rw_slots.p;
+      ra.chords = (Chord*)s->rw_chords.p;
+      ra.ev_words = (uint32_t*)s->rw_ev.p;
+      ra.tab = (RowBand*)s->rw_tab.p;
+      ra.res = (uint32_t*)s->rw_res.p;
+      ra.rec_off = (uint32_t*)s->rw_rec_off.p;
+      ra.rec_cnt = (uint32_t*)s->rw_rec_cnt.p;
+      ra.rank = (uint16_t*)s->rw_rank.p;
+      ra.ord = (int32_t*)s->ord.p;
+      ra.pool = (TrapRec*)s->pool.p;
+      ra.pool_cap = pool_cap;
+      ra.pool_next = counters;
+      ra.overflow = counters + 1;
+      ra.rows = (uint2*)s->rows.p;
+      ra.n_failed = counters + 10;
+      const uint32_t g_slots = cdiv(n_slots, 128), g_ops = cdiv(n_ops, 128), g_rows = cdiv(n_wrows, RW_ROWS_BLOCK);
+      SKB_CUDA(cudaMemsetAsync(s->rw_ev.p, 0, n_wrows + 64, st));
+      k_rw_events<<<g_slots, 128, 0, st>>>(ra);
+      k_rw_bands0<<<g_ops, 128, 0, st>>>(ra, 0);
+      launches += 2;
+      for (int phase = 0; phase < 2; phase++) {
+        if (phase == 1) {
+          k_rw_bands0<<<g_ops, 128, 0, st>>>(ra, 1);
+          launches++;
+        }
+        k_rw_chain<<<g_slots, 128, 0, st>>>(ra, phase);
+        k_rw_rows<0><<<g_rows, RW_ROWS_BLOCK, 0, st>>>(ra, phase);
+        k_rw_resolve<<<g_ops, 128, 0, st>>>(ra, phase);
+        launches += 3;
+        if (phase == 0) {
+          SKB_CUDA(cudaMemsetAsync(ra.rec_cnt + n_ops, 0, 4, st));
+          SKB_TRY(scan_exclusive(s, ra.rec_cnt, n_ops + 1, &launches));
+          k_rw_rec_base<<<g_ops, 128, 0, st>>>(ra);
+          launches++;
+        }
+        k_rw_chain<<<g_slots, 128, 0, st>>>(ra, phase);
+        k_rw_rows<1><<<g_rows, RW_ROWS_BLOCK, 0, st>>>(ra, phase);
+        launches += 2;
+      }
+      k_rw_fallback_list<<<g_ops, 128, 0, st>>>(ra, counters + 4, (uint32_t*)s->walk_lists.p);
       launches++;
     }
-    uint32_t hc[2];
-    SKB_TRY(fetch_words(s, hc, counters, 2));
+    {
+      // the sequential sweep: every path (SKB_WALK_MODE=0, or a re-run after a pool overflow), else only those listed.
+      // Paths are spread over warps while the GPU has spare thread slots (about 32 warps per SM wanted; measured on C1:
+      // stride 1 5.2 ms, 4 2.6 ms, 8 2.0 ms, 32 2.6 ms)
+      int lane_stride = 1;
+      const uint64_t want_threads = (uint64_t)s->dev->sm_count * 32 * 32;
+      while (lane_stride < 8 && (uint64_t)n_seq * lane_stride * 2 <= want_threads) lane_stride *= 2;
+      if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
+      k_walk<<<cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK), WALK_BLOCK, 0, st>>>(wa, lane_stride);
+      launches++;
+    }
+    uint32_t hc[12];
+    SKB_TRY(fetch_words(s, hc, counters, 12));
     launches++;
     S.n_records = hc[0];
+    S.n_rw_retried = hc[10];
+    S.n_rw_sequential = hc[11];
     if (!hc[1]) break;
     if (attempt >= 6 || pool_cap >= 0x7FFFFFF0u) {
       set_error("trapezoid record pool exhausted");
@@ -1893,7 +2327,7 @@ static skb_result run_frame(skb_surface s) {
     S.n_retries++;
     uint64_t bigger = (uint64_t)pool_cap * 2;
     pool_cap = bigger > 0x7FFFFFF0ull ? 0x7FFFFFF0u : (uint32_t)bigger;
-    // the sweep mutates the edges: rebuild them and walk again
+    // the sweep mutates the edges: rebuild them and walk again (the re-run is the sequential sweep of every path)
   }
   cudaEventRecord(s->ev[3], st);
 
@@ -2039,6 +2473,7 @@ static skb_result run_frame(skb_surface s) {
   fa.surfs = (const SurfDesc*)s->surfs.p;
   fa.surf_tile_base = (const uint32_t*)s->surf_tile_base.p;
   fa.n_surfaces = h.n_surfaces;
+  fa.remote_store = s->remote_canvas ? 1u : 0u;
   fa.geom = geom;
   fa.ops = t.ops;
   fa.paints = t.paints;
@@ -2202,6 +2637,12 @@ static skb_result run_frame(skb_surface s) {
   S.bytes_fine = band_px * 8 + (uint64_t)n_cmds * (8 + 256);
   S.bytes_cover = S.n_records * 32 + (uint64_t)n_cmds * 256;
   S.bytes_walk = (uint64_t)S.n_edges_slots * (sizeof(Edge) + sizeof(QuadState)) + S.n_records * 32 + S.n_rows * 8;
+  if (rowwalk) S.bytes_walk += n_chords * sizeof(Chord) * 2 + n_wrows * (sizeof(RowBand) + 8);  // chords written once and read by the rows; band table, row results
+  S.bytes_blur = 0;
+  for (uint32_t i = 0; i < nj; i++) {
+    const int r = jobs[i].radius > 254 ? 254 : jobs[i].radius;
+    if (jobs[i].style < 6 && r > 1) S.bytes_blur += (uint64_t)surfs[jobs[i].dst].w * surfs[jobs[i].dst].h * 16;
+  }
   s->flushed = true;
   return SKB_SUCCESS;
 }
@@ -2279,7 +2720,7 @@ void skb_surface_destroy(skb_surface s) {
   if (!s) return;
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  Buf* bufs[] = {&s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
+  Buf* bufs[] = {&s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
@@ -2295,13 +2736,18 @@ void skb_surface_destroy(skb_surface s) {
   delete s;
 }
 
+// x + w <= surface width and y + h <= surface height, without the uint32 wrap of the sums
+static bool rect_inside(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h) {
+  return x <= s->w && w <= s->w - x && y <= s->h && h <= s->h - y;
+}
+
 skb_result skb_surface_set_band(skb_surface s, uint32_t y0, uint32_t y1) {
   if (!s) return SKB_ERROR_INVALID_ARGUMENT;
   if (y1 == 0) {
     s->band_y0 = s->band_y1 = 0;
     return SKB_SUCCESS;
   }
-  if (y0 >= y1 || y0 % SKB_TILE != 0 || (y1 % SKB_TILE != 0 && y1 < s->h)) {
+  if (y0 >= y1 || y0 >= s->h || y0 % SKB_TILE != 0 || (y1 % SKB_TILE != 0 && y1 < s->h)) {
     set_error("band rows must be multiples of 16");
     return SKB_ERROR_INVALID_ARGUMENT;
   }
@@ -2319,7 +2765,21 @@ skb_result skb_surface_set_coord_mode(skb_surface s, int mode) {
 skb_result skb_frame_begin(skb_surface s, int clear) {
   if (!s) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
-  if (clear) SKB_CUDA(cudaMemsetAsync(s->canvas, 0, (size_t)s->pitch * s->tiles_y * SKB_TILE, s->stream));
+  if (!clear && s->remote_canvas) {
+    set_error("a band whose pixels are stored into another GPU's canvas starts from a cleared band: skb_frame_begin(clear = 0) "
+              "would blend onto this device's copy, not onto the gathering canvas");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+  if (clear) {
+    // with a band set only the band's rows are this device's business: the rows of a gathering canvas that other
+    // devices store into (skb_surface_set_remote_canvas on their side) must not be cleared under their feet
+    size_t r0 = 0, r1 = (size_t)s->tiles_y * SKB_TILE;
+    if (s->band_y1 > 0) {
+      r0 = s->band_y0;
+      r1 = ((size_t)(s->band_y1 < s->h ? s->band_y1 : s->h) + SKB_TILE - 1) / SKB_TILE * SKB_TILE;
+    }
+    SKB_CUDA(cudaMemsetAsync(s->canvas + r0 * s->pitch, 0, (r1 - r0) * s->pitch, s->stream));
+  }
   // the last encoded display list stays resident: a frame may be flushed again without re-uploading it
   s->flushed = false;
   return SKB_SUCCESS;
@@ -2394,7 +2854,7 @@ skb_result skb_surface_sync(skb_surface s) {
 }
 
 skb_result skb_surface_read_pixels(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst, size_t stride) {
-  if (!s || !dst || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  if (!s || !dst || !rect_inside(s, x, y, w, h) || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
                              cudaMemcpyDeviceToHost, s->stream));
@@ -2404,7 +2864,7 @@ skb_result skb_surface_read_pixels(skb_surface s, uint32_t x, uint32_t y, uint32
 
 skb_result skb_surface_read_pixels_async(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst,
                                          size_t stride) {
-  if (!s || !dst || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  if (!s || !dst || !rect_inside(s, x, y, w, h) || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
                              cudaMemcpyDeviceToHost, s->stream));
@@ -2440,7 +2900,7 @@ skb_result skb_surface_set_remote_canvas(skb_surface s, const void* handle64) {
 
 skb_result skb_surface_write_pixels(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, const void* src,
                                     size_t stride) {
-  if (!s || !src || x + w > s->w || y + h > s->h || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
+  if (!s || !src || !rect_inside(s, x, y, w, h) || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
   SKB_CUDA(cudaMemcpy2DAsync(s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, src, stride, (size_t)w * 4, h,
                              cudaMemcpyHostToDevice, s->stream));

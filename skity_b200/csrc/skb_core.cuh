@@ -510,6 +510,13 @@ SKB_HD uint8_t alpha_above_at(int j, fx l, fx r, fx dY, uint32_t full) {
   return (uint8_t)(a16 >> 8);
 }
 
+// approximate_intersection's mean (sw_raster.cc:253-262): `(max(l1,l2) + min(r1,r2)) / 2`.  The reference adds in int32; the sum
+// stays below 2^31 for every coordinate the reference can represent without wrapping (|x| < 8192 px -> |sum| < 2^30), so
+// the 64-bit sum used here is identical to it there.  In the wide-coordinate mode two x at the right clip of a 16384-px
+// canvas add up to exactly 2^31: the int32 sum would flip sign and turn the band into a 32768-pixel trapezoid (and in
+// the reference's SpanBuilder into a write before its row buffer).
+SKB_HD fx mean_no_overflow(fx a, fx b) { return (fx)(((int64_t)a + (int64_t)b) / 2); }
+
 // blit_aaa_trapezoid_row at pixel x (sw_raster.cc:370-455). `accum` = the row goes through the
 // accumulating SpanBuilder (partial-height band or "too close"), which scales single alphas.
 // `side` (a compile-time constant at every call): 0 = both slanted sides; 1 / 2 = only the left / right one, for the
@@ -582,7 +589,7 @@ SKB_HDN bool trap_alpha_at(const TrapRec& r, int x, uint8_t* out) {
     fx l1 = ul, r1 = ll, l2 = ur, r2 = lr;
     if (l1 > r1) { fx t = l1; l1 = r1; r1 = t; }
     if (l2 > r2) { fx t = l2; l2 = r2; r2 = t; }
-    ll = lr = fx_add(fx_max(l1, l2), fx_min(r1, r2)) / 2;
+    ll = lr = mean_no_overflow(fx_max(l1, l2), fx_min(r1, r2));
   }
   if (ul == ur && ll == lr) return false;
   if (ul > ll) { fx t = ul; ul = ll; ll = t; }
@@ -675,7 +682,7 @@ SKB_HDN TrapPrep trap_prepare(const TrapRec& r) {
     fx l1 = ul, r1 = ll, l2 = ur, r2 = lr;
     if (l1 > r1) { fx t = l1; l1 = r1; r1 = t; }
     if (l2 > r2) { fx t = l2; l2 = r2; r2 = t; }
-    ll = lr = fx_add(fx_max(l1, l2), fx_min(r1, r2)) / 2;
+    ll = lr = mean_no_overflow(fx_max(l1, l2), fx_min(r1, r2));
   }
   if (ul == ur && ll == lr) return p;
   if (ul > ll) { fx t = ul; ul = ll; ll = t; }

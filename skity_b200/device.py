@@ -20,7 +20,8 @@ class FrameStats(ctypes.Structure):
                 ("pool_capacity", ctypes.c_uint64),
                 ("n_launches", ctypes.c_uint32), ("n_retries", ctypes.c_uint32),
                 ("ms_total", ctypes.c_float), ("ms_stage", ctypes.c_float * 8),
-                ("bytes_fine", ctypes.c_uint64), ("bytes_cover", ctypes.c_uint64), ("bytes_walk", ctypes.c_uint64)]
+                ("bytes_fine", ctypes.c_uint64), ("bytes_cover", ctypes.c_uint64), ("bytes_walk", ctypes.c_uint64),
+                ("bytes_blur", ctypes.c_uint64), ("n_rw_retried", ctypes.c_uint32), ("n_rw_sequential", ctypes.c_uint32)]
 
     def as_dict(self):
         d = {}

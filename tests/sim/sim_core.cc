@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
 #include <vector>
 
 #include "skity_b200/csrc/skb_stages.cuh"
@@ -19,6 +20,9 @@ static int sim_walk_mode() {
   return m ? atoi(m) : 1;
 }
 
+
+static int g_sim_wide = 0;  // wide-coordinate mode (include/skb.h SKB_COORD_WIDE)
+extern "C" void sim_set_wide(int w) { g_sim_wide = w; }
 
 extern "C" {
 
@@ -54,7 +58,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
       V2 p[3];
       int np = seg_prim(segs, i, k, n, ctm, p);
       for (int j = 0; j < np; j++) bound(p[j]);
-      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)]);
+      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)], g_sim_wide);
     }
   }
   op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
@@ -81,7 +85,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
     sink.n_rows = n_rows;
     sink_init(sink);
     walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
-              g.right_clip, even_odd, sink, sim_walk_mode());
+              g.right_clip, even_odd, sink, sim_walk_mode(), g_sim_wide);
     if (!overflow) break;
     pool.resize(pool.size() * 4);
     pool_next = 0;
@@ -149,7 +153,7 @@ void sim_raster_op(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, co
       V2 p[3];
       int np = seg_prim(segs, i, k, n, ctm, p);
       for (int j = 0; j < np; j++) bound(p[j]);
-      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)]);
+      flatten_prim(np, p, &E[2 + 2 * (size_t)(prim_off[i] + k)], &Q[2 + 2 * (size_t)(prim_off[i] + k)], g_sim_wide);
     }
   }
   op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
@@ -173,7 +177,7 @@ void sim_raster_op(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, co
     sink.n_rows = n_rows;
     sink_init(sink);
     walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y,
-              g.left_clip, g.right_clip, even_odd, sink, sim_walk_mode());
+              g.left_clip, g.right_clip, even_odd, sink, sim_walk_mode(), g_sim_wide);
     if (!overflow) break;
     out.pool.resize(out.pool.size() * 4);
     pool_next = 0;
@@ -335,4 +339,250 @@ extern "C" long sim_atan2f_mismatches(long n, unsigned long long seed) {
     if (memcmp(&r, &m, 4) != 0) bad++;
   }
   return bad;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-parallel walk (skb_rowwalk.cuh) against the sequential sweep (skb_walk.cuh), record by record.
+#include "skity_b200/csrc/skb_rowwalk.cuh"
+
+namespace {
+struct RwSimPath {
+  OpGeom g;
+  std::vector<Edge> E;
+  std::vector<QuadState> Q;
+  bool ok = false;
+};
+
+void rw_sim_flatten(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, const float* clip, int surf_w, int surf_h, RwSimPath& out) {
+  std::vector<uint32_t> prim_off(n_segs + 1, 0);
+  for (uint32_t i = 0; i < n_segs; i++) prim_off[i + 1] = prim_off[i] + (uint32_t)seg_prim_count(segs[i]);
+  uint32_t n_prims = prim_off[n_segs];
+  OpGeom& g = out.g;
+  std::memset(&g, 0, sizeof(g));
+  g.bmin_x = g.bmin_y = INT_MAX;
+  g.bmax_x = g.bmax_y = INT_MIN;
+  bool have = false;
+  auto bound = [&](V2 p) {
+    have = true;
+    int32_t kx = float_key(p.x), ky = float_key(p.y);
+    if (kx < g.bmin_x) g.bmin_x = kx;
+    if (kx > g.bmax_x) g.bmax_x = kx;
+    if (ky < g.bmin_y) g.bmin_y = ky;
+    if (ky > g.bmax_y) g.bmax_y = ky;
+  };
+  out.E.assign(2 + 2 * (size_t)n_prims, Edge());
+  out.Q.assign(out.E.size(), QuadState());
+  std::memset(out.E.data(), 0, out.E.size() * sizeof(Edge));
+  std::memset(out.Q.data(), 0, out.Q.size() * sizeof(QuadState));
+  for (uint32_t i = 0; i < n_segs; i++) {
+    if ((segs[i].type_flags & SKB_SEG_TYPE_MASK) == SKB_SEG_POINT) bound(xform(ctm, seg_start_point(segs, i)));
+    int n = (int)(prim_off[i + 1] - prim_off[i]);
+    for (int k = 0; k < n; k++) {
+      V2 p[3];
+      int np = seg_prim(segs, i, k, n, ctm, p);
+      for (int j = 0; j < np; j++) bound(p[j]);
+      flatten_prim(np, p, &out.E[2 + 2 * (size_t)(prim_off[i] + k)], &out.Q[2 + 2 * (size_t)(prim_off[i] + k)], g_sim_wide);
+    }
+  }
+  op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
+  out.ok = !g.empty;
+}
+}  // namespace
+
+// Returns 0: the row-parallel form produced exactly the sequential sweep's records; 1: it flagged the path for the
+// sequential fallback; 2: MISMATCH (a bug); 3: path empty.  stats[0] = records, [1] = walk rows, [2] = chords, [3] = fail stage.
+extern "C" int sim_rowwalk_check(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, const float* clip, int even_odd,
+                                 int surf_w, int surf_h, int64_t* stats) {
+  RwSimPath P;
+  rw_sim_flatten(segs, n_segs, ctm, clip, surf_w, surf_h, P);
+  stats[0] = stats[1] = stats[2] = stats[3] = 0;
+  if (!P.ok) return 3;
+  const OpGeom& g = P.g;
+  // ---- sequential sweep (reference for this check)
+  const int n_rows = g.scan_b - g.scan_t;
+  std::vector<uint2> rows((size_t)n_rows, uint2{0, 0});
+  std::vector<TrapRec> pool((size_t)1 << 16);
+  {
+    uint32_t pool_next = 0, overflow = 0;
+    std::vector<int32_t> ord(P.E.size());
+    for (;;) {
+      std::vector<Edge> Ew = P.E;
+      std::vector<QuadState> Qw = P.Q;
+      RecSink sink;
+      sink.pool = pool.data();
+      sink.pool_next = &pool_next;
+      sink.pool_cap = (uint32_t)pool.size();
+      sink.overflow = &overflow;
+      sink.rows = rows.data();
+      sink.row0 = g.scan_t;
+      sink.n_rows = n_rows;
+      sink_init(sink);
+      walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
+                g.right_clip, even_odd, sink, 1, g_sim_wide);
+      if (!overflow) break;
+      pool.resize(pool.size() * 4);
+      pool_next = 0;
+      overflow = 0;
+      std::fill(rows.begin(), rows.end(), uint2{0, 0});
+    }
+  }
+  // ---- row-parallel form, kernel by kernel
+  const int n_slots = (int)P.E.size();
+  const int origin = g.start_y;
+  const int n_wrows = g.stop_y - g.start_y;
+  if (n_wrows <= 0 || n_wrows * 4 > SKB_RW_MAXQ) { stats[3] = 1; return 1; }
+  const int stop_q = n_wrows * 4;
+  stats[1] = n_wrows;
+  std::vector<SlotInfo> slots((size_t)n_slots);
+  std::vector<uint32_t> cap((size_t)n_slots, 0), base((size_t)n_slots + 1, 0);
+  for (int s = 2; s < n_slots; s++) {
+    const Edge& e = P.E[s];
+    if (!((e.curve >> 24) & 1)) continue;
+    const bool quad = (e.curve >> 25) & 1;
+    cap[s] = quad ? 1u + (uint32_t)edge_count(e) : 1u;
+  }
+  for (int s = 0; s < n_slots; s++) base[s + 1] = base[s] + cap[s];
+  std::vector<Chord> chords(base[n_slots] + 1);
+  std::vector<uint32_t> ev_words((size_t)(n_wrows + 4) / 4 + 1, 0u);
+  int y0q = INT_MAX;
+  // K2: chord y's and events
+  for (int s = 0; s < n_slots; s++) {
+    slots[s] = SlotInfo{base[s], 0u, 0, 0};
+    if (!cap[s]) continue;
+    const Edge& e = P.E[s];
+    const bool quad = (e.curve >> 25) & 1;
+    const fx y0 = quad ? e.prev : e.upper_y, y1 = quad ? e.next : e.lower_y;
+    if (can_be_ignored(g.scan_top_f, g.scan_bottom_f, y0, y1, g_sim_wide)) continue;
+    const int n = rw_chain(e, P.Q[s], origin, stop_q, nullptr, &chords[base[s]], (int)cap[s], ev_words.data());
+    if (n <= 0) { stats[3] = 2; return 1; }
+    slots[s].n_chords = (uint32_t)n;
+    slots[s].q_first = chord_uq(chords[base[s]].yy);
+    slots[s].q_last = chord_lq(chords[base[s] + n - 1].yy);
+    if (slots[s].q_first < y0q) y0q = slots[s].q_first;
+    stats[2] += n;
+  }
+  if (y0q == INT_MAX) {  // every edge culled: the sweep has nothing to do (walk_prologue returns false)
+    for (int r = 0; r < n_rows; r++)
+      if (rows[(size_t)r].y) return 2;
+    return 0;
+  }
+  const uint8_t* ev = reinterpret_cast<const uint8_t*>(ev_words.data());
+  std::vector<RowBand> tab((size_t)n_wrows + 1);
+  std::vector<uint32_t> res((size_t)n_wrows, 0u), rec_off((size_t)n_wrows, 0u);
+  rw_bands_from_events(ev, n_wrows, y0q, tab.data());
+  RwRowIn in;
+  in.slots = slots.data();
+  in.n_slots = n_slots;
+  in.chords = chords.data();
+  in.tab = tab.data();
+  in.ev = ev;
+  in.y0q = y0q;
+  in.stop_q = stop_q;
+  in.origin_fx = i_to_fx(origin);
+  in.left_clip = g.left_clip;
+  in.right_clip = g.right_clip;
+  in.even_odd = even_odd;
+  in.rank = nullptr;
+  uint32_t total = 0;
+  std::vector<TrapRec> recs;
+  std::vector<uint16_t> rank((size_t)n_slots, 0);
+  std::vector<int32_t> ord2((size_t)n_slots, 0);
+  int max_rounds = getenv("SKB_SIM_RW_ROUNDS") ? atoi(getenv("SKB_SIM_RW_ROUNDS")) : 3;
+  int round = 0;
+  int why = 0;
+  for (;; round++) {
+    if (round >= max_rounds) { stats[3] = why; return 1; }
+    if (round == 1) {  // retry: with the sort ranks, and from the tables of the first attempt
+      rw_sort_ranks(P.E.data(), n_slots, ord2.data(), g.scan_top_f, g.scan_bottom_f, g_sim_wide, rank.data());
+      in.rank = rank.data();
+    }
+    why = 0;
+    // K4: chain with the current tables
+    for (int s = 0; s < n_slots && !why; s++) {
+      if (!slots[s].n_chords) continue;
+      const int n = rw_chain(P.E[s], P.Q[s], origin, stop_q, tab.data(), &chords[base[s]], (int)cap[s], nullptr);
+      if (n != (int)slots[s].n_chords) why = 4;
+    }
+    if (why) { stats[3] = why; return 1; }   // structural: retrying does not help
+    // K5: both hypotheses per row
+    in.exact = false;
+    for (int r = 0; r < n_wrows; r++) {
+      in.row = r;
+      RwRowOut o0, o1;
+      rw_row(in, false, nullptr, 0, o0);
+      rw_row(in, true, nullptr, 0, o1);
+      if (o0.n_recs > 255) o0.fail = SKB_RWF_EMIT;
+      if (o1.n_recs > 255) o1.fail = SKB_RWF_EMIT;
+      if (getenv("SKB_SIM_VERBOSE") && (o0.fail || o1.fail)) fprintf(stderr, "  round %d row %d fail codes %d %d\n", round, r, o0.fail, o1.fail);
+      res[r] = rw_pack(o0.f_ins, o0.f_surv, o1.f_surv, o0.mask, o1.mask, o0.fail != 0, o1.fail != 0, o0.n_recs & 255, o1.n_recs & 255);
+    }
+    // K6
+    total = rw_bands_resolve(res.data(), n_wrows, y0q, tab.data(), rec_off.data());
+    if (total == 0xFFFFFFFFu) {  // a row gave up: the tables it left are no basis for the retry
+      why = 6;
+      rw_bands_from_events(ev, n_wrows, y0q, tab.data());
+      continue;
+    }
+    // K4 again with the final tables
+    for (int s = 0; s < n_slots && !why; s++) {
+      if (!slots[s].n_chords) continue;
+      const int n = rw_chain(P.E[s], P.Q[s], origin, stop_q, tab.data(), &chords[base[s]], (int)cap[s], nullptr);
+      if (n != (int)slots[s].n_chords) why = 5;
+    }
+    if (why) { stats[3] = why; return 1; }
+    // K7: final rows
+    recs.assign((size_t)total + 1, TrapRec());
+    in.exact = true;
+    for (int r = 0; r < n_wrows && !why; r++) {
+      in.row = r;
+      const int n_alloc = (int)((r + 1 < n_wrows ? rec_off[r + 1] : total) - rec_off[r]);
+      RwRowOut o;
+      rw_row(in, (tab[r].fl & SKB_RB_FIN) != 0, recs.data() + rec_off[r], n_alloc, o);
+      const bool in_rows = r * 4 + 4 > y0q;
+      if (o.fail) {
+        why = 70 + o.fail;
+        if (getenv("SKB_SIM_VERBOSE")) fprintf(stderr, "  round %d final row %d fail code %d (fin %d mask tab %u)\n", round, r, o.fail, (int)(tab[r].fl & 1), tab[r].mask);
+        break;
+      }
+      if (in_rows && (o.mask != tab[r].mask || o.f_surv != ((tab[r].fl & SKB_RB_FSURV) != 0) || o.f_ins != ((tab[r].fl & SKB_RB_FINS) != 0) ||
+                      o.n_recs != n_alloc)) {
+        why = 8;
+        if (getenv("SKB_SIM_VERBOSE"))
+          fprintf(stderr, "  round %d verify row %d: mask %u/%u fsurv %d/%d fins %d/%d recs %d/%d fin %d res %08x\n", round, r, o.mask, tab[r].mask, (int)o.f_surv,
+                  (int)((tab[r].fl & SKB_RB_FSURV) != 0), (int)o.f_ins, (int)((tab[r].fl & SKB_RB_FINS) != 0), o.n_recs, n_alloc,
+                  (int)(tab[r].fl & SKB_RB_FIN), res[r]);
+      }
+    }
+    if (!why) break;
+  }
+  stats[3] = round;
+  // ---- compare with the sequential sweep's records, row by row, in order
+  stats[0] = total;
+  for (int r = 0; r < n_wrows; r++) {
+    const int y = origin + r;
+    const int rel = y - g.scan_t;
+    const int n_alloc = (int)((r + 1 < n_wrows ? rec_off[r + 1] : total) - rec_off[r]);
+    if (rel < 0 || rel >= n_rows) continue;   // rows above the scan rectangle are swept but emit nothing
+    const uint2 row = rows[(size_t)rel];
+    if ((int)row.y != n_alloc) {
+      if (getenv("SKB_SIM_VERBOSE")) fprintf(stderr, "row %d (y %d): %d records, sequential %u\n", r, y, n_alloc, row.y);
+      return 2;
+    }
+    uint32_t idx = row.x;
+    for (uint32_t k = 0; k < row.y; k++, idx++) {
+      TrapRec a = pool[idx];
+      if (a.flags & SKB_REC_LINK) {
+        idx = (uint32_t)a.y;
+        a = pool[idx];
+      }
+      const TrapRec& b = recs[rec_off[r] + k];
+      if (std::memcmp(&a, &b, sizeof(TrapRec)) != 0) {
+        if (getenv("SKB_SIM_VERBOSE"))
+          fprintf(stderr, "row %d (y %d) rec %u: seq y %d ul %d ur %d ll %d lr %d ldy %d rdy %d fl %x | row y %d ul %d ur %d ll %d lr %d ldy %d rdy %d fl %x\n",
+                  r, y, k, a.y, a.ul, a.ur, a.ll, a.lr, a.ldy, a.rdy, a.flags, b.y, b.ul, b.ur, b.ll, b.lr, b.ldy, b.rdy, b.flags);
+        return 2;
+      }
+    }
+  }
+  return 0;
 }

@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [_SRC] + [os.path.join(_REPO, "skity_b200", "csrc", f) for f in
-                         ("skb_core.cuh", "skb_walk.cuh", "skb_stages.cuh", "skb_clip.cuh")] + [os.path.join(_REPO, "include", "skb_dl.h")]
+                         ("skb_core.cuh", "skb_walk.cuh", "skb_stages.cuh", "skb_clip.cuh", "skb_rowwalk.cuh")] + [os.path.join(_REPO, "include", "skb_dl.h")]
         if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
                                    f"-I{_REPO}", _SRC, "-o", _LIB])
@@ -24,6 +24,9 @@ def lib():
         _lib.sim_path_cover.restype = ctypes.c_long
         _lib.sim_path_cover.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.sim_rowwalk_check.restype = ctypes.c_int
+        _lib.sim_rowwalk_check.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         _lib.sim_render_dl.restype = ctypes.c_int
         _lib.sim_render_dl.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
@@ -52,3 +55,14 @@ def path_cover(segs, ctm, clip, even_odd, w, h):
     n = lib().sim_path_cover(segs.ctypes.data, len(segs), m.ctypes.data, c.ctypes.data, int(even_odd), w, h,
                              d.ctypes.data, a.ctypes.data, stats.ctypes.data)
     return d, a, int(n), stats
+
+
+def rowwalk_check(segs, ctm, clip, even_odd, w, h):
+    """Row-parallel walk vs the sequential sweep on one path -> (status, stats): 0 identical records, 1 flagged for the
+    sequential fallback, 2 MISMATCH, 3 empty path."""
+    segs = np.ascontiguousarray(segs)
+    m = np.asarray(ctm, dtype=np.float32)
+    c = np.asarray(clip, dtype=np.float32)
+    stats = np.zeros(4, dtype=np.int64)
+    rc = lib().sim_rowwalk_check(segs.ctypes.data, len(segs), m.ctypes.data, c.ctypes.data, int(even_odd), w, h, stats.ctypes.data)
+    return int(rc), stats

@@ -136,3 +136,56 @@ def test_sweep_gradient_angle_is_the_c_librarys_atan2f():
     lib.sim_atan2f_mismatches.restype = ctypes.c_long
     lib.sim_atan2f_mismatches.argtypes = [ctypes.c_long, ctypes.c_ulonglong]
     assert lib.sim_atan2f_mismatches(3_000_000, 12345) == 0
+
+
+# ---- row-parallel walk (skb_rowwalk.cuh) against the sequential sweep, record by record ---------------------------
+def _rowwalk_scene(s, w=None, h=None):
+    import collections
+    dl = hostlib.encode_scene(s.encode(), allow_unsupported=True)
+    hd = port.dl_header(dl)
+    res = collections.Counter()
+    for i in range(hd["n_ops"]):
+        op = struct.unpack_from("<8I10f", dl, hd["off_ops"] + 72 * i)
+        if op[0] not in (1, 2):
+            continue
+        segs = port.dl_segments(dl, op[2])
+        rc, _ = simlib.rowwalk_check(segs, op[8:14], op[14:18], op[6], w or s.width, h or s.height)
+        assert rc != 2, f"op {i}: the row-parallel walk's records differ from the sequential sweep's"
+        res[rc] += 1
+    return res
+
+
+def test_rowwalk_records_equal_the_sequential_sweep():
+    """The row-parallel form of the sweep (one thread per path row: chords chained through per-path band tables,
+    forcing bits composed over rows, every table entry re-derived by the final pass) must emit, row by row and in
+    order, exactly the trapezoid records of the sequential sweep — or flag the path for it.  Fills, strokes with
+    every join/cap, nested clip paths with their clip bounds (edges culled in y), star."""
+    total = _rowwalk_scene(scene.scene_c0(blur=False))
+    total += _rowwalk_scene(scene.scene_random_fills_fast(1500, 2048, 1, 256.0))
+    total += _rowwalk_scene(scene.scene_random_fills_fast(1500, 1024, 4, 128.0))
+    total += _rowwalk_scene(scene.scene_c2(400, 1024, 2, clip_every=0))
+    total += _rowwalk_scene(scene.scene_c2(600, 1024, 5, clip_every=40, clip_box=300.0))
+    done, flagged = total[0], total[1]
+    assert done > 3500
+    assert flagged <= 0.005 * done, f"{flagged} of {done + flagged} paths fell back to the sequential sweep"
+
+
+@pytest.mark.parametrize("seed0", [0, 40])
+def test_rowwalk_fuzz_scenes(seed0):
+    """... and on the feature fuzz scenes (transforms, conics, layers, filters' temporaries, clips)."""
+    total = {0: 0, 1: 0, 3: 0}
+    for seed in range(seed0, seed0 + 40):
+        for k, v in _rowwalk_scene(scene.scene_fuzz(seed)[0], 4096, 4096).items():
+            total[k] = total.get(k, 0) + v
+    assert total[0] > 500 and total[1] <= 0.01 * total[0]
+
+
+def test_rowwalk_wide_coordinates():
+    lib = simlib.lib()
+    lib.sim_set_wide(1)
+    try:
+        s = scene.scene_random_fills_fast(1200, 16384, 4, 128.0)
+        res = _rowwalk_scene(s)
+    finally:
+        lib.sim_set_wide(0)
+    assert res[0] > 1100 and res[1] <= 3
