@@ -97,6 +97,12 @@ SKB_API skb_result skb_surface_set_band(skb_surface surface, uint32_t y0, uint32
 #define SKB_COORD_WIDE 2
 SKB_API skb_result skb_surface_set_coord_mode(skb_surface surface, int mode);
 
+/* Which form of stage 3 (the reference's active-edge sweep, src/render/sw/sw_raster.cc:546-677) runs:
+ *   0  one thread per path (default);
+ *   1  row-parallel: one thread per (path, pixel row), chords chained through per-path band tables, bit-identical
+ *      trapezoid records (skity_b200/csrc/skb_rowwalk.cuh); paths it cannot settle are swept as in mode 0. */
+SKB_API skb_result skb_surface_set_walk_mode(skb_surface surface, int mode);
+
 /* clear != 0 zeroes the surface (transparent black), like LockCanvas(true). */
 SKB_API skb_result skb_frame_begin(skb_surface surface, int clear);
 /* Copies the display list to the device (host -> device, asynchronous on the surface's stream

@@ -1807,6 +1807,7 @@ struct skb_surface_s {
   uint32_t w = 0, h = 0;
   uint32_t band_y0 = 0, band_y1 = 0;
   int coord_mode = SKB_COORD_AUTO;
+  int walk_mode = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[12] = {};
   // host-mapped words the device writes counts into: reading them does not queue behind another
@@ -2144,8 +2145,9 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->walk_lists, (size_t)n_ops * 4 + 16));
   SKB_TRY(buf_reserve(s->ord, n_slots * 4));
   Edge* edges = (Edge*)s->edges.p;
-  // stage 3 in its row-parallel form (skb_rowwalk.cuh) unless SKB_WALK_MODE=0 asks for the sequential sweep alone
-  const bool rowwalk = !(getenv("SKB_WALK_MODE") && atoi(getenv("SKB_WALK_MODE")) == 0);
+  // stage 3: the sequential sweep (one thread per path), or — skb_surface_set_walk_mode / SKB_WALK_MODE=1 — its
+  // row-parallel form (skb_rowwalk.cuh), which emits the same records
+  const bool rowwalk = getenv("SKB_WALK_MODE") ? atoi(getenv("SKB_WALK_MODE")) == 1 : s->walk_mode == 1;
   uint32_t* chord_base = nullptr;
   uint32_t* wrow_base = nullptr;
   if (rowwalk) {
@@ -2759,6 +2761,12 @@ skb_result skb_surface_set_band(skb_surface s, uint32_t y0, uint32_t y1) {
 skb_result skb_surface_set_coord_mode(skb_surface s, int mode) {
   if (!s || mode < SKB_COORD_AUTO || mode > SKB_COORD_WIDE) return SKB_ERROR_INVALID_ARGUMENT;
   s->coord_mode = mode;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_set_walk_mode(skb_surface s, int mode) {
+  if (!s || mode < 0 || mode > 1) return SKB_ERROR_INVALID_ARGUMENT;
+  s->walk_mode = mode;
   return SKB_SUCCESS;
 }
 

@@ -57,6 +57,7 @@ def lib():
         L.skb_surface_destroy.restype = None
         L.skb_surface_set_band.argtypes = [vp, u32, u32]
         L.skb_surface_set_coord_mode.argtypes = [vp, ctypes.c_int]
+        L.skb_surface_set_walk_mode.argtypes = [vp, ctypes.c_int]
         L.skb_frame_begin.argtypes = [vp, ctypes.c_int]
         L.skb_frame_encode.argtypes = [vp, vp, sz]
         L.skb_frame_flush.argtypes = [vp]
@@ -121,6 +122,10 @@ class Surface:
     def set_coord_mode(self, mode):
         """0 auto (wide above 8192 px), 1 the reference's int32 arithmetic (wraps at 8192 px), 2 wide."""
         _check(lib().skb_surface_set_coord_mode(self._h, int(mode)), "skb_surface_set_coord_mode")
+
+    def set_walk_mode(self, mode):
+        """0 the sequential sweep (one thread per path), 1 the row-parallel sweep (same records)."""
+        _check(lib().skb_surface_set_walk_mode(self._h, int(mode)), "skb_surface_set_walk_mode")
 
     def begin(self, clear=True):
         _check(lib().skb_frame_begin(self._h, 1 if clear else 0), "skb_frame_begin")

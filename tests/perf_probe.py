@@ -32,6 +32,6 @@ for name in which:
         st = surf.stats()
     print(name, 'encode %.2fs' % te, 'wall %.1f ms' % (tw * 1e3), 'dev %.2f ms' % st['ms_total'],
           dict(zip(device.STAGE_NAMES, [round(x, 3) for x in st['ms_stage']])),
-          {k: st[k] for k in ('n_prims', 'n_rows', 'n_records', 'n_items', 'n_cmds', 'n_launches', 'n_retries')},
+          {k: st[k] for k in ('n_prims', 'n_rows', 'n_records', 'n_items', 'n_cmds', 'n_launches', 'n_retries', 'n_rw_retried', 'n_rw_sequential')},
           'Mpix/s %.0f' % (s.width * s.height / 1e3 / st['ms_total']), 'paths/s %.0f' % (s.n_draws / st['ms_total'] * 1e3), flush=True)
     surf.close()

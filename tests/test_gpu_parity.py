@@ -403,3 +403,45 @@ def test_config_c4a_full_size_vs_wide_oracle(dev):
             assert np.array_equal(rows, got[y0:y1])
     finally:
         surf.close()
+
+
+# ---- stage 3 in its row-parallel form (opt-in): same frames as the sequential sweep ----------------------------------
+@pytest.mark.parametrize("name", ["c1_fills_120_512", "c2_gradients_90_512", "c2_clips_90_512", "mixed_transform_clip_400x300",
+                                  "wrap_8192_256", "clip_zero_length_span_532", "c0_star_blur_800x600"])
+def test_rowwalk_mode_golden(dev, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    want = z["rgba"]
+    surf = dev.create_surface(want.shape[1], want.shape[0])
+    try:
+        surf.set_walk_mode(1)
+        got = surf.render(z["dl"].tobytes())
+        st = surf.stats()
+    finally:
+        surf.close()
+    if name == "c2_gradients_90_512":
+        assert_within_tolerance(got, want)
+    else:
+        assert np.array_equal(got, want)
+    assert st["n_rw_sequential"] <= max(2, st["n_ops"] // 20)
+
+
+def test_rowwalk_mode_full_size_c1_and_c2(dev):
+    """The row-parallel sweep on C1 (10k paths, 4096^2) against the sequential sweep's frame, and on C2 at its named
+    size against the reference's digest; few paths may fall back to the sequential sweep."""
+    import config_digest
+    sc = scene.scene_c1()
+    dl = hostlib.encode_scene(sc.encode())
+    surf = dev.create_surface(sc.width, sc.height)
+    try:
+        want = surf.render(dl)
+        surf.set_walk_mode(1)
+        got = surf.render(dl)
+        st = surf.stats()
+        assert np.array_equal(got, want)
+        assert st["n_rw_sequential"] <= 50, st
+        sc2 = scene.scene_c2(20000, 4096, 2)
+        got2 = surf.render(hostlib.encode_scene(sc2.encode()))
+        ok, msg = config_digest.compare(_digest_store(), "c2", got2)
+        assert ok, msg
+    finally:
+        surf.close()
