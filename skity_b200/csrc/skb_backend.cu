@@ -2312,7 +2312,11 @@ static skb_result run_frame(skb_surface s) {
       const uint64_t want_threads = (uint64_t)s->dev->sm_count * 32 * 32;
       while (lane_stride < 8 && (uint64_t)n_seq * lane_stride * 2 <= want_threads) lane_stride *= 2;
       if (getenv("SKB_WALK_LANE_STRIDE")) lane_stride = atoi(getenv("SKB_WALK_LANE_STRIDE"));
-      k_walk<<<cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK), WALK_BLOCK, 0, st>>>(wa, lane_stride);
+      // SKB_WALK_SMEM: dynamic shared memory per block, only to cap the blocks (= paths) in flight per SM — the sweep's
+      // working set is ~3 KB of edges per path, and with every thread slot taken it spills from L2 to DRAM
+      static const int walk_smem = getenv("SKB_WALK_SMEM") ? atoi(getenv("SKB_WALK_SMEM")) : 0;
+      if (walk_smem > 48 * 1024) cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem);
+      k_walk<<<cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK), WALK_BLOCK, walk_smem, st>>>(wa, lane_stride);
       launches++;
     }
     uint32_t hc[12];

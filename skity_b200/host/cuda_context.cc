@@ -176,3 +176,70 @@ extern "C" int skbh_render_scene_cuda(const uint8_t* scene, size_t n, int device
   }
   return 0;
 }
+
+// The same path over several frames on ONE context and surface, the way an application draws: per frame
+// LockCanvas(true) -> Canvas calls -> Flush -> ReadPixels.  ms_out[0..3] receive the mean wall-clock milliseconds per
+// frame of the frames after the first: whole frame, the Canvas calls (host encode), Flush (upload + device work is
+// asynchronous: mostly the upload), ReadPixels (waits for the device, copies back).  out_rgba: the last frame.
+#include <chrono>
+extern "C" int skbh_render_scene_cuda_frames(const uint8_t* scene, size_t n, int device_ordinal, int frames, uint8_t* out_rgba,
+                                             double* ms_out, char* err, size_t err_cap) {
+  auto fail = [&](const char* m, int rc) {
+    if (err && err_cap) {
+      std::strncpy(err, m, err_cap - 1);
+      err[err_cap - 1] = 0;
+    }
+    return rc;
+  };
+  if (n < sizeof(skb_scene::Header) || frames < 1) return fail("short scene", -1);
+  skb_scene::Header h;
+  std::memcpy(&h, scene, sizeof(h));
+  if (h.magic != skb_scene::kMagic) return fail("bad magic", -1);
+  skity::CudaContextDesc cd;
+  cd.device_ordinal = device_ordinal;
+  auto ctx = skity::CudaContextCreate(&cd);
+  if (!ctx) return fail(skb_get_last_error_string(), -2);
+  std::string cb_msg;
+  ctx->SetErrorCallback(
+      [](skity::GPUError, const char* message, void* user) { *static_cast<std::string*>(user) = message ? message : ""; },
+      &cb_msg);
+  skity::GPUSurfaceDescriptorCuda sd;
+  sd.backend = skity::kGPUBackendTypeCUDA;
+  sd.width = h.width;
+  sd.height = h.height;
+  auto surf = ctx->CreateSurface(&sd);
+  if (!surf) return fail(cb_msg.c_str(), -3);
+  using clk = std::chrono::steady_clock;
+  auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  double acc[4] = {0, 0, 0, 0};
+  for (int f = 0; f < frames; f++) {
+    const auto t0 = clk::now();
+    skity::Canvas* canvas = surf->LockCanvas(true);
+    int rc = skb_scene::Play(scene, n, canvas);
+    if (rc != 0) return fail("malformed scene", rc);
+    const auto t1 = clk::now();
+    surf->Flush();
+    if (!cb_msg.empty()) return fail(cb_msg.c_str(), -4);
+    const auto t2 = clk::now();
+    auto pm = surf->ReadPixels(skity::Rect::MakeWH(h.width, h.height));
+    if (!pm) return fail(cb_msg.c_str(), -5);
+    const auto t3 = clk::now();
+    if (f > 0 || frames == 1) {
+      acc[0] += ms(t0, t3);
+      acc[1] += ms(t0, t1);
+      acc[2] += ms(t1, t2);
+      acc[3] += ms(t2, t3);
+    }
+    if (f == frames - 1 && out_rgba) {
+      for (uint32_t y = 0; y < h.height; y++) {
+        std::memcpy(out_rgba + static_cast<size_t>(y) * h.width * 4,
+                    static_cast<const uint8_t*>(pm->Addr()) + static_cast<size_t>(y) * pm->RowBytes(),
+                    static_cast<size_t>(h.width) * 4);
+      }
+    }
+  }
+  const double cnt = frames > 1 ? frames - 1 : 1;
+  if (ms_out)
+    for (int i = 0; i < 4; i++) ms_out[i] = acc[i] / cnt;
+  return 0;
+}

@@ -27,6 +27,9 @@ def lib():
         _lib.skbh_render_scene_cuda.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_render_scene_cuda.restype = ctypes.c_int
+        _lib.skbh_render_scene_cuda_frames.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                       ctypes.POINTER(ctypes.c_double), ctypes.c_char_p, ctypes.c_size_t]
+        _lib.skbh_render_scene_cuda_frames.restype = ctypes.c_int
     return _lib
 
 
@@ -83,3 +86,21 @@ def render_scene_cuda(blob, device_ordinal=0):
     if rc != 0:
         raise RuntimeError(f"skbh_render_scene_cuda failed ({rc}): {msg.value.decode(errors='replace')}")
     return out
+
+
+def render_scene_cuda_frames(blob, frames, device_ordinal=0, want_pixels=False):
+    """`frames` frames of the scene through the skity plug-in path on ONE context and surface
+    (LockCanvas -> Canvas calls -> Flush -> ReadPixels per frame).  -> (mean ms per frame of the frames after the first:
+    dict(total, canvas_calls, flush, read_pixels), pixels of the last frame or None)."""
+    import struct
+
+    import numpy as np
+    _, _, w, h, _, _ = struct.unpack_from("<6I", blob, 0)
+    out = np.zeros((h, w, 4), dtype=np.uint8) if want_pixels else None
+    ms = (ctypes.c_double * 4)()
+    msg = ctypes.create_string_buffer(512)
+    rc = lib().skbh_render_scene_cuda_frames(blob, len(blob), device_ordinal, int(frames), out.ctypes.data if want_pixels else None,
+                                             ms, msg, 512)
+    if rc != 0:
+        raise RuntimeError(f"skbh_render_scene_cuda_frames failed ({rc}): {msg.value.decode(errors='replace')}")
+    return dict(total=ms[0], canvas_calls=ms[1], flush=ms[2], read_pixels=ms[3]), out
