@@ -108,6 +108,11 @@ SKB_API skb_result skb_frame_begin(skb_surface surface, int clear);
 /* Copies the display list to the device (host -> device, asynchronous on the surface's stream
  * when `display_list` is pinned) and validates it.  One display list per frame. */
 SKB_API skb_result skb_frame_encode(skb_surface surface, const void* display_list, size_t bytes);
+/* The validation skb_frame_encode performs, on its own (no device needed): SKB_SUCCESS, SKB_ERROR_BAD_DISPLAY_LIST or
+ * SKB_ERROR_UNSUPPORTED, with the reason in skb_get_last_error_string().  A list that passes is safe to hand to the
+ * kernels: every index is in range, sections are in order, every fill / clip op owns the next path and the paths tile
+ * the segment table (include/skb_dl.h). */
+SKB_API skb_result skb_display_list_validate(const void* display_list, size_t bytes);
 /* Launches every stage for the encoded frame.  Asynchronous unless the record pool overflows. */
 SKB_API skb_result skb_frame_flush(skb_surface surface);
 /* Blocks until the surface's stream is idle; returns the first asynchronous error. */

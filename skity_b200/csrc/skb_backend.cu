@@ -1953,10 +1953,45 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
     set_error("display list: section out of range");
     return SKB_ERROR_BAD_DISPLAY_LIST;
   }
+  // the surface and op tables stay on the host as dl[0 .. off_paths) (skb_frame_encode): they must lie before the paths
+  if ((uint64_t)h.off_surfaces + (uint64_t)h.n_surfaces * sizeof(skb_dl_surface) > h.off_ops ||
+      (uint64_t)h.off_ops + (uint64_t)h.n_ops * sizeof(skb_dl_op) > h.off_paths || h.off_paths > h.off_segs) {
+    set_error("display list: sections out of order (surfaces, ops, paths, segments)");
+    return SKB_ERROR_BAD_DISPLAY_LIST;
+  }
+  if (h.n_clip_states > h.n_ops) {
+    set_error("display list: more clip states than ops");
+    return SKB_ERROR_BAD_DISPLAY_LIST;
+  }
   const skb_dl_op* ops = (const skb_dl_op*)(dl + h.off_ops);
   const skb_dl_path* paths = (const skb_dl_path*)(dl + h.off_paths);
   const skb_dl_paint* paints = (const skb_dl_paint*)(dl + h.off_paints);
   const skb_dl_surface* vsurfs = (const skb_dl_surface*)(dl + h.off_surfaces);
+  for (uint32_t i = 1; i < h.n_surfaces; i++) {  // surface 0 takes the size of the skb_surface it is rendered into
+    if (vsurfs[i].width == 0 || vsurfs[i].height == 0 || vsurfs[i].width > 65535u * 16 || vsurfs[i].height > 65535u * 16) {
+      set_error("display list: surface size out of range");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
+  }
+  // The flatten stage lays edge regions out from "op i owns path i's segments, paths in op order, every segment owned":
+  // path k (k-th FILL/CLIP op) must be path index k and the paths must tile the segment table without gaps or overlap.
+  {
+    uint64_t next_seg = 0;
+    uint32_t next_path = 0;
+    for (uint32_t i = 0; i < h.n_ops; i++) {
+      if (ops[i].kind != SKB_OP_FILL && ops[i].kind != SKB_OP_CLIP) continue;
+      if (ops[i].path != next_path || next_path >= h.n_paths || paths[next_path].seg_off != next_seg) {
+        set_error("display list: every fill / clip op owns the next path, and paths follow each other in the segment table");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      next_seg += paths[next_path].n_segs;
+      next_path++;
+    }
+    if (next_path != h.n_paths || next_seg != h.n_segs) {
+      set_error("display list: paths or segments that no op owns");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
+  }
   for (uint32_t i = 0; i < h.n_surfaces; i++) {
     if (!(vsurfs[i].flags & SKB_SURFACE_IMAGE)) continue;
     if (i == 0 || (uint64_t)vsurfs[i].reserved + (uint64_t)vsurfs[i].width * vsurfs[i].height * 4 > h.total_bytes) {
@@ -2549,8 +2584,6 @@ static skb_result run_frame(skb_surface s) {
     SKB_CUDA(cudaMemcpyAsync(s->blur_rows.p, rowb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
     SKB_CUDA(cudaMemcpyAsync(s->blur_cols.p, colb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
     SKB_CUDA(cudaMemcpyAsync(s->blur_tmp_ptrs.p, tmp_ptrs.data(), nj * sizeof(void*), cudaMemcpyHostToDevice, st));
-    if (blur_smem > 48 * 1024)
-      SKB_CUDA(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
   }
   if (s->max_level >= 16) {
     set_error("more than 16 dependent passes (nested layers / filters)");
@@ -2683,6 +2716,9 @@ skb_result skb_device_create(int ordinal, skb_device* out) {
   }
   skb_device d = new skb_device_s();
   d->ordinal = ordinal;
+  // process-wide kernel attribute, set once here (to the most run_frame ever asks for) rather than per frame: surfaces
+  // of one device may be driven from different threads
+  SKB_CUDA(cudaFuncSetAttribute(k_blur_h, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   d->sm_count = prop.multiProcessorCount;
   *out = d;
   return SKB_SUCCESS;
@@ -2795,6 +2831,11 @@ skb_result skb_frame_begin(skb_surface s, int clear) {
   // the last encoded display list stays resident: a frame may be flushed again without re-uploading it
   s->flushed = false;
   return SKB_SUCCESS;
+}
+
+skb_result skb_display_list_validate(const void* dl, size_t bytes) {
+  if (!dl) return SKB_ERROR_INVALID_ARGUMENT;
+  return validate_dl((const uint8_t*)dl, bytes);
 }
 
 skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {

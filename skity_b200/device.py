@@ -61,6 +61,7 @@ def lib():
         L.skb_frame_begin.argtypes = [vp, ctypes.c_int]
         L.skb_frame_encode.argtypes = [vp, vp, sz]
         L.skb_frame_flush.argtypes = [vp]
+        L.skb_display_list_validate.argtypes = [vp, sz]
         L.skb_surface_sync.argtypes = [vp]
         L.skb_surface_read_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_surface_read_pixels_async.argtypes = [vp, u32, u32, u32, u32, vp, sz]
@@ -221,3 +222,11 @@ class Surface:
             self.close()
         except Exception:
             pass
+
+
+def validate_display_list(dl):
+    """skb_display_list_validate: raises SkbError with the library's reason when the list is malformed (no GPU needed)."""
+    buf = bytes(dl)
+    rc = lib().skb_display_list_validate(buf, len(buf))
+    if rc != 0:
+        raise SkbError(f"skb_display_list_validate failed ({rc}): {lib().skb_get_last_error_string().decode(errors='replace')}")

@@ -530,9 +530,12 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
         auto pixmap_shader = std::static_pointer_cast<PixmapShader>(shader);
         const std::shared_ptr<Pixmap>& pixmap = *pm;
         uint32_t iw = pixmap->Width(), ih = pixmap->Height();
-        // the Colors Bitmap::GetPixel hands the sampler, whatever the pixmap's colour type
-        std::vector<uint8_t> rgba(static_cast<size_t>(iw) * ih * 4);
-        {
+        // the image is identified by its pixmap and the bytes it holds right now; only a new (pixmap, content) pair
+        // pays the conversion to the Colors Bitmap::GetPixel hands the sampler, whatever the pixmap's colour type
+        const uint64_t content = skb::DlBuilder::HashBytes(pixmap->Addr(), pixmap->RowBytes() * static_cast<size_t>(ih));
+        uint32_t sid = builder_->FindImageSurface(pixmap.get(), content, iw, ih);
+        if (sid == 0) {
+          std::vector<uint8_t> rgba(static_cast<size_t>(iw) * ih * 4);
           Bitmap bm(pixmap, true);
           for (uint32_t yy = 0; yy < ih; yy++) {
             for (uint32_t xx = 0; xx < iw; xx++) {
@@ -544,8 +547,8 @@ uint32_t CudaCanvas::MakeBrush(const Paint& paint, bool stroke) {
               d[3] = ColorGetA(c);
             }
           }
+          sid = builder_->AddImageSurface(pixmap.get(), content, pixmap, iw, ih, rgba.data());
         }
-        uint32_t sid = builder_->AddImageSurface(pixmap.get(), iw, ih, rgba.data());
         Matrix inverse;
         shader->GetLocalMatrix().Invert(&inverse);
         Matrix matrix = Matrix::Scale(1.f / iw, 1.f / ih) * inverse;

@@ -9,6 +9,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "include/skb_dl.h"
@@ -40,14 +41,38 @@ class DlBuilder {
     return static_cast<uint32_t>(surfaces_.size() - 1);
   }
 
-  // An application image: RGBA8 pixels (width*height*4 bytes) carried in the display list.  `key` identifies the
-  // source pixmap so that one image drawn many times is stored once.
-  uint32_t AddImageSurface(const void* key, uint32_t w, uint32_t h, const uint8_t* rgba) {
+  // An application image: RGBA8 pixels (width*height*4 bytes) carried in the display list, stored once however
+  // often it is drawn.  An image is identified by its source object AND a hash of the source's bytes at the time
+  // of the draw: `keep_alive` (the source pixmap) is held until Reset so that its address cannot be recycled for a
+  // different image within the frame, and the hash tells a pixmap that was modified between two draws from itself.
+  // FindImageSurface is consulted first so that a repeated draw skips the RGBA conversion.
+  static uint64_t HashBytes(const void* p, size_t n) {  // FNV-1a, 8 bytes at a time
+    const uint8_t* b = static_cast<const uint8_t*>(p);
+    uint64_t h = 1469598103934665603ull;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+      uint64_t w;
+      std::memcpy(&w, b + i, 8);
+      h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+  }
+  // -> surface id, or 0 (the canvas is never an image) when this (source, content) pair is not in the list yet
+  uint32_t FindImageSurface(const void* key, uint64_t content_hash, uint32_t w, uint32_t h) const {
     for (const auto& im : images_)
-      if (im.key == key && surfaces_[im.surface].width == w && surfaces_[im.surface].height == h) return im.surface;
+      if (im.key == key && im.content_hash == content_hash && surfaces_[im.surface].width == w &&
+          surfaces_[im.surface].height == h)
+        return im.surface;
+    return 0;
+  }
+  uint32_t AddImageSurface(const void* key, uint64_t content_hash, std::shared_ptr<const void> keep_alive, uint32_t w,
+                           uint32_t h, const uint8_t* rgba) {
     uint32_t id = AddSurface(w, h, SKB_SURFACE_IMAGE);
     ImageBlob b;
     b.key = key;
+    b.content_hash = content_hash;
+    b.keep_alive = std::move(keep_alive);
     b.surface = id;
     b.pixels.assign(rgba, rgba + static_cast<size_t>(w) * h * 4);
     images_.push_back(std::move(b));
@@ -147,6 +172,8 @@ class DlBuilder {
  private:
   struct ImageBlob {
     const void* key;
+    uint64_t content_hash;
+    std::shared_ptr<const void> keep_alive;
     uint32_t surface;
     std::vector<uint8_t> pixels;
   };

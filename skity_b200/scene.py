@@ -676,6 +676,20 @@ def scene_color_filters(seed=66, size=512):
     return s
 
 
+def scene_images_same_size(seed=91, size=256):
+    """Two application images of the SAME size and different content, each created as a temporary for its draw (the
+    scene player destroys the Image as soon as the Canvas call returns, so the second pixmap may sit at the first
+    one's address): every draw must show its own pixels."""
+    s = Scene(size, size)
+    s.draw_rect(0, 0, size, size, Paint(fill=(0.2, 0.2, 0.25, 1.0)))
+    img_a, img_b = (24, 24, seed, 0), (24, 24, seed + 5, 0)
+    s.draw_image_rect(img_a, (0, 0, 24, 24), (8, 8, 120, 120), Paint(), filter=0)
+    s.draw_image_rect(img_b, (0, 0, 24, 24), (136, 8, 248, 120), Paint(), filter=0)
+    s.draw_image_rect(img_a, (0, 0, 24, 24), (8, 136, 120, 248), Paint(), filter=1)
+    s.draw_image_rect(img_b, (0, 0, 24, 24), (136, 136, 248, 248), Paint(), filter=1)
+    return s
+
+
 def scene_images(seed=77, size=512):
     """Application images (Canvas::DrawImageRect and image shaders, src/render/sw/sw_canvas.cc:641-677,755-787;
     BitmapSampler, src/graphic/bitmap_sampler.cc): premultiplied and unpremultiplied pixels, nearest / bilinear /

@@ -103,6 +103,8 @@ def golden_scenes():
     # ... and such spans are handed down: here a third-level clip consists of one zero-length span inherited from
     # the zero-length / zero-coverage spans of the second level
     out["clip_inherited_ghost_span_354"] = scene.scene_fuzz(22152)[0]
+    # two same-size images of different content, both temporaries (the encoder's image table must not confuse them)
+    out["images_same_size_256"] = scene.scene_images_same_size()
     return out
 
 

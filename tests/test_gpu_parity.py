@@ -48,7 +48,7 @@ def assert_within_tolerance(got, want):
 EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c3_blur_12_640",
          "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144",
          "blend_modes_480", "filters_512", "layers_512", "filters_channel_carry_283", "blend_zero_then_accum_418",
-         "clipped_blends_400", "filtered_layers_384", "filters_morphology_512"]
+         "clipped_blends_400", "filtered_layers_384", "filters_morphology_512", "images_same_size_256"]
 
 
 @pytest.mark.parametrize("name", EXACT)

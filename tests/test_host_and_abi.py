@@ -103,3 +103,49 @@ def test_recorded_display_list_replays_to_the_same_frame():
     for s in scenes:
         blob = s.encode()
         assert hostlib.encode_scene(blob, recorded=True) == hostlib.encode_scene(blob)
+
+
+def test_display_list_validation_accepts_every_fixture_and_rejects_broken_structure():
+    """skb_display_list_validate (what skb_frame_encode runs) on the host: every committed display list passes; lists
+    that break the layout the kernels rely on (sections out of order, a path owned by no op or by two, segment gaps,
+    oversized surfaces, too many clip states) are refused before they reach the device."""
+    import glob
+    from skity_b200 import device
+    n_ok = 0
+    for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
+        z = np.load(f)
+        if "dl" in z.files:
+            device.validate_display_list(z["dl"].tobytes())
+            n_ok += 1
+    assert n_ok >= 20
+    z = np.load(os.path.join(ROOT, "tests", "golden", "c1_fills_120_512.npz"))
+    good = bytearray(z["dl"].tobytes())
+    hd = port.dl_header(bytes(good))
+    device.validate_display_list(good)
+
+    def broken(mutate):
+        b = bytearray(good)
+        mutate(b)
+        with pytest.raises(device.SkbError):
+            device.validate_display_list(b)
+
+    op_sz, off_ops, off_paths = 72, hd["off_ops"], hd["off_paths"]
+    # two ops share path 0
+    broken(lambda b: struct.pack_into("<I", b, off_ops + op_sz * 1 + 8, 0))
+    # ops out of path order
+    def swap_paths(b):
+        struct.pack_into("<I", b, off_ops + op_sz * 0 + 8, 1)
+        struct.pack_into("<I", b, off_ops + op_sz * 1 + 8, 0)
+    broken(swap_paths)
+    # a gap in the segment table: path 1 starts one segment late
+    def gap(b):
+        so, ns = struct.unpack_from("<2I", b, off_paths + 16)
+        struct.pack_into("<2I", b, off_paths + 16, so + 1, ns - 1)
+    broken(gap)
+    # header claims one more clip state than there are ops
+    names = list(hd.keys())
+    def field(name):
+        return 4 * names.index(name)
+    broken(lambda b: struct.pack_into("<I", b, field("n_clip_states"), hd["n_ops"] + 1))
+    # ops placed behind the paths (the host keeps only dl[0 .. off_paths))
+    broken(lambda b: struct.pack_into("<I", b, field("off_paths"), hd["off_ops"]))
