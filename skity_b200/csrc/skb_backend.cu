@@ -407,8 +407,8 @@ __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   uint8_t* region = reinterpret_cast<uint8_t*>(a.edges) + (size_t)g.slot_base * (sizeof(Edge) + sizeof(QuadState));
   Edge* E = reinterpret_cast<Edge*>(region);
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
-  walk_path(E, Q, nullptr, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y,
-            g.left_clip, g.right_clip, (int)a.t.ops[op].fill_type, sink, 1, (int)a.t.wide);
+  walk_path(E, Q, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y, g.left_clip,
+            g.right_clip, (int)a.t.ops[op].fill_type, sink, (int)a.t.wide);
 }
 
 // ------------------------------------------------- stage 3 (row-parallel form): skb_rowwalk.cuh

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "skity_b200/csrc/skb_stages.cuh"
+#include "tests/sim/walk_nested.hpp"
 
 using namespace skb;
 
@@ -84,7 +85,7 @@ long sim_path_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, c
     sink.row0 = g.scan_t;
     sink.n_rows = n_rows;
     sink_init(sink);
-    walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
+    sim_walk_path(Ew.data(), Qw.data(), (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
               g.right_clip, even_odd, sink, sim_walk_mode(), g_sim_wide);
     if (!overflow) break;
     pool.resize(pool.size() * 4);
@@ -176,7 +177,7 @@ void sim_raster_op(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, co
     sink.row0 = g.scan_t;
     sink.n_rows = n_rows;
     sink_init(sink);
-    walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y,
+    sim_walk_path(Ew.data(), Qw.data(), (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y,
               g.left_clip, g.right_clip, even_odd, sink, sim_walk_mode(), g_sim_wide);
     if (!overflow) break;
     out.pool.resize(out.pool.size() * 4);
@@ -417,7 +418,7 @@ extern "C" int sim_rowwalk_check(const skb_dl_seg* segs, uint32_t n_segs, const 
       sink.row0 = g.scan_t;
       sink.n_rows = n_rows;
       sink_init(sink);
-      walk_path(Ew.data(), Qw.data(), nullptr, (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
+      sim_walk_path(Ew.data(), Qw.data(), (int)Ew.size(), ord.data(), g.scan_top_f, g.scan_bottom_f, g.start_y, g.stop_y, g.left_clip,
                 g.right_clip, even_odd, sink, 1, g_sim_wide);
       if (!overflow) break;
       pool.resize(pool.size() * 4);
