@@ -17,8 +17,9 @@ SEG_DTYPE = np.dtype([("type_flags", "<u4"), ("w", "<f4"), ("p", "<f4", (8,)), (
 
 def build(force=False):
     hdr = os.path.join(os.path.dirname(_HERE), "include", "skb_dl.h")
+    area = os.path.join(_HERE, "skb_area_oracle.h")
     if (not force and os.path.exists(LIB_PATH)
-            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(SRC_PATH), os.path.getmtime(hdr))):
+            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(SRC_PATH), os.path.getmtime(hdr), os.path.getmtime(area))):
         return LIB_PATH
     subprocess.check_call(["gcc", "-O2", "-std=c99", "-ffp-contract=off", "-fPIC", "-shared", "-fvisibility=hidden",
                            "-Wall", "-Wno-unused-function", "-o", LIB_PATH, SRC_PATH, "-lm"])
@@ -37,6 +38,14 @@ def lib():
         _lib.skbo_raster_path.restype = ctypes.c_long
         _lib.skbo_set_coord_mode.argtypes = [ctypes.c_int]
         _lib.skbo_set_row_band.argtypes = [ctypes.c_int, ctypes.c_int]
+        _lib.skbo_set_coverage_mode.argtypes = [ctypes.c_int]
+        _lib.skbo_area_tile_path.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long,
+                                             ctypes.POINTER(ctypes.c_long)]
+        _lib.skbo_area_tile_path.restype = ctypes.c_long
+        _lib.skbo_area_raster_path.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_long]
+        _lib.skbo_area_raster_path.restype = ctypes.c_long
         _lib.skbo_stack_blur.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     return _lib
 
@@ -113,6 +122,53 @@ def raster_path(segs, ctm=(1, 0, 0, 0, 1, 0), clip=(-1e9, -1e9, 1e9, 1e9), even_
     if n > cap:
         return raster_path(segs, ctm, clip, even_odd, int(n))
     return spans[:n].copy(), bounds
+
+
+def set_coverage_mode(mode):
+    """0 = the software backend's analytic AA (default); 1 = the reference's coverage-AA path for unclipped fills
+    (what the CUDA backend computes under SKB_COVERAGE_AREA)."""
+    lib().skbo_set_coverage_mode(int(mode))
+
+
+def render_area(dl, initial=None):
+    """render() with coverage-AA ("AREA") coverage."""
+    set_coverage_mode(1)
+    try:
+        return render(dl, initial)
+    finally:
+        set_coverage_mode(0)
+
+
+def area_tile_path(segs, ctm=(1, 0, 0, 0, 1, 0), scissor=None, even_odd=False, tile_cap=1 << 16, line_cap=1 << 20):
+    """The port's CoverageAAPathTiler restatement on one path -> (tiles (n, 5) int32: tile_x, tile_y, first line or -1,
+    line count, backdrop; lines (m, 4) uint16 in range order)."""
+    segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    m = np.asarray(ctm, dtype=np.float32)
+    sc = None if scissor is None else np.asarray(scissor, dtype=np.float32)
+    tiles = np.zeros((tile_cap, 5), dtype=np.int32)
+    lines = np.zeros((line_cap, 4), dtype=np.uint16)
+    nl = ctypes.c_long(0)
+    n = lib().skbo_area_tile_path(segs.ctypes.data, len(segs), m.ctypes.data, None if sc is None else sc.ctypes.data,
+                                  int(even_odd), tiles.ctypes.data, tile_cap, lines.ctypes.data, line_cap, ctypes.byref(nl))
+    if n < 0:
+        return area_tile_path(segs, ctm, scissor, even_odd, tile_cap * 8, line_cap * 8)
+    return tiles[:n].copy(), lines[:nl.value].copy()
+
+
+def area_coverage(segs, w, h, ctm=(1, 0, 0, 0, 1, 0), clip=None, even_odd=False, cap=1 << 22):
+    """Coverage-AA ("AREA") coverage of one path on a w x h surface -> (h, w) uint8."""
+    segs = np.ascontiguousarray(segs, dtype=SEG_DTYPE)
+    m = np.asarray(ctm, dtype=np.float32)
+    c = np.asarray(clip if clip is not None else (0, 0, w, h), dtype=np.float32)
+    spans = np.zeros((cap, 4), dtype=np.int32)
+    n = lib().skbo_area_raster_path(segs.ctypes.data, len(segs), m.ctypes.data, c.ctypes.data, int(even_odd), int(w), int(h),
+                                    spans.ctypes.data, cap)
+    if n > cap:
+        return area_coverage(segs, w, h, ctm, clip, even_odd, int(n))
+    out = np.zeros((h, w), dtype=np.uint8)
+    for x, y, ln, cv in spans[:n]:
+        out[y, x:x + ln] = cv
+    return out
 
 
 def stack_blur(rgba, radius):

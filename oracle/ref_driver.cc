@@ -17,6 +17,8 @@
 #include <skity/render/canvas.hpp>
 
 #include "skity_b200/host/scene_player.hpp"
+#include "src/render/hw/coverage/coverage_aa_line_encoder.hpp"
+#include "src/render/hw/coverage/coverage_aa_tiler.hpp"
 #include "src/render/sw/sw_raster.hpp"
 #include "src/render/sw/sw_stack_blur.hpp"
 
@@ -95,6 +97,41 @@ int ref_stack_blur(const uint8_t* src_rgba, uint32_t w, uint32_t h, int radius, 
                 static_cast<size_t>(w) * 4);
   }
   return 0;
+}
+
+// The reference's own CoverageAAPathTiler (src/render/hw/coverage/coverage_aa_tiler.cc:73-94) and line encoder
+// (coverage_aa_line_encoder.cc:39-75) on one path (SKSC path record): what its GPU backends upload for a
+// coverage-AA draw.  tiles_out[i] = tile_x, tile_y, first line (-1: none), line count, backdrop;
+// lines_out[j] = from_x, from_y, to_x, to_y (unsigned 8.8) in the encoded (per-tile) order.  scissor4 may be null.
+// Returns the tile count (negative: capacity exceeded); *n_lines_out = encoded lines.
+long ref_coverage_aa_tile(const uint8_t* path_rec, size_t n, const float* matrix6, const float* scissor4, int32_t* tiles_out,
+                          long tile_cap, uint16_t* lines_out, long line_cap, long* n_lines_out) {
+  skb_scene::Reader r(path_rec, n);
+  skity::Path path;
+  if (!skb_scene::ReadPath(r, &path)) return -2;
+  std::vector<skity::CoverageAATile> tiles;
+  std::vector<skity::CoverageAATileLine> lines;
+  std::vector<uint32_t> counts;
+  skity::CoverageAAPathTiler tiler(tiles, lines, counts);
+  skity::Rect sc;
+  if (scissor4) sc = skity::Rect::MakeLTRB(scissor4[0], scissor4[1], scissor4[2], scissor4[3]);
+  skity::CoverageAATiledPath tp = tiler.Tile(path, skb_scene::Affine(matrix6), scissor4 ? &sc : nullptr);
+  std::vector<uint32_t> range_counts = counts;   // EncodeCoverageAALines consumes its copy
+  skity::CoverageAAEncodedLines enc;
+  skity::EncodeCoverageAALines(lines, counts, 16384, enc);
+  if (static_cast<long>(tp.tile_count) > tile_cap || static_cast<long>(lines.size()) > line_cap) return -1;
+  for (size_t i = 0; i < tp.tile_count; i++) {
+    const auto& t = tiles[tp.tile_offset + i];
+    int32_t* o = tiles_out + 5 * i;
+    o[0] = t.tile_x;
+    o[1] = t.tile_y;
+    o[2] = t.line_range_id.IsValid() ? static_cast<int32_t>(enc.range_offsets[t.line_range_id.value]) : -1;
+    o[3] = t.line_range_id.IsValid() ? static_cast<int32_t>(range_counts[t.line_range_id.value]) : 0;
+    o[4] = t.backdrop;
+  }
+  std::memcpy(lines_out, enc.texture_data.data(), lines.size() * 4 * sizeof(uint16_t));
+  *n_lines_out = static_cast<long>(lines.size());
+  return static_cast<long>(tp.tile_count);
 }
 
 const char* ref_version() { return "skity-sw-reference (unmodified sources, glm stand-in)"; }

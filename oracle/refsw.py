@@ -29,6 +29,10 @@ def lib():
         _lib.ref_stack_blur.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int,
                                         ctypes.c_void_p]
         _lib.ref_stack_blur.restype = ctypes.c_int
+        _lib.ref_coverage_aa_tile.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_long,
+                                              ctypes.POINTER(ctypes.c_long)]
+        _lib.ref_coverage_aa_tile.restype = ctypes.c_long
     return _lib
 
 
@@ -67,3 +71,21 @@ def stack_blur(rgba, radius):
     if rc != 0:
         raise RuntimeError("ref_stack_blur failed")
     return out
+
+
+def coverage_aa_tile(path, matrix6=(1, 0, 0, 0, 1, 0), scissor=None, tile_cap=1 << 16, line_cap=1 << 20):
+    """The reference's CoverageAAPathTiler + line encoder on one PathData -> (tiles (n, 5) int32: tile_x, tile_y, first
+    line or -1, line count, backdrop; lines (m, 4) uint16 8.8 in encoded order)."""
+    rec = path.encode()
+    m = np.asarray(matrix6, dtype=np.float32)
+    sc = None if scissor is None else np.asarray(scissor, dtype=np.float32)
+    tiles = np.zeros((tile_cap, 5), dtype=np.int32)
+    lines = np.zeros((line_cap, 4), dtype=np.uint16)
+    nl = ctypes.c_long(0)
+    n = lib().ref_coverage_aa_tile(rec, len(rec), m.ctypes.data, None if sc is None else sc.ctypes.data, tiles.ctypes.data,
+                                   tile_cap, lines.ctypes.data, line_cap, ctypes.byref(nl))
+    if n == -1:
+        return coverage_aa_tile(path, matrix6, scissor, tile_cap * 8, line_cap * 8)
+    if n < 0:
+        raise RuntimeError(f"ref_coverage_aa_tile failed: {n}")
+    return tiles[:n].copy(), lines[:nl.value].copy()

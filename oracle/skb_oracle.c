@@ -1005,6 +1005,12 @@ static void raster_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ct
   free(E);
 }
 
+/* Coverage mode of unclipped fills: 0 = the software backend's analytic-AA scan converter (raster_path above), 1 = the
+ * reference's coverage-AA path (tile-binned lines + signed-area accumulation, skb_area_oracle.h) — what the CUDA
+ * backend computes under SKB_COVERAGE_AREA. */
+static int g_coverage_mode = 0;
+#include "skb_area_oracle.h"
+
 /* ------------------------------------------------------- colour and blend */
 /* Colours are kept in the reference's register layout A<<24|R<<16|G<<8|B
  * (include/skity/graphic/color.hpp:34-63); pixels in memory are R,G,B,A bytes. */
@@ -1518,6 +1524,42 @@ static int g_coord_mode = 0;
 SKBO_API void skbo_set_coord_mode(int mode) { g_coord_mode = mode; g_wide = mode == 2; }
 /* rows [y0, y1) of the canvas only (y1 <= y0: the whole canvas); see g_band_y0 */
 SKBO_API void skbo_set_row_band(int y0, int y1) { g_band_y0 = y0; g_band_y1 = y1; }
+/* 0 = software analytic AA (default), 1 = coverage-AA ("AREA") for unclipped fills */
+SKBO_API void skbo_set_coverage_mode(int mode) { g_coverage_mode = mode; }
+
+/* The tiled form of one path in coverage-AA mode, for pinning against the reference's own CoverageAAPathTiler:
+ * tiles_out[i] = tile_x, tile_y, first line, line count, backdrop; lines_out[j] = from_x, from_y, to_x, to_y (8.8), in
+ * range order.  Returns the tile count (negative: capacity exceeded); *n_lines_out = lines written. */
+SKBO_API long skbo_area_tile_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm6, const float* scissor4, int even_odd,
+                                  int32_t* tiles_out, long tile_cap, uint16_t* lines_out, long line_cap, long* n_lines_out) {
+  area_tiler t;
+  if (!area_tile_path(&t, segs, n_segs, ctm6, scissor4)) { area_tiler_free(&t); *n_lines_out = 0; return 0; }
+  area_resolve_backdrops(&t, even_odd);
+  uint32_t* off = (uint32_t*)calloc(t.n_ranges + 1, sizeof(uint32_t));
+  for (size_t i = 0; i < t.n_ranges; i++) off[i + 1] = off[i] + t.range_counts[i];
+  uint32_t* cursor = (uint32_t*)malloc((t.n_ranges + 1) * sizeof(uint32_t));
+  memcpy(cursor, off, (t.n_ranges + 1) * sizeof(uint32_t));
+  long rc = (long)t.n_tiles;
+  if ((long)t.n_tiles > tile_cap || (long)t.n_lines > line_cap) rc = -1;
+  if (rc >= 0) {
+    for (size_t i = 0; i < t.n_lines; i++) {
+      uint16_t* o = lines_out + 4 * (size_t)cursor[t.lines[i].range]++;
+      o[0] = t.lines[i].from_x; o[1] = t.lines[i].from_y; o[2] = t.lines[i].to_x; o[3] = t.lines[i].to_y;
+    }
+    for (size_t i = 0; i < t.n_tiles; i++) {
+      int32_t* o = tiles_out + 5 * i;
+      uint32_t r = t.tiles[i].range;
+      o[0] = t.tiles[i].tile_x; o[1] = t.tiles[i].tile_y;
+      o[2] = r == AREA_NO_RANGE ? -1 : (int32_t)off[r];
+      o[3] = r == AREA_NO_RANGE ? 0 : (int32_t)t.range_counts[r];
+      o[4] = t.tiles[i].backdrop;
+    }
+    *n_lines_out = (long)t.n_lines;
+  }
+  free(off); free(cursor);
+  area_tiler_free(&t);
+  return rc;
+}
 
 SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial, uint8_t* canvas_rgba) {
   if (bytes < sizeof(skb_dl_header)) return -1;
@@ -1554,7 +1596,11 @@ SKBO_API int skbo_render(const uint8_t* dl, size_t bytes, const uint8_t* initial
         spans.n = 0;
         const int banded = g_band_y1 > g_band_y0 && op->surface == 0 && !op->clip_in;
         g_band_skip = banded;
-        raster_path(segs + p->seg_off, p->n_segs, op->ctm, op->clip_bounds, (int)op->fill_type, &spans, NULL);
+        if (g_coverage_mode == 1 && !op->clip_in)
+          area_raster_path(segs + p->seg_off, p->n_segs, op->ctm, op->clip_bounds, (int)op->fill_type, (int)surfs[op->surface].w,
+                           (int)surfs[op->surface].h, &spans);
+        else
+          raster_path(segs + p->seg_off, p->n_segs, op->ctm, op->clip_bounds, (int)op->fill_type, &spans, NULL);
         g_band_skip = 0;
         if (banded) {
           size_t k = 0;
@@ -1644,6 +1690,17 @@ SKBO_API long skbo_raster_path(const skb_dl_seg* segs, uint32_t n_segs, const fl
                                int even_odd, int32_t* spans_out, long cap, float* bounds4) {
   spanvec sv = {0, 0, 0};
   raster_path(segs, n_segs, ctm6, clip4, even_odd, &sv, bounds4);
+  long n = (long)sv.n;
+  for (long i = 0; i < n && i < cap; i++) memcpy(spans_out + 4 * i, &sv.v[i], 16);
+  free(sv.v);
+  return n;
+}
+
+/* Coverage-AA ("AREA") coverage of one path as spans (x, y, len, A8 cover), on a surf_w x surf_h surface. */
+SKBO_API long skbo_area_raster_path(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm6, const float* clip4, int even_odd,
+                                    int surf_w, int surf_h, int32_t* spans_out, long cap) {
+  spanvec sv = {0, 0, 0};
+  area_raster_path(segs, n_segs, ctm6, clip4, even_odd, surf_w, surf_h, &sv);
   long n = (long)sv.n;
   for (long i = 0; i < n && i < cap; i++) memcpy(spans_out + 4 * i, &sv.v[i], 16);
   free(sv.v);
