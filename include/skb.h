@@ -71,6 +71,9 @@ typedef struct skb_frame_stats {
   uint64_t bytes_blur;   /* algorithmic bytes of the blur passes: 2 passes x (4 B read + 4 B write) per temp pixel */
   uint32_t n_rw_retried;     /* paths whose row-parallel sweep was retried (tables not self-consistent at first) */
   uint32_t n_rw_sequential;  /* paths swept by the sequential walker */
+  uint32_t n_area_lines;       /* coverage mode AREA: lines the unclipped fills flattened to */
+  uint32_t n_area_tile_lines;  /* ... and the (line, tile) pairs they were binned to */
+  uint64_t bytes_area;         /* algorithmic bytes of the AREA coverage pass (binned lines in, masks out) */
 } skb_frame_stats;
 
 SKB_API skb_result skb_device_create(int ordinal, skb_device* out_device);
@@ -102,6 +105,19 @@ SKB_API skb_result skb_surface_set_coord_mode(skb_surface surface, int mode);
  *   1  row-parallel: one thread per (path, pixel row), chords chained through per-path band tables, bit-identical
  *      trapezoid records (skity_b200/csrc/skb_rowwalk.cuh); paths it cannot settle are swept as in mode 0. */
 SKB_API skb_result skb_surface_set_walk_mode(skb_surface surface, int mode);
+
+/* How the coverage of UNCLIPPED fills is computed (clip paths and clipped draws always take the exact route):
+ *   SKB_COVERAGE_EXACT  (default) the software backend's analytic-AA scan converter, reproduced bit for bit
+ *                       (src/render/sw/sw_raster.cc): flatten to 16.16 edges, sweep, trapezoid rows -> A8 masks;
+ *   SKB_COVERAGE_AREA   the algorithm of the reference's GPU coverage-AA path (src/render/hw/coverage/
+ *                       coverage_aa_tiler.cc, wgsl_coverage_aa_common.hpp): curves flattened by Wang's formula, lines
+ *                       binned to 16x16 tiles with backdrop deltas, per-tile signed-area accumulation, backdrop prefix
+ *                       sums — fully parallel.  Its A8 coverage equals that algorithm's (bit-exact against the oracle's
+ *                       restatement and the reference's exact-match golden canonical_edges_exact.png); it is NOT the
+ *                       software backend's coverage: edge pixels differ (tests/ and DESIGN.md give the histogram). */
+#define SKB_COVERAGE_EXACT 0
+#define SKB_COVERAGE_AREA 1
+SKB_API skb_result skb_surface_set_coverage_mode(skb_surface surface, int mode);
 
 /* clear != 0 zeroes the surface (transparent black), like LockCanvas(true). */
 SKB_API skb_result skb_frame_begin(skb_surface surface, int clear);

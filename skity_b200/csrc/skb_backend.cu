@@ -24,6 +24,7 @@
 #include "skity_b200/csrc/skb_clip.cuh"
 #include "skity_b200/csrc/skb_stages.cuh"
 #include "skity_b200/csrc/skb_rowwalk.cuh"
+#include "skity_b200/csrc/skb_area.cuh"
 
 namespace skb {
 
@@ -140,7 +141,7 @@ struct FrameTables {
 // of their extent (a quad's control point from Cubic::ToQuads is (3(c1'+c2') - (p0'+p3'))/4 with all four inside the
 // control polygon's bounds), so a path whose control points' y range, widened by half its height plus 2 px, misses the
 // band gets no primitives at all (`culled`: k_seg_count counts 0 for its segments).  Clip paths are never culled.
-__global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op, const SurfDesc* surfs) {
+__global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op, const SurfDesc* surfs, int area_mode) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   OpGeom g;
@@ -153,12 +154,26 @@ __global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op, const S
     const skb_dl_path p = t.paths[o.path];
     const SurfDesc sd = surfs[o.surface];
     const bool banded = o.kind == SKB_OP_FILL && (sd.row0 > 0 || sd.row1 < sd.h);
+    // coverage mode AREA (skb_surface_set_coverage_mode): unclipped fills are binned as lines and never swept; their
+    // bounds are those of the transformed path's points (Path::GetBounds in CoverageAAPathTiler::Tile)
+    const bool area = area_mode != 0 && o.kind == SKB_OP_FILL && o.clip_in == 0;
+    g.area = area ? 1u : 0u;
     float ymin = 3.0e38f, ymax = -3.0e38f;
     bool all_finite = true;
     for (uint32_t i = 0; i < p.n_segs; i++) {
       uint32_t s = p.seg_off + i;
       seg_op[s] = op;
       const uint32_t type = t.segs[s].type_flags & SKB_SEG_TYPE_MASK;
+      if (area && type != SKB_SEG_POINT) {
+        const skb_dl_seg& sg = t.segs[s];
+        const int last = (type == SKB_SEG_LINE || type == SKB_SEG_CLOSE) ? 1 : type == SKB_SEG_CUBIC ? 3 : 2;
+        for (int k = 0; k <= last; k++) {
+          const V2 q = xform(o.ctm, v2(sg.p[2 * k], sg.p[2 * k + 1]));
+          const int32_t kx = float_key(q.x), ky = float_key(q.y);
+          g.bmin_x = min(g.bmin_x, kx); g.bmax_x = max(g.bmax_x, kx);
+          g.bmin_y = min(g.bmin_y, ky); g.bmax_y = max(g.bmax_y, ky);
+        }
+      }
       if (banded) {
         const skb_dl_seg& sg = t.segs[s];
         int first = 1, last = 0;  // control points p[2*first .. 2*last+1]; p[0..1] repeats the start point
@@ -196,7 +211,8 @@ __global__ void k_op_init(FrameTables t, OpGeom* geom, uint32_t* seg_op, const S
 __global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt, const uint32_t* seg_op, const OpGeom* geom) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= t.n_segs) return;
-  prim_cnt[s] = geom[seg_op[s]].culled ? 0u : (uint32_t)seg_prim_count(t.segs[s]);
+  const OpGeom& g = geom[seg_op[s]];
+  prim_cnt[s] = (g.culled || g.area) ? 0u : (uint32_t)seg_prim_count(t.segs[s]);
 }
 
 // One thread per lowered primitive: resolve (segment, k) from the scanned counts, evaluate and
@@ -341,6 +357,7 @@ __global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, 
     uint32_t* o = trow_op + row_base[op] / SKB_TILE;
     for (int r = 0; r < g.nty; r++) o[r] = op;
   }
+  if (g.area) return;   // coverage mode AREA: binned as lines (k_area_*), not swept
   if (rwops) {   // row-parallel walk: where the op's walk rows are, and who owns each group of 16 of them
     const uint32_t wb = wrow_base[op], we = wrow_base[op + 1];
     rwops[op].wrow_base = wb;
@@ -989,6 +1006,248 @@ __global__ void COVER_BOUNDS k_cover(CoverArgs c) {
         uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
         atomicAdd(&c.tile_cnt[tile], (flags & SKB_ITEM_PLANE1) ? 2u : 1u);
       }
+    }
+  }
+}
+
+// ------------------------------------------------ stages 2-3, coverage mode AREA (skb_area.cuh)
+// Unclipped fills under SKB_COVERAGE_AREA take this route instead of walk + k_cover: lines are flattened and binned to
+// (op, tile) items, the backdrop deltas are prefix-summed along each tile row, and one warp per tile row accumulates
+// the signed areas of each tile's lines into the same A8 masks / item flags k_cover writes.
+struct AreaArgs {
+  FrameTables t;
+  const OpGeom* geom;
+  const uint32_t* seg_op;
+  const uint32_t* line_off;    // n_segs + 1: first global line of every segment (scanned k_area_seg_count)
+  uint32_t n_lines;
+  uint32_t* item_cnt;          // n_items + 1: lines binned to the item; scanned in place into item offsets
+  uint32_t* item_cursor;       // n_items: write cursors of the second binning pass
+  int32_t* item_local;         // n_items: local backdrop; k_area_backdrop turns it into the tile's backdrop
+  int32_t* item_delta;         // n_items: backdrop delta applied to the tiles on the right
+  int32_t* row_backdrop;       // n_trows: crossings left of the op's tile rectangle
+  uint4* lines;                // binned lines: from_x | from_y << 16, to_x | to_y << 16 (8.8), key, 0
+  CoverArgs c;
+};
+
+__global__ void k_area_seg_count(AreaArgs a, uint32_t* cnt) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.t.n_segs) return;
+  const uint32_t op = a.seg_op[s];
+  const OpGeom& g = a.geom[op];
+  cnt[s] = (g.area && !g.culled) ? (uint32_t)area_seg_line_count(a.t.segs[s], a.t.ops[op].ctm) : 0u;
+}
+
+struct AreaBinSink {
+  int tx0, ty0, ntx, nty;
+  uint32_t item_base, trow_base, key;
+  bool write;
+  const AreaArgs* a;
+  __device__ __forceinline__ void line(V2 p, V2 q, int tx, int ty, int aux) {
+    const int dx = tx - tx0, dy = ty - ty0;
+    if (dx < 0 || dy < 0 || dx >= ntx || dy >= nty) return;   // CoverageAATileRect::Contains
+    uint32_t w0 = 0, w1 = 0;
+    int local = 0;
+    const int kind = area_tile_line(p, q, tx, ty, &w0, &w1, &local);
+    if (kind == 0) return;
+    const uint32_t item = item_base + (uint32_t)(dy * ntx + dx);
+    if (kind == 2) {
+      if (!write) atomicAdd(&a->item_local[item], local);
+      return;
+    }
+    if (!write) {
+      atomicAdd(&a->item_cnt[item], 1u);
+    } else {
+      const uint32_t pos = a->item_cnt[item] + atomicAdd(&a->item_cursor[item], 1u);
+      a->lines[pos] = make_uint4(w0, w1, key | (uint32_t)aux, 0u);
+    }
+  }
+  __device__ __forceinline__ void backdrop(int tx, int ty, int delta) {
+    if (write) return;
+    const int dx = tx - tx0, dy = ty - ty0;
+    if (dy < 0 || dy >= nty || dx >= ntx) return;
+    if (dx < 0) atomicAdd(&a->row_backdrop[trow_base + (uint32_t)dy], delta);
+    else atomicAdd(&a->item_delta[item_base + (uint32_t)(dy * ntx + dx)], delta);
+  }
+};
+
+// One thread per flattened line, run twice: pass 0 counts the lines of every item and accumulates the backdrops (integer
+// atomics: order-independent), pass 1 writes the lines behind the scanned offsets.  The key (global line number, auxiliary
+// bit) is the order the reference's sequential tiler would have emitted them in.
+__global__ void k_area_bin(AreaArgs a, int write) {
+  uint32_t ln = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ln >= a.n_lines) return;
+  const uint32_t seg = find_interval(a.line_off, a.t.n_segs, ln);
+  const int k = (int)(ln - a.line_off[seg]);
+  const int n = (int)(a.line_off[seg + 1] - a.line_off[seg]);
+  const uint32_t op = a.seg_op[seg];
+  const OpGeom& g = a.geom[op];
+  if (g.empty || g.ntx <= 0 || g.nty <= 0) return;
+  V2 from, to;
+  area_seg_line(a.t.segs[seg], a.t.ops[op].ctm, k, n, &from, &to);
+  if (!(finite_f(from.x) && finite_f(from.y) && finite_f(to.x) && finite_f(to.y))) return;
+  AreaBinSink sink;
+  sink.tx0 = g.tx0;
+  sink.ty0 = g.ty0;
+  sink.ntx = g.ntx;
+  sink.nty = g.nty;
+  sink.item_base = a.c.item_base[op];
+  sink.trow_base = a.c.row_base[op] / SKB_TILE;
+  sink.key = ln << 1;
+  sink.write = write != 0;
+  sink.a = &a;
+  area_walk_line(from, to, sink);
+}
+
+// ResolveBackdrops: one thread per tile row of an AREA op.
+__global__ void k_area_backdrop(AreaArgs a) {
+  uint32_t trow = blockIdx.x * blockDim.x + threadIdx.x;
+  if (trow >= a.c.n_trows) return;
+  const uint32_t op = a.c.trow_op[trow];
+  const OpGeom& g = a.geom[op];
+  if (!g.area) return;
+  const uint32_t tr = trow - a.c.row_base[op] / SKB_TILE;
+  const uint32_t item0 = a.c.item_base[op] + tr * (uint32_t)g.ntx;
+  int acc = a.row_backdrop[trow];
+  for (int x = 0; x < g.ntx; x++) {
+    const int b = acc + a.item_local[item0 + x];
+    acc += a.item_delta[item0 + x];
+    a.item_local[item0 + x] = b;
+  }
+}
+
+#define AREA_WARPS 4
+#define AREA_CAP 128               // lines of a tile held in shared memory at a time
+struct alignas(16) AreaWarpSmem {
+  AreaLine line[AREA_CAP];
+  uint32_t key[AREA_CAP];
+};
+
+// One warp per (op, tile row); tiles left to right.  A tile's lines are put in key order (rank sort in shared memory; a
+// tile with more than AREA_CAP lines is first sorted in place in global memory by selection, then streamed), unpacked
+// once, and every lane accumulates the windings of its 8 pixels (lane -> pixel row lane >> 1, half lane & 1) over the
+// lines that reach its pixel row.
+__global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
+  __shared__ AreaWarpSmem sm_all[AREA_WARPS];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t trow = blockIdx.x * AREA_WARPS + wib;
+  if (trow >= a.c.n_trows) return;
+  const uint32_t op = a.c.trow_op[trow];
+  const OpGeom g = a.geom[op];
+  if (!g.area || g.empty || g.ntx <= 0) return;
+  AreaWarpSmem& sm = sm_all[wib];
+  const skb_dl_op& o = a.c.ops[op];
+  const SurfDesc sd = a.c.surfs[o.surface];
+  const uint32_t tr = trow - a.c.row_base[op] / SKB_TILE;
+  const int ty = g.ty0 + (int)tr;
+  const int even_odd = (int)o.fill_type;
+  const int xmin = max(g.scan_l, 0), xmax = min(g.scan_r, (int)sd.w);
+  const int ymin = max(g.scan_t, 0), ymax = min(g.scan_b, (int)sd.h);
+  const int prow = lane >> 1, half = lane & 1;
+  const int y = ty * SKB_TILE + prow;
+  const bool row_in = y >= ymin && y < ymax;
+  const float pixel_top = (float)prow, pixel_bottom = (float)prow + 1.0f;
+  const uint32_t item_row = a.c.item_base[op] + tr * (uint32_t)g.ntx;
+  for (int txi = 0; txi < g.ntx; txi++) {
+    const uint32_t item = item_row + (uint32_t)txi;
+    const uint32_t beg = a.item_cnt[item];
+    const int n = (int)(a.item_cnt[item + 1] - beg);
+    const int backdrop = a.item_local[item];
+    const int x0 = (g.tx0 + txi) * SKB_TILE + half * 8;
+    uint32_t inmask = 0;   // bit i: pixel i of this lane's 8 lies in the scan rectangle
+#pragma unroll
+    for (int i = 0; i < 8; i++) inmask |= (row_in && x0 + i >= xmin && x0 + i < xmax) ? 1u << i : 0u;
+    uint32_t d0 = 0, d1 = 0;
+    if (n == 0) {
+      const uint32_t v = area_alpha_u8(area_resolve_alpha((float)backdrop, even_odd));
+      if (v == 0) continue;   // uniform over the warp
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        d0 |= ((inmask >> i) & 1u) ? v << (8 * i) : 0u;
+        d1 |= ((inmask >> (4 + i)) & 1u) ? v << (8 * i) : 0u;
+      }
+    } else {
+      if (n > AREA_CAP) {
+        // in-place selection sort by key (rare: more lines in one 16x16 tile than the shared-memory window holds)
+        for (int i = 0; i < n - 1; i++) {
+          uint32_t best = 0xFFFFFFFFu;
+          int best_j = i;
+          for (int j = i + lane; j < n; j += 32) {
+            const uint32_t kj = a.lines[beg + j].z;
+            if (kj < best) { best = kj; best_j = j; }
+          }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) {
+            const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+            if (ob < best) { best = ob; best_j = oj; }
+          }
+          if (lane == 0 && best_j != i) {
+            const uint4 t0 = a.lines[beg + i];
+            a.lines[beg + i] = a.lines[beg + best_j];
+            a.lines[beg + best_j] = t0;
+          }
+          __syncwarp();
+        }
+      }
+      float w[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) w[i] = (float)backdrop;
+      for (int c0 = 0; c0 < n; c0 += AREA_CAP) {
+        const int m = min(AREA_CAP, n - c0);
+        __syncwarp();
+        if (n <= AREA_CAP) {
+          uint4 mine[AREA_CAP / 32];
+#pragma unroll
+          for (int q = 0; q < AREA_CAP / 32; q++) {
+            const int j = lane + 32 * q;
+            if (j < m) {
+              mine[q] = a.lines[beg + j];
+              sm.key[j] = mine[q].z;
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < AREA_CAP / 32; q++) {
+            const int j = lane + 32 * q;
+            if (j < m) {
+              int rank = 0;
+              for (int i = 0; i < m; i++) rank += sm.key[i] < mine[q].z ? 1 : 0;
+              sm.line[rank] = area_line_unpack(mine[q].x, mine[q].y);
+            }
+          }
+        } else {
+          for (int j = lane; j < m; j += 32) {
+            const uint4 l = a.lines[beg + c0 + j];
+            sm.line[j] = area_line_unpack(l.x, l.y);
+          }
+        }
+        __syncwarp();
+        for (int k = 0; k < m; k++) {
+          const AreaLine& l = sm.line[k];
+          const float y_min = l.edge_top < pixel_top ? pixel_top : l.edge_top;
+          const float y_max = l.edge_bottom < pixel_bottom ? l.edge_bottom : pixel_bottom;
+          if (y_min >= y_max) continue;
+          const AreaLine lv = l;
+#pragma unroll
+          for (int i = 0; i < 8; i++) w[i] = w[i] + area_edge_contribution(lv, (float)(half * 8 + i), y_min, y_max);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        d0 |= ((inmask >> i) & 1u) ? area_alpha_u8(area_resolve_alpha(w[i], even_odd)) << (8 * i) : 0u;
+        d1 |= ((inmask >> (4 + i)) & 1u) ? area_alpha_u8(area_resolve_alpha(w[4 + i], even_odd)) << (8 * i) : 0u;
+      }
+    }
+    const bool any = __any_sync(0xffffffffu, (d0 | d1) != 0);
+    if (!any) continue;
+    const bool solid = __all_sync(0xffffffffu, (d0 & d1) == 0xFFFFFFFFu);
+    uint32_t flags = SKB_ITEM_PLANE0;
+    if (solid) flags |= SKB_ITEM_SOLID;
+    else reinterpret_cast<uint2*>(a.c.mask0 + (size_t)item * 256)[lane] = make_uint2(d0, d1);
+    if (lane == 0) {
+      a.c.item_flags[item] = (uint16_t)flags;
+      const uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)(g.tx0 + txi);
+      atomicAdd(&a.c.tile_cnt[tile], 1u);
     }
   }
 }
@@ -1808,6 +2067,7 @@ struct skb_surface_s {
   uint32_t band_y0 = 0, band_y1 = 0;
   int coord_mode = SKB_COORD_AUTO;
   int walk_mode = 0;
+  int coverage_mode = SKB_COVERAGE_EXACT;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[12] = {};
   // host-mapped words the device writes counts into: reading them does not queue behind another
@@ -1830,6 +2090,7 @@ struct skb_surface_s {
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
+  Buf area_line_cnt, area_item_cnt, area_item_cursor, area_item_local, area_item_delta, area_row_backdrop, area_lines;
   Buf rw_chord_cnt, rw_slot_op, rw_slots, rw_rank, rw_ops, rw_wrow_cnt, rw_rec_cnt, rw_chords, rw_wgrp_op, rw_ev, rw_tab, rw_res, rw_rec_off;
   Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
@@ -2162,18 +2423,45 @@ static skb_result run_frame(skb_surface s) {
   cudaEventRecord(s->ev[0], st);
   // ---- stage 1: flatten
   SKB_CUDA(cudaMemsetAsync(seg_op, 0, (size_t)(n_segs + 1) * 4, st));  // segments no op refers to count as op 0's (validate_dl rejects such lists)
-  k_op_init<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, seg_op, (const SurfDesc*)s->surfs.p);
+  // coverage mode (skb_surface_set_coverage_mode / SKB_COVERAGE_MODE): AREA sends the unclipped fills through
+  // k_area_* (tile-binned lines, signed-area accumulation) instead of flatten-to-edges + walk + k_cover
+  const bool area_mode = getenv("SKB_COVERAGE_MODE") ? atoi(getenv("SKB_COVERAGE_MODE")) == SKB_COVERAGE_AREA
+                                                      : s->coverage_mode == SKB_COVERAGE_AREA;
+  k_op_init<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, seg_op, (const SurfDesc*)s->surfs.p, area_mode ? 1 : 0);
   launches++;
-  uint32_t n_prims = 0;
+  uint32_t n_prims = 0, n_area_lines = 0;
+  AreaArgs aa;
+  memset(&aa, 0, sizeof(aa));
   if (n_segs) {
     SKB_CUDA(cudaMemsetAsync(prim_off + n_segs, 0, 4, st));
     k_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(t, prim_off, seg_op, geom);
     launches++;
     SKB_TRY(scan_exclusive(s, prim_off, n_segs + 1, &launches));
-    SKB_TRY(fetch_words(s, &n_prims, prim_off + n_segs, 1));
-    launches++;
+    uint32_t two[2] = {0, 0};
+    if (area_mode) {
+      SKB_TRY(buf_reserve(s->area_line_cnt, (size_t)(n_segs + 1) * 4));
+      uint32_t* line_off = (uint32_t*)s->area_line_cnt.p;
+      aa.t = t;
+      aa.geom = geom;
+      aa.seg_op = seg_op;
+      aa.line_off = line_off;
+      SKB_CUDA(cudaMemsetAsync(line_off + n_segs, 0, 4, st));
+      k_area_seg_count<<<cdiv(n_segs, 256), 256, 0, st>>>(aa, line_off);
+      launches++;
+      SKB_TRY(scan_exclusive(s, line_off, n_segs + 1, &launches));
+      k_gather5<<<1, 32, 0, st>>>(counters + 8, prim_off + n_segs, line_off + n_segs, counters + 6, nullptr, nullptr);
+      SKB_TRY(fetch_words(s, two, counters + 8, 2));
+      launches += 2;
+    } else {
+      SKB_TRY(fetch_words(s, two, prim_off + n_segs, 1));
+      launches++;
+    }
+    n_prims = two[0];
+    n_area_lines = two[1];
   }
   S.n_prims = n_prims;
+  S.n_area_lines = n_area_lines;
+  S.n_area_tile_lines = 0;
   const size_t n_slots = (size_t)2 * n_prims + (size_t)2 * n_ops + 2;
   S.n_edges_slots = (uint32_t)n_slots;
   SKB_TRY(buf_reserve(s->edges, n_slots * (sizeof(Edge) + sizeof(QuadState))));
@@ -2241,12 +2529,13 @@ static skb_result run_frame(skb_surface s) {
       s->n_items = (uint32_t)n_items;
       uint64_t want = 2 * n_rows + (uint64_t)SKB_CHUNK * 2 * n_ops + 4096;
       if (rowwalk) want = 2 * n_rows + n_rows / 4 + 65536;   // linear records; chunks only for the few paths swept sequentially
+      if (area_mode && n_prims == 0) want = 4096;   // every draw took the AREA route: nothing is swept
       if (want > 0x7FFFFFF0ull) want = 0x7FFFFFF0ull;
       pool_cap = (uint32_t)want;
       SKB_TRY(buf_reserve(s->rows, (n_rows + 1) * sizeof(uint2)));
       SKB_TRY(buf_reserve(s->trow_op, (n_rows / SKB_TILE + 1) * 4));
       SKB_TRY(buf_reserve(s->mask0, (n_items + 1) * 256));
-      SKB_TRY(buf_reserve(s->mask1, (n_items + 1) * 256));
+      SKB_TRY(buf_reserve(s->mask1, (area_mode && n_prims == 0) ? 256 : (n_items + 1) * 256));   // AREA coverage is one plane
       SKB_TRY(buf_reserve(s->item_flags, 2 * n_items + 16));
       SKB_TRY(buf_reserve(s->tile_cnt, (size_t)(n_tiles + 1) * 4));
       SKB_TRY(buf_reserve(s->tile_fill, (size_t)(n_tiles + 1) * 4));
@@ -2442,8 +2731,45 @@ static skb_result run_frame(skb_surface s) {
   SKB_CUDA(cudaMemsetAsync(s->tile_fill.p, 0, (size_t)(n_tiles + 1) * 4, st));
   if (n_items) {
     SKB_CUDA(cudaMemsetAsync(s->item_flags.p, 0, 2 * n_items, st));
-    k_cover<<<cdiv(ca.n_trows, COVER_WARPS), COVER_WARPS * 32, 0, st>>>(ca);
+    if (!area_mode || n_prims) {   // nothing was swept when every draw took the AREA route
+      k_cover<<<cdiv(ca.n_trows, COVER_WARPS), COVER_WARPS * 32, 0, st>>>(ca);
+      launches++;
+    }
+  }
+  if (area_mode && n_area_lines && n_items) {
+    // ---- stages 2-3 of the AREA mode: bin the lines (count, scan, write), resolve the backdrops, accumulate
+    const uint32_t n_trows = ca.n_trows;
+    SKB_TRY(buf_reserve(s->area_item_cnt, (n_items + 1) * 4));
+    SKB_TRY(buf_reserve(s->area_item_cursor, (n_items + 1) * 4));
+    SKB_TRY(buf_reserve(s->area_item_local, (n_items + 1) * 4));
+    SKB_TRY(buf_reserve(s->area_item_delta, (n_items + 1) * 4));
+    SKB_TRY(buf_reserve(s->area_row_backdrop, ((size_t)n_trows + 1) * 4));
+    aa.n_lines = n_area_lines;
+    aa.item_cnt = (uint32_t*)s->area_item_cnt.p;
+    aa.item_cursor = (uint32_t*)s->area_item_cursor.p;
+    aa.item_local = (int32_t*)s->area_item_local.p;
+    aa.item_delta = (int32_t*)s->area_item_delta.p;
+    aa.row_backdrop = (int32_t*)s->area_row_backdrop.p;
+    aa.lines = nullptr;
+    aa.c = ca;
+    SKB_CUDA(cudaMemsetAsync(aa.item_cnt, 0, (n_items + 1) * 4, st));
+    SKB_CUDA(cudaMemsetAsync(aa.item_cursor, 0, (n_items + 1) * 4, st));
+    SKB_CUDA(cudaMemsetAsync(aa.item_local, 0, (n_items + 1) * 4, st));
+    SKB_CUDA(cudaMemsetAsync(aa.item_delta, 0, (n_items + 1) * 4, st));
+    SKB_CUDA(cudaMemsetAsync(aa.row_backdrop, 0, ((size_t)n_trows + 1) * 4, st));
+    k_area_bin<<<cdiv(n_area_lines, 128), 128, 0, st>>>(aa, 0);
     launches++;
+    SKB_TRY(scan_exclusive(s, aa.item_cnt, (uint32_t)n_items + 1, &launches));
+    uint32_t n_tile_lines = 0;
+    SKB_TRY(fetch_words(s, &n_tile_lines, aa.item_cnt + n_items, 1));
+    launches++;
+    S.n_area_tile_lines = n_tile_lines;
+    SKB_TRY(buf_reserve(s->area_lines, ((size_t)n_tile_lines + 1) * sizeof(uint4)));
+    aa.lines = (uint4*)s->area_lines.p;
+    k_area_bin<<<cdiv(n_area_lines, 128), 128, 0, st>>>(aa, 1);
+    k_area_backdrop<<<cdiv(n_trows, 128), 128, 0, st>>>(aa);
+    k_area_cover<<<cdiv(n_trows, AREA_WARPS), AREA_WARPS * 32, 0, st>>>(aa);
+    launches += 3;
   }
   cudaEventRecord(s->ev[9], st);
   if (has_clip_ops && n_rows) {
@@ -2675,6 +3001,8 @@ static skb_result run_frame(skb_surface s) {
   uint64_t band_px = (uint64_t)(surfs[0].row1 - surfs[0].row0) * s->w;
   S.bytes_fine = band_px * 8 + (uint64_t)n_cmds * (8 + 256);
   S.bytes_cover = S.n_records * 32 + (uint64_t)n_cmds * 256;
+  // AREA coverage pass (k_area_cover): 16 B per binned line in, 4 B backdrop per item in, 256 B per non-empty mask out
+  S.bytes_area = (uint64_t)S.n_area_tile_lines * 16 + (area_mode ? n_items * 4 + (uint64_t)n_cmds * 256 : 0);
   S.bytes_walk = (uint64_t)S.n_edges_slots * (sizeof(Edge) + sizeof(QuadState)) + S.n_records * 32 + S.n_rows * 8;
   if (rowwalk) S.bytes_walk += n_chords * sizeof(Chord) * 2 + n_wrows * (sizeof(RowBand) + 8);  // chords written once and read by the rows; band table, row results
   S.bytes_blur = 0;
@@ -2762,7 +3090,8 @@ void skb_surface_destroy(skb_surface s) {
   if (!s) return;
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  Buf* bufs[] = {&s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
+  Buf* bufs[] = {&s->area_line_cnt, &s->area_item_cnt, &s->area_item_cursor, &s->area_item_local, &s->area_item_delta, &s->area_row_backdrop, &s->area_lines,
+                 &s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};
@@ -2801,6 +3130,12 @@ skb_result skb_surface_set_band(skb_surface s, uint32_t y0, uint32_t y1) {
 skb_result skb_surface_set_coord_mode(skb_surface s, int mode) {
   if (!s || mode < SKB_COORD_AUTO || mode > SKB_COORD_WIDE) return SKB_ERROR_INVALID_ARGUMENT;
   s->coord_mode = mode;
+  return SKB_SUCCESS;
+}
+
+skb_result skb_surface_set_coverage_mode(skb_surface s, int mode) {
+  if (!s || (mode != SKB_COVERAGE_EXACT && mode != SKB_COVERAGE_AREA)) return SKB_ERROR_INVALID_ARGUMENT;
+  s->coverage_mode = mode;
   return SKB_SUCCESS;
 }
 

@@ -51,7 +51,8 @@ struct OpGeom {
   uint32_t color;                          // SOLID paints: premultiplied colour, A<<24|R<<16|G<<8|B
   uint32_t fast_solid;                     // SOLID paint blended kSrcOver: the fine pass needs nothing but `color`
   uint32_t culled;                         // the draw cannot reach this device's band: it was given no primitives (k_op_init)
-  uint32_t pad0;
+  uint32_t area;                           // coverage mode AREA takes this draw (an unclipped fill): no edges, no sweep; its
+                                           // bounds are those of its transformed control points (skb_area.cuh)
 };
 static_assert(offsetof(OpGeom, color) % 8 == 0 && sizeof(OpGeom) % 8 == 0, "the fine pass loads (color, fast_solid) as one 64-bit word");
 

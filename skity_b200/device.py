@@ -21,7 +21,8 @@ class FrameStats(ctypes.Structure):
                 ("n_launches", ctypes.c_uint32), ("n_retries", ctypes.c_uint32),
                 ("ms_total", ctypes.c_float), ("ms_stage", ctypes.c_float * 8),
                 ("bytes_fine", ctypes.c_uint64), ("bytes_cover", ctypes.c_uint64), ("bytes_walk", ctypes.c_uint64),
-                ("bytes_blur", ctypes.c_uint64), ("n_rw_retried", ctypes.c_uint32), ("n_rw_sequential", ctypes.c_uint32)]
+                ("bytes_blur", ctypes.c_uint64), ("n_rw_retried", ctypes.c_uint32), ("n_rw_sequential", ctypes.c_uint32),
+                ("n_area_lines", ctypes.c_uint32), ("n_area_tile_lines", ctypes.c_uint32), ("bytes_area", ctypes.c_uint64)]
 
     def as_dict(self):
         d = {}
@@ -58,6 +59,7 @@ def lib():
         L.skb_surface_set_band.argtypes = [vp, u32, u32]
         L.skb_surface_set_coord_mode.argtypes = [vp, ctypes.c_int]
         L.skb_surface_set_walk_mode.argtypes = [vp, ctypes.c_int]
+        L.skb_surface_set_coverage_mode.argtypes = [vp, ctypes.c_int]
         L.skb_frame_begin.argtypes = [vp, ctypes.c_int]
         L.skb_frame_encode.argtypes = [vp, vp, sz]
         L.skb_frame_flush.argtypes = [vp]
@@ -127,6 +129,10 @@ class Surface:
     def set_walk_mode(self, mode):
         """0 the sequential sweep (one thread per path), 1 the row-parallel sweep (same records)."""
         _check(lib().skb_surface_set_walk_mode(self._h, int(mode)), "skb_surface_set_walk_mode")
+
+    def set_coverage_mode(self, mode):
+        """0 exact (the software backend's analytic AA, default), 1 AREA (tile-binned signed-area coverage)."""
+        _check(lib().skb_surface_set_coverage_mode(self._h, int(mode)), "skb_surface_set_coverage_mode")
 
     def begin(self, clear=True):
         _check(lib().skb_frame_begin(self._h, 1 if clear else 0), "skb_frame_begin")

@@ -587,3 +587,109 @@ extern "C" int sim_rowwalk_check(const skb_dl_seg* segs, uint32_t n_segs, const 
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coverage mode AREA (skb_area.cuh): the device stages k_area_seg_count / k_area_bin / k_area_backdrop / k_area_cover
+// on one path, thread by thread in an arbitrary (here: reversed) order — binning must not depend on it.
+#include <algorithm>
+#include <map>
+
+#include "skity_b200/csrc/skb_area.cuh"
+
+namespace {
+struct SimAreaLine { uint32_t w0, w1, key; };
+struct SimAreaSink {
+  int tx0, ty0, ntx, nty;
+  uint32_t key;
+  std::vector<std::vector<SimAreaLine>>* items;
+  std::vector<int>* local;
+  std::vector<int>* delta;
+  std::vector<int>* row_backdrop;
+  void line(V2 p, V2 q, int tx, int ty, int aux) {
+    const int dx = tx - tx0, dy = ty - ty0;
+    if (dx < 0 || dy < 0 || dx >= ntx || dy >= nty) return;
+    uint32_t w0 = 0, w1 = 0;
+    int lc = 0;
+    const int kind = area_tile_line(p, q, tx, ty, &w0, &w1, &lc);
+    if (kind == 0) return;
+    const size_t item = (size_t)dy * ntx + dx;
+    if (kind == 2) { (*local)[item] += lc; return; }
+    (*items)[item].push_back(SimAreaLine{w0, w1, key | (uint32_t)aux});
+  }
+  void backdrop(int tx, int ty, int d) {
+    const int dx = tx - tx0, dy = ty - ty0;
+    if (dy < 0 || dy >= nty || dx >= ntx) return;
+    if (dx < 0) (*row_backdrop)[dy] += d;
+    else (*delta)[(size_t)dy * ntx + dx] += d;
+  }
+};
+}  // namespace
+
+extern "C" {
+// cover: surf_w * surf_h bytes, pre-zeroed.  stats[0] = lines, stats[1] = binned (line, tile) pairs.  Returns 0.
+int sim_area_cover(const skb_dl_seg* segs, uint32_t n_segs, const float* ctm, const float* clip, int even_odd, int surf_w,
+                   int surf_h, uint8_t* cover, int64_t* stats) {
+  OpGeom g;
+  std::memset(&g, 0, sizeof(g));
+  g.bmin_x = g.bmin_y = INT_MAX;
+  g.bmax_x = g.bmax_y = INT_MIN;
+  bool have = false;
+  for (uint32_t i = 0; i < n_segs; i++) {   // k_op_init, area branch (+ the POINT rule)
+    const uint32_t type = segs[i].type_flags & SKB_SEG_TYPE_MASK;
+    int last = (type == SKB_SEG_LINE || type == SKB_SEG_CLOSE) ? 1 : type == SKB_SEG_CUBIC ? 3 : 2;
+    V2 pts[4];
+    int np = 0;
+    if (type == SKB_SEG_POINT) pts[np++] = xform(ctm, seg_start_point(segs, i));
+    else for (int k = 0; k <= last; k++) pts[np++] = xform(ctm, v2(segs[i].p[2 * k], segs[i].p[2 * k + 1]));
+    for (int k = 0; k < np; k++) {
+      have = true;
+      const int32_t kx = float_key(pts[k].x), ky = float_key(pts[k].y);
+      g.bmin_x = std::min(g.bmin_x, kx); g.bmax_x = std::max(g.bmax_x, kx);
+      g.bmin_y = std::min(g.bmin_y, ky); g.bmax_y = std::max(g.bmax_y, ky);
+    }
+  }
+  op_setup(g, clip, (uint32_t)surf_w, (uint32_t)surf_h, have);
+  stats[0] = stats[1] = 0;
+  if (g.empty || g.ntx <= 0 || g.nty <= 0) return 0;
+  std::vector<uint32_t> line_off(n_segs + 1, 0);
+  for (uint32_t i = 0; i < n_segs; i++) line_off[i + 1] = line_off[i] + (uint32_t)area_seg_line_count(segs[i], ctm);
+  const uint32_t n_lines = line_off[n_segs];
+  stats[0] = n_lines;
+  std::vector<std::vector<SimAreaLine>> items((size_t)g.ntx * g.nty);
+  std::vector<int> local(items.size(), 0), delta(items.size(), 0), row_backdrop((size_t)g.nty, 0);
+  for (uint32_t r = 0; r < n_lines; r++) {
+    const uint32_t ln = n_lines - 1 - r;   // any order
+    const uint32_t seg = (uint32_t)(std::upper_bound(line_off.begin(), line_off.end(), ln) - line_off.begin()) - 1;
+    V2 from, to;
+    area_seg_line(segs[seg], ctm, (int)(ln - line_off[seg]), (int)(line_off[seg + 1] - line_off[seg]), &from, &to);
+    if (!(finite_f(from.x) && finite_f(from.y) && finite_f(to.x) && finite_f(to.y))) continue;
+    SimAreaSink sink{g.tx0, g.ty0, g.ntx, g.nty, ln << 1, &items, &local, &delta, &row_backdrop};
+    area_walk_line(from, to, sink);
+  }
+  const int xmin = std::max(g.scan_l, 0), xmax = std::min(g.scan_r, surf_w);
+  const int ymin = std::max(g.scan_t, 0), ymax = std::min(g.scan_b, surf_h);
+  for (int tr = 0; tr < g.nty; tr++) {
+    int acc = row_backdrop[tr];
+    for (int txi = 0; txi < g.ntx; txi++) {
+      const size_t item = (size_t)tr * g.ntx + txi;
+      const int backdrop = acc + local[item];
+      acc += delta[item];
+      auto& v = items[item];
+      stats[1] += (int64_t)v.size();
+      std::sort(v.begin(), v.end(), [](const SimAreaLine& a, const SimAreaLine& b) { return a.key < b.key; });
+      std::vector<uint32_t> words(v.size() * 2 + 2);
+      for (size_t k = 0; k < v.size(); k++) { words[2 * k] = v[k].w0; words[2 * k + 1] = v[k].w1; }
+      for (int py = 0; py < 16; py++) {
+        const int y = (g.ty0 + tr) * 16 + py;
+        if (y < ymin || y >= ymax) continue;
+        for (int px = 0; px < 16; px++) {
+          const int x = (g.tx0 + txi) * 16 + px;
+          if (x < xmin || x >= xmax) continue;
+          cover[(size_t)y * surf_w + x] = (uint8_t)area_pixel(words.data(), (int)v.size(), 2, backdrop, even_odd, px, py);
+        }
+      }
+    }
+  }
+  return 0;
+}
+}

@@ -445,3 +445,113 @@ def test_rowwalk_mode_full_size_c1_and_c2(dev):
         assert ok, msg
     finally:
         surf.close()
+
+
+# ---- coverage mode AREA (north star stages 2-3): tile-binned lines, signed-area accumulation, backdrop prefix sums ---
+# Parity target: the algorithm of the reference's GPU coverage-AA path as the oracle restates it (oracle/
+# skb_area_oracle.h, pinned in test_area_mode.py against the reference's compiled tiler and its exact-match golden) —
+# bit-exact A8 coverage, hence bit-exact frames for integer paints.
+def render_area(dev, dl, w, h):
+    surf = dev.create_surface(w, h)
+    try:
+        surf.set_coverage_mode(1)
+        out = surf.render(dl)
+        st = surf.stats()
+        return out, st
+    finally:
+        surf.close()
+
+
+AREA_EXACT = ["c0_star_plain_800x600", "c0_star_blur_800x600", "c1_fills_120_512", "mixed_transform_clip_400x300",
+              "golden_canonical_edges_192x144", "ut_stroke_then_fill_48", "c3_blur_12_640", "layers_512", "blend_modes_480",
+              "c2_clips_90_512", "clipped_blends_400", "images_512", "filters_512"]
+
+
+@pytest.mark.parametrize("name", AREA_EXACT)
+def test_area_mode_golden_scenes_bit_exact_vs_port(dev, name):
+    """Every fixture scene (fills, strokes, rect clips, blur temporaries, layers, blend modes; path clips and clipped draws
+    stay on the exact route inside the same frame) rendered with AREA coverage equals the oracle's AREA rendering."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dl = z["dl"].tobytes()
+    want = port.render_area(dl)
+    got, st = render_area(dev, dl, want.shape[1], want.shape[0])
+    assert st["n_area_lines"] > 0 or name == "c2_clips_90_512"     # (every draw of that scene is clipped: all exact)
+    assert np.array_equal(got, want), f"{int((got != want).any(axis=2).sum())} pixels differ"
+
+
+def test_area_mode_gradients_within_tolerance_of_port(dev):
+    z = np.load(os.path.join(GOLDEN, "c2_gradients_90_512.npz"))
+    dl = z["dl"].tobytes()
+    want = port.render_area(dl)
+    got, _ = render_area(dev, dl, 512, 512)
+    assert_within_tolerance(got, want)
+
+
+def test_area_mode_reference_golden_image(dev):
+    """The reference's own golden for its coverage-AA path (exact-match rule): with AREA coverage the frame is within
+    1/255 of it everywhere (the software brush's AlphaMulQ truncates where the GPU blend rounds)."""
+    z = np.load(os.path.join(GOLDEN, "golden_canonical_edges_192x144.npz"))
+    got, _ = render_area(dev, z["dl"].tobytes(), 192, 144)
+    assert np.abs(got.astype(int) - z["reference_png"].astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("n,size,seed,box", [(2000, 2048, 31, 256.0), (300, 1000, 32, 700.0), (5000, 1024, 33, 64.0)])
+def test_area_mode_random_fills_bit_exact_vs_port(dev, n, size, seed, box):
+    s = scene.scene_random_fills(n, size, seed, box=box)
+    dl = hostlib.encode_scene(s.encode())
+    got, st = render_area(dev, dl, size, size)
+    assert np.array_equal(got, port.render_area(dl))
+    assert st["n_prims"] == 0 and st["n_records"] == 0      # nothing was swept
+
+
+def test_area_mode_many_lines_in_one_tile(dev):
+    """More lines in single tiles than the kernel's shared-memory window holds (the in-place key sort in global memory)."""
+    rng = np.random.RandomState(3)
+    s = Scene(64, 64)
+    p = PathData(scene.EVEN_ODD)
+    for i in range(400):
+        x, y = rng.uniform(2, 30, 2)
+        p.move_to(x, y).line_to(x + rng.uniform(1, 30), y + rng.uniform(-2, 2)).line_to(x + rng.uniform(-2, 2), y + rng.uniform(1, 30)).close()
+    s.draw_path(p, Paint(fill=(0.1, 0.5, 0.9, 0.8)))
+    dl = hostlib.encode_scene(s.encode())
+    got, st = render_area(dev, dl, 64, 64)
+    assert st["n_area_tile_lines"] > 1200
+    assert np.array_equal(got, port.render_area(dl))
+
+
+def test_area_mode_bands_equal_whole_frame(dev):
+    s = scene.scene_random_fills_fast(20000, 4096, 4, box=128.0)
+    dl = hostlib.encode_scene(s.encode())
+    surf = dev.create_surface(4096, 4096)
+    surf.set_coverage_mode(1)
+    whole = surf.render(dl)
+    from skity_b200 import multigpu
+    got = np.zeros_like(whole)
+    for (y0, y1) in multigpu.band_ranges(4096, 4):
+        surf.set_band(y0, y1)
+        surf.begin(True)
+        surf.flush()
+        got[y0:y1] = surf.read_pixels(0, y0, 4096, y1 - y0)
+    surf.close()
+    assert whole.any()
+    assert np.array_equal(got, whole)
+    # ... and the frame is the oracle's (rendered in row bands by forked processes)
+    port.set_coverage_mode(1)
+    try:
+        want = port.render_parallel(dl)
+    finally:
+        port.set_coverage_mode(0)
+    assert np.array_equal(whole, want)
+
+
+def test_area_versus_exact_mode_histogram(dev):
+    """How far AREA coverage is from the software backend's (the default, exact mode) on curved fills: reported, and
+    bounded loosely — AREA is a different anti-aliasing algorithm, not an approximation of the exact mode."""
+    s = scene.scene_c1(2000, 2048, 1)
+    dl = hostlib.encode_scene(s.encode())
+    exact = render(dev, dl, 2048, 2048)
+    area, _ = render_area(dev, dl, 2048, 2048)
+    d = np.abs(area.astype(np.int16) - exact.astype(np.int16)).max(axis=2)
+    print(f"AREA vs exact, c1-style 2000 paths 2048^2: <=1/255 on {float((d <= 1).mean()):.4%}, <=2/255 on "
+          f"{float((d <= 2).mean()):.4%}, <=8/255 on {float((d <= 8).mean()):.4%}, max {int(d.max())}")
+    assert float((d <= 8).mean()) > 0.9
