@@ -8,12 +8,32 @@ import struct
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libskity_ref.so")
+LIB_PATH = os.path.join(_HERE, "_ref", "libskity_ref.so")           # -O2, baseline x86-64: the parity authority
+FAST_LIB_PATH = os.path.join(_HERE, "_ref", "libskity_ref_O3.so")   # -O3 -march=x86-64-v3: the CPU-baseline timing build
 _lib = None
 
 
 def available():
     return os.path.exists(LIB_PATH)
+
+
+def fast_available():
+    """The -O3 -march=x86-64-v3 build exists and this host can run it (AVX2, FMA, BMI2)."""
+    if not os.path.exists(FAST_LIB_PATH):
+        return False
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return False
+    return all(f in flags for f in ("avx2", "fma", "bmi2", "movbe", "f16c"))
+
+
+def use_fast_build():
+    """Switch this process to the timing build (before the first call; bench.py's CPU-baseline legs only)."""
+    global LIB_PATH, _lib
+    if _lib is not None:
+        raise RuntimeError("refsw: library already loaded")
+    LIB_PATH = FAST_LIB_PATH
 
 
 def lib():

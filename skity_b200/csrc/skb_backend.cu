@@ -10,6 +10,7 @@
 //   7 blur      k_blur_h, k_blur_v                         StackBlur-exact triangular filter
 // HBM layout: see DESIGN.md §3.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <climits>
@@ -41,6 +42,22 @@ static void set_error(const std::string& s) { g_last_error = s; }
   } while (0)
 
 // ------------------------------------------------------------------ device tables
+// NVTX ranges named after the reference's own trace hooks (SKITY_TRACE_EVENT, src/tracing.hpp:14-30), so that a
+// timeline of this backend reads like a trace of the software backend: SWRaster_RastePath (sw_raster.cc:734) covers
+// flatten / setup / walk / coverage, SWCanvas_OnClipPath (sw_canvas.cc:316) the clip stage, SWSpanBrush_Brush
+// (sw_span_brush.cc:67) bin + fine, SWCanvas_HandleFilter the blur passes.  Free when no tool is attached.
+struct NvtxStage {
+  bool open = false;
+  void next(const char* name) {
+    if (open) nvtxRangePop();
+    nvtxRangePushA(name);
+    open = true;
+  }
+  ~NvtxStage() {
+    if (open) nvtxRangePop();
+  }
+};
+
 struct SurfDesc {
   uint8_t* px;          // premultiplied RGBA8, rows `pitch` bytes apart, padded to whole tiles
   uint32_t w, h;        // logical size
@@ -2420,6 +2437,8 @@ static skb_result run_frame(skb_surface s) {
   uint32_t* item_base = (uint32_t*)s->item_cnt.p;
   uint32_t* counters = (uint32_t*)s->counters.p;  // [0] pool_next, [1] overflow
 
+  NvtxStage nvtx;
+  nvtx.next("SWRaster_RastePath/flatten");
   cudaEventRecord(s->ev[0], st);
   // ---- stage 1: flatten
   SKB_CUDA(cudaMemsetAsync(seg_op, 0, (size_t)(n_segs + 1) * 4, st));  // segments no op refers to count as op 0's (validate_dl rejects such lists)
@@ -2496,6 +2515,7 @@ static skb_result run_frame(skb_surface s) {
     }
     if (attempt == 0) {
       cudaEventRecord(s->ev[1], st);
+      nvtx.next("SWRaster_RastePath/setup");
       // ---- stage 2: setup
       SKB_CUDA(cudaMemsetAsync(row_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(item_base + n_ops, 0, 4, st));
@@ -2553,6 +2573,7 @@ static skb_result run_frame(skb_surface s) {
     pool_cap = (uint32_t)(s->pool.cap / sizeof(TrapRec));
     S.pool_capacity = pool_cap;
     // ---- stage 3: walk
+    nvtx.next("SWRaster_RastePath/WalkEdges");
     SKB_CUDA(cudaMemsetAsync(counters, 0, 64, st));
     if (n_rows) SKB_CUDA(cudaMemsetAsync(s->rows.p, 0, n_rows * sizeof(uint2), st));
     WalkArgs wa;
@@ -2662,6 +2683,7 @@ static skb_result run_frame(skb_surface s) {
   cudaEventRecord(s->ev[3], st);
 
   // ---- stage 4: coverage
+  nvtx.next("SWRaster_RastePath/SpanBuilder");
   CoverArgs ca;
   ca.geom = geom;
   ca.item_base = item_base;
@@ -2772,6 +2794,7 @@ static skb_result run_frame(skb_surface s) {
     launches += 3;
   }
   cudaEventRecord(s->ev[9], st);
+  nvtx.next("SWCanvas_OnClipPath");
   if (has_clip_ops && n_rows) {
     // ---- stage 4b: clip states (by nesting depth), then the clipped draws
     const uint32_t n_states = h.n_clip_states;
@@ -2818,6 +2841,7 @@ static skb_result run_frame(skb_surface s) {
     }
   }
   cudaEventRecord(s->ev[4], st);
+  nvtx.next("SWSpanBrush_Brush/bin");
   // ---- stage 5: bin
   SKB_TRY(scan_exclusive(s, (uint32_t*)s->tile_cnt.p, n_tiles + 1, &launches));
   uint32_t n_cmds = 0;
@@ -2833,6 +2857,7 @@ static skb_result run_frame(skb_surface s) {
   cudaEventRecord(s->ev[5], st);
 
   // ---- stages 6 + 7: fine pass over temporaries, blur, fine pass over the canvas
+  nvtx.next("SWSpanBrush_Brush/fine+SWCanvas_HandleFilter");
   FineArgs fa;
   fa.tile_off = (const uint32_t*)s->tile_cnt.p;
   fa.cmds = (const uint2*)s->cmds.p;

@@ -4,6 +4,7 @@
 #include "src/effect/image_filter_base.hpp"
 #include "src/effect/pixmap_shader.hpp"
 #include "src/graphic/color_priv.hpp"
+#include "src/tracing.hpp"  // SKITY_TRACE_EVENT: the reference's own hooks (sw_canvas.cc:298,316,358,414,442,644), same build switch
 
 #include <cmath>
 #include <functional>
@@ -249,6 +250,7 @@ void CudaCanvas::OnFlush() {}
 // SWCanvas::OnClipRect (sw_canvas.cc:297-313): an intersecting rect under a
 // scale/translate CTM only tightens the integer scan rectangle.
 void CudaCanvas::OnClipRect(const Rect& rect, ClipOp op) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnClipRect);
   if (PeekLayerStack()) {
     PeekLayerStack()->canvas->ClipRect(rect, op);
     return;
@@ -261,6 +263,7 @@ void CudaCanvas::OnClipRect(const Rect& rect, ClipOp op) {
 
 // SWCanvas::OnClipPath (sw_canvas.cc:315-336)
 void CudaCanvas::OnClipPath(const Path& path, ClipOp op) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnClipPath);
   if (PeekLayerStack()) {
     PeekLayerStack()->canvas->ClipPath(path, op);
     return;
@@ -585,6 +588,7 @@ void CudaCanvas::FillPath(const Path& path, const Paint& paint, bool stroke) {
 
 // SWCanvas::OnDrawPath (sw_canvas.cc:357-411)
 void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnDrawPath);
   if (PeekLayerStack()) {
     PeekLayerStack()->canvas->DrawPath(path, paint);
     return;
@@ -631,6 +635,7 @@ void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
 
 // SWCanvas::OnDrawPaint (sw_canvas.cc:413-439): the whole bitmap, identity transform, no scan clip.
 void CudaCanvas::OnDrawPaint(const Paint& paint) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnDrawPaint);
   if (PeekLayerStack()) {
     PeekLayerStack()->canvas->DrawPaint(paint);
     return;
@@ -663,6 +668,7 @@ void CudaCanvas::OnDrawPaint(const Paint& paint) {
 // path is drawn into an offscreen surface, blurred into a second one, post-processed per pixel for the
 // blur styles / the shadow colour, and composited back as an image.
 void CudaCanvas::HandleFilter(const Path& path, const Paint& paint) {
+  SKITY_TRACE_EVENT(CudaCanvas_HandleFilter);
   HandleFilterOf(path.GetBounds(), paint, [&](CudaCanvas& temp_canvas, const Paint& work_paint) { temp_canvas.DrawPath(path, work_paint); });
 }
 
@@ -813,6 +819,7 @@ void CudaCanvas::DrawSurfaceImage(uint32_t src_surface, uint32_t iw, uint32_t ih
 // an offscreen surface as large as the layer's device-space bounds, drawn into by a sub-canvas that
 // shares this canvas's CTM stack and global clip, shifted by the layer's device-space origin.
 void CudaCanvas::OnSaveLayer(const Rect& bounds, const Paint& paint) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnSaveLayer);
   state_stack_.emplace_back(state_stack_.back());
   if (PeekLayerStack()) PeekLayerStack()->canvas->OnSave();
   state_stack_.back().has_layer = true;
@@ -874,6 +881,7 @@ void CudaCanvas::OnDrawGlyphs(uint32_t, const GlyphID*, const float*, const floa
 // SWCanvas::OnDrawImageRect (sw_canvas.cc:641-677): the image becomes a decal shader over the destination rectangle
 void CudaCanvas::OnDrawImageRect(std::shared_ptr<Image> image, const Rect& src, const Rect& dst, const SamplingOptions& sampling,
                                  Paint const* paint) {
+  SKITY_TRACE_EVENT(CudaCanvas_OnDrawImageRect);
   if (!image) return;
   if (src.Width() == 0 || src.Height() == 0 || dst.Width() == 0 || dst.Height() == 0) return;
   Paint work_paint = (paint == nullptr) ? Paint() : *paint;
