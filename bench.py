@@ -298,17 +298,33 @@ def run_ours(args):
         outs = [out_np, torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() if out_np is not None else None]
 
         def run_pipelined(n_steps):
+            if not banded:
+                # one host thread per surface (the C ABI is thread-safe per surface): the threads take alternate frames,
+                # so frame k + 1 is uploaded and rendered while frame k is still being read back
+                def worker(j):
+                    sf = pair[j]
+                    for k in range(j, n_steps, 2):
+                        sf.begin(True)
+                        sf.encode((dl_pinned.data_ptr(), n_dl))
+                        sf.flush()
+                        sf.read_pixels_async(outs[j])
+                        sf.sync()
+                ths = [threading.Thread(target=worker, args=(j,)) for j in range(2)]
+                for th in ths:
+                    th.start()
+                for th in ths:
+                    th.join()
+                return
             for k in range(n_steps):
                 sf = pair[k & 1]
-                if banded and k >= 2:
+                if k >= 2:
                     sf.sync()           # rank 0: the read-back of frame k - 2 has left this canvas
                     dist.barrier()
                 sf.begin(True)
                 sf.encode((dl_pinned.data_ptr(), n_dl))
                 sf.flush()
-                if banded:
-                    sf.sync()
-                    dist.barrier()      # every band of frame k is in rank 0's canvas
+                sf.sync()
+                dist.barrier()      # every band of frame k is in rank 0's canvas
                 if outs[k & 1] is not None:
                     sf.read_pixels_async(outs[k & 1])
             for sf in pair:
@@ -381,7 +397,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(canvases * W * H * 4), "ms_per_step": round(ms_e2e_used, 4),
                     "what": "C ABI with host buffers: display list H2D from pinned memory on every rank, frame, "
                             + ("bands into rank 0's canvas over NVLink, barrier, " if banded else "") + "canvas D2H into pinned memory; "
-                            + ("two frames in flight on two surfaces (the read-back of one overlaps the next)" if pipelined else "one frame at a time"),
+                            + (("two frames in flight on two surfaces" + ("" if banded else ", one host thread each") + " (the read-back of one overlaps the next)") if pipelined else "one frame at a time"),
                     "frames_in_flight": 2 if pipelined else 1,
                     "one_frame_at_a_time": {"value": round(mpix / (ms_e2e_serial / 1e3), 2), "ms_per_step": round(ms_e2e_serial, 4)}},
             "gpu_launches": int(launches),

@@ -429,11 +429,13 @@ __device__ __forceinline__ void walk_setup_sink(const WalkArgs& a, uint32_t op, 
 __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid % (uint32_t)lane_stride) return;
-  const uint32_t i = tid / (uint32_t)lane_stride;
-  if (i >= *a.count) return;
+  // a grid smaller than the list (SKB_WALK_RESIDENT: a cap on the paths in flight, i.e. on the sweep's cache footprint)
+  // takes the paths in strides of the grid
+  const uint32_t n_list = *a.count, step = gridDim.x * blockDim.x / (uint32_t)lane_stride;
+  for (uint32_t i = tid / (uint32_t)lane_stride; i < n_list; i += step) {
   const uint32_t op = a.list[i];
   const OpGeom g = a.geom[op];
-  if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  if (g.empty || g.ntx == 0 || g.nty == 0) continue;
   RecSink sink;
   walk_setup_sink(a, op, g, sink);
   // rows below the last tile row are never read: stop the sweep there (rows do not depend on later ones)
@@ -443,6 +445,7 @@ __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
   walk_path(E, Q, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y, g.left_clip,
             g.right_clip, (int)a.t.ops[op].fill_type, sink, (int)a.t.wide);
+  }
 }
 
 // ------------------------------------------------- stage 3 (row-parallel form): skb_rowwalk.cuh
@@ -2083,6 +2086,12 @@ struct skb_surface_s {
   uint32_t w = 0, h = 0;
   uint32_t band_y0 = 0, band_y1 = 0;
   int coord_mode = SKB_COORD_AUTO;
+  // structure of the encoded frame, worked out once by skb_frame_encode so that run_frame has no host loop over the
+  // ops between two launches (at 1M ops such a loop is milliseconds of idle GPU inside the frame)
+  bool plan_clip_ops = false, plan_clipped_fills = false;
+  int plan_max_depth = 0;
+  std::vector<uint8_t> plan_op_depth;     // nesting depth of the clip state a CLIP op defines (empty without clip ops)
+  std::vector<uint32_t> plan_blur_ops;    // indices of the BLUR ops, in op order
   int walk_mode = 0;
   int coverage_mode = SKB_COVERAGE_EXACT;
   cudaStream_t stream = nullptr;
@@ -2661,7 +2670,10 @@ static skb_result run_frame(skb_surface s) {
       // working set is ~3 KB of edges per path, and with every thread slot taken it spills from L2 to DRAM
       static const int walk_smem = getenv("SKB_WALK_SMEM") ? atoi(getenv("SKB_WALK_SMEM")) : 0;
       if (walk_smem > 48 * 1024) cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem);
-      k_walk<<<cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK), WALK_BLOCK, walk_smem, st>>>(wa, lane_stride);
+      uint32_t walk_grid = cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK);
+      static const int walk_resident = getenv("SKB_WALK_RESIDENT") ? atoi(getenv("SKB_WALK_RESIDENT")) : 0;   // blocks per SM
+      if (walk_resident > 0) walk_grid = std::min(walk_grid, (uint32_t)(walk_resident * s->dev->sm_count));
+      k_walk<<<walk_grid, WALK_BLOCK, walk_smem, st>>>(wa, lane_stride);
       launches++;
     }
     uint32_t hc[12];
@@ -2711,29 +2723,10 @@ static skb_result run_frame(skb_surface s) {
     ca.zmask = (uint8_t*)s->zmask.p;
     ca.zplane[0] = ca.zmask;
   }
-  // clip structure of the frame (host side): nesting depth of every clip state, clipped draws present?
-  bool has_clip_ops = false, has_clipped_fills = false;
-  int max_depth = 0;
-  std::vector<uint8_t> op_depth;
-  {
-    std::vector<int> state_depth(h.n_clip_states + 1, 0);
-    for (uint32_t i = 0; i < n_ops; i++) {
-      if (hops[i].kind == SKB_OP_CLIP) {
-        if (!has_clip_ops) op_depth.assign(n_ops, 0);
-        has_clip_ops = true;
-        int d = state_depth[hops[i].clip_in] + 1;
-        if (d > 250) {
-          set_error("clip stack deeper than 250");
-          return SKB_ERROR_UNSUPPORTED;
-        }
-        state_depth[hops[i].clip_out] = d;
-        op_depth[i] = (uint8_t)d;
-        max_depth = std::max(max_depth, d);
-      } else if (hops[i].kind == SKB_OP_FILL && hops[i].clip_in != 0) {
-        has_clipped_fills = true;
-      }
-    }
-  }
+  // clip structure of the frame (worked out by skb_frame_encode): nesting depth of every clip state, clipped draws present?
+  const bool has_clip_ops = s->plan_clip_ops, has_clipped_fills = s->plan_clipped_fills;
+  const int max_depth = s->plan_max_depth;
+  const std::vector<uint8_t>& op_depth = s->plan_op_depth;
   if (has_clipped_fills) {
     for (int k = 2; k < SKB_CLIP_PLANES; k++) {
       SKB_TRY(buf_reserve(s->mask_extra[k - 2], (n_items + 1) * 256));
@@ -2875,8 +2868,8 @@ static skb_result run_frame(skb_surface s) {
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.zplane[k] = ca.zplane[k];
   // blur jobs of the whole frame, sorted by the level of their destination
   std::vector<BlurJob> jobs;
-  for (uint32_t i = 0; i < n_ops; i++) {
-    if (hops[i].kind == SKB_OP_BLUR) {
+  for (uint32_t i : s->plan_blur_ops) {
+    {
       BlurJob j;
       j.src = hops[i].aux;
       j.dst = hops[i].surface;
@@ -3213,14 +3206,32 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
     const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
     s->surf_level.assign(h.n_surfaces, 0);
     s->surf_drawn.assign(h.n_surfaces, 0);
+    s->plan_clip_ops = s->plan_clipped_fills = false;
+    s->plan_max_depth = 0;
+    s->plan_op_depth.clear();
+    s->plan_blur_ops.clear();
+    std::vector<int> state_depth(h.n_clip_states + 1, 0);
     for (uint32_t i = 0; i < h.n_ops; i++) {
       const skb_dl_op& o = ops[i];
       uint32_t src = 0xFFFFFFFFu;
       if (o.kind == SKB_OP_FILL) {
         s->surf_drawn[o.surface] = 1;
         if (paints[o.paint].type == SKB_PAINT_IMAGE) src = paints[o.paint].image_surface;
+        if (o.clip_in != 0) s->plan_clipped_fills = true;
       } else if (o.kind == SKB_OP_BLUR) {
         src = o.aux;
+        s->plan_blur_ops.push_back(i);
+      } else if (o.kind == SKB_OP_CLIP) {
+        if (!s->plan_clip_ops) s->plan_op_depth.assign(h.n_ops, 0);
+        s->plan_clip_ops = true;
+        const int d = state_depth[o.clip_in] + 1;
+        if (d > 250) {
+          set_error("clip stack deeper than 250");
+          return SKB_ERROR_UNSUPPORTED;
+        }
+        state_depth[o.clip_out] = d;
+        s->plan_op_depth[i] = (uint8_t)d;
+        s->plan_max_depth = std::max(s->plan_max_depth, d);
       }
       if (src != 0xFFFFFFFFu) s->surf_level[o.surface] = std::max(s->surf_level[o.surface], s->surf_level[src] + 1);
     }
