@@ -7,9 +7,10 @@
  * load it.  It is PINNED: tests/test_oracle_pinning.py checks it bit-for-bit
  * against the reference's own compiled backend (oracle/_ref, built from the
  * unmodified sources by oracle/build_ref.py) on spans, pixels and blur, and
- * against the golden vectors committed under tests/golden/.  One exception: ClipOp::kDifference (spans_subtract,
- * the merge in clip_refine) is restated but UNPINNED — the reference's result depends on std::sort's order of
- * equal keys, qsort's differs on some scenes; the CUDA backend refuses difference clips.
+ * against the golden vectors committed under tests/golden/.  That includes ClipOp::kDifference (spans_subtract, the
+ * merge in clip_refine), whose result in the reference depends on how std::sort orders equal keys: the sorts are
+ * restated as libstdc++'s algorithm (sort_spans), and 350 random difference-clip scenes (single, nested with
+ * intersect, difference on difference) equal the compiled reference's bit for bit.
  *
  * Every function cites the reference file:line it restates (paths relative to
  * the reference root).  Arithmetic notes that matter for bit-exactness:
@@ -1343,10 +1344,109 @@ static void find_span(const spanvec* clip, const skbo_span* s, spanvec* out) {
     }
   }
 }
-static int span_x_cmp(const void* a, const void* b) {
-  int xa = ((const skbo_span*)a)->x, xb = ((const skbo_span*)b)->x;
-  return xa < xb ? -1 : (xa > xb);
+/* std::sort on a span array with a strict-weak "less" — the same libstdc++ algorithm as sort_edges above (GCC 13
+ * bits/stl_algo.h: introsort, threshold 16, median-of-three to first, unguarded partition, final insertion sort,
+ * heapsort at the depth limit).  spans_subtraction and PerformMerge sort with comparators that leave ties
+ * (equal x; equal y, x and cover), and what the reference does next depends on how those ties come out. */
+typedef int (*span_less_fn)(const skbo_span*, const skbo_span*);
+static inline void span_swap(skbo_span* a, skbo_span* b) { skbo_span t = *a; *a = *b; *b = t; }
+static void sp_unguarded_linear_insert(skbo_span* last, span_less_fn less) {
+  skbo_span val = *last;
+  skbo_span* next = last - 1;
+  while (less(&val, next)) { *last = *next; last = next; --next; }
+  *last = val;
 }
+static void sp_insertion_sort(skbo_span* first, skbo_span* last, span_less_fn less) {
+  if (first == last) return;
+  for (skbo_span* i = first + 1; i != last; ++i) {
+    if (less(i, first)) {
+      skbo_span val = *i;
+      memmove(first + 1, first, (size_t)(i - first) * sizeof(skbo_span));
+      *first = val;
+    } else {
+      sp_unguarded_linear_insert(i, less);
+    }
+  }
+}
+static void sp_adjust_heap(skbo_span* first, long hole, long len, skbo_span value, span_less_fn less) {
+  const long top = hole;
+  long child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (less(first + child, first + (child - 1))) child--;
+    first[hole] = first[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    first[hole] = first[child - 1];
+    hole = child - 1;
+  }
+  long parent = (hole - 1) / 2;
+  while (hole > top && less(first + parent, &value)) {
+    first[hole] = first[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  first[hole] = value;
+}
+static void sp_heap_sort(skbo_span* first, skbo_span* last, span_less_fn less) {
+  long len = last - first;
+  if (len >= 2) {
+    long parent = (len - 2) / 2;
+    for (;;) {
+      skbo_span v = first[parent];
+      sp_adjust_heap(first, parent, len, v, less);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  while (last - first > 1) {
+    --last;
+    skbo_span v = *last;
+    *last = *first;
+    sp_adjust_heap(first, 0, last - first, v, less);
+  }
+}
+static void sp_introsort_loop(skbo_span* first, skbo_span* last, long depth, span_less_fn less) {
+  while (last - first > 16) {
+    if (depth == 0) { sp_heap_sort(first, last, less); return; }
+    --depth;
+    skbo_span* mid = first + (last - first) / 2;
+    skbo_span *a = first + 1, *b = mid, *c = last - 1;
+    if (less(a, b)) {
+      if (less(b, c)) span_swap(first, b);
+      else if (less(a, c)) span_swap(first, c);
+      else span_swap(first, a);
+    } else if (less(a, c)) span_swap(first, a);
+    else if (less(b, c)) span_swap(first, c);
+    else span_swap(first, b);
+    skbo_span *lo = first + 1, *hi = last;
+    for (;;) {
+      while (less(lo, first)) ++lo;
+      --hi;
+      while (less(first, hi)) --hi;
+      if (!(lo < hi)) break;
+      span_swap(lo, hi);
+      ++lo;
+    }
+    sp_introsort_loop(lo, last, depth, less);
+    last = lo;
+  }
+}
+static void sort_spans(skbo_span* first, size_t n, span_less_fn less) {
+  if (n == 0) return;
+  long lg = 0;
+  for (size_t v = n; v > 1; v >>= 1) lg++;
+  sp_introsort_loop(first, first + n, lg * 2, less);
+  if (n > 16) {
+    sp_insertion_sort(first, first + 16, less);
+    for (skbo_span* i = first + 16; i != first + n; ++i) sp_unguarded_linear_insert(i, less);
+  } else {
+    sp_insertion_sort(first, first + n, less);
+  }
+}
+static int span_x_less(const skbo_span* a, const skbo_span* b) { return a->x < b->x; }
 /* spans_subtraction — sw_canvas.cc:43-133 */
 static void spans_subtract(const spanvec* sub, const spanvec* min, spanvec* out) {
   spanvec ms = {0, 0, 0};
@@ -1356,8 +1456,7 @@ static void spans_subtract(const spanvec* sub, const spanvec* min, spanvec* out)
     for (size_t j = 0; j < min->n; j++)
       if (min->v[j].y == s->y) sv_push(&ms, min->v[j].x, min->v[j].y, min->v[j].len, min->v[j].cover);
     if (ms.n == 0) { sv_push(out, s->x, s->y, s->len, s->cover); continue; }
-    /* the reference uses std::sort on x (unstable); ties only reorder equal-x minuend spans */
-    qsort(ms.v, ms.n, sizeof(skbo_span), span_x_cmp);
+    sort_spans(ms.v, ms.n, span_x_less);   /* std::sort by x alone (sw_canvas.cc:71-72): ties as libstdc++ leaves them */
     int cx = s->x, cl = s->len;
     for (size_t j = 0; j < ms.n; j++) {
       const skbo_span* m = &ms.v[j];
@@ -1395,12 +1494,10 @@ static void perform_clip(const clip_state* st, const spanvec* in, spanvec* out) 
   if (st->op == 0) { spans_subtract(in, &st->spans, out); return; }
   for (size_t i = 0; i < in->n; i++) find_span(&st->spans, &in->v[i], out);
 }
-static int merge_cmp(const void* pa, const void* pb) {
-  const skbo_span* a = (const skbo_span*)pa;
-  const skbo_span* b = (const skbo_span*)pb;
-  if (a->y != b->y) return a->y < b->y ? -1 : 1;
-  if (a->x != b->x) return a->x < b->x ? -1 : 1;
-  return a->cover > b->cover ? -1 : (a->cover < b->cover);
+static int merge_less(const skbo_span* a, const skbo_span* b) {   /* PerformMerge's comparator, sw_canvas.cc:201-213 */
+  if (a->y < b->y) return 1;
+  if (a->y == b->y) return a->x != b->x ? a->x < b->x : a->cover > b->cover;
+  return 0;
 }
 /* SWCanvas::OnClipPath + State::RecursiveClip/PerformMerge — sw_canvas.cc:178-217,315-336 */
 static void clip_refine(const clip_state* parent, const spanvec* fresh, int op, clip_state* out) {
@@ -1419,7 +1516,7 @@ static void clip_refine(const clip_state* parent, const spanvec* fresh, int op, 
         const skbo_span* s = &parent->spans.v[i];
         sv_push(&out->spans, s->x, s->y, s->len, s->cover);
       }
-      qsort(out->spans.v, out->spans.n, sizeof(skbo_span), merge_cmp);
+      sort_spans(out->spans.v, out->spans.n, merge_less);
     }
     out->op = parent->op;
   } else {

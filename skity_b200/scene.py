@@ -788,3 +788,66 @@ def scene_filtered_layers(seed=99, size=384):
     s.restore()
     s.restore()
     return s
+
+
+def scene_difference_clips(seed, mode="single", size=None):
+    """Solid (and a few stroked / translucent) draws under ClipOp::kDifference clips (sw_canvas.cc:56-133,158-217).
+    mode "single": every Save level holds ONE difference clip (path, rounded shape or rotated rectangle) — how the
+    reference's own goldens and examples use the op; "mixed": difference and intersect clips nested in one Save level
+    (difference after intersect, intersect after difference); "merge": difference on difference (PerformMerge)."""
+    rng = np.random.RandomState(seed)
+    w = h = size or int(rng.randint(60, 520))
+    if size is None:
+        h = int(rng.randint(60, 520))
+    s = Scene(w, h)
+
+    def clip_shape(intersect):
+        k = rng.uniform()
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        if k < 0.6:
+            s.clip_path(_random_closed_path(rng, cx, cy, float(rng.uniform(40, 400)), int(rng.randint(0, 6))), intersect)
+        elif k < 0.8:
+            s.clip_rect(float(cx), float(cy), float(cx + rng.uniform(10, 300)), float(cy + rng.uniform(10, 300)), intersect)
+        else:
+            s.rotate(float(rng.uniform(-40, 40)))
+            s.clip_rect(float(cx), float(cy), float(cx + rng.uniform(10, 300)), float(cy + rng.uniform(10, 300)), intersect)
+
+    depth = 0
+    for i in range(int(rng.randint(4, 40))):
+        if rng.uniform() < 0.3 and depth < 2:
+            s.save(); depth += 1
+            if mode == "single":
+                clip_shape(False)
+            elif mode == "mixed":
+                first = rng.uniform() < 0.5
+                clip_shape(first)
+                clip_shape(not first)
+                if rng.uniform() < 0.3:
+                    clip_shape(True)
+            else:
+                clip_shape(False)
+                clip_shape(False)
+        elif rng.uniform() < 0.15 and depth > 0:
+            s.restore(); depth -= 1
+        col = tuple(np.float32(v) for v in rng.uniform(0, 1, 4))
+        if rng.uniform() < 0.5:
+            col = col[:3] + (np.float32(1.0),)
+        s.draw_path(_random_closed_path(rng, rng.uniform(0, w), rng.uniform(0, h), float(rng.uniform(20, 400)), i),
+                    Paint(style=int(rng.randint(0, 3)), fill=col, stroke=col, stroke_width=float(rng.uniform(0.5, 9))))
+    while depth:
+        s.restore(); depth -= 1
+    return s
+
+
+def scene_ref_clip_path_difference():
+    """The reference's own golden case ClipGolden.ClipPathDifference (test/golden/cases/clip/clip.cc:171-203): the star
+    stroked green, a two-quad clip path stroked red, ClipPath(kDifference), the star filled blue; 400x400."""
+    s = Scene(400, 400)
+    star = star_path()
+    green, red, blue = (0.0, 1.0, 0.0, 1.0), (1.0, 0.0, 0.0, 1.0), (0.0, 0.0, 1.0, 1.0)
+    s.draw_path(star, Paint(style=STROKE, stroke=green, stroke_width=1.0))
+    clip = PathData().move_to(10.0, 10.0).quad_to(300.0, 10.0, 150.0, 150.0).quad_to(10.0, 300.0, 300.0, 300.0).close()
+    s.draw_path(clip, Paint(style=STROKE, stroke=red, stroke_width=1.0))
+    s.clip_path(clip, False)
+    s.draw_path(star, Paint(style=FILL, fill=blue))
+    return s

@@ -103,6 +103,14 @@ def golden_scenes():
     # ... and such spans are handed down: here a third-level clip consists of one zero-length span inherited from
     # the zero-length / zero-coverage spans of the second level
     out["clip_inherited_ghost_span_354"] = scene.scene_fuzz(22152)[0]
+    # ClipOp::kDifference (sw_canvas.cc:56-133,158-217): the reference's own golden case, and seeded scenes of the three
+    # ways the op combines (one difference clip per Save level; difference and intersect nested; difference on
+    # difference = PerformMerge)
+    out["ref_clip_path_difference_400"] = scene.scene_ref_clip_path_difference()
+    out["clip_difference_single_317"] = scene.scene_difference_clips(317, "single")
+    out["clip_difference_single_44"] = scene.scene_difference_clips(44, "single")
+    out["clip_difference_mixed_23"] = scene.scene_difference_clips(23, "mixed")
+    out["clip_difference_merge_5"] = scene.scene_difference_clips(5, "merge")
     # two same-size images of different content, both temporaries (the encoder's image table must not confuse them)
     out["images_same_size_256"] = scene.scene_images_same_size()
     return out
