@@ -1285,8 +1285,12 @@ struct ClipStateDesc {
   uint32_t table_off;        // first pixel of the table (in pixels)
   uint32_t nonempty;         // SWCanvas::State::HasClip(): some span exists
   uint32_t op;
-  uint32_t pad;
+  uint32_t kind;             // 0: intersecting state (per-pixel entry table); 1: ClipOp::kDifference state (per-row sorted span lists)
 };
+// A difference state lives in the same arena as an intersecting one (8 words per pixel of its region, rows of rw pixels):
+// row r holds [n_spans, 0, (x, len) * n_spans]; a row of rw pixels has at most rw direct and rw accumulated spans, and
+// 2 + 4 * rw <= 8 * rw.
+#define SKB_CLIP_KIND_DIFF 1u
 
 __global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* surfs, ClipStateDesc* states, uint32_t* px_cnt) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1300,7 +1304,7 @@ __global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* 
   d.table_off = 0;
   d.nonempty = 0;
   d.op = op;
-  d.pad = 0;
+  d.kind = o.aux == 0 ? SKB_CLIP_KIND_DIFF : 0u;
   if (!g.empty && g.ntx > 0) {
     // the whole scan rectangle (+ the column FindSpan's `+ 1` can reach), on the surface or not: HasClip() and
     // nested clips see every span of a clip path (sw_canvas.cc:315-336)
@@ -1339,9 +1343,9 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   const uint32_t op = c.trow_op[r / SKB_TILE];
   const skb_dl_op o = c.ops[op];
   if (mode == 0) {
-    if (o.kind != SKB_OP_CLIP || a.op_depth[op] != (uint8_t)level) return;
+    if (o.kind != SKB_OP_CLIP || a.op_depth[op] != (uint8_t)level || o.aux == 0) return;   // difference clips: k_clip_diff
   } else {
-    if (o.kind != SKB_OP_FILL || o.clip_in == 0) return;
+    if (o.kind != SKB_OP_FILL || o.clip_in == 0 || a.states[o.clip_in].kind == SKB_CLIP_KIND_DIFF) return;
   }
   const OpGeom g = c.geom[op];
   if (g.empty || g.ntx == 0) return;
@@ -1451,6 +1455,136 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   }
   if (wrote) a.states[o.clip_out].nonempty = 1;
   if (over) *a.overflow = 1;
+}
+
+// ClipOp::kDifference (skb_clip.cuh).  One warp per pixel row of an op: the lanes prepare the row's records into shared
+// memory, lane 0 walks the row's spans in the reference's list order.
+//   mode 0  a difference CLIP op (its state has no parent: validate_dl): the row's spans are stored and sorted by x the
+//           way std::sort leaves them;
+//   mode 1  a FILL under a difference state: every span of the draw is cut by the state's spans of that row; what is
+//           left goes to coverage plane 0 (directly emitted spans) or 1 (accumulated spans) — a pixel has at most one
+//           of each, blended in that order, as for an unclipped draw.
+// Rare and small next to the draws themselves; no attempt is made to share a row among lanes.
+struct DiffStoreD {
+  uint2* spans;
+  int n;
+  __device__ void operator()(int x, int len, uint32_t) { spans[n++] = make_uint2((uint32_t)x, (uint32_t)len); }
+};
+struct DiffStoreA {
+  uint2* spans;   // filled from the END of the row's array backwards (the accumulated spans follow the direct ones in the list)
+  int cap, n;
+  __device__ void operator()(int x, int len, uint32_t) { spans[cap - 1 - n++] = make_uint2((uint32_t)x, (uint32_t)len); }
+};
+struct DiffPiece {
+  uint8_t* plane;
+  uint8_t* zplane;
+  const OpGeom* g;
+  uint32_t item_row;
+  int y, w;
+  uint32_t cover;
+  __device__ void operator()(int x, int len) {
+    for (int px = max(x, 0); px < min(x + len, w); px++) {
+      const int tx = px / SKB_TILE;
+      if (tx < g->tx0 || tx >= g->tx0 + g->ntx) continue;
+      const size_t at = (size_t)(item_row + (uint32_t)(tx - g->tx0)) * 256 + (size_t)(y % SKB_TILE) * SKB_TILE + (px % SKB_TILE);
+      plane[at] = (uint8_t)cover;
+      if (zplane) zplane[at] = 1;
+    }
+  }
+};
+struct DiffCut {
+  DiffPiece piece;
+  const uint2* ms;
+  int n_ms;
+  bool keep_zero;   // the blend mode / colour filter acts on zero-coverage pixels
+  __device__ void operator()(int x, int len, uint32_t cover) {
+    if (cover == 0 && !keep_zero) return;
+    piece.cover = cover;
+    span_subtract(x, len, ms, n_ms, piece);
+  }
+};
+
+__global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode) {
+  const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= a.n_rows) return;
+  const int lane = (int)(threadIdx.x & 31);
+  const CoverArgs& c = a.c;
+  const uint32_t op = c.trow_op[r / SKB_TILE];
+  const skb_dl_op o = c.ops[op];
+  if (mode == 0) {
+    if (o.kind != SKB_OP_CLIP || o.aux != 0) return;
+  } else {
+    if (o.kind != SKB_OP_FILL || o.clip_in == 0 || a.states[o.clip_in].kind != SKB_CLIP_KIND_DIFF) return;
+  }
+  const OpGeom g = c.geom[op];
+  if (g.empty || g.ntx == 0) return;
+  const SurfDesc sd = c.surfs[o.surface];
+  const int y = g.ty0 * SKB_TILE + (int)(r - c.row_base[op]);
+  if (y < g.scan_t || y >= g.scan_b || (mode == 1 && y >= (int)sd.h)) return;
+  uint2 row = c.rows[r];
+  row.y &= ~SKB_ROW_LINEAR;
+  if (row.y == 0) return;
+  __shared__ TrapPrep s_prep[4][SKB_CLIP_RMAX];
+  ClipRowState st;
+  clip_row_begin(st, c.pool, row, s_prep[threadIdx.x >> 5], lane, 32);
+  __syncwarp();
+  if (lane != 0) return;
+  int x_first = g.scan_l, x_last = g.scan_r;
+  if (st.n_prep >= 0) {
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int k = 0; k < st.n_prep; k++) {
+      if (st.prep[k].mode == 0) continue;
+      lo = min(lo, st.prep[k].L);
+      hi = max(hi, st.prep[k].R);
+    }
+    if (hi <= lo) return;
+    x_first = max(x_first, lo);
+    x_last = min(x_last, hi);
+  }
+  if (mode == 0) {
+    const ClipStateDesc own = a.states[o.clip_out];
+    if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
+    uint32_t* base = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+    uint2* spans = reinterpret_cast<uint2*>(base + 2);
+    DiffStoreD sd_{spans, 0};
+    DiffStoreA sa_{spans, 2 * own.rw, 0};
+    x_first = max(x_first, own.rx0);
+    x_last = min(x_last, own.rx0 + own.rw - 1);
+    clip_row_spans(st, c.pool, row, x_first, x_last, sd_, sa_);
+    // the accumulated spans behind the direct ones, in their own order
+    for (int k = 0; k < sa_.n; k++) {
+      const uint2 v = spans[2 * own.rw - 1 - k];
+      spans[sd_.n + k] = v;
+    }
+    const int n = sd_.n + sa_.n;
+    std_sort_replica(spans, n, SpanXLess());
+    base[0] = (uint32_t)n;
+    if (n) a.states[o.clip_out].nonempty = 1;
+  } else {
+    const ClipStateDesc par = a.states[o.clip_in];
+    const uint2* ms = nullptr;
+    int n_ms = 0;
+    if (par.nonempty && par.rw > 0 && y >= par.ry0 && y < par.ry0 + par.rh) {
+      const uint32_t* base = a.table + ((size_t)a.state_px_off[o.clip_in] + (size_t)(y - par.ry0) * par.rw) * SKB_CLIP_MAXE;
+      n_ms = (int)base[0];
+      ms = reinterpret_cast<const uint2*>(base + 2);
+    }
+    bool zm = false;
+    if (c.zplane[1] != nullptr) {
+      const skb_dl_paint pt = c.paints[o.paint];
+      zm = blend_zero_src_matters(paint_blend_mode(pt)) || SKB_PAINT_CF_OFFSET(pt) != 0;
+    }
+    const uint32_t item_row = c.item_base[op] + (uint32_t)((y / SKB_TILE) - g.ty0) * (uint32_t)g.ntx;
+    DiffCut cd, ca_;
+    cd.piece = DiffPiece{c.mask[0], zm ? c.zplane[0] : nullptr, &g, item_row, y, (int)sd.w, 0u};
+    cd.ms = ms;
+    cd.n_ms = n_ms;
+    cd.keep_zero = zm;
+    ca_ = cd;
+    ca_.piece.plane = c.mask[1];
+    ca_.piece.zplane = zm ? c.zplane[1] : nullptr;
+    clip_row_spans(st, c.pool, row, x_first, x_last, cd, ca_);
+  }
 }
 
 // One warp per (op, tile) item of a clipped draw: which planes are present, is plane 0 solid.
@@ -2091,7 +2225,7 @@ struct skb_surface_s {
   int coord_mode = SKB_COORD_AUTO;
   // structure of the encoded frame, worked out once by skb_frame_encode so that run_frame has no host loop over the
   // ops between two launches (at 1M ops such a loop is milliseconds of idle GPU inside the frame)
-  bool plan_clip_ops = false, plan_clipped_fills = false;
+  bool plan_clip_ops = false, plan_clipped_fills = false, plan_diff_clips = false;
   int plan_max_depth = 0;
   std::vector<uint8_t> plan_op_depth;     // nesting depth of the clip state a CLIP op defines (empty without clip ops)
   std::vector<uint32_t> plan_blur_ops;    // indices of the BLUR ops, in op order
@@ -2289,6 +2423,7 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
       return SKB_ERROR_BAD_DISPLAY_LIST;
     }
   }
+  std::vector<uint8_t> diff_state((size_t)h.n_clip_states + 1, 0);   // states defined by a ClipOp::kDifference clip
   for (uint32_t i = 0; i < h.n_ops; i++) {
     const skb_dl_op& o = ops[i];
     if (o.surface < h.n_surfaces && (vsurfs[o.surface].flags & SKB_SURFACE_IMAGE)) {
@@ -2334,9 +2469,23 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
         set_error("display list: clip state id out of range");
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
-      if (o.kind == SKB_OP_CLIP && o.aux != 1) {
-        set_error("ClipOp::kDifference path clips are not implemented on the device (intersecting clips are)");
-        return SKB_ERROR_UNSUPPORTED;
+      if (o.kind == SKB_OP_CLIP) {
+        // ClipOp::kDifference: a state of its own (one difference clip per Save level, how the reference's goldens and
+        // examples use the op).  Combined with another path clip in the same chain the reference goes through
+        // RecursiveClip's subtraction of whole span lists / PerformMerge (sw_canvas.cc:178-217): not on the device.
+        if (o.aux > 1) {
+          set_error("display list: unknown clip op");
+          return SKB_ERROR_BAD_DISPLAY_LIST;
+        }
+        if (o.aux == 0 && o.clip_in != 0) {
+          set_error("ClipOp::kDifference on top of another path clip is not implemented on the device");
+          return SKB_ERROR_UNSUPPORTED;
+        }
+        if (o.aux == 1 && o.clip_in != 0 && diff_state[o.clip_in]) {
+          set_error("a path clip on top of a ClipOp::kDifference clip is not implemented on the device");
+          return SKB_ERROR_UNSUPPORTED;
+        }
+        diff_state[o.clip_out] = o.aux == 0;
       }
     } else if (o.kind == SKB_OP_BLUR) {
       if (o.surface >= h.n_surfaces || o.aux >= h.n_surfaces || o.surface == 0 || o.aux == 0 || o.surface == o.aux) {
@@ -2822,9 +2971,17 @@ static skb_result run_frame(skb_surface s) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level);
       launches++;
     }
+    if (s->plan_diff_clips && clip_grid) {
+      k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0);
+      launches++;
+    }
     if (has_clipped_fills && clip_grid && n_items) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0);
       launches++;
+      if (s->plan_diff_clips) {
+        k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 1);
+        launches++;
+      }
       k_clip_classify<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);
       launches++;
     }
@@ -3209,7 +3366,7 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
     const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
     s->surf_level.assign(h.n_surfaces, 0);
     s->surf_drawn.assign(h.n_surfaces, 0);
-    s->plan_clip_ops = s->plan_clipped_fills = false;
+    s->plan_clip_ops = s->plan_clipped_fills = s->plan_diff_clips = false;
     s->plan_max_depth = 0;
     s->plan_op_depth.clear();
     s->plan_blur_ops.clear();
@@ -3227,6 +3384,7 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
       } else if (o.kind == SKB_OP_CLIP) {
         if (!s->plan_clip_ops) s->plan_op_depth.assign(h.n_ops, 0);
         s->plan_clip_ops = true;
+        if (o.aux == 0) s->plan_diff_clips = true;
         const int d = state_depth[o.clip_in] + 1;
         if (d > 250) {
           set_error("clip stack deeper than 250");

@@ -21,6 +21,7 @@
 #define SKB_CLIP_CUH
 
 #include "skity_b200/csrc/skb_core.cuh"
+#include "skity_b200/csrc/skb_sort.cuh"
 
 namespace skb {
 
@@ -291,6 +292,71 @@ SKB_HDN void clip_row_focus(ClipRowState& st, int xa, int xb) {
     st.act[n++] = (uint8_t)k;
   }
   st.n_act = n;
+}
+
+// ---- ClipOp::kDifference ------------------------------------------------------------------------------------------
+// A state whose op is kDifference keeps the clip path's spans as they were rasterised and a draw is cut span by span
+// (SWCanvas::State::PerformClip -> spans_subtraction, src/render/sw/sw_canvas.cc:56-133,158-161).  The reference's
+// subtraction is sequential over the row's clip spans SORTED BY x (std::sort, ties as libstdc++ leaves them), ignores
+// their coverage, and — by its own comment "not correct" — keeps what a clip span overlaps on the LEFT of the running
+// span; all of it is observable and reproduced.  A difference state is therefore stored as per-row sorted span lists
+// (x, len), not as the per-pixel entry table of intersecting states.
+//
+// The spans of one rasterised row in the order the reference's list holds them: the directly emitted spans as the
+// sweep emits them (ascending x: one-pixel spans under slanted edges, one span per fully covered interior), then the
+// row's accumulated coverage run-length encoded (SpanBuilder::Flush, sw_raster.cc:108-136) — an accumulated row is
+// flushed after the sweep has left it.  Calls onD(x, len, cover) / onA(x, len, cover).
+template <class OnD, class OnA>
+SKB_HDN void clip_row_spans(ClipRowState& st, const TrapRec* pool, uint2 row, int x_first, int x_last, OnD& onD, OnA& onA) {
+  for (int x = x_first; x <= x_last; x++) {
+    SpanSide ld, od, la, oa;
+    clip_row_step(st, pool, row, x, ld, od, la, oa);
+    if (la.present) onA(la.start, x - la.start, la.cover);
+    if (od.present && st.prev_d_ends) onD(od.start, x + 1 - od.start, od.cover);
+  }
+  if (st.prev_a != 0) onA(st.prev_a_start, x_last + 1 - st.prev_a_start, st.prev_a);
+}
+
+struct SpanXLess {
+  SKB_HD bool operator()(const uint2& a, const uint2& b) const { return (int)a.x < (int)b.x; }
+};
+
+// spans_subtraction for ONE span [sx, sx + slen) against the row's clip spans ms[0..n) (x, len; sorted by x).
+// Calls emit(x, len) for every piece the reference appends, zero-length pieces included.
+template <class Emit>
+SKB_HDN void span_subtract(int sx, int slen, const uint2* ms, int n, Emit& emit) {
+  if (n == 0) {   // "no spans in this line means minus zero"
+    emit(sx, slen);
+    return;
+  }
+  int cx = sx, cl = slen;
+  for (int j = 0; j < n; j++) {
+    const int mx = (int)ms[j].x, ml = (int)ms[j].y;
+    if (mx + ml < cx || mx > cx + cl) continue;
+    if (mx < cx) {
+      if (mx + ml > cx + cl) {
+        cl = 0;
+        break;
+      }
+      const int last = cx + cl, len = mx + ml - cx;
+      if (len == 0) continue;
+      emit(cx, len);   // the overlapped part is KEPT (sw_canvas.cc:84-98)
+      cx += len;
+      cl = last - cx;
+    } else {
+      if (mx + ml < cx + cl) {
+        const int last = cx + cl;
+        emit(cx, mx - cx);
+        cx = mx + ml;
+        cl = last - cx;
+      } else {
+        emit(cx, mx - cx);
+        cl = 0;
+      }
+    }
+    if (cl <= 0) break;
+  }
+  if (cl > 0) emit(cx, cl);
 }
 
 }  // namespace skb

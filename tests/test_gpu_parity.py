@@ -48,7 +48,8 @@ def assert_within_tolerance(got, want):
 EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c3_blur_12_640",
          "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144",
          "blend_modes_480", "filters_512", "layers_512", "filters_channel_carry_283", "blend_zero_then_accum_418",
-         "clipped_blends_400", "filtered_layers_384", "filters_morphology_512", "images_same_size_256"]
+         "clipped_blends_400", "filtered_layers_384", "filters_morphology_512", "images_same_size_256",
+         "ref_clip_path_difference_400", "clip_difference_flat_8", "clip_difference_flat_31"]
 
 
 @pytest.mark.parametrize("name", EXACT)
@@ -230,19 +231,53 @@ def test_clip_that_rasterises_to_nothing_clips_nothing(dev):
     assert np.array_equal(render(dev, dl, 200, 200), want)
 
 
-def test_difference_clip_is_refused_not_approximated(dev):
-    from skity_b200 import device
-    s = Scene(64, 64)
+@pytest.mark.parametrize("seed0", [2000, 2040])
+def test_difference_clips_seeded(dev, seed0):
+    """ClipOp::kDifference, one clip per Save level (sw_canvas.cc:56-133): the reference's sequential span subtraction
+    with its std::sort tie order and its left-overlap quirk, bit for bit; translucent and stroked draws included."""
+    bad = []
+    for seed in range(seed0, seed0 + 40):
+        s = scene.scene_difference_clips(seed, "flat")
+        dl = hostlib.encode_scene(s.encode())
+        if not np.array_equal(render(dev, dl, s.width, s.height), port.render(dl)):
+            bad.append(seed)
+    assert not bad, bad
+
+
+def test_difference_clip_under_zero_source_blend_modes(dev):
+    """Blend modes that act on zero-coverage pixels (kClear, kSrc, kSrcIn ...) under a difference clip: the pieces of a
+    directly emitted span of coverage 0 still blend."""
+    from skity_b200.scene import _random_closed_path
+    rng = np.random.RandomState(7)
+    s = Scene(320, 260)
+    s.draw_rect(0, 0, 320, 260, Paint(fill=(0.2, 0.6, 0.3, 1.0)))
     s.save()
-    s.clip_path(scene.star_path(), False)
-    s.draw_rect(0, 0, 64, 64, Paint(fill=(0, 0, 1, 1)))
+    s.clip_path(_random_closed_path(rng, 150, 120, 260.0, 3), False)
+    for i, mode in enumerate([0, 1, 5, 6, 7, 9, 3]):
+        col = tuple(np.float32(v) for v in rng.uniform(0.2, 1, 4))
+        s.draw_path(_random_closed_path(rng, rng.uniform(40, 280), rng.uniform(40, 220), 220.0, i), Paint(fill=col, blend=mode))
     s.restore()
     dl = hostlib.encode_scene(s.encode())
-    surf = dev.create_surface(64, 64)
-    surf.begin(True)
-    with pytest.raises(device.SkbError):
-        surf.encode(dl)
-    surf.close()
+    assert np.array_equal(render(dev, dl, 320, 260), port.render(dl))
+
+
+def test_combined_difference_clips_are_refused_not_approximated(dev):
+    """A difference clip combined with another PATH clip in one chain goes through RecursiveClip's whole-list
+    subtraction / PerformMerge in the reference (sw_canvas.cc:178-217): not on the device, and never approximated."""
+    from skity_b200 import device
+    for first, second in ((True, False), (False, True), (False, False)):
+        s = Scene(64, 64)
+        s.save()
+        s.clip_path(scene.star_path(), first)
+        s.clip_path(scene.star_path(), second)
+        s.draw_rect(0, 0, 64, 64, Paint(fill=(0, 0, 1, 1)))
+        s.restore()
+        dl = hostlib.encode_scene(s.encode())
+        surf = dev.create_surface(64, 64)
+        surf.begin(True)
+        with pytest.raises(device.SkbError):
+            surf.encode(dl)
+        surf.close()
 
 
 def test_plugin_path_matches_reference():
