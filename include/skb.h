@@ -134,7 +134,14 @@ SKB_API skb_result skb_frame_flush(skb_surface surface);
 /* Blocks until the surface's stream is idle; returns the first asynchronous error. */
 SKB_API skb_result skb_surface_sync(skb_surface surface);
 
-/* Copies the rectangle to host memory (rows `stride` bytes apart).  Synchronises. */
+/* Page-locked host memory: display lists encoded into it upload asynchronously at PCIe speed, read-backs into it need no
+ * staging.  (The plug-in keeps its per-frame display list in such a buffer.) */
+SKB_API skb_result skb_host_alloc(size_t bytes, void** out_ptr);
+SKB_API void skb_host_free(void* ptr);
+
+/* Copies the rectangle to host memory (rows `stride` bytes apart).  Synchronises.  A large read into pageable memory
+ * (a fresh Pixmap) is staged through two page-locked buffers of the surface, chunk by chunk, with the host copy done by
+ * several threads. */
 SKB_API skb_result skb_surface_read_pixels(skb_surface surface, uint32_t x, uint32_t y, uint32_t width,
                                            uint32_t height, void* dst, size_t stride);
 /* Same copy, enqueued on the surface's stream without waiting: `dst` (pinned host memory for a truly

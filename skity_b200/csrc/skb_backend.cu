@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "include/skb.h"
@@ -1686,6 +1687,8 @@ struct FineArgs {
 #endif
 __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   __shared__ uint2 s_cmd[FINE_WARPS][FINE_SORT_CAP];
+  __shared__ uint32_t s_src[FINE_WARPS][256];   // paint colours of a tile's covered pixels (gradient commands)
+  __shared__ uint8_t s_pix[FINE_WARPS][256];    // which pixels those are
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint8_t* const s_requant = nullptr;  // the sampler's byte round trip is the identity (skb_core.cuh)
   const uint32_t tile = a.tile_begin + blockIdx.x * FINE_WARPS + warp;
@@ -1822,7 +1825,10 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
       }
       const uint32_t pidx = a.ops[op].paint;
       const uint32_t ptype = a.paints[pidx].type;
-      if ((lo | hi | zlo | zhi) == 0) continue;
+      // gradients (and bilinear images) are evaluated for the tile's covered pixels dealt evenly to the lanes; the
+      // per-lane shortcut below would leave that warp-wide step
+      const bool dealt = (ptype >= SKB_PAINT_LINEAR && ptype <= SKB_PAINT_SWEEP) || ptype == SKB_PAINT_CONICAL;
+      if (!dealt && (lo | hi | zlo | zhi) == 0) continue;
       const skb_dl_paint pt = a.paints[pidx];
       const uint32_t galpha = ptype == SKB_PAINT_IMAGE ? (pt.global_alpha & 0xFF) : 0xFFu;
       SurfaceView img;
@@ -1863,6 +1869,55 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
             else dst[j] = porter_duff(src, dst[j], mode);
           }
         }
+        continue;
+      }
+      if (dealt) {
+        // Gradient paint: paint_color() is by far the most expensive step (fp32 with IEEE division / square root, the
+        // fdlibm atan2f of the sweep gradient) and a mask covers only part of a tile — evaluated by the owner of each
+        // pixel, half of the lanes wait for the other half.  Instead the covered pixels of the tile are listed (ballot-
+        // free prefix over the lanes' counts) and dealt out 32 at a time: every lane computes the colour of ONE covered
+        // pixel per round, into shared memory; then each lane scales / filters / blends its own eight from there.
+        uint32_t need = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t cvj = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
+          const bool touched = cvj != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
+          if ((cvj & galpha) || (touched && zmode)) need |= 1u << j;
+        }
+        const int cnt = __popc(need);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total == 0) continue;   // uniform over the warp
+        {
+          int k = incl - cnt;
+          for (uint32_t m = need; m; m &= m - 1) s_pix[warp][k++] = (uint8_t)(lane * 8 + (__ffs((int)m) - 1));
+        }
+        __syncwarp();
+        for (int b = 0; b < total; b += 32) {
+          const int idx = b + lane;
+          if (idx < total) {
+            const int pid = s_pix[warp][idx];
+            const int ln = pid >> 3;
+            const int px_ = tx * SKB_TILE + (ln & 1) * 8 + (pid & 7), py_ = ty * SKB_TILE + (ln >> 1);
+            s_src[warp][pid] = paint_color(pt, a.stops, img, px_, py_, s_requant);
+          }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+          if (!((need >> j) & 1u)) continue;
+          const uint32_t cv = (((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF) & galpha;
+          uint32_t src = swap_rb(s_src[warp][lane * 8 + j]);
+          if (cv != 255) src = alpha_mul_q(src, cv);
+          if (cf) src = apply_color_filter(cf, src);
+          dst[j] = porter_duff(src, dst[j], mode);
+        }
+        __syncwarp();   // the next command reuses the lists
         continue;
       }
 #pragma unroll 1
@@ -2228,7 +2283,9 @@ struct skb_surface_s {
   bool plan_clip_ops = false, plan_clipped_fills = false, plan_diff_clips = false;
   int plan_max_depth = 0;
   std::vector<uint8_t> plan_op_depth;     // nesting depth of the clip state a CLIP op defines (empty without clip ops)
-  std::vector<uint32_t> plan_blur_ops;    // indices of the BLUR ops, in op order
+  std::vector<skb_dl_op> plan_blur_ops;   // the BLUR ops, in op order
+  uint8_t* stage[2] = {nullptr, nullptr};   // page-locked staging for reads into pageable memory (skb_surface_read_pixels)
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int walk_mode = 0;
   int coverage_mode = SKB_COVERAGE_EXACT;
   cudaStream_t stream = nullptr;
@@ -2509,7 +2566,6 @@ static skb_result run_frame(skb_surface s) {
   skb_dl_header h;
   memcpy(&h, dl, sizeof(h));
   const skb_dl_surface* hs = (const skb_dl_surface*)(dl + h.off_surfaces);
-  const skb_dl_op* hops = (const skb_dl_op*)(dl + h.off_ops);
   cudaStream_t st = s->stream;
   skb_frame_stats& S = s->stats;
   memset(&S, 0, sizeof(S));
@@ -2581,6 +2637,9 @@ static skb_result run_frame(skb_surface s) {
   const uint32_t n_ops = h.n_ops, n_segs = h.n_segs;
   s->n_ops = n_ops;
   if (n_ops == 0) {
+    // nothing to launch; the (tiny) upload must still have left the caller's buffer when this returns, as it has
+    // on every other path (the first count fetched from the device waits for it)
+    SKB_CUDA(cudaStreamSynchronize(st));
     s->flushed = true;
     return SKB_SUCCESS;
   }
@@ -3028,16 +3087,16 @@ static skb_result run_frame(skb_surface s) {
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.zplane[k] = ca.zplane[k];
   // blur jobs of the whole frame, sorted by the level of their destination
   std::vector<BlurJob> jobs;
-  for (uint32_t i : s->plan_blur_ops) {
+  for (const skb_dl_op& bo : s->plan_blur_ops) {
     {
       BlurJob j;
-      j.src = hops[i].aux;
-      j.dst = hops[i].surface;
-      j.radius = (int32_t)hops[i].clip_bounds[0];
-      j.style = hops[i].fill_type;
-      j.color = hops[i].paint;
-      j.morph_rx = hops[i].clip_bounds[0];
-      j.morph_ry = hops[i].clip_bounds[1];
+      j.src = bo.aux;
+      j.dst = bo.surface;
+      j.radius = (int32_t)bo.clip_bounds[0];
+      j.style = bo.fill_type;
+      j.color = bo.paint;
+      j.morph_rx = bo.clip_bounds[0];
+      j.morph_ry = bo.clip_bounds[1];
       if (surfs[j.src].w != surfs[j.dst].w || surfs[j.src].h != surfs[j.dst].h) {
         set_error("blur: source and destination surfaces differ in size");
         return SKB_ERROR_BAD_DISPLAY_LIST;
@@ -3277,6 +3336,10 @@ void skb_surface_destroy(skb_surface s) {
   if (s->remote_canvas) cudaIpcCloseMemHandle(s->remote_canvas);
   if (s->canvas) cudaFree(s->canvas);
   if (s->mapped_host) cudaFreeHost(s->mapped_host);
+  for (int i = 0; i < 2; i++) {
+    if (s->stage[i]) cudaFreeHost(s->stage[i]);
+    if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]);
+  }
   for (int i = 0; i < 12; i++)
     if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   for (int i = 0; i < 32; i++)
@@ -3357,8 +3420,9 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
   SKB_TRY(validate_dl((const uint8_t*)dl, bytes));
   skb_dl_header h;
   memcpy(&h, dl, sizeof(h));
-  // the header tables (surfaces, ops) are also read on the host while launching
-  s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_paths);
+  // the header and the surface table are also read on the host while launching (what run_frame needs of the ops is
+  // worked out below, once)
+  s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_ops);
   // dependency depth of every surface: a surface is composited after the surfaces its draws sample
   // (image paints) and after the source of the blur that produces it
   {
@@ -3380,7 +3444,7 @@ skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
         if (o.clip_in != 0) s->plan_clipped_fills = true;
       } else if (o.kind == SKB_OP_BLUR) {
         src = o.aux;
-        s->plan_blur_ops.push_back(i);
+        s->plan_blur_ops.push_back(o);
       } else if (o.kind == SKB_OP_CLIP) {
         if (!s->plan_clip_ops) s->plan_op_depth.assign(h.n_ops, 0);
         s->plan_clip_ops = true;
@@ -3438,13 +3502,89 @@ skb_result skb_surface_sync(skb_surface s) {
   return SKB_SUCCESS;
 }
 
+// Copies rows [r0, r1) of a staged chunk into the caller's buffer with a few host threads: the destination of a large
+// read-back is usually memory nobody has touched yet (a fresh Pixmap), and one thread page-faulting its way through it
+// is several times slower than the PCIe copy that feeds it.
+static void copy_rows_parallel(uint8_t* dst, size_t dst_stride, const uint8_t* src, size_t src_stride, size_t row_bytes, uint32_t rows) {
+  const size_t bytes = (size_t)rows * row_bytes;
+  unsigned nt = bytes >= ((size_t)8 << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+  auto work = [&](uint32_t a, uint32_t b) {
+    if (dst_stride == row_bytes && src_stride == row_bytes) {
+      memcpy(dst + (size_t)a * row_bytes, src + (size_t)a * row_bytes, (size_t)(b - a) * row_bytes);
+    } else {
+      for (uint32_t r = a; r < b; r++) memcpy(dst + (size_t)r * dst_stride, src + (size_t)r * src_stride, row_bytes);
+    }
+  };
+  if (nt <= 1) {
+    work(0, rows);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < nt; t++) th.emplace_back(work, (uint32_t)((uint64_t)rows * t / nt), (uint32_t)((uint64_t)rows * (t + 1) / nt));
+  for (auto& t : th) t.join();
+}
+
+#define SKB_STAGE_BYTES ((size_t)32 << 20)
+
 skb_result skb_surface_read_pixels(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst, size_t stride) {
   if (!s || !dst || !rect_inside(s, x, y, w, h) || stride < (size_t)w * 4) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
-  SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, (size_t)w * 4, h,
+  const size_t row_bytes = (size_t)w * 4;
+  // Pageable destination and a transfer worth the trouble: the driver would stage it through its own small bounce
+  // buffer at a few GB/s.  Instead the rectangle travels in chunks through two page-locked buffers of the surface, the
+  // copy of chunk k + 1 over PCIe overlapping the host copy of chunk k into the destination.
+  cudaPointerAttributes pa;
+  const bool pageable = cudaPointerGetAttributes(&pa, dst) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+  cudaGetLastError();
+  if (pageable && row_bytes * h >= ((size_t)4 << 20) && row_bytes <= SKB_STAGE_BYTES) {
+    for (int i = 0; i < 2; i++) {
+      if (!s->stage[i]) SKB_CUDA(cudaHostAlloc((void**)&s->stage[i], SKB_STAGE_BYTES, cudaHostAllocDefault));
+      if (!s->stage_ev[i]) SKB_CUDA(cudaEventCreateWithFlags(&s->stage_ev[i], cudaEventDisableTiming));
+    }
+    const uint32_t rows_per = (uint32_t)(SKB_STAGE_BYTES / row_bytes);
+    uint32_t issued = 0, done = 0;
+    int k_issue = 0, k_done = 0;
+    uint32_t rows_of[2] = {0, 0}, row0_of[2] = {0, 0};
+    while (done < h) {
+      while (issued < h && k_issue - k_done < 2) {
+        const int b = k_issue & 1;
+        const uint32_t n = std::min(rows_per, h - issued);
+        SKB_CUDA(cudaMemcpy2DAsync(s->stage[b], row_bytes, s->canvas + (size_t)(y + issued) * s->pitch + (size_t)x * 4, s->pitch,
+                                   row_bytes, n, cudaMemcpyDeviceToHost, s->stream));
+        SKB_CUDA(cudaEventRecord(s->stage_ev[b], s->stream));
+        rows_of[b] = n;
+        row0_of[b] = issued;
+        issued += n;
+        k_issue++;
+      }
+      const int b = k_done & 1;
+      SKB_CUDA(cudaEventSynchronize(s->stage_ev[b]));
+      copy_rows_parallel((uint8_t*)dst + (size_t)row0_of[b] * stride, stride, s->stage[b], row_bytes, row_bytes, rows_of[b]);
+      done += rows_of[b];
+      k_done++;
+    }
+    return SKB_SUCCESS;
+  }
+  SKB_CUDA(cudaMemcpy2DAsync(dst, stride, s->canvas + (size_t)y * s->pitch + (size_t)x * 4, s->pitch, row_bytes, h,
                              cudaMemcpyDeviceToHost, s->stream));
   SKB_CUDA(cudaStreamSynchronize(s->stream));
   return SKB_SUCCESS;
+}
+
+skb_result skb_host_alloc(size_t bytes, void** out) {
+  if (!out || bytes == 0) return SKB_ERROR_INVALID_ARGUMENT;
+  *out = nullptr;
+  const cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error(std::string("page-locked host allocation failed: ") + cudaGetErrorString(e));
+    return SKB_ERROR_OUT_OF_MEMORY;
+  }
+  return SKB_SUCCESS;
+}
+
+void skb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
 }
 
 skb_result skb_surface_read_pixels_async(skb_surface s, uint32_t x, uint32_t y, uint32_t w, uint32_t h, void* dst,

@@ -21,7 +21,10 @@ class CudaGPUSurface : public GPUSurface {
  public:
   CudaGPUSurface(GPUContext* ctx, skb_surface surface, uint32_t w, uint32_t h, float scale)
       : ctx_(ctx), surface_(surface), width_(w), height_(h), content_scale_(scale) {}
-  ~CudaGPUSurface() override { skb_surface_destroy(surface_); }
+  ~CudaGPUSurface() override {
+    skb_surface_destroy(surface_);
+    skb_host_free(dl_buf_);
+  }
 
   GPUBackendType GetBackendType() const override { return kGPUBackendTypeCUDA; }
   uint32_t GetWidth() const override { return width_; }
@@ -43,8 +46,27 @@ class CudaGPUSurface : public GPUSurface {
       std::string msg = "skity-b200: dropped draws using " + canvas_->Unsupported();
       ctx_->TriggerErrorCallback(GPUError::kGPUError, msg.c_str());
     }
-    std::vector<uint8_t> dl = builder_.Serialize();
-    if (skb_frame_encode(surface_, dl.data(), dl.size()) != SKB_SUCCESS || skb_frame_flush(surface_) != SKB_SUCCESS) {
+    // The frame's display list is laid out straight into a page-locked buffer the surface keeps (grown geometrically):
+    // the upload is then one asynchronous copy at PCIe speed.  skb_frame_flush returns after the device has consumed
+    // the list's tables, so the buffer is free again when the next frame is flushed.
+    const skb::DlBuilder::Layout layout = builder_.MakeLayout();
+    const size_t need = layout.h.total_bytes;
+    if (need > dl_cap_) {
+      skb_host_free(dl_buf_);
+      dl_buf_ = nullptr;
+      dl_cap_ = 0;
+      const size_t want = need + need / 2 + (static_cast<size_t>(1) << 20);
+      void* p = nullptr;
+      if (skb_host_alloc(want, &p) != SKB_SUCCESS) {
+        Report();
+        canvas_.reset();
+        return;
+      }
+      dl_buf_ = p;
+      dl_cap_ = want;
+    }
+    builder_.SerializeInto(layout, static_cast<uint8_t*>(dl_buf_));
+    if (skb_frame_encode(surface_, dl_buf_, need) != SKB_SUCCESS || skb_frame_flush(surface_) != SKB_SUCCESS) {
       Report();
     }
     canvas_.reset();
@@ -77,6 +99,8 @@ class CudaGPUSurface : public GPUSurface {
   float content_scale_;
   skb::DlBuilder builder_;
   std::unique_ptr<CudaCanvas> canvas_;
+  void* dl_buf_ = nullptr;   // page-locked (skb_host_alloc)
+  size_t dl_cap_ = 0;
 };
 
 class CudaGPUContext : public GPUContext {

@@ -9,7 +9,9 @@
 
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "include/skb_dl.h"
@@ -123,9 +125,17 @@ class DlBuilder {
   size_t OpCount() const { return ops_.size(); }
   uint32_t SurfaceCount() const { return static_cast<uint32_t>(surfaces_.size()); }
 
-  std::vector<uint8_t> Serialize() const {
+  // The flat display list in two steps, so that the caller can hand in its own (page-locked) buffer:
+  // Layout() fixes the section offsets and the total size, SerializeInto() writes `total_bytes` bytes.
+  struct Layout {
+    skb_dl_header h;
+    std::vector<uint32_t> image_off;   // byte offset of every image's pixels
+  };
+  Layout MakeLayout() const {
     auto align16 = [](size_t v) { return (v + 15) & ~static_cast<size_t>(15); };
-    skb_dl_header h{};
+    Layout L;
+    skb_dl_header& h = L.h;
+    h = skb_dl_header{};
     h.magic = SKB_DL_MAGIC;
     h.version = SKB_DL_VERSION;
     h.n_surfaces = static_cast<uint32_t>(surfaces_.size());
@@ -148,24 +158,61 @@ class DlBuilder {
     off = align16(off + paints_.size() * sizeof(skb_dl_paint));
     h.off_stops = static_cast<uint32_t>(off);
     off = align16(off + stops_.size() * sizeof(float));
-    std::vector<skb_dl_surface> surfaces = surfaces_;
     for (const auto& im : images_) {  // image pixels go last
-      surfaces[im.surface].reserved = static_cast<uint32_t>(off);
+      L.image_off.push_back(static_cast<uint32_t>(off));
       off = align16(off + im.pixels.size());
     }
     h.total_bytes = static_cast<uint32_t>(off);
-    std::vector<uint8_t> out(off, 0);
-    std::memcpy(out.data(), &h, sizeof(h));
-    auto put = [&](uint32_t o, const void* p, size_t n) {
-      if (n) std::memcpy(out.data() + o, p, n);
+    return L;
+  }
+
+  // `out`: L.h.total_bytes bytes.  Every byte is written (padding as zero), so a reused buffer needs no clearing.  The
+  // large sections are copied by a few threads: at 1M draws the list is ~0.5 GB and one thread's memcpy would cost more
+  // than the frame takes on the device.
+  void SerializeInto(const Layout& L, uint8_t* out) const {
+    const skb_dl_header& h = L.h;
+    std::vector<skb_dl_surface> surfaces = surfaces_;
+    for (size_t i = 0; i < images_.size(); i++) surfaces[images_[i].surface].reserved = L.image_off[i];
+    struct Part { size_t off; const void* p; size_t n; };
+    std::vector<Part> parts;
+    parts.push_back({0, &h, sizeof(h)});
+    parts.push_back({h.off_surfaces, surfaces.data(), surfaces.size() * sizeof(skb_dl_surface)});
+    parts.push_back({h.off_ops, ops_.data(), ops_.size() * sizeof(skb_dl_op)});
+    parts.push_back({h.off_paths, paths_.data(), paths_.size() * sizeof(skb_dl_path)});
+    parts.push_back({h.off_segs, segs_.data(), segs_.size() * sizeof(skb_dl_seg)});
+    parts.push_back({h.off_paints, paints_.data(), paints_.size() * sizeof(skb_dl_paint)});
+    parts.push_back({h.off_stops, stops_.data(), stops_.size() * sizeof(float)});
+    for (size_t i = 0; i < images_.size(); i++) parts.push_back({L.image_off[i], images_[i].pixels.data(), images_[i].pixels.size()});
+    // the gaps between the parts (alignment padding, at most 15 bytes each) are zeroed
+    for (size_t i = 0; i < parts.size(); i++) {
+      const size_t end = parts[i].off + parts[i].n;
+      const size_t next = i + 1 < parts.size() ? parts[i + 1].off : h.total_bytes;
+      if (next > end) std::memset(out + end, 0, next - end);
+    }
+    // work items of at most 8 MB, dealt to the threads round-robin
+    struct Item { uint8_t* d; const uint8_t* s; size_t n; };
+    std::vector<Item> items;
+    const size_t kChunk = static_cast<size_t>(8) << 20;
+    for (const Part& p : parts)
+      for (size_t o = 0; o < p.n; o += kChunk)
+        items.push_back({out + p.off + o, static_cast<const uint8_t*>(p.p) + o, std::min(kChunk, p.n - o)});
+    unsigned nt = h.total_bytes >= (static_cast<size_t>(32) << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+    auto work = [&](unsigned t) {
+      for (size_t i = t; i < items.size(); i += nt) std::memcpy(items[i].d, items[i].s, items[i].n);
     };
-    put(h.off_surfaces, surfaces.data(), surfaces.size() * sizeof(skb_dl_surface));
-    for (const auto& im : images_) put(surfaces[im.surface].reserved, im.pixels.data(), im.pixels.size());
-    put(h.off_ops, ops_.data(), ops_.size() * sizeof(skb_dl_op));
-    put(h.off_paths, paths_.data(), paths_.size() * sizeof(skb_dl_path));
-    put(h.off_segs, segs_.data(), segs_.size() * sizeof(skb_dl_seg));
-    put(h.off_paints, paints_.data(), paints_.size() * sizeof(skb_dl_paint));
-    put(h.off_stops, stops_.data(), stops_.size() * sizeof(float));
+    if (nt <= 1) {
+      work(0);
+      return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto& t : th) t.join();
+  }
+
+  std::vector<uint8_t> Serialize() const {
+    const Layout L = MakeLayout();
+    std::vector<uint8_t> out(L.h.total_bytes);
+    SerializeInto(L, out.data());
     return out;
   }
 

@@ -590,3 +590,21 @@ def test_area_versus_exact_mode_histogram(dev):
     print(f"AREA vs exact, c1-style 2000 paths 2048^2: <=1/255 on {float((d <= 1).mean()):.4%}, <=2/255 on "
           f"{float((d <= 2).mean()):.4%}, <=8/255 on {float((d <= 8).mean()):.4%}, max {int(d.max())}")
     assert float((d <= 8).mean()) > 0.9
+
+
+@pytest.mark.parametrize("seed0", [50000, 50050, 50100, 50150])
+def test_fuzz_scenes_of_every_feature_class(dev, seed0):
+    """200 seeded random scenes of the ten feature classes of scene.scene_fuzz (fills, gradients, nested clips, blur,
+    transforms + conics + strokes, blend modes, filters, layers, conical gradients; tests/gpu_fuzz.py is the manual
+    form of this loop): integer paths bit-exact against the pinned port, fp32 paints within the north star's tolerance."""
+    bad = []
+    for seed in range(seed0, seed0 + 50):
+        s, exact = scene.scene_fuzz(seed)
+        dl = hostlib.encode_scene(s.encode())
+        want = port.render(dl)
+        got = render(dev, dl, s.width, s.height)
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2)
+        ok = d.max() == 0 if exact else (d.max() <= 2 and float((d <= 1).mean()) >= 0.999)
+        if not ok:
+            bad.append((seed, int(d.max()), int((d > 0).sum())))
+    assert not bad, bad
