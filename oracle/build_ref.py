@@ -48,6 +48,18 @@ src/base/platform/posix/file_posix.cc src/base/platform/posix/mapping_posix.cc
 """.split()
 
 
+IO_TUS = """
+module/io/src/io/flat/blender_flat.cc module/io/src/io/flat/blob_flat.cc module/io/src/io/flat/color_filter_flat.cc
+module/io/src/io/flat/font_desc_flat.cc module/io/src/io/flat/font_flat.cc module/io/src/io/flat/image_filter_flat.cc
+module/io/src/io/flat/local_matrix_flat.cc module/io/src/io/flat/mask_filter_flat.cc module/io/src/io/flat/matrix_flat.cc
+module/io/src/io/flat/paint_flat.cc module/io/src/io/flat/path_flat.cc module/io/src/io/flat/path_effect_flat.cc
+module/io/src/io/flat/rrect_flat.cc module/io/src/io/flat/shader_flat.cc module/io/src/io/flat/vertices_flat.cc
+module/io/src/io/read/read_typeface.cc module/io/src/io/memory_read.cc module/io/src/io/memory_writer.cc
+module/io/src/record/record_playback.cc module/io/src/stream/file_read_stream.cc module/io/src/stream/file_write_stream.cc
+module/io/src/stream/stream.cc module/io/src/utils/parse_path.cc module/io/src/picture.cc
+""".split()   # module/io (.skp), as in skity_b200/build.py
+
+
 def cxx_flags(ref, opt, march=None):
     return [
         "-std=c++17", opt, *([f"-march={march}", "-ffp-contract=off"] if march else []), "-fPIC", "-w", "-DSKITY_CPU", "-DSKITY_RELEASE", "-DNDEBUG",
@@ -57,6 +69,7 @@ def cxx_flags(ref, opt, march=None):
         # (-std=c++17 => -ffp-contract=off), so it renders the same bytes — checked by tests/test_oracle_pinning.py
         f"-I{ref}", f"-I{ref}/include", f"-I{ref}/module/wgx/include",
         f"-I{REPO}/third_party/glm_shim", f"-I{REPO}",
+        f"-I{ref}/module/io/include", f"-I{ref}/module/io", f"-I{ref}/module/io/src", f"-I{ref}/module/codec/include",
     ]
 
 
@@ -100,6 +113,8 @@ def build(ref="/root/reference", out=None, opt="-O2", jobs=None, name="libskity_
         if not os.path.exists(src):
             raise FileNotFoundError(src)
         work.append((src, os.path.join(objdir, tu.replace("/", "_") + ".o"), flags))
+    for tu in IO_TUS:   # picture.cc uses std::memcpy without including <cstring>
+        work.append((os.path.join(ref, tu), os.path.join(objdir, tu.replace("/", "_") + ".o"), flags + ["-include", "cstring"]))
     drv_obj = os.path.join(objdir, os.path.basename(driver) + ".o")
     # the driver replays scenes with the repo's scene player: rebuild it when that header changes
     player = os.path.join(REPO, "skity_b200", "host", "scene_player.hpp")
@@ -120,7 +135,7 @@ def build(ref="/root/reference", out=None, opt="-O2", jobs=None, name="libskity_
     lib = os.path.join(out, name)
     subprocess.check_call(["g++", "-shared", "-o", lib, *objs, stubs_o, "-Wl,--no-undefined", "-lpthread"])
     if verbose:
-        print(f"built {lib} ({len(TUS)} reference TUs, {len(missing)} text stubs)")
+        print(f"built {lib} ({len(TUS)} reference + {len(IO_TUS)} module/io TUs, {len(missing)} text stubs)")
     return lib
 
 

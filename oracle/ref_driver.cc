@@ -17,6 +17,7 @@
 #include <skity/render/canvas.hpp>
 
 #include "skity_b200/host/scene_player.hpp"
+#include "skity_b200/host/skp_player.hpp"
 #include "src/render/hw/coverage/coverage_aa_line_encoder.hpp"
 #include "src/render/hw/coverage/coverage_aa_tiler.hpp"
 #include "src/render/sw/sw_raster.hpp"
@@ -47,6 +48,26 @@ int ref_render_scene(const uint8_t* scene, size_t n, uint8_t* out_rgba, double* 
     std::memcpy(out_rgba + static_cast<size_t>(y) * h.width * 4,
                 bitmap.GetPixelAddr() + static_cast<size_t>(y) * bitmap.RowBytes(),
                 static_cast<size_t>(h.width) * 4);
+  }
+  return 0;
+}
+
+// Plays a serialized picture (.skp, module/io) onto the reference software canvas of a width x height bitmap under the
+// affine matrix m6 (sx kx tx ky sy ty) — the reference side of tests/golden's skp fixtures.
+int ref_render_skp(const uint8_t* skp, size_t n, uint32_t width, uint32_t height, const float* m6, uint8_t* out_rgba, double* seconds) {
+  skity::Bitmap bitmap(width, height, skity::AlphaType::kPremul_AlphaType);
+  if (bitmap.GetPixelAddr() == nullptr) return -6;
+  auto canvas = skity::Canvas::MakeSoftwareCanvas(&bitmap);
+  if (!canvas) return -7;
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = skb_skp::Play(skp, n, m6, canvas.get());
+  canvas->Flush();
+  auto t1 = std::chrono::steady_clock::now();
+  if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+  if (rc != 0) return rc;
+  for (uint32_t y = 0; y < height; y++) {
+    std::memcpy(out_rgba + static_cast<size_t>(y) * width * 4, bitmap.GetPixelAddr() + static_cast<size_t>(y) * bitmap.RowBytes(),
+                static_cast<size_t>(width) * 4);
   }
   return 0;
 }

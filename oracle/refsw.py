@@ -43,6 +43,9 @@ def lib():
         _lib.ref_render_scene.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p,
                                           ctypes.POINTER(ctypes.c_double)]
         _lib.ref_render_scene.restype = ctypes.c_int
+        _lib.ref_render_skp.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float),
+                                        ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+        _lib.ref_render_skp.restype = ctypes.c_int
         _lib.ref_raster_path.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
         _lib.ref_raster_path.restype = ctypes.c_long
@@ -64,6 +67,17 @@ def render_scene(blob, return_seconds=False):
     rc = lib().ref_render_scene(blob, len(blob), out.ctypes.data, ctypes.byref(sec))
     if rc != 0:
         raise RuntimeError(f"ref_render_scene failed: {rc}")
+    return (out, sec.value) if return_seconds else out
+
+
+def render_skp(skp, width, height, matrix6=(1, 0, 0, 0, 1, 0), return_seconds=False):
+    """A serialized picture (.skp bytes) played back onto the reference SW canvas -> (H, W, 4) uint8 premul RGBA."""
+    out = np.zeros((height, width, 4), dtype=np.uint8)
+    sec = ctypes.c_double(0.0)
+    m = (ctypes.c_float * 6)(*matrix6)
+    rc = lib().ref_render_skp(skp, len(skp), int(width), int(height), m, out.ctypes.data, ctypes.byref(sec))
+    if rc != 0:
+        raise RuntimeError(f"ref_render_skp failed: {rc}")
     return (out, sec.value) if return_seconds else out
 
 

@@ -48,6 +48,24 @@ src/base/mapping.cc src/base/unique_fd.cc
 src/base/platform/posix/file_posix.cc src/base/platform/posix/mapping_posix.cc
 """.split()
 
+# The reference's .skp reader / writer (module/io/CMakeLists.txt:5-43): linked so that serialized pictures can be played
+# onto the canvas (skp_player.hpp).  Its text and image-codec references resolve to the aborting stubs like the core's.
+SKITY_IO_TUS = """
+module/io/src/io/flat/blender_flat.cc module/io/src/io/flat/blob_flat.cc module/io/src/io/flat/color_filter_flat.cc
+module/io/src/io/flat/font_desc_flat.cc module/io/src/io/flat/font_flat.cc module/io/src/io/flat/image_filter_flat.cc
+module/io/src/io/flat/local_matrix_flat.cc module/io/src/io/flat/mask_filter_flat.cc module/io/src/io/flat/matrix_flat.cc
+module/io/src/io/flat/paint_flat.cc module/io/src/io/flat/path_flat.cc module/io/src/io/flat/path_effect_flat.cc
+module/io/src/io/flat/rrect_flat.cc module/io/src/io/flat/shader_flat.cc module/io/src/io/flat/vertices_flat.cc
+module/io/src/io/read/read_typeface.cc module/io/src/io/memory_read.cc module/io/src/io/memory_writer.cc
+module/io/src/record/record_playback.cc module/io/src/stream/file_read_stream.cc module/io/src/stream/file_write_stream.cc
+module/io/src/stream/stream.cc module/io/src/utils/parse_path.cc module/io/src/picture.cc
+""".split()
+IO_FLAGS = ["-include", "cstring"]   # module/io/src/picture.cc uses std::memcpy without including <cstring>
+
+
+def io_include_flags(ref):
+    return [f"-I{ref}/module/io/include", f"-I{ref}/module/io", f"-I{ref}/module/io/src", f"-I{ref}/module/codec/include"]
+
 
 def _run(cmd):
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -129,7 +147,9 @@ def build_host(ref="/root/reference", verbose=True):
     flags = ["g++", "-std=c++17", "-O2", "-fPIC", "-w", "-DSKITY_CPU", "-DSKITY_RELEASE", "-DNDEBUG",
              "-fno-exceptions", "-fno-rtti", f"-I{ref}", f"-I{ref}/include", f"-I{ref}/module/wgx/include",
              f"-I{REPO}/third_party/glm_shim", f"-I{REPO}", f"-I{REPO}/include"]
+    flags = flags + io_include_flags(ref)
     jobs = [(os.path.join(ref, tu), os.path.join(objdir, tu.replace("/", "_") + ".o"), flags) for tu in SKITY_CORE_TUS]
+    jobs += [(os.path.join(ref, tu), os.path.join(objdir, tu.replace("/", "_") + ".o"), flags + IO_FLAGS) for tu in SKITY_IO_TUS]
     own = sorted(glob.glob(os.path.join(PKG, "host", "*.cc")))
     hdr_time = max(os.path.getmtime(h) for h in glob.glob(os.path.join(PKG, "host", "*.hpp")) +
                    glob.glob(os.path.join(REPO, "include", "*.h")))
@@ -152,7 +172,7 @@ def build_host(ref="/root/reference", verbose=True):
             "-Wl,--no-undefined", "-lpthread", "-ldl"]
     _run(link)
     if verbose:
-        print(f"built {lib} ({len(SKITY_CORE_TUS)} skity core TUs + {len(own)} plug-in sources, {len(missing)} stubs)")
+        print(f"built {lib} ({len(SKITY_CORE_TUS)} skity core + {len(SKITY_IO_TUS)} module/io TUs + {len(own)} plug-in sources, {len(missing)} stubs)")
     return lib
 
 

@@ -12,6 +12,7 @@
 
 #include "skity_b200/host/cuda_canvas.hpp"
 #include "skity_b200/host/scene_player.hpp"
+#include "skity_b200/host/skp_player.hpp"
 
 extern "C" {
 
@@ -96,6 +97,29 @@ int skbh_encode_recorded_scene(const uint8_t* scene, size_t n, uint8_t** out, si
   builder.Reset(h.width, h.height);
   skity::CudaCanvas canvas(&builder, 0, h.width, h.height);
   picture->Draw(&canvas);
+  canvas.Flush();
+  std::vector<uint8_t> blob = builder.Serialize();
+  *out = static_cast<uint8_t*>(std::malloc(blob.size() ? blob.size() : 1));
+  if (!*out) return -8;
+  std::memcpy(*out, blob.data(), blob.size());
+  *out_n = blob.size();
+  if (unsupported && cap) {
+    std::strncpy(unsupported, canvas.Unsupported().c_str(), cap - 1);
+    unsupported[cap - 1] = 0;
+  }
+  return 0;
+}
+
+// A serialized picture (.skp, the reference's module/io) as input: read from memory and played back onto the CUDA
+// canvas of a width x height surface under the affine matrix m6 (sx kx tx ky sy ty).
+int skbh_encode_skp(const uint8_t* skp, size_t n, uint32_t width, uint32_t height, const float* m6, uint8_t** out, size_t* out_n,
+                    char* unsupported, size_t cap) {
+  if (!skp || !m6 || width == 0 || height == 0) return -1;
+  skb::DlBuilder builder;
+  builder.Reset(width, height);
+  skity::CudaCanvas canvas(&builder, 0, width, height);
+  int rc = skb_skp::Play(skp, n, m6, &canvas);
+  if (rc != 0) return rc;
   canvas.Flush();
   std::vector<uint8_t> blob = builder.Serialize();
   *out = static_cast<uint8_t*>(std::malloc(blob.size() ? blob.size() : 1));

@@ -24,6 +24,9 @@ def lib():
                                                  ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
                                                  ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_encode_scene_batch.restype = ctypes.c_int
+        _lib.skbh_encode_skp.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_float),
+                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t]
+        _lib.skbh_encode_skp.restype = ctypes.c_int
         _lib.skbh_render_scene_cuda.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
         _lib.skbh_render_scene_cuda.restype = ctypes.c_int
@@ -49,6 +52,25 @@ def encode_scene(blob, allow_unsupported=False, recorded=False):
         lib().skbh_free(out)
     if msg.value and not allow_unsupported:
         raise RuntimeError(f"scene uses a feature outside the CUDA backend's scope: {msg.value.decode()}")
+    return data
+
+
+def encode_skp(skp, width, height, matrix6=(1, 0, 0, 0, 1, 0), allow_unsupported=False):
+    """A serialized picture (.skp bytes, the reference's module/io) played back through CudaCanvas onto a width x height
+    canvas under the affine matrix (sx kx tx ky sy ty) -> SKDL display list bytes."""
+    out = ctypes.c_void_p()
+    n = ctypes.c_size_t()
+    msg = ctypes.create_string_buffer(256)
+    m = (ctypes.c_float * 6)(*matrix6)
+    rc = lib().skbh_encode_skp(skp, len(skp), int(width), int(height), m, ctypes.byref(out), ctypes.byref(n), msg, 256)
+    if rc != 0:
+        raise RuntimeError(f"skbh_encode_skp failed: {rc}")
+    try:
+        data = ctypes.string_at(out, n.value)
+    finally:
+        lib().skbh_free(out)
+    if msg.value and not allow_unsupported:
+        raise RuntimeError(f"picture uses a feature outside the CUDA backend's scope: {msg.value.decode()}")
     return data
 
 

@@ -118,9 +118,30 @@ def golden_scenes():
     return out
 
 
+SKP_TIGER = "/root/reference/resources/skp/tiger.skp"
+SKP_TIGER_MATRIX = (1.0, 0.0, -130.0, 0.0, 1.0, 20.0)   # canvas->Translate(-130, 20), test/golden/cases/skp/skp.cc:60
+
+
+def skp_fixture():
+    """The reference's own SKP golden case (SKP_Golden.Tiger, test/golden/cases/skp/skp.cc:51-68): tiger.skp read by the
+    reference's module/io and played back onto a 1000x1000 canvas under Translate(-130, 20) — onto the reference's
+    software canvas (rgba) and onto the CUDA canvas (dl).  The .skp itself stays in the reference tree; its SHA-256 is
+    stored so that a test can tell which file the vector came from."""
+    import hashlib
+    skp = open(SKP_TIGER, "rb").read()
+    rgba = refsw.render_skp(skp, 1000, 1000, SKP_TIGER_MATRIX)
+    dl = hostlib.encode_skp(skp, 1000, 1000, SKP_TIGER_MATRIX)
+    path = os.path.join(HERE, "skp_tiger_1000.npz")
+    np.savez_compressed(path, dl=np.frombuffer(dl, dtype=np.uint8), rgba=rgba,
+                        skp_sha256=np.frombuffer(hashlib.sha256(skp).digest(), dtype=np.uint8))
+    print(f"skp_tiger_1000: sum={int(rgba.astype(np.int64).sum())} -> {os.path.getsize(path)} bytes")
+
+
 def main():
     assert refsw.available(), "build oracle/_ref first (python oracle/build_ref.py)"
     only = set(sys.argv[1:])        # optional: regenerate just the named fixtures
+    if not only or "skp_tiger_1000" in only:
+        skp_fixture()
     for name, s in golden_scenes().items():
         if only and name not in only:
             continue

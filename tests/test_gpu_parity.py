@@ -49,7 +49,7 @@ EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c
          "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144",
          "blend_modes_480", "filters_512", "layers_512", "filters_channel_carry_283", "blend_zero_then_accum_418",
          "clipped_blends_400", "filtered_layers_384", "filters_morphology_512", "images_same_size_256",
-         "ref_clip_path_difference_400", "clip_difference_flat_8", "clip_difference_flat_31"]
+         "ref_clip_path_difference_400", "clip_difference_flat_8", "clip_difference_flat_31", "skp_tiger_1000"]
 
 
 @pytest.mark.parametrize("name", EXACT)
