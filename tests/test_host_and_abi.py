@@ -175,3 +175,22 @@ def test_skp_ingest_reproduces_the_committed_vector():
     assert dl == z["dl"].tobytes()
     with pytest.raises(RuntimeError):
         hostlib.encode_skp(b"not a picture" * 10, 64, 64)
+
+
+def test_golden_harness_env_compiles_against_the_reference_headers(tmp_path):
+    """skity_b200/integration/golden_test_env_cuda.cc is the GoldenTestEnv a maintainer adds to the reference's golden
+    harness (test/golden/common/golden_test_env.hpp:27-82).  gtest is not in this image, so the harness cannot be
+    built; the file is at least compiled (-fsyntax-only) against the harness's real headers with a stand-in for
+    <gtest/gtest.h> that declares ::testing::Environment."""
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "test", "golden", "common")):
+        pytest.skip("reference tree absent")
+    (tmp_path / "gtest").mkdir()
+    (tmp_path / "gtest" / "gtest.h").write_text(
+        "#pragma once\nnamespace testing { class Environment { public: virtual ~Environment() {} "
+        "virtual void SetUp() {} virtual void TearDown() {} }; }\n")
+    src = os.path.join(ROOT, "skity_b200", "integration", "golden_test_env_cuda.cc")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-DSKITY_CPU", f"-I{tmp_path}", f"-I{ref}", f"-I{ref}/include",
+                        f"-I{ref}/test/golden", f"-I{ROOT}/third_party/glm_shim", f"-I{ROOT}", src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
