@@ -160,7 +160,12 @@ SKB_API skb_result skb_surface_device_ptr(skb_surface surface, void** out_ptr, s
  * gathering process exports its canvas as a 64-byte CUDA IPC handle; every other process (one per GPU, same
  * surface size) opens it, after which its fine pass stores the finished pixels of its band straight into the
  * gathering GPU's canvas over NVLink (peer memory) instead of its own — no copy, no collective, only a barrier
- * before the read-back.  NULL restores local stores. */
+ * before the read-back.  NULL restores local stores.
+ * Preconditions (the caller's, not checked): the fine pass blends against the LOCAL canvas and stores the result to the
+ * remote one, and skips tiles nothing was drawn into unless they lie in its band — so every process must start the
+ * frame from the same content (skb_frame_begin(clear = 1) on all of them, or identical skb_surface_write_pixels), and a
+ * barrier must separate the gathering process's clear from the other processes' skb_frame_flush (skity_b200/multigpu.py:
+ * fuse_gather_into_fine_pass, tests/multigpu_check.py). */
 SKB_API skb_result skb_surface_export_canvas(skb_surface surface, void* out_handle64);
 SKB_API skb_result skb_surface_set_remote_canvas(skb_surface surface, const void* handle64);
 SKB_API skb_result skb_surface_stream(skb_surface surface, void** out_cuda_stream);
