@@ -2273,17 +2273,26 @@ struct skb_device_s {
   int sm_count = 0;
 };
 
+// Structure of an encoded frame, worked out by the ONE pass validate_dl makes over the op table, so that neither
+// skb_frame_encode nor run_frame loops over the ops again (at 1M ops every such loop is ~10 ms of host time per frame, and
+// inside run_frame it is idle GPU time).
+struct FramePlan {
+  bool clip_ops = false, clipped_fills = false, diff_clips = false;
+  bool zero_blend = false;               // some draw's paint blends with a mode (or colour filter) that acts on zero-coverage pixels
+  int max_depth = 0;
+  std::vector<uint8_t> op_depth;         // nesting depth of the clip state a CLIP op defines (empty without clip ops)
+  std::vector<skb_dl_op> blur_ops;       // the BLUR ops, in op order
+  std::vector<uint32_t> surf_level;      // per surface: dependency depth (see SurfDesc::level)
+  uint32_t max_level = 0;
+  std::vector<uint8_t> surf_drawn;       // per surface: some FILL op targets it
+};
+
 struct skb_surface_s {
   skb_device dev = nullptr;
   uint32_t w = 0, h = 0;
   uint32_t band_y0 = 0, band_y1 = 0;
   int coord_mode = SKB_COORD_AUTO;
-  // structure of the encoded frame, worked out once by skb_frame_encode so that run_frame has no host loop over the
-  // ops between two launches (at 1M ops such a loop is milliseconds of idle GPU inside the frame)
-  bool plan_clip_ops = false, plan_clipped_fills = false, plan_diff_clips = false;
-  int plan_max_depth = 0;
-  std::vector<uint8_t> plan_op_depth;     // nesting depth of the clip state a CLIP op defines (empty without clip ops)
-  std::vector<skb_dl_op> plan_blur_ops;   // the BLUR ops, in op order
+  FramePlan plan;   // structure of the encoded frame (validate_dl)
   uint8_t* stage[2] = {nullptr, nullptr};   // page-locked staging for reads into pageable memory (skb_surface_read_pixels)
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   int walk_mode = 0;
@@ -2301,12 +2310,8 @@ struct skb_surface_s {
   // frame
   std::vector<uint8_t> host_dl;
   bool have_frame = false;
-  std::vector<uint32_t> surf_level;  // per surface: dependency depth (see SurfDesc::level)
-  uint32_t max_level = 0;
   cudaEvent_t ev_blur[2 * 16] = {};  // around the blur section of every level
   uint32_t n_levels_timed = 0;
-  std::vector<uint8_t> surf_drawn;   // per surface: some FILL op targets it
-  bool zero_blend = false;  // some paint blends with a mode that acts on zero-coverage pixels
   bool flushed = false;
   skb_frame_stats stats = {};
   // device buffers (grow-only)
@@ -2418,7 +2423,9 @@ static skb_result scan_exclusive(skb_surface s, uint32_t* data, uint32_t n_plus_
   return SKB_SUCCESS;
 }
 
-static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
+// Validates the list and, when `plan` is given, works out the frame's structure in the same pass: the op table (72 B per
+// op), the path table and each draw's paint are read exactly once.
+static skb_result validate_dl(const uint8_t* dl, size_t bytes, FramePlan* plan = nullptr) {
   if (bytes < sizeof(skb_dl_header)) return SKB_ERROR_BAD_DISPLAY_LIST;
   skb_dl_header h;
   memcpy(&h, dl, sizeof(h));
@@ -2454,25 +2461,6 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
       return SKB_ERROR_BAD_DISPLAY_LIST;
     }
   }
-  // The flatten stage lays edge regions out from "op i owns path i's segments, paths in op order, every segment owned":
-  // path k (k-th FILL/CLIP op) must be path index k and the paths must tile the segment table without gaps or overlap.
-  {
-    uint64_t next_seg = 0;
-    uint32_t next_path = 0;
-    for (uint32_t i = 0; i < h.n_ops; i++) {
-      if (ops[i].kind != SKB_OP_FILL && ops[i].kind != SKB_OP_CLIP) continue;
-      if (ops[i].path != next_path || next_path >= h.n_paths || paths[next_path].seg_off != next_seg) {
-        set_error("display list: every fill / clip op owns the next path, and paths follow each other in the segment table");
-        return SKB_ERROR_BAD_DISPLAY_LIST;
-      }
-      next_seg += paths[next_path].n_segs;
-      next_path++;
-    }
-    if (next_path != h.n_paths || next_seg != h.n_segs) {
-      set_error("display list: paths or segments that no op owns");
-      return SKB_ERROR_BAD_DISPLAY_LIST;
-    }
-  }
   for (uint32_t i = 0; i < h.n_surfaces; i++) {
     if (!(vsurfs[i].flags & SKB_SURFACE_IMAGE)) continue;
     if (i == 0 || (uint64_t)vsurfs[i].reserved + (uint64_t)vsurfs[i].width * vsurfs[i].height * 4 > h.total_bytes) {
@@ -2481,8 +2469,28 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
     }
   }
   std::vector<uint8_t> diff_state((size_t)h.n_clip_states + 1, 0);   // states defined by a ClipOp::kDifference clip
+  std::vector<int> state_depth(plan ? (size_t)h.n_clip_states + 1 : 0, 0);
+  std::vector<uint32_t> levels(h.n_surfaces, 0);     // dependency depth of every surface: a surface is composited after the
+  std::vector<uint2> uses;                           // surfaces its draws sample and after the source of the blur that makes it
+  if (plan) {
+    *plan = FramePlan();
+    plan->surf_drawn.assign(h.n_surfaces, 0);
+  }
+  // The flatten stage lays edge regions out from "op i owns path i's segments, paths in op order, every segment owned":
+  // path k (k-th FILL/CLIP op) must be path index k and the paths must tile the segment table without gaps or overlap.
+  uint64_t next_seg = 0;
+  uint32_t next_path = 0;
   for (uint32_t i = 0; i < h.n_ops; i++) {
     const skb_dl_op& o = ops[i];
+    uint32_t src = 0xFFFFFFFFu;   // surface this op samples
+    if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+      if (o.path != next_path || next_path >= h.n_paths || paths[next_path].seg_off != next_seg) {
+        set_error("display list: every fill / clip op owns the next path, and paths follow each other in the segment table");
+        return SKB_ERROR_BAD_DISPLAY_LIST;
+      }
+      next_seg += paths[next_path].n_segs;
+      next_path++;
+    }
     if (o.surface < h.n_surfaces && (vsurfs[o.surface].flags & SKB_SURFACE_IMAGE)) {
       set_error("display list: an image surface is read-only");
       return SKB_ERROR_BAD_DISPLAY_LIST;
@@ -2522,6 +2530,15 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
           }
         }
       }
+      if (o.kind == SKB_OP_FILL) {
+        const skb_dl_paint& pt = paints[o.paint];
+        if (pt.type == SKB_PAINT_IMAGE) src = pt.image_surface;
+        if (plan) {
+          plan->surf_drawn[o.surface] = 1;
+          if (o.clip_in != 0) plan->clipped_fills = true;
+          if ((pt.blend && blend_zero_src_matters(pt.blend - 1)) || SKB_PAINT_CF_OFFSET(pt)) plan->zero_blend = true;
+        }
+      }
       if (o.kind == SKB_OP_CLIP && (o.clip_out == 0 || o.clip_out > h.n_clip_states)) {
         set_error("display list: clip state id out of range");
         return SKB_ERROR_BAD_DISPLAY_LIST;
@@ -2543,6 +2560,19 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
           return SKB_ERROR_UNSUPPORTED;
         }
         diff_state[o.clip_out] = o.aux == 0;
+        if (plan) {
+          if (!plan->clip_ops) plan->op_depth.assign(h.n_ops, 0);
+          plan->clip_ops = true;
+          if (o.aux == 0) plan->diff_clips = true;
+          const int d = state_depth[o.clip_in] + 1;
+          if (d > 250) {
+            set_error("clip stack deeper than 250");
+            return SKB_ERROR_UNSUPPORTED;
+          }
+          state_depth[o.clip_out] = d;
+          plan->op_depth[i] = (uint8_t)d;
+          plan->max_depth = std::max(plan->max_depth, d);
+        }
       }
     } else if (o.kind == SKB_OP_BLUR) {
       if (o.surface >= h.n_surfaces || o.aux >= h.n_surfaces || o.surface == 0 || o.aux == 0 || o.surface == o.aux) {
@@ -2553,13 +2583,34 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes) {
         set_error("display list: unknown blur style");
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
+      src = o.aux;
+      if (plan) plan->blur_ops.push_back(o);
     } else {
       set_error("display list: unknown op kind");
       return SKB_ERROR_BAD_DISPLAY_LIST;
     }
+    if (src != 0xFFFFFFFFu) {
+      levels[o.surface] = std::max(levels[o.surface], levels[src] + 1);
+      uses.push_back(make_uint2(src, o.surface));
+    }
+  }
+  if (next_path != h.n_paths || next_seg != h.n_segs) {
+    set_error("display list: paths or segments that no op owns");
+    return SKB_ERROR_BAD_DISPLAY_LIST;
+  }
+  for (const uint2& u : uses) {   // a source must have been complete when it was used
+    if (levels[u.x] >= levels[u.y]) {
+      set_error("display list: a surface is sampled before the draws and blurs that feed it");
+      return SKB_ERROR_BAD_DISPLAY_LIST;
+    }
+  }
+  if (plan) {
+    for (uint32_t l : levels) plan->max_level = std::max(plan->max_level, l);
+    plan->surf_level = std::move(levels);
   }
   return SKB_SUCCESS;
 }
+
 
 static skb_result run_frame(skb_surface s) {
   const uint8_t* dl = s->host_dl.data();
@@ -2594,7 +2645,7 @@ static skb_result run_frame(skb_surface s) {
     d.tile_base = tile_base[i];
     d.row0 = 0;
     d.row1 = d.h;
-    d.level = s->surf_level[i];
+    d.level = s->plan.surf_level[i];
     d.pad = 0;
     tile_base[i + 1] = tile_base[i] + d.tiles_x * d.tiles_y;
     if (i > 0) {
@@ -2929,15 +2980,15 @@ static skb_result run_frame(skb_surface s) {
   ca.paints = t.paints;
   ca.zmask = nullptr;
   for (int k = 0; k < SKB_CLIP_PLANES; k++) ca.zplane[k] = nullptr;
-  if (s->zero_blend) {
+  if (s->plan.zero_blend) {
     SKB_TRY(buf_reserve(s->zmask, (n_items + 1) * 256));
     ca.zmask = (uint8_t*)s->zmask.p;
     ca.zplane[0] = ca.zmask;
   }
   // clip structure of the frame (worked out by skb_frame_encode): nesting depth of every clip state, clipped draws present?
-  const bool has_clip_ops = s->plan_clip_ops, has_clipped_fills = s->plan_clipped_fills;
-  const int max_depth = s->plan_max_depth;
-  const std::vector<uint8_t>& op_depth = s->plan_op_depth;
+  const bool has_clip_ops = s->plan.clip_ops, has_clipped_fills = s->plan.clipped_fills;
+  const int max_depth = s->plan.max_depth;
+  const std::vector<uint8_t>& op_depth = s->plan.op_depth;
   if (has_clipped_fills) {
     for (int k = 2; k < SKB_CLIP_PLANES; k++) {
       SKB_TRY(buf_reserve(s->mask_extra[k - 2], (n_items + 1) * 256));
@@ -2945,7 +2996,7 @@ static skb_result run_frame(skb_surface s) {
     }
     // clipped draws write single bytes of their planes: start from zero
     for (int k = 0; k < SKB_CLIP_PLANES; k++) SKB_CUDA(cudaMemsetAsync(ca.mask[k], 0, n_items * 256, st));
-    if (s->zero_blend) {  // ... and of the per-plane "a span reaches this pixel" maps, when some paint needs them
+    if (s->plan.zero_blend) {  // ... and of the per-plane "a span reaches this pixel" maps, when some paint needs them
       for (int k = 1; k < SKB_CLIP_PLANES; k++) {
         SKB_TRY(buf_reserve(s->zplane_extra[k - 1], (n_items + 1) * 256));
         ca.zplane[k] = (uint8_t*)s->zplane_extra[k - 1].p;
@@ -3030,14 +3081,14 @@ static skb_result run_frame(skb_surface s) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level);
       launches++;
     }
-    if (s->plan_diff_clips && clip_grid) {
+    if (s->plan.diff_clips && clip_grid) {
       k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0);
       launches++;
     }
     if (has_clipped_fills && clip_grid && n_items) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0);
       launches++;
-      if (s->plan_diff_clips) {
+      if (s->plan.diff_clips) {
         k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 1);
         launches++;
       }
@@ -3087,7 +3138,7 @@ static skb_result run_frame(skb_surface s) {
   for (int k = 0; k < SKB_CLIP_PLANES; k++) fa.zplane[k] = ca.zplane[k];
   // blur jobs of the whole frame, sorted by the level of their destination
   std::vector<BlurJob> jobs;
-  for (const skb_dl_op& bo : s->plan_blur_ops) {
+  for (const skb_dl_op& bo : s->plan.blur_ops) {
     {
       BlurJob j;
       j.src = bo.aux;
@@ -3148,15 +3199,15 @@ static skb_result run_frame(skb_surface s) {
     SKB_CUDA(cudaMemcpyAsync(s->blur_cols.p, colb.data(), (nj + 1) * 4, cudaMemcpyHostToDevice, st));
     SKB_CUDA(cudaMemcpyAsync(s->blur_tmp_ptrs.p, tmp_ptrs.data(), nj * sizeof(void*), cudaMemcpyHostToDevice, st));
   }
-  if (s->max_level >= 16) {
+  if (s->plan.max_level >= 16) {
     set_error("more than 16 dependent passes (nested layers / filters)");
     return SKB_ERROR_UNSUPPORTED;
   }
   // Level by level: first the blurs that produce surfaces of this level, then the fine pass of the
   // surfaces drawn at this level (their image sources and blur inputs are complete by construction).
-  s->n_levels_timed = s->max_level + 1;
+  s->n_levels_timed = s->plan.max_level + 1;
   uint32_t j0 = 0;
-  for (uint32_t level = 0; level <= s->max_level; level++) {
+  for (uint32_t level = 0; level <= s->plan.max_level; level++) {
     if (!s->ev_blur[2 * level]) {
       SKB_CUDA(cudaEventCreate(&s->ev_blur[2 * level]));
       SKB_CUDA(cudaEventCreate(&s->ev_blur[2 * level + 1]));
@@ -3222,7 +3273,7 @@ static skb_result run_frame(skb_surface s) {
       }
     }
     bool others = false;
-    for (uint32_t i = 1; i < h.n_surfaces && !others; i++) others = surfs[i].level == level && s->surf_drawn[i];
+    for (uint32_t i = 1; i < h.n_surfaces && !others; i++) others = surfs[i].level == level && s->plan.surf_drawn[i];
     if (others) {
       fa.tile_begin = tile_base[1];
       fa.tile_end = n_tiles;
@@ -3417,70 +3468,21 @@ skb_result skb_display_list_validate(const void* dl, size_t bytes) {
 skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {
   if (!s || !dl) return SKB_ERROR_INVALID_ARGUMENT;
   SKB_CUDA(cudaSetDevice(s->dev->ordinal));
-  SKB_TRY(validate_dl((const uint8_t*)dl, bytes));
   skb_dl_header h;
+  if (bytes >= sizeof(h)) {
+    // the upload does not wait for the validation: the copy engine moves the list (456 MB for 1M paths) while this
+    // thread reads the op table; nothing is launched on it before validate_dl has accepted it (skb_frame_flush)
+    memcpy(&h, dl, sizeof(h));
+    if (h.magic == SKB_DL_MAGIC && h.version == SKB_DL_VERSION && h.total_bytes <= bytes && h.total_bytes >= sizeof(h)) {
+      SKB_TRY(buf_reserve(s->dl, h.total_bytes));
+      SKB_CUDA(cudaMemcpyAsync(s->dl.p, dl, h.total_bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+  }
+  s->have_frame = false;
+  SKB_TRY(validate_dl((const uint8_t*)dl, bytes, &s->plan));
   memcpy(&h, dl, sizeof(h));
-  // the header and the surface table are also read on the host while launching (what run_frame needs of the ops is
-  // worked out below, once)
+  // the header and the surface table are also read on the host while launching
   s->host_dl.assign((const uint8_t*)dl, (const uint8_t*)dl + h.off_ops);
-  // dependency depth of every surface: a surface is composited after the surfaces its draws sample
-  // (image paints) and after the source of the blur that produces it
-  {
-    const skb_dl_op* ops = (const skb_dl_op*)((const uint8_t*)dl + h.off_ops);
-    const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
-    s->surf_level.assign(h.n_surfaces, 0);
-    s->surf_drawn.assign(h.n_surfaces, 0);
-    s->plan_clip_ops = s->plan_clipped_fills = s->plan_diff_clips = false;
-    s->plan_max_depth = 0;
-    s->plan_op_depth.clear();
-    s->plan_blur_ops.clear();
-    std::vector<int> state_depth(h.n_clip_states + 1, 0);
-    for (uint32_t i = 0; i < h.n_ops; i++) {
-      const skb_dl_op& o = ops[i];
-      uint32_t src = 0xFFFFFFFFu;
-      if (o.kind == SKB_OP_FILL) {
-        s->surf_drawn[o.surface] = 1;
-        if (paints[o.paint].type == SKB_PAINT_IMAGE) src = paints[o.paint].image_surface;
-        if (o.clip_in != 0) s->plan_clipped_fills = true;
-      } else if (o.kind == SKB_OP_BLUR) {
-        src = o.aux;
-        s->plan_blur_ops.push_back(o);
-      } else if (o.kind == SKB_OP_CLIP) {
-        if (!s->plan_clip_ops) s->plan_op_depth.assign(h.n_ops, 0);
-        s->plan_clip_ops = true;
-        if (o.aux == 0) s->plan_diff_clips = true;
-        const int d = state_depth[o.clip_in] + 1;
-        if (d > 250) {
-          set_error("clip stack deeper than 250");
-          return SKB_ERROR_UNSUPPORTED;
-        }
-        state_depth[o.clip_out] = d;
-        s->plan_op_depth[i] = (uint8_t)d;
-        s->plan_max_depth = std::max(s->plan_max_depth, d);
-      }
-      if (src != 0xFFFFFFFFu) s->surf_level[o.surface] = std::max(s->surf_level[o.surface], s->surf_level[src] + 1);
-    }
-    s->max_level = 0;
-    for (uint32_t i = 0; i < h.n_ops; i++) {  // a source must have been complete when it was used
-      const skb_dl_op& o = ops[i];
-      uint32_t src = 0xFFFFFFFFu;
-      if (o.kind == SKB_OP_FILL && paints[o.paint].type == SKB_PAINT_IMAGE) src = paints[o.paint].image_surface;
-      if (o.kind == SKB_OP_BLUR) src = o.aux;
-      if (src != 0xFFFFFFFFu && s->surf_level[src] >= s->surf_level[o.surface]) {
-        set_error("display list: a surface is sampled before the draws and blurs that feed it");
-        return SKB_ERROR_BAD_DISPLAY_LIST;
-      }
-    }
-    for (uint32_t l : s->surf_level) s->max_level = std::max(s->max_level, l);
-  }
-  s->zero_blend = false;
-  {
-    const skb_dl_paint* paints = (const skb_dl_paint*)((const uint8_t*)dl + h.off_paints);
-    for (uint32_t i = 0; i < h.n_paints; i++)
-      if ((paints[i].blend && blend_zero_src_matters(paints[i].blend - 1)) || SKB_PAINT_CF_OFFSET(paints[i])) s->zero_blend = true;
-  }
-  SKB_TRY(buf_reserve(s->dl, h.total_bytes));
-  SKB_CUDA(cudaMemcpyAsync(s->dl.p, dl, h.total_bytes, cudaMemcpyHostToDevice, s->stream));
   s->have_frame = true;
   return SKB_SUCCESS;
 }
