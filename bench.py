@@ -283,15 +283,17 @@ def run_ours(args):
     # ---- the same with several frames in flight: every step still uploads its display list and reads its canvas back
     # to pinned host memory, but frames alternate between surfaces (each with its own stream, arenas and canvas), so
     # the upload, the host-side validation and the read-back of one frame overlap the rendering of the others — what an
-    # application streaming frames does.  N = 1: three surfaces, one host thread each (measured on C4a: 1 / 2 / 3
-    # frames in flight = 94 / 76 / 66 ms per frame against 60.6 ms of device time).  Banded (N > 1): two surfaces
-    # driven by one thread, because every frame needs two barriers across the ranks.
+    # application streaming frames does.  Three surfaces, one host thread each (measured on C4a at N = 1: 1 / 2 / 3
+    # frames in flight = 94 / 76 / 66 ms per frame against 60.6 ms of device time).  Banded (N > 1): a frame needs two
+    # host barriers across the ranks (bands complete; rank 0 has read the canvas), each thread on a gloo group of its own.
     ms_e2e_wall = ms_e2e_serial
     pipelined = partition != "batch"
     n_flight = 1
     if pipelined:
-        n_flight = 2 if banded else 3
+        n_flight = 3
         extra = [dev.create_surface(surf_w, surf_h) for _ in range(n_flight - 1)]
+        # banded: every surface's host thread has a gloo group of its own for the two host barriers of a frame
+        flight_groups = [dist.new_group(backend="gloo") for _ in range(n_flight)] if banded else None
         for sb in extra:
             if banded:
                 sb.set_band(*bands[rank])
@@ -305,37 +307,35 @@ def run_ours(args):
                            for _ in extra]
 
         def run_pipelined(n_steps):
-            if not banded:
-                # one host thread per surface (the C ABI is thread-safe per surface): the threads take alternate frames,
-                # so frame k + 1 is uploaded and rendered while frame k is still being read back
-                def worker(j):
+            # one host thread per surface (the C ABI is thread-safe per surface): the threads take frames in turn, so
+            # frame k + 1 is uploaded, validated and rendered while frame k is still being read back
+            errors = []
+
+            def worker(j):
+                try:
+                    torch.cuda.set_device(local_rank)
                     sf = pair[j]
                     for k in range(j, n_steps, n_flight):
                         sf.begin(True)
                         sf.encode((dl_pinned.data_ptr(), n_dl))
                         sf.flush()
-                        sf.read_pixels_async(outs[j])
+                        if banded:
+                            sf.sync()
+                            dist.barrier(group=flight_groups[j])     # every band of frame k is in rank 0's canvas j
+                        if outs[j] is not None:
+                            sf.read_pixels_async(outs[j])
                         sf.sync()
-                ths = [threading.Thread(target=worker, args=(j,)) for j in range(n_flight)]
-                for th in ths:
-                    th.start()
-                for th in ths:
-                    th.join()
-                return
-            for k in range(n_steps):
-                sf = pair[k & 1]
-                if k >= 2:
-                    sf.sync()           # rank 0: the read-back of frame k - 2 has left this canvas
-                    dist.barrier()
-                sf.begin(True)
-                sf.encode((dl_pinned.data_ptr(), n_dl))
-                sf.flush()
-                sf.sync()
-                dist.barrier()      # every band of frame k is in rank 0's canvas
-                if outs[k & 1] is not None:
-                    sf.read_pixels_async(outs[k & 1])
-            for sf in pair:
-                sf.sync()
+                        if banded:
+                            dist.barrier(group=flight_groups[j])     # rank 0 has its copy: canvas j may be overwritten
+                except Exception as e:  # noqa: BLE001
+                    errors.append(e)
+            ths = [threading.Thread(target=worker, args=(j,)) for j in range(n_flight)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            if errors:
+                raise errors[0]
 
         run_pipelined(n_flight)
         barrier()
@@ -345,9 +345,11 @@ def run_ours(args):
         barrier()
         ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_e2e
         if out_np is not None:
-            for o in outs[1:]:
-                if not np.array_equal(outs[0][:64], o[:64]):
+            for o in outs[1:]:      # first rows (rank 0's band) and last rows (the last rank's band, stored over NVLink)
+                if not (np.array_equal(outs[0][:64], o[:64]) and np.array_equal(outs[0][-64:], o[-64:])):
                     raise SystemExit("frames rendered on different surfaces differ")
+            if banded and int(outs[0][bands[-1][0]:bands[-1][0] + min(64, bands[-1][1] - bands[-1][0])].astype(np.uint64).sum()) != single_check:
+                raise SystemExit("the last band read back end to end differs from the band gathered by NCCL")
         for sb in extra:
             sb.close()
     clocks = sampler.stop() if rank == 0 else None
@@ -408,7 +410,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(canvases * W * H * 4), "ms_per_step": round(ms_e2e_used, 4),
                     "what": "C ABI with host buffers: display list H2D from pinned memory on every rank, frame, "
                             + ("bands into rank 0's canvas over NVLink, barrier, " if banded else "") + "canvas D2H into pinned memory; "
-                            + ((f"{n_flight} frames in flight on {n_flight} surfaces" + ("" if banded else ", one host thread each") + " (upload, validation and read-back of one frame overlap the rendering of the others)") if pipelined else "one frame at a time"),
+                            + ((f"{n_flight} frames in flight on {n_flight} surfaces, one host thread each (upload, validation and read-back of one frame overlap the rendering of the others)") if pipelined else "one frame at a time"),
                     "frames_in_flight": n_flight, "frames_timed": n_e2e if pipelined else args.steps,
                     "one_frame_at_a_time": {"value": round(mpix / (ms_e2e_serial / 1e3), 2), "ms_per_step": round(ms_e2e_serial, 4)}},
             "gpu_launches": int(launches),
