@@ -1345,6 +1345,7 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
   const skb_dl_op o = c.ops[op];
   if (mode == 0) {
     if (o.kind != SKB_OP_CLIP || a.op_depth[op] != (uint8_t)level || o.aux == 0) return;   // difference clips: k_clip_diff
+    if (o.clip_in != 0 && a.states[o.clip_in].kind == SKB_CLIP_KIND_DIFF) return;            // on top of one: k_clip_diff mode 2
   } else {
     if (o.kind != SKB_OP_FILL || o.clip_in == 0 || a.states[o.clip_in].kind == SKB_CLIP_KIND_DIFF) return;
   }
@@ -1493,19 +1494,48 @@ struct DiffPiece {
     }
   }
 };
-struct DiffCut {
-  DiffPiece piece;
+// A piece of a new INTERSECTING state's span (mode 2): appended to the entry lists of the pixels it covers, a
+// zero-length piece as a marker entry (skb_clip.cuh) — the same table k_clip_rows builds for nested intersecting clips.
+struct DiffTablePiece {
+  uint32_t* own_row;
+  int rx0, rw;
+  uint32_t cover;
+  bool wrote, over;
+  __device__ void append(int px, uint32_t e) {
+    if (px < rx0 || px >= rx0 + rw) return;
+    uint32_t* slot = own_row + (size_t)(px - rx0) * SKB_CLIP_MAXE;
+    int k = 0;
+    while (k < SKB_CLIP_MAXE && slot[k]) k++;
+    if (k == SKB_CLIP_MAXE) {
+      over = true;
+      return;
+    }
+    slot[k] = e;
+    wrote = true;
+  }
+  __device__ void operator()(int x, int len) {
+    if (len == 0) {
+      append(x, clip_entry(x, cover) | SKB_CLIP_MARKER);
+      return;
+    }
+    for (int px = x; px < x + len; px++) append(px, clip_entry(x, cover));
+  }
+};
+template <class Piece>
+struct DiffCutT {
+  Piece piece;
   const uint2* ms;
   int n_ms;
-  bool keep_zero;   // the blend mode / colour filter acts on zero-coverage pixels
+  bool keep_zero;   // spans of coverage 0 matter: the blend mode / colour filter acts on them, or a clip state is being built
   __device__ void operator()(int x, int len, uint32_t cover) {
     if (cover == 0 && !keep_zero) return;
     piece.cover = cover;
     span_subtract(x, len, ms, n_ms, piece);
   }
 };
+typedef DiffCutT<DiffPiece> DiffCut;
 
-__global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode) {
+__global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int level) {
   const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= a.n_rows) return;
   const int lane = (int)(threadIdx.x & 31);
@@ -1514,8 +1544,12 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode) {
   const skb_dl_op o = c.ops[op];
   if (mode == 0) {
     if (o.kind != SKB_OP_CLIP || o.aux != 0) return;
-  } else {
+  } else if (mode == 1) {
     if (o.kind != SKB_OP_FILL || o.clip_in == 0 || a.states[o.clip_in].kind != SKB_CLIP_KIND_DIFF) return;
+  } else {
+    if (o.kind != SKB_OP_CLIP || o.aux != 1 || a.op_depth[op] != (uint8_t)level || o.clip_in == 0 ||
+        a.states[o.clip_in].kind != SKB_CLIP_KIND_DIFF)
+      return;
   }
   const OpGeom g = c.geom[op];
   if (g.empty || g.ntx == 0) return;
@@ -1569,6 +1603,32 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode) {
       const uint32_t* base = a.table + ((size_t)a.state_px_off[o.clip_in] + (size_t)(y - par.ry0) * par.rw) * SKB_CLIP_MAXE;
       n_ms = (int)base[0];
       ms = reinterpret_cast<const uint2*>(base + 2);
+    }
+    if (mode == 2) {
+      // an intersecting clip on top of a difference state: RecursiveClip's spans_subtraction(fresh spans, clip spans)
+      // (sw_canvas.cc:186-187); the result is an intersecting state (:328-330), every span of the fresh path kept
+      // (coverage 0 included), every piece an entry
+      const ClipStateDesc own = a.states[o.clip_out];
+      if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
+      DiffCutT<DiffTablePiece> cd, ca_;
+      cd.piece.own_row = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+      cd.piece.rx0 = own.rx0;
+      cd.piece.rw = own.rw;
+      cd.piece.cover = 0;
+      cd.piece.wrote = cd.piece.over = false;
+      cd.ms = ms;
+      cd.n_ms = n_ms;
+      cd.keep_zero = true;
+      // the direct spans precede the accumulated ones in the list: two walks of the row, so that every pixel's entries
+      // come out in list order (all pieces of direct spans, then all pieces of accumulated spans)
+      struct Skip { __device__ void operator()(int, int, uint32_t) {} } skip;
+      ClipRowState st2 = st;
+      clip_row_spans(st, c.pool, row, x_first, x_last, cd, skip);
+      ca_ = cd;
+      clip_row_spans(st2, c.pool, row, x_first, x_last, skip, ca_);
+      if (cd.piece.wrote || ca_.piece.wrote) a.states[o.clip_out].nonempty = 1;
+      if (cd.piece.over || ca_.piece.over) *a.overflow = 1;
+      return;
     }
     bool zm = false;
     if (c.zplane[1] != nullptr) {
@@ -2545,18 +2605,15 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes, FramePlan* plan =
       }
       if (o.kind == SKB_OP_CLIP) {
         // ClipOp::kDifference: a state of its own (one difference clip per Save level, how the reference's goldens and
-        // examples use the op).  Combined with another path clip in the same chain the reference goes through
-        // RecursiveClip's subtraction of whole span lists / PerformMerge (sw_canvas.cc:178-217): not on the device.
+        // examples use the op), possibly refined by intersecting clips afterwards (k_clip_diff mode 2).  A difference
+        // clip ON TOP of another path clip goes through RecursiveClip's subtraction of the parent's whole span list or
+        // PerformMerge (sw_canvas.cc:188-217): not on the device.
         if (o.aux > 1) {
           set_error("display list: unknown clip op");
           return SKB_ERROR_BAD_DISPLAY_LIST;
         }
         if (o.aux == 0 && o.clip_in != 0) {
           set_error("ClipOp::kDifference on top of another path clip is not implemented on the device");
-          return SKB_ERROR_UNSUPPORTED;
-        }
-        if (o.aux == 1 && o.clip_in != 0 && diff_state[o.clip_in]) {
-          set_error("a path clip on top of a ClipOp::kDifference clip is not implemented on the device");
           return SKB_ERROR_UNSUPPORTED;
         }
         diff_state[o.clip_out] = o.aux == 0;
@@ -3077,19 +3134,23 @@ static skb_result run_frame(skb_surface s) {
     cl.overflow = counters + 2;
     cl.n_rows = (uint32_t)n_rows;
     const uint32_t clip_grid = cdiv(n_rows * 32, 128);
+    if (s->plan.diff_clips && clip_grid) {   // difference states have no parent: all of them first
+      k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0, 0);
+      launches++;
+    }
     for (int level = 1; level <= max_depth && clip_grid; level++) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 0, level);
       launches++;
-    }
-    if (s->plan.diff_clips && clip_grid) {
-      k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0);
-      launches++;
+      if (s->plan.diff_clips && level >= 2) {   // intersecting clips on top of a difference state
+        k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 2, level);
+        launches++;
+      }
     }
     if (has_clipped_fills && clip_grid && n_items) {
       k_clip_rows<<<clip_grid, 128, 0, st>>>(cl, 1, 0);
       launches++;
       if (s->plan.diff_clips) {
-        k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 1);
+        k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 1, 0);
         launches++;
       }
       k_clip_classify<<<cdiv(n_items * 32, 128), 128, 0, st>>>(ca);

@@ -49,7 +49,8 @@ EXACT = ["c0_star_blur_800x600", "c0_star_plain_800x600", "c1_fills_120_512", "c
          "mixed_transform_clip_400x300", "wrap_8192_256", "ut_stroke_then_fill_48", "golden_canonical_edges_192x144",
          "blend_modes_480", "filters_512", "layers_512", "filters_channel_carry_283", "blend_zero_then_accum_418",
          "clipped_blends_400", "filtered_layers_384", "filters_morphology_512", "images_same_size_256",
-         "ref_clip_path_difference_400", "clip_difference_flat_8", "clip_difference_flat_31", "skp_tiger_1000"]
+         "ref_clip_path_difference_400", "clip_difference_flat_8", "clip_difference_flat_31", "clip_difference_refined_12",
+         "skp_tiger_1000"]
 
 
 @pytest.mark.parametrize("name", EXACT)
@@ -231,6 +232,19 @@ def test_clip_that_rasterises_to_nothing_clips_nothing(dev):
     assert np.array_equal(render(dev, dl, 200, 200), want)
 
 
+@pytest.mark.parametrize("seed0", [3000, 3040])
+def test_difference_clips_refined_by_intersecting_clips_seeded(dev, seed0):
+    """An intersecting clip on top of a difference clip (RecursiveClip: spans_subtraction(fresh, clip spans), the result an
+    intersecting state, sw_canvas.cc:186-187,328-330), draws and further intersecting clips under it."""
+    bad = []
+    for seed in range(seed0, seed0 + 40):
+        s = scene.scene_difference_clips(seed, "refined")
+        dl = hostlib.encode_scene(s.encode())
+        if not np.array_equal(render(dev, dl, s.width, s.height), port.render(dl)):
+            bad.append(seed)
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("seed0", [2000, 2040])
 def test_difference_clips_seeded(dev, seed0):
     """ClipOp::kDifference, one clip per Save level (sw_canvas.cc:56-133): the reference's sequential span subtraction
@@ -262,10 +276,10 @@ def test_difference_clip_under_zero_source_blend_modes(dev):
 
 
 def test_combined_difference_clips_are_refused_not_approximated(dev):
-    """A difference clip combined with another PATH clip in one chain goes through RecursiveClip's whole-list
-    subtraction / PerformMerge in the reference (sw_canvas.cc:178-217): not on the device, and never approximated."""
+    """A difference clip ON TOP of another path clip goes through RecursiveClip's subtraction of the parent's whole span
+    list / PerformMerge in the reference (sw_canvas.cc:188-217): not on the device, and never approximated."""
     from skity_b200 import device
-    for first, second in ((True, False), (False, True), (False, False)):
+    for first, second in ((True, False), (False, False)):
         s = Scene(64, 64)
         s.save()
         s.clip_path(scene.star_path(), first)
