@@ -329,6 +329,16 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
   }
   row_cnt[op] = rows;
   item_cnt[op] = items;
+  {
+    // 64-bit totals beside the 32-bit prefix scans (too_big + 10: rows, + 12: items): a frame whose scan rows or
+    // (op, tile) items do not fit 32 bits is refused by run_frame instead of wrapping into undersized buffers
+    const unsigned m = __activemask();
+    const uint32_t wr = __reduce_add_sync(m, rows), wi = __reduce_add_sync(m, items);
+    if ((int)(threadIdx.x & 31) == __ffs((int)m) - 1) {
+      if (wr) atomicAdd(reinterpret_cast<unsigned long long*>(too_big + 10), (unsigned long long)wr);
+      if (wi) atomicAdd(reinterpret_cast<unsigned long long*>(too_big + 12), (unsigned long long)wi);
+    }
+  }
   if (rwops) {
     // row-parallel walk: the rows the sweep covers, from WalkEdges' start_y (the top of the path's bounds — above the
     // scan rectangle when the path is clipped at the top) to where the records stop being read
@@ -1144,12 +1154,30 @@ __global__ void k_area_backdrop(AreaArgs a) {
 struct alignas(16) AreaWarpSmem {
   AreaLine line[AREA_CAP];
   uint32_t key[AREA_CAP];
+  int32_t cover[16][17];   // per pixel row: 8.8 sums of the lines' "pixel lies right of the line" terms, scattered at the
+                           // first column right of each line, then prefix-summed along the row
+  uint32_t mixed[16];      // per pixel row: bit c = pixel (row, c) lies under some line (needs the full formula, in line order)
+  float wmix[256];         // windings of those pixels
+  uint8_t list[256];       // which pixels they are
 };
 
-// One warp per (op, tile row); tiles left to right.  A tile's lines are put in key order (rank sort in shared memory; a
-// tile with more than AREA_CAP lines is first sorted in place in global memory by selection, then streamed), unpacked
-// once, and every lane accumulates the windings of its 8 pixels (lane -> pixel row lane >> 1, half lane & 1) over the
-// lines that reach its pixel row.
+// One warp per (op, tile row); tiles left to right.  A tile's lines are put in key order (rank sort in shared memory)
+// and unpacked once.  The reference sums a pixel's contributions in fp32 in line order, so the order must be kept — but
+// only where it matters: a line contributes exactly 0 to the pixels left of it and an exact multiple of 1/256 (the
+// height of its overlap with the pixel row, signed) to the pixels right of it; only the one or two pixels per row that
+// lie UNDER the line get an inexact area term.  So per tile:
+//   1. every (line, pixel row) pair is classified by a lane: the columns under the line (with the reference's own
+//      expression for the line's y at a pixel edge, so that "left" and "right" are exactly the cases in which the
+//      reference's clamps collapse) are marked in a per-row bit mask, the right-of-line term goes into an integer 8.8
+//      grid at the first column right of the line (integer adds: order-free);
+//   2. the grid is prefix-summed along the rows: the winding of every pixel no line passes over, exactly (sums of
+//      multiples of 1/256 below 2^15 are exact in fp32 in any order);
+//   3. the marked pixels — typically a tenth of the tile — are dealt to the lanes, 32 at a time, and each is evaluated
+//      the reference's way: all lines in key order, full formula;
+//   4. every lane resolves the alphas of its 8 pixels (lane -> pixel row lane >> 1, half lane & 1) and the tile's mask
+//      is stored.
+// A tile with more than AREA_CAP lines (first sorted in place in global memory by selection, then streamed) takes the
+// plain form: every lane accumulates its 8 pixels over all lines that reach its row.
 __global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
   __shared__ AreaWarpSmem sm_all[AREA_WARPS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1213,6 +1241,133 @@ __global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
           __syncwarp();
         }
       }
+      if (n <= AREA_CAP) {
+        const int m = n;
+        __syncwarp();
+        {   // lines in key order, unpacked
+          uint4 mine[AREA_CAP / 32];
+#pragma unroll
+          for (int q = 0; q < AREA_CAP / 32; q++) {
+            const int j = lane + 32 * q;
+            if (j < m) {
+              mine[q] = a.lines[beg + j];
+              sm.key[j] = mine[q].z;
+            }
+          }
+          for (int j = lane; j < 16 * 17; j += 32) (&sm.cover[0][0])[j] = 0;
+          if (lane < 16) sm.mixed[lane] = 0u;
+          __syncwarp();
+#pragma unroll
+          for (int q = 0; q < AREA_CAP / 32; q++) {
+            const int j = lane + 32 * q;
+            if (j < m) {
+              int rank = 0;
+              for (int i = 0; i < m; i++) rank += sm.key[i] < mine[q].z ? 1 : 0;
+              sm.line[rank] = area_line_unpack(mine[q].x, mine[q].y);
+            }
+          }
+        }
+        __syncwarp();
+        // 1. classify (line, pixel row) pairs: two lines at a time, 16 rows each
+        for (int k0 = 0; k0 < m; k0 += 2) {
+          const int k = k0 + (lane >> 4), r = lane & 15;
+          if (k < m) {
+            const AreaLine l = sm.line[k];
+            const float rt = (float)r, rb = (float)r + 1.0f;
+            const float y_min = l.edge_top < rt ? rt : l.edge_top;
+            const float y_max = l.edge_bottom < rb ? l.edge_bottom : rb;
+            if (y_min < y_max) {
+              int lo, hi;      // columns [lo, hi] lie under the line in this row; columns > hi right of it, < lo left of it
+              float rterm;     // what a pixel right of the line receives
+              if (l.dx == 0.0f) {
+                // vertical: sign * h * clamp(pixel_right - x, 0, 1) — 0 for pixel_right <= x, sign * h for pixel_right >= x + 1
+                lo = hi = (int)ceilf(l.fx_) - 1;
+                rterm = l.sign * (y_max - y_min) * 1.0f;
+              } else {
+                const bool up = l.y_slope > 0.0f;   // the line's y grows with x
+                const float xa = l.fx_ + (y_min - l.fy_) * l.x_slope, xb = l.fx_ + (y_max - l.fy_) * l.x_slope;
+                lo = (int)floorf(xa < xb ? xa : xb);
+                hi = (int)floorf(xa < xb ? xb : xa);
+                lo = lo < 0 ? 0 : (lo > 15 ? 15 : lo);
+                hi = hi < lo ? lo : (hi > 15 ? 15 : hi);
+                // Widen until the reference's own expressions say "right" / "left": the line's y at the left edge of
+                // column hi + 1 is at or beyond the row overlap's far end (then both clamped ys of every pixel from there
+                // on coincide: zero area, full cover term), its y at the right edge of column lo - 1 at or before the near
+                // end (zero area, zero cover).  The expression is monotone in the column, so one test each side decides.
+                while (hi < 15) {
+                  const float ly = l.fy_ + ((float)(hi + 1) - l.fx_) * l.y_slope;
+                  if (up ? ly >= y_max : ly <= y_min) break;
+                  hi++;
+                }
+                while (lo > 0) {
+                  const float ry = l.fy_ + ((float)lo - l.fx_) * l.y_slope;   // right edge of column lo - 1
+                  if (up ? ry <= y_min : ry >= y_max) break;
+                  lo--;
+                }
+                const float ley = area_clampf(l.left_endpoint_y, y_min, y_max);
+                rterm = l.sign * fabsf((up ? y_max : y_min) - ley);
+              }
+              if (hi >= 0 && lo <= 15) {
+                const int c0 = lo < 0 ? 0 : lo, c1 = hi > 15 ? 15 : hi;
+                if (c1 >= c0) atomicOr(&sm.mixed[r], ((2u << c1) - 1u) & ~((1u << c0) - 1u));
+              }
+              if (hi < 15) atomicAdd(&sm.cover[r][hi < -1 ? 0 : hi + 1], (int32_t)(rterm * 256.0f));
+            }
+          }
+        }
+        __syncwarp();
+        // 2. windings of the pixels no line passes over; 3a. the list of the others
+        int cnt = 0;
+        if (lane < 16) {
+          int acc = 0;
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            acc += sm.cover[lane][c];
+            sm.cover[lane][c] = acc;
+          }
+          cnt = __popc(sm.mixed[lane]);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane < 16) {
+          int at = incl - cnt;
+          for (uint32_t mm = sm.mixed[lane]; mm; mm &= mm - 1) sm.list[at++] = (uint8_t)(lane * 16 + (__ffs((int)mm) - 1));
+        }
+        __syncwarp();
+        // 3b. the pixels under lines: the reference's loop, all lines in key order
+        for (int b = 0; b < total; b += 32) {
+          const int idx = b + lane;
+          if (idx < total) {
+            const int pid = sm.list[idx];
+            const float pt = (float)(pid >> 4), pb = (float)(pid >> 4) + 1.0f, pxf = (float)(pid & 15);
+            float wv = (float)backdrop;
+            for (int k = 0; k < m; k++) {
+              const AreaLine& l = sm.line[k];
+              const float y_min = l.edge_top < pt ? pt : l.edge_top;
+              const float y_max = l.edge_bottom < pb ? l.edge_bottom : pb;
+              if (y_min >= y_max) continue;
+              wv = wv + area_edge_contribution(l, pxf, y_min, y_max);
+            }
+            sm.wmix[pid] = wv;
+          }
+        }
+        __syncwarp();
+        // 4. alphas of this lane's 8 pixels
+        const uint32_t mrow = sm.mixed[prow];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int c = half * 8 + i;
+          const float wv = ((mrow >> c) & 1u) ? sm.wmix[prow * 16 + c] : (float)(backdrop * 256 + sm.cover[prow][c]) / 256.0f;
+          const uint32_t v = ((inmask >> i) & 1u) ? area_alpha_u8(area_resolve_alpha(wv, even_odd)) : 0u;
+          if (i < 4) d0 |= v << (8 * i);
+          else d1 |= v << (8 * (i - 4));
+        }
+      } else {
       float w[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) w[i] = (float)backdrop;
@@ -1260,6 +1415,7 @@ __global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
       for (int i = 0; i < 4; i++) {
         d0 |= ((inmask >> i) & 1u) ? area_alpha_u8(area_resolve_alpha(w[i], even_odd)) << (8 * i) : 0u;
         d1 |= ((inmask >> (4 + i)) & 1u) ? area_alpha_u8(area_resolve_alpha(w[4 + i], even_odd)) << (8 * i) : 0u;
+      }
       }
     }
     const bool any = __any_sync(0xffffffffu, (d0 | d1) != 0);
@@ -2848,6 +3004,7 @@ static skb_result run_frame(skb_surface s) {
       SKB_CUDA(cudaMemsetAsync(row_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(item_base + n_ops, 0, 4, st));
       SKB_CUDA(cudaMemsetAsync(counters + 6, 0, 4, st));
+      SKB_CUDA(cudaMemsetAsync(counters + 16, 0, 16, st));   // 64-bit row / item totals (k_op_setup)
       if (rowwalk) SKB_CUDA(cudaMemsetAsync(wrow_base + n_ops, 0, 4, st));
       k_op_setup<<<cdiv(n_ops, 128), 128, 0, st>>>(t, prim_off, geom, (const SurfDesc*)s->surfs.p, row_base, item_base, counters + 6,
                                                    rowwalk ? (RwOp*)s->rw_ops.p : nullptr, wrow_base);
@@ -2858,12 +3015,19 @@ static skb_result run_frame(skb_surface s) {
         SKB_TRY(scan_exclusive(s, wrow_base, n_ops + 1, &launches));
         SKB_TRY(scan_exclusive(s, chord_base, (uint32_t)n_slots + 1, &launches));
       }
-      uint32_t tot[5] = {0, 0, 0, 0, 0};  // one round trip for all the totals
+      uint32_t tot[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // one round trip for all the totals: [0..4] gathered, [8..11] the 64-bit totals
       k_gather5<<<1, 32, 0, st>>>(counters + 8, row_base + n_ops, item_base + n_ops, counters + 6, rowwalk ? wrow_base + n_ops : nullptr,
                                   rowwalk ? chord_base + n_slots : nullptr);
-      SKB_TRY(fetch_words(s, tot, counters + 8, 5));
+      SKB_TRY(fetch_words(s, tot, counters + 8, 12));
       const uint32_t too_big = tot[2];
       launches += 2;
+      {
+        const uint64_t rows64 = (uint64_t)tot[8] | ((uint64_t)tot[9] << 32), items64 = (uint64_t)tot[10] | ((uint64_t)tot[11] << 32);
+        if (rows64 > 0xFFFFFFF0ull || items64 > 0xFFFFFFF0ull) {
+          set_error("the frame's scan rows or (draw, tile) items exceed 2^32: too many large draws for one display list");
+          return SKB_ERROR_OUT_OF_MEMORY;
+        }
+      }
       if (too_big) {
         set_error("the scan rectangle of a clip path exceeds 2^28 pixels (it reaches far beyond the surface)");
         return SKB_ERROR_UNSUPPORTED;
