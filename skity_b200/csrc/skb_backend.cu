@@ -1149,8 +1149,18 @@ __global__ void k_area_backdrop(AreaArgs a) {
   }
 }
 
-#define AREA_WARPS 4
-#define AREA_CAP 128               // lines of a tile held in shared memory at a time
+// Block shape of k_area_cover, measured on C4a (coverage stage, ms): 4 warps / 128 lines / compiler's registers (80) 67.5;
+// 4 warps / 32 lines with at least 8 / 10 / 12 / 14 blocks per SM 49.7 / 45.2 / 46.2 / 51.5; 2 warps / 32 lines / 24 blocks
+// (42 registers, 48 warps per SM) 44.0 — the kernel is a chain of short dependent phases per tile and needs the warps.
+#ifndef AREA_WARPS
+#define AREA_WARPS 2
+#endif
+#ifndef AREA_CAP
+#define AREA_CAP 32                // lines of a tile held in shared memory at a time (more: the plain form below)
+#endif
+#ifndef AREA_MINB
+#define AREA_MINB 24
+#endif
 struct alignas(16) AreaWarpSmem {
   AreaLine line[AREA_CAP];
   uint32_t key[AREA_CAP];
@@ -1178,7 +1188,7 @@ struct alignas(16) AreaWarpSmem {
 //      is stored.
 // A tile with more than AREA_CAP lines (first sorted in place in global memory by selection, then streamed) takes the
 // plain form: every lane accumulates its 8 pixels over all lines that reach its row.
-__global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
+__global__ void __launch_bounds__(AREA_WARPS * 32, AREA_MINB) k_area_cover(AreaArgs a) {
   __shared__ AreaWarpSmem sm_all[AREA_WARPS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t trow = blockIdx.x * AREA_WARPS + wib;
@@ -1204,10 +1214,14 @@ __global__ void __launch_bounds__(AREA_WARPS * 32) k_area_cover(AreaArgs a) {
     const uint32_t beg = a.item_cnt[item];
     const int n = (int)(a.item_cnt[item + 1] - beg);
     const int backdrop = a.item_local[item];
+    if (n == 0 && (backdrop == 0 || (even_odd && !(backdrop & 1)))) continue;   // nothing inside: alpha 0 (uniform over the warp)
     const int x0 = (g.tx0 + txi) * SKB_TILE + half * 8;
-    uint32_t inmask = 0;   // bit i: pixel i of this lane's 8 lies in the scan rectangle
-#pragma unroll
-    for (int i = 0; i < 8; i++) inmask |= (row_in && x0 + i >= xmin && x0 + i < xmax) ? 1u << i : 0u;
+    // bit i: pixel i of this lane's 8 lies in the scan rectangle — all 8, as a span of bits (columns lo .. hi - 1)
+    uint32_t inmask = 0;
+    if (row_in) {
+      const int lo = min(max(xmin - x0, 0), 8), hi = min(max(xmax - x0, 0), 8);
+      inmask = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+    }
     uint32_t d0 = 0, d1 = 0;
     if (n == 0) {
       const uint32_t v = area_alpha_u8(area_resolve_alpha((float)backdrop, even_odd));
