@@ -1167,7 +1167,7 @@ struct alignas(16) AreaWarpSmem {
   int32_t cover[16][17];   // per pixel row: 8.8 sums of the lines' "pixel lies right of the line" terms, scattered at the
                            // first column right of each line, then prefix-summed along the row
   uint32_t mixed[16];      // per pixel row: bit c = pixel (row, c) lies under some line (needs the full formula, in line order)
-  float wmix[256];         // windings of those pixels
+  uint8_t amix[256];       // alphas of those pixels
   uint8_t list[256];       // which pixels they are
 };
 
@@ -1184,8 +1184,8 @@ struct alignas(16) AreaWarpSmem {
 //      multiples of 1/256 below 2^15 are exact in fp32 in any order);
 //   3. the marked pixels — typically a tenth of the tile — are dealt to the lanes, 32 at a time, and each is evaluated
 //      the reference's way: all lines in key order, full formula;
-//   4. every lane resolves the alphas of its 8 pixels (lane -> pixel row lane >> 1, half lane & 1) and the tile's mask
-//      is stored.
+//   4. every lane resolves the alphas of its 8 pixels (lane -> pixel row lane >> 1, half lane & 1; integer arithmetic for
+//      the pixels of step 2, on which the reference's fp32 resolve is exact) and the tile's mask is stored.
 // A tile with more than AREA_CAP lines (first sorted in place in global memory by selection, then streamed) takes the
 // plain form: every lane accumulates its 8 pixels over all lines that reach its row.
 __global__ void __launch_bounds__(AREA_WARPS * 32, AREA_MINB) k_area_cover(AreaArgs a) {
@@ -1367,17 +1367,28 @@ __global__ void __launch_bounds__(AREA_WARPS * 32, AREA_MINB) k_area_cover(AreaA
               if (y_min >= y_max) continue;
               wv = wv + area_edge_contribution(l, pxf, y_min, y_max);
             }
-            sm.wmix[pid] = wv;
+            sm.amix[pid] = (uint8_t)area_alpha_u8(area_resolve_alpha(wv, even_odd));
           }
         }
         __syncwarp();
-        // 4. alphas of this lane's 8 pixels
+        // 4. alphas of this lane's 8 pixels.  A pixel no line passes over has a winding k / 256 with k an integer, and
+        //    coverage_aa_resolve_alpha + the A8 quantisation are exact on such values: |w| (or its distance to the nearest
+        //    even integer) clamped to 1, times 255, plus 0.5, truncated = (a * 255 + 128) >> 8 with a in 1/256ths.
         const uint32_t mrow = sm.mixed[prow];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const int c = half * 8 + i;
-          const float wv = ((mrow >> c) & 1u) ? sm.wmix[prow * 16 + c] : (float)(backdrop * 256 + sm.cover[prow][c]) / 256.0f;
-          const uint32_t v = ((inmask >> i) & 1u) ? area_alpha_u8(area_resolve_alpha(wv, even_odd)) : 0u;
+          const int kw = backdrop * 256 + sm.cover[prow][c];
+          uint32_t ak = (uint32_t)(kw < 0 ? -kw : kw);
+          if (even_odd) {
+            const uint32_t kk = ak & 511u;
+            ak = kk > 256u ? 512u - kk : kk;
+          } else {
+            ak = ak > 256u ? 256u : ak;
+          }
+          uint32_t v = (ak * 255u + 128u) >> 8;
+          if ((mrow >> c) & 1u) v = sm.amix[prow * 16 + c];
+          if (!((inmask >> i) & 1u)) v = 0u;
           if (i < 4) d0 |= v << (8 * i);
           else d1 |= v << (8 * (i - 4));
         }
