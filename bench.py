@@ -167,6 +167,14 @@ def run_ours(args):
     n_dl = dl_pinned.numel()
 
     dev = device.Device(local_rank)
+    if args.coverage_mode == "area":
+        _create = dev.create_surface
+
+        def create_area_surface(w, h):
+            sf = _create(w, h)
+            sf.set_coverage_mode(1)
+            return sf
+        dev.create_surface = create_area_surface
     surf = dev.create_surface(surf_w, surf_h)
     stream = torch.cuda.ExternalStream(surf.stream(), device=torch.device("cuda", local_rank))
     bands = multigpu.band_ranges(H, world) if partition == "bands" else None
@@ -357,7 +365,7 @@ def run_ours(args):
     # ---- the complete plug-in path (what a skity::Canvas user pays): CudaContextCreate'd surface -> LockCanvas ->
     # Canvas calls (host encode) -> Flush -> ReadPixels, per step; N = 1 only
     ms_canvas = None
-    if world == 1 and partition != "batch" and not args.no_canvas_e2e:
+    if world == 1 and partition != "batch" and not args.no_canvas_e2e and args.coverage_mode == "exact":
         try:
             surf.close()      # its arenas: the plug-in's own surface needs the room
             surf = None
@@ -386,7 +394,9 @@ def run_ours(args):
         peak, peak_kind = measured_peak()
         names = device.STAGE_NAMES
         cands = [("k_walk", "sweep: edges -> trapezoid rows", float(stage_ms[2]), st["bytes_walk"]),
-                 ("k_cover", "coverage: trapezoid rows -> A8 tile masks", float(stage_ms[3]), st["bytes_cover"]),
+                 ("k_cover", "coverage: trapezoid rows -> A8 tile masks", float(stage_ms[3]), st["bytes_cover"])
+                 if args.coverage_mode == "exact" else
+                 ("k_area_bin+k_area_cover", "AREA coverage: binned lines -> A8 tile masks", float(stage_ms[3]), st["bytes_area"]),
                  ("k_fine", "fine: paint + blend, RGBA8 tiles", float(stage_ms[5]), st["bytes_fine"])]
         if stage_ms[6] > 0 and st.get("bytes_blur"):
             cands.append(("k_blur", "blur: separable StackBlur, 2 passes", float(stage_ms[6]), st["bytes_blur"]))
@@ -404,7 +414,7 @@ def run_ours(args):
                                               "bands stored into rank 0's canvas by the fine pass (NVLink peer memory)" if world > 1 else "single GPU, whole canvas",
                                      "canvas": "one canvas per rank", "batch": "canvases dealt to ranks, one display list per rank"}[partition],
                        "coord_mode": "wide (canvas > 8192 px: the reference's 16.16 conversion without its int32 wrap)" if max(W, H) > 8192 else "reference",
-                       "frames_in_flight": 1},
+                       "frames_in_flight": 1, "coverage_mode": args.coverage_mode},
             "paths_per_s": round(paths / (ms_resident / 1e3), 1),
             "e2e": {"value": round(mpix / (ms_e2e_used / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(n_dl) * world,
                     "d2h_bytes_per_step": int(canvases * W * H * 4), "ms_per_step": round(ms_e2e_used, 4),
@@ -630,6 +640,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4a")
+    ap.add_argument("--coverage-mode", default="exact", choices=["exact", "area"],
+                    help="exact (default): the software backend's coverage, bit for bit — the parity path and the headline; "
+                         "area: the coverage-AA tiler's algorithm (north star stages 2-3), exact against its own oracle, NOT the "
+                         "software backend's coverage (DESIGN.md 4c)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-canvas-e2e", action="store_true")
     args = ap.parse_args()
