@@ -769,7 +769,8 @@ struct alignas(16) CoverWarpSmem {
 //   4. lane L then owns pixel row L>>1 and the 8-pixel half L&1 of each tile: two vector loads,
 //      classification (empty / solid / one plane / two planes) by ballot, coalesced 256-byte stores.
 #ifndef COVER_MINB
-#define COVER_MINB 24  // measured: C1 0.629 -> 0.595 ms, C4a 23.6 -> 22.4 ms (no spill left; the cap itself is above what ptxas uses)
+#define COVER_MINB 32  // 64 registers.  Measured, C1 / C4a coverage (ms): unset 0.629 / 23.6, 24 blocks 0.595 / 22.4, 28: 0.609 / 23.0,
+                       // 32: 0.581 / 21.5; two warps per block with 14 / 16 blocks: 0.632 / 24.1, 0.638 / 24.5; four warps: 0.694 / 27.6
 #endif
 #ifdef COVER_MINB  // minimum resident blocks per SM (caps the registers); unset = the compiler's own choice
 #define COVER_BOUNDS __launch_bounds__(COVER_WARPS * 32, COVER_MINB)
