@@ -1475,30 +1475,56 @@ struct ClipStateDesc {
 // 2 + 4 * rw <= 8 * rw.
 #define SKB_CLIP_KIND_DIFF 1u
 
-__global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* surfs, ClipStateDesc* states, uint32_t* px_cnt) {
+// A ClipOp::kDifference clip applied while a path clip is in force ("T2": RecursiveClip's spans_subtraction(clip spans,
+// fresh spans), sw_canvas.cc:188-189): the result is an intersecting state over the PARENT's region — the region of the
+// first clip of the chain (`region_op`) —, made by k_clip_t2 from the parent's table and the fresh path's sorted row
+// spans.  The records are worked out on the host (validate_dl) in op order.
+struct ClipT2Rec {
+  uint32_t op, region_op, depth, pad;
+};
+
+// the scan rectangle of a clip path as a table region (+ the column FindSpan's `+ 1` can reach), on the surface or not:
+// HasClip() and nested clips see every span of a clip path (sw_canvas.cc:315-336)
+__device__ __forceinline__ void clip_region_of(const OpGeom& g, int32_t* rx0, int32_t* ry0, int32_t* rw, int32_t* rh) {
+  *rx0 = *ry0 = *rw = *rh = 0;
+  if (!g.empty && g.ntx > 0) {
+    *rx0 = g.scan_l;
+    *ry0 = g.scan_t;
+    *rw = g.scan_r + 1 - g.scan_l;
+    *rh = g.scan_b - g.scan_t;
+    if (*rw <= 0 || *rh <= 0) *rw = *rh = 0;
+  }
+}
+
+__global__ void k_clip_sizes(FrameTables t, const OpGeom* geom, const SurfDesc* surfs, ClipStateDesc* states, uint32_t* px_cnt,
+                             const ClipT2Rec* t2, uint32_t n_t2) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const skb_dl_op o = t.ops[op];
   if (o.kind != SKB_OP_CLIP) return;
-  const OpGeom g = geom[op];
-  const SurfDesc sd = surfs[o.surface];
   ClipStateDesc d;
-  d.rx0 = d.ry0 = d.rw = d.rh = 0;
   d.table_off = 0;
   d.nonempty = 0;
   d.op = op;
   d.kind = o.aux == 0 ? SKB_CLIP_KIND_DIFF : 0u;
-  if (!g.empty && g.ntx > 0) {
-    // the whole scan rectangle (+ the column FindSpan's `+ 1` can reach), on the surface or not: HasClip() and
-    // nested clips see every span of a clip path (sw_canvas.cc:315-336)
-    d.rx0 = g.scan_l;
-    d.ry0 = g.scan_t;
-    d.rw = g.scan_r + 1 - g.scan_l;
-    d.rh = g.scan_b - g.scan_t;
-    if (d.rw <= 0 || d.rh <= 0) d.rw = d.rh = 0;
+  clip_region_of(geom[op], &d.rx0, &d.ry0, &d.rw, &d.rh);
+  uint32_t px = (uint32_t)(d.rw * d.rh);
+  if (o.aux == 0 && o.clip_in != 0) {
+    // T2: the state's arena holds the fresh path's sorted row spans (difference layout, the fresh path's own region)
+    // followed by the new intersecting table over the parent's region
+    uint32_t lo = 0, hi = n_t2;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (t2[mid].op < op) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t fresh_px = px;
+    d.kind = 0u;
+    clip_region_of(geom[lo < n_t2 && t2[lo].op == op ? t2[lo].region_op : op], &d.rx0, &d.ry0, &d.rw, &d.rh);
+    d.table_off = fresh_px;
+    px = fresh_px + (uint32_t)(d.rw * d.rh);
   }
   states[o.clip_out] = d;
-  px_cnt[o.clip_out] = (uint32_t)(d.rw * d.rh);
+  px_cnt[o.clip_out] = px;
 }
 
 struct ClipArgs {
@@ -1509,7 +1535,14 @@ struct ClipArgs {
   const uint8_t* op_depth;       // nesting depth of the state a CLIP op defines
   uint32_t* overflow;            // set when a pixel needs more entries / planes than provided
   uint32_t n_rows;
+  const ClipT2Rec* t2;           // difference clips on top of a path clip, in op order
+  uint32_t n_t2;
 };
+
+// Row y of a state's table (intersecting: SKB_CLIP_MAXE entries per pixel; difference: [n, 0, spans ...]).
+__device__ __forceinline__ uint32_t* clip_state_row(const ClipArgs& a, uint32_t state, const ClipStateDesc& d, int y) {
+  return a.table + ((size_t)a.state_px_off[state] + (size_t)d.table_off + (size_t)(y - d.ry0) * (size_t)d.rw) * SKB_CLIP_MAXE;
+}
 
 // mode 0: build the clip states of nesting depth `level`; mode 1: rasterise the clipped draws.
 // One WARP per row: every lane takes a run of consecutive pixels (at least SKB_CLIP_SEG_MIN) and, except the
@@ -1549,15 +1582,14 @@ __global__ void __launch_bounds__(128) k_clip_rows(ClipArgs a, int mode, int lev
     clipped = par.nonempty != 0;
   }
   const bool c_row_in = clipped && y >= par.ry0 && y < par.ry0 + par.rh;
-  const uint32_t* c_row = c_row_in ? a.table + ((size_t)a.state_px_off[o.clip_in] + (size_t)(y - par.ry0) * par.rw) * SKB_CLIP_MAXE
-                                   : nullptr;
+  const uint32_t* c_row = c_row_in ? clip_state_row(a, o.clip_in, par, y) : nullptr;
   // own state (mode 0)
   ClipStateDesc own;
   uint32_t* own_row = nullptr;
   if (mode == 0) {
     own = a.states[o.clip_out];
     if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
-    own_row = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+    own_row = clip_state_row(a, o.clip_out, own, y);
   }
 
   // the row's prepared records: one array per warp in shared memory, every lane prepares its share
@@ -1725,7 +1757,10 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int lev
   const uint32_t op = c.trow_op[r / SKB_TILE];
   const skb_dl_op o = c.ops[op];
   if (mode == 0) {
+    // level 0: the difference states proper (no parent); level > 0: the fresh row spans of the difference clips applied
+    // on top of a path clip at that nesting depth (k_clip_t2 consumes them)
     if (o.kind != SKB_OP_CLIP || o.aux != 0) return;
+    if (level == 0 ? o.clip_in != 0 : (o.clip_in == 0 || a.op_depth[op] != (uint8_t)level)) return;
   } else if (mode == 1) {
     if (o.kind != SKB_OP_FILL || o.clip_in == 0 || a.states[o.clip_in].kind != SKB_CLIP_KIND_DIFF) return;
   } else {
@@ -1759,9 +1794,14 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int lev
     x_last = min(x_last, hi);
   }
   if (mode == 0) {
-    const ClipStateDesc own = a.states[o.clip_out];
+    // where the row's list goes: the state's own table (a difference state), or the head of a T2 state's arena
+    ClipStateDesc own = a.states[o.clip_out];
+    if (o.clip_in != 0) {
+      clip_region_of(g, &own.rx0, &own.ry0, &own.rw, &own.rh);
+      own.table_off = 0;
+    }
     if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
-    uint32_t* base = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+    uint32_t* base = clip_state_row(a, o.clip_out, own, y);
     uint2* spans = reinterpret_cast<uint2*>(base + 2);
     DiffStoreD sd_{spans, 0};
     DiffStoreA sa_{spans, 2 * own.rw, 0};
@@ -1776,13 +1816,13 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int lev
     const int n = sd_.n + sa_.n;
     std_sort_replica(spans, n, SpanXLess());
     base[0] = (uint32_t)n;
-    if (n) a.states[o.clip_out].nonempty = 1;
+    if (n && o.clip_in == 0) a.states[o.clip_out].nonempty = 1;
   } else {
     const ClipStateDesc par = a.states[o.clip_in];
     const uint2* ms = nullptr;
     int n_ms = 0;
     if (par.nonempty && par.rw > 0 && y >= par.ry0 && y < par.ry0 + par.rh) {
-      const uint32_t* base = a.table + ((size_t)a.state_px_off[o.clip_in] + (size_t)(y - par.ry0) * par.rw) * SKB_CLIP_MAXE;
+      const uint32_t* base = clip_state_row(a, o.clip_in, par, y);
       n_ms = (int)base[0];
       ms = reinterpret_cast<const uint2*>(base + 2);
     }
@@ -1793,7 +1833,7 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int lev
       const ClipStateDesc own = a.states[o.clip_out];
       if (own.rw == 0 || y < own.ry0 || y >= own.ry0 + own.rh) return;
       DiffCutT<DiffTablePiece> cd, ca_;
-      cd.piece.own_row = a.table + ((size_t)a.state_px_off[o.clip_out] + (size_t)(y - own.ry0) * own.rw) * SKB_CLIP_MAXE;
+      cd.piece.own_row = clip_state_row(a, o.clip_out, own, y);
       cd.piece.rx0 = own.rx0;
       cd.piece.rw = own.rw;
       cd.piece.cover = 0;
@@ -1828,6 +1868,168 @@ __global__ void __launch_bounds__(128) k_clip_diff(ClipArgs a, int mode, int lev
     ca_.piece.zplane = zm ? c.zplane[1] : nullptr;
     clip_row_spans(st, c.pool, row, x_first, x_last, cd, ca_);
   }
+}
+
+// T2 (see ClipT2Rec): one thread per row of the parent's region.  The parent's spans are read back from its per-pixel
+// table by a left-to-right sweep that keeps the spans open at the current pixel (an entry = span start + coverage; the
+// same word in consecutive pixels is one span); when a span ends it is cut by the fresh path's row spans the way
+// spans_subtraction does, and every piece is written to the SAME slot its span occupied in the parent's entry list of
+// each pixel — the reference appends the pieces span by span in list order, so the order of a pixel's entries is the
+// parent's.  Zero-length spans (marker entries) are cut on their own.  Rows the fresh path does not reach are copied.
+// Two spans of the parent with the same start and coverage open at one pixel cannot be told apart in the table: flagged
+// (the frame is refused).  A parent that turned out EMPTY makes the op an ordinary difference clip (sw_canvas.cc:331-334):
+// the state becomes a difference state over the fresh path's region, whose sorted rows are already in place.
+struct T2Piece {
+  const uint32_t* par_row;
+  uint32_t* own_row;
+  int rx0, rw;
+  uint32_t value;    // the parent's entry word of the span being cut
+  bool wrote, lost;
+  __device__ void put(int px, uint32_t e) {
+    if (px < rx0 || px >= rx0 + rw) return;
+    const uint32_t* ps = par_row + (size_t)(px - rx0) * SKB_CLIP_MAXE;
+    for (int j = 0; j < SKB_CLIP_MAXE; j++) {
+      if (ps[j] == value) {
+        own_row[(size_t)(px - rx0) * SKB_CLIP_MAXE + j] = e;
+        wrote = true;
+        return;
+      }
+    }
+    lost = true;
+  }
+  __device__ void operator()(int x, int len) {
+    const uint32_t cover = clip_entry_cover(value);
+    if (len == 0) {
+      put(x, clip_entry(x, cover) | SKB_CLIP_MARKER);
+      return;
+    }
+    for (int px = x; px < x + len; px++) put(px, clip_entry(x, cover));
+  }
+};
+
+__global__ void __launch_bounds__(128) k_clip_t2(ClipArgs a, int level) {
+  const ClipT2Rec rec = a.t2[blockIdx.y];
+  if ((int)rec.depth != level) return;
+  const CoverArgs& c = a.c;
+  const skb_dl_op o = c.ops[rec.op];
+  ClipStateDesc own = a.states[o.clip_out];
+  const ClipStateDesc par = a.states[o.clip_in];
+  const OpGeom g = c.geom[rec.op];
+  int fx0, fy0, fw, fh;   // the fresh path's region: where its sorted row spans are
+  clip_region_of(g, &fx0, &fy0, &fw, &fh);
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, n_thr = gridDim.x * blockDim.x;
+  if (par.kind == SKB_CLIP_KIND_DIFF) {   // difference on difference (PerformMerge): only reachable through an empty parent
+    if (tid == 0) *a.overflow = 1;
+    return;
+  }
+  if (!par.nonempty) {
+    // HasClip() is false: the clip simply becomes the state, with its own op
+    if (tid == 0) {
+      ClipStateDesc d = own;
+      d.kind = SKB_CLIP_KIND_DIFF;
+      d.rx0 = fx0;
+      d.ry0 = fy0;
+      d.rw = fw;
+      d.rh = fh;
+      d.table_off = 0;
+      bool any = false;
+      for (int r = 0; r < fh && !any; r++) any = clip_state_row(a, o.clip_out, d, fy0 + r)[0] != 0;
+      d.nonempty = any ? 1u : 0u;
+      a.states[o.clip_out] = d;
+    }
+    return;
+  }
+  if (own.rw == 0) return;
+  bool wrote = false, bad = false;
+  for (uint32_t r = tid; r < (uint32_t)own.rh; r += n_thr) {
+    const int y = own.ry0 + (int)r;
+    const uint32_t* prow = clip_state_row(a, o.clip_in, par, y);   // same region as ours
+    uint32_t* orow = clip_state_row(a, o.clip_out, own, y);
+    const uint2* ms = nullptr;
+    int n_ms = 0;
+    if (fw > 0 && y >= fy0 && y < fy0 + fh) {
+      ClipStateDesc f = own;
+      f.rx0 = fx0;
+      f.ry0 = fy0;
+      f.rw = fw;
+      f.rh = fh;
+      f.table_off = 0;
+      const uint32_t* base = clip_state_row(a, o.clip_out, f, y);
+      n_ms = (int)base[0];
+      ms = reinterpret_cast<const uint2*>(base + 2);
+    }
+    if (n_ms == 0) {   // "no spans in this line means minus zero": the row's spans stay as they are
+      for (int k = 0; k < own.rw * SKB_CLIP_MAXE; k++) {
+        const uint32_t v = prow[k];
+        orow[k] = v;
+        wrote |= v != 0;
+      }
+      continue;
+    }
+    T2Piece piece;
+    piece.par_row = prow;
+    piece.own_row = orow;
+    piece.rx0 = own.rx0;
+    piece.rw = own.rw;
+    piece.value = 0;
+    piece.wrote = piece.lost = false;
+    uint32_t open_v[2 * SKB_CLIP_MAXE];   // spans open at the previous pixel
+    int n_open = 0;
+    for (int x = 0; x <= own.rw; x++) {
+      uint32_t here[SKB_CLIP_MAXE];
+      int n_here = 0;
+      if (x < own.rw) {
+        const uint32_t* ps = prow + (size_t)x * SKB_CLIP_MAXE;
+        for (int j = 0; j < SKB_CLIP_MAXE && ps[j]; j++) {
+          const uint32_t v = ps[j];
+          if (clip_entry_is_marker(v)) {   // a zero-length span of the parent at this pixel
+            piece.value = v;
+            struct ZeroLen {
+              T2Piece* p;
+              int px;
+              __device__ void operator()(int x_, int len) {
+                if (len == 0) p->put(px, p->value);   // handed down as it is (start and coverage kept)
+                // a zero-length span has no pixels: a piece with length cannot come out of it
+              }
+            } zl{&piece, own.rx0 + x};
+            span_subtract(clip_entry_start(v), 0, ms, n_ms, zl);
+            continue;
+          }
+          for (int k = 0; k < n_here; k++) bad |= here[k] == v;   // twins: indistinguishable in the table
+          here[n_here++] = v;
+        }
+      }
+      // spans that were open and are not here any more end at this pixel
+      for (int k = 0; k < n_open; k++) {
+        bool goes_on = false;
+        for (int j = 0; j < n_here; j++) goes_on |= here[j] == open_v[k];
+        if (goes_on) continue;
+        const int start = clip_entry_start(open_v[k]);
+        piece.value = open_v[k];
+        span_subtract(start, own.rx0 + x - start, ms, n_ms, piece);
+      }
+      // a span whose start lies left of the pixel where it first shows (it began off the region) still counts from
+      // its start: the open list is simply what is here now
+      n_open = n_here;
+      for (int j = 0; j < n_here; j++) open_v[j] = here[j];
+    }
+    // close the gaps the removed pixels left in the entry lists (order kept)
+    for (int x = 0; x < own.rw; x++) {
+      uint32_t* e = orow + (size_t)x * SKB_CLIP_MAXE;
+      int k = 0;
+      for (int j = 0; j < SKB_CLIP_MAXE; j++) {
+        const uint32_t v = e[j];
+        if (v) {
+          e[j] = 0;
+          e[k++] = v;
+        }
+      }
+    }
+    wrote |= piece.wrote;
+    bad |= piece.lost;
+  }
+  if (wrote) a.states[o.clip_out].nonempty = 1;
+  if (bad) *a.overflow = 1;
 }
 
 // One warp per (op, tile) item of a clipped draw: which planes are present, is plane 0 solid.
@@ -2524,6 +2726,7 @@ struct FramePlan {
   int max_depth = 0;
   std::vector<uint8_t> op_depth;         // nesting depth of the clip state a CLIP op defines (empty without clip ops)
   std::vector<skb_dl_op> blur_ops;       // the BLUR ops, in op order
+  std::vector<ClipT2Rec> t2;             // difference clips applied on top of a path clip, in op order
   std::vector<uint32_t> surf_level;      // per surface: dependency depth (see SurfDesc::level)
   uint32_t max_level = 0;
   std::vector<uint8_t> surf_drawn;       // per surface: some FILL op targets it
@@ -2559,7 +2762,7 @@ struct skb_surface_s {
   // device buffers (grow-only)
   Buf area_line_cnt, area_item_cnt, area_item_cursor, area_item_local, area_item_delta, area_row_backdrop, area_lines;
   Buf rw_chord_cnt, rw_slot_op, rw_slots, rw_rank, rw_ops, rw_wrow_cnt, rw_rec_cnt, rw_chords, rw_wgrp_op, rw_ev, rw_tab, rw_res, rw_rec_off;
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, clip_t2, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -2711,6 +2914,7 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes, FramePlan* plan =
     }
   }
   std::vector<uint8_t> diff_state((size_t)h.n_clip_states + 1, 0);   // states defined by a ClipOp::kDifference clip
+  std::vector<uint32_t> region_of_state((size_t)h.n_clip_states + 1, 0);   // the op whose scan rectangle is the state's table region
   std::vector<int> state_depth(plan ? (size_t)h.n_clip_states + 1 : 0, 0);
   std::vector<uint32_t> levels(h.n_surfaces, 0);     // dependency depth of every surface: a surface is composited after the
   std::vector<uint2> uses;                           // surfaces its draws sample and after the source of the blur that makes it
@@ -2786,19 +2990,30 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes, FramePlan* plan =
         return SKB_ERROR_BAD_DISPLAY_LIST;
       }
       if (o.kind == SKB_OP_CLIP) {
-        // ClipOp::kDifference: a state of its own (one difference clip per Save level, how the reference's goldens and
-        // examples use the op), possibly refined by intersecting clips afterwards (k_clip_diff mode 2).  A difference
-        // clip ON TOP of another path clip goes through RecursiveClip's subtraction of the parent's whole span list or
-        // PerformMerge (sw_canvas.cc:188-217): not on the device.
+        // ClipOp::kDifference: a state of its own (k_clip_diff mode 0), refined by intersecting clips afterwards
+        // (mode 2), or applied on top of intersecting path clips (k_clip_t2).  Difference on difference goes through
+        // PerformMerge (sw_canvas.cc:194-217), a std::sort of the two whole span lists with ties: not on the device.
         if (o.aux > 1) {
           set_error("display list: unknown clip op");
           return SKB_ERROR_BAD_DISPLAY_LIST;
         }
-        if (o.aux == 0 && o.clip_in != 0) {
-          set_error("ClipOp::kDifference on top of another path clip is not implemented on the device");
+        if (o.aux == 0 && o.clip_in != 0 && diff_state[o.clip_in]) {
+          set_error("ClipOp::kDifference on top of a ClipOp::kDifference clip (PerformMerge) is not implemented on the device");
           return SKB_ERROR_UNSUPPORTED;
         }
-        diff_state[o.clip_out] = o.aux == 0;
+        // a difference clip on top of an intersecting state leaves an intersecting state over the parent's region,
+        // which is the region of the first clip of the chain
+        const bool t2 = o.aux == 0 && o.clip_in != 0;
+        diff_state[o.clip_out] = o.aux == 0 && !t2;
+        region_of_state[o.clip_out] = t2 ? region_of_state[o.clip_in] : i;
+        if (t2 && plan) {
+          ClipT2Rec rec;
+          rec.op = i;
+          rec.region_op = region_of_state[o.clip_in];
+          rec.depth = 0;   // set below, with the op's depth
+          rec.pad = 0;
+          plan->t2.push_back(rec);
+        }
         if (plan) {
           if (!plan->clip_ops) plan->op_depth.assign(h.n_ops, 0);
           plan->clip_ops = true;
@@ -2811,6 +3026,7 @@ static skb_result validate_dl(const uint8_t* dl, size_t bytes, FramePlan* plan =
           state_depth[o.clip_out] = d;
           plan->op_depth[i] = (uint8_t)d;
           plan->max_depth = std::max(plan->max_depth, d);
+          if (!plan->t2.empty() && plan->t2.back().op == i) plan->t2.back().depth = (uint32_t)d;
         }
       }
     } else if (o.kind == SKB_OP_BLUR) {
@@ -3306,8 +3522,11 @@ static skb_result run_frame(skb_surface s) {
     SKB_CUDA(cudaMemsetAsync(s->clip_states.p, 0, (size_t)(n_states + 2) * sizeof(ClipStateDesc), st));
     SKB_CUDA(cudaMemsetAsync(s->clip_px.p, 0, (size_t)(n_states + 2) * 4, st));
     SKB_CUDA(cudaMemcpyAsync(s->op_depth.p, op_depth.data(), n_ops, cudaMemcpyHostToDevice, st));
+    const uint32_t n_t2 = (uint32_t)s->plan.t2.size();
+    SKB_TRY(buf_reserve(s->clip_t2, (size_t)(n_t2 + 1) * sizeof(ClipT2Rec)));
+    if (n_t2) SKB_CUDA(cudaMemcpyAsync(s->clip_t2.p, s->plan.t2.data(), (size_t)n_t2 * sizeof(ClipT2Rec), cudaMemcpyHostToDevice, st));
     k_clip_sizes<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, (const SurfDesc*)s->surfs.p, (ClipStateDesc*)s->clip_states.p,
-                                                 (uint32_t*)s->clip_px.p);
+                                                 (uint32_t*)s->clip_px.p, (const ClipT2Rec*)s->clip_t2.p, n_t2);
     launches++;
     SKB_TRY(scan_exclusive(s, (uint32_t*)s->clip_px.p, n_states + 2, &launches));
     uint32_t total_px = 0;
@@ -3323,6 +3542,8 @@ static skb_result run_frame(skb_surface s) {
     cl.op_depth = (const uint8_t*)s->op_depth.p;
     cl.overflow = counters + 2;
     cl.n_rows = (uint32_t)n_rows;
+    cl.t2 = (const ClipT2Rec*)s->clip_t2.p;
+    cl.n_t2 = n_t2;
     const uint32_t clip_grid = cdiv(n_rows * 32, 128);
     if (s->plan.diff_clips && clip_grid) {   // difference states have no parent: all of them first
       k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0, 0);
@@ -3334,6 +3555,11 @@ static skb_result run_frame(skb_surface s) {
       if (s->plan.diff_clips && level >= 2) {   // intersecting clips on top of a difference state
         k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 2, level);
         launches++;
+      }
+      if (n_t2 && level >= 2) {   // difference clips on top of an intersecting state: their row spans, then the cut
+        k_clip_diff<<<clip_grid, 128, 0, st>>>(cl, 0, level);
+        k_clip_t2<<<dim3(32, n_t2), 128, 0, st>>>(cl, level);
+        launches += 2;
       }
     }
     if (has_clipped_fills && clip_grid && n_items) {
@@ -3350,7 +3576,7 @@ static skb_result run_frame(skb_surface s) {
     SKB_TRY(fetch_words(s, &over, counters + 2, 1));
     launches++;
     if (over) {
-      set_error("clip stack: a pixel is covered by more clip spans / coverage planes than the device tables hold");
+      set_error("clip stack: a pixel is covered by more clip spans / coverage planes than the device tables hold, two clip spans of one row are indistinguishable (same start and coverage), or a difference clip met an empty parent that was itself a difference clip");
       return SKB_ERROR_UNSUPPORTED;
     }
   }
@@ -3630,7 +3856,7 @@ void skb_surface_destroy(skb_surface s) {
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
   Buf* bufs[] = {&s->area_line_cnt, &s->area_item_cnt, &s->area_item_cursor, &s->area_item_local, &s->area_item_delta, &s->area_row_backdrop, &s->area_lines,
-                 &s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
+                 &s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->clip_t2, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};

@@ -796,7 +796,8 @@ def scene_difference_clips(seed, mode="single", size=None):
     reference's own goldens and examples use the op; Save levels nest, so an inner difference clip lands on the outer
     one (PerformMerge).  "flat": the same without nesting, sometimes behind an axis-aligned intersecting ClipRect (which
     the software backend keeps as clip bounds, not as a span list); "refined": a difference clip followed by one or two
-    intersecting clips in the same Save level — the two forms the CUDA backend implements; "mixed": difference and intersect clips nested in one Save level
+    intersecting clips in the same Save level; "carved": a difference clip applied while intersecting path clips are in
+    force — the forms the CUDA backend implements; "mixed": difference and intersect clips nested in one Save level
     (difference after intersect, intersect after difference); "merge": difference on difference (PerformMerge)."""
     rng = np.random.RandomState(seed)
     w = h = size or int(rng.randint(60, 520))
@@ -817,9 +818,16 @@ def scene_difference_clips(seed, mode="single", size=None):
 
     depth = 0
     for i in range(int(rng.randint(4, 40))):
-        if rng.uniform() < 0.3 and depth < (1 if mode in ("flat", "refined") else 2):
+        if rng.uniform() < 0.3 and depth < (1 if mode in ("flat", "refined", "carved") else 2):
             s.save(); depth += 1
-            if mode == "refined":   # a difference clip refined by intersecting clips in the same Save level
+            if mode == "carved":    # a difference clip applied while intersecting path clips are in force (and clips after it)
+                clip_shape(True)
+                if rng.uniform() < 0.3:
+                    clip_shape(True)
+                clip_shape(False)
+                if rng.uniform() < 0.4:
+                    clip_shape(True)
+            elif mode == "refined":   # a difference clip refined by intersecting clips in the same Save level
                 clip_shape(False)
                 clip_shape(True)
                 if rng.uniform() < 0.4:

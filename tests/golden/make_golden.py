@@ -110,6 +110,7 @@ def golden_scenes():
     out["clip_difference_flat_8"] = scene.scene_difference_clips(8, "flat")
     out["clip_difference_flat_31"] = scene.scene_difference_clips(31, "flat")
     out["clip_difference_refined_12"] = scene.scene_difference_clips(12, "refined")
+    out["clip_difference_carved_9"] = scene.scene_difference_clips(9, "carved")
     out["clip_difference_single_317"] = scene.scene_difference_clips(317, "single")
     out["clip_difference_single_44"] = scene.scene_difference_clips(44, "single")
     out["clip_difference_mixed_23"] = scene.scene_difference_clips(23, "mixed")

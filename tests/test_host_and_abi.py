@@ -112,9 +112,9 @@ def test_display_list_validation_accepts_every_fixture_and_rejects_broken_struct
     import glob
     from skity_b200 import device
     n_ok = n_refused = 0
-    # oracle-only fixtures: a difference clip combined with another path clip in one chain is well formed but not
-    # implemented on the device — refused as such (never approximated)
-    combined = ("clip_difference_single_", "clip_difference_mixed_", "clip_difference_merge_")
+    # oracle-only fixtures: difference on difference (PerformMerge) is well formed but not implemented on the device —
+    # refused as such (never approximated)
+    combined = ("clip_difference_single_", "clip_difference_mixed_", "clip_difference_merge_")   # all hold a difference-on-difference chain
     for f in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
         z = np.load(f)
         if "dl" in z.files:
