@@ -407,6 +407,7 @@ struct WalkArgs {
   const OpGeom* geom;
   const uint32_t* row_base;
   Edge* edges;
+  uint8_t* edges2;   // same layout and size as `edges`: the sweep's compact copy in sweep order (walk_prologue), or null
   QuadState* quads;
   int32_t* ord;
   TrapRec* pool;
@@ -454,8 +455,14 @@ __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
   uint8_t* region = reinterpret_cast<uint8_t*>(a.edges) + (size_t)g.slot_base * (sizeof(Edge) + sizeof(QuadState));
   Edge* E = reinterpret_cast<Edge*>(region);
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)g.n_slots * sizeof(Edge));
+  Edge* E2 = nullptr;
+  QuadState* Q2 = nullptr;
+  if (a.edges2) {
+    uint8_t* region2 = a.edges2 + (size_t)g.slot_base * (sizeof(Edge) + sizeof(QuadState));
+    E2 = reinterpret_cast<Edge*>(region2);   // the quadratic states follow the compact edges (walk_prologue)
+  }
   walk_path(E, Q, (int)g.n_slots, a.ord + g.slot_base, g.scan_top_f, g.scan_bottom_f, g.start_y, stop_y, g.left_clip,
-            g.right_clip, (int)a.t.ops[op].fill_type, sink, (int)a.t.wide);
+            g.right_clip, (int)a.t.ops[op].fill_type, sink, (int)a.t.wide, E2, Q2);
   }
 }
 
@@ -2762,7 +2769,7 @@ struct skb_surface_s {
   // device buffers (grow-only)
   Buf area_line_cnt, area_item_cnt, area_item_cursor, area_item_local, area_item_delta, area_row_backdrop, area_lines;
   Buf rw_chord_cnt, rw_slot_op, rw_slots, rw_rank, rw_ops, rw_wrow_cnt, rw_rec_cnt, rw_chords, rw_wgrp_op, rw_ev, rw_tab, rw_res, rw_rec_off;
-  Buf dl, geom, seg_op, prim_cnt, edges, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, clip_t2, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
+  Buf dl, geom, seg_op, prim_cnt, edges, edges2, quads, walk_lists, mask_extra[SKB_CLIP_PLANES - 2], clip_states, clip_px, clip_table, clip_t2, op_depth, ord, row_cnt, item_cnt, rows, trow_op, pool, counters, mask0, mask1, zmask, zplane_extra[SKB_CLIP_PLANES - 1], item_flags, tile_cnt,
       tile_fill, cmds, cmds_sorted, surfs, surf_tile_base, temp_px, scan_tmp, blur_jobs, blur_rows, blur_cols, blur_tmp_ptrs,
       blur_tmp;
   // host mirrors kept for the debug tap
@@ -3315,6 +3322,11 @@ static skb_result run_frame(skb_surface s) {
     wa.geom = geom;
     wa.row_base = row_base;
     wa.edges = edges;
+    wa.edges2 = nullptr;
+#ifndef SKB_WALK_NO_COMPACT
+    SKB_TRY(buf_reserve(s->edges2, n_slots * (sizeof(Edge) + sizeof(QuadState))));
+    wa.edges2 = (uint8_t*)s->edges2.p;
+#endif
     wa.quads = nullptr;
     wa.ord = (int32_t*)s->ord.p;
     wa.pool = (TrapRec*)s->pool.p;
@@ -3856,7 +3868,7 @@ void skb_surface_destroy(skb_surface s) {
   cudaSetDevice(s->dev->ordinal);
   if (s->stream) cudaStreamSynchronize(s->stream);
   Buf* bufs[] = {&s->area_line_cnt, &s->area_item_cnt, &s->area_item_cursor, &s->area_item_local, &s->area_item_delta, &s->area_row_backdrop, &s->area_lines,
-                 &s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->clip_t2, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
+                 &s->rw_chord_cnt, &s->rw_slot_op, &s->rw_slots, &s->rw_rank, &s->rw_ops, &s->rw_wrow_cnt, &s->rw_rec_cnt, &s->rw_chords, &s->rw_wgrp_op, &s->rw_ev, &s->rw_tab, &s->rw_res, &s->rw_rec_off, &s->dl, &s->geom, &s->seg_op, &s->prim_cnt, &s->edges, &s->edges2, &s->quads, &s->walk_lists, &s->mask_extra[0], &s->mask_extra[1], &s->mask_extra[2], &s->mask_extra[3], &s->mask_extra[4], &s->mask_extra[5], &s->clip_states, &s->clip_px, &s->clip_table, &s->clip_t2, &s->op_depth, &s->ord, &s->row_cnt, &s->item_cnt, &s->rows, &s->trow_op, &s->pool,
                  &s->counters, &s->mask0, &s->mask1, &s->zmask, &s->zplane_extra[0], &s->zplane_extra[1], &s->zplane_extra[2], &s->zplane_extra[3], &s->zplane_extra[4], &s->zplane_extra[5], &s->zplane_extra[6], &s->item_flags, &s->tile_cnt, &s->tile_fill, &s->cmds, &s->cmds_sorted,
                  &s->surfs, &s->surf_tile_base, &s->temp_px, &s->scan_tmp, &s->blur_jobs, &s->blur_rows, &s->blur_cols,
                  &s->blur_tmp_ptrs, &s->blur_tmp};

@@ -27,6 +27,21 @@ SKB_HD uint32_t skb_host_fetch_add(uint32_t* p, uint32_t v) {
 }
 #endif
 
+// Records and row entries are written once by the sweep and read once, a whole stage later, by the coverage kernels:
+// they are stored with the streaming (evict-first) hint so that they do not push the sweep's own working set — the
+// edges of the paths in flight, re-read and re-written every band — out of the L2 (C4a: 27.9 -> 26.4 ms).
+#if defined(__CUDA_ARCH__) && !defined(SKB_WALK_NO_STREAM)
+#define SKB_STORE_REC(p, r)                                                                                      \
+  do {                                                                                                           \
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4((uint32_t)(r).y, (uint32_t)(r).ul, (uint32_t)(r).ur, (uint32_t)(r).ll)); \
+    __stcs(reinterpret_cast<uint4*>(p) + 1, make_uint4((uint32_t)(r).lr, (uint32_t)(r).ldy, (uint32_t)(r).rdy, (r).flags)); \
+  } while (0)
+#define SKB_STORE_ROW(p, e) __stcs((p), (e))
+#else
+#define SKB_STORE_REC(p, r) (*(p) = (r))
+#define SKB_STORE_ROW(p, e) (*(p) = (e))
+#endif
+
 // Where a walking thread puts its records.  rows[] has one (first index, count) pair per scan
 // row of the path, rows processed top-down.
 struct RecSink {
@@ -60,7 +75,7 @@ SKB_HD void sink_flush_row(RecSink& s) {
     uint2 e;
     e.x = s.row_first;
     e.y = s.row_count;
-    s.rows[s.cur_row] = e;
+    SKB_STORE_ROW(&s.rows[s.cur_row], e);
   }
 }
 
@@ -89,7 +104,7 @@ SKB_HDN void sink_emit(RecSink& s, const TrapRec& r) {
     s.row_first = s.cur;
     s.row_count = 0;
   }
-  s.pool[s.cur] = r;
+  SKB_STORE_REC(&s.pool[s.cur], r);
   s.cur++;
   s.left--;
   s.row_count++;
@@ -305,8 +320,14 @@ struct WalkState {
 
 // SWEdgeBuilder culling (sw_edge.cc:322-336) + SortEdges + ProcessEdges (sw_raster.cc:679-729) and
 // the prologue of WalkEdges (:549-563).  Returns false when the path has no edge to sweep.
-SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
-                           fx left_clip, fx right_clip, WalkState& ws, int wide = 0) {
+// With E2 (room for 2 * n_slots entries; Q2 null = the quadratic states go right behind the compact edges) the edges that take part are copied there in sweep order, one after the
+// other (slots 2..n+1, the links simply i-1 / i+1), and the sweep runs on the copy: the edges that are active together
+// — neighbours in sweep order far more often than along the contour — then share cache lines, and the invalid slots
+// between them are gone.  Slot numbers are only names to the sweep (ties of the sort are decided before the copy), so
+// the records are the same.  (Measured on C4a: 27.9 -> 24.7 ms; the copy kept in shared memory instead — 10 to 30 edges
+// per thread — is slower at every size, 35 to 62 ms: the sweep lives on the number of paths in flight.)
+SKB_HDN bool walk_prologue(Edge*& E, QuadState*& Q, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
+                           fx left_clip, fx right_clip, WalkState& ws, int wide = 0, Edge* E2 = nullptr, QuadState* Q2 = nullptr) {
   int n = 0;
   for (int i = 2; i < n_slots; i++) {
     if (!((E[i].curve >> 24) & 1)) continue;
@@ -320,16 +341,34 @@ SKB_HDN bool walk_prologue(Edge* E, int n_slots, int32_t* ord, float scan_top_f,
   }
   if (n == 0) return false;
   sort_edge_indices(E, ord, n);
-  for (int i = 0; i < n; i++) {
-    E[ord[i]].prev = i == 0 ? SKB_HEAD : ord[i - 1];
-    E[ord[i]].next = i == n - 1 ? SKB_TAIL : ord[i + 1];
+  int first = ord[0], last = ord[n - 1];
+  if (E2) {
+    if (!Q2) Q2 = reinterpret_cast<QuadState*>(E2 + (n + 2));   // right behind the compact edges (same element size)
+    for (int i = 0; i < n; i++) {
+      const int src = ord[i];
+      Edge e = E[src];
+      const bool quad = (e.curve >> 25) & 1;
+      e.prev = i == 0 ? SKB_HEAD : i + 1;
+      e.next = i == n - 1 ? SKB_TAIL : i + 3;
+      E2[i + 2] = e;
+      if (quad) Q2[i + 2] = Q[src];
+    }
+    E = E2;
+    Q = Q2;
+    first = 2;
+    last = n + 1;
+  } else {
+    for (int i = 0; i < n; i++) {
+      E[ord[i]].prev = i == 0 ? SKB_HEAD : ord[i - 1];
+      E[ord[i]].next = i == n - 1 ? SKB_TAIL : ord[i + 1];
+    }
   }
   Edge& H = E[SKB_HEAD];
   Edge& T = E[SKB_TAIL];
-  H.prev = -1; H.next = ord[0];
+  H.prev = -1; H.next = first;
   H.upper_y = H.lower_y = SKB_FX_MIN; H.dx = 0; H.dy = SKB_FX_MAX;
   H.curve = 0;
-  T.prev = ord[n - 1]; T.next = -1;
+  T.prev = last; T.next = -1;
   T.upper_y = T.lower_y = SKB_FX_MAX; T.dx = 0; T.dy = SKB_FX_MAX;
   T.curve = 0;
   // WalkEdges (sw_raster.cc:546-677)
@@ -501,9 +540,10 @@ SKB_HDN void walk_bands_flat(Edge* E, QuadState* Q, WalkState ws, int stop_y, fx
 // The band loop in the reference's own shape (a loop over bands around a loop over the active edges) lives in
 // tests/sim/walk_nested.hpp: the CPU simulation uses it to cross-check the flat loop; the product never runs it.
 SKB_HDN void walk_path(Edge* E, QuadState* Q, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
-                       int stop_y, fx left_clip, fx right_clip, int even_odd, RecSink& sink, int wide = 0) {
+                       int stop_y, fx left_clip, fx right_clip, int even_odd, RecSink& sink, int wide = 0,
+                       Edge* E2 = nullptr, QuadState* Q2 = nullptr) {
   WalkState ws;
-  if (!walk_prologue(E, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws, wide)) return;
+  if (!walk_prologue(E, Q, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws, wide, E2, Q2)) return;
   walk_bands_flat(E, Q, ws, stop_y, left_clip, right_clip, even_odd, sink);
 }
 

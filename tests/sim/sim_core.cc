@@ -18,7 +18,7 @@ using namespace skb;
 // SKB_SIM_WALK_MODE selects the sweep variant (skb_walk.cuh walk_path `mode`); default = what the GPU runs.
 static int sim_walk_mode() {
   const char* m = getenv("SKB_SIM_WALK_MODE");
-  return m ? atoi(m) : 1;
+  return m ? atoi(m) : 2;
 }
 
 

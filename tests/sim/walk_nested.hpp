@@ -7,6 +7,8 @@
 #ifndef SKB_TESTS_SIM_WALK_NESTED_HPP
 #define SKB_TESTS_SIM_WALK_NESTED_HPP
 
+#include <vector>
+
 #include "skity_b200/csrc/skb_walk.cuh"
 
 namespace skb {
@@ -110,12 +112,18 @@ SKB_HDN void walk_bands_nested(Edge* E, QuadState* Q, const uint16_t* qmap, Walk
 // mode 0: nested loops (cross-check); otherwise the flat loop
 inline void sim_walk_path(Edge* E, QuadState* Q, int n_slots, int32_t* ord, float scan_top_f, float scan_bottom_f, int start_y,
                           int stop_y, fx left_clip, fx right_clip, int even_odd, RecSink& sink, int mode, int wide) {
+  if (mode == 2) {  // the flat loop on the compact copy in sweep order (what k_walk runs)
+    std::vector<Edge> E2((size_t)n_slots * 2);
+    walk_path(E, Q, n_slots, ord, scan_top_f, scan_bottom_f, start_y, stop_y, left_clip, right_clip, even_odd, sink, wide,
+              E2.data(), nullptr);
+    return;
+  }
   if (mode != 0) {
     walk_path(E, Q, n_slots, ord, scan_top_f, scan_bottom_f, start_y, stop_y, left_clip, right_clip, even_odd, sink, wide);
     return;
   }
   WalkState ws;
-  if (!walk_prologue(E, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws, wide)) return;
+  if (!walk_prologue(E, Q, n_slots, ord, scan_top_f, scan_bottom_f, start_y, left_clip, right_clip, ws, wide)) return;
   walk_bands_nested(E, Q, nullptr, ws, stop_y, left_clip, right_clip, even_odd, sink);
 }
 

@@ -96,10 +96,13 @@ def test_sim_whole_frame_with_nested_clips():
     assert np.array_equal(got, port.render(dl))
 
 
-def test_sim_sweep_nested_form_agrees(monkeypatch):
-    """The sweep exists in two forms (skb_walk.cuh): the flat single loop the GPU runs (covered
-    above) and the reference-shaped nested loops; both must produce the oracle's coverage."""
-    monkeypatch.setenv("SKB_SIM_WALK_MODE", "0")
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_sim_sweep_other_forms_agree(monkeypatch, mode):
+    """The sweep exists in more forms than the flat single loop covered above (skb_walk.cuh): the reference-shaped
+    nested loops (0), and the flat loop run on the edges where the flatten stage left them (1; the default, like k_walk,
+    runs it on a compact copy in sweep order, walk_prologue E2); all
+    must produce the oracle's coverage."""
+    monkeypatch.setenv("SKB_SIM_WALK_MODE", mode)
     check_scene(scene.scene_c0(blur=False))
     check_scene(scene.scene_c2(16, 256, 5, clip_every=0))
     check_scene(scene.scene_random_fills(24, 256, 9, box=160.0))
