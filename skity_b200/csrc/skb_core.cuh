@@ -47,24 +47,38 @@ SKB_HD fx fx_add(fx a, fx b) { return (fx)((uint32_t)a + (uint32_t)b); }
 SKB_HD fx fx_sub(fx a, fx b) { return (fx)((uint32_t)a - (uint32_t)b); }
 SKB_HD fx fx_abs(fx v) { return v < 0 ? (fx)(0u - (uint32_t)v) : v; }
 SKB_HD fx fx_mul(fx a, fx b) { return (fx)(((int64_t)a * (int64_t)b) >> 16); }
-SKB_HD fx fx_div(fx n, fx d) {  // SWFixedDiv: 64-bit quotient (truncating) clamped to +-0x7FFFFFFF
-#if defined(__CUDA_ARCH__) && !defined(SKB_NO_FAST_DIV)
-  // |n << 16| < 2^47 and |d| < 2^31: an FP64 quotient is within one of the exact integer quotient,
-  // one remainder check makes it exact — far cheaper than the emulated 64-bit integer division.
-  const bool neg = (n < 0) != (d < 0);
-  const uint64_t a = (uint64_t)(n < 0 ? -(int64_t)n : (int64_t)n) << 16;
-  const uint64_t b = (uint64_t)(d < 0 ? -(int64_t)d : (int64_t)d);
-  uint64_t qa = (uint64_t)__double2ull_rz(__ddiv_rn((double)a, (double)b));
-  int64_t r = (int64_t)(a - qa * b);
-  if (r < 0) qa--;
-  else if ((uint64_t)r >= b) qa++;
-  int64_t q = neg ? -(int64_t)qa : (int64_t)qa;
-#else
+// SWFixedDiv: the truncating 64-bit quotient (n << 16) / d clamped to +-0x7FFFFFFF.
+// Computed in FP64 (the emulated 64-bit integer division costs several times as much on the device): with a = |n| * 2^16
+// < 2^47 and b = |d| < 2^31 both exact doubles, a * (1 / b) with a correctly rounded reciprocal is within 2^-5 of a / b,
+// so its truncation is the exact quotient or one off; the remainder a - q * b (an integer below 2^48: the fused
+// multiply-add is exact) tells which, and one step corrects it.  Every operation is a single IEEE operation, the same on
+// the host and on the device (checked against the integer form by tests/test_sim_stages.py).
+SKB_HD fx fx_div_int(fx n, fx d) {
   int64_t q = (int64_t)((uint64_t)(int64_t)n << 16) / (int64_t)d;
-#endif
   if (q < (int64_t)SKB_FX_MIN) q = SKB_FX_MIN;
   if (q > (int64_t)SKB_FX_MAX) q = SKB_FX_MAX;
   return (fx)q;
+}
+SKB_HD fx fx_div(fx n, fx d) {
+#if !defined(SKB_NO_FAST_DIV)
+  const bool neg = (n < 0) != (d < 0);
+  const double a = (double)(n < 0 ? 0u - (uint32_t)n : (uint32_t)n) * 65536.0;
+  const double b = (double)(d < 0 ? 0u - (uint32_t)d : (uint32_t)d);
+#if defined(__CUDA_ARCH__)
+  double q = trunc(__dmul_rn(a, __drcp_rn(b)));
+  const double r = __fma_rn(-q, b, a);
+#else
+  double q = trunc(a * (1.0 / b));
+  const double r = fma(-q, b, a);
+#endif
+  if (r < 0.0) q -= 1.0;
+  else if (r >= b) q += 1.0;
+  q = q < 2147483647.0 ? q : 2147483647.0;
+  const int32_t qi = (int32_t)q;
+  return neg ? -qi : qi;
+#else
+  return fx_div_int(n, d);
+#endif
 }
 SKB_HD fx snap_y(fx y) { return (fx)((((uint32_t)y + (SKB_FX1 >> 3)) >> 14) << 14); }
 SKB_HD int fx_floor_i(fx x) { return x >> 16; }

@@ -342,6 +342,33 @@ extern "C" long sim_atan2f_mismatches(long n, unsigned long long seed) {
   return bad;
 }
 
+// Number of inputs on which fx_div (FP64 with an exact correction step) differs from the integer form of SWFixedDiv:
+// n pseudo-random operand pairs of every magnitude, plus the corner values against each other.
+extern "C" long sim_fx_div_mismatches(long n, unsigned long long seed) {
+  unsigned long long s = seed ? seed : 88172645463325252ull;
+  long bad = 0;
+  const int32_t corner[] = {1, -1, 2, -2, 3, 255, 256, 65535, 65536, 65537, -65536, 0x7FFF, 0x8000, 0x10000, 0xFFFFF, 0x100000,
+                            0x1FFFFF, 0x200000, 0x7FFFFFFF, -0x7FFFFFFF, (int32_t)0x80000000, 0x40000000, -0x40000000, 0x7FFFFFFE,
+                            0x55555555, 0x33333333, 46341, 46340, 92681, 1000003};
+  const int nc = (int)(sizeof(corner) / sizeof(corner[0]));
+  for (int i = 0; i < nc; i++)
+    for (int j = 0; j < nc; j++)
+      for (int z = 0; z < 2; z++) {
+        const int32_t a = z ? 0 : corner[i], b = corner[j];
+        if (skb::fx_div(a, b) != skb::fx_div_int(a, b)) bad++;
+      }
+  for (long i = 0; i < n; i++) {
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    int32_t a = (int32_t)(s >> 32) >> (int)(s & 31);
+    s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+    int32_t b = (int32_t)(s >> 32) >> (int)(s & 31);
+    if (b == 0) b = 1;
+    if (i % 5 == 0) a = (int32_t)((int64_t)b * (int32_t)((s >> 8) & 0xFFFF) >> 16);   // near-exact multiples
+    if (skb::fx_div(a, b) != skb::fx_div_int(a, b)) bad++;
+  }
+  return bad;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row-parallel walk (skb_rowwalk.cuh) against the sequential sweep (skb_walk.cuh), record by record.
 #include "skity_b200/csrc/skb_rowwalk.cuh"

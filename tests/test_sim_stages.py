@@ -141,6 +141,16 @@ def test_sweep_gradient_angle_is_the_c_librarys_atan2f():
     assert lib.sim_atan2f_mismatches(3_000_000, 12345) == 0
 
 
+def test_fixed_point_division_in_fp64_is_the_integer_division():
+    """fx_div computes SWFixedDiv's truncating 64-bit quotient in FP64 with one exact correction step (skb_core.cuh); the
+    host build runs the same IEEE operations as the device: no operand pair may differ from the integer form."""
+    import ctypes
+    lib = simlib.lib()
+    lib.sim_fx_div_mismatches.restype = ctypes.c_long
+    lib.sim_fx_div_mismatches.argtypes = [ctypes.c_long, ctypes.c_ulonglong]
+    assert lib.sim_fx_div_mismatches(20_000_000, 777) == 0
+
+
 # ---- row-parallel walk (skb_rowwalk.cuh) against the sequential sweep, record by record ---------------------------
 def _rowwalk_scene(s, w=None, h=None):
     import collections
