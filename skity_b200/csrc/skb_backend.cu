@@ -2218,6 +2218,14 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
   uint32_t dst[8] = {swap_rb(q0.x), swap_rb(q0.y), swap_rb(q0.z), swap_rb(q0.w),
                      swap_rb(q1.x), swap_rb(q1.y), swap_rb(q1.z), swap_rb(q1.w)};
 
+  // The loops over a lane's eight pixels that stay rolled (the paints with a lot of code per pixel) work on dst[0] and
+  // rotate the array once per pixel: every index is a constant, so dst[] lives in registers — indexed by the loop
+  // counter it sat in local memory, loaded and stored around every command, the branch-free solid path included.
+#define SKB_ROTATE_DST(d)                                                                                       \
+  do {                                                                                                          \
+    dst[0] = dst[1]; dst[1] = dst[2]; dst[2] = dst[3]; dst[3] = dst[4];                                         \
+    dst[4] = dst[5]; dst[5] = dst[6]; dst[6] = dst[7]; dst[7] = (d);                                            \
+  } while (0)
   // A command that covers the whole tile with an opaque solid colour (SrcOver) leaves nothing of what was blended
   // before it: start at the last such command.
   uint32_t first = 0;
@@ -2304,11 +2312,12 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
         const float uy = fyc * pt.m[1], vy = fyc * pt.m[4];
         const float m0 = pt.m[0], m2 = pt.m[2], m3 = pt.m[3], m5 = pt.m[5];
         const uint32_t tmode = pt.tile_mode;
-#pragma unroll 2
+#pragma unroll 1
         for (int j = 0; j < 8; j++) {
           uint32_t cv = ((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF;
           const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
           cv &= galpha;
+          uint32_t d = dst[0];
           if (cv || (touched && zmode)) {
             const float fxc = (x0 + j) + 0.5f;
             const float u = fxc * m0 + uy + m2;  // paint_color: fxc * m[0] + fyc * m[1] + m[2], same order
@@ -2316,9 +2325,10 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
             uint32_t src = swap_rb(sample_image_nearest(tmode, img, u, v, s_requant));
             if (cv != 255) src = alpha_mul_q(src, cv);
             if (cf) src = apply_color_filter(cf, src);
-            if (mode == SKB_BLEND_SRC_OVER) dst[j] = (src >> 24) == 0 ? dst[j] : src + alpha_mul_q(dst[j], 256 - (src >> 24));
-            else dst[j] = porter_duff(src, dst[j], mode);
+            if (mode == SKB_BLEND_SRC_OVER) d = (src >> 24) == 0 ? d : src + alpha_mul_q(d, 256 - (src >> 24));
+            else d = porter_duff(src, d, mode);
           }
+          SKB_ROTATE_DST(d);
         }
         continue;
       }
@@ -2361,12 +2371,15 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
         __syncwarp();
 #pragma unroll 1
         for (int j = 0; j < 8; j++) {
-          if (!((need >> j) & 1u)) continue;
-          const uint32_t cv = (((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF) & galpha;
-          uint32_t src = swap_rb(s_src[warp][lane * 8 + j]);
-          if (cv != 255) src = alpha_mul_q(src, cv);
-          if (cf) src = apply_color_filter(cf, src);
-          dst[j] = porter_duff(src, dst[j], mode);
+          uint32_t d = dst[0];
+          if ((need >> j) & 1u) {
+            const uint32_t cv = (((j < 4 ? lo : hi) >> (8 * (j & 3))) & 0xFF) & galpha;
+            uint32_t src = swap_rb(s_src[warp][lane * 8 + j]);
+            if (cv != 255) src = alpha_mul_q(src, cv);
+            if (cf) src = apply_color_filter(cf, src);
+            d = porter_duff(src, d, mode);
+          }
+          SKB_ROTATE_DST(d);
         }
         __syncwarp();   // the next command reuses the lists
         continue;
@@ -2377,13 +2390,15 @@ __global__ void FINE_BOUNDS k_fine(FineArgs a) {
         // a span reaches the pixel when its coverage is non-zero, or zero on a direct span (zmask)
         const bool touched = cv != 0 || (((j < 4 ? zlo : zhi) >> (8 * (j & 3))) & 0xFF) != 0;
         cv &= galpha;  // `cover & global_alpha_` (sw_span_brush.cc:101)
+        uint32_t d = dst[0];
         if (cv || (touched && zmode)) {
           // BrushH: colour, scaled by the coverage, colour filter, blend (sw_span_brush.cc:108-133)
           uint32_t src = swap_rb(paint_color(pt, a.stops, img, x0 + j, y, s_requant));
           if (cv != 255) src = alpha_mul_q(src, cv);
           if (cf) src = apply_color_filter(cf, src);
-          dst[j] = porter_duff(src, dst[j], mode);
+          d = porter_duff(src, d, mode);
         }
+        SKB_ROTATE_DST(d);
       }
     }
   }
