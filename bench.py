@@ -131,6 +131,28 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
+def bind_near_gpu(local_rank):
+    """Keeps this process (and the host buffers it touches first) on the NUMA node its GPU hangs off.  -> node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -142,6 +164,7 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_near_gpu(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -165,6 +188,21 @@ def run_ours(args):
     dl_pinned.copy_(torch.frombuffer(bytearray(dl), dtype=torch.uint8))
     del dl
     n_dl = dl_pinned.numel()
+    bands = multigpu.band_ranges(H, world) if partition == "bands" else None
+    banded = partition == "bands" and world > 1
+    cull_ms = None
+    n_dl_full = n_dl
+    if banded:
+        # the band's own display list (skb_display_list_cull_rows, host side, once per scene like the encode): a rank
+        # uploads and processes what can reach its rows, not N copies of everything
+        t_c = time.perf_counter()
+        y0b, y1b = bands[rank]
+        dl_band = torch.empty(device.cull_display_list_rows((dl_pinned.data_ptr(), n_dl), y0b, y1b, size_only=True),
+                              dtype=torch.uint8).pin_memory()
+        device.cull_display_list_rows((dl_pinned.data_ptr(), n_dl), y0b, y1b, out=(dl_band.data_ptr(), dl_band.numel()))
+        cull_ms = (time.perf_counter() - t_c) * 1e3
+        dl_pinned = dl_band
+        n_dl = dl_pinned.numel()
 
     dev = device.Device(local_rank)
     if args.coverage_mode == "area":
@@ -177,8 +215,6 @@ def run_ours(args):
         dev.create_surface = create_area_surface
     surf = dev.create_surface(surf_w, surf_h)
     stream = torch.cuda.ExternalStream(surf.stream(), device=torch.device("cuda", local_rank))
-    bands = multigpu.band_ranges(H, world) if partition == "bands" else None
-    banded = partition == "bands" and world > 1
     if banded:
         surf.set_band(*bands[rank])
 
@@ -287,32 +323,67 @@ def run_ours(args):
     barrier()
     ms_e2e_serial = (time.perf_counter() - t0) * 1e3 / args.steps
     ms_e2e = max(f0.elapsed_time(f1) / args.steps, 0.0)
+    ms_e2e_via_rank0 = None
+
+    # ---- banded (N > 1): the host does not need the frame on rank 0's GPU first.  Every rank copies the band it rendered
+    # from its own canvas into its rows of ONE host image in shared memory (multigpu.SharedHostImage, page-locked in every
+    # process): the canvas reaches the host over N PCIe links at once and sits, whole, in rank 0's address space.  The
+    # figures above (bands into rank 0's canvas over NVLink, rank 0 reads everything back) stay as `via_rank0_canvas`.
+    n_flight = 3
+    shared = None
+    shm_ok = [bool(banded and multigpu.SharedHostImage.room_for(n_flight * H * W * 4))]
+    if banded:
+        dist.broadcast_object_list(shm_ok, src=0)
+    band_e2e = banded and shm_ok[0]
+    if band_e2e:
+        ms_e2e_via_rank0 = ms_e2e_serial
+        surf.sync()
+        barrier()
+        surf.set_remote_canvas(None)          # from here on the band stays in this rank's own canvas
+        tag = os.environ.get("MASTER_PORT", "0")
+        shared = [multigpu.SharedHostImage(f"skb_bench_{tag}_{j}", (H, W, 4), rank, dist, register=True, my_rows=bands[rank]) for j in range(n_flight)]
+        y0b, y1b = bands[rank]
+        host_image_locked = all(sh.registered for sh in shared)
+
+        def step_e2e_band(sf, img, group=None):
+            sf.begin(True)
+            sf.encode((dl_pinned.data_ptr(), n_dl))
+            sf.flush()
+            if y1b > y0b:
+                sf.read_pixels_async(img.rows(y0b, y1b), 0, y0b)
+            sf.sync()
+            dist.barrier(group=group)         # every band of the frame is in the host image
+
+        step_e2e_band(surf, shared[0])
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e_band(surf, shared[0])
+        barrier()
+        ms_e2e_serial = (time.perf_counter() - t0) * 1e3 / args.steps
 
     # ---- the same with several frames in flight: every step still uploads its display list and reads its canvas back
     # to pinned host memory, but frames alternate between surfaces (each with its own stream, arenas and canvas), so
     # the upload, the host-side validation and the read-back of one frame overlap the rendering of the others — what an
     # application streaming frames does.  Three surfaces, one host thread each (measured on C4a at N = 1: 1 / 2 / 3
-    # frames in flight = 94 / 76 / 66 ms per frame against 60.6 ms of device time).  Banded (N > 1): a frame needs two
-    # host barriers across the ranks (bands complete; rank 0 has read the canvas), each thread on a gloo group of its own.
+    # frames in flight = 94 / 76 / 66 ms per frame against 60.6 ms of device time).  Banded (N > 1): a frame ends with a
+    # host barrier across the ranks (all its bands are in the host image), each thread on a gloo group of its own.
     ms_e2e_wall = ms_e2e_serial
-    pipelined = partition != "batch"
-    n_flight = 1
+    pipelined = partition != "batch" and (not banded or band_e2e)
+    if not pipelined:
+        n_flight = 1
     if pipelined:
-        n_flight = 3
         extra = [dev.create_surface(surf_w, surf_h) for _ in range(n_flight - 1)]
-        # banded: every surface's host thread has a gloo group of its own for the two host barriers of a frame
-        flight_groups = [dist.new_group(backend="gloo") for _ in range(n_flight)] if banded else None
+        flight_groups = [dist.new_group(backend="gloo") for _ in range(n_flight)] if band_e2e else None
         for sb in extra:
             if banded:
                 sb.set_band(*bands[rank])
-                sb.begin(True)
-                sb.sync()
-                barrier()
-                multigpu.fuse_gather_into_fine_pass(sb, rank, dist)
-                barrier()
         pair = [surf] + extra
-        outs = [out_np] + [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() if out_np is not None else None
-                           for _ in extra]
+        if band_e2e:
+            outs = [sh.array if rank == 0 else None for sh in shared]
+        else:
+            outs = [out_np] + [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory().numpy() if out_np is not None else None
+                               for _ in extra]
 
         def run_pipelined(n_steps):
             # one host thread per surface (the C ABI is thread-safe per surface): the threads take frames in turn, so
@@ -324,17 +395,15 @@ def run_ours(args):
                     torch.cuda.set_device(local_rank)
                     sf = pair[j]
                     for k in range(j, n_steps, n_flight):
+                        if band_e2e:
+                            step_e2e_band(sf, shared[j], flight_groups[j])
+                            continue
                         sf.begin(True)
                         sf.encode((dl_pinned.data_ptr(), n_dl))
                         sf.flush()
-                        if banded:
-                            sf.sync()
-                            dist.barrier(group=flight_groups[j])     # every band of frame k is in rank 0's canvas j
                         if outs[j] is not None:
                             sf.read_pixels_async(outs[j])
                         sf.sync()
-                        if banded:
-                            dist.barrier(group=flight_groups[j])     # rank 0 has its copy: canvas j may be overwritten
                 except Exception as e:  # noqa: BLE001
                     errors.append(e)
             ths = [threading.Thread(target=worker, args=(j,)) for j in range(n_flight)]
@@ -352,14 +421,19 @@ def run_ours(args):
         run_pipelined(n_e2e)
         barrier()
         ms_e2e_wall = (time.perf_counter() - t0) * 1e3 / n_e2e
-        if out_np is not None:
-            for o in outs[1:]:      # first rows (rank 0's band) and last rows (the last rank's band, stored over NVLink)
+        if outs[0] is not None:
+            for o in outs[1:]:      # first rows (rank 0's band) and last rows (the last rank's band)
                 if not (np.array_equal(outs[0][:64], o[:64]) and np.array_equal(outs[0][-64:], o[-64:])):
                     raise SystemExit("frames rendered on different surfaces differ")
-            if banded and int(outs[0][bands[-1][0]:bands[-1][0] + min(64, bands[-1][1] - bands[-1][0])].astype(np.uint64).sum()) != single_check:
+            if band_e2e and int(outs[0][bands[-1][0]:bands[-1][0] + min(64, bands[-1][1] - bands[-1][0])].astype(np.uint64).sum()) != single_check:
                 raise SystemExit("the last band read back end to end differs from the band gathered by NCCL")
         for sb in extra:
             sb.close()
+        if shared:
+            barrier()
+            outs = None
+            for sh in shared:
+                sh.close()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the complete plug-in path (what a skity::Canvas user pays): CudaContextCreate'd surface -> LockCanvas ->
@@ -373,10 +447,15 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             ms_canvas = f"failed: {e}"
 
+    h2d_total = int(n_dl) * world
     if world > 1:
-        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_wall, ms_e2e_serial], device="cuda")
+        t = torch.tensor([ms_resident, ms_e2e, ms_e2e_wall, ms_e2e_serial, ms_e2e_via_rank0 or 0.0, cull_ms or 0.0], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_resident, ms_e2e, ms_e2e_wall, ms_e2e_serial = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms_e2e_via_rank0, cull_ms = (float(t[4]) or None), (float(t[5]) or None)
+        tb = torch.tensor([int(n_dl)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        h2d_total = int(tb[0])
         ts = torch.tensor(stage_ms, device="cuda")
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
         stage_ms = ts.cpu().numpy()
@@ -410,16 +489,20 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": desc, "canvases_per_step": canvases, "paths_per_step": paths,
                        "l2": "working set per step (display list, edges, records, A8 masks, canvas) is several GB at N=1, far above the 126 MB L2; no explicit flush",
-                       "partition": {"bands": f"tile-row bands of one canvas over {world} GPU(s), display list replicated, culled per band on the device, "
+                       "partition": {"bands": f"tile-row bands of one canvas over {world} GPU(s); every rank holds the part of the display list that can reach "
+                                              "its band (skb_display_list_cull_rows on the host, once per scene; the device culls again before flattening); "
                                               "bands stored into rank 0's canvas by the fine pass (NVLink peer memory)" if world > 1 else "single GPU, whole canvas",
                                      "canvas": "one canvas per rank", "batch": "canvases dealt to ranks, one display list per rank"}[partition],
                        "coord_mode": "wide (canvas > 8192 px: the reference's 16.16 conversion without its int32 wrap)" if max(W, H) > 8192 else "reference",
                        "frames_in_flight": 1, "coverage_mode": args.coverage_mode},
             "paths_per_s": round(paths / (ms_resident / 1e3), 1),
-            "e2e": {"value": round(mpix / (ms_e2e_used / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": int(n_dl) * world,
+            "e2e": {"value": round(mpix / (ms_e2e_used / 1e3), 2), "unit": UNIT, "h2d_bytes_per_step": h2d_total,
                     "d2h_bytes_per_step": int(canvases * W * H * 4), "ms_per_step": round(ms_e2e_used, 4),
-                    "what": "C ABI with host buffers: display list H2D from pinned memory on every rank, frame, "
-                            + ("bands into rank 0's canvas over NVLink, barrier, " if banded else "") + "canvas D2H into pinned memory; "
+                    "what": "C ABI with host buffers: "
+                            + ("every rank uploads ITS band's display list from pinned memory (H2D), renders its band and copies it (D2H) into its rows of "
+                               "one page-locked host image in shared memory that rank 0 owns — N PCIe links at once, no gather; a host barrier ends the frame; "
+                               if band_e2e else ("display list H2D from pinned memory, frame, " + ("bands into rank 0's canvas over NVLink, barrier, " if banded else "")
+                                                 + "canvas D2H into pinned memory; "))
                             + ((f"{n_flight} frames in flight on {n_flight} surfaces, one host thread each (upload, validation and read-back of one frame overlap the rendering of the others)") if pipelined else "one frame at a time"),
                     "frames_in_flight": n_flight, "frames_timed": n_e2e if pipelined else args.steps,
                     "one_frame_at_a_time": {"value": round(mpix / (ms_e2e_serial / 1e3), 2), "ms_per_step": round(ms_e2e_serial, 4)}},
@@ -440,6 +523,15 @@ def run_ours(args):
         if banded:
             line["gather"] = {"fused_in_fine_pass": True, "nccl_send_recv_ms": round(nccl_gather_ms, 4),
                               "bytes_into_rank0": int((H - bands[0][1]) * W * 4)}
+            if ms_e2e_via_rank0:
+              line["e2e"]["via_rank0_canvas"] = {
+                "value": round(mpix / (ms_e2e_via_rank0 / 1e3), 2), "ms_per_step": round(ms_e2e_via_rank0, 4),
+                "what": "one frame at a time: bands stored into rank 0's canvas by the fine pass (NVLink), barrier, rank 0 reads the whole canvas back"}
+            if band_e2e:
+                line["e2e"]["host_image_page_locked_on_rank0"] = bool(host_image_locked)
+                line["e2e"]["rank0_bound_to_numa_node"] = numa_node
+            line["band_display_lists"] = {"bytes_all_ranks": h2d_total, "bytes_whole_list": int(n_dl_full),
+                                          "host_cull_ms_outside_timed_region": round(cull_ms or 0.0, 1)}
         if ms_canvas is not None:
             line["e2e_canvas"] = ({"value": round(mpix / (ms_canvas["total"] / 1e3), 2), "unit": UNIT, "ms_per_step": round(ms_canvas["total"], 3),
                                    "ms_canvas_calls_host_encode": round(ms_canvas["canvas_calls"], 3), "ms_flush": round(ms_canvas["flush"], 3),

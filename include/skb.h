@@ -129,6 +129,15 @@ SKB_API skb_result skb_frame_encode(skb_surface surface, const void* display_lis
  * kernels: every index is in range, sections are in order, every fill / clip op owns the next path and the paths tile
  * the segment table (include/skb_dl.h). */
 SKB_API skb_result skb_display_list_validate(const void* display_list, size_t bytes);
+/* Host-side band partition of a display list (no device needed): writes to `out` the part of `display_list` that can
+ * reach rows [row0, row1) of the canvas — the list a device rendering that band of the canvas (skb_surface_set_band)
+ * needs.  Only fills of the canvas whose path cannot reach the rows are dropped, by the same conservative test the
+ * device applies before flattening with a wider margin, so the band's pixels are identical to those rendered from the
+ * whole list; clip paths, blurs and draws into other surfaces all stay.  `out` null: only `*out_bytes` (the size
+ * needed) is set.  This is the multi-GPU counterpart of the reference handing one display list to one canvas
+ * (src/recorder/display_list.hpp:41-64, DisplayList::Draw): N devices, N culled lists, instead of N copies of it. */
+SKB_API skb_result skb_display_list_cull_rows(const void* display_list, size_t bytes, int32_t row0, int32_t row1, void* out,
+                                              size_t out_capacity, size_t* out_bytes);
 /* Launches every stage for the encoded frame.  Asynchronous unless the record pool overflows. */
 SKB_API skb_result skb_frame_flush(skb_surface surface);
 /* Blocks until the surface's stream is idle; returns the first asynchronous error. */

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -3967,6 +3968,143 @@ skb_result skb_frame_begin(skb_surface s, int clear) {
 skb_result skb_display_list_validate(const void* dl, size_t bytes) {
   if (!dl) return SKB_ERROR_INVALID_ARGUMENT;
   return validate_dl((const uint8_t*)dl, bytes);
+}
+
+// The part of a display list that can reach rows [row0, row1) of the canvas (surface 0): the list of one band of a
+// canvas split over several GPUs.  Dropped are fills of the canvas whose path cannot reach those rows — by the test
+// k_op_init applies on the device (control points' y range widened by half its height + 2 px), with one more pixel of
+// margin, so every op dropped here is one the device would have culled anyway and the band's pixels are the same as with
+// the whole list.  Everything else stays: clip paths, blurs, draws into other surfaces.  Paths, segments and paints of the
+// dropped ops go too; what is kept keeps its order.
+skb_result skb_display_list_cull_rows(const void* dl_v, size_t bytes, int32_t row0, int32_t row1, void* out_v, size_t out_capacity,
+                                      size_t* out_bytes) {
+  if (!dl_v || !out_bytes || row1 < row0) return SKB_ERROR_INVALID_ARGUMENT;
+  const uint8_t* dl = (const uint8_t*)dl_v;
+  skb_result vr = validate_dl(dl, bytes);
+  if (vr != SKB_SUCCESS) return vr;
+  skb_dl_header h;
+  memcpy(&h, dl, sizeof(h));
+  const skb_dl_surface* surfs = (const skb_dl_surface*)(dl + h.off_surfaces);
+  const skb_dl_op* ops = (const skb_dl_op*)(dl + h.off_ops);
+  const skb_dl_path* paths = (const skb_dl_path*)(dl + h.off_paths);
+  const skb_dl_seg* segs = (const skb_dl_seg*)(dl + h.off_segs);
+  const skb_dl_paint* paints = (const skb_dl_paint*)(dl + h.off_paints);
+  auto align16 = [](uint64_t v) { return (v + 15) & ~(uint64_t)15; };
+  const uint64_t tail_old = align16((uint64_t)h.off_stops + (uint64_t)h.n_stop_floats * 4);   // image pixels, if any
+  for (uint32_t i = 0; i < h.n_surfaces; i++)
+    if ((surfs[i].flags & SKB_SURFACE_IMAGE) && surfs[i].reserved < tail_old) {
+      set_error("display list: image pixels before the end of the stop pool (not a layout this function rewrites)");
+      return SKB_ERROR_UNSUPPORTED;
+    }
+  const bool canvas0 = !(surfs[0].flags & SKB_SURFACE_IMAGE);
+  std::vector<uint8_t> keep(h.n_ops, 1);
+  std::vector<uint32_t> paint_map(h.n_paints, 0xFFFFFFFFu);
+  uint64_t n_ops = 0, n_paths = 0, n_segs = 0, n_paints = 0;
+  const int n_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  {
+    auto classify = [&](uint32_t a, uint32_t b) {
+      for (uint32_t i = a; i < b; i++) {
+        const skb_dl_op& o = ops[i];
+        if (o.kind != SKB_OP_FILL || o.surface != 0 || !canvas0) continue;
+        const skb_dl_path& p = paths[o.path];
+        if (p.n_segs == 0) continue;
+        float ymin = 3.0e38f, ymax = -3.0e38f;
+        bool all_finite = true;
+        for (uint32_t k = 0; k < p.n_segs; k++) {
+          const uint32_t si = p.seg_off + k;
+          const skb_dl_seg& sg = segs[si];
+          const uint32_t type = sg.type_flags & SKB_SEG_TYPE_MASK;
+          int last = 0;
+          if (type == SKB_SEG_LINE || type == SKB_SEG_CLOSE) last = 1;
+          else if (type == SKB_SEG_QUAD || type == SKB_SEG_CONIC) last = 2;
+          else if (type == SKB_SEG_CUBIC) last = 3;
+          const V2 st = xform(o.ctm, seg_start_point(segs, si));
+          all_finite &= std::isfinite(st.y);
+          ymin = std::min(ymin, st.y); ymax = std::max(ymax, st.y);
+          for (int c = 1; c <= last; c++) {
+            const V2 q = xform(o.ctm, v2(sg.p[2 * c], sg.p[2 * c + 1]));
+            all_finite &= std::isfinite(q.y);
+            ymin = std::min(ymin, q.y); ymax = std::max(ymax, q.y);
+          }
+        }
+        if (!all_finite) continue;
+        const float pad = 0.5f * (ymax - ymin) + 3.0f;
+        if (ymax + pad < (float)row0 || ymin - pad > (float)row1) keep[i] = 0;
+      }
+    };
+    std::vector<std::thread> th;
+    const uint32_t per = (h.n_ops + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+      const uint32_t a = std::min(h.n_ops, (uint32_t)t * per), b = std::min(h.n_ops, a + per);
+      if (a < b) th.emplace_back(classify, a, b);
+    }
+    for (auto& t : th) t.join();
+  }
+  for (uint32_t i = 0; i < h.n_ops; i++) {
+    if (!keep[i]) continue;
+    const skb_dl_op& o = ops[i];
+    n_ops++;
+    if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+      n_paths++;
+      n_segs += paths[o.path].n_segs;
+    }
+    if (o.kind == SKB_OP_FILL && paint_map[o.paint] == 0xFFFFFFFFu) paint_map[o.paint] = (uint32_t)n_paints++;
+  }
+  skb_dl_header nh = h;
+  nh.n_ops = (uint32_t)n_ops;
+  nh.n_paths = (uint32_t)n_paths;
+  nh.n_segs = (uint32_t)n_segs;
+  nh.n_paints = (uint32_t)n_paints;
+  uint64_t off = align16(sizeof(skb_dl_header));
+  nh.off_surfaces = (uint32_t)off; off = align16(off + (uint64_t)h.n_surfaces * sizeof(skb_dl_surface));
+  nh.off_ops = (uint32_t)off;      off = align16(off + n_ops * sizeof(skb_dl_op));
+  nh.off_paths = (uint32_t)off;    off = align16(off + n_paths * sizeof(skb_dl_path));
+  nh.off_segs = (uint32_t)off;     off = align16(off + n_segs * sizeof(skb_dl_seg));
+  nh.off_paints = (uint32_t)off;   off = align16(off + n_paints * sizeof(skb_dl_paint));
+  nh.off_stops = (uint32_t)off;    off = align16(off + (uint64_t)h.n_stop_floats * 4);
+  const uint64_t tail_new = off;
+  const uint64_t tail_bytes = h.total_bytes > tail_old ? h.total_bytes - tail_old : 0;
+  off += tail_bytes;
+  nh.total_bytes = (uint32_t)off;
+  *out_bytes = (size_t)off;
+  if (!out_v) return SKB_SUCCESS;   // size query
+  if (out_capacity < off) {
+    set_error("skb_display_list_cull_rows: output buffer too small");
+    return SKB_ERROR_INVALID_ARGUMENT;
+  }
+  uint8_t* out = (uint8_t*)out_v;
+  memset(out, 0, nh.off_ops);
+  memcpy(out, &nh, sizeof(nh));
+  skb_dl_surface* nsurfs = (skb_dl_surface*)(out + nh.off_surfaces);
+  memcpy(nsurfs, surfs, (size_t)h.n_surfaces * sizeof(skb_dl_surface));
+  for (uint32_t i = 0; i < h.n_surfaces; i++)
+    if (nsurfs[i].flags & SKB_SURFACE_IMAGE) nsurfs[i].reserved = (uint32_t)(nsurfs[i].reserved - tail_old + tail_new);
+  skb_dl_op* nops = (skb_dl_op*)(out + nh.off_ops);
+  skb_dl_path* npaths = (skb_dl_path*)(out + nh.off_paths);
+  skb_dl_seg* nsegs = (skb_dl_seg*)(out + nh.off_segs);
+  skb_dl_paint* npaints = (skb_dl_paint*)(out + nh.off_paints);
+  uint32_t wo = 0, wp = 0, ws = 0;
+  for (uint32_t i = 0; i < h.n_ops; i++) {
+    if (!keep[i]) continue;
+    skb_dl_op o = ops[i];
+    if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+      const skb_dl_path& p = paths[o.path];
+      skb_dl_path np = p;
+      np.seg_off = ws;
+      memcpy(nsegs + ws, segs + p.seg_off, (size_t)p.n_segs * sizeof(skb_dl_seg));
+      ws += p.n_segs;
+      npaths[wp] = np;
+      o.path = wp++;
+    }
+    if (o.kind == SKB_OP_FILL) {
+      npaints[paint_map[o.paint]] = paints[o.paint];
+      o.paint = paint_map[o.paint];
+    }
+    nops[wo++] = o;
+  }
+  memcpy(out + nh.off_stops, dl + h.off_stops, (size_t)h.n_stop_floats * 4);
+  if (tail_bytes) memcpy(out + tail_new, dl + tail_old, (size_t)tail_bytes);
+  return SKB_SUCCESS;
 }
 
 skb_result skb_frame_encode(skb_surface s, const void* dl, size_t bytes) {

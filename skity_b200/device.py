@@ -64,6 +64,7 @@ def lib():
         L.skb_frame_encode.argtypes = [vp, vp, sz]
         L.skb_frame_flush.argtypes = [vp]
         L.skb_display_list_validate.argtypes = [vp, sz]
+        L.skb_display_list_cull_rows.argtypes = [vp, sz, i32, i32, vp, sz, ctypes.POINTER(sz)]
         L.skb_surface_sync.argtypes = [vp]
         L.skb_surface_read_pixels.argtypes = [vp, u32, u32, u32, u32, vp, sz]
         L.skb_surface_read_pixels_async.argtypes = [vp, u32, u32, u32, u32, vp, sz]
@@ -236,3 +237,29 @@ def validate_display_list(dl):
     rc = lib().skb_display_list_validate(buf, len(buf))
     if rc != 0:
         raise SkbError(f"skb_display_list_validate failed ({rc}): {lib().skb_get_last_error_string().decode(errors='replace')}")
+
+
+def cull_display_list_rows(dl, row0, row1, out=None, size_only=False):
+    """skb_display_list_cull_rows: the part of display list `dl` (bytes, or a (pointer, size) pair) that can reach canvas
+    rows [row0, row1).  Returns bytes — or, with `out` = (pointer, capacity), the number of bytes written there; with
+    `size_only` just the size the result needs."""
+    if isinstance(dl, tuple):
+        src, n = ctypes.c_void_p(dl[0]), dl[1]
+    else:
+        buf = bytes(dl)
+        src, n = buf, len(buf)
+    need = ctypes.c_size_t(0)
+    L = lib()
+
+    def check(rc):
+        if rc != 0:
+            raise SkbError(f"skb_display_list_cull_rows failed ({rc}): {L.skb_get_last_error_string().decode(errors='replace')}")
+    if out is not None:
+        check(L.skb_display_list_cull_rows(src, n, int(row0), int(row1), ctypes.c_void_p(out[0]), out[1], ctypes.byref(need)))
+        return need.value
+    check(L.skb_display_list_cull_rows(src, n, int(row0), int(row1), None, 0, ctypes.byref(need)))
+    if size_only:
+        return need.value
+    res = ctypes.create_string_buffer(need.value)
+    check(L.skb_display_list_cull_rows(src, n, int(row0), int(row1), res, need.value, ctypes.byref(need)))
+    return res.raw[:need.value]

@@ -86,3 +86,72 @@ def fuse_gather_into_fine_pass(surface, rank, dist, root=0):
     dist.broadcast_object_list(box, src=root)
     if rank != root:
         surface.set_remote_canvas(box[0])
+
+
+class SharedHostImage:
+    """A host image (H, W, 4 uint8) in POSIX shared memory that every rank of one node maps: each rank copies the band
+    it rendered straight from its own GPU into its rows (skb_surface_read_pixels_async), so a canvas split over N GPUs
+    reaches the host over N PCIe links at once instead of through rank 0's alone — and the whole frame sits in rank
+    0's address space.  With `register` the mapping is page-locked for CUDA (cudaHostRegister), which is what makes
+    the copies asynchronous and full speed.  Collective: every rank constructs it with the same name."""
+
+    def __init__(self, name, shape, rank, dist=None, register=False, my_rows=None):
+        import mmap
+        import os
+        self.shape = tuple(int(v) for v in shape)
+        self.nbytes = int(np.prod(self.shape))
+        self.path = os.path.join("/dev/shm", name)
+        self.owner = rank == 0
+        self._registered = False
+        if self.owner:
+            fd = os.open(self.path, os.O_CREAT | os.O_RDWR | os.O_TRUNC, 0o600)
+            os.ftruncate(fd, self.nbytes)
+        if dist is not None:
+            dist.barrier()
+        if not self.owner:
+            fd = os.open(self.path, os.O_RDWR)
+        self._mm = mmap.mmap(fd, self.nbytes)
+        os.close(fd)
+        self.array = np.frombuffer(self._mm, dtype=np.uint8).reshape(self.shape)
+        # first touch decides which NUMA node a page lives on: every rank touches the rows it will fill (my_rows), so the
+        # DMA writes of a GPU land in memory near the process that drives it instead of all on rank 0's node
+        if my_rows is not None:
+            self.array[my_rows[0]:my_rows[1]] = 0
+        if dist is not None:
+            dist.barrier()
+        if self.owner and my_rows is None:
+            self.array[...] = 0          # touch every page once
+        if dist is not None:
+            dist.barrier()
+        if self.owner:
+            os.unlink(self.path)         # the mappings keep it alive
+        if register:
+            import torch
+            rc = torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.nbytes, 0)
+            self._registered = int(rc) == 0     # not page-locked: the copies still work, staged by the library
+
+    @property
+    def registered(self):
+        return self._registered
+
+    @staticmethod
+    def room_for(nbytes):
+        import shutil
+        try:
+            return shutil.disk_usage("/dev/shm").free > nbytes + (256 << 20)
+        except OSError:
+            return False
+
+    def rows(self, y0, y1):
+        return self.array[y0:y1]
+
+    def close(self):
+        if self._registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self._registered = False
+        self.array = None
+        try:
+            self._mm.close()
+        except BufferError:
+            pass

@@ -396,6 +396,32 @@ def test_large_canvas_band_split_and_determinism(dev):
     assert np.array_equal(got, whole)
 
 
+def test_band_rendered_from_its_culled_display_list(dev):
+    """skb_display_list_cull_rows + skb_surface_set_band: every band rendered from ITS part of the display list equals
+    the band of the frame rendered whole — fills, nested clips (kept whole), blurred draws."""
+    from skity_b200 import device, multigpu
+    for s in (scene.scene_random_fills_fast(3000, 2048, 11, 160.0), scene.scene_c2(300, 1024, 3, clip_every=25, clip_box=400.0),
+              scene.scene_c3(24, 1024, 5)):
+        dl = hostlib.encode_scene(s.encode())
+        surf = dev.create_surface(s.width, s.height)
+        try:
+            whole = surf.render(dl)
+            sizes = []
+            for (y0, y1) in multigpu.band_ranges(s.height, 4):
+                part = device.cull_display_list_rows(dl, y0, y1)
+                sizes.append(len(part))
+                surf.set_band(y0, y1)
+                surf.begin(True)
+                surf.encode(part)
+                surf.flush()
+                assert np.array_equal(surf.read_pixels(0, y0, s.width, y1 - y0), whole[y0:y1])
+            assert max(sizes) <= len(dl)
+            if s.n_draws >= 3000:                 # plain fills: a quarter of the canvas sees a fraction of them
+                assert max(sizes) < len(dl) // 2
+        finally:
+            surf.close()
+
+
 def test_two_surfaces_in_flight_with_async_read_back(dev):
     """skb_surface_read_pixels_async: frames alternate between two surfaces without waiting for the
     read-back (what bench.py's end-to-end loop does); every frame must equal the synchronous result."""

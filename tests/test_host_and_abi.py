@@ -194,3 +194,53 @@ def test_golden_harness_env_compiles_against_the_reference_headers(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-DSKITY_CPU", f"-I{tmp_path}", f"-I{ref}", f"-I{ref}/include",
                         f"-I{ref}/test/golden", f"-I{ROOT}/third_party/glm_shim", f"-I{ROOT}", src], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def _dl_header(dl):
+    return np.frombuffer(dl[:80], dtype=np.uint32)
+
+
+@pytest.mark.parametrize("fixture", ["c1_fills_120_512", "c2_clips_90_512", "c0_star_blur_800x600", "images_512", "layers_512"])
+def test_display_list_culled_to_a_band_renders_the_same_band(fixture):
+    """skb_display_list_cull_rows (host-side band partition for a canvas split over several GPUs): the culled list is a
+    valid display list, drops fills only, and — rendered by the oracle port — gives the whole list's pixels on its rows."""
+    from skity_b200 import device
+    from oracle import port
+    z = np.load(os.path.join(ROOT, "tests", "golden", fixture + ".npz"))
+    dl = z["dl"].tobytes()
+    want = port.render(dl)
+    H = want.shape[0]
+    n_ops = int(_dl_header(dl)[5])
+    kept = []
+    for (y0, y1) in [(0, 64), (H // 2 - 32, H // 2 + 32), (H - 48, H)]:
+        part = device.cull_display_list_rows(dl, y0, y1)
+        device.validate_display_list(part)
+        hp = _dl_header(part)
+        assert hp[5] <= n_ops and hp[2] == len(part)
+        kept.append(int(hp[5]))
+        got = port.render(part)
+        assert np.array_equal(got[y0:y1], want[y0:y1]), (fixture, y0, y1)
+    whole = device.cull_display_list_rows(dl, 0, H)
+    device.validate_display_list(whole)
+    assert np.array_equal(port.render(whole), want)
+    if fixture == "c1_fills_120_512":
+        assert min(kept) < n_ops // 2          # random fills: a 64-row band sees a fraction of them
+
+
+def test_display_list_cull_drops_paths_segments_and_paints_of_dropped_fills():
+    from skity_b200 import device
+    s = scene.scene_random_fills(400, 1024, 5, box=96.0)
+    dl = hostlib.encode_scene(s.encode())
+    h = _dl_header(dl)
+    part = device.cull_display_list_rows(dl, 256, 512)
+    hp = _dl_header(part)
+    # ops, paths, segments and paints all shrink; every kept fill's path is the next path, paths tile the segments (validated)
+    assert 0 < hp[5] < h[5] and hp[6] < h[6] and hp[7] < h[7] and hp[8] <= h[8] and len(part) < len(dl) // 2
+    device.validate_display_list(part)
+    # a size query without an output buffer, and an undersized buffer
+    import ctypes
+    need = ctypes.c_size_t(0)
+    L = device.lib()
+    assert L.skb_display_list_cull_rows(dl, len(dl), 256, 512, None, 0, ctypes.byref(need)) == 0 and need.value == len(part)
+    small = ctypes.create_string_buffer(64)
+    assert L.skb_display_list_cull_rows(dl, len(dl), 256, 512, small, 64, ctypes.byref(need)) != 0

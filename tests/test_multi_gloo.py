@@ -59,3 +59,37 @@ def test_two_rank_band_gather_reassembles_frame(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), dl, 150, 200, out), nprocs=2, join=True)
     got = np.load(out)
     assert np.array_equal(got, want)
+
+
+def _worker_shared(rank, world, port_no, dl, h, w, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from skity_b200 import device
+    y0, y1 = multigpu.band_ranges(h, world)[rank]
+    # every rank gets ITS part of the display list (skb_display_list_cull_rows), renders it (the CPU port stands in for
+    # the device) and puts its band into the host image all ranks share; no gather at all
+    part = device.cull_display_list_rows(dl, y0, y1)
+    shared = multigpu.SharedHostImage(f"skb_test_{port_no}", (h, w, 4), rank, dist)
+    shared.rows(y0, y1)[...] = port.render(part)[y0:y1]
+    dist.barrier()
+    if rank == 0:
+        np.save(out_path, np.array(shared.array))
+        np.save(out_path + ".sizes.npy", np.array([len(part), len(dl)]))
+    dist.barrier()
+    shared.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not os.path.exists(hostlib.LIB_PATH), reason="host plug-in not built")
+def test_two_rank_culled_lists_and_shared_host_image(tmp_path):
+    """The end-to-end multi-GPU path of bench.py on CPU: per-band display lists, every rank writes its band into one
+    shared host image (multigpu.SharedHostImage), rank 0 sees the whole frame."""
+    s = scene.scene_random_fills(60, 0, 78, box=90.0, width=240, height=320)
+    dl = hostlib.encode_scene(s.encode())
+    want = port.render(dl)
+    out = str(tmp_path / "shared.npy")
+    mp.spawn(_worker_shared, args=(2, _free_port(), dl, 320, 240, out), nprocs=2, join=True)
+    assert np.array_equal(np.load(out), want)
+    part_bytes, all_bytes = np.load(out + ".sizes.npy")
+    assert part_bytes < all_bytes
