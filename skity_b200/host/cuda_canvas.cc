@@ -304,13 +304,18 @@ void CudaCanvas::EmitFill(const Path& path, const Matrix& m, uint32_t paint_inde
   std::vector<skb_dl_seg> segs;
   LowerPathToSegs(path, &segs);
   if (segs.empty()) return;
+  EmitFillOp(builder_->AddPath(segs), path.GetFillType(), m, paint_index);
+}
+
+// The fill op of a path that is already in the builder (possibly still being worked out: AddDeferredPath).
+void CudaCanvas::EmitFillOp(uint32_t path_index, Path::PathFillType fill_type, const Matrix& m, uint32_t paint_index) {
   skb_dl_op o{};
   o.kind = SKB_OP_FILL;
   o.surface = surface_;
-  o.path = builder_->AddPath(segs);
+  o.path = path_index;
   o.paint = paint_index;
   o.clip_in = state_stack_.back().clip_id;
-  o.fill_type = path.GetFillType() == Path::PathFillType::kEvenOdd ? 1u : 0u;
+  o.fill_type = fill_type == Path::PathFillType::kEvenOdd ? 1u : 0u;
   o.ctm[0] = m.GetScaleX();
   o.ctm[1] = m.GetSkewX();
   o.ctm[2] = m.GetTranslateX();
@@ -609,19 +614,31 @@ void CudaCanvas::OnDrawPath(const Path& path, const Paint& paint) {
       FillPath(path, paint, false);
     }
   };
+  // The outline (the reference's own Stroke, sw_canvas.cc:388-401) is worked out on one of the display-list builder's
+  // threads from copies of the path and the paint; the fill op that draws it takes its place in the list right away.
   auto draw_stroke = [&]() {
-    Stroke stroke(paint);
-    Path temp;
-    Path quad;
-    Path outline;
-    if (paint.GetPathEffect() && paint.GetPathEffect()->FilterPath(&temp, path, true, paint)) {
-      stroke.QuadPath(temp, &quad);
-      stroke.StrokePath(quad, &outline);
-    } else {
-      stroke.QuadPath(path, &quad);
-      stroke.StrokePath(quad, &outline);
+    if (surface_ == kNoSurface) return;
+    const Matrix m = CurrentTransform();
+    if (m.HasPersp()) {
+      NoteUnsupported("perspective CTM");
+      return;
     }
-    FillPath(outline, paint, true);
+    const uint32_t paint_index = MakeBrush(paint, true);
+    const uint32_t path_index = builder_->AddDeferredPath([path, paint](std::vector<skb_dl_seg>* out) {
+      Stroke stroke(paint);
+      Path temp;
+      Path quad;
+      Path outline;
+      if (paint.GetPathEffect() && paint.GetPathEffect()->FilterPath(&temp, path, true, paint)) {
+        stroke.QuadPath(temp, &quad);
+        stroke.StrokePath(quad, &outline);
+      } else {
+        stroke.QuadPath(path, &quad);
+        stroke.StrokePath(quad, &outline);
+      }
+      LowerPathToSegs(outline, out);
+    });
+    EmitFillOp(path_index, Path::PathFillType::kWinding, m, paint_index);
   };
   // DrawFillStrokeInPaintOrder (src/render/paint_order.hpp:12-31)
   if (paint.GetStyle() == Paint::kStrokeThenFill_Style) {

@@ -77,6 +77,7 @@ class CudaCanvas : public Canvas {
   Rect ScanClipBounds() const;
   void FillPath(const Path& path, const Paint& paint, bool stroke);
   void EmitFill(const Path& path, const Matrix& ctm, uint32_t paint_index);
+  void EmitFillOp(uint32_t path_index, Path::PathFillType fill_type, const Matrix& ctm, uint32_t paint_index);
   uint32_t MakeBrush(const Paint& paint, bool stroke);
   uint32_t EncodeColorFilter(const Paint& paint);
   void HandleFilter(const Path& path, const Paint& paint);

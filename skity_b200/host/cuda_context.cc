@@ -49,6 +49,7 @@ class CudaGPUSurface : public GPUSurface {
     // The frame's display list is laid out straight into a page-locked buffer the surface keeps (grown geometrically):
     // the upload is then one asynchronous copy at PCIe speed.  skb_frame_flush returns after the device has consumed
     // the list's tables, so the buffer is free again when the next frame is flushed.
+    builder_.Finish();   // the stroke outlines still being worked out on the builder's threads
     const skb::DlBuilder::Layout layout = builder_.MakeLayout();
     const size_t need = layout.h.total_bytes;
     if (need > dl_cap_) {

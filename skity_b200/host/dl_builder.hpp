@@ -8,9 +8,14 @@
 #define SKITY_B200_HOST_DL_BUILDER_HPP
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -21,8 +26,13 @@ namespace skb {
 class DlBuilder {
  public:
   DlBuilder() = default;
+  DlBuilder(const DlBuilder&) = delete;
+  DlBuilder& operator=(const DlBuilder&) = delete;
+  ~DlBuilder() { StopWorkers(); }
 
   void Reset(uint32_t canvas_w, uint32_t canvas_h) {
+    WaitForJobs();
+    deferred_.clear();
     surfaces_.clear();
     images_.clear();
     ops_.clear();
@@ -90,6 +100,80 @@ class DlBuilder {
     segs_.insert(segs_.end(), segs.begin(), segs.end());
     paths_.push_back(p);
     return static_cast<uint32_t>(paths_.size() - 1);
+  }
+
+  // A path whose segments are worked out later, by `job`, on one of the builder's worker threads: the outline of a
+  // stroke (Stroke::StrokePath is by far the most expensive thing a Canvas call does on the host, and one draw's
+  // outline does not depend on another's).  The op that owns the path is added right away, so draw order is kept;
+  // Finish() waits for the jobs and drops the ops whose path came out empty — what the immediate route does by not
+  // adding them in the first place.  `job` must own copies of everything it reads.
+  using SegJob = std::function<void(std::vector<skb_dl_seg>*)>;
+  uint32_t AddDeferredPath(SegJob job) {
+    deferred_.emplace_back();
+    std::vector<skb_dl_seg>* out = &deferred_.back();   // a deque: the address stays valid while more are added
+    skb_dl_path p{};
+    p.seg_off = static_cast<uint32_t>(segs_.size());
+    p.n_segs = 0;
+    p.reserved[0] = static_cast<uint32_t>(deferred_.size());   // 1 + index into deferred_
+    paths_.push_back(p);
+    static const unsigned want = [] {   // SKB_HOST_THREADS=1: outlines worked out by the calling thread
+      const char* e = std::getenv("SKB_HOST_THREADS");
+      const unsigned n = e ? static_cast<unsigned>(std::atoi(e)) : std::thread::hardware_concurrency();
+      return std::max(1u, std::min(16u, n));
+    }();
+    if (want <= 1) {
+      job(out);
+    } else {
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (workers_.empty())
+          for (unsigned t = 0; t < want; t++) workers_.emplace_back([this] { WorkerLoop(); });
+        jobs_.emplace_back([job = std::move(job), out] { job(out); });
+        pending_++;
+      }
+      cv_work_.notify_one();
+    }
+    return static_cast<uint32_t>(paths_.size() - 1);
+  }
+
+  // Waits for the deferred paths and folds them into the flat tables (every fill / clip op owns the next path, the
+  // paths tile the segment table).  Must be called before MakeLayout / Serialize when AddDeferredPath was used; cheap
+  // otherwise.
+  void Finish() {
+    WaitForJobs();
+    if (deferred_.empty()) return;
+    std::vector<skb_dl_op> ops;
+    std::vector<skb_dl_path> paths;
+    std::vector<skb_dl_seg> segs;
+    ops.reserve(ops_.size());
+    paths.reserve(paths_.size());
+    size_t total = segs_.size();
+    for (const auto& d : deferred_) total += d.size();
+    segs.reserve(total);
+    for (skb_dl_op o : ops_) {
+      if (o.kind == SKB_OP_FILL || o.kind == SKB_OP_CLIP) {
+        const skb_dl_path& p = paths_[o.path];
+        const skb_dl_seg* src = segs_.data() + p.seg_off;
+        size_t n = p.n_segs;
+        if (p.reserved[0]) {
+          const std::vector<skb_dl_seg>& d = deferred_[p.reserved[0] - 1];
+          if (d.empty()) continue;   // nothing to fill: the op is not part of the list
+          src = d.data();
+          n = d.size();
+        }
+        skb_dl_path np{};
+        np.seg_off = static_cast<uint32_t>(segs.size());
+        np.n_segs = static_cast<uint32_t>(n);
+        segs.insert(segs.end(), src, src + n);
+        o.path = static_cast<uint32_t>(paths.size());
+        paths.push_back(np);
+      }
+      ops.push_back(o);
+    }
+    ops_.swap(ops);
+    paths_.swap(paths);
+    segs_.swap(segs);
+    deferred_.clear();
   }
 
   uint32_t AddPaint(const skb_dl_paint& p) {
@@ -209,7 +293,8 @@ class DlBuilder {
     for (auto& t : th) t.join();
   }
 
-  std::vector<uint8_t> Serialize() const {
+  std::vector<uint8_t> Serialize() {
+    Finish();
     const Layout L = MakeLayout();
     std::vector<uint8_t> out(L.h.total_bytes);
     SerializeInto(L, out.data());
@@ -232,6 +317,47 @@ class DlBuilder {
   std::vector<skb_dl_paint> paints_;
   std::vector<float> stops_;
   uint32_t n_clip_states_ = 0;
+
+  // deferred paths and the threads that work them out
+  void WorkerLoop() {
+    for (;;) {
+      std::function<void()> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_work_.wait(lk, [this] { return stop_ || !jobs_.empty(); });
+        if (jobs_.empty()) return;   // stop_
+        job = std::move(jobs_.front());
+        jobs_.pop_front();
+      }
+      job();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      cv_done_.notify_all();
+    }
+  }
+  void WaitForJobs() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [this] { return pending_ == 0; });
+  }
+  void StopWorkers() {
+    WaitForJobs();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : workers_) t.join();
+    workers_.clear();
+  }
+  std::deque<std::vector<skb_dl_seg>> deferred_;
+  std::deque<std::function<void()>> jobs_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  size_t pending_ = 0;
+  bool stop_ = false;
 };
 
 }  // namespace skb

@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT"
+for v in both fdiv; do
+echo "== $v"
+SKB_LIB=gpurun_variants/$v.so timeout 300 python tests/perf_probe.py c1 c2clip c4a 2>&1 | tail -n 3 | cut -c1-200
+done > gpurun_out/s25_variants.log 2>&1
+cat gpurun_out/s25_variants.log
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/s25_tests.log 2>&1
+tail -n 3 gpurun_out/s25_tests.log
