@@ -73,8 +73,12 @@ SKB_HD fx fx_div(fx n, fx d) {
 #endif
   if (r < 0.0) q -= 1.0;
   else if (r >= b) q += 1.0;
+#if defined(__CUDA_ARCH__)
+  const int32_t qi = __double2int_rz(q);   // cvt.rzi.s32.f64 saturates: a quotient of 2^31 or more gives 0x7FFFFFFF
+#else
   q = q < 2147483647.0 ? q : 2147483647.0;
   const int32_t qi = (int32_t)q;
+#endif
   return neg ? -qi : qi;
 #else
   return fx_div_int(n, d);
