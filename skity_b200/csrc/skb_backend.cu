@@ -234,28 +234,20 @@ __global__ void k_seg_count(FrameTables t, uint32_t* prim_cnt, const uint32_t* s
   prim_cnt[s] = (g.culled || g.area) ? 0u : (uint32_t)seg_prim_count(t.segs[s]);
 }
 
-// One thread per lowered primitive: resolve (segment, k) from the scanned counts, evaluate and
-// transform its control points, fold them into the path bounds, emit its 0..2 edges.
+// One thread per segment, looping over the primitives it lowers to (a line / quad gives one, a conic two, a cubic a
+// handful — their first index is the segment's entry in the scanned counts): evaluate and transform the control points,
+// fold them into the path bounds, emit each primitive's 0..2 edges.  (One thread per primitive had to find its segment by
+// a binary search over the scanned counts — 23 dependent loads at 6M segments; C4a flatten stage 2.1 -> see DESIGN.)
 __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_prims, const uint32_t* seg_op, OpGeom* geom,
                           Edge* edges, QuadState* quads, uint32_t* chord_cap, uint32_t* slot_op) {
-  uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
-  if (prim >= n_prims) return;
-  uint32_t seg = find_interval(prim_off, t.n_segs, prim);
-  int k = (int)(prim - prim_off[seg]);
-  int n = (int)(prim_off[seg + 1] - prim_off[seg]);
-  uint32_t op = seg_op[seg];
+  const uint32_t seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= t.n_segs) return;
+  const uint32_t p0 = prim_off[seg];
+  const int n = (int)(prim_off[seg + 1] - p0);
+  if (n <= 0) return;
+  const uint32_t op = seg_op[seg];
   const float* ctm = t.ops[op].ctm;
-  V2 p[3];
-  int np = seg_prim(t.segs, seg, k, n, ctm, p);
   OpGeom* g = &geom[op];
-  for (int j = 0; j < np; j++) {
-    int32_t kx = float_key(p[j].x), ky = float_key(p[j].y);
-    atomicMin(&g->bmin_x, kx); atomicMax(&g->bmax_x, kx);
-    atomicMin(&g->bmin_y, ky); atomicMax(&g->bmax_y, ky);
-  }
-  Edge slot[2];
-  QuadState qslot[2];
-  flatten_prim(np, p, slot, qslot, (int)t.wide);
   // Each path owns one contiguous region of 64 bytes per slot: its Edge array followed by its
   // QuadState array, so the sweep's working set per path stays within a few cache lines.
   const skb_dl_path pa = t.paths[t.ops[op].path];
@@ -265,20 +257,38 @@ __global__ void k_flatten(FrameTables t, const uint32_t* prim_off, uint32_t n_pr
   uint8_t* region = reinterpret_cast<uint8_t*>(edges) + slot_base * (sizeof(Edge) + sizeof(QuadState));
   Edge* E = reinterpret_cast<Edge*>(region);
   QuadState* Q = reinterpret_cast<QuadState*>(region + (size_t)n_slots * sizeof(Edge));
-  const uint32_t at = 2 + 2 * (prim - first_prim);
-  E[at] = slot[0];
-  E[at + 1] = slot[1];
-  if ((slot[0].curve >> 25) & 1) Q[at] = qslot[0];
-  if ((slot[1].curve >> 25) & 1) Q[at + 1] = qslot[1];
-  if (chord_cap) {
-    // row-parallel walk (skb_rowwalk.cuh): an upper bound of the chords each edge can give — a line is one, a
-    // quadratic its first chord plus one per remaining subdivision — and the op that owns the slot
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const bool valid = (slot[j].curve >> 24) & 1, quad = (slot[j].curve >> 25) & 1;
-      chord_cap[slot_base + at + j] = valid ? (quad ? 1u + (uint32_t)edge_count(slot[j]) : 1u) : 0u;
-      slot_op[slot_base + at + j] = op;
+  int32_t bx0 = INT_MAX, bx1 = INT_MIN, by0 = INT_MAX, by1 = INT_MIN;
+  for (int k = 0; k < n; k++) {
+    const uint32_t prim = p0 + (uint32_t)k;
+    V2 p[3];
+    int np = seg_prim(t.segs, seg, k, n, ctm, p);
+    for (int j = 0; j < np; j++) {
+      int32_t kx = float_key(p[j].x), ky = float_key(p[j].y);
+      bx0 = min(bx0, kx); bx1 = max(bx1, kx);
+      by0 = min(by0, ky); by1 = max(by1, ky);
     }
+    Edge slot[2];
+    QuadState qslot[2];
+    flatten_prim(np, p, slot, qslot, (int)t.wide);
+    const uint32_t at = 2 + 2 * (prim - first_prim);
+    E[at] = slot[0];
+    E[at + 1] = slot[1];
+    if ((slot[0].curve >> 25) & 1) Q[at] = qslot[0];
+    if ((slot[1].curve >> 25) & 1) Q[at + 1] = qslot[1];
+    if (chord_cap) {
+      // row-parallel walk (skb_rowwalk.cuh): an upper bound of the chords each edge can give — a line is one, a
+      // quadratic its first chord plus one per remaining subdivision — and the op that owns the slot
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const bool valid = (slot[j].curve >> 24) & 1, quad = (slot[j].curve >> 25) & 1;
+        chord_cap[slot_base + at + j] = valid ? (quad ? 1u + (uint32_t)edge_count(slot[j]) : 1u) : 0u;
+        slot_op[slot_base + at + j] = op;
+      }
+    }
+  }
+  if (bx0 <= bx1) {
+    atomicMin(&g->bmin_x, bx0); atomicMax(&g->bmax_x, bx1);
+    atomicMin(&g->bmin_y, by0); atomicMax(&g->bmax_y, by1);
   }
 }
 
@@ -2083,25 +2093,34 @@ __global__ void __launch_bounds__(128) k_clip_classify(CoverArgs c) {
 }
 
 // --------------------------------------------------------------------- stage 5: bin
+// One thread per (op, tile row) — the owner of a tile row comes from the table the walk list wrote, where a thread per
+// item had to find its op by a binary search over a million item offsets — appending the row's non-empty items to their
+// tiles' command lists.
 __global__ void k_scatter(CoverArgs c, const uint32_t* tile_off, uint32_t* tile_fill, uint2* cmds) {
-  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= c.n_items) return;
-  const uint32_t flags = c.item_flags[item];
-  if (!flags) return;
-  const uint32_t op = find_interval(c.item_base, c.n_ops, item);
-  if (c.ops[op].kind != SKB_OP_FILL) return;
+  const uint32_t trow = blockIdx.x * blockDim.x + threadIdx.x;
+  if (trow >= c.n_trows) return;
+  const uint32_t op = c.trow_op[trow];
+  const skb_dl_op o = c.ops[op];
+  if (o.kind != SKB_OP_FILL) return;
   const OpGeom g = c.geom[op];
-  const uint32_t local = item - c.item_base[op];
-  const int tx = g.tx0 + (int)(local % (uint32_t)g.ntx);
-  const int ty = g.ty0 + (int)(local / (uint32_t)g.ntx);
-  const SurfDesc sd = c.surfs[c.ops[op].surface];
-  const uint32_t tile = sd.tile_base + (uint32_t)ty * sd.tiles_x + (uint32_t)tx;
-  const uint32_t n = (uint32_t)__popc(flags & SKB_ITEM_PLANE_MASK);
-  uint32_t pos = tile_off[tile] + atomicAdd(&tile_fill[tile], n);
-  for (uint32_t k = 0; k < SKB_CLIP_PLANES; k++) {
-    if (!((flags >> k) & 1u)) continue;
-    cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u) |
-                                                (((flags & SKB_ITEM_ZERO) && (k == 0 || c.ops[op].clip_in != 0)) ? SKB_CMD_ZERO : 0u));
+  if (g.empty || g.ntx == 0 || g.nty == 0) return;
+  const uint32_t tr = trow - c.row_base[op] / SKB_TILE;
+  if (tr >= (uint32_t)g.nty) return;
+  const SurfDesc sd = c.surfs[o.surface];
+  const uint32_t item0 = c.item_base[op] + tr * (uint32_t)g.ntx;
+  const uint32_t tile0 = sd.tile_base + (uint32_t)(g.ty0 + (int)tr) * sd.tiles_x + (uint32_t)g.tx0;
+  for (int i = 0; i < g.ntx; i++) {
+    const uint32_t item = item0 + (uint32_t)i;
+    const uint32_t flags = c.item_flags[item];
+    if (!flags) continue;
+    const uint32_t tile = tile0 + (uint32_t)i;
+    const uint32_t n = (uint32_t)__popc(flags & SKB_ITEM_PLANE_MASK);
+    uint32_t pos = tile_off[tile] + atomicAdd(&tile_fill[tile], n);
+    for (uint32_t k = 0; k < SKB_CLIP_PLANES; k++) {
+      if (!((flags >> k) & 1u)) continue;
+      cmds[pos++] = make_uint2((op << 3) | k, item | ((k == 0 && (flags & SKB_ITEM_SOLID)) ? SKB_CMD_SOLID : 0u) |
+                                                  (((flags & SKB_ITEM_ZERO) && (k == 0 || o.clip_in != 0)) ? SKB_CMD_ZERO : 0u));
+    }
   }
 }
 
@@ -3258,7 +3277,7 @@ static skb_result run_frame(skb_surface s) {
   for (int attempt = 0;; attempt++) {
     if (n_prims) {
       if (rowwalk && attempt == 0) SKB_CUDA(cudaMemsetAsync(chord_base, 0, (n_slots + 1) * 4, st));
-      k_flatten<<<cdiv(n_prims, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, nullptr, (rowwalk && attempt == 0) ? chord_base : nullptr,
+      k_flatten<<<cdiv(n_segs, 128), 128, 0, st>>>(t, prim_off, n_prims, seg_op, geom, edges, nullptr, (rowwalk && attempt == 0) ? chord_base : nullptr,
                                                     (uint32_t*)s->rw_slot_op.p);
       launches++;
     }
@@ -3619,7 +3638,7 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->cmds, ((size_t)n_cmds + 1) * sizeof(uint2)));
   SKB_TRY(buf_reserve(s->cmds_sorted, ((size_t)n_cmds + 1) * sizeof(uint2)));
   if (n_items) {
-    k_scatter<<<cdiv(n_items, 256), 256, 0, st>>>(ca, (const uint32_t*)s->tile_cnt.p, (uint32_t*)s->tile_fill.p, (uint2*)s->cmds.p);
+    k_scatter<<<cdiv(ca.n_trows, 128), 128, 0, st>>>(ca, (const uint32_t*)s->tile_cnt.p, (uint32_t*)s->tile_fill.p, (uint2*)s->cmds.p);
     launches++;
   }
   cudaEventRecord(s->ev[5], st);
