@@ -341,7 +341,8 @@ def run_ours(args):
         barrier()
         surf.set_remote_canvas(None)          # from here on the band stays in this rank's own canvas
         tag = os.environ.get("MASTER_PORT", "0")
-        shared = [multigpu.SharedHostImage(f"skb_bench_{tag}_{j}", (H, W, 4), rank, dist, register=True, my_rows=bands[rank]) for j in range(n_flight)]
+        shared = [multigpu.SharedHostImage(f"skb_bench_{tag}_{j}", (H, W, 4), rank, dist, register=True,
+                                           my_rows=None if os.environ.get("SKB_BENCH_SHM_TOUCH") == "owner" else bands[rank]) for j in range(n_flight)]
         y0b, y1b = bands[rank]
         host_image_locked = all(sh.registered for sh in shared)
 
