@@ -3442,6 +3442,8 @@ static skb_result run_frame(skb_surface s) {
       // working set is ~3 KB of edges per path, and with every thread slot taken it spills from L2 to DRAM
       static const int walk_smem = getenv("SKB_WALK_SMEM") ? atoi(getenv("SKB_WALK_SMEM")) : 0;
       if (walk_smem > 48 * 1024) cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem);
+      static const int walk_carveout = getenv("SKB_WALK_CARVEOUT") ? atoi(getenv("SKB_WALK_CARVEOUT")) : -2;
+      if (walk_carveout >= -1) cudaFuncSetAttribute(k_walk, cudaFuncAttributePreferredSharedMemoryCarveout, walk_carveout);
       uint32_t walk_grid = cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK);
       static const int walk_resident = getenv("SKB_WALK_RESIDENT") ? atoi(getenv("SKB_WALK_RESIDENT")) : 0;   // blocks per SM
       if (walk_resident > 0) walk_grid = std::min(walk_grid, (uint32_t)(walk_resident * s->dev->sm_count));
