@@ -101,7 +101,14 @@ struct LoweredPath {
 }  // namespace
 
 void LowerPathToSegs(const Path& src, std::vector<skb_dl_seg>* out) {
-  LoweredPath dst;
+  // one scratch path per thread, reused from call to call: its three vectors keep their capacity, so lowering a path
+  // allocates nothing (a Canvas user's thread and the builder's outline threads each have their own)
+  static thread_local LoweredPath scratch;
+  LoweredPath& dst = scratch;
+  dst.items.clear();
+  dst.points.clear();
+  dst.verbs.clear();
+  dst.last_move_to_index = ~0;
   {
     Path::Iter iter{src, false};
     Point pts[4] = {};
@@ -301,7 +308,8 @@ void CudaCanvas::EmitFill(const Path& path, const Matrix& m, uint32_t paint_inde
     NoteUnsupported("perspective CTM");
     return;
   }
-  std::vector<skb_dl_seg> segs;
+  static thread_local std::vector<skb_dl_seg> segs;   // reused: AddPath copies what it holds
+  segs.clear();
   LowerPathToSegs(path, &segs);
   if (segs.empty()) return;
   EmitFillOp(builder_->AddPath(segs), path.GetFillType(), m, paint_index);
