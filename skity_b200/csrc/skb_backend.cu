@@ -386,8 +386,39 @@ __global__ void k_op_setup(FrameTables t, const uint32_t* prim_off, OpGeom* geom
 // interleave.  k_walk_list first compacts the non-empty ops into a list.
 // Also writes the owner of every tile row (trow_op): the coverage and clip stages start from a tile row or a
 // pixel row and would otherwise find its op by a binary search over row_base — 20 dependent loads at 1M ops.
+// When the paths are few, the frame's sweep lasts as long as its longest path, and a path sharing its warp with
+// others advances only as fast as the warp gets through every lane's branch of every iteration.  The longest paths (by
+// rows x edge slots, a histogram in half octaves: k_walk_hist, k_walk_pick) are therefore put at the front of the list
+// and get a warp each; the others share warps as before.
+__device__ __forceinline__ uint32_t walk_work_bucket(const OpGeom& g) {
+  const uint32_t w = (uint32_t)g.nty * g.n_slots;
+  if (w == 0) return 0;
+  const int e = 31 - __clz((int)w);
+  const uint32_t frac = e >= 1 ? (w >> (e - 1)) & 1u : 0u;
+  return min(63u, 2u * (uint32_t)e + frac);
+}
+__global__ void k_walk_hist(FrameTables t, const OpGeom* geom, uint32_t* hist) {
+  uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= t.n_ops) return;
+  const OpGeom g = geom[op];
+  if (g.empty || g.ntx == 0 || g.nty == 0 || g.area) return;
+  atomicAdd(&hist[walk_work_bucket(g)], 1u);
+}
+// pick[0] = the bucket above which a path is "long", pick[1] = how many those are (at most max_long)
+__global__ void k_walk_pick(const uint32_t* hist, uint32_t max_long, uint32_t* pick) {
+  uint32_t cum = 0;
+  int b = 63;
+  for (; b >= 0; b--) {
+    if (cum + hist[b] > max_long) break;
+    cum += hist[b];
+  }
+  pick[0] = (uint32_t)b;   // -1 (all buckets fit): every path is long
+  pick[1] = cum;
+}
+
 __global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, uint32_t* list, const uint32_t* row_base,
-                            uint32_t* trow_op, RwOp* rwops, const uint32_t* wrow_base, uint32_t* wgrp_op) {
+                            uint32_t* trow_op, RwOp* rwops, const uint32_t* wrow_base, uint32_t* wgrp_op,
+                            const uint32_t* pick, uint32_t* cursors) {
   uint32_t op = blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= t.n_ops) return;
   const OpGeom g = geom[op];
@@ -402,6 +433,13 @@ __global__ void k_walk_list(FrameTables t, const OpGeom* geom, uint32_t* count, 
     rwops[op].wrow_base = wb;
     for (uint32_t gq = wb >> 4; gq < (we >> 4); gq++) wgrp_op[gq] = op;
     return;   // the sequential sweep's list is made later, of the paths the row-parallel form gives up on
+  }
+  if (pick) {   // long paths to the front of the list (pick[1] of them), the others behind
+    const bool is_long = (int)walk_work_bucket(g) > (int)pick[0];
+    const uint32_t pos = is_long ? atomicAdd(&cursors[0], 1u) : pick[1] + atomicAdd(&cursors[1], 1u);
+    list[pos] = op;
+    atomicAdd(count, 1u);
+    return;
   }
   // warp-aggregated append
   const unsigned m = __activemask();
@@ -428,6 +466,7 @@ struct WalkArgs {
   uint2* rows;
   const uint32_t* list;   // ops of this class
   const uint32_t* count;  // how many
+  const uint32_t* pick;   // [1] = how many paths at the front of the list get a warp each (null: none)
 };
 
 __device__ __forceinline__ void walk_setup_sink(const WalkArgs& a, uint32_t op, const OpGeom& g, RecSink& sink) {
@@ -450,12 +489,24 @@ __device__ __forceinline__ void walk_setup_sink(const WalkArgs& a, uint32_t op, 
 #define WALK_BOUNDS __launch_bounds__(WALK_BLOCK)
 #endif
 __global__ void WALK_BOUNDS k_walk(WalkArgs a, int lane_stride) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid % (uint32_t)lane_stride) return;
-  // a grid smaller than the list (SKB_WALK_RESIDENT: a cap on the paths in flight, i.e. on the sweep's cache footprint)
-  // takes the paths in strides of the grid
-  const uint32_t n_list = *a.count, step = gridDim.x * blockDim.x / (uint32_t)lane_stride;
-  for (uint32_t i = tid / (uint32_t)lane_stride; i < n_list; i += step) {
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t n_list = *a.count;
+  // the first n_long paths of the list have a warp each (its lane 0); the threads behind those warps take the rest
+  const uint32_t n_long = a.pick ? min(a.pick[1], n_list) : 0u;
+  uint32_t first, step;
+  if ((tid >> 5) < n_long) {
+    if (tid & 31u) return;
+    first = tid >> 5;
+    step = 0xFFFFFFFFu - first;   // one path only
+  } else {
+    tid -= n_long * 32u;
+    if (tid % (uint32_t)lane_stride) return;
+    // a grid smaller than the list (SKB_WALK_RESIDENT: a cap on the paths in flight, i.e. on the sweep's cache
+    // footprint) takes the paths in strides of the grid
+    first = n_long + tid / (uint32_t)lane_stride;
+    step = max(1u, (gridDim.x * blockDim.x - n_long * 32u) / (uint32_t)lane_stride);
+  }
+  for (uint32_t i = first; i < n_list; i += step) {
   const uint32_t op = a.list[i];
   const OpGeom g = a.geom[op];
   if (g.empty || g.ntx == 0 || g.nty == 0) continue;
@@ -3197,7 +3248,7 @@ static skb_result run_frame(skb_surface s) {
   SKB_TRY(buf_reserve(s->prim_cnt, (size_t)(n_segs + 1) * 4));
   SKB_TRY(buf_reserve(s->row_cnt, (size_t)(n_ops + 1) * 4));
   SKB_TRY(buf_reserve(s->item_cnt, (size_t)(n_ops + 1) * 4));
-  SKB_TRY(buf_reserve(s->counters, 128));
+  SKB_TRY(buf_reserve(s->counters, 1024));   // words 0..31 counters, 64..127 the sweep's work histogram, 128..129 its pick
   OpGeom* geom = (OpGeom*)s->geom.p;
   uint32_t* seg_op = (uint32_t*)s->seg_op.p;
   uint32_t* prim_off = (uint32_t*)s->prim_cnt.p;
@@ -3372,8 +3423,24 @@ static skb_result run_frame(skb_surface s) {
     wa.list = (const uint32_t*)s->walk_lists.p;
     wa.count = counters + 4;
     // counters: [0] pool_next, [1] overflow, [4] number of ops to sweep sequentially, [10] retried, [11] swept sequentially
+    // few paths (the GPU has thread slots to spare): the longest ones get a warp each (k_walk_hist / k_walk_pick)
+    // ... when the paths share their warps eight or sixteen to a warp (lane stride 4 or 2 below); with four paths to a
+    // warp the longest path is no faster alone (measured: C1 1.10 vs 1.17 ms; C2 with clips 3.94 -> 3.02 ms)
+    static const bool walk_no_long = getenv("SKB_WALK_NO_LONG") != nullptr;
+    const uint64_t walk_slots = (uint64_t)s->dev->sm_count * 32 * 32;
+    const bool long_first = !rowwalk && !walk_no_long && (uint64_t)n_ops * 2 <= walk_slots && (uint64_t)n_ops * 4 * 2 > walk_slots;
+    const uint32_t max_long = long_first ? std::min<uint32_t>(n_ops, (uint32_t)s->dev->sm_count * 8u) : 0u;
+    wa.pick = nullptr;
+    if (long_first) {
+      SKB_CUDA(cudaMemsetAsync(counters + 64, 0, 66 * 4, st));
+      k_walk_hist<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 64);
+      k_walk_pick<<<1, 1, 0, st>>>(counters + 64, max_long, counters + 128);
+      launches += 2;
+      wa.pick = counters + 128;
+    }
     k_walk_list<<<cdiv(n_ops, 128), 128, 0, st>>>(t, geom, counters + 4, (uint32_t*)s->walk_lists.p, row_base, (uint32_t*)s->trow_op.p,
-                                                  (rowwalk && attempt == 0) ? (RwOp*)s->rw_ops.p : nullptr, wrow_base, (uint32_t*)s->rw_wgrp_op.p);
+                                                  (rowwalk && attempt == 0) ? (RwOp*)s->rw_ops.p : nullptr, wrow_base, (uint32_t*)s->rw_wgrp_op.p,
+                                                  wa.pick, counters + 12);
     launches++;
     uint32_t n_seq = n_ops;   // upper bound of the paths the sequential sweep gets
     if (rowwalk && n_wrows && attempt == 0) {
@@ -3444,7 +3511,7 @@ static skb_result run_frame(skb_surface s) {
       if (walk_smem > 48 * 1024) cudaFuncSetAttribute(k_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, walk_smem);
       static const int walk_carveout = getenv("SKB_WALK_CARVEOUT") ? atoi(getenv("SKB_WALK_CARVEOUT")) : -2;
       if (walk_carveout >= -1) cudaFuncSetAttribute(k_walk, cudaFuncAttributePreferredSharedMemoryCarveout, walk_carveout);
-      uint32_t walk_grid = cdiv((uint64_t)n_seq * lane_stride, WALK_BLOCK);
+      uint32_t walk_grid = cdiv((uint64_t)n_seq * lane_stride + (uint64_t)max_long * 32, WALK_BLOCK);
       static const int walk_resident = getenv("SKB_WALK_RESIDENT") ? atoi(getenv("SKB_WALK_RESIDENT")) : 0;   // blocks per SM
       if (walk_resident > 0) walk_grid = std::min(walk_grid, (uint32_t)(walk_resident * s->dev->sm_count));
       k_walk<<<walk_grid, WALK_BLOCK, walk_smem, st>>>(wa, lane_stride);
