@@ -405,14 +405,24 @@ __global__ void k_walk_hist(FrameTables t, const OpGeom* geom, uint32_t* hist) {
   atomicAdd(&hist[walk_work_bucket(g)], 1u);
 }
 // pick[0] = the bucket above which a path is "long", pick[1] = how many those are (at most max_long)
+// A path is long only when it is well above the frame's median (more than two half octaves: about three times the
+// median's work) — in a frame of similar paths (C4b: 64 canvases of 1 000 random paths) nobody gains from a warp of
+// its own, and the warps spent on it are missing elsewhere.
 __global__ void k_walk_pick(const uint32_t* hist, uint32_t max_long, uint32_t* pick) {
+  uint32_t total = 0;
+  for (int b = 0; b < 64; b++) total += hist[b];
+  int median = 0;
+  for (uint32_t below = 0; median < 63; median++) {
+    below += hist[median];
+    if (2 * below >= total) break;
+  }
   uint32_t cum = 0;
   int b = 63;
-  for (; b >= 0; b--) {
+  for (; b > median + 2; b--) {
     if (cum + hist[b] > max_long) break;
     cum += hist[b];
   }
-  pick[0] = (uint32_t)b;   // -1 (all buckets fit): every path is long
+  pick[0] = (uint32_t)b;
   pick[1] = cum;
 }
 
