@@ -6,18 +6,21 @@
 
 Default workload = the configuration BASELINE.json's metric is quoted on ("at 1/2/4/8 B200"): config 4a,
 1M random quad/cubic paths on ONE 16384x16384 canvas (seed 4), which fits one GPU.  At N > 1 the canvas is
-partitioned into N contiguous bands of tile rows (STRONG scaling: the same frame, N times the hardware): the
-display list is replicated, every rank culls the draws that cannot reach its band before flattening, renders
-its band, and its fine pass stores the finished pixels straight into rank 0's canvas over NVLink peer memory
-(skb_surface_set_remote_canvas) — the gather of the north star fused into the producing kernel.  The same
-gather done by NCCL send/recv after the frame is timed beside it (`gather`).
+partitioned into N contiguous bands of tile rows (STRONG scaling: the same frame, N times the hardware): every
+rank holds the part of the display list that can reach its band (skb_display_list_cull_rows, made once per scene on
+the host like the encode itself; the device culls again before flattening), renders its band, and its fine pass
+stores the finished pixels straight into rank 0's canvas over NVLink peer memory (skb_surface_set_remote_canvas) —
+the gather of the north star fused into the producing kernel.  The same gather done by NCCL send/recv after the
+frame is timed beside it (`gather`).
 
 A "step" is one frame: clear, flatten, setup, walk, coverage, bin, fine — all paths, all pixels.
   value  Mpix/s of canvas filled, whole job, display list resident in HBM, CUDA events on the surface's stream
          over exactly K steps, max over ranks.
-  e2e    the same metric through the C ABI with HOST buffers: every step uploads the display list from pinned
-         host memory on every rank (H2D), renders, and rank 0 reads the gathered canvas back into pinned host
-         memory (D2H) — all inside the timed region.
+  e2e    the same metric through the C ABI with HOST buffers, all inside the timed region, three frames in flight:
+         N = 1: every step uploads the display list from pinned host memory (H2D), renders, reads the canvas back
+         into pinned host memory (D2H).  N > 1: every rank uploads its band's list, renders its band and copies it
+         into its rows of ONE page-locked host image in shared memory (multigpu.SharedHostImage) — N PCIe links at
+         once, the frame whole in rank 0's address space; the route through rank 0's canvas is `e2e.via_rank0_canvas`.
 Other workloads (--workload): c1 (10k paths 4096^2; at N > 1 one canvas per rank, weak scaling), c4b (batch
 of 1920x1080 canvases split by canvas, 64 per display list), c2, c3.
 One JSON line on stdout (rank 0).
